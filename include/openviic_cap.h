@@ -1,0 +1,229 @@
+/*
+ * openviic_cap.h -- C ABI of the B200-native caption hot path (libopenviic_cap.so).
+ *
+ * The reference (hieunghia-pat/OpenViIC) has NO native code and NO FFI: its hot path is Python
+ * calling stock ATen ops behind a name->class Registry (builders/registry.py:8-90).  This header
+ * is therefore the boundary *introduced* underneath the registered Python classes; each entry
+ * point names the reference symbol (file:line, relative to the reference root) whose arithmetic
+ * it replaces.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no torch / C++ types in any signature;
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - activations are bf16 (uint16 storage), statistics / logits / log-probs fp32, ids int64 at the
+ *     boundary (int32 inside), masks uint8 with 1 = masked (the reference's bool True = masked);
+ *   - weights use nn.Linear layout [out, in] row-major;
+ *   - every call takes an explicit cudaStream_t (as void*), never synchronises the device and is
+ *     CUDA-graph capturable, except the *_host convenience calls which end with a stream sync;
+ *   - return value: CAP_OK or an error code; cap_last_error() returns a thread-local message;
+ *   - callers keep ownership of every buffer; the library allocates only inside handles
+ *     (cap_beam_*, cap_engine_*) and frees in the matching destroy call.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef OPENVIIC_CAP_H
+#define OPENVIIC_CAP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAP_ABI_VERSION 1
+
+#define CAP_OK 0
+#define CAP_ERR_INVALID 1 /* bad argument / unsupported shape */
+#define CAP_ERR_CUDA 2    /* a CUDA runtime or driver call failed */
+#define CAP_ERR_STATE 3   /* handle used in the wrong order */
+
+typedef void* cap_stream_t; /* cudaStream_t */
+
+enum cap_dtype { CAP_BF16 = 0, CAP_F32 = 1 };
+enum cap_activation { CAP_ACT_NONE = 0, CAP_ACT_RELU = 1, CAP_ACT_SIGMOID = 2 };
+
+int cap_abi_version(void);
+const char* cap_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-operator entry points (used by the registered Python modules and by the parity tests)
+ * ------------------------------------------------------------------------------------------ */
+
+/* y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]).  tcgen05/TMEM GEMM fed by TMA.
+ * Replaces every nn.Linear on the path: models/modules/attentions.py:47-49,56,313-314;
+ * models/modules/positionwise_feed_forward.py:24; models/modules/vision_embeddings.py:17;
+ * models/modules/decoders.py:61,121.
+ * x, w bf16; bias fp32 or NULL; y bf16 or fp32 (out_dtype).  ldx/ldy in elements; K % 8 == 0,
+ * ldx % 8 == 0, x and w 16-byte aligned. */
+int cap_linear(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy,
+               int out_dtype, int act, int M, int N, int K, cap_stream_t stream);
+
+/* Same contract on plain CUDA cores: the on-device cross-check for cap_linear in the tests. */
+int cap_linear_simt(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy,
+                    int out_dtype, int act, int M, int N, int K, cap_stream_t stream);
+
+/* out = LayerNorm(residual + y) * gamma + beta [+ pos[row % pos_rows]] ; rows with
+ * zero_rows[row] != 0 are written as 0.  y is fp32 or bf16 (y_dtype); residual bf16 or NULL.
+ * Replaces models/modules/attentions.py:308-309, positionwise_feed_forward.py:26,
+ * encoders.py:20,36 (LN(x)+pos and the padded-row zeroing), decoders.py:26. */
+int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void* residual, int ldr,
+                      const float* gamma, const float* beta, float eps, const float* pos,
+                      int pos_rows, const uint8_t* zero_rows, void* out, int ldo, int rows, int d,
+                      cap_stream_t stream);
+
+/* Visual-token padding mask + cast: mask[row] = (sum_k feats[row,k] == 0) (fp32 sum), and
+ * out[row,:] = bf16(feats[row,:]).  feats fp32 or bf16.
+ * Replaces models/utils.py:48-61 as called from models/modules/vision_embeddings.py:16. */
+int cap_feature_mask_cast(const void* feats, int feat_dtype, void* out_bf16, uint8_t* mask,
+                          int rows, int d_feature, cap_stream_t stream);
+
+/* Box-relation bias g[B,H,n,n] = relu(W_g . embed(box_i, box_j) + b_g) (fp32).
+ * w_g [H, d_g], b_g [H]; d_g = 4 (raw) or d_model/H (sin/cos) selected by `trig`.
+ * Replaces models/utils.py:156-215 + models/modules/encoders.py:94-101. */
+int cap_geometry_bias(const float* boxes, const float* w_g, const float* b_g, float* g, int B,
+                      int n, int H, int d_g, int trig, cap_stream_t stream);
+
+typedef struct cap_attention_args {
+    const void* q;            /* bf16 (B, nq, H*64), row stride ldq, batch stride q_bs (elements) */
+    const void* k;            /* bf16 (B, nk, H*64) */
+    const void* v;            /* bf16 (B, nk, H*64) */
+    void* out;                /* bf16 (B, nq, H*64) */
+    int64_t q_bs, k_bs, v_bs, o_bs;
+    int ldq, ldk, ldv, ldo;
+    const uint8_t* mask;      /* (B, nq or 1, nk), 1 = masked; NULL = none */
+    int64_t mask_bs;          /* batch stride of mask */
+    int mask_qs;              /* query stride of mask (0 = broadcast over queries) */
+    const float* geometry;    /* (B, H, nq, nk) fp32 >= 0, added as log(max(g,1e-6)); NULL = none */
+    const void* mem_k;        /* bf16 (n_mem, H*64): sqrt(d_k)*m_k, never masked; NULL = none */
+    const void* mem_v;        /* bf16 (n_mem, H*64): sqrt(n_mem)*m_v */
+    int n_mem;
+    int B, H, nq, nk;
+    float scale;              /* 1/sqrt(d_k) */
+} cap_attention_args;
+
+/* softmax(q.k^T*scale + mask + log g | memory slots).v per (batch, head); d_k = d_v = 64,
+ * nk + n_mem <= 160.  Replaces the body of ScaledDotProductAttention.forward
+ * (models/modules/attentions.py:51-55), AugmentedGeometry... (:104-111) and AugmentedMemory...
+ * (:164-182) between the projections. */
+int cap_attention(const cap_attention_args* args, cap_stream_t stream);
+
+/* Decode-step self-attention over the beam-indirected KV cache (nq = 1 per row).
+ *   qkv      bf16 [T][R][3*H*64]  (q|k|v of the token each row consumed at step t')
+ *   ancestry int32 [T][R]  ancestry[t'][r] = cache row at step t' on row r's history (t' < t)
+ *   padflag  uint8 [T][R]  1 if the token consumed at step t' by that cache row was <pad>
+ * Replaces the stateful branch of MultiHeadAttention.forward (models/modules/attentions.py:
+ * 297-304) + the running mask of Decoder.forward (decoders.py:101-103) + the per-step state
+ * gather of BeamSearch._expand_state (beam_search.py:19-34) -- by indirection, no copy. */
+int cap_decode_self_attention(const void* qkv, const int32_t* ancestry, const uint8_t* padflag,
+                              void* out, int ldo, int t, int R, int H, float scale,
+                              cap_stream_t stream);
+
+/* Decode-step cross-attention: row r attends to image r / beam.  kv bf16 [B][n][2*H*64] (k|v,
+ * projected once per image), key_mask uint8 [B][n].  out bf16 [R][H*64].
+ * Replaces models/modules/decoders.py:23 (enc_attn) between its projections. */
+int cap_decode_cross_attention(const void* q, int ldq, const void* kv, const uint8_t* key_mask,
+                               void* out, int ldo, int B, int beam, int n, int H, float scale,
+                               cap_stream_t stream);
+
+/* x[r,:] = word_emb[token[r],:] + pos_table[position,:] (bf16 out); padflag_out[r] = token==pad.
+ * Replaces models/modules/decoders.py:105-112 (stateful: position = t+1 for every row). */
+int cap_embed_tokens(const int32_t* tokens, const void* word_emb_bf16, const float* pos_table,
+                     int position, int pad_idx, void* out, uint8_t* padflag_out, int R, int d,
+                     cap_stream_t stream);
+
+/* Meshed mix: out = sum_i sigmoid(a_i) * c_i / sqrt(levels)  (bf16), a_i fp32 [levels][R][d]
+ * pre-activation gates, c_i bf16 [levels][R][d].  Replaces models/modules/decoders.py:60-67. */
+int cap_meshed_mix(const float* gates, const void* c, void* out, int levels, int R, int d,
+                   cap_stream_t stream);
+
+/* AoA gate: out = info * sigmoid(gate); ig fp32 [R][2*d] = (info | gate).  attentions.py:311-315 */
+int cap_aoa_gate(const float* ig, void* out, int R, int d, cap_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Beam-search state machine (models/modules/beam_search.py:36-118)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cap_beam cap_beam;
+
+int cap_beam_create(int max_batch, int beam, int max_len, int vocab, int eos_idx, cap_beam** out);
+int cap_beam_destroy(cap_beam* h);
+/* seq_mask = 1, seq_logprob = 0, histories cleared, ancestry = identity; tokens = bos. */
+int cap_beam_reset(cap_beam* h, int batch, int bos_idx, cap_stream_t stream);
+/* One BeamSearch.iter(t): scores (R, ld) fp32 are either raw logits (is_logprob = 0: the
+ * log-softmax of decoders.py:123 is fused in) or log-probs exactly as model.step returns them
+ * (is_logprob = 1: selection is bit-exact with the reference's sort-based select()).
+ * R = batch*beam rows at every t; at t = 0 only beam 0 of each image is a candidate (cur_beam = 1). */
+int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, int is_logprob,
+                  cap_stream_t stream);
+/* Final descending sort by seq_logprob + gather; ids int64 (B,out_size,T), logp fp32 same shape. */
+int cap_beam_finalize(cap_beam* h, int out_size, int64_t* ids, float* logp, cap_stream_t stream);
+/* Device views of the running state (valid until destroy): */
+const int32_t* cap_beam_tokens(cap_beam* h);    /* [R]    token each row consumes next       */
+const int32_t* cap_beam_ancestry(cap_beam* h);  /* [T][R] see cap_decode_self_attention      */
+const float* cap_beam_seq_logprob(cap_beam* h); /* [R]                                       */
+const int32_t* cap_beam_parents(cap_beam* h);   /* [R]    selected_beam of the last step     */
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path engine: encoder_forward once + max_len decode steps (models/base_transformer.py:
+ * 30-53), one handle per GPU / rank.
+ * ------------------------------------------------------------------------------------------ */
+enum cap_encoder_kind { CAP_ENC_PLAIN = 0, CAP_ENC_MULTILEVEL = 1, CAP_ENC_GEOMETRIC = 2 };
+enum cap_attention_kind { CAP_ATT_SDPA = 0, CAP_ATT_GEOMETRY = 1, CAP_ATT_MEMORY = 2 };
+enum cap_decoder_kind { CAP_DEC_PLAIN = 0, CAP_DEC_MESHED = 1 };
+
+typedef struct cap_model_desc {
+    int d_model, heads, d_k, d_v, d_ff, d_feature;
+    int enc_layers, dec_layers;
+    int encoder_kind;      /* cap_encoder_kind */
+    int enc_attention;     /* cap_attention_kind of the encoder self-attention */
+    int n_memory;          /* memory slots when enc_attention == CAP_ATT_MEMORY */
+    int trig_geometry;     /* TRIGNOMETRIC_EMBEDDING of GeometricEncoder */
+    int decoder_kind;      /* cap_decoder_kind */
+    int n_enc_levels;      /* encoder levels the meshed decoder attends to (1 for plain) */
+    int aoa_enc, aoa_dec_self, aoa_dec_cross; /* USE_AOA flags */
+    int vocab, max_len, pad_idx, bos_idx, eos_idx;
+} cap_model_desc;
+
+typedef struct cap_engine cap_engine;
+
+int cap_engine_create(const cap_model_desc* desc, cap_engine** out);
+int cap_engine_destroy(cap_engine* e);
+/* Upload one state_dict entry (fp32, HOST memory) under its reference name, e.g.
+ * "encoder.layers.0.mhatt.attention.fc_q.weight".  Unknown names are an error. */
+int cap_engine_load_weight(cap_engine* e, const char* name, const float* data_host,
+                           const int64_t* shape, int ndim);
+/* Check every required tensor arrived, build fused bf16 weights (q|k|v stacks, scaled memory
+ * slots, position tables).  Must precede reserve/encode. */
+int cap_engine_finalize(cap_engine* e);
+/* Allocate workspaces, KV caches and the beam state for up to max_batch images of n_tokens
+ * visual tokens decoded with `beam` beams. */
+int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, int beam);
+/* encoder_forward + cross K/V projection; feats (B, n, d_feature) fp32 or bf16, boxes (B,n,4) fp32
+ * (GeometricEncoder only, else NULL). */
+int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtype, const float* boxes, int B,
+                      int n, cap_stream_t stream);
+/* Decoder stack for step t on the beam state's current tokens -> logits (R, ld) fp32. */
+int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t stream);
+/* cap_beam_step on the engine's own logits. */
+int cap_engine_beam_advance(cap_engine* e, int t, cap_stream_t stream);
+int cap_engine_begin_decode(cap_engine* e, cap_stream_t stream);
+/* All max_len steps + finalize; ids int64 (B,out_size,T), logp fp32.  use_graph != 0 replays a
+ * captured CUDA graph of one decode step. */
+int cap_engine_beam_search(cap_engine* e, int out_size, int64_t* ids, float* logp, int use_graph,
+                           cap_stream_t stream);
+/* End-to-end with HOST buffers (pinned for full speed): H2D features, encode, beam search, D2H
+ * ids/log-probs, stream sync.  The reference-facing call: trainers/vi_trainer.py:244 does
+ * `items.to(device)` + `model.beam_search(...)` + `.tolist()`. */
+int cap_engine_caption_host(cap_engine* e, const void* feats_host, int feat_dtype,
+                            const float* boxes_host, int B, int n, int out_size, int64_t* ids_host,
+                            float* logp_host, int use_graph, cap_stream_t stream);
+/* Debug / parity views: */
+const void* cap_engine_encoder_output(cap_engine* e);   /* bf16 [levels][B*n][d_model] */
+const uint8_t* cap_engine_encoder_mask(cap_engine* e);  /* uint8 [B*n]                 */
+const float* cap_engine_logits(cap_engine* e, int* ld); /* fp32 [R][ld]                */
+cap_beam* cap_engine_beam(cap_engine* e);
+/* Kernels launched by this library since load (all entry points); for bench.py's gpu_launches. */
+int64_t cap_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENVIIC_CAP_H */

@@ -1,0 +1,93 @@
+// Shared device/host helpers for the caption hot-path kernels (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/openviic_cap.h"
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+// ---------------------------------------------------------------------------------------------
+// Error plumbing: every C-ABI entry point returns an int and records a message (no exceptions,
+// no exit() across the ABI -- SURVEY.md section 8b "Error convention").
+// ---------------------------------------------------------------------------------------------
+int cap_set_error(int code, const char* fmt, ...);
+
+#define CAP_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return cap_set_error(CAP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define CAP_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) return cap_set_error(CAP_ERR_INVALID, __VA_ARGS__);                       \
+    } while (0)
+
+#define CAP_PROPAGATE(expr)                                                                    \
+    do {                                                                                       \
+        int _rc = (expr);                                                                      \
+        if (_rc != CAP_OK) return _rc;                                                         \
+    } while (0)
+
+static inline int cap_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cap_set_error(CAP_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return CAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// 8 bf16 <-> 8 floats through one 16-byte vector
+struct __align__(16) bf16x8 {
+    bf162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(p.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+
+// Ordering used everywhere a "stable descending sort" is restated: larger value first, and on
+// equal values the smaller flat index first (the reference's torch.sort tie order on its CPU
+// path, models/modules/beam_search.py:37).
+__device__ __forceinline__ bool cand_before(float va, int ia, float vb, int ib) {
+    return (va > vb) || (va == vb && ia < ib);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,422 @@
+// y[M,N] = act(x[M,K] . w[N,K]^T + bias) -- bf16 operands, fp32 accumulation in TMEM.
+//
+// Blackwell-native structure (one output tile per CTA, 128 x BLOCK_N):
+//   warp 0  : TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of 64 bf16 along K)
+//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16)
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b -> bias/activation -> vectorised global store)
+// smem ring of `num_stages` {A 128x64, B BLOCK_Nx64} tiles guarded by full/empty mbarriers;
+// tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
+//
+// Replaces every nn.Linear on the caption path (see include/openviic_cap.h: cap_linear).
+#include "cap_common.cuh"
+
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
+extern std::atomic<long long> g_cap_launches;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct GemmParams {
+    void* out;
+    const float* bias;
+    int M, N, K, ldo;
+    int out_f32, act, num_stages, vec_ok;
+};
+
+// ----------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+// Bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long start = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (spin == 64) start = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
+                                            int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner),
+        "r"(c_outer)
+        : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 bytes apart (SBO),
+// LBO unused for swizzled K-major, descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((smem_u32(tile) & 0x3FFFF) >> 4);  // [0,14)  start address
+    desc |= static_cast<uint64_t>(1) << 16;                          // [16,30) leading byte offset (ignored)
+    desc |= static_cast<uint64_t>(1024 >> 4) << 32;                  // [32,46) stride byte offset
+    desc |= static_cast<uint64_t>(1) << 46;                          // [46,48) version
+    desc |= static_cast<uint64_t>(2) << 61;                          // [61,64) SWIZZLE_128B
+    return desc;
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, shape M x N.
+__host__ __device__ constexpr uint32_t make_instr_desc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == CAP_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == CAP_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const GemmParams p) {
+    constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.num_stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BLOCK_M;
+    const int n0 = blockIdx.x * BLOCK_N;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < stages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            mbar_init(tmem_full_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t phase = (kb / stages) & 1;
+                mbar_wait(&empty_bar[s], phase ^ 1);
+                uint8_t* a_tile = smem + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+                tma_load_2d(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t phase = (kb / stages) & 1;
+                mbar_wait(&full_bar[s], phase);
+                tcgen05_fence_after();
+                const uint8_t* a_tile = smem + s * STAGE_BYTES;
+                const uint64_t a_desc = make_smem_desc(a_tile);
+                const uint64_t b_desc = make_smem_desc(a_tile + A_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                    umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int row = m0 + quad * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            const int col0 = n0 + c0;
+            if (!row_ok || col0 >= p.N) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]);
+                const int col = col0 + j;
+                if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+                f[j] = apply_act(x, p.act);
+            }
+            const bool full_chunk = (col0 + 32 <= p.N) && p.vec_ok;
+            if (p.out_f32) {
+                float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                if (full_chunk) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
+                }
+            } else {
+                bf16* dst = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                if (full_chunk) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(dst + j) = pack8(f + j);
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------- host launcher
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride `ld` elements; box = box_rows x 64, SWIZZLE_128B.
+int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return cap_set_error(CAP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return cap_set_error(CAP_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%d cols=%d ld=%d",
+                             static_cast<int>(r), rows, cols, ld);
+    return CAP_OK;
+}
+
+template <int BLOCK_N>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
+    constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
+    const size_t smem = 1024 + static_cast<size_t>(p.num_stages) * stage_bytes + (2 * MAX_STAGES + 1) * 8 + 16;
+    static bool attr_set = false;
+    static size_t attr_smem = 0;
+    if (!attr_set || smem > attr_smem) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+        attr_smem = 200 * 1024;
+    }
+    dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
+    gemm_tn_bf16_tcgen05<BLOCK_N><<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("gemm_tn_bf16_tcgen05");
+}
+
+int env_int(const char* name, int fallback) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : fallback;
+}
+
+}  // namespace
+
+extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int out_dtype,
+                          int act, int M, int N, int K, cap_stream_t stream) {
+    CAP_REQUIRE(x && w && y, "cap_linear: null pointer");
+    CAP_REQUIRE(M > 0 && N > 0 && K > 0, "cap_linear: empty problem M=%d N=%d K=%d", M, N, K);
+    CAP_REQUIRE(K % 8 == 0 && ldx % 8 == 0, "cap_linear: K=%d and ldx=%d must be multiples of 8 (TMA 16-byte strides)",
+                K, ldx);
+    CAP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                "cap_linear: x and w must be 16-byte aligned");
+    CAP_REQUIRE(ldx >= K && ldy >= N, "cap_linear: leading dimensions too small");
+    static const int forced_bn = env_int("OPENVIIC_GEMM_BLOCK_N", 0);
+    static const int forced_stages = env_int("OPENVIIC_GEMM_STAGES", 0);
+
+    const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+    int bn = 32;
+    if (forced_bn) {
+        bn = forced_bn;
+    } else {
+        const int cands[3] = {128, 64, 32};
+        for (int i = 0; i < 3; ++i) {
+            if (static_cast<long long>(tiles_m) * ((N + cands[i] - 1) / cands[i]) >= 148 || cands[i] == 32) {
+                bn = cands[i];
+                break;
+            }
+        }
+    }
+    CAP_REQUIRE(bn == 32 || bn == 64 || bn == 128, "cap_linear: unsupported BLOCK_N %d", bn);
+
+    GemmParams p;
+    p.out = y;
+    p.bias = bias;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.ldo = ldy;
+    p.out_f32 = (out_dtype == CAP_F32);
+    p.act = act;
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    int stages = forced_stages ? forced_stages : (bn == 128 ? 3 : 4);
+    if (stages > num_kb) stages = num_kb;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 1) stages = 1;
+    p.num_stages = stages;
+    const size_t esz = p.out_f32 ? 4 : 2;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((static_cast<size_t>(ldy) * esz) % 16 == 0);
+
+    CUtensorMap ta, tb;
+    CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
+    CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, bn));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (bn) {
+        case 128: return launch_gemm<128>(ta, tb, p, s);
+        case 64: return launch_gemm<64>(ta, tb, p, s);
+        default: return launch_gemm<32>(ta, tb, p, s);
+    }
+}
+
+// ------------------------------------------------------------------ CUDA-core cross-check GEMM
+namespace {
+__global__ void gemm_tn_simt(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w,
+                             const float* __restrict__ bias, void* out, int ldo, int out_f32, int act, int M, int N,
+                             int K) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (col >= N || row >= M) return;
+    const bf16* xr = x + static_cast<size_t>(row) * ldx;
+    const bf16* wr = w + static_cast<size_t>(col) * K;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(__bfloat162float(xr[k]), __bfloat162float(wr[k]), acc);
+    if (bias) acc += bias[col];
+    acc = apply_act(acc, act);
+    if (out_f32)
+        reinterpret_cast<float*>(out)[static_cast<size_t>(row) * ldo + col] = acc;
+    else
+        reinterpret_cast<bf16*>(out)[static_cast<size_t>(row) * ldo + col] = __float2bfloat16_rn(acc);
+}
+}  // namespace
+
+extern "C" int cap_linear_simt(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy,
+                               int out_dtype, int act, int M, int N, int K, cap_stream_t stream) {
+    CAP_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, "cap_linear_simt: bad arguments");
+    dim3 grid((N + 127) / 128, M);
+    gemm_tn_simt<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(w), bias, y, ldy, out_dtype == CAP_F32, act, M, N,
+        K);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("gemm_tn_simt");
+}

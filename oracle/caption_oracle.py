@@ -1,0 +1,390 @@
+"""CPU fp32 oracle for OpenViIC's caption-generation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``openviic_b200/`` may import this file.  It is the
+checker used by ``tests/``, by ``__graft_entry__.smoke()`` and by the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` -- never the thing that is shipped or measured as
+the product.
+
+What it is: a functional (no ``nn.Module``) restatement, in plain PyTorch fp32 on the CPU, of
+the algorithm the reference executes for ``model.beam_search`` / ``model.forward``.  It keeps
+the reference's operation order *as written* -- including the redundant work (cross-attention
+K/V re-projected for every beam row at every step, self-attention K/V re-projected for every
+cached token, every state gathered every step) -- so that
+
+  * its results equal the reference's to fp32 round-off (pinned by ``tests/golden/*.npz``,
+    generated from the real reference by ``oracle/ref_harness/gen_golden.py``), and
+  * timing it is a fair stand-in for "the reference's CPU path" (``cpu_baseline.kind =
+    "port"``), because ``/root/reference`` itself does not exist on the GPU box.
+
+Parity status: PINNED.  The reference ships no tests or golden vectors,
+so the pin is the reference itself, imported and run in the build container with fixed seeds.
+
+All citations are ``file:line`` relative to the reference repository root.
+Weights are addressed by the reference's own ``state_dict`` names.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Weights = Dict[str, Tensor]
+
+NEG_SENTINEL = -999.0  # models/modules/beam_search.py:54
+
+
+# ----------------------------------------------------------------------------------------------
+# Tables and masks
+# ----------------------------------------------------------------------------------------------
+
+def word_position_table(rows: int, d_model: int) -> Tensor:
+    """Decoder position table: sin on even columns, cos on odd, row 0 zeroed.
+
+    models/utils.py:21-40 (``positional_embedding`` + ``sinusoid_encoding_table`` with
+    ``padding_idx=0``), consumed at models/modules/decoders.py:87-88.
+    """
+    pos = torch.arange(rows, dtype=torch.float32).view(-1, 1)
+    j = torch.arange(d_model // 2, dtype=torch.float32).view(1, -1)
+    angle = pos / 10000 ** (2 * j / d_model)
+    table = torch.zeros(rows, d_model)
+    table[:, 0::2] = torch.sin(angle)
+    table[:, 1::2] = torch.cos(angle)
+    table[0] = 0
+    return table
+
+
+def visual_position_table(n: int, d_model: int, normalize: bool = False) -> Tensor:
+    """DETR-style 1-D sinusoid over token index 1..n (no mask => cumsum of ones).
+
+    models/modules/pos_embeddings.py:58-72.  Input-independent, so a constant (n, d) table.
+    """
+    embed = torch.arange(1, n + 1, dtype=torch.float32)
+    if normalize:
+        embed = embed / (embed[-1:] + 1e-6) * (2 * math.pi)
+    dim_t = torch.arange(d_model, dtype=torch.float32)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / d_model)
+    pos = embed[:, None] / dim_t
+    return torch.stack((pos[:, 0::2].sin(), pos[:, 1::2].cos()), dim=-1).flatten(-2)
+
+
+def feature_padding_mask(x: Tensor) -> Tensor:
+    """True where a visual token is padding: the sum over its raw feature vector is 0.
+
+    models/utils.py:48-61 called from models/modules/vision_embeddings.py:16.  -> (B,1,1,n) bool.
+    """
+    return (x.sum(dim=-1) == 0)[:, None, None, :]
+
+
+def box_relation_embedding(boxes: Tensor, dim_g: int, trig: bool, wave_len: float = 1000.0) -> Tensor:
+    """Pairwise box-geometry features, models/utils.py:156-215.  boxes (B,n,4) -> (B,n,n,dim_g)."""
+    b = boxes.size(0)
+    x0, y0, x1, y1 = torch.chunk(boxes, 4, dim=-1)
+    cx, cy = (x0 + x1) * 0.5, (y0 + y1) * 0.5
+    w, h = (x1 - x0) + 1.0, (y1 - y0) + 1.0
+    dx = torch.log(torch.clamp(torch.abs((cx - cx.view(b, 1, -1)) / w), min=1e-3))
+    dy = torch.log(torch.clamp(torch.abs((cy - cy.view(b, 1, -1)) / h), min=1e-3))
+    dw = torch.log(w / w.view(b, 1, -1))
+    dh = torch.log(h / h.view(b, 1, -1))
+    mat = torch.stack((dx, dy, dw, dh), dim=-1)  # (B,n,n,4)
+    if not trig:
+        return mat
+    rng = torch.arange(dim_g / 8)
+    freq = 1.0 / torch.pow(wave_len, rng / (dim_g / 8))
+    scaled = (100.0 * mat).unsqueeze(-1) * freq.view(1, 1, 1, 1, -1)
+    scaled = scaled.flatten(-2)
+    return torch.cat((torch.sin(scaled), torch.cos(scaled)), dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Attention variants (A1-A3), the multi-head wrapper (A5) and the feed-forward block (F1)
+# ----------------------------------------------------------------------------------------------
+
+def _lin(w: Weights, name: str, x: Tensor) -> Tensor:
+    return F.linear(x, w[name + ".weight"], w.get(name + ".bias"))
+
+
+def dot_product_attention(w: Weights, p: str, att_cfg, queries: Tensor, keys: Tensor, values: Tensor,
+                          mask: Optional[Tensor], geometry: Optional[Tensor] = None) -> Tensor:
+    """The three live attention variants, selected by ``att_cfg.ARCHITECTURE``.
+
+    ScaledDotProductAttention                    models/modules/attentions.py:44-58
+    AugmentedGeometryScaledDotProductAttention   models/modules/attentions.py:97-114
+    AugmentedMemoryScaledDotProductAttention     models/modules/attentions.py:158-185
+    """
+    kind = att_cfg.ARCHITECTURE
+    h, d_k, d_v = att_cfg.HEAD, att_cfg.D_KEY, att_cfg.D_VALUE
+    b, nq = queries.shape[:2]
+    nk = keys.shape[1]
+    q = _lin(w, p + "fc_q", queries).view(b, nq, h, d_k).permute(0, 2, 1, 3)
+    k = _lin(w, p + "fc_k", keys)
+    v = _lin(w, p + "fc_v", values)
+    if kind == "AugmentedMemoryScaledDotProductAttention":
+        m = att_cfg.MEMORY
+        k = torch.cat([k, math.sqrt(d_k) * w[p + "m_k"].expand(b, m, h * d_k)], 1)
+        v = torch.cat([v, math.sqrt(m) * w[p + "m_v"].expand(b, m, h * d_v)], 1)
+    nk_all = k.shape[1]
+    k = k.view(b, nk_all, h, d_k).permute(0, 2, 3, 1)
+    v = v.view(b, nk_all, h, d_v).permute(0, 2, 1, 3)
+    att = torch.matmul(q, k) / math.sqrt(d_k)
+    if mask is not None:
+        if kind == "AugmentedMemoryScaledDotProductAttention":
+            att[:, :, :, :nk] = att[:, :, :, :nk].masked_fill(mask, -math.inf)  # memory slots never masked
+        else:
+            att = att.masked_fill(mask, -math.inf)
+    if kind == "AugmentedGeometryScaledDotProductAttention":
+        att = torch.log(torch.clamp(geometry, min=1e-6)) + att
+    att = torch.softmax(att, dim=-1)
+    out = torch.matmul(att, v).permute(0, 2, 1, 3).contiguous().view(b, nq, h * d_v)
+    return _lin(w, p + "fc_o", out)
+
+
+def multi_head_attention(w: Weights, p: str, att_cfg, queries: Tensor, keys: Tensor, values: Tensor,
+                         mask: Optional[Tensor], cache: Optional[dict] = None,
+                         geometry: Optional[Tensor] = None) -> Tensor:
+    """MultiHeadAttention.forward, models/modules/attentions.py:296-317 (eval: dropout = identity).
+
+    ``cache`` (stateful decode) holds the raw, pre-projection inputs, exactly like the reference.
+    """
+    if cache is not None:
+        cache["keys"] = torch.cat([cache["keys"], keys], 1)
+        cache["values"] = torch.cat([cache["values"], values], 1)
+        keys, values = cache["keys"], cache["values"]
+    out = dot_product_attention(w, p + "attention.", att_cfg, queries, keys, values, mask, geometry)
+    d = queries.shape[-1]
+    out = F.layer_norm(queries + out, (d,), w[p + "layer_norm.weight"], w[p + "layer_norm.bias"])
+    if att_cfg.USE_AOA:
+        x = torch.cat([queries, out], dim=-1)
+        out = _lin(w, p + "informative_attention", x) * torch.sigmoid(_lin(w, p + "gated_attention", x))
+    return out
+
+
+def feed_forward(w: Weights, p: str, x: Tensor) -> Tensor:
+    """PositionWiseFeedForward.forward, models/modules/positionwise_feed_forward.py:23-28."""
+    y = _lin(w, p + "fc2", F.relu(_lin(w, p + "fc1", x)))
+    return F.layer_norm(x + y, (x.shape[-1],), w[p + "layer_norm.weight"], w[p + "layer_norm.bias"])
+
+
+# ----------------------------------------------------------------------------------------------
+# Encoders (E0-E3)
+# ----------------------------------------------------------------------------------------------
+
+def _encoder_layer(w: Weights, p: str, att_cfg, x: Tensor, pad_mask: Tensor, geometry=None) -> Tensor:
+    """EncoderLayer.forward, models/modules/encoders.py:17-22."""
+    att = multi_head_attention(w, p + "mhatt.", att_cfg, x, x, x, pad_mask, geometry=geometry)
+    ff = feed_forward(w, p + "pwff.", att)
+    return ff.masked_fill(pad_mask.squeeze(1).squeeze(1).unsqueeze(-1), 0)
+
+
+def geometry_weights(w: Weights, p: str, enc_cfg, boxes: Tensor) -> Tensor:
+    """Per-head ReLU(Linear(box embedding)), models/modules/encoders.py:94-101.  -> (B,h,n,n)."""
+    h = enc_cfg.SELF_ATTENTION.HEAD
+    trig = bool(enc_cfg.TRIGNOMETRIC_EMBEDDING)
+    d_g = enc_cfg.D_MODEL // h if trig else 4
+    emb = box_relation_embedding(boxes, d_g, trig)
+    b, n = emb.shape[:2]
+    flat = emb.view(-1, d_g)
+    per_head = [_lin(w, f"{p}fc_gs.{i}", flat).view(b, 1, n, n) for i in range(h)]
+    return F.relu(torch.cat(per_head, dim=1))
+
+
+def encode(w: Weights, model_cfg, feats: Tensor, boxes: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """``encoder_forward``: vision embedding + encoder stack.
+
+    FeatureEmbedding      models/modules/vision_embeddings.py:15-20
+    Encoder               models/modules/encoders.py:35-40
+    MultilevelEncoder     models/modules/encoders.py:53-63   (returns all levels, (B,L,n,d))
+    GeometricEncoder      models/modules/encoders.py:93-112  (called with boxes -- the documented
+                          ORT call-site patch)
+    """
+    enc_cfg = model_cfg.ENCODER
+    pad_mask = feature_padding_mask(feats)
+    x = _lin(w, "vision_embedding.proj", feats)
+    d = enc_cfg.D_MODEL
+    kind = enc_cfg.ARCHITECTURE
+    geometry = geometry_weights(w, "encoder.", enc_cfg, boxes) if kind == "GeometricEncoder" else None
+    x = F.layer_norm(x, (d,), w["encoder.layer_norm.weight"], w["encoder.layer_norm.bias"])
+    x = x + visual_position_table(x.shape[1], d)
+    levels = []
+    for i in range(enc_cfg.LAYERS):
+        x = _encoder_layer(w, f"encoder.layers.{i}.", enc_cfg.SELF_ATTENTION, x, pad_mask, geometry)
+        levels.append(x)
+    if kind == "MultilevelEncoder":
+        return torch.stack(levels, dim=1), pad_mask
+    if kind in ("Encoder", "GeometricEncoder"):
+        return x, pad_mask
+    raise KeyError(f"oracle has no encoder {kind!r}")
+
+
+# ----------------------------------------------------------------------------------------------
+# Decoders (D1-D3)
+# ----------------------------------------------------------------------------------------------
+
+def new_decode_state(model_cfg, rows: int) -> dict:
+    """Registered states after ``enable_statefulness`` (models/modules/containers.py:34-56):
+    empty running mask (R,1,1,0), running_seq (R,1)=0, empty per-layer raw K/V caches (R,0,d)."""
+    d = model_cfg.DECODER.D_MODEL
+    return {
+        "mask": torch.zeros(rows, 1, 1, 0, dtype=torch.bool),
+        "seq": torch.zeros(rows, 1, dtype=torch.long),
+        "layers": [{"keys": torch.zeros(rows, 0, d), "values": torch.zeros(rows, 0, d)}
+                   for _ in range(model_cfg.DECODER.LAYERS)],
+    }
+
+
+def _decoder_layer(w: Weights, p: str, dec_cfg, x: Tensor, enc: Tensor, pad_rows: Tensor,
+                   self_mask: Tensor, enc_mask: Tensor, cache: Optional[dict]) -> Tensor:
+    """DecoderLayer.forward models/modules/decoders.py:21-28; MeshedDecoderLayer.forward :51-73."""
+    att_cfg = dec_cfg.ATTENTION
+    s = multi_head_attention(w, p + "self_attn.", att_cfg.SELF_ATTENTION, x, x, x, self_mask, cache=cache)
+    if dec_cfg.ARCHITECTURE == "MeshedDecoder":
+        n_lv = att_cfg.N_ENCODER_LAYERS
+        crosses = [multi_head_attention(w, p + "enc_attn.", att_cfg.ENC_ATTENTION, s, enc[:, i], enc[:, i], enc_mask)
+                   for i in range(n_lv)]
+        alphas = [torch.sigmoid(_lin(w, f"{p}fc_alphas.{i}", torch.cat([s, c], dim=-1)))
+                  for i, c in enumerate(crosses)]
+        mixed = 0
+        for a, c in zip(alphas, crosses):
+            mixed = mixed + a * c
+        c = mixed / n_lv ** 0.5
+    else:
+        c = multi_head_attention(w, p + "enc_attn.", att_cfg.ENC_ATTENTION, s, enc, enc, enc_mask)
+    ff = feed_forward(w, p + "pwff.", c)
+    return ff.masked_fill(pad_rows.unsqueeze(-1), 0)
+
+
+def decode(w: Weights, model_cfg, tokens: Tensor, enc: Tensor, enc_mask: Tensor, pad_idx: int,
+           state: Optional[dict] = None) -> Tensor:
+    """Decoder.forward / MeshedDecoder.forward, models/modules/decoders.py:95-123 / :145-173.
+
+    tokens (R,S) int64 -> log-probs (R,S,V).  With ``state`` it is the stateful single-step path.
+    """
+    dec_cfg = model_cfg.DECODER
+    rows, s_len = tokens.shape
+    pad = (tokens == pad_idx)                                   # (R,S)
+    pad4 = pad[:, None, None, :]                                # generate_padding_mask on ids
+    causal = torch.triu(torch.ones(s_len, s_len), diagonal=1).to(torch.bool)[None, None]
+    self_mask = torch.logical_or(pad4, causal)
+    if state is not None:
+        state["mask"] = torch.cat([state["mask"], self_mask], -1)
+        self_mask = state["mask"]
+        state["seq"] = state["seq"] + 1                         # running_seq.add_(1); NOT zeroed for pad
+        seq = state["seq"]
+    else:
+        seq = torch.arange(1, s_len + 1).view(1, -1).expand(rows, -1).masked_fill(pad, 0)
+    x = F.embedding(tokens, w["decoder.word_emb.components.weight"]) + F.embedding(seq, w["decoder.pos_emb.weight"])
+    for i in range(dec_cfg.LAYERS):
+        cache = state["layers"][i] if state is not None else None
+        x = _decoder_layer(w, f"decoder.layers.{i}.", dec_cfg, x, enc, pad, self_mask, enc_mask, cache)
+    return F.log_softmax(F.linear(x, w["decoder.fc.weight"]), dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Beam search (B1-B4, S1)
+# ----------------------------------------------------------------------------------------------
+
+def _reorder(s: Tensor, b_s: int, cur: int, beam_idx: Tensor) -> Tensor:
+    """BeamSearch._expand_state, models/modules/beam_search.py:19-34: view (B,cur,...) and pick
+    ``beam_idx`` (B,beam) along dim 1, flatten back to (B*beam, ...)."""
+    tail = list(s.shape[1:])
+    s = s.view(b_s, cur, *tail)
+    picked = s[torch.arange(b_s)[:, None], beam_idx]
+    return picked.reshape(-1, *tail)
+
+
+def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states: Callable[[Callable], None],
+                b_s: int, beam: int, max_len: int, eos_idx: int, out_size: int = 1,
+                trace: Optional[list] = None) -> Tuple[Tensor, Tensor]:
+    """BeamSearch.apply/iter/select, models/modules/beam_search.py:36-118.
+
+    ``step(t, prev_tokens)`` returns (rows,1,V) log-probs; ``reorder_states(fn)`` maps ``fn`` over
+    every decode state (models/modules/containers.py:27-32).  Always runs ``max_len`` steps.
+    """
+    seq_mask = torch.ones(b_s, beam, 1)
+    seq_logprob = torch.zeros(b_s, 1, 1)
+    outputs: List[Tensor] = []
+    log_probs: List[Tensor] = []
+    selected_words: Optional[Tensor] = None
+    for t in range(max_len):
+        cur = 1 if t == 0 else beam
+        word_lp = step(t, selected_words).view(b_s, cur, -1)
+        vocab = word_lp.shape[-1]
+        cand = seq_logprob + word_lp
+        if t > 0:
+            alive = (selected_words.view(b_s, cur) != eos_idx).float().unsqueeze(-1)
+            seq_mask = seq_mask * alive
+            word_lp = word_lp * seq_mask.expand_as(word_lp)
+            frozen = seq_logprob.expand_as(cand).contiguous()
+            frozen[:, :, 1:] = NEG_SENTINEL
+            cand = seq_mask * cand + frozen * (1 - seq_mask)
+        # select(): full descending sort of the (cur*V) candidates, keep the first `beam`
+        sorted_lp, sorted_idx = torch.sort(cand.view(b_s, -1), -1, descending=True)
+        sel_lp, sel_idx = sorted_lp[:, :beam], sorted_idx[:, :beam]
+        sel_beam = torch.div(sel_idx, vocab, rounding_mode="trunc")
+        sel_word = sel_idx - sel_beam * vocab
+        reorder_states(lambda s, _b=sel_beam, _c=cur: _reorder(s, b_s, _c, _b))
+        seq_logprob = sel_lp.unsqueeze(-1)
+        seq_mask = torch.gather(seq_mask, 1, sel_beam.unsqueeze(-1))
+        outputs = [torch.gather(o, 1, sel_beam.unsqueeze(-1)) for o in outputs]
+        outputs.append(sel_word.unsqueeze(-1))
+        this_lp = torch.gather(word_lp, 1, sel_beam.unsqueeze(-1).expand(b_s, beam, vocab))
+        this_lp = torch.gather(this_lp, 2, sel_word.unsqueeze(-1))
+        log_probs = [torch.gather(o, 1, sel_beam.unsqueeze(-1)) for o in log_probs]
+        log_probs.append(this_lp)
+        selected_words = sel_word.reshape(-1, 1)
+        if trace is not None:
+            trace.append({"beam": sel_beam.clone(), "word": sel_word.clone(), "seq_logprob": sel_lp.clone()})
+    _, order = torch.sort(seq_logprob, 1, descending=True)
+    ids = torch.gather(torch.cat(outputs, -1), 1, order.expand(b_s, beam, max_len))
+    lps = torch.gather(torch.cat(log_probs, -1), 1, order.expand(b_s, beam, max_len))
+    ids, lps = ids.contiguous()[:, :out_size], lps.contiguous()[:, :out_size]
+    if out_size == 1:
+        ids, lps = ids.squeeze(1), lps.squeeze(1)
+    return ids, lps
+
+
+# ----------------------------------------------------------------------------------------------
+# Whole-path entry points (M1, M2)
+# ----------------------------------------------------------------------------------------------
+
+def caption_beam_search(w: Weights, model_cfg, vocab, feats: Tensor, boxes: Optional[Tensor] = None,
+                        beam: int = 5, out_size: int = 1, trace: Optional[list] = None,
+                        logits_trace: Optional[list] = None) -> Tuple[Tensor, Tensor]:
+    """BaseTransformer.beam_search + .step, models/base_transformer.py:30-53.
+
+    Returns (ids (B,T) int64, log_probs (B,T) fp32) for out_size == 1, else (B,out_size,T).
+    """
+    b_s = feats.shape[0]
+    with torch.no_grad():
+        enc, enc_mask = encode(w, model_cfg, feats, boxes)
+        st = {"enc": enc, "enc_mask": enc_mask, "dec": new_decode_state(model_cfg, b_s)}
+
+        def step(t, prev):
+            rows = st["enc"].shape[0]
+            tokens = torch.full((rows, 1), vocab.bos_idx, dtype=torch.long) if t == 0 else prev
+            lp = decode(w, model_cfg, tokens, st["enc"], st["enc_mask"], vocab.padding_idx, st["dec"])
+            if logits_trace is not None:
+                logits_trace.append(lp.squeeze(1).clone())
+            return lp
+
+        def reorder_states(fn):
+            # traversal order of containers.Module.apply_to_states
+            st["enc"], st["enc_mask"] = fn(st["enc"]), fn(st["enc_mask"])
+            d = st["dec"]
+            d["mask"], d["seq"] = fn(d["mask"]), fn(d["seq"])
+            for lay in d["layers"]:
+                lay["keys"], lay["values"] = fn(lay["keys"]), fn(lay["values"])
+
+        return beam_search(step, reorder_states, b_s, beam, vocab.max_caption_length, vocab.eos_idx,
+                           out_size, trace)
+
+
+def teacher_forced_log_probs(w: Weights, model_cfg, vocab, feats: Tensor, tokens: Tensor,
+                             boxes: Optional[Tensor] = None) -> Tensor:
+    """``model.forward(items)``: models/standard_stransformer.py:21-31 -> (B,T,V) log-probs."""
+    with torch.no_grad():
+        enc, enc_mask = encode(w, model_cfg, feats, boxes)
+        return decode(w, model_cfg, tokens, enc, enc_mask, vocab.padding_idx, None)
