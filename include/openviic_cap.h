@@ -138,6 +138,10 @@ int cap_meshed_mix(const float* gates, const void* c, void* out, int levels, int
 /* AoA gate: out = info * sigmoid(gate); ig fp32 [R][2*d] = (info | gate).  attentions.py:311-315 */
 int cap_aoa_gate(const float* ig, void* out, int R, int d, cap_stream_t stream);
 
+/* out[r,:] = log_softmax(logits[r,:]) over V columns, fp32 (models/modules/decoders.py:123). */
+int cap_log_softmax(const float* logits, int ld, float* out, int ldo, int rows, int V,
+                    cap_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Beam-search state machine (models/modules/beam_search.py:36-118)
  * ------------------------------------------------------------------------------------------ */

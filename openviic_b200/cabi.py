@@ -60,6 +60,7 @@ SIGNATURES = {
     "cap_embed_tokens": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "cap_meshed_mix": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cap_aoa_gate": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cap_log_softmax": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "cap_beam_create": (_i, [_i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "cap_beam_destroy": (_i, [_vp]),
     "cap_beam_reset": (_i, [_vp, _i, _i, _vp]),

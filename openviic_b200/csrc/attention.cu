@@ -1,0 +1,289 @@
+// Fused attention kernels (d_k = d_v = 64).
+//
+//  attention_kernel            softmax(q.k^T*scale + mask + log g | memory slots).v for one
+//                              (batch, head, 64-query tile) per CTA; K/V staged once in shared
+//                              memory (K rows padded to 33 words => conflict-free lane-per-key dots),
+//                              fp32 softmax with warp shuffles.  Serves the encoder self-attention
+//                              (all three variants), teacher-forced decoder attention and the
+//                              decode-step cross-attention (the `beam` rows of an image are the
+//                              queries of one CTA, so the image's K/V is read once, not per beam).
+//  decode_self_attention_kernel  one warp per (row, head) over the beam-indirected KV cache.
+//
+// These are HBM/L2-bound (nq*nk*64 MACs per head is tiny); the tensor cores are reserved for the
+// projections (gemm_tcgen05.cu).
+#include "cap_common.cuh"
+
+#include <atomic>
+
+extern std::atomic<long long> g_cap_launches;
+
+namespace {
+
+constexpr int HEAD_DIM = 64;
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_WARPS = ATT_THREADS / 32;
+constexpr int Q_TILE = 64;
+constexpr int MAX_KEYS = 160;
+constexpr int KEY_CHUNKS = MAX_KEYS / 32;
+constexpr int K_STRIDE = HEAD_DIM + 2;  // bf16 elements: 33 words per row
+
+struct AttnDev {
+    const bf16 *q, *k, *v;
+    bf16* out;
+    long long q_bs, k_bs, v_bs, o_bs;
+    int ldq, ldk, ldv, ldo;
+    const uint8_t* mask;
+    long long mask_bs;
+    int mask_qs;
+    const float* geometry;
+    const bf16 *mem_k, *mem_v;
+    int n_mem, B, H, nq, nk;
+    float scale;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnDev a) {
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    const int nk_all = a.nk + a.n_mem;
+    bf16* sk = reinterpret_cast<bf16*>(att_smem);                       // [nk_all][K_STRIDE]
+    bf16* sv = sk + static_cast<size_t>(nk_all) * K_STRIDE;             // [nk_all][64]
+    float* sq = reinterpret_cast<float*>(sv + static_cast<size_t>(nk_all) * HEAD_DIM);  // [warps][64]
+    float* sp = sq + ATT_WARPS * HEAD_DIM;                              // [warps][MAX_KEYS]
+
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * Q_TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- stage K (4-byte stores into the padded layout) and V (dense) ----
+    const bf16* kbase = a.k + b * a.k_bs + h * HEAD_DIM;
+    const bf16* vbase = a.v + b * a.v_bs + h * HEAD_DIM;
+    for (int j = warp; j < nk_all; j += ATT_WARPS) {
+        const bf16* krow = (j < a.nk) ? kbase + static_cast<size_t>(j) * a.ldk
+                                      : a.mem_k + static_cast<size_t>(j - a.nk) * (a.H * HEAD_DIM) + h * HEAD_DIM;
+        const bf16* vrow = (j < a.nk) ? vbase + static_cast<size_t>(j) * a.ldv
+                                      : a.mem_v + static_cast<size_t>(j - a.nk) * (a.H * HEAD_DIM) + h * HEAD_DIM;
+        reinterpret_cast<bf162*>(sk + j * K_STRIDE)[lane] = reinterpret_cast<const bf162*>(krow)[lane];
+        reinterpret_cast<bf162*>(sv + j * HEAD_DIM)[lane] = reinterpret_cast<const bf162*>(vrow)[lane];
+    }
+    __syncthreads();
+
+    float* myq = sq + warp * HEAD_DIM;
+    float* myp = sp + warp * MAX_KEYS;
+    const int q_end = min(q0 + Q_TILE, a.nq);
+    for (int i = q0 + warp; i < q_end; i += ATT_WARPS) {
+        const bf16* qrow = a.q + b * a.q_bs + static_cast<size_t>(i) * a.ldq + h * HEAD_DIM;
+        const float2 qv = __bfloat1622float2(reinterpret_cast<const bf162*>(qrow)[lane]);
+        myq[2 * lane] = qv.x * a.scale;
+        myq[2 * lane + 1] = qv.y * a.scale;
+        __syncwarp();
+
+        const uint8_t* mrow = a.mask ? a.mask + b * a.mask_bs + static_cast<size_t>(i) * a.mask_qs : nullptr;
+        const float* grow = a.geometry
+                                ? a.geometry + ((static_cast<size_t>(b) * a.H + h) * a.nq + i) * a.nk
+                                : nullptr;
+        float s[KEY_CHUNKS];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < KEY_CHUNKS; ++c) {
+            const int j = c * 32 + lane;
+            s[c] = -INFINITY;
+            if (j < nk_all) {
+                const bf162* kr = reinterpret_cast<const bf162*>(sk + j * K_STRIDE);
+                float acc = 0.f;
+#pragma unroll
+                for (int d2 = 0; d2 < HEAD_DIM / 2; ++d2) {
+                    const float2 kk = __bfloat1622float2(kr[d2]);
+                    acc = fmaf(myq[2 * d2], kk.x, acc);
+                    acc = fmaf(myq[2 * d2 + 1], kk.y, acc);
+                }
+                if (j < a.nk) {
+                    if (mrow && mrow[j]) acc = -INFINITY;
+                    if (grow) acc += logf(fmaxf(grow[j], 1e-6f));
+                }
+                s[c] = acc;
+            }
+            mx = fmaxf(mx, s[c]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < KEY_CHUNKS; ++c) {
+            const int j = c * 32 + lane;
+            const float p = (j < nk_all && mx != -INFINITY) ? __expf(s[c] - mx) : 0.f;
+            if (j < nk_all) myp[j] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        __syncwarp();
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < nk_all; ++j) {
+            const float p = myp[j];
+            const float2 vv = __bfloat1622float2(reinterpret_cast<const bf162*>(sv + j * HEAD_DIM)[lane]);
+            o0 = fmaf(p, vv.x, o0);
+            o1 = fmaf(p, vv.y, o1);
+        }
+        bf16* orow = a.out + b * a.o_bs + static_cast<size_t>(i) * a.ldo + h * HEAD_DIM;
+        reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------ decode self-attn
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_MAX_T = 64;
+
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_self_attention_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
+                             const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
+                             int H, float scale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * DEC_WARPS + warp;
+    if (item >= R * H) return;
+    const int r = item / H, h = item % H;
+    const int hd = H * HEAD_DIM;
+    const size_t step_stride = static_cast<size_t>(R) * 3 * hd;
+    const int nkeys = t + 1;
+
+    // whole query vector in registers (broadcast 16-byte loads), packed bf16x2
+    bf162 qreg[HEAD_DIM / 2];
+    {
+        const bf16x8* qp = reinterpret_cast<const bf16x8*>(qkv + t * step_stride + static_cast<size_t>(r) * 3 * hd +
+                                                          h * HEAD_DIM);
+#pragma unroll
+        for (int c = 0; c < HEAD_DIM / 8; ++c) {
+            const bf16x8 v = qp[c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qreg[c * 4 + i] = v.v[i];
+        }
+    }
+    float s[2];
+    int slot[2];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int j = c * 32 + lane;
+        s[c] = -INFINITY;
+        slot[c] = 0;
+        if (j < nkeys) {
+            const int sl = (j == t) ? r : ancestry[static_cast<size_t>(j) * R + r];
+            slot[c] = sl;
+            const bf16x8* kp = reinterpret_cast<const bf16x8*>(qkv + j * step_stride + static_cast<size_t>(sl) * 3 * hd +
+                                                              hd + h * HEAD_DIM);
+            float acc = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < HEAD_DIM / 8; ++cc) {
+                const bf16x8 kv = kp[cc];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 kk = __bfloat1622float2(kv.v[i]);
+                    const float2 qq = __bfloat1622float2(qreg[cc * 4 + i]);
+                    acc = fmaf(qq.x, kk.x, acc);
+                    acc = fmaf(qq.y, kk.y, acc);
+                }
+            }
+            acc *= scale;
+            if (padflag[static_cast<size_t>(j) * R + sl]) acc = -INFINITY;
+            s[c] = acc;
+        }
+        mx = fmaxf(mx, s[c]);
+    }
+    mx = warp_max(mx);
+    float p[2], sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int j = c * 32 + lane;
+        p[c] = (j < nkeys && mx != -INFINITY) ? __expf(s[c] - mx) : 0.f;
+        sum += p[c];
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < nkeys; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p[j >> 5], j & 31);
+        const int sl = __shfl_sync(0xffffffffu, slot[j >> 5], j & 31);
+        const bf162* vp = reinterpret_cast<const bf162*>(qkv + j * step_stride + static_cast<size_t>(sl) * 3 * hd +
+                                                        2 * hd + h * HEAD_DIM);
+        const float2 vv = __bfloat1622float2(vp[lane]);
+        o0 = fmaf(pj, vv.x, o0);
+        o1 = fmaf(pj, vv.y, o1);
+    }
+    bf16* orow = out + static_cast<size_t>(r) * ldo + h * HEAD_DIM;
+    reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+}
+
+int launch_attention(const AttnDev& a, cudaStream_t stream) {
+    const int nk_all = a.nk + a.n_mem;
+    const size_t smem = static_cast<size_t>(nk_all) * (K_STRIDE + HEAD_DIM) * 2 + ATT_WARPS * HEAD_DIM * 4 +
+                        ATT_WARPS * MAX_KEYS * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+    }
+    dim3 grid((a.nq + Q_TILE - 1) / Q_TILE, a.H, a.B);
+    attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(a);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("attention_kernel");
+}
+
+}  // namespace
+
+extern "C" int cap_attention(const cap_attention_args* args, cap_stream_t stream) {
+    CAP_REQUIRE(args != nullptr, "cap_attention: null args");
+    const cap_attention_args& g = *args;
+    CAP_REQUIRE(g.q && g.k && g.v && g.out, "cap_attention: null tensor");
+    CAP_REQUIRE(g.B > 0 && g.H > 0 && g.nq > 0 && g.nk > 0, "cap_attention: empty problem");
+    CAP_REQUIRE(g.B <= 65535 && g.H <= 65535, "cap_attention: B and H must be <= 65535");
+    CAP_REQUIRE(g.n_mem >= 0 && g.nk + g.n_mem <= MAX_KEYS, "cap_attention: nk + n_mem = %d exceeds %d",
+                g.nk + g.n_mem, MAX_KEYS);
+    CAP_REQUIRE(g.n_mem == 0 || (g.mem_k && g.mem_v), "cap_attention: memory slots requested without tensors");
+    CAP_REQUIRE(g.ldq % 2 == 0 && g.ldk % 2 == 0 && g.ldv % 2 == 0 && g.ldo % 2 == 0,
+                "cap_attention: leading dimensions must be even");
+    AttnDev a;
+    a.q = static_cast<const bf16*>(g.q);
+    a.k = static_cast<const bf16*>(g.k);
+    a.v = static_cast<const bf16*>(g.v);
+    a.out = static_cast<bf16*>(g.out);
+    a.q_bs = g.q_bs; a.k_bs = g.k_bs; a.v_bs = g.v_bs; a.o_bs = g.o_bs;
+    a.ldq = g.ldq; a.ldk = g.ldk; a.ldv = g.ldv; a.ldo = g.ldo;
+    a.mask = g.mask; a.mask_bs = g.mask_bs; a.mask_qs = g.mask_qs;
+    a.geometry = g.geometry;
+    a.mem_k = static_cast<const bf16*>(g.mem_k);
+    a.mem_v = static_cast<const bf16*>(g.mem_v);
+    a.n_mem = g.n_mem; a.B = g.B; a.H = g.H; a.nq = g.nq; a.nk = g.nk;
+    a.scale = g.scale;
+    return launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv, const uint8_t* key_mask, void* out,
+                                          int ldo, int B, int beam, int n, int H, float scale, cap_stream_t stream) {
+    CAP_REQUIRE(q && kv && out, "cap_decode_cross_attention: null pointer");
+    CAP_REQUIRE(B > 0 && beam > 0 && n > 0 && n <= MAX_KEYS && H > 0, "cap_decode_cross_attention: bad shape");
+    const int hd = H * HEAD_DIM;
+    AttnDev a;
+    a.q = static_cast<const bf16*>(q);
+    a.k = static_cast<const bf16*>(kv);
+    a.v = static_cast<const bf16*>(kv) + hd;
+    a.out = static_cast<bf16*>(out);
+    a.q_bs = static_cast<long long>(beam) * ldq;
+    a.k_bs = a.v_bs = static_cast<long long>(n) * 2 * hd;
+    a.o_bs = static_cast<long long>(beam) * ldo;
+    a.ldq = ldq; a.ldk = a.ldv = 2 * hd; a.ldo = ldo;
+    a.mask = key_mask; a.mask_bs = n; a.mask_qs = 0;
+    a.geometry = nullptr; a.mem_k = a.mem_v = nullptr; a.n_mem = 0;
+    a.B = B; a.H = H; a.nq = beam; a.nk = n;
+    a.scale = scale;
+    return launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestry, const uint8_t* padflag, void* out,
+                                         int ldo, int t, int R, int H, float scale, cap_stream_t stream) {
+    CAP_REQUIRE(qkv && ancestry && padflag && out, "cap_decode_self_attention: null pointer");
+    CAP_REQUIRE(t >= 0 && t < DEC_MAX_T, "cap_decode_self_attention: step %d outside [0,%d)", t, DEC_MAX_T);
+    CAP_REQUIRE(R > 0 && H > 0 && ldo % 2 == 0, "cap_decode_self_attention: bad shape");
+    const int items = R * H;
+    decode_self_attention_kernel<<<(items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0,
+                                   static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(qkv), ancestry, padflag, static_cast<bf16*>(out), ldo, t, R, H, scale);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_self_attention_kernel");
+}

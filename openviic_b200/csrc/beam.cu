@@ -1,0 +1,417 @@
+// Beam-search state machine on the device (models/modules/beam_search.py:36-118 restated as three
+// kernels, no host round trip inside the loop).
+//
+//   beam_rowpass_kernel   one CTA per beam row: EOS bookkeeping (seq_mask *= prev != eos), fused
+//                         log-softmax (or pass-through log-probs), candidate value
+//                         seq_logprob + word_logprob with the reference's -999 sentinel for
+//                         finished beams, and the row-local top-`beam` under the stable-descending
+//                         order (value desc, flat index asc).
+//   beam_select_kernel    one CTA per image: merge the rows' candidates, pick the `beam` best,
+//                         then reorder every per-beam state IN PLACE inside the image's group:
+//                         seq_logprob, seq_mask, id / log-prob histories, next tokens and the
+//                         ancestry table that replaces the reference's per-step KV-cache gather.
+//   beam_finalize_kernel  final descending sort by seq_logprob + gather, int64 ids out.
+#include "cap_common.cuh"
+
+#include <atomic>
+
+extern std::atomic<long long> g_cap_launches;
+
+namespace {
+
+constexpr int BEAM_MAX = 8;
+constexpr int ROW_THREADS = 256;
+constexpr float SENTINEL = -999.0f;  // models/modules/beam_search.py:54
+
+struct Cand {
+    float val;
+    int idx;
+};
+
+__device__ __forceinline__ bool before(const Cand& a, const Cand& b) { return cand_before(a.val, a.idx, b.val, b.idx); }
+
+__device__ __forceinline__ Cand warp_best(Cand c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand other;
+        other.val = __shfl_xor_sync(0xffffffffu, c.val, o);
+        other.idx = __shfl_xor_sync(0xffffffffu, c.idx, o);
+        if (before(other, c)) c = other;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int w = 1; w < ROW_THREADS / 32; ++w) r = fmaxf(r, red[w]);
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int w = 0; w < ROW_THREADS / 32; ++w) r += red[w];
+    __syncthreads();
+    return r;
+}
+
+struct BeamDev {
+    int32_t* tokens;      // [R]
+    float* seq_logprob;   // [R]
+    float* seq_mask;      // [R]
+    int32_t* hist_ids;    // [R][T]
+    float* hist_lp;       // [R][T]
+    int32_t* ancestry;    // [T][R]
+    int32_t* parents;     // [R]
+    float* cand_val;      // [R][BEAM_MAX]
+    float* cand_lp;       // [R][BEAM_MAX]
+    int32_t* cand_idx;    // [R][BEAM_MAX]
+    int batch, beam, max_len, vocab, eos;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS)
+beam_rowpass_kernel(const BeamDev st, const float* __restrict__ scores, int ld, int is_logprob, int t, int stage_smem) {
+    extern __shared__ __align__(16) float row_smem[];
+    __shared__ float red[ROW_THREADS / 32];
+    __shared__ Cand warp_cand[ROW_THREADS / 32];
+    __shared__ int s_winner;
+    const int r = blockIdx.x;
+    const int beam = st.beam, V = st.vocab;
+    const int tid = threadIdx.x;
+
+    float mask = st.seq_mask[r];
+    if (t > 0) mask *= (st.tokens[r] != st.eos) ? 1.f : 0.f;
+    const float seq_lp = st.seq_logprob[r];
+    __syncthreads();  // everyone has read seq_mask before thread 0 rewrites it
+    if (tid == 0) st.seq_mask[r] = mask;
+
+    float* cval = st.cand_val + static_cast<size_t>(r) * BEAM_MAX;
+    float* clp = st.cand_lp + static_cast<size_t>(r) * BEAM_MAX;
+    int32_t* cidx = st.cand_idx + static_cast<size_t>(r) * BEAM_MAX;
+
+    if (t == 0 && (r % beam) != 0) {  // cur_beam_size == 1: only beam 0 of each image competes
+        if (tid < beam) { cval[tid] = -INFINITY; clp[tid] = 0.f; cidx[tid] = tid; }
+        return;
+    }
+    if (mask == 0.f) {  // finished beam: column 0 keeps seq_logprob, every other column is -999
+        if (tid < beam) {
+            cval[tid] = (tid == 0) ? seq_lp : SENTINEL;
+            clp[tid] = 0.f;  // word_logprob * seq_mask
+            cidx[tid] = tid;
+        }
+        return;
+    }
+
+    const float* grow = scores + static_cast<size_t>(r) * ld;
+    const float* row = grow;
+    if (stage_smem) {
+        for (int v = tid; v < V; v += ROW_THREADS) row_smem[v] = grow[v];
+        __syncthreads();
+        row = row_smem;
+    }
+    float mx = 0.f, log_sum = 0.f;
+    if (!is_logprob) {
+        float m = -INFINITY;
+        for (int v = tid; v < V; v += ROW_THREADS) m = fmaxf(m, row[v]);
+        mx = block_reduce_max(m, red);
+        float s = 0.f;
+        for (int v = tid; v < V; v += ROW_THREADS) s += __expf(row[v] - mx);
+        log_sum = logf(block_reduce_sum(s, red));
+    }
+
+    // thread-local sorted top-`beam` over this thread's strided slice
+    Cand best[BEAM_MAX];
+#pragma unroll
+    for (int i = 0; i < BEAM_MAX; ++i) { best[i].val = -INFINITY; best[i].idx = 0x7fffffff; }
+    for (int v = tid; v < V; v += ROW_THREADS) {
+        const float lp = is_logprob ? row[v] : (row[v] - mx) - log_sum;
+        Cand c;
+        c.val = seq_lp + lp;
+        c.idx = v;
+        if (before(c, best[BEAM_MAX - 1])) {  // static top-8 list keeps best[] in registers
+#pragma unroll
+            for (int i = BEAM_MAX - 1; i >= 0; --i) {
+                if (i > 0 && before(c, best[i - 1])) {
+                    best[i] = best[i - 1];
+                } else {
+                    best[i] = c;
+                    break;
+                }
+            }
+        }
+    }
+    // `beam` rounds of block-wide arg-best over the heads of the per-thread lists
+    int head = 0;
+    for (int round = 0; round < beam; ++round) {
+        Cand mine;
+        mine.val = -INFINITY;
+        mine.idx = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < BEAM_MAX; ++i)
+            if (i == head && i < beam) mine = best[i];
+        const Cand wb = warp_best(mine);
+        if ((tid & 31) == 0) warp_cand[tid >> 5] = wb;
+        __syncthreads();
+        if (tid == 0) {
+            Cand bb = warp_cand[0];
+            for (int w = 1; w < ROW_THREADS / 32; ++w)
+                if (before(warp_cand[w], bb)) bb = warp_cand[w];
+            const float x = row[bb.idx];
+            cval[round] = bb.val;
+            cidx[round] = bb.idx;
+            clp[round] = is_logprob ? x : (x - mx) - log_sum;
+            s_winner = bb.idx;
+        }
+        __syncthreads();
+        if (head < beam && mine.idx == s_winner && mine.val != -INFINITY) ++head;  // indices are unique per row
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) beam_select_kernel(const BeamDev st, int t) {
+    __shared__ Cand s_sel[BEAM_MAX];
+    __shared__ float s_sel_lp[BEAM_MAX];
+    __shared__ int s_sel_beam[BEAM_MAX];
+    __shared__ float s_mask[BEAM_MAX];
+    extern __shared__ __align__(16) uint8_t sel_smem[];
+    const int b = blockIdx.x, beam = st.beam, V = st.vocab, T = st.max_len, R = st.batch * st.beam;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cur = (t == 0) ? 1 : beam;
+    const int row0 = b * beam;
+
+    if (warp == 0) {
+        // up to BEAM_MAX*BEAM_MAX = 64 candidates: two per lane, flat index = src_beam*V + word
+        Cand c[2];
+        float lp[2];
+        int src[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int slot = e * 32 + lane;
+            const int kb = slot / beam, kc = slot % beam;
+            c[e].val = -INFINITY; c[e].idx = 0x7fffffff; lp[e] = 0.f; src[e] = 0;
+            if (kb < cur) {
+                const size_t o = static_cast<size_t>(row0 + kb) * BEAM_MAX + kc;
+                c[e].val = st.cand_val[o];
+                c[e].idx = kb * V + st.cand_idx[o];
+                lp[e] = st.cand_lp[o];
+                src[e] = kb;
+            }
+        }
+        for (int round = 0; round < beam; ++round) {
+            Cand mine = before(c[1], c[0]) ? c[1] : c[0];
+            const Cand wb = warp_best(mine);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (c[e].idx == wb.idx && c[e].val == wb.val && wb.idx != 0x7fffffff) {
+                    s_sel[round] = wb;
+                    s_sel_lp[round] = lp[e];
+                    s_sel_beam[round] = src[e];
+                    c[e].val = -INFINITY;
+                    c[e].idx = 0x7fffffff;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- stage the image's old per-beam state, then rewrite it in the selected order ----
+    int32_t* s_ids = reinterpret_cast<int32_t*>(sel_smem);                 // [beam][T]
+    float* s_lps = reinterpret_cast<float*>(s_ids + beam * T);             // [beam][T]
+    int32_t* s_anc = reinterpret_cast<int32_t*>(s_lps + beam * T);         // [T][beam]
+    for (int i = tid; i < beam * t; i += blockDim.x) {
+        const int k = i / t, tt = i % t;
+        s_ids[k * T + tt] = st.hist_ids[static_cast<size_t>(row0 + k) * T + tt];
+        s_lps[k * T + tt] = st.hist_lp[static_cast<size_t>(row0 + k) * T + tt];
+        s_anc[tt * beam + k] = st.ancestry[static_cast<size_t>(tt) * R + row0 + k];
+    }
+    if (tid < beam) s_mask[tid] = st.seq_mask[row0 + tid];
+    __syncthreads();
+    for (int i = tid; i < beam * t; i += blockDim.x) {
+        const int k = i / t, tt = i % t;
+        const int src = s_sel_beam[k];
+        st.hist_ids[static_cast<size_t>(row0 + k) * T + tt] = s_ids[src * T + tt];
+        st.hist_lp[static_cast<size_t>(row0 + k) * T + tt] = s_lps[src * T + tt];
+        st.ancestry[static_cast<size_t>(tt) * R + row0 + k] = s_anc[tt * beam + src];
+    }
+    if (tid < beam) {
+        const int k = tid, src = s_sel_beam[k];
+        const int word = s_sel[k].idx - src * V;
+        const int row = row0 + k;
+        st.hist_ids[static_cast<size_t>(row) * T + t] = word;
+        st.hist_lp[static_cast<size_t>(row) * T + t] = s_sel_lp[k];
+        st.ancestry[static_cast<size_t>(t) * R + row] = row0 + src;
+        st.seq_logprob[row] = s_sel[k].val;
+        st.seq_mask[row] = s_mask[src];
+        st.tokens[row] = word;
+        st.parents[row] = src;
+    }
+}
+
+__global__ void beam_finalize_kernel(const BeamDev st, int out_size, int64_t* __restrict__ ids,
+                                     float* __restrict__ logp) {
+    __shared__ int order[BEAM_MAX];
+    const int b = blockIdx.x, beam = st.beam, T = st.max_len;
+    if (threadIdx.x == 0) {
+        // stable descending selection sort of the image's beams by seq_logprob
+        bool used[BEAM_MAX];
+        for (int i = 0; i < BEAM_MAX; ++i) used[i] = false;
+        for (int o = 0; o < beam; ++o) {
+            int bi = -1;
+            float bv = 0.f;
+            for (int k = 0; k < beam; ++k) {
+                if (used[k]) continue;
+                const float v = st.seq_logprob[b * beam + k];
+                if (bi < 0 || v > bv) { bi = k; bv = v; }
+            }
+            used[bi] = true;
+            order[o] = bi;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < out_size * T; i += blockDim.x) {
+        const int o = i / T, tt = i % T;
+        const size_t src = static_cast<size_t>(b * beam + order[o]) * T + tt;
+        const size_t dst = (static_cast<size_t>(b) * out_size + o) * T + tt;
+        ids[dst] = st.hist_ids[src];
+        logp[dst] = st.hist_lp[src];
+    }
+}
+
+// out[r,:] = log_softmax(logits[r,:])  (decoders.py:123) -- standalone form for the module-level API
+__global__ void __launch_bounds__(ROW_THREADS)
+log_softmax_rows_kernel(const float* __restrict__ logits, int ld, float* __restrict__ out, int ldo, int V) {
+    __shared__ float red[ROW_THREADS / 32];
+    const float* row = logits + static_cast<size_t>(blockIdx.x) * ld;
+    float* orow = out + static_cast<size_t>(blockIdx.x) * ldo;
+    float m = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += ROW_THREADS) m = fmaxf(m, row[v]);
+    const float mx = block_reduce_max(m, red);
+    float s = 0.f;
+    for (int v = threadIdx.x; v < V; v += ROW_THREADS) s += __expf(row[v] - mx);
+    const float log_sum = logf(block_reduce_sum(s, red));
+    for (int v = threadIdx.x; v < V; v += ROW_THREADS) orow[v] = (row[v] - mx) - log_sum;
+}
+
+__global__ void beam_reset_kernel(const BeamDev st, int bos) {
+    const int R = st.batch * st.beam;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < R) {
+        st.tokens[i] = bos;
+        st.seq_logprob[i] = 0.f;
+        st.seq_mask[i] = 1.f;
+        st.parents[i] = 0;
+    }
+    for (int j = i; j < R * st.max_len; j += gridDim.x * blockDim.x) {
+        st.hist_ids[j] = 0;
+        st.hist_lp[j] = 0.f;
+        st.ancestry[j] = j % R;
+    }
+}
+
+}  // namespace
+
+struct cap_beam {
+    BeamDev dev;
+    int max_batch;
+    void* arena;
+};
+
+extern "C" int cap_beam_create(int max_batch, int beam, int max_len, int vocab, int eos_idx, cap_beam** out) {
+    CAP_REQUIRE(out != nullptr, "cap_beam_create: null out");
+    CAP_REQUIRE(max_batch > 0 && beam > 0 && beam <= BEAM_MAX, "cap_beam_create: beam must be in [1,%d]", BEAM_MAX);
+    CAP_REQUIRE(max_len > 0 && max_len <= 64 && vocab >= beam, "cap_beam_create: bad max_len/vocab");
+    const size_t R = static_cast<size_t>(max_batch) * beam, T = max_len;
+    const size_t words = R * 4 /*tokens,seq_lp,seq_mask,parents*/ + R * T * 3 + R * BEAM_MAX * 3;
+    void* arena = nullptr;
+    CAP_CHECK_CUDA(cudaMalloc(&arena, words * 4));
+    cap_beam* h = new cap_beam();
+    h->arena = arena;
+    h->max_batch = max_batch;
+    uint32_t* p = static_cast<uint32_t*>(arena);
+    BeamDev& d = h->dev;
+    d.tokens = reinterpret_cast<int32_t*>(p); p += R;
+    d.seq_logprob = reinterpret_cast<float*>(p); p += R;
+    d.seq_mask = reinterpret_cast<float*>(p); p += R;
+    d.parents = reinterpret_cast<int32_t*>(p); p += R;
+    d.hist_ids = reinterpret_cast<int32_t*>(p); p += R * T;
+    d.hist_lp = reinterpret_cast<float*>(p); p += R * T;
+    d.ancestry = reinterpret_cast<int32_t*>(p); p += R * T;
+    d.cand_val = reinterpret_cast<float*>(p); p += R * BEAM_MAX;
+    d.cand_lp = reinterpret_cast<float*>(p); p += R * BEAM_MAX;
+    d.cand_idx = reinterpret_cast<int32_t*>(p); p += R * BEAM_MAX;
+    d.batch = max_batch;
+    d.beam = beam;
+    d.max_len = max_len;
+    d.vocab = vocab;
+    d.eos = eos_idx;
+    *out = h;
+    return CAP_OK;
+}
+
+extern "C" int cap_beam_destroy(cap_beam* h) {
+    if (!h) return CAP_OK;
+    cudaFree(h->arena);
+    delete h;
+    return CAP_OK;
+}
+
+extern "C" int cap_beam_reset(cap_beam* h, int batch, int bos_idx, cap_stream_t stream) {
+    CAP_REQUIRE(h != nullptr, "cap_beam_reset: null handle");
+    CAP_REQUIRE(batch > 0 && batch <= h->max_batch, "cap_beam_reset: batch %d outside (0,%d]", batch, h->max_batch);
+    h->dev.batch = batch;  // the [T][R] tables are laid out for the CURRENT R = batch*beam
+    const int R = batch * h->dev.beam;
+    beam_reset_kernel<<<(R + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, bos_idx);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("beam_reset_kernel");
+}
+
+extern "C" int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, int is_logprob, cap_stream_t stream) {
+    CAP_REQUIRE(h && scores, "cap_beam_step: null pointer");
+    CAP_REQUIRE(t >= 0 && t < h->dev.max_len, "cap_beam_step: step %d outside [0,%d)", t, h->dev.max_len);
+    CAP_REQUIRE(ld >= h->dev.vocab, "cap_beam_step: ld < vocab");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const BeamDev& d = h->dev;
+    const int R = d.batch * d.beam;
+    const size_t row_bytes = static_cast<size_t>(d.vocab) * 4;
+    const int stage = row_bytes <= 160 * 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(beam_rowpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            160 * 1024));
+        attr_done = true;
+    }
+    beam_rowpass_kernel<<<R, ROW_THREADS, stage ? row_bytes : 0, s>>>(d, scores, ld, is_logprob, t, stage);
+    CAP_PROPAGATE(cap_check_launch("beam_rowpass_kernel"));
+    const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
+    beam_select_kernel<<<d.batch, 128, sel_smem, s>>>(d, t);
+    g_cap_launches.fetch_add(2, std::memory_order_relaxed);
+    return cap_check_launch("beam_select_kernel");
+}
+
+extern "C" int cap_beam_finalize(cap_beam* h, int out_size, int64_t* ids, float* logp, cap_stream_t stream) {
+    CAP_REQUIRE(h && ids && logp, "cap_beam_finalize: null pointer");
+    CAP_REQUIRE(out_size >= 1 && out_size <= h->dev.beam, "cap_beam_finalize: out_size %d outside [1,%d]", out_size,
+                h->dev.beam);
+    beam_finalize_kernel<<<h->dev.batch, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, out_size, ids, logp);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("beam_finalize_kernel");
+}
+
+extern "C" int cap_log_softmax(const float* logits, int ld, float* out, int ldo, int rows, int V, cap_stream_t stream) {
+    CAP_REQUIRE(logits && out && rows > 0 && V > 0 && ld >= V && ldo >= V, "cap_log_softmax: bad arguments");
+    log_softmax_rows_kernel<<<rows, ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, out, ldo, V);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("log_softmax_rows_kernel");
+}
+
+extern "C" const int32_t* cap_beam_tokens(cap_beam* h) { return h ? h->dev.tokens : nullptr; }
+extern "C" const int32_t* cap_beam_ancestry(cap_beam* h) { return h ? h->dev.ancestry : nullptr; }
+extern "C" const float* cap_beam_seq_logprob(cap_beam* h) { return h ? h->dev.seq_logprob : nullptr; }
+extern "C" const int32_t* cap_beam_parents(cap_beam* h) { return h ? h->dev.parents : nullptr; }

@@ -1,0 +1,79 @@
+"""Beam search over any stateful model exposing ``step`` / ``apply_to_states``.
+
+Same constructor and ``apply`` contract as the reference's models/modules/beam_search.py:5-118, but
+select / EOS bookkeeping / history reordering run in the device state machine (``cap_beam_*``):
+no full sort over beam*V, no host round trip per step.  The model's own states are reordered with
+one ``index_select`` per state (the generic path; the engine avoids even that).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ... import cabi
+
+
+class BeamSearch(object):
+    def __init__(self, model, b_s: int, max_len: int, eos_idx: int, beam_size: int, device):
+        self.model, self.b_s, self.max_len = model, b_s, max_len
+        self.eos_idx, self.beam_size, self.device = eos_idx, beam_size, torch.device(device)
+
+    def _expand_state(self, selected_rows: torch.Tensor):
+        """Reorder a state whose dim 0 is (image, beam) rows (beam_search.py:19-34)."""
+        def fn(s):
+            return s.index_select(0, selected_rows)
+        return fn
+
+    def apply(self, out_size=1, return_probs=False, **kwargs):
+        if self.device.type != "cuda":
+            raise RuntimeError("BeamSearch runs on CUDA only (no CPU fallback)")
+        if return_probs:
+            raise NotImplementedError("return_probs=True (the full per-step distributions) is not on the hot path")
+        b_s, beam, T = self.b_s, self.beam_size, self.max_len
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        handle = C.c_void_p()
+        state = None
+        try:
+            selected_words = None
+            for t in range(T):
+                cur = 1 if t == 0 else beam
+                word_logprob = self.model.step(t, selected_words, **kwargs).reshape(b_s, cur, -1).float()
+                vocab = word_logprob.shape[-1]
+                if state is None:
+                    cabi.call("cap_beam_create", b_s, beam, T, vocab, self.eos_idx, C.byref(handle))
+                    state = handle
+                    cabi.call("cap_beam_reset", state, b_s, 0, stream)
+                    lib = cabi.load_library()
+                    tokens = self._view(lib.cap_beam_tokens(state), b_s * beam, torch.int32)
+                    parents = self._view(lib.cap_beam_parents(state), b_s * beam, torch.int32)
+                scores = word_logprob.expand(b_s, beam, vocab).contiguous() if cur == 1 else word_logprob.contiguous()
+                cabi.call("cap_beam_step", state, t, scores.data_ptr(), vocab, 1, stream)
+                sel_beam = parents.view(b_s, beam).long()
+                base = torch.arange(b_s, device=self.device).view(-1, 1) * cur
+                self.model.apply_to_states(self._expand_state((base + sel_beam).reshape(-1)))
+                selected_words = tokens.long().view(-1, 1).clone()
+            ids = torch.empty((b_s, out_size, T), device=self.device, dtype=torch.int64)
+            logp = torch.empty((b_s, out_size, T), device=self.device, dtype=torch.float32)
+            cabi.call("cap_beam_finalize", state, out_size, ids.data_ptr(), logp.data_ptr(), stream)
+            torch.cuda.current_stream().synchronize()
+        finally:
+            if state is not None:
+                cabi.call("cap_beam_destroy", state)
+        if out_size == 1:
+            ids, logp = ids.squeeze(1), logp.squeeze(1)
+        return ids, logp
+
+    def _view(self, ptr: int, count: int, dtype: torch.dtype) -> torch.Tensor:
+        """Zero-copy torch view of a device array owned by the beam handle."""
+        itemsize = torch.empty((), dtype=dtype).element_size()
+
+        class _Holder:
+            pass
+
+        holder = _Holder()
+        holder.__cuda_array_interface__ = {
+            "shape": (count,), "typestr": {torch.int32: "<i4", torch.float32: "<f4"}[dtype],
+            "data": (int(ptr), False), "version": 2, "strides": (itemsize,)}
+        return torch.as_tensor(holder, device=self.device)

@@ -1,0 +1,90 @@
+"""Encoders (reference: models/modules/encoders.py:11-112), running on the sm_100a kernels."""
+
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ... import ops
+from ...builders.encoder_builder import META_ENCODER
+from ..utils import clones
+from .attentions import MultiHeadAttention
+from .pos_embeddings import SinusoidPositionalEmbedding
+from .positionwise_feed_forward import PositionWiseFeedForward
+
+
+class EncoderLayer(nn.Module):
+    """Attention -> feed-forward -> zero the padded query rows (encoders.py:11-22)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.mhatt = MultiHeadAttention(config)
+        self.pwff = PositionWiseFeedForward(config)
+
+    def forward(self, queries, keys, values, padding_mask, attention_mask, **kwargs):
+        att = self.mhatt(queries=queries, keys=keys, values=values, padding_mask=padding_mask,
+                         attention_mask=attention_mask, **kwargs)
+        return self.pwff(att, zero_rows=padding_mask.squeeze(1).squeeze(1))
+
+
+class _LayerStack(nn.Module):
+    """LN(x) + pos(x), then the layer stack; shared by the three single-stream encoders."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.pos_embedding = SinusoidPositionalEmbedding(config.D_MODEL)
+        self.layer_norm = nn.LayerNorm(config.D_MODEL)
+        self.d_model = config.D_MODEL
+        self.layers = nn.ModuleList([EncoderLayer(config.SELF_ATTENTION) for _ in range(config.LAYERS)])
+
+    def _embed(self, features):
+        n = features.shape[1]
+        return ops.add_layernorm(features, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
+                                 pos=self.pos_embedding.table(n, features.device))
+
+    def _run(self, features, padding_mask, **kwargs):
+        with torch.no_grad():
+            out = self._embed(features)
+            outs = []
+            for layer in self.layers:
+                out = layer(queries=out, keys=out, values=out, padding_mask=padding_mask,
+                            attention_mask=padding_mask, **kwargs)
+                outs.append(out)
+            return outs
+
+
+@META_ENCODER.register()
+class Encoder(_LayerStack):
+    """encoders.py:24-40."""
+
+    def forward(self, features: torch.Tensor, padding_mask: torch.Tensor):
+        return self._run(features, padding_mask)[-1]
+
+
+@META_ENCODER.register()
+class MultilevelEncoder(_LayerStack):
+    """Returns every layer's output stacked as (B, L, n, d) (encoders.py:42-63)."""
+
+    def forward(self, features: torch.Tensor, padding_mask: torch.Tensor):
+        return torch.stack(self._run(features, padding_mask), dim=1)
+
+
+@META_ENCODER.register()
+class GeometricEncoder(_LayerStack):
+    """Box-relation biased encoder (encoders.py:65-112); takes the boxes next to the features."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.trignometric_embedding = config.TRIGNOMETRIC_EMBEDDING
+        self.d_g = config.D_MODEL // config.SELF_ATTENTION.HEAD if self.trignometric_embedding else 4
+        self.fc_gs = clones(nn.Linear(self.d_g, 1), config.SELF_ATTENTION.HEAD)
+        for fc_g in self.fc_gs:
+            nn.init.xavier_uniform_(fc_g.weight)
+            nn.init.constant_(fc_g.bias, 0)
+
+    def forward(self, features: torch.Tensor, boxes: torch.Tensor, padding_mask: torch.Tensor):
+        with torch.no_grad():
+            w_g = torch.cat([fc.weight for fc in self.fc_gs], dim=0)
+            b_g = torch.cat([fc.bias for fc in self.fc_gs], dim=0)
+            geometry = ops.geometry_bias(boxes, w_g, b_g, bool(self.trignometric_embedding))
+        return self._run(features, padding_mask, relative_geometry_weights=geometry)[-1]

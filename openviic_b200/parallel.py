@@ -1,0 +1,75 @@
+"""Data-parallel sharding of the image batch: one process per GPU, no data-path collective.
+
+Images are independent units (nothing in encoder, decoder or beam search mixes information across
+the batch dimension -- SURVEY.md section 8e), so rank r captions a contiguous slice of the batch with
+its own engine; the only exchange is one final all-gather of the caption ids (and log-probs).
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment; initialises the process group
+    when WORLD_SIZE > 1 (NCCL on GPUs, gloo otherwise)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of `total` images for `rank`; the first total % world ranks get one more."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_tensor(t: Optional[torch.Tensor], world: int, rank: int) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    lo, hi = shard_bounds(t.shape[0], world, rank)
+    return t[lo:hi]
+
+
+def gather_captions(ids: torch.Tensor, logp: torch.Tensor, total: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather the per-rank (b_r, ..., T) ids / log-probs into the full (total, ..., T) batch order.
+
+    Shards may differ by one image, so every rank pads to the largest shard before the collective
+    (NCCL all_gather needs equal sizes) and the padding is dropped afterwards.  ids travel as int32.
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ids, logp
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
+    biggest = max(sizes)
+    tail = tuple(ids.shape[1:])
+
+    def padded(x, dtype):
+        out = torch.zeros((biggest,) + tail, dtype=dtype, device=x.device)
+        out[: x.shape[0]] = x.to(dtype)
+        return out
+
+    ids32, lp = padded(ids, torch.int32), padded(logp, torch.float32)
+    all_ids = [torch.empty_like(ids32) for _ in range(world)]
+    all_lp = [torch.empty_like(lp) for _ in range(world)]
+    dist.all_gather(all_ids, ids32, group=group)
+    dist.all_gather(all_lp, lp, group=group)
+    full_ids = torch.cat([a[:s] for a, s in zip(all_ids, sizes)], 0).to(torch.int64)
+    full_lp = torch.cat([a[:s] for a, s in zip(all_lp, sizes)], 0)
+    return full_ids, full_lp

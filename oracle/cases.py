@@ -1,0 +1,34 @@
+"""Parity cases shared by the golden-fixture generator and the tests (test infrastructure).
+
+Every case is fully determined by this table: YAML config (+ overrides), synthetic-input shape and
+seed.  ``std_region_A`` is BASELINE.json's config A at full size (the reference's own CPU-runnable
+case); the others are the remaining configs at sizes the oracle finishes in seconds.
+"""
+
+CASES = {
+    # name: config file, batch, visual tokens, beam, max_len (T), vocab, seed [, overrides]
+    "std_region_A": dict(config="standard_transformer_using_region.yaml", batch=16, n=50, beam=3, max_len=20,
+                         vocab=10201, seed=11),
+    "std_grid": dict(config="standard_transformer.yaml", batch=6, n=49, beam=5, max_len=20, vocab=1000, seed=12),
+    "m2": dict(config="meshed_memory_transformer.yaml", batch=5, n=50, beam=5, max_len=20, vocab=1000, seed=13),
+    "ort": dict(config="object_relation_transformer.yaml", batch=5, n=50, beam=5, max_len=20, vocab=1000, seed=14),
+    "ort_trig": dict(config="object_relation_transformer.yaml", batch=4, n=50, beam=5, max_len=12, vocab=600, seed=15,
+                     overrides={"MODEL": {"ENCODER": {"TRIGNOMETRIC_EMBEDDING": True}}}),
+    "aoa": dict(config="attention_on_attention.yaml", batch=4, n=50, beam=5, max_len=16, vocab=800, seed=16),
+    "aug_mem": dict(config="augmented_memory_transformer.yaml", batch=4, n=37, beam=4, max_len=16, vocab=777, seed=17),
+}
+
+
+def _merge(node, overrides):
+    for key, value in overrides.items():
+        if isinstance(value, dict):
+            _merge(node[key], value)
+        else:
+            node[key] = value
+
+
+def apply_overrides(cfg, case):
+    """Apply a case's nested overrides to a config node (works for our CfgNode and the yacs shim)."""
+    if case.get("overrides"):
+        _merge(cfg, case["overrides"])
+    return cfg

@@ -1,0 +1,84 @@
+"""The oracle against the golden fixtures produced by the REAL reference (oracle/ref_harness)."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import caption_oracle as oracle
+from oracle.cases import CASES
+from helpers import golden, load_case
+from kat import ScriptedModel, scripted_kat
+
+FAST = [c for c in CASES if c != "std_region_A"]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_reference_beam_search(name):
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case(name)
+    g = golden(name)
+    ltrace = []
+    ids, lp = oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=case["beam"], out_size=1,
+                                         logits_trace=ltrace)
+    assert np.array_equal(ids.numpy(), g["ids"])                       # bit-exact token ids
+    assert np.abs(lp.numpy() - g["logp"]).max() < 2e-5
+    stride = max(1, case["vocab"] // 256)
+    assert np.abs(ltrace[0][:, ::stride].numpy() - g["step0_logp"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_oracle_reproduces_reference_all_beams_encoder_and_forward(name):
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case(name)
+    g = golden(name)
+    ids, lp = oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=case["beam"],
+                                         out_size=case["beam"])
+    assert np.array_equal(ids.numpy(), g["ids_all"])
+    assert np.abs(lp.numpy() - g["logp_all"]).max() < 2e-5
+    with torch.no_grad():
+        enc, mask = oracle.encode(weights, cfg.MODEL, feats, boxes)
+    assert np.array_equal(mask.view(case["batch"], -1).numpy(), g["enc_mask"])
+    rows = enc.reshape(-1, enc.shape[-1])[:: int(g["enc_row_stride"])][:64]
+    assert np.abs(rows.numpy() - g["enc_rows"]).max() < 2e-5
+    tokens = torch.cat([torch.full((case["batch"], 1), vocab.bos_idx, dtype=torch.long),
+                        torch.from_numpy(g["ids"])[:, :-1]], 1)
+    tf = oracle.teacher_forced_log_probs(weights, cfg.MODEL, vocab, feats, tokens, boxes)
+    assert np.abs(tf[:, :, :: max(1, case["vocab"] // 128)].numpy() - g["tf_logp"]).max() < 2e-5
+
+
+def test_fixtures_cover_finished_beams_and_padding():
+    eos = sum(int((golden(c)["ids_all"] == 2).sum()) for c in CASES)
+    pad = sum(int((golden(c)["ids_all"] == 0).sum()) for c in CASES)
+    ragged = sum(int(golden(c)["enc_mask"].sum()) for c in CASES)
+    assert eos > 10 and pad > 100 and ragged > 100
+
+
+def test_scripted_model_known_answer():
+    m = ScriptedModel()
+    ids, lp = oracle.beam_search(m.step, lambda fn: None, 1, 3, 4, 2, out_size=3)
+    exp_ids, exp_lp, exp_fed = scripted_kat()
+    assert ids.tolist() == exp_ids
+    assert torch.allclose(lp, torch.tensor(exp_lp), atol=1e-6)
+    assert m.fed == exp_fed
+    assert torch.allclose(lp.sum(-1), torch.tensor([[-0.15, -0.25, -0.35]]), atol=1e-6)
+
+
+def test_stable_descending_tie_order():
+    """select() keeps the lowest flat index among equal candidates."""
+    scores = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0, 1.0]]).log_softmax(-1).view(1, 1, 6)
+    ids, _ = oracle.beam_search(lambda t, prev: scores.expand(1 if t == 0 else 3, 1, 6), lambda fn: None, 1, 3, 1, 99,
+                                out_size=3)
+    assert ids.view(-1).tolist() == [1, 2, 4]
+
+
+def test_position_tables_and_masks():
+    tab = oracle.word_position_table(21, 512)
+    assert tab.shape == (21, 512) and float(tab[0].abs().sum()) == 0.0
+    assert abs(float(tab[1, 0]) - np.sin(1.0)) < 1e-6 and abs(float(tab[1, 1]) - np.cos(1.0)) < 1e-6
+    vis = oracle.visual_position_table(49, 512)
+    assert abs(float(vis[0, 0]) - np.sin(1.0)) < 1e-6 and abs(float(vis[48, 1]) - np.cos(49.0)) < 1e-5
+    x = torch.randn(2, 5, 8)
+    x[1, 3:] = 0
+    assert oracle.feature_padding_mask(x).view(2, 5).tolist() == [[False] * 5, [False, False, False, True, True]]
+    boxes = torch.tensor([[[0.0, 0.0, 1.0, 1.0], [0.5, 0.5, 1.0, 2.0]]])
+    emb = oracle.box_relation_embedding(boxes, 4, False)
+    assert emb.shape == (1, 2, 2, 4) and abs(float(emb[0, 0, 0, 0]) - np.log(1e-3)) < 1e-6
+    assert oracle.box_relation_embedding(boxes, 64, True).shape == (1, 2, 2, 64)
