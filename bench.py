@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Headline benchmark: captions/sec, beam 5, caption length 20 (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA engine)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One "step" is one pass of the hot path over one batch of synthetic visual features:
+``encoder_forward`` once + 20 beam-search decode steps + (N > 1) the all-gather of caption ids.
+N = 1 workload = BASELINE.json configs[1]: standard transformer, 7x7x2048 grid features, beam 5,
+batch 256 on one B200, bf16.  N > 1: every rank captions its own 256 images (weak scaling), launched
+by torchrun, one rank per GPU; the time is the max over ranks of the CUDA-event time on each rank.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract: value (device-resident inputs),
+e2e (host buffers, H2D + D2H inside the timed region, through the C-ABI host entry point),
+roofline (the dominant kernel family, measured live with CUDA events), cpu_baseline (the oracle port of the
+reference's algorithm on this box's host cores), clocks, gpu_launches.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "captions_per_sec_beam5_len20"
+UNIT = "captions/s"
+BEAM, MAX_LEN, VOCAB, SEED = 5, 20, 10201, 1234
+WORKLOADS = {
+    # name: (yaml, visual tokens, per-GPU batch, algorithmic GFLOP per caption -- BASELINE.md section 3)
+    "standard_grid": ("standard_transformer.yaml", 49, 256, 4.35),
+    "standard_region": ("standard_transformer_using_region.yaml", 50, 256, 4.37),
+    "meshed_memory": ("meshed_memory_transformer.yaml", 50, 128, 5.97),
+    "object_relation": ("object_relation_transformer.yaml", 50, 256, 4.37),
+}
+
+
+def measured_peaks():
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        p = json.loads(path.read_text())
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, sm_max, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                sm_max = max(sm_max, float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, cell in zip(names, row[4:8]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": sm_max or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- model / inputs
+def build_model(workload: str, device):
+    import openviic_b200 as ov
+    from openviic_b200 import synthetic
+    yaml_name, n, batch, _ = WORKLOADS[workload]
+    cfg = ov.get_config(yaml_name)
+    cfg.MODEL.DEVICE = str(device)
+    vocab = synthetic.SyntheticVocab(VOCAB, MAX_LEN)
+    model = ov.build_model(cfg.MODEL, vocab).eval()
+    weights = synthetic.load_synthetic_weights(model, SEED)
+    return cfg, vocab, model, weights
+
+
+def gemm_shapes(cfg, n: int, batch: int, levels: int):
+    """(M, N, K, launches per step) of every projection GEMM in one step (encoder once + 20 decode steps)."""
+    m = cfg.MODEL
+    d, dff, dfeat = m.ENCODER.D_MODEL, m.ENCODER.SELF_ATTENTION.D_FF, m.VISION_EMBEDDING.D_FEATURE
+    le, ld = m.ENCODER.LAYERS, m.DECODER.LAYERS
+    rows, r = batch * n, batch * BEAM
+    shapes = [(rows, d, dfeat, 1), (rows, 3 * d, d, le), (rows, d, d, le), (rows, dff, d, le), (rows, d, dff, le),
+              (rows, 2 * d, d, ld * levels),
+              (r, 3 * d, d, ld * MAX_LEN), (r, d, d, 2 * ld * MAX_LEN), (r * levels, d, d, ld * MAX_LEN),
+              (r, dff, d, ld * MAX_LEN), (r, d, dff, ld * MAX_LEN), (r, VOCAB, d, MAX_LEN)]
+    if levels > 1:
+        shapes.append((r, d, 2 * d, ld * levels * MAX_LEN))
+    return shapes
+
+
+def time_gemm_family(cfg, n, batch, levels, device):
+    """Average launch duration of the tcgen05 GEMM at every shape of the step, with CUDA events on the
+    launching stream; returns (flops per step, seconds per step) of the whole family."""
+    from openviic_b200 import ops
+    total_flops, total_s = 0.0, 0.0
+    for (m_, n_, k_, count) in gemm_shapes(cfg, n, batch, levels):
+        x = torch.randn(m_, k_, device=device).to(torch.bfloat16)
+        w = torch.randn(n_, k_, device=device).to(torch.bfloat16)
+        for _ in range(3):
+            ops.linear(x, w)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ops.linear(x, w)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) / 1e3 / reps
+        total_flops += 2.0 * m_ * n_ * k_ * count
+        total_s += sec * count
+    return total_flops, total_s
+
+
+# ------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_run(workload: str, steps: int, warmup: int, sample_batch: int = 8):
+    """The reference's algorithm (oracle port, fp32, as written) on this box's host cores."""
+    import openviic_b200 as ov
+    from openviic_b200 import synthetic
+    from oracle import caption_oracle as oracle
+    yaml_name, n, _, _ = WORKLOADS[workload]
+    cfg = ov.get_config(yaml_name)
+    cfg.MODEL.DEVICE = "cpu"
+    vocab = synthetic.SyntheticVocab(VOCAB, MAX_LEN)
+    model = ov.build_model(cfg.MODEL, vocab)
+    weights = synthetic.load_synthetic_weights(model, SEED)
+    _, feats, boxes = synthetic.synth_inputs(cfg.MODEL, sample_batch, n, SEED)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(warmup):
+        oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=BEAM)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=BEAM)
+    sec = time.perf_counter() - t0
+    return {"value": sample_batch * steps / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} x {sample_batch} images of the same workload (beam {BEAM}, len {MAX_LEN}, V {VOCAB}, "
+                      f"fp32, torch CPU ops, {sec:.1f} s)"}, sec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base, sec = cpu_reference_run(args.workload, max(1, args.steps), args.warmup, args.cpu_batch)
+    yaml_name, n, _, _ = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / max(1, args.steps) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{yaml_name} n={n} beam{BEAM} len{MAX_LEN} V{VOCAB}; CPU sample of "
+                                   f"{args.cpu_batch} images per step", "parallelism": "host threads"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from openviic_b200 import cabi, parallel, synthetic
+
+    rank, world, local_rank = parallel.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the caption path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    yaml_name, n, per_gpu_batch, gflop_per_caption = WORKLOADS[args.workload]
+    batch = args.batch or per_gpu_batch
+    cfg, vocab, model, weights = build_model(args.workload, device)
+    eng = model.engine(batch, n, BEAM)
+    levels = eng.desc.n_enc_levels
+    needs_boxes = synthetic.needs_boxes(cfg.MODEL)
+
+    # Rotating input sets: 4 x (B,n,2048) bf16 = 4 x 51 MB > 126 MB L2, so no step finds its input cached
+    # (the step's own working set -- 236 MB self-KV cache + 77 MB cross K/V + 52 MB logits -- exceeds L2 too).
+    n_sets = 4
+    feats_host, feats_dev, boxes_host, boxes_dev = [], [], [], []
+    for i in range(n_sets):
+        f = synthetic.synth_features(batch, n, cfg.MODEL.VISION_EMBEDDING.D_FEATURE, SEED + 17 * i + 1000 * rank,
+                                     ragged=synthetic.feature_field(cfg.MODEL) == "region_features")
+        fh = f.to(torch.bfloat16).pin_memory()
+        feats_host.append(fh)
+        feats_dev.append(fh.to(device))
+        bx = synthetic.synth_boxes(batch, n, SEED + i).pin_memory() if needs_boxes else None
+        boxes_host.append(bx)
+        boxes_dev.append(None if bx is None else bx.to(device))
+
+    def step(i):
+        eng.encode(feats_dev[i % n_sets], boxes_dev[i % n_sets])
+        ids, logp = eng.beam_search(out_size=1, use_graph=not args.no_graph)
+        return parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world) if world > 1 else (ids, logp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # kernels per step, counted on one eager (non-graph) pass: graph replays launch the same kernel nodes
+    eng.encode(feats_dev[0], boxes_dev[0])
+    eng.beam_search(out_size=1, use_graph=False)
+    torch.cuda.synchronize()
+    c0 = cabi.launch_count()
+    eng.encode(feats_dev[0], boxes_dev[0])
+    eng.beam_search(out_size=1, use_graph=False)
+    torch.cuda.synchronize()
+    launches_per_step = cabi.launch_count() - c0
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            out = step(i)
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = batch * world * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI host entry point (H2D + compute + D2H + sync per step) ----
+    out_host = (torch.empty((batch, 1, MAX_LEN), dtype=torch.int64).pin_memory(),
+                torch.empty((batch, 1, MAX_LEN), dtype=torch.float32).pin_memory())
+    for i in range(3):
+        eng.caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, out_host)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, out_host)
+        if world > 1:
+            parallel.gather_captions(out_host[0].squeeze(1).to(device), out_host[1].squeeze(1).to(device), batch * world)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = batch * world * args.steps / float(e2e_s.item())
+    h2d = feats_host[0].numel() * feats_host[0].element_size() + (boxes_host[0].numel() * 4 if needs_boxes else 0)
+    d2h = batch * MAX_LEN * (8 + 4)
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM), measured live with CUDA events ----
+    peaks = measured_peaks()
+    flops, gemm_s = time_gemm_family(cfg, n, batch, levels, device)
+    achieved = flops / gemm_s / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_tn_bf16_tcgen05 (all projection/FFN/vocab GEMMs of one step)",
+                "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "share_of_step": gemm_s / (total_ms / 1e3 / args.steps),
+                "step_algorithmic_tflops": gflop_per_caption * 1e9 * value / world / 1e12,
+                "step_frac_of_tensor_peak": gflop_per_caption * 1e9 * value / world / 1e12 / peaks["tflops_sustained"]}
+
+    cpu_base = None
+    if not args.skip_cpu:
+        cpu_base, _ = cpu_reference_run(args.workload, steps=args.cpu_steps, warmup=1, sample_batch=args.cpu_batch)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{yaml_name}: {n} visual tokens x 2048, beam {BEAM}, len {MAX_LEN}, V {VOCAB}, "
+                               f"batch {batch}/GPU", "global_batch": batch * world, "parallelism": f"dp{world}",
+                   "l2": f"{n_sets} rotating input batches ({n_sets} x {h2d / 1e6:.0f} MB > 126 MB L2); step working set > L2",
+                   "cuda_graph": not args.no_graph, "weights": "synthetic seed 1234 (openviic_b200/synthetic.py)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "host_features": "bf16 pinned", "api": "cap_engine_caption_host"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="standard_grid", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    try:
+        return run_gpu_arm(args)
+    finally:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

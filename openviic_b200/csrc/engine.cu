@@ -108,6 +108,7 @@ struct cap_engine {
 
     // CUDA graph of a full beam search (begin + T steps + finalize)
     cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t capture_stream = nullptr;  // the legacy default stream cannot be captured: capture here, replay anywhere
     int graph_batch = 0, graph_out_size = 0;
     int64_t* graph_ids = nullptr;
     float* graph_logp = nullptr;
@@ -280,6 +281,7 @@ extern "C" int cap_engine_create(const cap_model_desc* desc, cap_engine** out) {
 extern "C" int cap_engine_destroy(cap_engine* e) {
     if (!e) return CAP_OK;
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->beam_state) cap_beam_destroy(e->beam_state);
     for (void* p : e->allocations) cudaFree(p);
     delete e;
@@ -592,9 +594,11 @@ extern "C" int cap_engine_beam_search(cap_engine* e, int out_size, int64_t* ids,
             e->graph_exec = nullptr;
         }
         cudaGraph_t graph = nullptr;
-        CAP_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const int rc = run_search_eager(e, out_size, ids, logp, s);
-        const cudaError_t end = cudaStreamEndCapture(s, &graph);
+        if (!e->capture_stream) CAP_CHECK_CUDA(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+        cudaStream_t cs = e->capture_stream;
+        CAP_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_search_eager(e, out_size, ids, logp, cs);
+        const cudaError_t end = cudaStreamEndCapture(cs, &graph);
         if (rc != CAP_OK) {
             if (graph) cudaGraphDestroy(graph);
             return rc;

@@ -297,11 +297,20 @@ def _reorder(s: Tensor, b_s: int, cur: int, beam_idx: Tensor) -> Tensor:
 
 def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states: Callable[[Callable], None],
                 b_s: int, beam: int, max_len: int, eos_idx: int, out_size: int = 1,
-                trace: Optional[list] = None) -> Tuple[Tensor, Tensor]:
+                trace: Optional[list] = None, stable_ties: bool = False) -> Tuple[Tensor, Tensor]:
     """BeamSearch.apply/iter/select, models/modules/beam_search.py:36-118.
 
     ``step(t, prev_tokens)`` returns (rows,1,V) log-probs; ``reorder_states(fn)`` maps ``fn`` over
     every decode state (models/modules/containers.py:27-32).  Always runs ``max_len`` steps.
+
+    Tie order.  The reference calls ``torch.sort(descending=True)`` WITHOUT ``stable=True``.  Probed in
+    the build container (torch 2.11 CPU): for rows of more than 16 elements that is an unstable
+    introsort whose order among exactly equal candidates is implementation-defined (neither lowest-
+    nor highest-index-first; the CUDA sort differs again), so the reference has no portable tie
+    order to reproduce.  ``stable_ties=False`` restates the call as written (identical to the
+    reference whenever the selected candidates are distinct); ``stable_ties=True`` pins the order
+    this repo defines -- value descending, then lowest flat index -- which is what the CUDA
+    kernels implement and what the tie-laden known-answer tests use.
     """
     seq_mask = torch.ones(b_s, beam, 1)
     seq_logprob = torch.zeros(b_s, 1, 1)
@@ -321,7 +330,10 @@ def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states:
             frozen[:, :, 1:] = NEG_SENTINEL
             cand = seq_mask * cand + frozen * (1 - seq_mask)
         # select(): full descending sort of the (cur*V) candidates, keep the first `beam`
-        sorted_lp, sorted_idx = torch.sort(cand.view(b_s, -1), -1, descending=True)
+        if stable_ties:
+            sorted_lp, sorted_idx = torch.sort(cand.view(b_s, -1), stable=True, dim=-1, descending=True)
+        else:
+            sorted_lp, sorted_idx = torch.sort(cand.view(b_s, -1), -1, descending=True)
         sel_lp, sel_idx = sorted_lp[:, :beam], sorted_idx[:, :beam]
         sel_beam = torch.div(sel_idx, vocab, rounding_mode="trunc")
         sel_word = sel_idx - sel_beam * vocab

@@ -61,12 +61,20 @@ def test_scripted_model_known_answer():
     assert torch.allclose(lp.sum(-1), torch.tensor([[-0.15, -0.25, -0.35]]), atol=1e-6)
 
 
-def test_stable_descending_tie_order():
-    """select() keeps the lowest flat index among equal candidates."""
+def test_tie_order_contract():
+    """Rows of <= 16 candidates: the reference's sort is lowest-index-first.
+    Longer rows: torch's unstable sort has no portable tie order, so `stable_ties=True` is the pinned
+    contract (value desc, lowest flat index first) that the CUDA kernels implement."""
     scores = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0, 1.0]]).log_softmax(-1).view(1, 1, 6)
-    ids, _ = oracle.beam_search(lambda t, prev: scores.expand(1 if t == 0 else 3, 1, 6), lambda fn: None, 1, 3, 1, 99,
-                                out_size=3)
-    assert ids.view(-1).tolist() == [1, 2, 4]
+    for stable in (False, True):
+        ids, _ = oracle.beam_search(lambda t, prev: scores.expand(1 if t == 0 else 3, 1, 6), lambda fn: None, 1, 3, 1,
+                                    99, out_size=3, stable_ties=stable)
+        assert ids.view(-1).tolist() == [1, 2, 4]
+    wide = torch.zeros(1, 1, 500)
+    wide[0, 0, [7, 300, 450]] = 1.0
+    ids, _ = oracle.beam_search(lambda t, prev: wide.expand(1 if t == 0 else 3, 1, 500), lambda fn: None, 1, 3, 1, 99,
+                                out_size=3, stable_ties=True)
+    assert ids.view(-1).tolist() == [7, 300, 450]
 
 
 def test_position_tables_and_masks():
