@@ -224,6 +224,10 @@ const void* cap_engine_encoder_output(cap_engine* e);   /* bf16 [levels][B*n][d_
 const uint8_t* cap_engine_encoder_mask(cap_engine* e);  /* uint8 [B*n]                 */
 const float* cap_engine_logits(cap_engine* e, int* ld); /* fp32 [R][ld]                */
 cap_beam* cap_engine_beam(cap_engine* e);
+/* Debug: when non-NULL, every later cap_linear writes 8 %globaltimer stamps (ns) per CTA into
+ * device_buffer[cta*8 + k]: 0 entry, 1 prologue done, 2 first TMA issued, 3 first stage landed,
+ * 4 last MMA committed, 5 accumulator visible to the epilogue, 6 stores issued, 7 TMEM freed. */
+int cap_debug_gemm_trace(unsigned long long* device_buffer);
 /* Kernels launched by this library since load (all entry points); for bench.py's gpu_launches. */
 int64_t cap_launch_count(void);
 

@@ -49,6 +49,7 @@ SIGNATURES = {
     "cap_abi_version": (_i, []),
     "cap_last_error": (C.c_char_p, []),
     "cap_launch_count": (_i64, []),
+    "cap_debug_gemm_trace": (_i, [_vp]),
     "cap_linear": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_linear_simt": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_add_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),

@@ -210,6 +210,107 @@ decode_self_attention_kernel(const bf16* __restrict__ qkv, const int32_t* __rest
     reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
 }
 
+// Wide variant for H*64 == 32*EPL (H = 4, 8, 16): ONE warp per row covers all heads.  Lane l owns
+// EPL consecutive elements of the H*64-wide q/k/v rows (head = l*EPL/64), so every key costs one fully
+// coalesced row read for K and one for V with all 32 lanes busy at any step t; per-head scores are
+// reduced across the 64/EPL lanes of the head with shuffles; softmax is online (single pass over keys).
+template <int EPL>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
+                                  const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
+                                  float scale) {
+    constexpr int LANES_PER_HEAD = HEAD_DIM / EPL;
+    constexpr int VEC = EPL / 8;  // 16-byte vectors per lane
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * DEC_WARPS + warp;
+    if (r >= R) return;
+    const int hd = 32 * EPL;
+    const size_t row_stride = static_cast<size_t>(3) * hd;
+    const size_t step_stride = static_cast<size_t>(R) * row_stride;
+    const int nkeys = t + 1;
+
+    float q[EPL];
+    {
+        const bf16x8* qp = reinterpret_cast<const bf16x8*>(qkv + t * step_stride + r * row_stride + lane * EPL);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            unpack8(qp[c], q + c * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[c * 8 + i] *= scale;
+        }
+    }
+    // this lane's key slot / pad flag for key index == lane (and lane + 32), fetched once
+    int my_slot[2];
+    bool my_pad[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int j = c * 32 + lane;
+        my_slot[c] = 0;
+        my_pad[c] = true;
+        if (j < nkeys) {
+            my_slot[c] = (j == t) ? r : ancestry[static_cast<size_t>(j) * R + r];
+            my_pad[c] = padflag[static_cast<size_t>(j) * R + my_slot[c]] != 0;
+        }
+    }
+    float m = -INFINITY, l = 0.f;
+    float acc[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+
+    constexpr int UNROLL = 4;
+    for (int j0 = 0; j0 < nkeys; j0 += UNROLL) {
+        bf16x8 kreg[UNROLL][VEC], vreg[UNROLL][VEC];
+        bool pad[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int j = min(j0 + u, nkeys - 1);  // tail iterations re-read the last key, masked below
+            const int sl = __shfl_sync(0xffffffffu, my_slot[j >> 5], j & 31);
+            pad[u] = __shfl_sync(0xffffffffu, static_cast<int>(my_pad[j >> 5]), j & 31) != 0 || (j0 + u >= nkeys);
+            const bf16* base = qkv + j * step_stride + sl * row_stride + lane * EPL;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                kreg[u][c] = reinterpret_cast<const bf16x8*>(base + hd)[c];
+                vreg[u][c] = reinterpret_cast<const bf16x8*>(base + 2 * hd)[c];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                float kf[8];
+                unpack8(kreg[u][c], kf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s = fmaf(q[c * 8 + i], kf[i], s);
+            }
+#pragma unroll
+            for (int o = LANES_PER_HEAD / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (pad[u]) continue;  // masked key (uniform across the warp)
+            const float m_new = fmaxf(m, s);
+            const float corr = __expf(m - m_new);  // exp(-inf) = 0 on the first live key
+            const float p = __expf(s - m_new);
+            l = l * corr + p;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                float vf[8];
+                unpack8(vreg[u][c], vf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c * 8 + i] = acc[c * 8 + i] * corr + p * vf[i];
+            }
+            m = m_new;
+        }
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    bf16* orow = out + static_cast<size_t>(r) * ldo + lane * EPL;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = acc[c * 8 + i] * inv;
+        reinterpret_cast<bf16x8*>(orow)[c] = pack8(o);
+    }
+}
+
 int launch_attention(const AttnDev& a, cudaStream_t stream) {
     const int nk_all = a.nk + a.n_mem;
     const size_t smem = static_cast<size_t>(nk_all) * (K_STRIDE + HEAD_DIM) * 2 + ATT_WARPS * HEAD_DIM * 4 +
@@ -280,10 +381,24 @@ extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestr
     CAP_REQUIRE(qkv && ancestry && padflag && out, "cap_decode_self_attention: null pointer");
     CAP_REQUIRE(t >= 0 && t < DEC_MAX_T, "cap_decode_self_attention: step %d outside [0,%d)", t, DEC_MAX_T);
     CAP_REQUIRE(R > 0 && H > 0 && ldo % 2 == 0, "cap_decode_self_attention: bad shape");
-    const int items = R * H;
-    decode_self_attention_kernel<<<(items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0,
-                                   static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(qkv), ancestry, padflag, static_cast<bf16*>(out), ldo, t, R, H, scale);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bf16* cache = static_cast<const bf16*>(qkv);
+    bf16* o = static_cast<bf16*>(out);
+    const int wide_blocks = (R + DEC_WARPS - 1) / DEC_WARPS;
+    if (H == 8 && ldo % 8 == 0) {
+        decode_self_attention_wide_kernel<16><<<wide_blocks, DEC_WARPS * 32, 0, s>>>(cache, ancestry, padflag, o, ldo, t,
+                                                                                    R, scale);
+    } else if (H == 4 && ldo % 8 == 0) {
+        decode_self_attention_wide_kernel<8><<<wide_blocks, DEC_WARPS * 32, 0, s>>>(cache, ancestry, padflag, o, ldo, t, R,
+                                                                                   scale);
+    } else if (H == 16 && ldo % 8 == 0) {
+        decode_self_attention_wide_kernel<32><<<wide_blocks, DEC_WARPS * 32, 0, s>>>(cache, ancestry, padflag, o, ldo, t,
+                                                                                    R, scale);
+    } else {
+        const int items = R * H;
+        decode_self_attention_kernel<<<(items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(
+            cache, ancestry, padflag, o, ldo, t, R, H, scale);
+    }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_self_attention_kernel");
 }

@@ -174,6 +174,96 @@ beam_rowpass_kernel(const BeamDev st, const float* __restrict__ scores, int ld, 
     }
 }
 
+// Register-resident row pass (vocab <= 256*ITEMS): the row is read from HBM exactly once into
+// statically indexed registers; max / sum-exp / `beam` rounds of block arg-best all run on registers
+// with one __syncthreads per reduction (double-buffered partials).
+template <int ITEMS>
+__global__ void __launch_bounds__(ROW_THREADS)
+beam_rowpass_reg_kernel(const BeamDev st, const float* __restrict__ scores, int ld, int is_logprob, int t) {
+    __shared__ float red[ROW_THREADS / 32];
+    __shared__ float s_val[2][ROW_THREADS / 32];
+    __shared__ int s_idx[2][ROW_THREADS / 32];
+    const int r = blockIdx.x;
+    const int beam = st.beam, V = st.vocab;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    float mask = st.seq_mask[r];
+    if (t > 0) mask *= (st.tokens[r] != st.eos) ? 1.f : 0.f;
+    const float seq_lp = st.seq_logprob[r];
+    __syncthreads();
+    if (tid == 0) st.seq_mask[r] = mask;
+
+    float* cval = st.cand_val + static_cast<size_t>(r) * BEAM_MAX;
+    float* clp = st.cand_lp + static_cast<size_t>(r) * BEAM_MAX;
+    int32_t* cidx = st.cand_idx + static_cast<size_t>(r) * BEAM_MAX;
+    if (t == 0 && (r % beam) != 0) {
+        if (tid < beam) { cval[tid] = -INFINITY; clp[tid] = 0.f; cidx[tid] = tid; }
+        return;
+    }
+    if (mask == 0.f) {
+        if (tid < beam) { cval[tid] = (tid == 0) ? seq_lp : SENTINEL; clp[tid] = 0.f; cidx[tid] = tid; }
+        return;
+    }
+
+    const float* row = scores + static_cast<size_t>(r) * ld;
+    float x[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int v = tid + i * ROW_THREADS;
+        x[i] = v < V ? __ldg(row + v) : -INFINITY;
+    }
+    float mx = 0.f, log_sum = 0.f;
+    if (!is_logprob) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) m = fmaxf(m, x[i]);
+        mx = block_reduce_max(m, red);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) s += __expf(x[i] - mx);  // padding lanes hold -inf -> 0
+        log_sum = logf(block_reduce_sum(s, red));
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int v = tid + i * ROW_THREADS;
+        const float lp = is_logprob ? x[i] : (x[i] - mx) - log_sum;
+        x[i] = v < V ? seq_lp + lp : -INFINITY;  // candidate_logprob = seq_logprob + word_logprob
+    }
+    for (int round = 0; round < beam; ++round) {
+        Cand mine;
+        mine.val = -INFINITY;
+        mine.idx = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {  // indices ascend with i: strict > keeps the lowest index on ties
+            if (x[i] > mine.val) { mine.val = x[i]; mine.idx = tid + i * ROW_THREADS; }
+        }
+        const Cand wb = warp_best(mine);
+        const int buf = round & 1;
+        if (lane == 0) { s_val[buf][warp] = wb.val; s_idx[buf][warp] = wb.idx; }
+        __syncthreads();
+        Cand bb;
+        bb.val = s_val[buf][0];
+        bb.idx = s_idx[buf][0];
+#pragma unroll
+        for (int w = 1; w < ROW_THREADS / 32; ++w) {
+            Cand c;
+            c.val = s_val[buf][w];
+            c.idx = s_idx[buf][w];
+            if (before(c, bb)) bb = c;
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            if (tid + i * ROW_THREADS == bb.idx) x[i] = -INFINITY;  // the owner retires the winner
+        if (tid == 0) {
+            const int widx = bb.idx == 0x7fffffff ? 0 : bb.idx;
+            const float xv = __ldg(row + widx);
+            cval[round] = bb.val;
+            cidx[round] = widx;
+            clp[round] = is_logprob ? xv : (xv - mx) - log_sum;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) beam_select_kernel(const BeamDev st, int t) {
     __shared__ Cand s_sel[BEAM_MAX];
     __shared__ float s_sel_lp[BEAM_MAX];
@@ -387,7 +477,19 @@ extern "C" int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, in
                                             160 * 1024));
         attr_done = true;
     }
-    beam_rowpass_kernel<<<R, ROW_THREADS, stage ? row_bytes : 0, s>>>(d, scores, ld, is_logprob, t, stage);
+    const int items = (d.vocab + ROW_THREADS - 1) / ROW_THREADS;
+    if (items <= 8)
+        beam_rowpass_reg_kernel<8><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else if (items <= 16)
+        beam_rowpass_reg_kernel<16><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else if (items <= 32)
+        beam_rowpass_reg_kernel<32><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else if (items <= 40)
+        beam_rowpass_reg_kernel<40><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else if (items <= 64)
+        beam_rowpass_reg_kernel<64><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else  // very large vocabularies: shared-memory / multi-pass variant
+        beam_rowpass_kernel<<<R, ROW_THREADS, stage ? row_bytes : 0, s>>>(d, scores, ld, is_logprob, t, stage);
     CAP_PROPAGATE(cap_check_launch("beam_rowpass_kernel"));
     const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
     beam_select_kernel<<<d.batch, 128, sel_smem, s>>>(d, t);

@@ -30,7 +30,17 @@ struct GemmParams {
     const float* bias;
     int M, N, K, ldo;
     int out_f32, act, num_stages, vec_ok;
+    uint32_t pipe_bytes;  // bytes reserved for the stage ring (>= the epilogue's staging tile), multiple of 1024
+    unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (cap_debug_gemm_trace), else nullptr
 };
+
+__device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
+    if (p.trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
 
 // ----------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -159,10 +169,11 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.num_stages;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.pipe_bytes);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -170,6 +181,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int n0 = blockIdx.x * BLOCK_N;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
+    if (threadIdx.x == 0) stamp(p, 0);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
@@ -190,6 +202,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(p, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -201,6 +214,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                 tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
                 tma_load_2d(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+                if (kb == 0) stamp(p, 2);
             }
         }
     } else if (warp == 1) {
@@ -210,6 +224,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(&full_bar[s], phase);
+                if (kb == 0) stamp(p, 3);
                 tcgen05_fence_after();
                 const uint8_t* a_tile = smem + s * STAGE_BYTES;
                 const uint64_t a_desc = make_smem_desc(a_tile);
@@ -222,55 +237,74 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
             }
             umma_commit(tmem_full_bar);  // accumulator complete
+            stamp(p, 4);
         }
     } else {
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-        const int row = m0 + quad * 32 + lane;
+        // ---- epilogue: TMEM -> registers -> (+bias, activation) -> smem transpose -> coalesced rows ----
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+        const int etid = threadIdx.x - 64;    // 0..127 among the epilogue threads
+        for (int i = etid; i < BLOCK_N; i += 128)
+            s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // bias tile visible to the 4 epilogue warps
         mbar_wait(tmem_full_bar, 0);
+        if (warp == 2 && lane == 0) stamp(p, 5);
         tcgen05_fence_after();
-        const bool row_ok = row < p.M;
+        // All MMAs have retired, so the pipeline stages are free: reuse them as the output staging tile.
+        const int esz = p.out_f32 ? 4 : 2;
+        const int row_bytes = BLOCK_N * esz;
+        const int pitch = row_bytes + 16;     // +16 B: consecutive rows start one bank group apart
+        uint8_t* stage_out = smem + static_cast<size_t>(quad * 32) * pitch;
+        uint8_t* my_row = stage_out + static_cast<size_t>(lane) * pitch;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
             tmem_ld_wait();
-            const int col0 = n0 + c0;
-            if (!row_ok || col0 >= p.N) continue;
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(v[j]);
-                const int col = col0 + j;
-                if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-                f[j] = apply_act(x, p.act);
-            }
-            const bool full_chunk = (col0 + 32 <= p.N) && p.vec_ok;
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(__uint_as_float(v[j]) + s_bias[c0 + j], p.act);
             if (p.out_f32) {
-                float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                if (full_chunk) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
-                }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(my_row + (c0 + j) * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
-                bf16* dst = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                if (full_chunk) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(dst + j) = pack8(f + j);
+                for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(my_row + (c0 + j) * 2) = pack8(f + j);
+            }
+        }
+        __syncwarp();
+        // write-out: each warp owns its 32 rows; lanes tile a row with 16-byte vectors
+        const int vecs_per_row = row_bytes / 16;
+        const int elems_per_vec = 16 / esz;
+        const int n_valid = min(BLOCK_N, p.N - n0);                 // valid columns of this tile
+        uint8_t* gout = reinterpret_cast<uint8_t*>(p.out);
+        for (int idx = lane; idx < 32 * vecs_per_row; idx += 32) {
+            const int rr = idx / vecs_per_row, vv = idx % vecs_per_row;
+            const int grow = m0 + quad * 32 + rr;
+            const int col = vv * elems_per_vec;
+            if (grow >= p.M || col >= n_valid) continue;
+            const uint8_t* src = stage_out + static_cast<size_t>(rr) * pitch + vv * 16;
+            uint8_t* dst = gout + (static_cast<size_t>(grow) * p.ldo + n0 + col) * esz;
+            if (p.vec_ok && col + elems_per_vec <= n_valid) {
+                *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(src);
+            } else {  // ragged last tile or unaligned output: element-wise
+                const int cnt = min(elems_per_vec, n_valid - col);
+                if (p.out_f32) {
+                    for (int e = 0; e < cnt; ++e) reinterpret_cast<float*>(dst)[e] = reinterpret_cast<const float*>(src)[e];
                 } else {
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+                    for (int e = 0; e < cnt; ++e) reinterpret_cast<bf16*>(dst)[e] = reinterpret_cast<const bf16*>(src)[e];
                 }
             }
         }
     }
+    if (warp == 2 && lane == 0) stamp(p, 6);
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
     }
+    if (threadIdx.x == 32) stamp(p, 7);
 }
 
 // ---------------------------------------------------------------------------------- host launcher
@@ -311,7 +345,11 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
 template <int BLOCK_N>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
     constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
-    const size_t smem = 1024 + static_cast<size_t>(p.num_stages) * stage_bytes + (2 * MAX_STAGES + 1) * 8 + 16;
+    const uint32_t staging = BLOCK_M * (BLOCK_N * (p.out_f32 ? 4 : 2) + 16);
+    uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
+    if (pipe < staging) pipe = (staging + 1023) / 1024 * 1024;
+    p.pipe_bytes = pipe;
+    const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4;
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
@@ -325,6 +363,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_bf16_tcgen05");
 }
+
+unsigned long long* g_gemm_trace = nullptr;
 
 int env_int(const char* name, int fallback) {
     const char* s = getenv(name);
@@ -377,6 +417,7 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     p.num_stages = stages;
     const size_t esz = p.out_f32 ? 4 : 2;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((static_cast<size_t>(ldy) * esz) % 16 == 0);
+    p.trace = g_gemm_trace;
 
     CUtensorMap ta, tb;
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
@@ -387,6 +428,11 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
         case 64: return launch_gemm<64>(ta, tb, p, s);
         default: return launch_gemm<32>(ta, tb, p, s);
     }
+}
+
+extern "C" int cap_debug_gemm_trace(unsigned long long* device_buffer) {
+    g_gemm_trace = device_buffer;
+    return CAP_OK;
 }
 
 // ------------------------------------------------------------------ CUDA-core cross-check GEMM

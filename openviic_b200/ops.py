@@ -211,31 +211,29 @@ def log_softmax(logits: Tensor) -> Tensor:
     return out.reshape(logits.shape)
 
 
-_BF16_CACHE = {}
+def _param_cache(kind: str, params, build):
+    """Derived tensor (bf16 cast / stacked bias) cached ON the first parameter object, so it dies with
+    the parameter; invalidated when any source is modified in place, replaced or moved."""
+    key = (kind,) + tuple((id(p), p.data_ptr(), p._version, str(p.device)) for p in params)
+    store = params[0].__dict__.setdefault("_cap_cache", {})
+    hit = store.get(kind + str(len(params)))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        value = build()
+    store[kind + str(len(params))] = (key, value)
+    return value
 
 
 def cached_bf16(*params: Tensor) -> Tensor:
-    """bf16 copy of one parameter -- or the row-wise stack of several -- cached until any of them
-    is modified in place, replaced or moved (keyed on storage pointer + version counter)."""
-    key = tuple((p.data_ptr(), p._version, p.device) for p in params)
-    slot = tuple(id(p) for p in params)
-    hit = _BF16_CACHE.get(slot)
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    with torch.no_grad():
+    """bf16 copy of one parameter, or the row-wise stack of several (e.g. fc_q|fc_k|fc_v)."""
+    def build():
         value = torch.cat([p.detach() for p in params], dim=0) if len(params) > 1 else params[0].detach()
-        value = value.to(torch.bfloat16).contiguous()
-    _BF16_CACHE[slot] = (key, value)
-    return value
+        return value.to(torch.bfloat16).contiguous()
+    return _param_cache("bf16", params, build)
 
 
 def cached_f32_cat(*params: Tensor) -> Tensor:
-    key = tuple((p.data_ptr(), p._version, p.device) for p in params)
-    slot = ("f32",) + tuple(id(p) for p in params)
-    hit = _BF16_CACHE.get(slot)
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    with torch.no_grad():
-        value = torch.cat([p.detach().float().reshape(-1) for p in params], dim=0).contiguous()
-    _BF16_CACHE[slot] = (key, value)
-    return value
+    """fp32 concatenation of several 1-D parameters (stacked biases)."""
+    return _param_cache("f32cat", params,
+                        lambda: torch.cat([p.detach().float().reshape(-1) for p in params], dim=0).contiguous())
