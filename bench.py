@@ -144,15 +144,23 @@ def time_gemm_family(cfg, n, batch, levels, device):
         w = torch.randn(n_, k_, device=device).to(torch.bfloat16)
         for _ in range(3):
             ops.linear(x, w)
+        torch.cuda.synchronize()
+        # replay 20 back-to-back launches from a CUDA graph so the events see device time, not the
+        # Python launch rate (the step itself runs from a graph too)
+        reps, graph, side = 20, torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(reps):
+                    ops.linear(x, w)
+        graph.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
-            ops.linear(x, w)
+        for _ in range(3):
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        sec = e0.elapsed_time(e1) / 1e3 / reps
+        sec = e0.elapsed_time(e1) / 1e3 / (3 * reps)
         total_flops += 2.0 * m_ * n_ * k_ * count
         total_s += sec * count
     return total_flops, total_s

@@ -311,6 +311,140 @@ decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* _
     }
 }
 
+// Decode-step cross-attention, wide variant (H = 8): one CTA per image, its 4 warps split the image's
+// keys round-robin, every warp serves ALL `BEAMS` rows of the image and all heads at once (lane l owns
+// 16 consecutive elements of the 512-wide rows, 4 lanes per head), so each K/V row is read from HBM
+// exactly once per step with 32 busy lanes; the per-warp online-softmax partials (m, l, acc) are
+// merged through shared memory (flash-decoding style).
+constexpr int XW_WARPS = 4;
+constexpr int XW_EPL = 16;
+
+template <int BEAMS>
+__global__ void __launch_bounds__(XW_WARPS * 32)
+decode_cross_attention_wide_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
+                                   const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
+                                   float scale) {
+    extern __shared__ __align__(16) float xw_smem[];
+    float* s_acc = xw_smem;                                             // [WARPS][BEAMS][32][EPL]
+    float* s_m = s_acc + XW_WARPS * BEAMS * 32 * XW_EPL;                // [WARPS][BEAMS][32]
+    float* s_l = s_m + XW_WARPS * BEAMS * 32;                           // [WARPS][BEAMS][32]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int hd = 32 * XW_EPL;
+    const bf16* kvb = kv + static_cast<size_t>(b) * n * 2 * hd + lane * XW_EPL;
+    const uint8_t* mrow = key_mask ? key_mask + static_cast<size_t>(b) * n : nullptr;
+
+    bf16x8 qreg[BEAMS][2];
+#pragma unroll
+    for (int bb = 0; bb < BEAMS; ++bb) {
+        const bf16x8* qp = reinterpret_cast<const bf16x8*>(q + static_cast<size_t>(b * BEAMS + bb) * ldq + lane * XW_EPL);
+        qreg[bb][0] = qp[0];
+        qreg[bb][1] = qp[1];
+    }
+    float m[BEAMS], l[BEAMS], acc[BEAMS][XW_EPL];
+#pragma unroll
+    for (int bb = 0; bb < BEAMS; ++bb) {
+        m[bb] = -INFINITY;
+        l[bb] = 0.f;
+#pragma unroll
+        for (int i = 0; i < XW_EPL; ++i) acc[bb][i] = 0.f;
+    }
+    for (int j0 = warp; j0 < n; j0 += 2 * XW_WARPS) {
+        bf16x8 kreg[2][2], vreg[2][2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * XW_WARPS;
+            live[u] = j < n && !(mrow && mrow[j]);
+            const bf16* base = kvb + static_cast<size_t>(min(j, n - 1)) * 2 * hd;
+            kreg[u][0] = reinterpret_cast<const bf16x8*>(base)[0];
+            kreg[u][1] = reinterpret_cast<const bf16x8*>(base)[1];
+            vreg[u][0] = reinterpret_cast<const bf16x8*>(base + hd)[0];
+            vreg[u][1] = reinterpret_cast<const bf16x8*>(base + hd)[1];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;  // warp-uniform
+            float kf[XW_EPL], vf[XW_EPL];
+            unpack8(kreg[u][0], kf);
+            unpack8(kreg[u][1], kf + 8);
+            unpack8(vreg[u][0], vf);
+            unpack8(vreg[u][1], vf + 8);
+#pragma unroll
+            for (int bb = 0; bb < BEAMS; ++bb) {
+                float qf[XW_EPL];
+                unpack8(qreg[bb][0], qf);
+                unpack8(qreg[bb][1], qf + 8);
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < XW_EPL; ++i) s = fmaf(qf[i], kf[i], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s *= scale;
+                const float m_new = fmaxf(m[bb], s);
+                const float corr = __expf(m[bb] - m_new);
+                const float p = __expf(s - m_new);
+                l[bb] = l[bb] * corr + p;
+#pragma unroll
+                for (int i = 0; i < XW_EPL; ++i) acc[bb][i] = acc[bb][i] * corr + p * vf[i];
+                m[bb] = m_new;
+            }
+        }
+    }
+#pragma unroll
+    for (int bb = 0; bb < BEAMS; ++bb) {
+        const int slot = (warp * BEAMS + bb) * 32 + lane;
+        s_m[slot] = m[bb];
+        s_l[slot] = l[bb];
+        float4* dst = reinterpret_cast<float4*>(s_acc + static_cast<size_t>(slot) * XW_EPL);
+#pragma unroll
+        for (int i = 0; i < XW_EPL; i += 4) dst[i / 4] = make_float4(acc[bb][i], acc[bb][i + 1], acc[bb][i + 2], acc[bb][i + 3]);
+    }
+    __syncthreads();
+    for (int bb = warp; bb < BEAMS; bb += XW_WARPS) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < XW_WARPS; ++w) mx = fmaxf(mx, s_m[(w * BEAMS + bb) * 32 + lane]);
+        float lsum = 0.f, o[XW_EPL];
+#pragma unroll
+        for (int i = 0; i < XW_EPL; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int w = 0; w < XW_WARPS; ++w) {
+            const int slot = (w * BEAMS + bb) * 32 + lane;
+            const float mw = s_m[slot];
+            const float f = (mw == -INFINITY) ? 0.f : __expf(mw - mx);
+            lsum += s_l[slot] * f;
+            const float4* src = reinterpret_cast<const float4*>(s_acc + static_cast<size_t>(slot) * XW_EPL);
+#pragma unroll
+            for (int i = 0; i < XW_EPL; i += 4) {
+                const float4 a4 = src[i / 4];
+                o[i] += a4.x * f; o[i + 1] += a4.y * f; o[i + 2] += a4.z * f; o[i + 3] += a4.w * f;
+            }
+        }
+        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+#pragma unroll
+        for (int i = 0; i < XW_EPL; ++i) o[i] *= inv;
+        bf16* orow = out + static_cast<size_t>(b * BEAMS + bb) * ldo + lane * XW_EPL;
+        reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
+        reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
+    }
+}
+
+template <int BEAMS>
+int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
+                      float scale, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(XW_WARPS) * BEAMS * 32 * (XW_EPL + 2) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_wide_kernel<BEAMS>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+    }
+    decode_cross_attention_wide_kernel<BEAMS><<<B, XW_WARPS * 32, smem, stream>>>(q, ldq, kv, key_mask, out, ldo, n, scale);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_cross_attention_wide_kernel");
+}
+
 int launch_attention(const AttnDev& a, cudaStream_t stream) {
     const int nk_all = a.nk + a.n_mem;
     const size_t smem = static_cast<size_t>(nk_all) * (K_STRIDE + HEAD_DIM) * 2 + ATT_WARPS * HEAD_DIM * 4 +
@@ -360,6 +494,19 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
     CAP_REQUIRE(q && kv && out, "cap_decode_cross_attention: null pointer");
     CAP_REQUIRE(B > 0 && beam > 0 && n > 0 && n <= MAX_KEYS && H > 0, "cap_decode_cross_attention: bad shape");
     const int hd = H * HEAD_DIM;
+    if (H == 8 && beam <= 5 && ldq % 8 == 0 && ldo % 8 == 0) {
+        const bf16* qp = static_cast<const bf16*>(q);
+        const bf16* kvp = static_cast<const bf16*>(kv);
+        bf16* op = static_cast<bf16*>(out);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        switch (beam) {
+            case 1: return launch_cross_wide<1>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+            case 2: return launch_cross_wide<2>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+            case 3: return launch_cross_wide<3>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+            case 4: return launch_cross_wide<4>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+            default: return launch_cross_wide<5>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+        }
+    }
     AttnDev a;
     a.q = static_cast<const bf16*>(q);
     a.k = static_cast<const bf16*>(kv);

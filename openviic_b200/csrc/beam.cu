@@ -20,7 +20,7 @@ extern std::atomic<long long> g_cap_launches;
 namespace {
 
 constexpr int BEAM_MAX = 8;
-constexpr int ROW_THREADS = 256;
+constexpr int ROW_THREADS = 512;
 constexpr float SENTINEL = -999.0f;  // models/modules/beam_search.py:54
 
 struct Cand {
@@ -178,11 +178,12 @@ beam_rowpass_kernel(const BeamDev st, const float* __restrict__ scores, int ld, 
 // statically indexed registers; max / sum-exp / `beam` rounds of block arg-best all run on registers
 // with one __syncthreads per reduction (double-buffered partials).
 template <int ITEMS>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, ITEMS <= 20 ? 2 : 1)
 beam_rowpass_reg_kernel(const BeamDev st, const float* __restrict__ scores, int ld, int is_logprob, int t) {
     __shared__ float red[ROW_THREADS / 32];
     __shared__ float s_val[2][ROW_THREADS / 32];
     __shared__ int s_idx[2][ROW_THREADS / 32];
+    __shared__ int s_win[BEAM_MAX];
     const int r = blockIdx.x;
     const int beam = st.beam, V = st.vocab;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -256,11 +257,123 @@ beam_rowpass_reg_kernel(const BeamDev st, const float* __restrict__ scores, int 
             if (tid + i * ROW_THREADS == bb.idx) x[i] = -INFINITY;  // the owner retires the winner
         if (tid == 0) {
             const int widx = bb.idx == 0x7fffffff ? 0 : bb.idx;
-            const float xv = __ldg(row + widx);
             cval[round] = bb.val;
             cidx[round] = widx;
-            clp[round] = is_logprob ? xv : (xv - mx) - log_sum;
+            s_win[round] = widx;
         }
+    }
+    __syncthreads();
+    if (tid < beam) {  // the winners' word log-probs, recomputed from the row exactly as above
+        const float xv = __ldg(row + s_win[tid]);
+        clp[tid] = is_logprob ? xv : (xv - mx) - log_sum;
+    }
+}
+
+// Row merge for the fused vocabulary epilogue (gemm_tcgen05.cu, TOPK > 0): one warp per beam row
+// combines the per-N-tile partials -- log-sum-exp from (max, sum exp) pairs, then the row's `beam` best
+// candidates seq_logprob + ((x - max) - log_sum) out of tiles*TOPK logits -- and does the same EOS /
+// sentinel bookkeeping as the row pass.  Same outputs (cand_val / cand_lp / cand_idx) as the row pass.
+constexpr int MERGE_WARPS = 4;
+constexpr int MERGE_TILES_PER_LANE = 4;  // up to 128 N tiles of 128 columns: vocab <= 16384
+
+template <int TOPK>
+__global__ void __launch_bounds__(MERGE_WARPS * 32)
+beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const float* __restrict__ part_val,
+                     const int32_t* __restrict__ part_idx, int tiles, int t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R = st.batch * st.beam;
+    const int r = blockIdx.x * MERGE_WARPS + warp;
+    if (r >= R) return;
+    const int beam = st.beam;
+
+    float mask = st.seq_mask[r];
+    if (t > 0) mask *= (st.tokens[r] != st.eos) ? 1.f : 0.f;
+    const float seq_lp = st.seq_logprob[r];
+    __syncwarp();
+    if (lane == 0) st.seq_mask[r] = mask;
+    float* cval = st.cand_val + static_cast<size_t>(r) * BEAM_MAX;
+    float* clp = st.cand_lp + static_cast<size_t>(r) * BEAM_MAX;
+    int32_t* cidx = st.cand_idx + static_cast<size_t>(r) * BEAM_MAX;
+    if (t == 0 && (r % beam) != 0) {
+        if (lane < beam) { cval[lane] = -INFINITY; clp[lane] = 0.f; cidx[lane] = lane; }
+        return;
+    }
+    if (mask == 0.f) {
+        if (lane < beam) { cval[lane] = (lane == 0) ? seq_lp : SENTINEL; clp[lane] = 0.f; cidx[lane] = lane; }
+        return;
+    }
+    const size_t row_base = static_cast<size_t>(r) * tiles;
+    float tm[MERGE_TILES_PER_LANE], ts[MERGE_TILES_PER_LANE];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
+        const int tile = lane + 32 * i;
+        tm[i] = -INFINITY;
+        ts[i] = 0.f;
+        if (tile < tiles) {
+            const float2 ms = *reinterpret_cast<const float2*>(part_ms + (row_base + tile) * 2);
+            tm[i] = ms.x;
+            ts[i] = ms.y;
+        }
+        mx = fmaxf(mx, tm[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MERGE_TILES_PER_LANE; ++i)
+        if (tm[i] != -INFINITY) sum += ts[i] * __expf(tm[i] - mx);
+    const float log_sum = logf(warp_sum(sum));
+
+    float cv[MERGE_TILES_PER_LANE][TOPK], lp[MERGE_TILES_PER_LANE][TOPK];
+    int ci[MERGE_TILES_PER_LANE][TOPK];
+#pragma unroll
+    for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
+        const int tile = lane + 32 * i;
+#pragma unroll
+        for (int k = 0; k < TOPK; ++k) {
+            cv[i][k] = -INFINITY;
+            lp[i][k] = 0.f;
+            ci[i][k] = 0x7fffffff;
+            if (tile < tiles) {
+                const float x = part_val[(row_base + tile) * TOPK + k];
+                const int idx = part_idx[(row_base + tile) * TOPK + k];
+                if (idx != 0x7fffffff) {
+                    lp[i][k] = (x - mx) - log_sum;   // word_logprob, same formula as the row pass
+                    cv[i][k] = seq_lp + lp[i][k];    // candidate_logprob
+                    ci[i][k] = idx;
+                }
+            }
+        }
+    }
+    for (int round = 0; round < beam; ++round) {
+        Cand mine;
+        mine.val = -INFINITY;
+        mine.idx = 0x7fffffff;
+        float mine_lp = 0.f;
+#pragma unroll
+        for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
+#pragma unroll
+            for (int k = 0; k < TOPK; ++k) {
+                if (cand_before(cv[i][k], ci[i][k], mine.val, mine.idx)) {
+                    mine.val = cv[i][k];
+                    mine.idx = ci[i][k];
+                    mine_lp = lp[i][k];
+                }
+            }
+        }
+        const Cand wb = warp_best(mine);
+        if (mine.idx == wb.idx && wb.idx != 0x7fffffff) {  // the owning lane publishes and retires it
+            cval[round] = wb.val;
+            cidx[round] = wb.idx;
+            clp[round] = mine_lp;
+#pragma unroll
+            for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
+#pragma unroll
+                for (int k = 0; k < TOPK; ++k)
+                    if (ci[i][k] == wb.idx) { cv[i][k] = -INFINITY; ci[i][k] = 0x7fffffff; }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -478,19 +591,43 @@ extern "C" int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, in
         attr_done = true;
     }
     const int items = (d.vocab + ROW_THREADS - 1) / ROW_THREADS;
-    if (items <= 8)
+    if (items <= 4)
+        beam_rowpass_reg_kernel<4><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else if (items <= 8)
         beam_rowpass_reg_kernel<8><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
     else if (items <= 16)
         beam_rowpass_reg_kernel<16><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+    else if (items <= 20)
+        beam_rowpass_reg_kernel<20><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
     else if (items <= 32)
         beam_rowpass_reg_kernel<32><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
-    else if (items <= 40)
-        beam_rowpass_reg_kernel<40><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
     else if (items <= 64)
         beam_rowpass_reg_kernel<64><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
     else  // very large vocabularies: shared-memory / multi-pass variant
         beam_rowpass_kernel<<<R, ROW_THREADS, stage ? row_bytes : 0, s>>>(d, scores, ld, is_logprob, t, stage);
     CAP_PROPAGATE(cap_check_launch("beam_rowpass_kernel"));
+    const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
+    beam_select_kernel<<<d.batch, 128, sel_smem, s>>>(d, t);
+    g_cap_launches.fetch_add(2, std::memory_order_relaxed);
+    return cap_check_launch("beam_select_kernel");
+}
+
+extern "C" int cap_beam_step_partials(cap_beam* h, int t, const float* part_ms, const float* part_val,
+                                      const int32_t* part_idx, int tiles, int topk, cap_stream_t stream) {
+    CAP_REQUIRE(h && part_ms && part_val && part_idx, "cap_beam_step_partials: null pointer");
+    CAP_REQUIRE(t >= 0 && t < h->dev.max_len, "cap_beam_step_partials: step %d outside [0,%d)", t, h->dev.max_len);
+    CAP_REQUIRE(tiles > 0 && tiles <= 32 * MERGE_TILES_PER_LANE, "cap_beam_step_partials: %d tiles unsupported", tiles);
+    CAP_REQUIRE((topk == 5 || topk == 8) && topk >= h->dev.beam, "cap_beam_step_partials: topk %d < beam or unsupported",
+                topk);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const BeamDev& d = h->dev;
+    const int R = d.batch * d.beam;
+    const int blocks = (R + MERGE_WARPS - 1) / MERGE_WARPS;
+    if (topk == 5)
+        beam_rowmerge_kernel<5><<<blocks, MERGE_WARPS * 32, 0, s>>>(d, part_ms, part_val, part_idx, tiles, t);
+    else
+        beam_rowmerge_kernel<8><<<blocks, MERGE_WARPS * 32, 0, s>>>(d, part_ms, part_val, part_idx, tiles, t);
+    CAP_PROPAGATE(cap_check_launch("beam_rowmerge_kernel"));
     const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
     beam_select_kernel<<<d.batch, 128, sel_smem, s>>>(d, t);
     g_cap_launches.fetch_add(2, std::memory_order_relaxed);

@@ -102,6 +102,9 @@ struct cap_engine {
     float* buf_y32 = nullptr;
     float* logits = nullptr;
     int ld_logits = 0;
+    float *part_ms = nullptr, *part_val = nullptr;  // fused vocabulary epilogue partials
+    int32_t* part_idx = nullptr;
+    int vocab_tiles = 0, topk = 5;
     int64_t* out_ids = nullptr;
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
@@ -412,6 +415,11 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->buf_y32, rows_max * static_cast<size_t>(std::max(2 * d, hd))));
     e->ld_logits = (m.vocab + 7) / 8 * 8;
     CAP_PROPAGATE(dev_alloc(e, &e->logits, R * e->ld_logits));
+    e->vocab_tiles = (m.vocab + 127) / 128;
+    e->topk = beam <= 5 ? 5 : 8;
+    CAP_PROPAGATE(dev_alloc(e, &e->part_ms, R * e->vocab_tiles * 2));
+    CAP_PROPAGATE(dev_alloc(e, &e->part_val, R * e->vocab_tiles * e->topk));
+    CAP_PROPAGATE(dev_alloc(e, &e->part_idx, R * e->vocab_tiles * e->topk));
     CAP_PROPAGATE(dev_alloc(e, &e->out_ids, R * T));
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));
     CAP_PROPAGATE(cap_beam_create(max_batch, beam, T, m.vocab, m.eos_idx, &e->beam_state));
@@ -493,11 +501,39 @@ extern "C" int cap_engine_begin_decode(cap_engine* e, cap_stream_t stream) {
     return cap_beam_reset(e->beam_state, e->cur_batch, e->desc.bos_idx, stream);
 }
 
+namespace {
+int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden);
+}
+
 extern "C" int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t stream) {
     CAP_REQUIRE(e && e->encoded, "cap_engine_decode_logits: encode first");
-    const cap_model_desc& m = e->desc;
-    CAP_REQUIRE(t >= 0 && t < m.max_len, "cap_engine_decode_logits: step %d outside [0,%d)", t, m.max_len);
+    CAP_REQUIRE(t >= 0 && t < e->desc.max_len, "cap_engine_decode_logits: step %d outside [0,%d)", t, e->desc.max_len);
+    bf16* x = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAP_PROPAGATE(run_decoder_stack(e, t, s, &x));
+    // bias-free vocabulary projection (decoders.py:90,121); log-softmax happens in the beam row pass
+    return run_linear(x, e->desc.d_model, e->vocab_fc, e->logits, e->ld_logits, CAP_F32, CAP_ACT_NONE,
+                      e->cur_batch * e->beam, s);
+}
+
+extern "C" int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream) {
+    CAP_REQUIRE(e && e->encoded, "cap_engine_decode_step: encode first");
+    CAP_REQUIRE(t >= 0 && t < e->desc.max_len, "cap_engine_decode_step: step %d outside [0,%d)", t, e->desc.max_len);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->vocab_tiles > 128)  // vocabularies beyond the merge kernel's reach: materialise logits
+        return cap_engine_decode_logits(e, t, stream) || cap_engine_beam_advance(e, t, stream);
+    bf16* x = nullptr;
+    CAP_PROPAGATE(run_decoder_stack(e, t, s, &x));
+    const int R = e->cur_batch * e->beam;
+    int tiles = 0;
+    CAP_PROPAGATE(cap_vocab_topk_partials(x, e->desc.d_model, e->vocab_fc.w, e->vocab_fc.b, R, e->desc.vocab,
+                                          e->desc.d_model, e->topk, e->part_ms, e->part_val, e->part_idx, &tiles, s));
+    return cap_beam_step_partials(e->beam_state, t, e->part_ms, e->part_val, e->part_idx, tiles, e->topk, s);
+}
+
+namespace {
+int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
+    const cap_model_desc& m = e->desc;
     const int d = m.d_model, hd = e->hd(), lv = e->levels(), T = m.max_len;
     const int B = e->cur_batch, n = e->cur_n, beam = e->beam;
     const int R = B * beam;
@@ -555,9 +591,10 @@ extern "C" int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t strea
         CAP_PROPAGATE(run_ln(e->buf_y32, d, c, d, L.ffn.ln, nullptr, 0, pad_t, e->buf_x, d, R, d, s));
         x = e->buf_x;
     }
-    // bias-free vocabulary projection (decoders.py:90,121); log-softmax is fused into the beam row pass
-    return run_linear(x, d, e->vocab_fc, e->logits, e->ld_logits, CAP_F32, CAP_ACT_NONE, R, s);
+    *hidden = x;
+    return CAP_OK;
 }
+}  // namespace
 
 extern "C" int cap_engine_beam_advance(cap_engine* e, int t, cap_stream_t stream) {
     CAP_REQUIRE(e && e->encoded, "cap_engine_beam_advance: encode first");
@@ -567,10 +604,7 @@ extern "C" int cap_engine_beam_advance(cap_engine* e, int t, cap_stream_t stream
 namespace {
 int run_search_eager(cap_engine* e, int out_size, int64_t* ids, float* logp, cudaStream_t s) {
     CAP_PROPAGATE(cap_engine_begin_decode(e, s));
-    for (int t = 0; t < e->desc.max_len; ++t) {
-        CAP_PROPAGATE(cap_engine_decode_logits(e, t, s));
-        CAP_PROPAGATE(cap_engine_beam_advance(e, t, s));
-    }
+    for (int t = 0; t < e->desc.max_len; ++t) CAP_PROPAGATE(cap_engine_decode_step(e, t, s));
     return cap_beam_finalize(e->beam_state, out_size, ids, logp, s);
 }
 }  // namespace

@@ -125,3 +125,59 @@ def test_beam_argument_errors(device):
             cabi.call("cap_beam_reset", h, 5, 1, None)
     finally:
         cabi.call("cap_beam_destroy", h)
+
+
+@pytest.mark.parametrize("B,beam,V", [(7, 5, 10201), (5, 3, 1000), (3, 8, 777)])
+def test_fused_vocab_epilogue_matches_logits_path(device, B, beam, V):
+    """Vocabulary GEMM with the log-softmax/top-k epilogue + row merge == GEMM -> logits -> row pass."""
+    from openviic_b200 import ops
+    from openviic_b200.engine import _device_view
+    T, d, eos = 6, 512, 2
+    R = B * beam
+    g = torch.Generator().manual_seed(V)
+    w = (torch.randn(V, d, generator=g) * 0.13).to(torch.bfloat16).to(device)
+    xs = [torch.randn(R, d, generator=g).to(torch.bfloat16).to(device) for _ in range(T)]
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib = cabi.load_library()
+    topk = 5 if beam <= 5 else 8
+    tiles = (V + 127) // 128
+    part_ms = torch.empty(R, tiles, 2, device=device)
+    part_val = torch.empty(R, tiles, topk, device=device)
+    part_idx = torch.empty(R, tiles, topk, device=device, dtype=torch.int32)
+    results = []
+    for fused in (False, True):
+        h = C.c_void_p()
+        cabi.call("cap_beam_create", B, beam, T, V, eos, C.byref(h))
+        try:
+            cabi.call("cap_beam_reset", h, B, 1, stream)
+            for t in range(T):
+                if fused:
+                    n_tiles = C.c_int()
+                    cabi.call("cap_vocab_topk_partials", xs[t].data_ptr(), d, w.data_ptr(), None, R, V, d, topk,
+                              part_ms.data_ptr(), part_val.data_ptr(), part_idx.data_ptr(), C.byref(n_tiles), stream)
+                    assert n_tiles.value == tiles
+                    cabi.call("cap_beam_step_partials", h, t, part_ms.data_ptr(), part_val.data_ptr(),
+                              part_idx.data_ptr(), tiles, topk, stream)
+                else:
+                    logits = ops.linear(xs[t], w, None, out_dtype=torch.float32).contiguous()
+                    cabi.call("cap_beam_step", h, t, logits.data_ptr(), logits.stride(0), 0, stream)
+            ids = torch.empty(B, beam, T, dtype=torch.int64, device=device)
+            lp = torch.empty(B, beam, T, dtype=torch.float32, device=device)
+            cabi.call("cap_beam_finalize", h, beam, ids.data_ptr(), lp.data_ptr(), stream)
+            torch.cuda.synchronize()
+            seq = _device_view(lib.cap_beam_seq_logprob(h), (R,), torch.float32, device).clone().cpu()
+            results.append((ids.cpu(), lp.cpu(), seq))
+        finally:
+            cabi.call("cap_beam_destroy", h)
+    (ids_a, lp_a, seq_a), (ids_b, lp_b, seq_b) = results
+    assert torch.equal(ids_a, ids_b)
+    assert (lp_a - lp_b).abs().max().item() < 1e-4 and (seq_a - seq_b).abs().max().item() < 1e-4
+    # partials against a direct fp32 statement of the last step
+    ref = xs[-1].float() @ w.float().t()
+    lse = torch.logsumexp(ref, -1).cpu()
+    pm, ps = part_ms[..., 0].cpu(), part_ms[..., 1].cpu()
+    mx = pm.max(1).values
+    mine = mx + torch.log((ps * torch.exp(pm - mx[:, None])).sum(1))
+    assert (mine - lse).abs().max().item() < 1e-3
+    best = part_val.cpu().reshape(R, -1).max(1).values
+    assert (best - ref.max(1).values.cpu()).abs().max().item() < 1e-3
