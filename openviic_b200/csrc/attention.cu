@@ -42,6 +42,7 @@ struct AttnDev {
 };
 
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnDev a) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint8_t att_smem[];
     const int nk_all = a.nk + a.n_mem;
     bf16* sk = reinterpret_cast<bf16*>(att_smem);                       // [nk_all][K_STRIDE]
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_self_attention_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
                              const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
                              int H, float scale) {
+    pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * DEC_WARPS + warp;
     if (item >= R * H) return;
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
                                   const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
                                   float scale) {
+    pdl_prologue();
     constexpr int LANES_PER_HEAD = HEAD_DIM / EPL;
     constexpr int VEC = EPL / 8;  // 16-byte vectors per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(XW_WARPS * 32)
 decode_cross_attention_wide_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
                                    const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
                                    float scale) {
+    pdl_prologue();
     extern __shared__ __align__(16) float xw_smem[];
     float* s_acc = xw_smem;                                             // [WARPS][BEAMS][32][EPL]
     float* s_m = s_acc + XW_WARPS * BEAMS * 32 * XW_EPL;                // [WARPS][BEAMS][32]
@@ -440,7 +444,7 @@ int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_done = true;
     }
-    decode_cross_attention_wide_kernel<BEAMS><<<B, XW_WARPS * 32, smem, stream>>>(q, ldq, kv, key_mask, out, ldo, n, scale);
+    CAP_LAUNCH((decode_cross_attention_wide_kernel<BEAMS>), B, XW_WARPS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n, scale);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_cross_attention_wide_kernel");
 }
@@ -455,7 +459,7 @@ int launch_attention(const AttnDev& a, cudaStream_t stream) {
         attr_done = true;
     }
     dim3 grid((a.nq + Q_TILE - 1) / Q_TILE, a.H, a.B);
-    attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(a);
+    CAP_LAUNCH((attention_kernel), grid, ATT_THREADS, smem, stream, a);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("attention_kernel");
 }
@@ -533,18 +537,14 @@ extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestr
     bf16* o = static_cast<bf16*>(out);
     const int wide_blocks = (R + DEC_WARPS - 1) / DEC_WARPS;
     if (H == 8 && ldo % 8 == 0) {
-        decode_self_attention_wide_kernel<16><<<wide_blocks, DEC_WARPS * 32, 0, s>>>(cache, ancestry, padflag, o, ldo, t,
-                                                                                    R, scale);
+        CAP_LAUNCH((decode_self_attention_wide_kernel<16>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else if (H == 4 && ldo % 8 == 0) {
-        decode_self_attention_wide_kernel<8><<<wide_blocks, DEC_WARPS * 32, 0, s>>>(cache, ancestry, padflag, o, ldo, t, R,
-                                                                                   scale);
+        CAP_LAUNCH((decode_self_attention_wide_kernel<8>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else if (H == 16 && ldo % 8 == 0) {
-        decode_self_attention_wide_kernel<32><<<wide_blocks, DEC_WARPS * 32, 0, s>>>(cache, ancestry, padflag, o, ldo, t,
-                                                                                    R, scale);
+        CAP_LAUNCH((decode_self_attention_wide_kernel<32>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else {
         const int items = R * H;
-        decode_self_attention_kernel<<<(items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(
-            cache, ancestry, padflag, o, ldo, t, R, H, scale);
+        CAP_LAUNCH((decode_self_attention_kernel), (items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, H, scale);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_self_attention_kernel");

@@ -77,6 +77,7 @@ struct BeamDev {
 
 __global__ void __launch_bounds__(ROW_THREADS)
 beam_rowpass_kernel(const BeamDev st, const float* __restrict__ scores, int ld, int is_logprob, int t, int stage_smem) {
+    pdl_prologue();
     extern __shared__ __align__(16) float row_smem[];
     __shared__ float red[ROW_THREADS / 32];
     __shared__ Cand warp_cand[ROW_THREADS / 32];
@@ -180,6 +181,7 @@ beam_rowpass_kernel(const BeamDev st, const float* __restrict__ scores, int ld, 
 template <int ITEMS>
 __global__ void __launch_bounds__(ROW_THREADS, ITEMS <= 20 ? 2 : 1)
 beam_rowpass_reg_kernel(const BeamDev st, const float* __restrict__ scores, int ld, int is_logprob, int t) {
+    pdl_prologue();
     __shared__ float red[ROW_THREADS / 32];
     __shared__ float s_val[2][ROW_THREADS / 32];
     __shared__ int s_idx[2][ROW_THREADS / 32];
@@ -280,6 +282,7 @@ template <int TOPK>
 __global__ void __launch_bounds__(MERGE_WARPS * 32)
 beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const float* __restrict__ part_val,
                      const int32_t* __restrict__ part_idx, int tiles, int t) {
+    pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = st.batch * st.beam;
     const int r = blockIdx.x * MERGE_WARPS + warp;
@@ -378,6 +381,7 @@ beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const 
 }
 
 __global__ void __launch_bounds__(128) beam_select_kernel(const BeamDev st, int t) {
+    pdl_prologue();
     __shared__ Cand s_sel[BEAM_MAX];
     __shared__ float s_sel_lp[BEAM_MAX];
     __shared__ int s_sel_beam[BEAM_MAX];
@@ -459,6 +463,7 @@ __global__ void __launch_bounds__(128) beam_select_kernel(const BeamDev st, int 
 
 __global__ void beam_finalize_kernel(const BeamDev st, int out_size, int64_t* __restrict__ ids,
                                      float* __restrict__ logp) {
+    pdl_prologue();
     __shared__ int order[BEAM_MAX];
     const int b = blockIdx.x, beam = st.beam, T = st.max_len;
     if (threadIdx.x == 0) {
@@ -490,6 +495,7 @@ __global__ void beam_finalize_kernel(const BeamDev st, int out_size, int64_t* __
 // out[r,:] = log_softmax(logits[r,:])  (decoders.py:123) -- standalone form for the module-level API
 __global__ void __launch_bounds__(ROW_THREADS)
 log_softmax_rows_kernel(const float* __restrict__ logits, int ld, float* __restrict__ out, int ldo, int V) {
+    pdl_prologue();
     __shared__ float red[ROW_THREADS / 32];
     const float* row = logits + static_cast<size_t>(blockIdx.x) * ld;
     float* orow = out + static_cast<size_t>(blockIdx.x) * ldo;
@@ -503,6 +509,7 @@ log_softmax_rows_kernel(const float* __restrict__ logits, int ld, float* __restr
 }
 
 __global__ void beam_reset_kernel(const BeamDev st, int bos) {
+    pdl_prologue();
     const int R = st.batch * st.beam;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < R) {
@@ -570,7 +577,7 @@ extern "C" int cap_beam_reset(cap_beam* h, int batch, int bos_idx, cap_stream_t 
     CAP_REQUIRE(batch > 0 && batch <= h->max_batch, "cap_beam_reset: batch %d outside (0,%d]", batch, h->max_batch);
     h->dev.batch = batch;  // the [T][R] tables are laid out for the CURRENT R = batch*beam
     const int R = batch * h->dev.beam;
-    beam_reset_kernel<<<(R + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, bos_idx);
+    CAP_LAUNCH((beam_reset_kernel), (R + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), h->dev, bos_idx);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("beam_reset_kernel");
 }
@@ -592,22 +599,22 @@ extern "C" int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, in
     }
     const int items = (d.vocab + ROW_THREADS - 1) / ROW_THREADS;
     if (items <= 4)
-        beam_rowpass_reg_kernel<4><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+        CAP_LAUNCH((beam_rowpass_reg_kernel<4>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);
     else if (items <= 8)
-        beam_rowpass_reg_kernel<8><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+        CAP_LAUNCH((beam_rowpass_reg_kernel<8>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);
     else if (items <= 16)
-        beam_rowpass_reg_kernel<16><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+        CAP_LAUNCH((beam_rowpass_reg_kernel<16>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);
     else if (items <= 20)
-        beam_rowpass_reg_kernel<20><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+        CAP_LAUNCH((beam_rowpass_reg_kernel<20>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);
     else if (items <= 32)
-        beam_rowpass_reg_kernel<32><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+        CAP_LAUNCH((beam_rowpass_reg_kernel<32>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);
     else if (items <= 64)
-        beam_rowpass_reg_kernel<64><<<R, ROW_THREADS, 0, s>>>(d, scores, ld, is_logprob, t);
+        CAP_LAUNCH((beam_rowpass_reg_kernel<64>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);
     else  // very large vocabularies: shared-memory / multi-pass variant
-        beam_rowpass_kernel<<<R, ROW_THREADS, stage ? row_bytes : 0, s>>>(d, scores, ld, is_logprob, t, stage);
+        CAP_LAUNCH((beam_rowpass_kernel), R, ROW_THREADS, stage ? row_bytes : 0, s, d, scores, ld, is_logprob, t, stage);
     CAP_PROPAGATE(cap_check_launch("beam_rowpass_kernel"));
     const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
-    beam_select_kernel<<<d.batch, 128, sel_smem, s>>>(d, t);
+    CAP_LAUNCH((beam_select_kernel), d.batch, 128, sel_smem, s, d, t);
     g_cap_launches.fetch_add(2, std::memory_order_relaxed);
     return cap_check_launch("beam_select_kernel");
 }
@@ -624,12 +631,12 @@ extern "C" int cap_beam_step_partials(cap_beam* h, int t, const float* part_ms, 
     const int R = d.batch * d.beam;
     const int blocks = (R + MERGE_WARPS - 1) / MERGE_WARPS;
     if (topk == 5)
-        beam_rowmerge_kernel<5><<<blocks, MERGE_WARPS * 32, 0, s>>>(d, part_ms, part_val, part_idx, tiles, t);
+        CAP_LAUNCH((beam_rowmerge_kernel<5>), blocks, MERGE_WARPS * 32, 0, s, d, part_ms, part_val, part_idx, tiles, t);
     else
-        beam_rowmerge_kernel<8><<<blocks, MERGE_WARPS * 32, 0, s>>>(d, part_ms, part_val, part_idx, tiles, t);
+        CAP_LAUNCH((beam_rowmerge_kernel<8>), blocks, MERGE_WARPS * 32, 0, s, d, part_ms, part_val, part_idx, tiles, t);
     CAP_PROPAGATE(cap_check_launch("beam_rowmerge_kernel"));
     const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
-    beam_select_kernel<<<d.batch, 128, sel_smem, s>>>(d, t);
+    CAP_LAUNCH((beam_select_kernel), d.batch, 128, sel_smem, s, d, t);
     g_cap_launches.fetch_add(2, std::memory_order_relaxed);
     return cap_check_launch("beam_select_kernel");
 }
@@ -638,14 +645,14 @@ extern "C" int cap_beam_finalize(cap_beam* h, int out_size, int64_t* ids, float*
     CAP_REQUIRE(h && ids && logp, "cap_beam_finalize: null pointer");
     CAP_REQUIRE(out_size >= 1 && out_size <= h->dev.beam, "cap_beam_finalize: out_size %d outside [1,%d]", out_size,
                 h->dev.beam);
-    beam_finalize_kernel<<<h->dev.batch, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, out_size, ids, logp);
+    CAP_LAUNCH((beam_finalize_kernel), h->dev.batch, 128, 0, static_cast<cudaStream_t>(stream), h->dev, out_size, ids, logp);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("beam_finalize_kernel");
 }
 
 extern "C" int cap_log_softmax(const float* logits, int ld, float* out, int ldo, int rows, int V, cap_stream_t stream) {
     CAP_REQUIRE(logits && out && rows > 0 && V > 0 && ld >= V && ldo >= V, "cap_log_softmax: bad arguments");
-    log_softmax_rows_kernel<<<rows, ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, out, ldo, V);
+    CAP_LAUNCH((log_softmax_rows_kernel), rows, ROW_THREADS, 0, static_cast<cudaStream_t>(stream), logits, ld, out, ldo, V);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("log_softmax_rows_kernel");
 }

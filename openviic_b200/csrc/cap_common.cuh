@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/openviic_cap.h"
 
@@ -39,6 +40,34 @@ int cap_set_error(int code, const char* fmt, ...);
         if (_rc != CAP_OK) return _rc;                                                         \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic Dependent Launch: every kernel is launched with the programmatic-stream-serialization
+// attribute, signals `launch_dependents` on entry and blocks in `griddepcontrol.wait` before it touches
+// memory a predecessor may still be writing.  The next kernel's launch latency and prologue (barrier
+// init, TMEM allocation, descriptor prefetch, bias staging) thereby overlap the current kernel's tail
+// -- in eager streams and inside captured CUDA graphs alike.  OPENVIIC_PDL=0 turns the attribute off
+// (the device instructions are then no-ops).
+// ---------------------------------------------------------------------------------------------
+bool cap_pdl_enabled();
+
+template <typename Kernel, typename... Args>
+inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cap_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#define CAP_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    cap_launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+
 static inline int cap_check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cap_set_error(CAP_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
@@ -49,6 +78,14 @@ static inline int cap_check_launch(const char* what) {
 // Small device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// simple kernels: let the successor start launching, then wait for the predecessor's results
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

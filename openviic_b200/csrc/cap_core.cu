@@ -2,6 +2,7 @@
 #include "cap_common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 std::atomic<long long> g_cap_launches{0};
@@ -16,6 +17,14 @@ int cap_set_error(int code, const char* fmt, ...) {
     vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
     va_end(ap);
     return code;
+}
+
+bool cap_pdl_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("OPENVIIC_PDL");
+        return !(v && v[0] == '0');
+    }();
+    return on;
 }
 
 extern "C" int cap_abi_version(void) { return CAP_ABI_VERSION; }

@@ -168,6 +168,7 @@ template <int BLOCK_N, int TOPK>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
+    pdl_launch_dependents();  // the next kernel may start its prologue now
     constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -212,6 +213,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
     if (warp == 0) {
         if (lane == 0) {
+            pdl_wait();  // A (and only A) may still be in flight from the previous kernel
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
@@ -424,7 +426,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
         attr_smem = 200 * 1024;
     }
     dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
-    gemm_tn_bf16_tcgen05<BLOCK_N, TOPK><<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+    CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, TOPK>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_bf16_tcgen05");
 }
@@ -529,6 +531,7 @@ namespace {
 __global__ void gemm_tn_simt(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w,
                              const float* __restrict__ bias, void* out, int ldo, int out_f32, int act, int M, int N,
                              int K) {
+    pdl_prologue();
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = blockIdx.y;
     if (col >= N || row >= M) return;
@@ -549,9 +552,7 @@ extern "C" int cap_linear_simt(const void* x, int ldx, const void* w, const floa
                                int out_dtype, int act, int M, int N, int K, cap_stream_t stream) {
     CAP_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, "cap_linear_simt: bad arguments");
     dim3 grid((N + 127) / 128, M);
-    gemm_tn_simt<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(w), bias, y, ldy, out_dtype == CAP_F32, act, M, N,
-        K);
+    CAP_LAUNCH((gemm_tn_simt), grid, 128, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(w), bias, y, ldy, out_dtype == CAP_F32, act, M, N, K);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_simt");
 }

@@ -31,6 +31,7 @@ add_layernorm_kernel(const YT* __restrict__ y, int ldy, const bf16* __restrict__
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      const float* __restrict__ pos, int pos_rows, const uint8_t* __restrict__ zero_rows,
                      bf16* __restrict__ out, int ldo, int rows, int d) {
+    pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * ROWS_PER_BLOCK + warp;
     if (row >= rows) return;
@@ -102,6 +103,7 @@ template <typename FT>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 feature_mask_cast_kernel(const FT* __restrict__ feats, bf16* __restrict__ out, uint8_t* __restrict__ mask, int rows,
                          int d) {
+    pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * ROWS_PER_BLOCK + warp;
     if (row >= rows) return;
@@ -123,6 +125,7 @@ feature_mask_cast_kernel(const FT* __restrict__ feats, bf16* __restrict__ out, u
 __global__ void geometry_bias_kernel(const float* __restrict__ boxes, const float* __restrict__ w_g,
                                      const float* __restrict__ b_g, float* __restrict__ g, int B, int n, int H,
                                      int d_g, int trig) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = B * n * n;
     if (idx >= total) return;
@@ -162,6 +165,7 @@ __global__ void geometry_bias_kernel(const float* __restrict__ boxes, const floa
 __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ emb,
                                     const float* __restrict__ pos_table, int position, int pad_idx,
                                     bf16* __restrict__ out, uint8_t* __restrict__ padflag, int R, int d) {
+    pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * ROWS_PER_BLOCK + warp;
     if (row >= R) return;
@@ -182,6 +186,7 @@ __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const bf
 
 __global__ void meshed_mix_kernel(const float* __restrict__ gates, const bf16* __restrict__ c, bf16* __restrict__ out,
                                   int levels, size_t per_level, float inv_sqrt_levels) {
+    pdl_prologue();
     const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
     if (idx >= per_level) return;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -198,6 +203,7 @@ __global__ void meshed_mix_kernel(const float* __restrict__ gates, const bf16* _
 }
 
 __global__ void aoa_gate_kernel(const float* __restrict__ ig, bf16* __restrict__ out, int R, int d) {
+    pdl_prologue();
     const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
     if (idx >= static_cast<size_t>(R) * d) return;
     const size_t row = idx / d, col = idx % d;
@@ -225,13 +231,9 @@ extern "C" int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int blocks = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
     if (y_dtype == CAP_F32)
-        add_layernorm_kernel<float><<<blocks, ROWS_PER_BLOCK * 32, 0, s>>>(
-            static_cast<const float*>(y), ldy, static_cast<const bf16*>(residual), ldr, gamma, beta, eps, pos,
-            pos_rows, zero_rows, static_cast<bf16*>(out), ldo, rows, d);
+        CAP_LAUNCH((add_layernorm_kernel<float>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const float*>(y), ldy, static_cast<const bf16*>(residual), ldr, gamma, beta, eps, pos, pos_rows, zero_rows, static_cast<bf16*>(out), ldo, rows, d);
     else
-        add_layernorm_kernel<bf16><<<blocks, ROWS_PER_BLOCK * 32, 0, s>>>(
-            static_cast<const bf16*>(y), ldy, static_cast<const bf16*>(residual), ldr, gamma, beta, eps, pos,
-            pos_rows, zero_rows, static_cast<bf16*>(out), ldo, rows, d);
+        CAP_LAUNCH((add_layernorm_kernel<bf16>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const bf16*>(y), ldy, static_cast<const bf16*>(residual), ldr, gamma, beta, eps, pos, pos_rows, zero_rows, static_cast<bf16*>(out), ldo, rows, d);
     count_launch();
     return cap_check_launch("add_layernorm_kernel");
 }
@@ -243,11 +245,9 @@ extern "C" int cap_feature_mask_cast(const void* feats, int feat_dtype, void* ou
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int blocks = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
     if (feat_dtype == CAP_F32)
-        feature_mask_cast_kernel<float><<<blocks, ROWS_PER_BLOCK * 32, 0, s>>>(
-            static_cast<const float*>(feats), static_cast<bf16*>(out_bf16), mask, rows, d_feature);
+        CAP_LAUNCH((feature_mask_cast_kernel<float>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const float*>(feats), static_cast<bf16*>(out_bf16), mask, rows, d_feature);
     else
-        feature_mask_cast_kernel<bf16><<<blocks, ROWS_PER_BLOCK * 32, 0, s>>>(
-            static_cast<const bf16*>(feats), static_cast<bf16*>(out_bf16), mask, rows, d_feature);
+        CAP_LAUNCH((feature_mask_cast_kernel<bf16>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const bf16*>(feats), static_cast<bf16*>(out_bf16), mask, rows, d_feature);
     count_launch();
     return cap_check_launch("feature_mask_cast_kernel");
 }
@@ -259,8 +259,7 @@ extern "C" int cap_geometry_bias(const float* boxes, const float* w_g, const flo
     CAP_REQUIRE(trig ? (d_g % 8 == 0 && d_g > 0) : d_g == 4, "cap_geometry_bias: d_g=%d invalid for trig=%d", d_g,
                 trig);
     const int total = B * n * n;
-    geometry_bias_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(boxes, w_g, b_g, g, B, n,
-                                                                                             H, d_g, trig);
+    CAP_LAUNCH((geometry_bias_kernel), (total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), boxes, w_g, b_g, g, B, n, H, d_g, trig);
     count_launch();
     return cap_check_launch("geometry_bias_kernel");
 }
@@ -270,10 +269,7 @@ extern "C" int cap_embed_tokens(const int32_t* tokens, const void* word_emb_bf16
                                 cap_stream_t stream) {
     CAP_REQUIRE(tokens && word_emb_bf16 && pos_table && out, "cap_embed_tokens: null pointer");
     CAP_REQUIRE(R > 0 && d % 8 == 0, "cap_embed_tokens: bad shape");
-    embed_tokens_kernel<<<(R + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0,
-                          static_cast<cudaStream_t>(stream)>>>(tokens, static_cast<const bf16*>(word_emb_bf16),
-                                                               pos_table, position, pad_idx, static_cast<bf16*>(out),
-                                                               padflag_out, R, d);
+    CAP_LAUNCH((embed_tokens_kernel), (R + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream), tokens, static_cast<const bf16*>(word_emb_bf16), pos_table, position, pad_idx, static_cast<bf16*>(out), padflag_out, R, d);
     count_launch();
     return cap_check_launch("embed_tokens_kernel");
 }
@@ -284,9 +280,7 @@ extern "C" int cap_meshed_mix(const float* gates, const void* c, void* out, int 
     const size_t per_level = static_cast<size_t>(R) * d;
     const int threads = 256;
     const int blocks = static_cast<int>((per_level / 8 + threads - 1) / threads);
-    meshed_mix_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        gates, static_cast<const bf16*>(c), static_cast<bf16*>(out), levels, per_level,
-        1.f / sqrtf(static_cast<float>(levels)));
+    CAP_LAUNCH((meshed_mix_kernel), blocks, threads, 0, static_cast<cudaStream_t>(stream), gates, static_cast<const bf16*>(c), static_cast<bf16*>(out), levels, per_level, 1.f / sqrtf(static_cast<float>(levels)));
     count_launch();
     return cap_check_launch("meshed_mix_kernel");
 }
@@ -296,7 +290,7 @@ extern "C" int cap_aoa_gate(const float* ig, void* out, int R, int d, cap_stream
     const size_t total = static_cast<size_t>(R) * d;
     const int threads = 256;
     const int blocks = static_cast<int>((total / 8 + threads - 1) / threads);
-    aoa_gate_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(ig, static_cast<bf16*>(out), R, d);
+    CAP_LAUNCH((aoa_gate_kernel), blocks, threads, 0, static_cast<cudaStream_t>(stream), ig, static_cast<bf16*>(out), R, d);
     count_launch();
     return cap_check_launch("aoa_gate_kernel");
 }
