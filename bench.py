@@ -57,7 +57,8 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons every 50 ms from the first warm-up step to the end of the
+    e2e pass (the GPU is under the same load throughout; the device-timed region alone can be < 0.2 s)."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -69,7 +70,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -226,6 +227,16 @@ def run_gpu_arm(args):
     cfg, vocab, model, weights = build_model(args.workload, device)
     eng = model.engine(batch, n, BEAM)
     levels = eng.desc.n_enc_levels
+    # Independent batches are pipelined over `streams` engines/streams: at batch 256 every decode kernel is a
+    # single partial wave and latency-bound, so kernels of different batches co-run on the idle SMs.
+    from openviic_b200 import CaptionEngine
+    n_streams = max(1, args.streams)
+    engines = [eng]
+    for _ in range(n_streams - 1):
+        extra = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device)
+        extra.reserve(batch, n, BEAM)
+        engines.append(extra)
+    streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
     needs_boxes = synthetic.needs_boxes(cfg.MODEL)
 
     # Rotating input sets: 4 x (B,n,2048) bf16 = 4 x 51 MB > 126 MB L2, so no step finds its input cached
@@ -243,9 +254,21 @@ def run_gpu_arm(args):
         boxes_dev.append(None if bx is None else bx.to(device))
 
     def step(i):
-        eng.encode(feats_dev[i % n_sets], boxes_dev[i % n_sets])
-        ids, logp = eng.beam_search(out_size=1, use_graph=not args.no_graph)
-        return parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world) if world > 1 else (ids, logp)
+        k = i % n_streams
+        with torch.cuda.stream(streams[k]):
+            engines[k].encode(feats_dev[i % n_sets], boxes_dev[i % n_sets])
+            ids, logp = engines[k].beam_search(out_size=1, use_graph=not args.no_graph)
+            if world > 1:
+                return parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world)
+            return ids, logp
+
+    def fork():   # side streams start after everything already queued on the timing stream
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream())
+
+    def join():   # the timing stream waits for every side stream
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
 
     def barrier():
         torch.cuda.synchronize()
@@ -263,16 +286,23 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     launches_per_step = cabi.launch_count() - c0
 
-    for i in range(max(3, args.warmup)):
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    for k in range(1, n_streams):   # warm every engine eagerly once (sets kernel attributes before capture)
+        with torch.cuda.stream(streams[k]):
+            engines[k].encode(feats_dev[0], boxes_dev[0])
+            engines[k].beam_search(out_size=1, use_graph=False)
+    for i in range(max(3, args.warmup) * n_streams):
         step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        e0.record()
-        for i in range(args.steps):
-            out = step(i)
-        e1.record()
-        barrier()
+    e0.record()
+    fork()
+    for i in range(args.steps):
+        out = step(i)
+    join()
+    e1.record()
+    barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -280,18 +310,29 @@ def run_gpu_arm(args):
     value = batch * world * args.steps / (total_ms / 1e3)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + compute + D2H + sync per step) ----
-    out_host = (torch.empty((batch, 1, MAX_LEN), dtype=torch.int64).pin_memory(),
-                torch.empty((batch, 1, MAX_LEN), dtype=torch.float32).pin_memory())
-    for i in range(3):
-        eng.caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, out_host)
+    outs_host = [(torch.empty((batch, 1, MAX_LEN), dtype=torch.int64).pin_memory(),
+                  torch.empty((batch, 1, MAX_LEN), dtype=torch.float32).pin_memory()) for _ in range(n_streams)]
+
+    def e2e_step(i):
+        k = i % n_streams
+        with torch.cuda.stream(streams[k]):
+            engines[k].caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, outs_host[k],
+                                    sync=False)
+            if world > 1:
+                streams[k].synchronize()
+                parallel.gather_captions(outs_host[k][0].squeeze(1).to(device), outs_host[k][1].squeeze(1).to(device),
+                                         batch * world)
+
+    for i in range(3 * n_streams):
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        eng.caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, out_host)
-        if world > 1:
-            parallel.gather_captions(out_host[0].squeeze(1).to(device), out_host[1].squeeze(1).to(device), batch * world)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=device)
+        e2e_step(i)
+    barrier()   # every stream drained: all ids / log-probs are in host memory
+    e2e_elapsed = time.perf_counter() - t0
+    clocks.__exit__(None, None, None)
+    e2e_s = torch.tensor([e2e_elapsed], device=device)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = batch * world * args.steps / float(e2e_s.item())
@@ -324,7 +365,8 @@ def run_gpu_arm(args):
         "config": {"workload": f"{yaml_name}: {n} visual tokens x 2048, beam {BEAM}, len {MAX_LEN}, V {VOCAB}, "
                                f"batch {batch}/GPU", "global_batch": batch * world, "parallelism": f"dp{world}",
                    "l2": f"{n_sets} rotating input batches ({n_sets} x {h2d / 1e6:.0f} MB > 126 MB L2); step working set > L2",
-                   "cuda_graph": not args.no_graph, "weights": "synthetic seed 1234 (openviic_b200/synthetic.py)"},
+                   "cuda_graph": not args.no_graph, "streams": n_streams,
+                   "pipelining": f"{n_streams} independent batches in flight on {n_streams} streams/engines", "weights": "synthetic seed 1234 (openviic_b200/synthetic.py)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_features": "bf16 pinned", "api": "cap_engine_caption_host"},
         "gpu_launches": int(launches_per_step * args.steps),
@@ -338,15 +380,16 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=80)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="standard_grid", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="independent batches kept in flight (engines/streams)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16)
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

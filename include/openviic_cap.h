@@ -232,6 +232,13 @@ int cap_engine_beam_search(cap_engine* e, int out_size, int64_t* ids, float* log
 int cap_engine_caption_host(cap_engine* e, const void* feats_host, int feat_dtype,
                             const float* boxes_host, int B, int n, int out_size, int64_t* ids_host,
                             float* logp_host, int use_graph, cap_stream_t stream);
+/* Same, without the final stream synchronisation: several engines on several streams can then keep
+ * H2D, compute and D2H of different batches in flight at once; the caller synchronises the stream
+ * before reading ids_host / logp_host or reusing feats_host. */
+int cap_engine_caption_host_async(cap_engine* e, const void* feats_host, int feat_dtype,
+                                  const float* boxes_host, int B, int n, int out_size,
+                                  int64_t* ids_host, float* logp_host, int use_graph,
+                                  cap_stream_t stream);
 /* Debug / parity views: */
 const void* cap_engine_encoder_output(cap_engine* e);   /* bf16 [levels][B*n][d_model] */
 const uint8_t* cap_engine_encoder_mask(cap_engine* e);  /* uint8 [B*n]                 */

@@ -650,9 +650,22 @@ extern "C" int cap_engine_beam_search(cap_engine* e, int out_size, int64_t* ids,
     return CAP_OK;
 }
 
+extern "C" int cap_engine_caption_host_async(cap_engine* e, const void* feats_host, int feat_dtype,
+                                             const float* boxes_host, int B, int n, int out_size, int64_t* ids_host,
+                                             float* logp_host, int use_graph, cap_stream_t stream);
+
 extern "C" int cap_engine_caption_host(cap_engine* e, const void* feats_host, int feat_dtype, const float* boxes_host,
                                        int B, int n, int out_size, int64_t* ids_host, float* logp_host, int use_graph,
                                        cap_stream_t stream) {
+    CAP_PROPAGATE(cap_engine_caption_host_async(e, feats_host, feat_dtype, boxes_host, B, n, out_size, ids_host,
+                                                logp_host, use_graph, stream));
+    CAP_CHECK_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return CAP_OK;
+}
+
+extern "C" int cap_engine_caption_host_async(cap_engine* e, const void* feats_host, int feat_dtype,
+                                             const float* boxes_host, int B, int n, int out_size, int64_t* ids_host,
+                                             float* logp_host, int use_graph, cap_stream_t stream) {
     CAP_REQUIRE(e && e->max_batch > 0, "cap_engine_caption_host: reserve the engine first");
     CAP_REQUIRE(feats_host && ids_host && logp_host, "cap_engine_caption_host: null pointer");
     CAP_REQUIRE(B > 0 && B <= e->max_batch && n > 0 && n <= e->n_tokens, "cap_engine_caption_host: bad batch shape");
@@ -671,7 +684,6 @@ extern "C" int cap_engine_caption_host(cap_engine* e, const void* feats_host, in
     const size_t count = static_cast<size_t>(B) * out_size * m.max_len;
     CAP_CHECK_CUDA(cudaMemcpyAsync(ids_host, e->out_ids, count * 8, cudaMemcpyDeviceToHost, s));
     CAP_CHECK_CUDA(cudaMemcpyAsync(logp_host, e->out_logp, count * 4, cudaMemcpyDeviceToHost, s));
-    CAP_CHECK_CUDA(cudaStreamSynchronize(s));
     return CAP_OK;
 }
 

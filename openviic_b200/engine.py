@@ -124,15 +124,17 @@ class CaptionEngine:
         return ids, logp
 
     def caption_host(self, feats_host: torch.Tensor, boxes_host: Optional[torch.Tensor] = None, out_size: int = 1,
-                     use_graph: bool = True, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
-        """End to end from HOST tensors (pin them for full PCIe speed) to HOST ids / log-probs."""
+                     use_graph: bool = True, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                     sync: bool = True):
+        """End to end from HOST tensors (pin them for full PCIe speed) to HOST ids / log-probs.
+        ``sync=False`` returns right after enqueueing (synchronise the current stream before reading)."""
         b, n, _ = feats_host.shape
         if out is None:
             out = (torch.empty((b, out_size, self.max_len), dtype=torch.int64).pin_memory(),
                    torch.empty((b, out_size, self.max_len), dtype=torch.float32).pin_memory())
         ids, logp = out
         with torch.cuda.device(self.device):
-            cabi.call("cap_engine_caption_host", self._h, feats_host.data_ptr(),
+            cabi.call("cap_engine_caption_host" if sync else "cap_engine_caption_host_async", self._h, feats_host.data_ptr(),
                       cabi.CAP_F32 if feats_host.dtype == torch.float32 else cabi.CAP_BF16,
                       None if boxes_host is None else boxes_host.data_ptr(), b, n, out_size, ids.data_ptr(),
                       logp.data_ptr(), 1 if use_graph else 0, self._stream())

@@ -178,6 +178,33 @@ def test_module_level_path_matches_engine(case_run):
     assert diff[live].max() < TOL_LOGP and diff[live].mean() < TOL_LOGP_MEAN
 
 
+def test_concurrent_engines_on_separate_streams_match_single_stream(device):
+    """bench.py pipelines independent batches over several engines/streams: results must not change."""
+    from openviic_b200 import CaptionEngine
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_grid", device)
+    b, n, beam = case["batch"], case["n"], case["beam"]
+    base = model.engine(b, n, beam)
+    base.encode(feats.to(device))
+    ref_ids, ref_lp = base.beam_search(out_size=beam, use_graph=False)
+    torch.cuda.synchronize()
+    engines = [CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device) for _ in range(3)]
+    streams = [torch.cuda.Stream(device=device) for _ in engines]
+    host = feats.to(torch.bfloat16).pin_memory()
+    outs = []
+    for eng in engines:
+        eng.reserve(b, n, beam)
+    for rounds in range(3):                                   # eager, then graph capture, then replay
+        outs = []
+        for eng, st in zip(engines, streams):
+            with torch.cuda.stream(st):
+                outs.append(eng.caption_host(host, None, out_size=beam, use_graph=rounds > 0, sync=False))
+        torch.cuda.synchronize()
+        for ids, lp in outs:
+            assert torch.equal(ids, ref_ids.cpu()) and torch.equal(lp, ref_lp.cpu())
+    for eng in engines:
+        eng.close()
+
+
 def test_engine_rejects_bad_calls(device):
     case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_grid", device)
     eng = model.engine(4, 49, 5)
