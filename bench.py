@@ -32,6 +32,7 @@ import torch
 
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
 
 METRIC = "captions_per_sec_beam5_len20"
 UNIT = "captions/s"
@@ -313,15 +314,25 @@ def run_gpu_arm(args):
     outs_host = [(torch.empty((batch, 1, MAX_LEN), dtype=torch.int64).pin_memory(),
                   torch.empty((batch, 1, MAX_LEN), dtype=torch.float32).pin_memory()) for _ in range(n_streams)]
 
+    gathered_host = [(torch.empty((batch * world, MAX_LEN), dtype=torch.int64).pin_memory(),
+                      torch.empty((batch * world, MAX_LEN), dtype=torch.float32).pin_memory()) for _ in range(n_streams)]
+
     def e2e_step(i):
         k = i % n_streams
         with torch.cuda.stream(streams[k]):
-            engines[k].caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, outs_host[k],
-                                    sync=False)
-            if world > 1:
-                streams[k].synchronize()
-                parallel.gather_captions(outs_host[k][0].squeeze(1).to(device), outs_host[k][1].squeeze(1).to(device),
-                                         batch * world)
+            if world == 1:   # the C-ABI host entry point: H2D + path + D2H enqueued by one call
+                engines[k].caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph,
+                                        outs_host[k], sync=False)
+                return
+            # N > 1: same copies, plus the all-gather of ids between the search and the D2H copy; nothing
+            # blocks the host, so the ranks' batches stay pipelined
+            f = feats_host[i % n_sets].to(device, non_blocking=True)
+            bx = boxes_host[i % n_sets].to(device, non_blocking=True) if needs_boxes else None
+            engines[k].encode(f, bx)
+            ids, logp = engines[k].beam_search(out_size=1, use_graph=not args.no_graph)
+            all_ids, all_lp = parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world)
+            gathered_host[k][0].copy_(all_ids, non_blocking=True)
+            gathered_host[k][1].copy_(all_lp, non_blocking=True)
 
     for i in range(3 * n_streams):
         e2e_step(i)
@@ -368,7 +379,8 @@ def run_gpu_arm(args):
                    "cuda_graph": not args.no_graph, "streams": n_streams,
                    "pipelining": f"{n_streams} independent batches in flight on {n_streams} streams/engines", "weights": "synthetic seed 1234 (openviic_b200/synthetic.py)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "host_features": "bf16 pinned", "api": "cap_engine_caption_host"},
+                "host_features": "bf16 pinned",
+                "api": "cap_engine_caption_host_async" if world == 1 else "pinned H2D + engine + NCCL all-gather + D2H"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks.summary(),

@@ -62,13 +62,15 @@ int cap_linear_simt(const void* x, int ldx, const void* w, const float* bias, vo
                     int out_dtype, int act, int M, int N, int K, cap_stream_t stream);
 
 /* out = LayerNorm(residual + y) * gamma + beta [+ pos[row % pos_rows]] ; rows with
- * zero_rows[row] != 0 are written as 0.  y is fp32 or bf16 (y_dtype); residual bf16 or NULL.
+ * zero_rows[row] != 0 are written as 0.  y and residual are fp32 or bf16 (y_dtype / res_dtype; residual
+ * may be NULL).  Two outputs, either may be NULL: `out` bf16 (the next GEMM's operand) and `out_f32`
+ * (the next residual) -- the residual stream is fp32 end to end, as in the reference.
  * Replaces models/modules/attentions.py:308-309, positionwise_feed_forward.py:26,
  * encoders.py:20,36 (LN(x)+pos and the padded-row zeroing), decoders.py:26. */
-int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void* residual, int ldr,
-                      const float* gamma, const float* beta, float eps, const float* pos,
-                      int pos_rows, const uint8_t* zero_rows, void* out, int ldo, int rows, int d,
-                      cap_stream_t stream);
+int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void* residual, int res_dtype,
+                      int ldr, const float* gamma, const float* beta, float eps, const float* pos,
+                      int pos_rows, const uint8_t* zero_rows, void* out, int ldo, float* out_f32,
+                      int ldo32, int rows, int d, cap_stream_t stream);
 
 /* Visual-token padding mask + cast: mask[row] = (sum_k feats[row,k] == 0) (fp32 sum), and
  * out[row,:] = bf16(feats[row,:]).  feats fp32 or bf16.
@@ -127,16 +129,16 @@ int cap_decode_cross_attention(const void* q, int ldq, const void* kv, const uin
 /* x[r,:] = word_emb[token[r],:] + pos_table[position,:] (bf16 out); padflag_out[r] = token==pad.
  * Replaces models/modules/decoders.py:105-112 (stateful: position = t+1 for every row). */
 int cap_embed_tokens(const int32_t* tokens, const void* word_emb_bf16, const float* pos_table,
-                     int position, int pad_idx, void* out, uint8_t* padflag_out, int R, int d,
-                     cap_stream_t stream);
+                     int position, int pad_idx, void* out, float* out_f32, uint8_t* padflag_out, int R,
+                     int d, cap_stream_t stream);
 
 /* Meshed mix: out = sum_i sigmoid(a_i) * c_i / sqrt(levels)  (bf16), a_i fp32 [levels][R][d]
- * pre-activation gates, c_i bf16 [levels][R][d].  Replaces models/modules/decoders.py:60-67. */
-int cap_meshed_mix(const float* gates, const void* c, void* out, int levels, int R, int d,
-                   cap_stream_t stream);
+ * pre-activation gates, c_i bf16 or fp32 [levels][R][d]; bf16 and/or fp32 output.  Replaces models/modules/decoders.py:60-67. */
+int cap_meshed_mix(const float* gates, const void* c, int c_dtype, void* out, float* out_f32,
+                   int levels, int R, int d, cap_stream_t stream);
 
 /* AoA gate: out = info * sigmoid(gate); ig fp32 [R][2*d] = (info | gate).  attentions.py:311-315 */
-int cap_aoa_gate(const float* ig, void* out, int R, int d, cap_stream_t stream);
+int cap_aoa_gate(const float* ig, void* out, float* out_f32, int R, int d, cap_stream_t stream);
 
 /* out[r,:] = log_softmax(logits[r,:]) over V columns, fp32 (models/modules/decoders.py:123). */
 int cap_log_softmax(const float* logits, int ld, float* out, int ldo, int rows, int V,

@@ -52,15 +52,15 @@ SIGNATURES = {
     "cap_debug_gemm_trace": (_i, [_vp]),
     "cap_linear": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_linear_simt": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "cap_add_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "cap_add_layernorm": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "cap_feature_mask_cast": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "cap_geometry_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "cap_attention": (_i, [C.POINTER(AttentionArgs), _vp]),
     "cap_decode_self_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "cap_decode_cross_attention": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
-    "cap_embed_tokens": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
-    "cap_meshed_mix": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    "cap_aoa_gate": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cap_embed_tokens": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "cap_meshed_mix": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "cap_aoa_gate": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "cap_log_softmax": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "cap_beam_create": (_i, [_i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "cap_beam_destroy": (_i, [_vp]),

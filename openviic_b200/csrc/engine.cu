@@ -99,6 +99,8 @@ struct cap_engine {
     bf16* buf_qkv = nullptr;       // encoder [rows_enc][3*hd]
     bf16* buf_c = nullptr;         // decoder [levels][R][d]
     bf16* buf_mix = nullptr;       // decoder [R][d] meshed mix
+    // fp32 twins of the residual stream (x -> a -> c -> x): only GEMM operands are rounded to bf16
+    float *res_x = nullptr, *res_a = nullptr, *res_c = nullptr, *res_mix = nullptr;
     float* buf_y32 = nullptr;
     float* logits = nullptr;
     int ld_logits = 0;
@@ -239,20 +241,21 @@ int run_linear(const bf16* x, int ldx, const Linear& l, void* y, int ldy, int ou
     return cap_linear(x, ldx, l.w, l.b, y, ldy, out_dtype, act, M, l.out, l.in, s);
 }
 
-int run_ln(const float* y32, int ldy, const bf16* res, int ldr, const Norm& n, const float* pos, int pos_rows,
-           const uint8_t* zero_rows, bf16* out, int ldo, int rows, int d, cudaStream_t s) {
-    return cap_add_layernorm(y32, CAP_F32, ldy, res, ldr, n.g, n.b, 1e-5f, pos, pos_rows, zero_rows, out, ldo, rows, d,
-                             s);
+// LN(res32 + y32): bf16 copy for the next GEMM, fp32 copy for the next residual (both dense, ld = d)
+int run_ln(const float* y32, const float* res32, const Norm& n, const float* pos, int pos_rows,
+           const uint8_t* zero_rows, bf16* out16, float* out32, int rows, int d, cudaStream_t s) {
+    return cap_add_layernorm(y32, CAP_F32, d, res32, CAP_F32, d, n.g, n.b, 1e-5f, pos, pos_rows, zero_rows, out16, d,
+                             out32, d, rows, d, s);
 }
 
 // AoA: out = Linear_i([q, a]) * sigmoid(Linear_g([q, a]))   (attentions.py:311-315)
-int run_aoa(cap_engine* e, const AttentionW& w, const bf16* queries, const bf16* att_out, bf16* out, int rows,
-            cudaStream_t s) {
+int run_aoa(cap_engine* e, const AttentionW& w, const bf16* queries, const bf16* att_out, bf16* out, float* out32,
+            int rows, cudaStream_t s) {
     const int d = e->desc.d_model;
     CAP_CHECK_CUDA(cudaMemcpy2DAsync(e->buf_cat, 2 * d * 2, queries, d * 2, d * 2, rows, cudaMemcpyDeviceToDevice, s));
     CAP_CHECK_CUDA(cudaMemcpy2DAsync(e->buf_cat + d, 2 * d * 2, att_out, d * 2, d * 2, rows, cudaMemcpyDeviceToDevice, s));
     CAP_PROPAGATE(run_linear(e->buf_cat, 2 * d, w.aoa, e->buf_y32, 2 * d, CAP_F32, CAP_ACT_NONE, rows, s));
-    return cap_aoa_gate(e->buf_y32, out, rows, d, s);
+    return cap_aoa_gate(e->buf_y32, out, out32, rows, d, s);
 }
 
 }  // namespace
@@ -412,6 +415,10 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->buf_qkv, rows_enc * 3 * hd));
     CAP_PROPAGATE(dev_alloc(e, &e->buf_c, R * lv * d));
     CAP_PROPAGATE(dev_alloc(e, &e->buf_mix, R * d));
+    CAP_PROPAGATE(dev_alloc(e, &e->res_x, rows_max * d));
+    CAP_PROPAGATE(dev_alloc(e, &e->res_a, rows_max * d));
+    CAP_PROPAGATE(dev_alloc(e, &e->res_c, R * lv * d));
+    CAP_PROPAGATE(dev_alloc(e, &e->res_mix, R * d));
     CAP_PROPAGATE(dev_alloc(e, &e->buf_y32, rows_max * static_cast<size_t>(std::max(2 * d, hd))));
     e->ld_logits = (m.vocab + 7) / 8 * 8;
     CAP_PROPAGATE(dev_alloc(e, &e->logits, R * e->ld_logits));
@@ -444,7 +451,7 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
     // V1: padding mask from the RAW features + cast; projection; E0: LN(x) + pos
     CAP_PROPAGATE(cap_feature_mask_cast(feats, feat_dtype, e->feat_bf16, e->enc_mask, rows, m.d_feature, s));
     CAP_PROPAGATE(run_linear(e->feat_bf16, m.d_feature, e->vis_proj, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
-    CAP_PROPAGATE(run_ln(e->buf_y32, d, nullptr, 0, e->enc_ln, e->vis_pos, n, nullptr, e->buf_x, d, rows, d, s));
+    CAP_PROPAGATE(run_ln(e->buf_y32, nullptr, e->enc_ln, e->vis_pos, n, nullptr, e->buf_x, e->res_x, rows, d, s));
     if (m.encoder_kind == CAP_ENC_GEOMETRIC)
         CAP_PROPAGATE(cap_geometry_bias(boxes, e->geo_w, e->geo_b, e->geometry, B, n, m.heads, e->d_g,
                                         m.trig_geometry, s));
@@ -476,11 +483,11 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
         a.scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
         CAP_PROPAGATE(cap_attention(&a, s));
         CAP_PROPAGATE(run_linear(e->buf_att, hd, L.att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, d, x, d, L.att.ln, nullptr, 0, nullptr, e->buf_a, d, rows, d, s));
-        if (m.aoa_enc) CAP_PROPAGATE(run_aoa(e, L.att, x, e->buf_a, e->buf_a, rows, s));
+        CAP_PROPAGATE(run_ln(e->buf_y32, e->res_x, L.att.ln, nullptr, 0, nullptr, e->buf_a, e->res_a, rows, d, s));
+        if (m.aoa_enc) CAP_PROPAGATE(run_aoa(e, L.att, x, e->buf_a, e->buf_a, e->res_a, rows, s));
         CAP_PROPAGATE(run_linear(e->buf_a, d, L.ffn.fc1, e->buf_h, m.d_ff, CAP_BF16, CAP_ACT_RELU, rows, s));
         CAP_PROPAGATE(run_linear(e->buf_h, m.d_ff, L.ffn.fc2, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, d, e->buf_a, d, L.ffn.ln, nullptr, 0, e->enc_mask, level_out, d, rows, d, s));
+        CAP_PROPAGATE(run_ln(e->buf_y32, e->res_a, L.ffn.ln, nullptr, 0, e->enc_mask, level_out, e->res_x, rows, d, s));
         x = level_out;
     }
     // Cross-attention K/V, once per image per decoder layer (and per level for the meshed decoder).
@@ -543,7 +550,7 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
 
     // D3: x = Emb[token] + pos[t+1]   (running_seq is t+1 for every row, decoders.py:107-109)
     CAP_PROPAGATE(cap_embed_tokens(cap_beam_tokens(e->beam_state), e->word_emb, e->word_pos, t + 1, m.pad_idx, e->buf_x,
-                                   pad_t, R, d, s));
+                                   e->res_x, pad_t, R, d, s));
     bf16* x = e->buf_x;
     for (int l = 0; l < m.dec_layers; ++l) {
         const DecoderLayerW& L = e->dec[l];
@@ -554,8 +561,8 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
         CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd,
                                                 t, R, m.heads, scale, s));
         CAP_PROPAGATE(run_linear(e->buf_att, hd, L.self_att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, R, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, d, x, d, L.self_att.ln, nullptr, 0, nullptr, e->buf_a, d, R, d, s));
-        if (m.aoa_dec_self) CAP_PROPAGATE(run_aoa(e, L.self_att, x, e->buf_a, e->buf_a, R, s));
+        CAP_PROPAGATE(run_ln(e->buf_y32, e->res_x, L.self_att.ln, nullptr, 0, nullptr, e->buf_a, e->res_a, R, d, s));
+        if (m.aoa_dec_self) CAP_PROPAGATE(run_aoa(e, L.self_att, x, e->buf_a, e->buf_a, e->res_a, R, s));
         const bf16* sa = e->buf_a;
         // A5 (cross): one q projection shared by every encoder level (same enc_attn weights)
         CAP_PROPAGATE(run_linear(sa, d, L.cross_att.q, e->buf_q, hd, CAP_BF16, CAP_ACT_NONE, R, s));
@@ -567,11 +574,13 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
         CAP_PROPAGATE(run_linear(e->buf_att, hd, L.cross_att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, lv * R, s));
         for (int i = 0; i < lv; ++i) {
             bf16* ci = e->buf_c + static_cast<size_t>(i) * R * d;
-            CAP_PROPAGATE(run_ln(e->buf_y32 + static_cast<size_t>(i) * R * d, d, sa, d, L.cross_att.ln, nullptr, 0, nullptr,
-                                 ci, d, R, d, s));
-            if (m.aoa_dec_cross) CAP_PROPAGATE(run_aoa(e, L.cross_att, sa, ci, ci, R, s));
+            float* ci32 = e->res_c + static_cast<size_t>(i) * R * d;
+            CAP_PROPAGATE(run_ln(e->buf_y32 + static_cast<size_t>(i) * R * d, e->res_a, L.cross_att.ln, nullptr, 0, nullptr,
+                                 ci, ci32, R, d, s));
+            if (m.aoa_dec_cross) CAP_PROPAGATE(run_aoa(e, L.cross_att, sa, ci, ci, ci32, R, s));
         }
         const bf16* c = e->buf_c;
+        const float* c32 = e->res_c;
         if (m.decoder_kind == CAP_DEC_MESHED) {
             // D2: alpha_i = sigmoid(W_i [s ; c_i]),  c = sum_i alpha_i * c_i / sqrt(levels)
             float* gates = e->buf_y32;
@@ -582,13 +591,14 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
                 CAP_PROPAGATE(run_linear(e->buf_cat, 2 * d, L.alphas[i], gates + static_cast<size_t>(i) * R * d, d, CAP_F32,
                                          CAP_ACT_NONE, R, s));
             }
-            CAP_PROPAGATE(cap_meshed_mix(gates, e->buf_c, e->buf_mix, lv, R, d, s));
+            CAP_PROPAGATE(cap_meshed_mix(gates, e->res_c, CAP_F32, e->buf_mix, e->res_mix, lv, R, d, s));
             c = e->buf_mix;
+            c32 = e->res_mix;
         }
         // F1 + zero rows whose input token was <pad> (decoders.py:26)
         CAP_PROPAGATE(run_linear(c, d, L.ffn.fc1, e->buf_h, m.d_ff, CAP_BF16, CAP_ACT_RELU, R, s));
         CAP_PROPAGATE(run_linear(e->buf_h, m.d_ff, L.ffn.fc2, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, R, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, d, c, d, L.ffn.ln, nullptr, 0, pad_t, e->buf_x, d, R, d, s));
+        CAP_PROPAGATE(run_ln(e->buf_y32, c32, L.ffn.ln, nullptr, 0, pad_t, e->buf_x, e->res_x, R, d, s));
         x = e->buf_x;
     }
     *hidden = x;

@@ -25,29 +25,39 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
 }
 
 // out = LN(residual + y) * gamma + beta (+ pos) ; optionally zero whole rows.
-template <typename YT>
+__device__ __forceinline__ void store8(bf16* p, const float* f) { *reinterpret_cast<bf16x8*>(p) = pack8(f); }
+__device__ __forceinline__ void store8(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// Outputs: a bf16 copy (the next GEMM's A operand) and/or an fp32 copy (the next residual): the
+// residual stream stays fp32 end to end, only GEMM inputs are rounded to bf16.
+template <typename YT, typename RT>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
-add_layernorm_kernel(const YT* __restrict__ y, int ldy, const bf16* __restrict__ res, int ldr,
+add_layernorm_kernel(const YT* __restrict__ y, int ldy, const RT* __restrict__ res, int ldr,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      const float* __restrict__ pos, int pos_rows, const uint8_t* __restrict__ zero_rows,
-                     bf16* __restrict__ out, int ldo, int rows, int d) {
+                     bf16* __restrict__ out, int ldo, float* __restrict__ out32, int ldo32, int rows, int d) {
     pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * ROWS_PER_BLOCK + warp;
     if (row >= rows) return;
     const int nchunks = d >> 3;
-    bf16* orow = out + static_cast<size_t>(row) * ldo;
+    bf16* orow = out ? out + static_cast<size_t>(row) * ldo : nullptr;
+    float* orow32 = out32 ? out32 + static_cast<size_t>(row) * ldo32 : nullptr;
     if (zero_rows != nullptr && zero_rows[row]) {
-        bf16x8 z;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
-        for (int c = lane; c < nchunks; c += 32) *reinterpret_cast<bf16x8*>(orow + c * 8) = z;
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = lane; c < nchunks; c += 32) {
+            if (orow) store8(orow + c * 8, z);
+            if (orow32) store8(orow32 + c * 8, z);
+        }
         return;
     }
     float v[LN_MAX_CHUNKS][8];
     float sum = 0.f;
     const YT* yrow = y + static_cast<size_t>(row) * ldy;
-    const bf16* rrow = res ? res + static_cast<size_t>(row) * ldr : nullptr;
+    const RT* rrow = res ? res + static_cast<size_t>(row) * ldr : nullptr;
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
         const int c = lane + 32 * i;
@@ -93,7 +103,8 @@ add_layernorm_kernel(const YT* __restrict__ y, int ldy, const bf16* __restrict__
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] += pp[j];
             }
-            *reinterpret_cast<bf16x8*>(orow + c * 8) = pack8(o);
+            if (orow) store8(orow + c * 8, o);
+            if (orow32) store8(orow32 + c * 8, o);
         }
     }
 }
@@ -164,7 +175,8 @@ __global__ void geometry_bias_kernel(const float* __restrict__ boxes, const floa
 // x[r] = emb[token[r]] + pos_table[position]; padflag[r] = token == pad
 __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ emb,
                                     const float* __restrict__ pos_table, int position, int pad_idx,
-                                    bf16* __restrict__ out, uint8_t* __restrict__ padflag, int R, int d) {
+                                    bf16* __restrict__ out, float* __restrict__ out32,
+                                    uint8_t* __restrict__ padflag, int R, int d) {
     pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * ROWS_PER_BLOCK + warp;
@@ -181,11 +193,13 @@ __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const bf
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] += b[j];
         *reinterpret_cast<bf16x8*>(o + c * 8) = pack8(a);
+        if (out32) store8(out32 + static_cast<size_t>(row) * d + c * 8, a);
     }
 }
 
-__global__ void meshed_mix_kernel(const float* __restrict__ gates, const bf16* __restrict__ c, bf16* __restrict__ out,
-                                  int levels, size_t per_level, float inv_sqrt_levels) {
+template <typename CT>
+__global__ void meshed_mix_kernel(const float* __restrict__ gates, const CT* __restrict__ c, bf16* __restrict__ out,
+                                  float* __restrict__ out32, int levels, size_t per_level, float inv_sqrt_levels) {
     pdl_prologue();
     const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
     if (idx >= per_level) return;
@@ -199,10 +213,12 @@ __global__ void meshed_mix_kernel(const float* __restrict__ gates, const bf16* _
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] *= inv_sqrt_levels;
-    *reinterpret_cast<bf16x8*>(out + idx) = pack8(acc);
+    if (out) store8(out + idx, acc);
+    if (out32) store8(out32 + idx, acc);
 }
 
-__global__ void aoa_gate_kernel(const float* __restrict__ ig, bf16* __restrict__ out, int R, int d) {
+__global__ void aoa_gate_kernel(const float* __restrict__ ig, bf16* __restrict__ out, float* __restrict__ out32, int R,
+                                int d) {
     pdl_prologue();
     const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
     if (idx >= static_cast<size_t>(R) * d) return;
@@ -212,28 +228,37 @@ __global__ void aoa_gate_kernel(const float* __restrict__ ig, bf16* __restrict__
     load8(ig + row * 2 * d + d + col, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = a[j] / (1.f + __expf(-b[j]));
-    *reinterpret_cast<bf16x8*>(out + idx) = pack8(a);
+    if (out) store8(out + idx, a);
+    if (out32) store8(out32 + idx, a);
 }
 
 inline void count_launch() { g_cap_launches.fetch_add(1, std::memory_order_relaxed); }
 
 }  // namespace
 
-extern "C" int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void* residual, int ldr,
+extern "C" int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void* residual, int res_dtype, int ldr,
                                  const float* gamma, const float* beta, float eps, const float* pos, int pos_rows,
-                                 const uint8_t* zero_rows, void* out, int ldo, int rows, int d, cap_stream_t stream) {
-    CAP_REQUIRE(y && gamma && beta && out, "cap_add_layernorm: null pointer");
+                                 const uint8_t* zero_rows, void* out, int ldo, float* out_f32, int ldo32, int rows,
+                                 int d, cap_stream_t stream) {
+    CAP_REQUIRE(y && gamma && beta && (out || out_f32), "cap_add_layernorm: null pointer");
     CAP_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= LN_MAX_CHUNKS * 256,
                 "cap_add_layernorm: d=%d must be a multiple of 8 and <= %d", d, LN_MAX_CHUNKS * 256);
-    CAP_REQUIRE(ldy % 8 == 0 && ldo % 8 == 0 && (!residual || ldr % 8 == 0),
+    CAP_REQUIRE(ldy % 8 == 0 && (!out || ldo % 8 == 0) && (!out_f32 || ldo32 % 4 == 0) && (!residual || ldr % 8 == 0),
                 "cap_add_layernorm: leading dimensions must be multiples of 8");
     CAP_REQUIRE(!pos || pos_rows > 0, "cap_add_layernorm: pos_rows must be positive");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int blocks = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
-    if (y_dtype == CAP_F32)
-        CAP_LAUNCH((add_layernorm_kernel<float>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const float*>(y), ldy, static_cast<const bf16*>(residual), ldr, gamma, beta, eps, pos, pos_rows, zero_rows, static_cast<bf16*>(out), ldo, rows, d);
-    else
-        CAP_LAUNCH((add_layernorm_kernel<bf16>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const bf16*>(y), ldy, static_cast<const bf16*>(residual), ldr, gamma, beta, eps, pos, pos_rows, zero_rows, static_cast<bf16*>(out), ldo, rows, d);
+    bf16* o16 = static_cast<bf16*>(out);
+#define CAP_LN(YT, RT)                                                                                              \
+    CAP_LAUNCH((add_layernorm_kernel<YT, RT>), blocks, ROWS_PER_BLOCK * 32, 0, s, static_cast<const YT*>(y), ldy,   \
+               static_cast<const RT*>(residual), ldr, gamma, beta, eps, pos, pos_rows, zero_rows, o16, ldo, out_f32, \
+               ldo32, rows, d)
+    const bool y32 = y_dtype == CAP_F32, r32 = res_dtype == CAP_F32;
+    if (y32 && r32) CAP_LN(float, float);
+    else if (y32) CAP_LN(float, bf16);
+    else if (r32) CAP_LN(bf16, float);
+    else CAP_LN(bf16, bf16);
+#undef CAP_LN
     count_launch();
     return cap_check_launch("add_layernorm_kernel");
 }
@@ -265,32 +290,40 @@ extern "C" int cap_geometry_bias(const float* boxes, const float* w_g, const flo
 }
 
 extern "C" int cap_embed_tokens(const int32_t* tokens, const void* word_emb_bf16, const float* pos_table,
-                                int position, int pad_idx, void* out, uint8_t* padflag_out, int R, int d,
-                                cap_stream_t stream) {
+                                int position, int pad_idx, void* out, float* out_f32, uint8_t* padflag_out, int R,
+                                int d, cap_stream_t stream) {
     CAP_REQUIRE(tokens && word_emb_bf16 && pos_table && out, "cap_embed_tokens: null pointer");
     CAP_REQUIRE(R > 0 && d % 8 == 0, "cap_embed_tokens: bad shape");
-    CAP_LAUNCH((embed_tokens_kernel), (R + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream), tokens, static_cast<const bf16*>(word_emb_bf16), pos_table, position, pad_idx, static_cast<bf16*>(out), padflag_out, R, d);
+    CAP_LAUNCH((embed_tokens_kernel), (R + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream), tokens, static_cast<const bf16*>(word_emb_bf16), pos_table, position, pad_idx, static_cast<bf16*>(out), out_f32, padflag_out, R, d);
     count_launch();
     return cap_check_launch("embed_tokens_kernel");
 }
 
-extern "C" int cap_meshed_mix(const float* gates, const void* c, void* out, int levels, int R, int d,
-                              cap_stream_t stream) {
-    CAP_REQUIRE(gates && c && out && levels > 0 && R > 0 && d % 8 == 0, "cap_meshed_mix: bad arguments");
+extern "C" int cap_meshed_mix(const float* gates, const void* c, int c_dtype, void* out, float* out_f32, int levels,
+                              int R, int d, cap_stream_t stream) {
+    CAP_REQUIRE(gates && c && (out || out_f32) && levels > 0 && R > 0 && d % 8 == 0, "cap_meshed_mix: bad arguments");
     const size_t per_level = static_cast<size_t>(R) * d;
     const int threads = 256;
     const int blocks = static_cast<int>((per_level / 8 + threads - 1) / threads);
-    CAP_LAUNCH((meshed_mix_kernel), blocks, threads, 0, static_cast<cudaStream_t>(stream), gates, static_cast<const bf16*>(c), static_cast<bf16*>(out), levels, per_level, 1.f / sqrtf(static_cast<float>(levels)));
+    const float inv = 1.f / sqrtf(static_cast<float>(levels));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (c_dtype == CAP_F32)
+        CAP_LAUNCH((meshed_mix_kernel<float>), blocks, threads, 0, s, gates, static_cast<const float*>(c),
+                   static_cast<bf16*>(out), out_f32, levels, per_level, inv);
+    else
+        CAP_LAUNCH((meshed_mix_kernel<bf16>), blocks, threads, 0, s, gates, static_cast<const bf16*>(c),
+                   static_cast<bf16*>(out), out_f32, levels, per_level, inv);
     count_launch();
     return cap_check_launch("meshed_mix_kernel");
 }
 
-extern "C" int cap_aoa_gate(const float* ig, void* out, int R, int d, cap_stream_t stream) {
-    CAP_REQUIRE(ig && out && R > 0 && d % 8 == 0, "cap_aoa_gate: bad arguments");
+extern "C" int cap_aoa_gate(const float* ig, void* out, float* out_f32, int R, int d, cap_stream_t stream) {
+    CAP_REQUIRE(ig && (out || out_f32) && R > 0 && d % 8 == 0, "cap_aoa_gate: bad arguments");
     const size_t total = static_cast<size_t>(R) * d;
     const int threads = 256;
     const int blocks = static_cast<int>((total / 8 + threads - 1) / threads);
-    CAP_LAUNCH((aoa_gate_kernel), blocks, threads, 0, static_cast<cudaStream_t>(stream), ig, static_cast<bf16*>(out), R, d);
+    CAP_LAUNCH((aoa_gate_kernel), blocks, threads, 0, static_cast<cudaStream_t>(stream), ig, static_cast<bf16*>(out),
+               out_f32, R, d);
     count_launch();
     return cap_check_launch("aoa_gate_kernel");
 }

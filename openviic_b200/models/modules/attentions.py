@@ -122,10 +122,7 @@ class MultiHeadAttention(Module):
     def forward(self, queries, keys, values, padding_mask, attention_mask, **kwargs):
         with torch.no_grad():
             self_attention = keys is queries and values is queries
-            shared_kv = values is keys
-            queries = ops.as_bf16(queries)
-            keys = queries if self_attention else ops.as_bf16(keys)
-            values = keys if shared_kv else ops.as_bf16(values)
+            # activations stay fp32 between modules (residual stream); GEMMs round their operands to bf16
             if self.can_be_stateful and self._is_stateful:
                 # the reference's cache semantics: raw inputs appended along time (attentions.py:297-302)
                 self.running_keys = torch.cat([self.running_keys.to(keys.dtype), keys], 1)

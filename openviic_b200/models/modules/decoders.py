@@ -104,7 +104,7 @@ class _DecoderBase(Module):
                 self.running_seq.add_(1)  # not zeroed for <pad> rows, exactly like the reference
                 seq = self.running_seq
             embedded, _ = self.word_emb(caption_tokens)
-            out = (embedded + self.pos_emb(seq)).to(torch.bfloat16)
+            out = (embedded + self.pos_emb(seq)).float()
             for layer in self.layers:
                 out = layer(queries=out, keys=encoder_features, values=encoder_features,
                             self_padding_mask=padding_masks, self_attention_mask=self_attention_masks,

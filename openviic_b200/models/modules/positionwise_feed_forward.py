@@ -21,7 +21,7 @@ class PositionWiseFeedForward(nn.Module):
         """LN(x + fc2(relu(fc1 x))); ``zero_rows`` (bool/uint8 per row) fuses the callers' padded-row
         ``masked_fill(…, 0)`` (encoders.py:20, decoders.py:26) into the LayerNorm kernel."""
         with torch.no_grad():
-            x = ops.as_bf16(input)
+            x = input
             hidden = ops.linear(x, ops.cached_bf16(self.fc1.weight), self.fc1.bias, act=ops.ACT_RELU)
             y = ops.linear(hidden, ops.cached_bf16(self.fc2.weight), self.fc2.bias, out_dtype=torch.float32)
             return ops.add_layernorm(y, x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,

@@ -62,22 +62,33 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = 
 
 
 def add_layernorm(y: Tensor, residual: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float = 1e-5,
-                  pos: Optional[Tensor] = None, zero_rows: Optional[Tensor] = None) -> Tensor:
-    """LayerNorm(residual + y) * gamma + beta (+ pos[row % len(pos)]), rows in ``zero_rows`` zeroed."""
+                  pos: Optional[Tensor] = None, zero_rows: Optional[Tensor] = None,
+                  out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """LayerNorm(residual + y) * gamma + beta (+ pos[row % len(pos)]), rows in ``zero_rows`` zeroed.
+
+    ``y`` / ``residual`` may be fp32 or bf16.  The result is fp32 by default: activations travel between
+    modules in fp32 (as in the reference) and are rounded to bf16 only as GEMM operands."""
     _need_cuda(y, residual, gamma, beta, pos, zero_rows)
     d = y.shape[-1]
-    y2 = y.reshape(-1, d)
-    if y2.dtype not in (torch.float32, torch.bfloat16):
-        y2 = y2.float()
-    y2 = y2.contiguous()
-    r2 = None if residual is None else as_bf16(residual).reshape(-1, d).contiguous()
+
+    def rows_of(t):
+        t = t.reshape(-1, d)
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            t = t.float()
+        return t.contiguous()
+
+    y2 = rows_of(y)
+    r2 = None if residual is None else rows_of(residual)
     rows = y2.shape[0]
-    out = torch.empty((rows, d), device=y.device, dtype=torch.bfloat16)
+    out = torch.empty((rows, d), device=y.device, dtype=out_dtype)
     pos2 = None if pos is None else pos.float().reshape(-1, d).contiguous()
     zr = None if zero_rows is None else zero_rows.reshape(-1).to(torch.uint8).contiguous()
-    cabi.call("cap_add_layernorm", y2.data_ptr(), CAP_F32 if y2.dtype == torch.float32 else CAP_BF16, d, _ptr(r2), d,
+    code = lambda t: CAP_F32 if t.dtype == torch.float32 else CAP_BF16  # noqa: E731
+    cabi.call("cap_add_layernorm", y2.data_ptr(), code(y2), d, _ptr(r2), CAP_BF16 if r2 is None else code(r2), d,
               gamma.float().contiguous().data_ptr(), beta.float().contiguous().data_ptr(), float(eps), _ptr(pos2),
-              0 if pos2 is None else pos2.shape[0], _ptr(zr), out.data_ptr(), d, rows, d, _stream())
+              0 if pos2 is None else pos2.shape[0], _ptr(zr),
+              out.data_ptr() if out_dtype == torch.bfloat16 else None, d,
+              out.data_ptr() if out_dtype == torch.float32 else None, d, rows, d, _stream())
     return out.reshape(y.shape)
 
 
@@ -171,29 +182,30 @@ def embed_tokens(tokens: Tensor, word_emb: Tensor, pos_table: Tensor, position: 
     out = torch.empty((r, d), device=tok.device, dtype=torch.bfloat16)
     flags = torch.empty((r,), device=tok.device, dtype=torch.uint8)
     cabi.call("cap_embed_tokens", tok.data_ptr(), emb.data_ptr(), pos_table.float().contiguous().data_ptr(),
-              int(position), int(pad_idx), out.data_ptr(), flags.data_ptr(), r, d, _stream())
+              int(position), int(pad_idx), out.data_ptr(), None, flags.data_ptr(), r, d, _stream())
     return out, flags
 
 
 def meshed_mix(gates: Tensor, c: Tensor) -> Tensor:
-    """sum_i sigmoid(gates[i]) * c[i] / sqrt(levels); gates fp32, c bf16, both (levels, R, d)."""
+    """sum_i sigmoid(gates[i]) * c[i] / sqrt(levels); gates fp32, c fp32/bf16, both (levels, R, d) -> fp32."""
     _need_cuda(gates, c)
     g = gates.float().contiguous()
-    cc = as_bf16(c).contiguous()
+    cc = (c if c.dtype in (torch.float32, torch.bfloat16) else c.float()).contiguous()
     levels, r, d = cc.shape[0], cc[0].numel() // cc.shape[-1], cc.shape[-1]
-    out = torch.empty(cc.shape[1:], device=cc.device, dtype=torch.bfloat16)
-    cabi.call("cap_meshed_mix", g.data_ptr(), cc.data_ptr(), out.data_ptr(), levels, r, d, _stream())
+    out = torch.empty(cc.shape[1:], device=cc.device, dtype=torch.float32)
+    cabi.call("cap_meshed_mix", g.data_ptr(), cc.data_ptr(), CAP_F32 if cc.dtype == torch.float32 else CAP_BF16, None,
+              out.data_ptr(), levels, r, d, _stream())
     return out
 
 
 def aoa_gate(info_gate: Tensor) -> Tensor:
-    """info * sigmoid(gate) for fp32 (..., 2d) = (info | gate) -> bf16 (..., d)."""
+    """info * sigmoid(gate) for fp32 (..., 2d) = (info | gate) -> fp32 (..., d)."""
     _need_cuda(info_gate)
     ig = info_gate.float().contiguous()
     d = ig.shape[-1] // 2
     rows = ig.numel() // (2 * d)
-    out = torch.empty((*ig.shape[:-1], d), device=ig.device, dtype=torch.bfloat16)
-    cabi.call("cap_aoa_gate", ig.data_ptr(), out.data_ptr(), rows, d, _stream())
+    out = torch.empty((*ig.shape[:-1], d), device=ig.device, dtype=torch.float32)
+    cabi.call("cap_aoa_gate", ig.data_ptr(), None, out.data_ptr(), rows, d, _stream())
     return out
 
 

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 
 # Encoder features pass through 3 layers (7 bf16 roundings each) and logits through 3 more; the
 # per-op bound of BASELINE.md section 5 is 2e-2, the accumulated whole-stack bounds used here are:
-TOL_ENC = 6e-2       # max-abs on encoder output (LayerNorm-scale values, |x| ~ 3)
-TOL_LOGP = 1e-1      # max-abs on per-step log-probs over the full vocabulary
-TOL_LOGP_MEAN = 2.5e-2 # mean-abs on the same
+TOL_ENC = 4e-2       # max-abs on encoder output (LayerNorm-scale values, |x| ~ 3); measured 0.017-0.027
+TOL_LOGP = 9e-2      # max-abs on per-step log-probs over the full vocabulary; measured 0.052-0.074
+TOL_LOGP_MEAN = 2.2e-2 # mean-abs on the same; measured 0.009-0.020
 NEAR_TIE = 0.5       # a caption that differs from the reference's must score within this (oracle log-prob sum over 20 tokens)
 
 
@@ -51,7 +51,7 @@ def test_encoder_matches_oracle_and_golden(case_run):
     assert np.array_equal(eng.encoder_mask().cpu().numpy(), g["enc_mask"])
     err = (enc - ref).abs()
     print(f"[{r['name']}] encoder max-abs {err.max():.4f} mean-abs {err.mean():.5f}")
-    assert err.max().item() < TOL_ENC and err.mean().item() < 5e-3
+    assert err.max().item() < TOL_ENC and err.mean().item() < 4e-3
     stride = int(g["enc_row_stride"])
     rows = enc.reshape(-1, enc.shape[-1])[::stride][:64]
     assert np.abs(rows.numpy() - g["enc_rows"]).max() < TOL_ENC      # against the REAL reference's output
