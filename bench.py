@@ -357,9 +357,13 @@ def run_gpu_arm(args):
     peaks = measured_peaks()
     flops, gemm_s = time_gemm_family(cfg, n, batch, levels, device)
     achieved = flops / gemm_s / 1e12
+    traffic = None   # dram__bytes_read+write per launch, averaged over the decode step's GEMMs (ncu --set full capture)
+    summary = REPO / "profiles" / "r01_gemm_ncu_full_summary.json"
+    if summary.exists() and args.workload == "standard_grid" and batch == 256:
+        traffic = json.loads(summary.read_text())["avg_dram_bytes_per_launch"]
     roofline = {"bound": "tensor", "kernel": "gemm_tn_bf16_tcgen05 (all projection/FFN/vocab GEMMs of one step)",
                 "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "share_of_step": gemm_s / (total_ms / 1e3 / args.steps),
                 "step_algorithmic_tflops": gflop_per_caption * 1e9 * value / world / 1e12,
@@ -398,7 +402,7 @@ def main():
     ap.add_argument("--workload", default="standard_grid", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="independent batches kept in flight (engines/streams)")
+    ap.add_argument("--streams", type=int, default=8, help="independent batches kept in flight (engines/streams)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=40)

@@ -159,17 +159,17 @@ int cap_beam_reset(cap_beam* h, int batch, int bos_idx, cap_stream_t stream);
  * R = batch*beam rows at every t; at t = 0 only beam 0 of each image is a candidate (cur_beam = 1). */
 int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, int is_logprob,
                   cap_stream_t stream);
-/* Vocabulary projection fused with the log-softmax / top-k epilogue: logits are never written.  For
- * every row and every 128-column tile: part_ms[row][tile] = (max, sum exp(x-max)), part_val /
- * part_idx[row][tile][topk] = the tile's topk largest logits (descending, lower column first on ties)
- * and their columns.  topk is 5 or 8; *tiles_out = ceil(N/128).  Replaces decoders.py:121-123 +
- * the sort of beam_search.py:37 together with cap_beam_step_partials. */
-int cap_vocab_topk_partials(const void* x, int ldx, const void* w, const float* bias, int M, int N,
-                            int K, int topk, float* part_ms, float* part_val, int32_t* part_idx,
-                            int* tiles_out, cap_stream_t stream);
-/* One BeamSearch.iter(t) from those partials (same state update as cap_beam_step). */
-int cap_beam_step_partials(cap_beam* h, int t, const float* part_ms, const float* part_val,
-                           const int32_t* part_idx, int tiles, int topk, cap_stream_t stream);
+/* Vocabulary projection with log-softmax statistics: logits (M, ld) fp32 are stored once and, for every
+ * row and every 32-column chunk, part_ms[row][chunk] = (max, sum exp(x - max)); *chunks_out = 4*ceil(N/128).
+ * Replaces decoders.py:121-123 (fc + log_softmax) together with cap_beam_step_stats. */
+int cap_vocab_logits_stats(const void* x, int ldx, const void* w, const float* bias, float* logits,
+                           int ld, int M, int N, int K, float* part_ms, int* chunks_out,
+                           cap_stream_t stream);
+/* One BeamSearch.iter(t) from those statistics: log-sum-exp from the chunk pairs, then only the `beam`
+ * chunks with the largest maxima are read back from `logits` (the row's best candidates lie there);
+ * same state update as cap_beam_step.  Replaces the full sort of beam_search.py:37. */
+int cap_beam_step_stats(cap_beam* h, int t, const float* logits, int ld, const float* part_ms,
+                        int chunks, cap_stream_t stream);
 /* Final descending sort by seq_logprob + gather; ids int64 (B,out_size,T), logp fp32 same shape. */
 int cap_beam_finalize(cap_beam* h, int out_size, int64_t* ids, float* logp, cap_stream_t stream);
 /* Device views of the running state (valid until destroy): */
@@ -219,7 +219,7 @@ int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtype, const fl
                       int n, cap_stream_t stream);
 /* Decoder stack for step t on the beam state's current tokens -> logits (R, ld) fp32. */
 int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t stream);
-/* Production step: decoder stack + fused vocabulary epilogue + beam update (no logits buffer). */
+/* Production step: decoder stack + vocabulary GEMM with chunk statistics + beam update. */
 int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream);
 /* cap_beam_step on the engine's own logits. */
 int cap_engine_beam_advance(cap_engine* e, int t, cap_stream_t stream);

@@ -66,8 +66,8 @@ SIGNATURES = {
     "cap_beam_destroy": (_i, [_vp]),
     "cap_beam_reset": (_i, [_vp, _i, _i, _vp]),
     "cap_beam_step": (_i, [_vp, _i, _vp, _i, _i, _vp]),
-    "cap_vocab_topk_partials": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_i), _vp]),
-    "cap_beam_step_partials": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "cap_vocab_logits_stats": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, C.POINTER(_i), _vp]),
+    "cap_beam_step_stats": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     "cap_engine_decode_step": (_i, [_vp, _i, _vp]),
     "cap_beam_finalize": (_i, [_vp, _i, _vp, _vp, _vp]),
     "cap_beam_tokens": (_vp, [_vp]),

@@ -14,6 +14,7 @@
 #include "cap_common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 extern std::atomic<long long> g_cap_launches;
 
@@ -125,6 +126,169 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnDev a)
         bf16* orow = a.out + b * a.o_bs + static_cast<size_t>(i) * a.ldo + h * HEAD_DIM;
         reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------- tensor-core variant
+// Same contract as attention_kernel for nk + n_mem <= 128.  One CTA = 4 warps = 64 query rows of one
+// (batch, head); each warp owns a 16-row tile and keeps S = q.k^T, the softmax and P entirely in
+// registers (FlashAttention-2 fragment reuse: the fp32 accumulator layout of two 8-key tiles is the bf16
+// A-operand layout of one 16-key step), with K, V^T and Q staged once in shared memory.  The contraction
+// runs on mma.sync m16n8k16 (bf16 in, fp32 accumulate): at 49..128 keys x 64 dims per head the tiles are
+// far below tcgen05's 128-row atoms, so the warp-level tensor path is the right tool here; the
+// projections around it are the tcgen05 GEMMs.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const bf162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+constexpr int MMA_Q_TILE = 64;
+constexpr int MMA_PITCH = HEAD_DIM + 8;  // bf16 elements: 36 words per row => conflict-free fragment loads
+
+template <int NT>  // number of 8-key tiles: 8 (<= 64 keys) or 16 (<= 128 keys)
+__global__ void __launch_bounds__(128) attention_mma_kernel(const AttnDev a) {
+    pdl_prologue();
+    constexpr int NKP = NT * 8;
+    constexpr int VP = NKP + 8;  // V^T pitch (bf16): (NKP+8)/2 words == 4 mod 32 => conflict-free too
+    __shared__ __align__(16) bf16 sK[NKP * MMA_PITCH];
+    __shared__ __align__(16) bf16 sVt[HEAD_DIM * VP];
+    __shared__ __align__(16) bf16 sQ[MMA_Q_TILE * MMA_PITCH];
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MMA_Q_TILE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk_all = a.nk + a.n_mem;
+    const int hd = a.H * HEAD_DIM;
+
+    const bf16* kbase = a.k + b * a.k_bs + h * HEAD_DIM;
+    const bf16* vbase = a.v + b * a.v_bs + h * HEAD_DIM;
+    const bf162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    for (int idx = tid; idx < NKP * 32; idx += 128) {
+        const int j = idx >> 5, dp = idx & 31;
+        bf162 kk = zero2, vv = zero2;
+        if (j < nk_all) {
+            const bf16* krow = (j < a.nk) ? kbase + static_cast<size_t>(j) * a.ldk
+                                          : a.mem_k + static_cast<size_t>(j - a.nk) * hd + h * HEAD_DIM;
+            const bf16* vrow = (j < a.nk) ? vbase + static_cast<size_t>(j) * a.ldv
+                                          : a.mem_v + static_cast<size_t>(j - a.nk) * hd + h * HEAD_DIM;
+            kk = reinterpret_cast<const bf162*>(krow)[dp];
+            vv = reinterpret_cast<const bf162*>(vrow)[dp];
+        }
+        *reinterpret_cast<bf162*>(sK + j * MMA_PITCH + 2 * dp) = kk;
+        sVt[(2 * dp) * VP + j] = vv.x;
+        sVt[(2 * dp + 1) * VP + j] = vv.y;
+    }
+    for (int idx = tid; idx < MMA_Q_TILE * 32; idx += 128) {
+        const int i = idx >> 5, dp = idx & 31;
+        bf162 qq = zero2;
+        if (q0 + i < a.nq)
+            qq = reinterpret_cast<const bf162*>(a.q + b * a.q_bs + static_cast<size_t>(q0 + i) * a.ldq + h * HEAD_DIM)[dp];
+        *reinterpret_cast<bf162*>(sQ + i * MMA_PITCH + 2 * dp) = qq;
+    }
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16;
+    if (q0 + r0 >= a.nq) return;  // whole 16-row tile out of range (warp-uniform)
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const bf16* base = sQ + (r0 + g) * MMA_PITCH + ks * 16 + 2 * t;
+        qa[ks][0] = *reinterpret_cast<const uint32_t*>(base);
+        qa[ks][1] = *reinterpret_cast<const uint32_t*>(base + 8 * MMA_PITCH);
+        qa[ks][2] = *reinterpret_cast<const uint32_t*>(base + 8);
+        qa[ks][3] = *reinterpret_cast<const uint32_t*>(base + 8 * MMA_PITCH + 8);
+    }
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const bf16* base = sK + (nt * 8 + g) * MMA_PITCH + ks * 16 + 2 * t;
+            mma_bf16_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(base),
+                           *reinterpret_cast<const uint32_t*>(base + 8));
+        }
+    }
+    // scale, mask, geometry bias; rows ra = g, rb = g + 8 of this warp's tile
+    const int ra = q0 + r0 + g, rb = ra + 8;
+    const bool va = ra < a.nq, vb = rb < a.nq;
+    const uint8_t* mra = (a.mask && va) ? a.mask + b * a.mask_bs + static_cast<size_t>(ra) * a.mask_qs : nullptr;
+    const uint8_t* mrb = (a.mask && vb) ? a.mask + b * a.mask_bs + static_cast<size_t>(rb) * a.mask_qs : nullptr;
+    const float* gra = (a.geometry && va) ? a.geometry + ((static_cast<size_t>(b) * a.H + h) * a.nq + ra) * a.nk : nullptr;
+    const float* grb = (a.geometry && vb) ? a.geometry + ((static_cast<size_t>(b) * a.H + h) * a.nq + rb) * a.nk : nullptr;
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int col = nt * 8 + 2 * t + (e & 1);
+            const bool second = e >= 2;
+            float x = s[nt][e] * a.scale;
+            if (col >= nk_all) {
+                x = -INFINITY;
+            } else if (col < a.nk) {
+                const uint8_t* mr = second ? mrb : mra;
+                const float* gr = second ? grb : gra;
+                if (mr && mr[col]) x = -INFINITY;
+                if (gr) x += logf(fmaxf(gr[col], 1e-6f));
+            }
+            s[nt][e] = x;
+            if (second) mb = fmaxf(mb, x); else ma = fmaxf(ma, x);
+        }
+    }
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    float suma = 0.f, sumb = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool second = e >= 2;
+            const float m = second ? mb : ma;
+            const float p = (m == -INFINITY) ? 0.f : __expf(s[nt][e] - m);
+            s[nt][e] = p;
+            if (second) sumb += p; else suma += p;
+        }
+    }
+    suma += __shfl_xor_sync(0xffffffffu, suma, 1);
+    suma += __shfl_xor_sync(0xffffffffu, suma, 2);
+    sumb += __shfl_xor_sync(0xffffffffu, sumb, 1);
+    sumb += __shfl_xor_sync(0xffffffffu, sumb, 2);
+    // O = P.V : two 8-key accumulator tiles form one 16-key A operand
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            const bf16* base = sVt + (dt * 8 + g) * VP + kk * 16 + 2 * t;
+            mma_bf16_16816(o[dt], pa, *reinterpret_cast<const uint32_t*>(base),
+                           *reinterpret_cast<const uint32_t*>(base + 8));
+        }
+    }
+    const float inva = suma > 0.f ? 1.f / suma : 0.f;
+    const float invb = sumb > 0.f ? 1.f / sumb : 0.f;
+    bf16* oa = a.out + b * a.o_bs + static_cast<size_t>(ra) * a.ldo + h * HEAD_DIM;
+    bf16* ob = a.out + b * a.o_bs + static_cast<size_t>(rb) * a.ldo + h * HEAD_DIM;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+        const int col = dt * 8 + 2 * t;
+        if (va) *reinterpret_cast<bf162*>(oa + col) = __floats2bfloat162_rn(o[dt][0] * inva, o[dt][1] * inva);
+        if (vb) *reinterpret_cast<bf162*>(ob + col) = __floats2bfloat162_rn(o[dt][2] * invb, o[dt][3] * invb);
     }
 }
 
@@ -451,6 +615,16 @@ int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key
 
 int launch_attention(const AttnDev& a, cudaStream_t stream) {
     const int nk_all = a.nk + a.n_mem;
+    static const bool force_simt = getenv("OPENVIIC_ATTENTION_SIMT") != nullptr;
+    if (nk_all <= 128 && !force_simt) {  // tensor-core variant
+        dim3 grid((a.nq + MMA_Q_TILE - 1) / MMA_Q_TILE, a.H, a.B);
+        if (nk_all <= 64)
+            CAP_LAUNCH((attention_mma_kernel<8>), grid, 128, 0, stream, a);
+        else
+            CAP_LAUNCH((attention_mma_kernel<16>), grid, 128, 0, stream, a);
+        g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+        return cap_check_launch("attention_mma_kernel");
+    }
     const size_t smem = static_cast<size_t>(nk_all) * (K_STRIDE + HEAD_DIM) * 2 + ATT_WARPS * HEAD_DIM * 4 +
                         ATT_WARPS * MAX_KEYS * 4;
     static bool attr_done = false;

@@ -271,23 +271,25 @@ beam_rowpass_reg_kernel(const BeamDev st, const float* __restrict__ scores, int 
     }
 }
 
-// Row merge for the fused vocabulary epilogue (gemm_tcgen05.cu, TOPK > 0): one warp per beam row
-// combines the per-N-tile partials -- log-sum-exp from (max, sum exp) pairs, then the row's `beam` best
-// candidates seq_logprob + ((x - max) - log_sum) out of tiles*TOPK logits -- and does the same EOS /
-// sentinel bookkeeping as the row pass.  Same outputs (cand_val / cand_lp / cand_idx) as the row pass.
+// Row merge for the vocabulary GEMM's STATS epilogue (gemm_tcgen05.cu): one warp per beam row.
+//   1. log-sum-exp of the row from the per-32-column-chunk (max, sum exp) pairs;
+//   2. the `beam` chunks with the largest maxima, ties to the lower chunk -- the row's `beam` best logits
+//      under (value desc, column asc) provably lie in them: a chunk ordered before another contributes
+//      an element ordered before every element of the other;
+//   3. only those chunks' logits are read back (lane = column) and the `beam` best candidates
+//      seq_logprob + ((x - max) - log_sum) selected, with the row pass's EOS / -999 bookkeeping.
 constexpr int MERGE_WARPS = 4;
-constexpr int MERGE_TILES_PER_LANE = 4;  // up to 128 N tiles of 128 columns: vocab <= 16384
+constexpr int MERGE_CHUNKS_PER_LANE = 16;  // up to 512 chunks: vocab <= 16384
 
-template <int TOPK>
 __global__ void __launch_bounds__(MERGE_WARPS * 32)
-beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const float* __restrict__ part_val,
-                     const int32_t* __restrict__ part_idx, int tiles, int t) {
+beam_chunkmerge_kernel(const BeamDev st, const float* __restrict__ logits, int ld, const float* __restrict__ part_ms,
+                       int chunks, int t) {
     pdl_prologue();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = st.batch * st.beam;
     const int r = blockIdx.x * MERGE_WARPS + warp;
     if (r >= R) return;
-    const int beam = st.beam;
+    const int beam = st.beam, V = st.vocab;
 
     float mask = st.seq_mask[r];
     if (t > 0) mask *= (st.tokens[r] != st.eos) ? 1.f : 0.f;
@@ -305,45 +307,50 @@ beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const 
         if (lane < beam) { cval[lane] = (lane == 0) ? seq_lp : SENTINEL; clp[lane] = 0.f; cidx[lane] = lane; }
         return;
     }
-    const size_t row_base = static_cast<size_t>(r) * tiles;
-    float tm[MERGE_TILES_PER_LANE], ts[MERGE_TILES_PER_LANE];
-    float mx = -INFINITY;
+    const float2* ms = reinterpret_cast<const float2*>(part_ms) + static_cast<size_t>(r) * chunks;
+    float cm[MERGE_CHUNKS_PER_LANE];
+    float mx = -INFINITY, sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
-        const int tile = lane + 32 * i;
-        tm[i] = -INFINITY;
-        ts[i] = 0.f;
-        if (tile < tiles) {
-            const float2 ms = *reinterpret_cast<const float2*>(part_ms + (row_base + tile) * 2);
-            tm[i] = ms.x;
-            ts[i] = ms.y;
-        }
-        mx = fmaxf(mx, tm[i]);
+    for (int i = 0; i < MERGE_CHUNKS_PER_LANE; ++i) {
+        const int chunk = lane + 32 * i;
+        cm[i] = -INFINITY;
+        if (chunk < chunks) cm[i] = ms[chunk].x;
+        mx = fmaxf(mx, cm[i]);
     }
     mx = warp_max(mx);
-    float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MERGE_TILES_PER_LANE; ++i)
-        if (tm[i] != -INFINITY) sum += ts[i] * __expf(tm[i] - mx);
+    for (int i = 0; i < MERGE_CHUNKS_PER_LANE; ++i) {
+        const int chunk = lane + 32 * i;
+        if (chunk < chunks && cm[i] != -INFINITY) sum += ms[chunk].y * __expf(cm[i] - mx);
+    }
     const float log_sum = logf(warp_sum(sum));
 
-    float cv[MERGE_TILES_PER_LANE][TOPK], lp[MERGE_TILES_PER_LANE][TOPK];
-    int ci[MERGE_TILES_PER_LANE][TOPK];
+    // the `beam` best chunks, then this lane's column of each
+    float cv[BEAM_MAX], lp[BEAM_MAX];
+    int ci[BEAM_MAX];
 #pragma unroll
-    for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
-        const int tile = lane + 32 * i;
+    for (int k = 0; k < BEAM_MAX; ++k) {
+        cv[k] = -INFINITY;
+        lp[k] = 0.f;
+        ci[k] = 0x7fffffff;
+        if (k < beam) {
+            Cand mine;
+            mine.val = -INFINITY;
+            mine.idx = 0x7fffffff;
 #pragma unroll
-        for (int k = 0; k < TOPK; ++k) {
-            cv[i][k] = -INFINITY;
-            lp[i][k] = 0.f;
-            ci[i][k] = 0x7fffffff;
-            if (tile < tiles) {
-                const float x = part_val[(row_base + tile) * TOPK + k];
-                const int idx = part_idx[(row_base + tile) * TOPK + k];
-                if (idx != 0x7fffffff) {
-                    lp[i][k] = (x - mx) - log_sum;   // word_logprob, same formula as the row pass
-                    cv[i][k] = seq_lp + lp[i][k];    // candidate_logprob
-                    ci[i][k] = idx;
+            for (int i = 0; i < MERGE_CHUNKS_PER_LANE; ++i)  // chunk ids ascend with i: strict > keeps the lower one
+                if (cm[i] > mine.val) { mine.val = cm[i]; mine.idx = lane + 32 * i; }
+            const Cand wb = warp_best(mine);
+#pragma unroll
+            for (int i = 0; i < MERGE_CHUNKS_PER_LANE; ++i)
+                if (lane + 32 * i == wb.idx) cm[i] = -INFINITY;  // retired by its owner
+            if (wb.idx != 0x7fffffff) {
+                const int col = wb.idx * 32 + lane;
+                if (col < V) {
+                    const float x = __ldg(logits + static_cast<size_t>(r) * ld + col);
+                    lp[k] = (x - mx) - log_sum;  // word_logprob, same formula as the row pass
+                    cv[k] = seq_lp + lp[k];      // candidate_logprob
+                    ci[k] = col;
                 }
             }
         }
@@ -354,14 +361,11 @@ beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const 
         mine.idx = 0x7fffffff;
         float mine_lp = 0.f;
 #pragma unroll
-        for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
-#pragma unroll
-            for (int k = 0; k < TOPK; ++k) {
-                if (cand_before(cv[i][k], ci[i][k], mine.val, mine.idx)) {
-                    mine.val = cv[i][k];
-                    mine.idx = ci[i][k];
-                    mine_lp = lp[i][k];
-                }
+        for (int k = 0; k < BEAM_MAX; ++k) {
+            if (cand_before(cv[k], ci[k], mine.val, mine.idx)) {
+                mine.val = cv[k];
+                mine.idx = ci[k];
+                mine_lp = lp[k];
             }
         }
         const Cand wb = warp_best(mine);
@@ -370,11 +374,8 @@ beam_rowmerge_kernel(const BeamDev st, const float* __restrict__ part_ms, const 
             cidx[round] = wb.idx;
             clp[round] = mine_lp;
 #pragma unroll
-            for (int i = 0; i < MERGE_TILES_PER_LANE; ++i) {
-#pragma unroll
-                for (int k = 0; k < TOPK; ++k)
-                    if (ci[i][k] == wb.idx) { cv[i][k] = -INFINITY; ci[i][k] = 0x7fffffff; }
-            }
+            for (int k = 0; k < BEAM_MAX; ++k)
+                if (ci[k] == wb.idx) { cv[k] = -INFINITY; ci[k] = 0x7fffffff; }
         }
         __syncwarp();
     }
@@ -619,22 +620,18 @@ extern "C" int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, in
     return cap_check_launch("beam_select_kernel");
 }
 
-extern "C" int cap_beam_step_partials(cap_beam* h, int t, const float* part_ms, const float* part_val,
-                                      const int32_t* part_idx, int tiles, int topk, cap_stream_t stream) {
-    CAP_REQUIRE(h && part_ms && part_val && part_idx, "cap_beam_step_partials: null pointer");
-    CAP_REQUIRE(t >= 0 && t < h->dev.max_len, "cap_beam_step_partials: step %d outside [0,%d)", t, h->dev.max_len);
-    CAP_REQUIRE(tiles > 0 && tiles <= 32 * MERGE_TILES_PER_LANE, "cap_beam_step_partials: %d tiles unsupported", tiles);
-    CAP_REQUIRE((topk == 5 || topk == 8) && topk >= h->dev.beam, "cap_beam_step_partials: topk %d < beam or unsupported",
-                topk);
+extern "C" int cap_beam_step_stats(cap_beam* h, int t, const float* logits, int ld, const float* part_ms, int chunks,
+                                   cap_stream_t stream) {
+    CAP_REQUIRE(h && logits && part_ms, "cap_beam_step_stats: null pointer");
+    CAP_REQUIRE(t >= 0 && t < h->dev.max_len, "cap_beam_step_stats: step %d outside [0,%d)", t, h->dev.max_len);
+    CAP_REQUIRE(chunks > 0 && chunks <= 32 * MERGE_CHUNKS_PER_LANE && chunks * 32 >= h->dev.vocab && ld >= h->dev.vocab,
+                "cap_beam_step_stats: %d chunks unsupported for vocab %d", chunks, h->dev.vocab);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const BeamDev& d = h->dev;
     const int R = d.batch * d.beam;
-    const int blocks = (R + MERGE_WARPS - 1) / MERGE_WARPS;
-    if (topk == 5)
-        CAP_LAUNCH((beam_rowmerge_kernel<5>), blocks, MERGE_WARPS * 32, 0, s, d, part_ms, part_val, part_idx, tiles, t);
-    else
-        CAP_LAUNCH((beam_rowmerge_kernel<8>), blocks, MERGE_WARPS * 32, 0, s, d, part_ms, part_val, part_idx, tiles, t);
-    CAP_PROPAGATE(cap_check_launch("beam_rowmerge_kernel"));
+    CAP_LAUNCH((beam_chunkmerge_kernel), (R + MERGE_WARPS - 1) / MERGE_WARPS, MERGE_WARPS * 32, 0, s, d, logits, ld, part_ms,
+               chunks, t);
+    CAP_PROPAGATE(cap_check_launch("beam_chunkmerge_kernel"));
     const size_t sel_smem = static_cast<size_t>(d.beam) * d.max_len * 12;
     CAP_LAUNCH((beam_select_kernel), d.batch, 128, sel_smem, s, d, t);
     g_cap_launches.fetch_add(2, std::memory_order_relaxed);

@@ -104,9 +104,8 @@ struct cap_engine {
     float* buf_y32 = nullptr;
     float* logits = nullptr;
     int ld_logits = 0;
-    float *part_ms = nullptr, *part_val = nullptr;  // fused vocabulary epilogue partials
-    int32_t* part_idx = nullptr;
-    int vocab_tiles = 0, topk = 5;
+    float* part_ms = nullptr;  // vocabulary GEMM chunk statistics [R][chunks][2]
+    int vocab_chunks = 0;
     int64_t* out_ids = nullptr;
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
@@ -422,11 +421,8 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->buf_y32, rows_max * static_cast<size_t>(std::max(2 * d, hd))));
     e->ld_logits = (m.vocab + 7) / 8 * 8;
     CAP_PROPAGATE(dev_alloc(e, &e->logits, R * e->ld_logits));
-    e->vocab_tiles = (m.vocab + 127) / 128;
-    e->topk = beam <= 5 ? 5 : 8;
-    CAP_PROPAGATE(dev_alloc(e, &e->part_ms, R * e->vocab_tiles * 2));
-    CAP_PROPAGATE(dev_alloc(e, &e->part_val, R * e->vocab_tiles * e->topk));
-    CAP_PROPAGATE(dev_alloc(e, &e->part_idx, R * e->vocab_tiles * e->topk));
+    e->vocab_chunks = ((m.vocab + 127) / 128) * 4;
+    CAP_PROPAGATE(dev_alloc(e, &e->part_ms, R * e->vocab_chunks * 2));
     CAP_PROPAGATE(dev_alloc(e, &e->out_ids, R * T));
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));
     CAP_PROPAGATE(cap_beam_create(max_batch, beam, T, m.vocab, m.eos_idx, &e->beam_state));
@@ -527,15 +523,15 @@ extern "C" int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream)
     CAP_REQUIRE(e && e->encoded, "cap_engine_decode_step: encode first");
     CAP_REQUIRE(t >= 0 && t < e->desc.max_len, "cap_engine_decode_step: step %d outside [0,%d)", t, e->desc.max_len);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (e->vocab_tiles > 128)  // vocabularies beyond the merge kernel's reach: materialise logits
+    if (e->vocab_chunks > 512)  // vocabularies beyond the merge kernel's reach: full row pass over the logits
         return cap_engine_decode_logits(e, t, stream) || cap_engine_beam_advance(e, t, stream);
     bf16* x = nullptr;
     CAP_PROPAGATE(run_decoder_stack(e, t, s, &x));
     const int R = e->cur_batch * e->beam;
-    int tiles = 0;
-    CAP_PROPAGATE(cap_vocab_topk_partials(x, e->desc.d_model, e->vocab_fc.w, e->vocab_fc.b, R, e->desc.vocab,
-                                          e->desc.d_model, e->topk, e->part_ms, e->part_val, e->part_idx, &tiles, s));
-    return cap_beam_step_partials(e->beam_state, t, e->part_ms, e->part_val, e->part_idx, tiles, e->topk, s);
+    int chunks = 0;
+    CAP_PROPAGATE(cap_vocab_logits_stats(x, e->desc.d_model, e->vocab_fc.w, e->vocab_fc.b, e->logits, e->ld_logits, R,
+                                         e->desc.vocab, e->desc.d_model, e->part_ms, &chunks, s));
+    return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, chunks, s);
 }
 
 namespace {

@@ -31,9 +31,7 @@ struct GemmParams {
     int M, N, K, ldo;
     int out_f32, act, num_stages, vec_ok;
     uint32_t pipe_bytes;  // bytes reserved for the stage ring (>= the epilogue's staging tile), multiple of 1024
-    float* part_ms;       // TOPK epilogue: [M][tiles_n][2]    (row max, sum exp(x - max)) per N tile
-    float* part_val;      //                [M][tiles_n][TOPK] largest logits of the tile, descending
-    int32_t* part_idx;    //                [M][tiles_n][TOPK] their column indices
+    float* part_ms;       // STATS epilogue: [M][chunks][2] (max, sum exp(x - max)) per 32-column chunk
     unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (cap_debug_gemm_trace), else nullptr
 };
 
@@ -161,10 +159,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-// TOPK == 0: store epilogue.  TOPK > 0 (vocabulary projection): nothing is stored; each row of the tile
-// emits its log-softmax partials (max, sum exp) and its TOPK largest logits with their column ids
-// (value desc, column asc), merged per row by beam_rowmerge_kernel (beam.cu).
-template <int BLOCK_N, int TOPK>
+// STATS (vocabulary projection, fp32 logits out): besides the store, every row emits (max, sum exp(x - max))
+// for each 32-column chunk.  beam_rowmerge_kernel (beam.cu) turns those into the row's log-sum-exp and
+// reads only the `beam` chunks with the largest maxima -- the row's top-`beam` logits provably lie there --
+// so the 52 MB logits buffer is written once and almost never read back.
+template <int BLOCK_N, bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
@@ -257,64 +256,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(tmem_full_bar, 0);
         if (warp == 2 && lane == 0) stamp(p, 5);
         tcgen05_fence_after();
-        if constexpr (TOPK > 0) {
-            const int row = m0 + quad * 32 + lane;
-            float top_v[TOPK];
-            int top_i[TOPK];
-#pragma unroll
-            for (int k = 0; k < TOPK; ++k) { top_v[k] = -INFINITY; top_i[k] = 0x7fffffff; }
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    const float x = col < p.N ? __uint_as_float(v[j]) + s_bias[c0 + j] : -INFINITY;
-                    mx = fmaxf(mx, x);
-                    if (x > top_v[TOPK - 1]) {  // strict: equal logits keep the lower column first
-                        // branch-free shift insertion on statically indexed registers: once the new
-                        // element has displaced an entry, every later entry shifts down by one
-                        float cv = x;
-                        int ci = col;
-                        bool shifting = false;
-#pragma unroll
-                        for (int k = 0; k < TOPK; ++k) {
-                            const bool sw = shifting || (cv > top_v[k]);
-                            const float tv = top_v[k];
-                            const int ti = top_i[k];
-                            top_v[k] = sw ? cv : tv;
-                            top_i[k] = sw ? ci : ti;
-                            cv = sw ? tv : cv;
-                            ci = sw ? ti : ci;
-                            shifting = sw;
-                        }
-                    }
-                }
-            }
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n0 + c0 + j < p.N) sum += __expf(__uint_as_float(v[j]) + s_bias[c0 + j] - mx);
-            }
-            if (row < p.M) {
-                const size_t slot = static_cast<size_t>(row) * gridDim.x + blockIdx.x;
-                p.part_ms[slot * 2] = mx;
-                p.part_ms[slot * 2 + 1] = sum;
-#pragma unroll
-                for (int k = 0; k < TOPK; ++k) {
-                    p.part_val[slot * TOPK + k] = top_v[k];
-                    p.part_idx[slot * TOPK + k] = top_i[k];
-                }
-            }
-        } else {
+        {
         // All MMAs have retired, so the pipeline stages are free: reuse them as the output staging tile.
         const int esz = p.out_f32 ? 4 : 2;
         const int row_bytes = BLOCK_N * esz;
@@ -329,6 +271,29 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = apply_act(__uint_as_float(v[j]) + s_bias[c0 + j], p.act);
+            if constexpr (STATS) {
+                const int grow = m0 + quad * 32 + lane;
+                const int valid = p.N - (n0 + c0);  // columns of this chunk inside the vocabulary (warp-uniform)
+                float cm = -INFINITY, cs = 0.f;
+                if (valid >= 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cm = fmaxf(cm, f[j]);
+                    const float cm2 = cm * 1.4426950408889634f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cs += exp2f(fmaf(f[j], 1.4426950408889634f, -cm2));
+                } else if (valid > 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < valid ? f[j] : -INFINITY);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cs += j < valid ? __expf(f[j] - cm) : 0.f;
+                }
+                if (grow < p.M) {
+                    const size_t chunk = static_cast<size_t>(blockIdx.x) * (BLOCK_N / 32) + c0 / 32;
+                    const size_t chunks = static_cast<size_t>(gridDim.x) * (BLOCK_N / 32);
+                    *reinterpret_cast<float2*>(p.part_ms + (static_cast<size_t>(grow) * chunks + chunk) * 2) =
+                        make_float2(cm, cs);
+                }
+            }
             if (p.out_f32) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -362,7 +327,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
             }
         }
-        }  // TOPK == 0
+        }
     }
     if (warp == 2 && lane == 0) stamp(p, 6);
     tcgen05_fence_before();
@@ -409,7 +374,7 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
     return CAP_OK;
 }
 
-template <int BLOCK_N, int TOPK = 0>
+template <int BLOCK_N, bool STATS = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
     constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
     const uint32_t staging = BLOCK_M * (BLOCK_N * (p.out_f32 ? 4 : 2) + 16);
@@ -420,13 +385,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N, TOPK>,
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N, STATS>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
         attr_smem = 200 * 1024;
     }
     dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
-    CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, TOPK>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
+    CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_bf16_tcgen05");
 }
@@ -475,7 +440,8 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     p.out_f32 = (out_dtype == CAP_F32);
     p.act = act;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-    int stages = forced_stages ? forced_stages : (bn == 128 ? 3 : 4);
+    // short K loops (<= 8 blocks) get a 2-deep ring: less smem per CTA, more CTAs of concurrent kernels per SM
+    int stages = forced_stages ? forced_stages : (bn == 128 ? (num_kb <= 8 ? 2 : 3) : 4);
     if (stages > num_kb) stages = num_kb;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 1) stages = 1;
@@ -495,28 +461,30 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     }
 }
 
-// Vocabulary projection with the fused log-softmax / top-k epilogue (no logits are materialised).
-extern "C" int cap_vocab_topk_partials(const void* x, int ldx, const void* w, const float* bias, int M, int N, int K,
-                                       int topk, float* part_ms, float* part_val, int32_t* part_idx, int* tiles_out,
-                                       cap_stream_t stream) {
-    CAP_REQUIRE(x && w && part_ms && part_val && part_idx, "cap_vocab_topk_partials: null pointer");
-    CAP_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldx >= K, "cap_vocab_topk_partials: bad shape");
-    CAP_REQUIRE(topk == 5 || topk == 8, "cap_vocab_topk_partials: topk must be 5 or 8");
+// Vocabulary projection: fp32 logits + per-32-column-chunk log-softmax statistics in one pass.
+extern "C" int cap_vocab_logits_stats(const void* x, int ldx, const void* w, const float* bias, float* logits, int ld,
+                                      int M, int N, int K, float* part_ms, int* chunks_out, cap_stream_t stream) {
+    CAP_REQUIRE(x && w && logits && part_ms, "cap_vocab_logits_stats: null pointer");
+    CAP_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldx >= K && ld >= N,
+                "cap_vocab_logits_stats: bad shape");
     CAP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
-                "cap_vocab_topk_partials: x and w must be 16-byte aligned");
+                "cap_vocab_logits_stats: x and w must be 16-byte aligned");
     GemmParams p = {};
+    p.out = logits;
     p.bias = bias;
-    p.M = M; p.N = N; p.K = K;
+    p.M = M; p.N = N; p.K = K; p.ldo = ld;
+    p.out_f32 = 1;
+    p.act = CAP_ACT_NONE;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     p.num_stages = num_kb < 3 ? num_kb : 3;
-    p.part_ms = part_ms; p.part_val = part_val; p.part_idx = part_idx;
-    p.trace = nullptr;
-    if (tiles_out) *tiles_out = (N + 127) / 128;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) && (ld % 4 == 0);
+    p.part_ms = part_ms;
+    p.trace = g_gemm_trace;
+    if (chunks_out) *chunks_out = ((N + 127) / 128) * 4;
     CUtensorMap ta, tb;
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return topk == 5 ? launch_gemm<128, 5>(ta, tb, p, s) : launch_gemm<128, 8>(ta, tb, p, s);
+    return launch_gemm<128, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cap_debug_gemm_trace(unsigned long long* device_buffer) {

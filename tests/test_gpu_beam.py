@@ -127,23 +127,26 @@ def test_beam_argument_errors(device):
         cabi.call("cap_beam_destroy", h)
 
 
-@pytest.mark.parametrize("B,beam,V", [(7, 5, 10201), (5, 3, 1000), (3, 8, 777)])
-def test_fused_vocab_epilogue_matches_logits_path(device, B, beam, V):
-    """Vocabulary GEMM with the log-softmax/top-k epilogue + row merge == GEMM -> logits -> row pass."""
+@pytest.mark.parametrize("B,beam,V", [(7, 5, 10201), (5, 3, 1000), (3, 8, 777), (4, 5, 97)])
+def test_vocab_stats_epilogue_matches_full_row_pass(device, B, beam, V):
+    """Vocabulary GEMM with chunk statistics + chunk merge == GEMM -> logits -> full row pass, including
+    exact ties that straddle chunks (quantised weights) and rows that finish (<eos>)."""
     from openviic_b200 import ops
     from openviic_b200.engine import _device_view
     T, d, eos = 6, 512, 2
     R = B * beam
     g = torch.Generator().manual_seed(V)
-    w = (torch.randn(V, d, generator=g) * 0.13).to(torch.bfloat16).to(device)
-    xs = [torch.randn(R, d, generator=g).to(torch.bfloat16).to(device) for _ in range(T)]
+    w = torch.round(torch.randn(V, d, generator=g) * 0.13 * 8) / 8         # coarse grid: many exactly equal logits
+    w[eos] = 0.25
+    w = w.to(torch.bfloat16).to(device)
+    xs = [torch.round(torch.randn(R, d, generator=g) * 2) / 2 for _ in range(T)]
+    xs = [x.to(torch.bfloat16).to(device) for x in xs]
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     lib = cabi.load_library()
-    topk = 5 if beam <= 5 else 8
-    tiles = (V + 127) // 128
-    part_ms = torch.empty(R, tiles, 2, device=device)
-    part_val = torch.empty(R, tiles, topk, device=device)
-    part_idx = torch.empty(R, tiles, topk, device=device, dtype=torch.int32)
+    ld = (V + 7) // 8 * 8
+    chunks = ((V + 127) // 128) * 4
+    logits = torch.empty(R, ld, device=device)
+    part_ms = torch.empty(R, chunks, 2, device=device)
     results = []
     for fused in (False, True):
         h = C.c_void_p()
@@ -152,15 +155,14 @@ def test_fused_vocab_epilogue_matches_logits_path(device, B, beam, V):
             cabi.call("cap_beam_reset", h, B, 1, stream)
             for t in range(T):
                 if fused:
-                    n_tiles = C.c_int()
-                    cabi.call("cap_vocab_topk_partials", xs[t].data_ptr(), d, w.data_ptr(), None, R, V, d, topk,
-                              part_ms.data_ptr(), part_val.data_ptr(), part_idx.data_ptr(), C.byref(n_tiles), stream)
-                    assert n_tiles.value == tiles
-                    cabi.call("cap_beam_step_partials", h, t, part_ms.data_ptr(), part_val.data_ptr(),
-                              part_idx.data_ptr(), tiles, topk, stream)
+                    n_chunks = C.c_int()
+                    cabi.call("cap_vocab_logits_stats", xs[t].data_ptr(), d, w.data_ptr(), None, logits.data_ptr(), ld,
+                              R, V, d, part_ms.data_ptr(), C.byref(n_chunks), stream)
+                    assert n_chunks.value == chunks
+                    cabi.call("cap_beam_step_stats", h, t, logits.data_ptr(), ld, part_ms.data_ptr(), chunks, stream)
                 else:
-                    logits = ops.linear(xs[t], w, None, out_dtype=torch.float32).contiguous()
-                    cabi.call("cap_beam_step", h, t, logits.data_ptr(), logits.stride(0), 0, stream)
+                    full = ops.linear(xs[t], w, None, out_dtype=torch.float32).contiguous()
+                    cabi.call("cap_beam_step", h, t, full.data_ptr(), full.stride(0), 0, stream)
             ids = torch.empty(B, beam, T, dtype=torch.int64, device=device)
             lp = torch.empty(B, beam, T, dtype=torch.float32, device=device)
             cabi.call("cap_beam_finalize", h, beam, ids.data_ptr(), lp.data_ptr(), stream)
@@ -172,12 +174,10 @@ def test_fused_vocab_epilogue_matches_logits_path(device, B, beam, V):
     (ids_a, lp_a, seq_a), (ids_b, lp_b, seq_b) = results
     assert torch.equal(ids_a, ids_b)
     assert (lp_a - lp_b).abs().max().item() < 1e-4 and (seq_a - seq_b).abs().max().item() < 1e-4
-    # partials against a direct fp32 statement of the last step
+    # statistics against a direct fp32 statement of the last step
     ref = xs[-1].float() @ w.float().t()
-    lse = torch.logsumexp(ref, -1).cpu()
+    assert (logits[:, :V] - ref).abs().max().item() < 1e-3
     pm, ps = part_ms[..., 0].cpu(), part_ms[..., 1].cpu()
     mx = pm.max(1).values
     mine = mx + torch.log((ps * torch.exp(pm - mx[:, None])).sum(1))
-    assert (mine - lse).abs().max().item() < 1e-3
-    best = part_val.cpu().reshape(R, -1).max(1).values
-    assert (best - ref.max(1).values.cpu()).abs().max().item() < 1e-3
+    assert (mine - torch.logsumexp(ref, -1).cpu()).abs().max().item() < 1e-3

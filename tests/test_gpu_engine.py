@@ -103,9 +103,9 @@ def test_stepwise_logprobs_and_captions(case_run):
     assert equal.float().mean().item() >= 0.4
 
 
-def test_fused_vocab_epilogue_path_equals_logits_path(case_run):
-    """Production step (vocabulary GEMM with fused log-softmax/top-k, no logits) vs the debug step
-    that materialises logits: same beams, log-probs equal to fp32 round-off."""
+def test_production_step_equals_full_row_pass(case_run):
+    """Production step (vocabulary GEMM with chunk statistics + chunk merge) vs the debug step that runs
+    the full row pass over the logits: same beams, log-probs equal to fp32 round-off."""
     r = case_run
     case, eng, dev = r["case"], r["eng"], r["device"]
     feats_d = r["feats"].to(dev)

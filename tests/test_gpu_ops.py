@@ -94,11 +94,13 @@ def _attention_ref(q, k, v, heads, mask=None, geometry=None, mem_k=None, mem_v=N
     return (att @ vh).permute(0, 2, 1, 3).reshape(b, nq, hd)
 
 
-@pytest.mark.parametrize("variant", ["sdpa", "geometry", "memory", "causal", "cross"])
+@pytest.mark.parametrize("variant", ["sdpa", "geometry", "memory", "causal", "cross", "wide", "long_q"])
 def test_attention_variants(device, variant):
+    """sdpa/geometry/causal/cross: <= 64 keys and memory: 90 keys (tensor-core kernel, 8- and 16-tile forms);
+    wide: 150 keys (CUDA-core kernel); long_q: 130 queries (several 64-row tiles, ragged last tile)."""
     g = torch.Generator().manual_seed(5)
-    b, h, n = 5, 8, 50
-    nq = {"causal": 20, "cross": 7}.get(variant, n)
+    b, h, n = 5, 8, {"wide": 150, "long_q": 99}.get(variant, 50)
+    nq = {"causal": 20, "cross": 7, "long_q": 130}.get(variant, n)
     nk = 20 if variant == "causal" else n
     q = _bf(torch.randn(b, nq, h * 64, generator=g))
     k = _bf(torch.randn(b, nk, h * 64, generator=g))
