@@ -160,7 +160,7 @@ int cap_beam_reset(cap_beam* h, int batch, int bos_idx, cap_stream_t stream);
 int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, int is_logprob,
                   cap_stream_t stream);
 /* Vocabulary projection with log-softmax statistics: logits (M, ld) fp32 are stored once and, for every
- * row and every 32-column chunk, part_ms[row][chunk] = (max, sum exp(x - max)); *chunks_out = 4*ceil(N/128).
+ * row and every 32-column chunk, part_ms[row][chunk] = (max, sum exp(x - max)); *chunks_out = 8*ceil(N/256).
  * Replaces decoders.py:121-123 (fc + log_softmax) together with cap_beam_step_stats. */
 int cap_vocab_logits_stats(const void* x, int ldx, const void* w, const float* bias, float* logits,
                            int ld, int M, int N, int K, float* part_ms, int* chunks_out,

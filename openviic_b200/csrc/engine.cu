@@ -421,7 +421,7 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->buf_y32, rows_max * static_cast<size_t>(std::max(2 * d, hd))));
     e->ld_logits = (m.vocab + 7) / 8 * 8;
     CAP_PROPAGATE(dev_alloc(e, &e->logits, R * e->ld_logits));
-    e->vocab_chunks = ((m.vocab + 127) / 128) * 4;
+    e->vocab_chunks = ((m.vocab + 255) / 256) * 8;
     CAP_PROPAGATE(dev_alloc(e, &e->part_ms, R * e->vocab_chunks * 2));
     CAP_PROPAGATE(dev_alloc(e, &e->out_ids, R * T));
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));

@@ -258,13 +258,17 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tcgen05_fence_after();
         {
         // All MMAs have retired, so the pipeline stages are free: reuse them as the output staging tile.
+        // Tiles wider than 128 columns go through the staging buffer in 128-column passes.
+        constexpr int EPI_N = BLOCK_N < 128 ? BLOCK_N : 128;
         const int esz = p.out_f32 ? 4 : 2;
-        const int row_bytes = BLOCK_N * esz;
+        const int row_bytes = EPI_N * esz;
         const int pitch = row_bytes + 16;     // +16 B: consecutive rows start one bank group apart
         uint8_t* stage_out = smem + static_cast<size_t>(quad * 32) * pitch;
         uint8_t* my_row = stage_out + static_cast<size_t>(lane) * pitch;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int h0 = 0; h0 < BLOCK_N; h0 += EPI_N) {
+#pragma unroll 1
+        for (int c0 = h0; c0 < h0 + EPI_N; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
             tmem_ld_wait();
@@ -297,17 +301,17 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (p.out_f32) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(my_row + (c0 + j) * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    *reinterpret_cast<float4*>(my_row + (c0 - h0 + j) * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(my_row + (c0 + j) * 2) = pack8(f + j);
+                for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(my_row + (c0 - h0 + j) * 2) = pack8(f + j);
             }
         }
         __syncwarp();
         // write-out: each warp owns its 32 rows; lanes tile a row with 16-byte vectors
         const int vecs_per_row = row_bytes / 16;
         const int elems_per_vec = 16 / esz;
-        const int n_valid = min(BLOCK_N, p.N - n0);                 // valid columns of this tile
+        const int n_valid = min(EPI_N, p.N - (n0 + h0));            // valid columns of this pass
         uint8_t* gout = reinterpret_cast<uint8_t*>(p.out);
         for (int idx = lane; idx < 32 * vecs_per_row; idx += 32) {
             const int rr = idx / vecs_per_row, vv = idx % vecs_per_row;
@@ -315,7 +319,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int col = vv * elems_per_vec;
             if (grow >= p.M || col >= n_valid) continue;
             const uint8_t* src = stage_out + static_cast<size_t>(rr) * pitch + vv * 16;
-            uint8_t* dst = gout + (static_cast<size_t>(grow) * p.ldo + n0 + col) * esz;
+            uint8_t* dst = gout + (static_cast<size_t>(grow) * p.ldo + n0 + h0 + col) * esz;
             if (p.vec_ok && col + elems_per_vec <= n_valid) {
                 *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(src);
             } else {  // ragged last tile or unaligned output: element-wise
@@ -327,6 +331,8 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
             }
         }
+        __syncwarp();  // the next pass overwrites the staging rows
+        }  // 128-column passes
         }
     }
     if (warp == 2 && lane == 0) stamp(p, 6);
@@ -377,7 +383,8 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
 template <int BLOCK_N, bool STATS = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
     constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
-    const uint32_t staging = BLOCK_M * (BLOCK_N * (p.out_f32 ? 4 : 2) + 16);
+    constexpr int epi_n = BLOCK_N < 128 ? BLOCK_N : 128;
+    const uint32_t staging = BLOCK_M * (epi_n * (p.out_f32 ? 4 : 2) + 16);
     uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
     if (pipe < staging) pipe = (staging + 1023) / 1024 * 1024;
     p.pipe_bytes = pipe;
@@ -425,10 +432,12 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
         // Widest tile that N fills: with several batches pipelined on separate streams the SMs are kept
         // busy by other kernels, so total L2->smem fill traffic (A is re-read once per N tile) matters
         // more than the CTA count of one GEMM (measured: +8.6 % captions/s vs. "at least one wave").
-        bn = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
+        // 128x256 tiles pay off when the grid still fills the GPU (encoder, vocabulary: measured 690-820 vs
+        // 510-730 TFLOP/s); for the small decode GEMMs 128-wide tiles gave the better end-to-end rate.
+        bn = (N >= 256 && tiles_m >= 32) ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : 32));
         (void)tiles_m;
     }
-    CAP_REQUIRE(bn == 32 || bn == 64 || bn == 128, "cap_linear: unsupported BLOCK_N %d", bn);
+    CAP_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "cap_linear: unsupported BLOCK_N %d", bn);
 
     GemmParams p;
     p.out = y;
@@ -441,7 +450,7 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     p.act = act;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     // short K loops (<= 8 blocks) get a 2-deep ring: less smem per CTA, more CTAs of concurrent kernels per SM
-    int stages = forced_stages ? forced_stages : (bn == 128 ? (num_kb <= 8 ? 2 : 3) : 4);
+    int stages = forced_stages ? forced_stages : (bn == 256 ? 2 : (bn == 128 ? (num_kb <= 8 ? 2 : 3) : 4));
     if (stages > num_kb) stages = num_kb;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 1) stages = 1;
@@ -455,6 +464,7 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, bn));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (bn) {
+        case 256: return launch_gemm<256>(ta, tb, p, s);
         case 128: return launch_gemm<128>(ta, tb, p, s);
         case 64: return launch_gemm<64>(ta, tb, p, s);
         default: return launch_gemm<32>(ta, tb, p, s);
@@ -476,15 +486,15 @@ extern "C" int cap_vocab_logits_stats(const void* x, int ldx, const void* w, con
     p.out_f32 = 1;
     p.act = CAP_ACT_NONE;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-    p.num_stages = num_kb < 3 ? num_kb : 3;
+    p.num_stages = num_kb < 2 ? num_kb : 2;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) && (ld % 4 == 0);
     p.part_ms = part_ms;
     p.trace = g_gemm_trace;
-    if (chunks_out) *chunks_out = ((N + 127) / 128) * 4;
+    if (chunks_out) *chunks_out = ((N + 255) / 256) * 8;
     CUtensorMap ta, tb;
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
-    CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));
-    return launch_gemm<128, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 256));
+    return launch_gemm<256, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cap_debug_gemm_trace(unsigned long long* device_buffer) {

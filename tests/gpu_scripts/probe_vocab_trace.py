@@ -26,7 +26,7 @@ def main():
     x = torch.randn(R, d, device=dev).to(torch.bfloat16)
     w = (torch.randn(V, d, device=dev) * 0.13).to(torch.bfloat16)
     ld = (V + 7) // 8 * 8
-    chunks = ((V + 127) // 128) * 4
+    chunks = ((V + 255) // 256) * 8
     logits = torch.empty(R, ld, device=dev)
     pm = torch.empty(R, chunks, 2, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -144,7 +144,7 @@ def test_vocab_stats_epilogue_matches_full_row_pass(device, B, beam, V):
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     lib = cabi.load_library()
     ld = (V + 7) // 8 * 8
-    chunks = ((V + 127) // 128) * 4
+    chunks = ((V + 255) // 256) * 8
     logits = torch.empty(R, ld, device=device)
     part_ms = torch.empty(R, chunks, 2, device=device)
     results = []
