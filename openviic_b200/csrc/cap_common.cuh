@@ -51,22 +51,34 @@ int cap_set_error(int code, const char* fmt, ...);
 bool cap_pdl_enabled();
 
 template <typename Kernel, typename... Args>
-inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cap_pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {  // thread-block cluster along x (CTA pairs of the 2-CTA GEMM)
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = cap_pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 #define CAP_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    cap_launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+    cap_launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__)
 
 static inline int cap_check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

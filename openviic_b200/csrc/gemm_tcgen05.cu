@@ -21,7 +21,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, each drains half the columns
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
@@ -137,6 +138,61 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- cta_group::2 forms: a pair of CTAs (one cluster, adjacent SMs) works on one 256-row tile ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Both CTAs load into their own smem but signal the LEADER's mbarrier (peer bit of the shared-window address
+// cleared), so one barrier phase covers the four tiles of a stage.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
+                                                int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have retired
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -163,12 +219,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // for each 32-column chunk.  beam_rowmerge_kernel (beam.cu) turns those into the row's log-sum-exp and
 // reads only the `beam` chunks with the largest maxima -- the row's top-`beam` logits provably lie there --
 // so the 52 MB logits buffer is written once and almost never read back.
-template <int BLOCK_N, bool STATS>
+//
+// CTA2: two CTAs of one cluster (adjacent M tiles, same N tile) form a pair; each loads its own 128 A rows
+// and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) reading both shared memories,
+// and every CTA drains its own 128 accumulator rows.  Per CTA the smem fill per k-block drops from
+// 16 + BLOCK_N/8 KB to 16 + BLOCK_N/16 KB for the same MMA work.
+template <int BLOCK_N, bool STATS, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
     pdl_launch_dependents();  // the next kernel may start its prologue now
-    constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // B rows this CTA stages
+    constexpr uint32_t B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 
@@ -183,8 +245,14 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BLOCK_M;
-    const int n0 = blockIdx.x * BLOCK_N;
+    // 1-CTA: grid (n tiles, m tiles).  2-CTA: grid (m tiles rounded up to even, n tiles), cluster (2,1,1).
+    const int m_tile = CTA2 ? blockIdx.x : blockIdx.y;
+    const int n_tile = CTA2 ? blockIdx.y : blockIdx.x;
+    const int n_tiles = CTA2 ? gridDim.y : gridDim.x;
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int m0 = m_tile * BLOCK_M;
+    const int n0 = n_tile * BLOCK_N;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
     if (threadIdx.x == 0) stamp(p, 0);
@@ -202,10 +270,10 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        tmem_alloc<TMEM_COLS>(tmem_slot);
+        if constexpr (CTA2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot);
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync(); else __syncthreads();  // barriers of BOTH CTAs initialised before use
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(p, 1);
@@ -218,15 +286,22 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(&empty_bar[s], phase ^ 1);
                 uint8_t* a_tile = smem + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
-                tma_load_2d(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+                if constexpr (CTA2) {
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // both CTAs' four tiles
+                    tma_load_2d_2sm(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+                    tma_load_2d_2sm(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K,
+                                    n0 + static_cast<int>(rank) * B_ROWS);
+                } else {
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+                    tma_load_2d(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+                }
                 if (kb == 0) stamp(p, 2);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_instr_desc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
@@ -239,20 +314,26 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                     // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                    umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if constexpr (CTA2)
+                        umma_bf16_2sm(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    else
+                        umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+                // stage reusable (in both CTAs) once these MMAs have read it
+                if constexpr (CTA2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
             }
-            umma_commit(tmem_full_bar);  // accumulator complete
+            // accumulator complete (in both CTAs)
+            if constexpr (CTA2) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
             stamp(p, 4);
         }
     } else {
         // ---- epilogue: TMEM -> registers -> (+bias, activation) -> smem transpose -> coalesced rows ----
         const int quad = warp & 3;            // TMEM lane quadrant this warp may read
-        const int etid = threadIdx.x - 64;    // 0..127 among the epilogue threads
-        for (int i = etid; i < BLOCK_N; i += 128)
+        const int half = (warp - 2) >> 2;     // which half of each column pass this warp drains (0 or 1)
+        const int etid = threadIdx.x - 64;    // 0..255 among the epilogue threads
+        for (int i = etid; i < BLOCK_N; i += EPI_WARPS * 32)
             s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // bias tile visible to the 4 epilogue warps
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // bias tile visible to the epilogue warps
         mbar_wait(tmem_full_bar, 0);
         if (warp == 2 && lane == 0) stamp(p, 5);
         tcgen05_fence_after();
@@ -267,8 +348,9 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         uint8_t* my_row = stage_out + static_cast<size_t>(lane) * pitch;
 #pragma unroll 1
         for (int h0 = 0; h0 < BLOCK_N; h0 += EPI_N) {
+        // the two warps of a quadrant split the pass: 32-column chunks alternate between them
 #pragma unroll 1
-        for (int c0 = h0; c0 < h0 + EPI_N; c0 += 32) {
+        for (int c0 = h0 + 32 * half; c0 < h0 + EPI_N; c0 += 64) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
             tmem_ld_wait();
@@ -292,8 +374,8 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     for (int j = 0; j < 32; ++j) cs += j < valid ? __expf(f[j] - cm) : 0.f;
                 }
                 if (grow < p.M) {
-                    const size_t chunk = static_cast<size_t>(blockIdx.x) * (BLOCK_N / 32) + c0 / 32;
-                    const size_t chunks = static_cast<size_t>(gridDim.x) * (BLOCK_N / 32);
+                    const size_t chunk = static_cast<size_t>(n_tile) * (BLOCK_N / 32) + c0 / 32;
+                    const size_t chunks = static_cast<size_t>(n_tiles) * (BLOCK_N / 32);
                     *reinterpret_cast<float2*>(p.part_ms + (static_cast<size_t>(grow) * chunks + chunk) * 2) =
                         make_float2(cm, cs);
                 }
@@ -307,13 +389,14 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(my_row + (c0 - h0 + j) * 2) = pack8(f + j);
             }
         }
-        __syncwarp();
-        // write-out: each warp owns its 32 rows; lanes tile a row with 16-byte vectors
+        // both warps of the quadrant have staged their chunks (named barrier 2+quad, 64 threads)
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        // write-out: the quadrant's 32 rows are split between its two warps; lanes tile a row with 16-byte vectors
         const int vecs_per_row = row_bytes / 16;
         const int elems_per_vec = 16 / esz;
         const int n_valid = min(EPI_N, p.N - (n0 + h0));            // valid columns of this pass
         uint8_t* gout = reinterpret_cast<uint8_t*>(p.out);
-        for (int idx = lane; idx < 32 * vecs_per_row; idx += 32) {
+        for (int idx = half * 16 * vecs_per_row + lane; idx < (half + 1) * 16 * vecs_per_row; idx += 32) {
             const int rr = idx / vecs_per_row, vv = idx % vecs_per_row;
             const int grow = m0 + quad * 32 + rr;
             const int col = vv * elems_per_vec;
@@ -331,16 +414,16 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
             }
         }
-        __syncwarp();  // the next pass overwrites the staging rows
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");  // the next pass overwrites the staging rows
         }  // 128-column passes
         }
     }
     if (warp == 2 && lane == 0) stamp(p, 6);
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync(); else __syncthreads();  // both epilogues done before TMEM is released
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        if constexpr (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
     }
     if (threadIdx.x == 32) stamp(p, 7);
 }
@@ -380,9 +463,9 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
     return CAP_OK;
 }
 
-template <int BLOCK_N, bool STATS = false>
+template <int BLOCK_N, bool STATS = false, bool CTA2 = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
-    constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t stage_bytes = A_TILE_BYTES + (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
     constexpr int epi_n = BLOCK_N < 128 ? BLOCK_N : 128;
     const uint32_t staging = BLOCK_M * (epi_n * (p.out_f32 ? 4 : 2) + 16);
     uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
@@ -392,13 +475,19 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N, STATS>,
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
         attr_smem = 200 * 1024;
     }
-    dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
-    CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
+    const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    if constexpr (CTA2) {
+        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2>, dim3((tiles_m + 1) / 2 * 2, tiles_n),
+                          dim3(GEMM_THREADS), smem, stream, /*cluster_x=*/2, ta, tb, p);
+    } else {
+        dim3 grid(tiles_n, tiles_m);
+        CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
+    }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_bf16_tcgen05");
 }
@@ -463,6 +552,13 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, bn));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static const bool use_2cta = env_int("OPENVIIC_GEMM_2CTA", 1) != 0;
+    if (bn == 256 && use_2cta) {
+        CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));  // each CTA of the pair stages half of the B tile
+        p.num_stages = forced_stages ? forced_stages : 3;
+        if (p.num_stages > num_kb) p.num_stages = num_kb;
+        return launch_gemm<256, false, true>(ta, tb, p, s);
+    }
     switch (bn) {
         case 256: return launch_gemm<256>(ta, tb, p, s);
         case 128: return launch_gemm<128>(ta, tb, p, s);
@@ -493,6 +589,12 @@ extern "C" int cap_vocab_logits_stats(const void* x, int ldx, const void* w, con
     if (chunks_out) *chunks_out = ((N + 255) / 256) * 8;
     CUtensorMap ta, tb;
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
+    static const bool use_2cta = env_int("OPENVIIC_GEMM_2CTA", 1) != 0;
+    if (use_2cta) {
+        p.num_stages = num_kb < 3 ? num_kb : 3;
+        CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));
+        return launch_gemm<256, true, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    }
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 256));
     return launch_gemm<256, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }
