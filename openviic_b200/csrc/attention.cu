@@ -598,6 +598,131 @@ decode_cross_attention_wide_kernel(const bf16* __restrict__ q, int ldq, const bf
     }
 }
 
+// Decode-step cross-attention, bulk-staged variant (H = 8, n*2 KB fits shared memory): one CTA per image.
+// The image's whole K|V block is contiguous in HBM, so thread 0 streams it into shared memory with a few
+// cp.async.bulk copies (no registers, the full block in flight at once, one mbarrier per chunk); warp b
+// then serves beam b over all keys straight from shared memory (lanes tile the 512-wide rows, 4 lanes per
+// head, online softmax) while later chunks are still landing.  Every K/V byte crosses HBM once per step.
+constexpr int XS_CHUNKS = 4;
+
+__device__ __forceinline__ uint32_t xs_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+template <int BEAMS>
+__global__ void __launch_bounds__(BEAMS * 32)
+decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
+                                   const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
+                                   float scale) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) uint8_t xs_smem[];
+    __shared__ __align__(8) uint64_t bars[XS_CHUNKS];
+    constexpr int hd = 32 * XW_EPL;          // 512
+    constexpr int ROW_BYTES = 2 * hd * 2;    // K|V row of one key: 2 KB
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows_per_chunk = (n + XS_CHUNKS - 1) / XS_CHUNKS;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < XS_CHUNKS; ++c)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs_smem_u32(&bars[c])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // K/V were projected at encode time, many kernels ago: safe to fetch before the PDL wait below
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + static_cast<size_t>(b) * n * ROW_BYTES;
+#pragma unroll
+        for (int c = 0; c < XS_CHUNKS; ++c) {
+            const int r0 = c * rows_per_chunk;
+            const int rows = min(rows_per_chunk, n - r0);
+            const uint32_t bytes = rows > 0 ? static_cast<uint32_t>(rows) * ROW_BYTES : 0u;
+            const uint32_t bar = xs_smem_u32(&bars[c]);
+            if (bytes) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        xs_smem_u32(xs_smem + static_cast<size_t>(r0) * ROW_BYTES)),
+                    "l"(reinterpret_cast<uint64_t>(src + static_cast<size_t>(r0) * ROW_BYTES)), "r"(bytes), "r"(bar)
+                    : "memory");
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            }
+        }
+    }
+    pdl_wait();  // q comes from the previous kernel
+    __syncthreads();  // barrier inits visible to every waiter
+
+    const int row = b * BEAMS + warp;
+    float qf[XW_EPL];
+    {
+        const bf16x8* qp = reinterpret_cast<const bf16x8*>(q + static_cast<size_t>(row) * ldq + lane * XW_EPL);
+        unpack8(qp[0], qf);
+        unpack8(qp[1], qf + 8);
+#pragma unroll
+        for (int i = 0; i < XW_EPL; ++i) qf[i] *= scale;
+    }
+    const uint8_t* mrow = key_mask ? key_mask + static_cast<size_t>(b) * n : nullptr;
+    float m = -INFINITY, l = 0.f, acc[XW_EPL];
+#pragma unroll
+    for (int i = 0; i < XW_EPL; ++i) acc[i] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < XS_CHUNKS; ++c) {
+        const int r0 = c * rows_per_chunk;
+        const int r1 = min(r0 + rows_per_chunk, n);
+        if (r0 >= r1) break;
+        {   // wait for this chunk (phase 0); bounded spin
+            const uint32_t bar = xs_smem_u32(&bars[c]);
+            uint32_t done = 0;
+            for (uint32_t spin = 0; !done; ++spin) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(done) : "r"(bar) : "memory");
+                if (spin > (1u << 26)) __trap();
+            }
+        }
+        for (int j = r0; j < r1; ++j) {
+            if (mrow && mrow[j]) continue;  // warp-uniform
+            const bf16x8* kp = reinterpret_cast<const bf16x8*>(xs_smem + static_cast<size_t>(j) * ROW_BYTES) + lane * 2;
+            const bf16x8* vp = kp + hd / 8;
+            float kf[XW_EPL], vf[XW_EPL];
+            unpack8(kp[0], kf);
+            unpack8(kp[1], kf + 8);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < XW_EPL; ++i) s = fmaf(qf[i], kf[i], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            unpack8(vp[0], vf);
+            unpack8(vp[1], vf + 8);
+            const float m_new = fmaxf(m, s);
+            const float corr = __expf(m - m_new);
+            const float p = __expf(s - m_new);
+            l = l * corr + p;
+#pragma unroll
+            for (int i = 0; i < XW_EPL; ++i) acc[i] = acc[i] * corr + p * vf[i];
+            m = m_new;
+        }
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    float o[XW_EPL];
+#pragma unroll
+    for (int i = 0; i < XW_EPL; ++i) o[i] = acc[i] * inv;
+    bf16* orow = out + static_cast<size_t>(row) * ldo + lane * XW_EPL;
+    reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
+    reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
+}
+
+template <int BEAMS>
+int launch_cross_smem(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
+                      float scale, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(n) * 2048;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_smem_kernel<BEAMS>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        attr_done = true;
+    }
+    CAP_LAUNCH((decode_cross_attention_smem_kernel<BEAMS>), B, BEAMS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n,
+               scale);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_cross_attention_smem_kernel");
+}
+
 template <int BEAMS>
 int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
                       float scale, cudaStream_t stream) {
@@ -677,6 +802,16 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
         const bf16* kvp = static_cast<const bf16*>(kv);
         bf16* op = static_cast<bf16*>(out);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        static const bool no_bulk = getenv("OPENVIIC_CROSS_NO_BULK") != nullptr;
+        if (!no_bulk && static_cast<size_t>(n) * 2048 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
+            switch (beam) {  // bulk-staged variant: the image's K|V block lives in shared memory
+                case 1: return launch_cross_smem<1>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+                case 2: return launch_cross_smem<2>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+                case 3: return launch_cross_smem<3>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+                case 4: return launch_cross_smem<4>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+                default: return launch_cross_smem<5>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
+            }
+        }
         switch (beam) {
             case 1: return launch_cross_wide<1>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
             case 2: return launch_cross_wide<2>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
