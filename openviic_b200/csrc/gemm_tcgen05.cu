@@ -9,6 +9,7 @@
 //
 // Replaces every nn.Linear on the caption path (see include/openviic_cap.h: cap_linear).
 #include "cap_common.cuh"
+#include "tcgen05_ptx.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -18,9 +19,7 @@ extern std::atomic<long long> g_cap_launches;
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int UMMA_K = 16;
+using namespace cap_ptx;
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, each drains half the columns
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int MAX_STAGES = 8;
@@ -33,6 +32,15 @@ struct GemmParams {
     int out_f32, act, num_stages, vec_ok;
     uint32_t pipe_bytes;  // bytes reserved for the stage ring (>= the epilogue's staging tile), multiple of 1024
     float* part_ms;       // STATS epilogue: [M][chunks][2] (max, sum exp(x - max)) per 32-column chunk
+    // LN epilogue (cluster of N/128 CTAs along N): out = LayerNorm(residual + x.w^T + bias) * gamma + beta (+pos)
+    const float* ln_gamma;
+    const float* ln_beta;
+    const float* residual;   // fp32 [M][ldr] or nullptr
+    const float* pos;        // fp32 [pos_rows][N] or nullptr
+    const uint8_t* zero_rows;  // uint8 [M] or nullptr: rows written as zeros
+    float* out32;            // fp32 copy [M][ldo32] or nullptr (`out` is the bf16 copy or nullptr)
+    int ldr, ldo32, pos_rows;
+    float eps;
     unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (cap_debug_gemm_trace), else nullptr
 };
 
@@ -43,170 +51,6 @@ __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
         p.trace[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = t;
     }
 }
-
-// ----------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-
-// Bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    long long start = 0;
-    for (uint32_t spin = 0;; ++spin) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (spin == 64) start = clock64();
-        if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
-                                            int c_outer) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner),
-        "r"(c_outer)
-        : "memory");
-}
-
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 bytes apart (SBO),
-// LBO unused for swizzled K-major, descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
-    uint64_t desc = 0;
-    desc |= static_cast<uint64_t>((smem_u32(tile) & 0x3FFFF) >> 4);  // [0,14)  start address
-    desc |= static_cast<uint64_t>(1) << 16;                          // [16,30) leading byte offset (ignored)
-    desc |= static_cast<uint64_t>(1024 >> 4) << 32;                  // [32,46) stride byte offset
-    desc |= static_cast<uint64_t>(1) << 46;                          // [46,48) version
-    desc |= static_cast<uint64_t>(2) << 61;                          // [61,64) SWIZZLE_128B
-    return desc;
-}
-
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, shape M x N.
-__host__ __device__ constexpr uint32_t make_instr_desc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-// ---- cta_group::2 forms: a pair of CTAs (one cluster, adjacent SMs) works on one 256-row tile ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-__device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// Both CTAs load into their own smem but signal the LEADER's mbarrier (peer bit of the shared-window address
-// cleared), so one barrier phase covers the four tiles of a stage.
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
-                                                int c_outer) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-        "[%2];" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
-        : "memory");
-}
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-// arrive on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have retired
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"(static_cast<uint16_t>(3))
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == CAP_ACT_RELU) return fmaxf(v, 0.f);
@@ -224,7 +68,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) reading both shared memories,
 // and every CTA drains its own 128 accumulator rows.  Per CTA the smem fill per k-block drops from
 // 16 + BLOCK_N/8 KB to 16 + BLOCK_N/16 KB for the same MMA work.
-template <int BLOCK_N, bool STATS, bool CTA2>
+//
+// LN (BLOCK_N = 128, 1-CTA MMA): the N/128 CTAs of one row tile form a cluster along N; the epilogue adds
+// bias and the fp32 residual, keeps the tile in shared memory, exchanges per-row sums and centred sums of
+// squares with its cluster peers through distributed shared memory (two cluster barriers), normalises and
+// writes a bf16 copy (next GEMM operand) and an fp32 copy (next residual).  One kernel instead of
+// GEMM -> fp32 round trip -> LayerNorm kernel.
+template <int BLOCK_N, bool STATS, bool CTA2, bool LN = false>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
@@ -299,6 +149,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 if (kb == 0) stamp(p, 2);
             }
         }
+        if constexpr (LN) { __syncwarp(); cluster_sync(); cluster_sync(); }  // the epilogue's two exchanges
     } else if (warp == 1) {
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = make_instr_desc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
@@ -326,6 +177,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if constexpr (CTA2) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
             stamp(p, 4);
         }
+        if constexpr (LN) { __syncwarp(); cluster_sync(); cluster_sync(); }
     } else {
         // ---- epilogue: TMEM -> registers -> (+bias, activation) -> smem transpose -> coalesced rows ----
         const int quad = warp & 3;            // TMEM lane quadrant this warp may read
@@ -333,11 +185,106 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int etid = threadIdx.x - 64;    // 0..255 among the epilogue threads
         for (int i = etid; i < BLOCK_N; i += EPI_WARPS * 32)
             s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        float* s_gamma = s_bias + BLOCK_N;          // LN only: gamma | beta | row sums [2][128] | row sq [2][128]
+        float* s_beta = s_gamma + BLOCK_N;
+        float* s_sum = s_beta + BLOCK_N;
+        float* s_sq = s_sum + 2 * BLOCK_M;
+        if constexpr (LN) {
+            for (int i = etid; i < BLOCK_N; i += EPI_WARPS * 32) {
+                s_gamma[i] = __ldg(p.ln_gamma + n0 + i);
+                s_beta[i] = __ldg(p.ln_beta + n0 + i);
+            }
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // bias tile visible to the epilogue warps
         mbar_wait(tmem_full_bar, 0);
         if (warp == 2 && lane == 0) stamp(p, 5);
         tcgen05_fence_after();
-        {
+        if constexpr (LN) {
+            pdl_wait();  // residual / zero_rows were written by earlier kernels
+            constexpr int PITCH = BLOCK_N * 4 + 16;
+            const int trow = quad * 32 + lane;
+            const int grow = m0 + trow;
+            const bool row_ok = grow < p.M;
+            const uint32_t cluster_n = static_cast<uint32_t>(n_tiles);
+            float* my_row = reinterpret_cast<float*>(smem + static_cast<size_t>(trow) * PITCH);
+            const float* rrow = (p.residual != nullptr && row_ok) ? p.residual + static_cast<size_t>(grow) * p.ldr + n0 : nullptr;
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c0 = 32 * half; c0 < BLOCK_N; c0 += 64) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + c0 + j);
+                    float4 y;
+                    y.x = __uint_as_float(v[j]) + s_bias[c0 + j] + r4.x;
+                    y.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1] + r4.y;
+                    y.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2] + r4.z;
+                    y.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3] + r4.w;
+                    sum += (y.x + y.y) + (y.z + y.w);
+                    *reinterpret_cast<float4*>(my_row + c0 + j) = y;
+                }
+            }
+            s_sum[half * BLOCK_M + trow] = sum;
+            cluster_sync();  // #1: every CTA of the row tile has published its partial row sums
+            float tot = 0.f;
+            for (uint32_t rk = 0; rk < cluster_n; ++rk)
+                tot += ld_dsmem_f32(s_sum + trow, rk) + ld_dsmem_f32(s_sum + BLOCK_M + trow, rk);
+            const float mean = tot / static_cast<float>(p.N);
+            float sq = 0.f;
+#pragma unroll 1
+            for (int c0 = 32 * half; c0 < BLOCK_N; c0 += 64) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 y = *reinterpret_cast<const float4*>(my_row + c0 + j);
+                    const float a0 = y.x - mean, a1 = y.y - mean, a2 = y.z - mean, a3 = y.w - mean;
+                    sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                }
+            }
+            s_sq[half * BLOCK_M + trow] = sq;
+            cluster_sync();  // #2
+            float vs = 0.f;
+            for (uint32_t rk = 0; rk < cluster_n; ++rk)
+                vs += ld_dsmem_f32(s_sq + trow, rk) + ld_dsmem_f32(s_sq + BLOCK_M + trow, rk);
+            const float rstd = rsqrtf(vs / static_cast<float>(p.N) + p.eps);
+            const bool zero = p.zero_rows != nullptr && row_ok && p.zero_rows[grow] != 0;
+            const float* prow = (p.pos != nullptr && row_ok)
+                                    ? p.pos + static_cast<size_t>(grow % p.pos_rows) * p.N + n0 : nullptr;
+#pragma unroll 1
+            for (int c0 = 32 * half; c0 < BLOCK_N; c0 += 64) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 y = *reinterpret_cast<const float4*>(my_row + c0 + j);
+                    float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (prow) pp = *reinterpret_cast<const float4*>(prow + c0 + j);
+                    y.x = (y.x - mean) * rstd * s_gamma[c0 + j] + s_beta[c0 + j] + pp.x;
+                    y.y = (y.y - mean) * rstd * s_gamma[c0 + j + 1] + s_beta[c0 + j + 1] + pp.y;
+                    y.z = (y.z - mean) * rstd * s_gamma[c0 + j + 2] + s_beta[c0 + j + 2] + pp.z;
+                    y.w = (y.w - mean) * rstd * s_gamma[c0 + j + 3] + s_beta[c0 + j + 3] + pp.w;
+                    if (zero) y = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(my_row + c0 + j) = y;
+                }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");  // both halves of the quadrant normalised
+            // coalesced write-out of the quadrant's 32 rows (16 per warp): 4 columns per lane-vector
+            constexpr int VECS = BLOCK_N / 4;
+            for (int idx = half * 16 * VECS + lane; idx < (half + 1) * 16 * VECS; idx += 32) {
+                const int rr = idx / VECS, vv = idx % VECS;
+                const int orow = m0 + quad * 32 + rr;
+                if (orow >= p.M) continue;
+                const float4 y = *reinterpret_cast<const float4*>(smem + static_cast<size_t>(quad * 32 + rr) * PITCH + vv * 16);
+                const size_t col = static_cast<size_t>(n0) + vv * 4;
+                if (p.out32 != nullptr) *reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(orow) * p.ldo32 + col) = y;
+                if (p.out != nullptr) {
+                    uint2 packed;
+                    packed.x = *reinterpret_cast<const uint32_t*>(&static_cast<const bf162&>(__floats2bfloat162_rn(y.x, y.y)));
+                    packed.y = *reinterpret_cast<const uint32_t*>(&static_cast<const bf162&>(__floats2bfloat162_rn(y.z, y.w)));
+                    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col) = packed;
+                }
+            }
+        } else {
         // All MMAs have retired, so the pipeline stages are free: reuse them as the output staging tile.
         // Tiles wider than 128 columns go through the staging buffer in 128-column passes.
         constexpr int EPI_N = BLOCK_N < 128 ? BLOCK_N : 128;
@@ -420,7 +367,8 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     if (warp == 2 && lane == 0) stamp(p, 6);
     tcgen05_fence_before();
-    if constexpr (CTA2) cluster_sync(); else __syncthreads();  // both epilogues done before TMEM is released
+    // 2-CTA: both epilogues done before TMEM is released; LN: no CTA leaves while peers may read its statistics
+    if constexpr (CTA2 || LN) cluster_sync(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
         if constexpr (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -463,7 +411,7 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
     return CAP_OK;
 }
 
-template <int BLOCK_N, bool STATS = false, bool CTA2 = false>
+template <int BLOCK_N, bool STATS = false, bool CTA2 = false, bool LN = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
     constexpr uint32_t stage_bytes = A_TILE_BYTES + (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
     constexpr int epi_n = BLOCK_N < 128 ? BLOCK_N : 128;
@@ -471,22 +419,25 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
     if (pipe < staging) pipe = (staging + 1023) / 1024 * 1024;
     p.pipe_bytes = pipe;
-    const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4;
+    const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
     static bool attr_set = false;
     static size_t attr_smem = 0;
     if (!attr_set || smem > attr_smem) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2>,
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
         attr_smem = 200 * 1024;
     }
     const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     if constexpr (CTA2) {
-        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2>, dim3((tiles_m + 1) / 2 * 2, tiles_n),
+        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, dim3((tiles_m + 1) / 2 * 2, tiles_n),
                           dim3(GEMM_THREADS), smem, stream, /*cluster_x=*/2, ta, tb, p);
+    } else if constexpr (LN) {  // the tiles_n CTAs of a row tile form one cluster along x
+        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, dim3(tiles_n, tiles_m), dim3(GEMM_THREADS), smem,
+                          stream, /*cluster_x=*/tiles_n, ta, tb, p);
     } else {
         dim3 grid(tiles_n, tiles_m);
-        CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
+        CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_bf16_tcgen05");
@@ -565,6 +516,39 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
         case 64: return launch_gemm<64>(ta, tb, p, s);
         default: return launch_gemm<32>(ta, tb, p, s);
     }
+}
+
+// out = LayerNorm(residual + x.w^T + bias) * gamma + beta (+pos), rows in zero_rows zeroed -- one kernel.
+extern "C" int cap_linear_layernorm(const void* x, int ldx, const void* w, const float* bias, const float* residual,
+                                    int ldr, const float* gamma, const float* beta, float eps, const float* pos,
+                                    int pos_rows, const uint8_t* zero_rows, void* out_bf16, int ldo, float* out_f32,
+                                    int ldo32, int M, int N, int K, cap_stream_t stream) {
+    CAP_REQUIRE(x && w && gamma && beta && (out_bf16 || out_f32), "cap_linear_layernorm: null pointer");
+    CAP_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldx >= K, "cap_linear_layernorm: bad shape");
+    CAP_REQUIRE(N % 128 == 0 && N >= 128 && N <= 1024, "cap_linear_layernorm: N=%d must be 128..1024 in steps of 128", N);
+    CAP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                "cap_linear_layernorm: x and w must be 16-byte aligned");
+    CAP_REQUIRE((!residual || (ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0)) &&
+                    (!out_f32 || (ldo32 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0)) &&
+                    (!out_bf16 || (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0)) &&
+                    (!pos || (pos_rows > 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0)),
+                "cap_linear_layernorm: residual / outputs / pos must be vector-aligned");
+    GemmParams p = {};
+    p.out = out_bf16;
+    p.bias = bias;
+    p.M = M; p.N = N; p.K = K; p.ldo = ldo;
+    p.out_f32 = 1;  // the staging tile is fp32
+    p.act = CAP_ACT_NONE;
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    p.num_stages = num_kb <= 8 ? (num_kb < 2 ? num_kb : 2) : 3;
+    p.vec_ok = 1;
+    p.ln_gamma = gamma; p.ln_beta = beta; p.residual = residual; p.ldr = ldr; p.pos = pos; p.pos_rows = pos_rows;
+    p.zero_rows = zero_rows; p.out32 = out_f32; p.ldo32 = ldo32; p.eps = eps;
+    p.trace = g_gemm_trace;
+    CUtensorMap ta, tb;
+    CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
+    CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));
+    return launch_gemm<128, false, false, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }
 
 // Vocabulary projection: fp32 logits + per-32-column-chunk log-softmax statistics in one pass.
