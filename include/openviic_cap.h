@@ -71,6 +71,14 @@ int cap_add_layernorm(const void* y, int y_dtype, int ldy, const void* residual,
                       int ldr, const float* gamma, const float* beta, float eps, const float* pos,
                       int pos_rows, const uint8_t* zero_rows, void* out, int ldo, float* out_f32,
                       int ldo32, int rows, int d, cap_stream_t stream);
+/* Linear + residual + LayerNorm in ONE kernel: out = LayerNorm(residual + x.w^T + bias) * gamma + beta
+ * [+ pos[row % pos_rows]], zero_rows as above; N = 128..1024 in steps of 128.  The N/128 CTAs of a row tile
+ * form a thread-block cluster and exchange row statistics through distributed shared memory.
+ * Replaces fc_o / fc2 followed by attentions.py:308-309 / positionwise_feed_forward.py:26. */
+int cap_linear_layernorm(const void* x, int ldx, const void* w, const float* bias, const float* residual,
+                         int ldr, const float* gamma, const float* beta, float eps, const float* pos,
+                         int pos_rows, const uint8_t* zero_rows, void* out_bf16, int ldo, float* out_f32,
+                         int ldo32, int M, int N, int K, cap_stream_t stream);
 
 /* Visual-token padding mask + cast: mask[row] = (sum_k feats[row,k] == 0) (fp32 sum), and
  * out[row,:] = bf16(feats[row,:]).  feats fp32 or bf16.
@@ -177,6 +185,52 @@ const int32_t* cap_beam_tokens(cap_beam* h);    /* [R]    token each row consume
 const int32_t* cap_beam_ancestry(cap_beam* h);  /* [T][R] see cap_decode_self_attention      */
 const float* cap_beam_seq_logprob(cap_beam* h); /* [R]                                       */
 const int32_t* cap_beam_parents(cap_beam* h);   /* [R]    selected_beam of the last step     */
+
+/* ------------------------------------------------------------------------------------------
+ * Fused decode step (csrc/decode_fused.cu): ONE kernel per BaseTransformer.step of the standard
+ * Decoder (decoders.py:95-123 at nq = 1) -- every CTA carries a tile of 128 beam rows through
+ * embedding, all DecoderLayers (decoders.py:21-28) and the vocabulary projection with its
+ * log-softmax chunk statistics.  All pointers are DEVICE memory owned by the caller (the engine);
+ * the handle owns stacked copies of the weights and its scratch tiles.  Needs d_model 512, 8 heads,
+ * d_ff 2048, beam <= 5, bias-free vocabulary projection.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cap_fused_layer {
+    const void *w_qkv, *w_o1, *w_q, *w_o2, *w_fc1, *w_fc2; /* bf16 [out,in]: self q|k|v, self fc_o, cross fc_q, cross fc_o, fc1, fc2 */
+    const float *b_qkv, *b_o1, *ln1_g, *ln1_b;             /* self-attention biases + its LayerNorm */
+    const float *b_q, *b_o2, *ln2_g, *ln2_b;               /* cross-attention */
+    const float *b_fc1, *b_fc2, *ln3_g, *ln3_b;            /* feed-forward */
+} cap_fused_layer;
+
+typedef struct cap_fused_desc {
+    int d_model, heads, d_ff, n_layers, vocab, max_len, beam, pad_idx;
+    int max_rows;                 /* max_batch * beam */
+    const cap_fused_layer* layers;
+    const void* w_vocab;          /* bf16 [vocab, d_model] */
+    const void* word_emb;         /* bf16 [vocab, d_model] */
+    const float* word_pos;        /* fp32 [max_len + 1, d_model] */
+    const int32_t* tokens;        /* [R]    cap_beam_tokens */
+    const int32_t* ancestry;      /* [T][R] cap_beam_ancestry */
+    uint8_t* padflag;             /* [T][R] written at step t, read at later steps */
+    void* qkv_cache;              /* bf16 [layers][T][R][3*d_model] */
+    const void* cross_kv;         /* bf16, layer l at + l*cross_layer_stride elements: [B][n][K|V] */
+    size_t cross_layer_stride;
+    const uint8_t* enc_mask;      /* [B][n] key padding */
+    float* logits;                /* fp32 [R][ld_logits], ld_logits % 32 == 0 */
+    int ld_logits;
+    float* part_ms;               /* fp32 [R][8*ceil(vocab/256)][2] */
+} cap_fused_desc;
+
+typedef struct cap_fused_decoder cap_fused_decoder;
+int cap_fused_create(const cap_fused_desc* desc, cap_fused_decoder** out);
+int cap_fused_destroy(cap_fused_decoder* f);
+/* Step t for B images (R = B*beam rows, n_keys visual tokens): fills qkv_cache[.][t], padflag[t], logits and
+ * part_ms; follow with cap_beam_step_stats. */
+int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_keys, cap_stream_t stream);
+/* Debug: when non-NULL, every later fused step writes %globaltimer stamps (ns) of its phase boundaries into
+ * device_buffer[tile*64 + k]: 0 entry, 1 dependencies resolved, then per layer L at 2+8L: layer start,
+ * q|k|v stored, self-attention done, LN1 done, cross q stored, cross-attention done, LN2 done, hidden stored;
+ * 2+8*layers: last LN done, 3+8*layers: vocabulary epilogue done. */
+int cap_debug_fused_trace(unsigned long long* device_buffer);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-path engine: encoder_forward once + max_len decode steps (models/base_transformer.py:

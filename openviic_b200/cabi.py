@@ -74,6 +74,11 @@ SIGNATURES = {
     "cap_beam_ancestry": (_vp, [_vp]),
     "cap_beam_seq_logprob": (_vp, [_vp]),
     "cap_beam_parents": (_vp, [_vp]),
+    "cap_fused_create": (_i, [_vp, C.POINTER(_vp)]),
+    "cap_fused_destroy": (_i, [_vp]),
+    "cap_fused_decode_step": (_i, [_vp, _i, _i, _i, _vp]),
+    "cap_debug_fused_trace": (_i, [_vp]),
+    "cap_linear_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cap_engine_create": (_i, [C.POINTER(ModelDesc), C.POINTER(_vp)]),
     "cap_engine_destroy": (_i, [_vp]),
     "cap_engine_load_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),

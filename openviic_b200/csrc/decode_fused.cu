@@ -1,0 +1,950 @@
+// One decode step of the standard caption decoder as ONE kernel: every CTA owns a tile of 128 beam rows and
+// carries it through token embedding, the decoder layers (decoders.py:21-28: self-attention, cross-attention,
+// position-wise feed-forward, each followed by residual + LayerNorm) and the vocabulary projection with its
+// log-softmax chunk statistics (decoders.py:121-123).  Rows never interact inside a step (beams interact only
+// in the selection, beam.cu), so there is no grid-wide dependency: nothing but the weights is shared between
+// CTAs, and the ~37 dependent launches of the per-operator path collapse into one.
+//
+// Structure of a CTA (384 threads; setmaxnreg moves registers from the control warpgroup to the workers):
+//   warp 0   : producer -- streams 128x64 weight tiles (TMA, SWIZZLE_128B) through a 4-stage ring, for ALL the
+//              step's GEMMs back to back: weights do not depend on activations, so the ring is refilled while
+//              the workers are still in an epilogue or an attention phase;
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x128x16, fp32 accumulators in two
+//              256-column TMEM buffers: the epilogue of one 256-column chunk overlaps the MMAs of the next);
+//   warps 4-11: workers -- TMEM epilogues (bias / ReLU / residual + LayerNorm / log-softmax statistics), the two
+//              attention phases on CUDA cores, and the embedding.
+// The activation tile is the RESIDENT A operand: 128 rows x 512 columns of bf16 in shared memory, stored
+// un-swizzled as 16-byte granules [granule (8 columns)][row][16 B] so that a thread-per-row epilogue writes it
+// conflict-free and tcgen05.mma reads it through a no-swizzle K-major descriptor (LBO = 2048, SBO = 128).
+// Only the 2048-wide FFN hidden tile does not fit: it goes through a global scratch buffer in the same granule
+// layout and comes back as the streamed A operand of the second FFN GEMM (one 16 KB bulk copy per k-block).
+// The fp32 residual stream lives in a global scratch buffer in granule layout too (coalesced for thread-per-row).
+#include "cap_common.cuh"
+#include "tcgen05_ptx.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+extern std::atomic<long long> g_cap_launches;
+namespace cap_gemm {
+int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows);
+}
+
+namespace {
+using namespace cap_ptx;
+
+constexpr int FD = 512;              // d_model = heads * d_k
+constexpr int FDFF = 2048;           // feed-forward width
+constexpr int FHEADS = 8;
+constexpr int TILE_ROWS = 128;
+constexpr int NW = 8;                // worker warps
+constexpr int FIRST_WORKER_WARP = 4;  // warps 0-3 form the control warpgroup (producer, MMA issuer, two idle)
+constexpr int FUSED_THREADS = (FIRST_WORKER_WARP + NW) * 32;
+constexpr int NB = 4;                // weight ring stages
+constexpr uint32_t B_STAGE_BYTES = 128 * 64 * 2;   // one 128-row x 64-column weight tile
+constexpr uint32_t A_KB_BYTES = 128 * 64 * 2;      // one k-block of the A operand (8 granules)
+constexpr uint32_t GRAN_BYTES = TILE_ROWS * 16;    // one 16-byte granule column of all 128 rows
+constexpr int A_SLOTS = 8;           // k-blocks of the resident A tile = slots of the streamed-A ring
+constexpr int STAGE_PITCH = 80;      // per-warp store staging: 32 rows x 64 B (+16 B skew)
+constexpr int MAXB = 5;              // beams served per image by the cross-attention phase
+constexpr int MAX_FUSED_LAYERS = 6;
+constexpr int W512_ROWS_PER_LAYER = 3 * FD + FD + FD + FD + FDFF;  // qkv | o1 | q | o2 | w1 (all K = 512)
+
+constexpr uint32_t OFF_A = 0;
+constexpr uint32_t OFF_B = OFF_A + A_SLOTS * A_KB_BYTES;
+constexpr uint32_t OFF_STAGE = OFF_B + NB * B_STAGE_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_STAGE + NW * 32 * STAGE_PITCH;
+constexpr uint32_t OFF_CBIAS = OFF_BIAS + FD * 4;     // [2][256] chunk biases of the plain projections
+constexpr uint32_t OFF_GAMMA = OFF_CBIAS + FD * 4;
+constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
+constexpr uint32_t OFF_STAT = OFF_BETA + FD * 4;       // [2 (sum, sumsq)][2 halves][128 rows]
+constexpr uint32_t OFF_BARS = OFF_STAT + 4 * TILE_ROWS * 4;
+constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1;
+constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
+constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16 + 1024;  // + alignment slack
+
+struct FusedLayerP {
+    const float *b_qkv, *b_o1, *g1, *be1, *b_q, *b_o2, *g2, *be2, *b_w1, *b_w2, *g3, *be3;
+};
+
+struct FusedParams {
+    CUtensorMap map_w512;   // [layers * 5120][512]: per layer qkv | self o | cross q | cross o | ffn1
+    CUtensorMap map_w2;     // [layers * 512][2048]
+    CUtensorMap map_vocab;  // [V][512]
+    FusedLayerP layer[MAX_FUSED_LAYERS];
+    int n_layers;
+    const int32_t* tokens;
+    const bf16* word_emb;
+    const float* word_pos;
+    int pad_idx;
+    bf16* qkv_cache;         // [layers][T][R][1536]
+    const int32_t* ancestry; // [T][R]
+    uint8_t* padflag;        // [T][R]
+    const bf16* cross_kv;    // layer l at cross_kv + l * cross_layer_stride: [B][n][K(512) | V(512)]
+    size_t cross_layer_stride;
+    const uint8_t* enc_mask; // [B][n]
+    int n_keys;
+    float* res;              // [tiles][128 granules of 4 floats][128 rows][4]   fp32 residual stream
+    bf16* qg;                // [tiles][64 granules][128 rows][8]                cross-attention queries
+    bf16* hbuf;              // [tiles][256 granules][128 rows][8]               FFN hidden
+    float* logits;
+    int ld_logits;
+    float* part_ms;          // [R][stat_chunks][2]
+    int vocab, vocab_tiles, stat_chunks;
+    int t, T, R, B, beam;
+    float scale;
+    int desc_swap;           // debug: swap LBO/SBO of the no-swizzle A descriptor
+    unsigned long long* trace;  // debug: 64 %globaltimer stamps per CTA (cap_debug_fused_trace), else nullptr
+};
+
+__device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot, bool who) {
+    if (p.trace != nullptr && who) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[static_cast<size_t>(tile) * 64 + slot] = t;
+    }
+}
+
+struct Job {
+    const CUtensorMap* map;
+    int row0, ntiles, kblocks, chunk;
+    bool stream;
+};
+
+__device__ __forceinline__ Job get_job(const FusedParams& p, int ji) {
+    Job j;
+    j.kblocks = FD / BLOCK_K;
+    j.stream = false;
+    j.map = &p.map_w512;
+    if (ji == p.n_layers * 6) {
+        j.map = &p.map_vocab;
+        j.row0 = 0;
+        j.ntiles = p.vocab_tiles;
+        j.chunk = 2;
+        return j;
+    }
+    const int L = ji / 6, k = ji % 6;
+    const int base = L * W512_ROWS_PER_LAYER;
+    switch (k) {
+        case 0: j.row0 = base; j.ntiles = 12; j.chunk = 2; break;             // q | k | v of the new token
+        case 1: j.row0 = base + 1536; j.ntiles = 4; j.chunk = 4; break;       // self fc_o (+ LN)
+        case 2: j.row0 = base + 2048; j.ntiles = 4; j.chunk = 2; break;       // cross fc_q
+        case 3: j.row0 = base + 2560; j.ntiles = 4; j.chunk = 4; break;       // cross fc_o (+ LN)
+        case 4: j.row0 = base + 3072; j.ntiles = 16; j.chunk = 2; break;      // fc1 (+ ReLU)
+        default:
+            j.map = &p.map_w2; j.row0 = L * FD; j.ntiles = 4; j.chunk = 4; j.kblocks = FDFF / BLOCK_K;
+            j.stream = true;                                                  // fc2 (+ LN), A = hidden tile
+            break;
+    }
+    return j;
+}
+
+// 64 bytes per lane (the lane's row) -> global rows, through the warp's staging tile: every store instruction
+// then covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
+__device__ __forceinline__ void staged_store64(uint8_t* stage, int lane, const uint4 (&v)[4], uint8_t* gbase,
+                                               size_t row_stride, int rows_valid) {
+    uint8_t* mine = stage + lane * STAGE_PITCH;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(mine + i * 16) = v[i];
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * 32 + lane;
+        const int rr = idx >> 2, part = idx & 3;
+        const uint4 x = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + part * 16);
+        if (rr < rows_valid) *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(rr) * row_stride + part * 16) = x;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint4 pack8_u4(const float* f) {
+    bf16x8 p = pack8(f);
+    return *reinterpret_cast<uint4*>(&p);
+}
+
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
+
+struct WorkerCtx {
+    uint8_t* A_buf;
+    uint8_t* stage;   // this warp's staging tile
+    float *s_bias, *s_cbias, *s_gamma, *s_beta, *s_stat;
+    uint64_t *acc_full, *acc_empty, *a_ready, *h_ready;
+    uint32_t tmem_base;
+    uint32_t use0, use1;  // completed uses of TMEM buffer 0 / 1 (scalars: no dynamically indexed state)
+    int toggle;
+    int ww, quad, half, lane, wtid;
+    int tile, r0, rows_valid_warp;  // rows of this warp's TMEM quadrant that exist (0..32)
+};
+
+__device__ __forceinline__ int acquire_acc(WorkerCtx& c, int chunk) {
+    if (chunk == 4) {
+        mbar_wait(&c.acc_full[0], c.use0 & 1);
+        mbar_wait(&c.acc_full[1], c.use1 & 1);
+        tcgen05_fence_after();
+        return 0;
+    }
+    const int b = c.toggle;
+    mbar_wait(&c.acc_full[b], (b ? c.use1 : c.use0) & 1);
+    tcgen05_fence_after();
+    return b;
+}
+
+__device__ __forceinline__ void release_acc(WorkerCtx& c, int chunk, int b) {
+    tcgen05_fence_before();
+    __syncwarp();
+    if (chunk == 4) {
+        if (c.lane == 0) { mbar_arrive(&c.acc_empty[0]); mbar_arrive(&c.acc_empty[1]); }
+        c.use0++; c.use1++;
+        c.toggle = 0;
+    } else {
+        if (c.lane == 0) mbar_arrive(&c.acc_empty[b]);
+        if (b) c.use1++; else c.use0++;
+        c.toggle ^= 1;
+    }
+}
+
+// the resident A tile was written with ordinary stores: make it visible to tcgen05.mma and tell the issuer
+__device__ __forceinline__ void publish_a(WorkerCtx& c) {
+    fence_proxy_async();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(c.a_ready);
+}
+
+enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
+
+// Epilogue of one 256-column chunk of a plain projection: + bias (ReLU for the hidden layer), bf16, to global.
+template <int KIND>
+__device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
+                                               bf16* dst_rowmajor, int ld_rowmajor) {
+    // stage this chunk's 256 bias values (double-buffered by chunk parity; see the barrier note below)
+    float* sb = c.s_cbias + (chunk_idx & 1) * 256;
+    sb[c.wtid] = __ldg(bias + chunk_idx * 256 + c.wtid);
+    workers_sync();  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
+    const int b = acquire_acc(c, 2);
+    const int row = c.quad * 32 + c.lane;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int colc = c.half * 128 + i * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]) + sb[colc + j];
+            if (KIND == EPI_HID) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint4 o[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) o[g] = pack8_u4(f + 8 * g);
+        const int gcol = chunk_idx * 256 + colc;
+        if (KIND == EPI_CACHE) {
+            uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
+            staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
+        } else {
+            // granule layout [tile][granule][row][16 B]: 32 lanes write 512 contiguous bytes per granule
+            const int grans = (KIND == EPI_QG) ? FD / 8 : FDFF / 8;
+            uint4* base = reinterpret_cast<uint4*>(KIND == EPI_QG ? p.qg : p.hbuf) +
+                          (static_cast<size_t>(c.tile) * grans + gcol / 8) * TILE_ROWS + row;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) base[static_cast<size_t>(g) * TILE_ROWS] = o[g];
+        }
+    }
+    release_acc(c, 2, b);
+}
+
+// Epilogue of an N = 512 projection followed by residual + LayerNorm (attentions.py:308-309,
+// positionwise_feed_forward.py:26): thread = row, the two warps of a TMEM quadrant take 256 columns each and
+// exchange (sum, sum of squares); the normalised row goes to the resident A tile (bf16) and back to the fp32
+// residual stream (in place: a thread only ever touches its own elements).
+__device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedParams& p, const float* bias,
+                                                   const float* gamma, const float* beta, const uint8_t* zero_rows) {
+    for (int i = c.wtid; i < FD; i += NW * 32) {
+        c.s_bias[i] = __ldg(bias + i);
+        c.s_gamma[i] = __ldg(gamma + i);
+        c.s_beta[i] = __ldg(beta + i);
+    }
+    workers_sync();
+    acquire_acc(c, 4);
+    const int row = c.quad * 32 + c.lane;
+    const int grow = c.r0 + row;
+    const bool live = grow < p.R;
+    float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS + row;
+    const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int c0 = c.half * 256 + i * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        float4 r4[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) r4[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float y0 = __uint_as_float(v[4 * g]) + c.s_bias[c0 + 4 * g] + r4[g].x;
+            const float y1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r4[g].y;
+            const float y2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r4[g].z;
+            const float y3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r4[g].w;
+            s1 += (y0 + y1) + (y2 + y3);
+            s2 = fmaf(y0, y0, s2); s2 = fmaf(y1, y1, s2); s2 = fmaf(y2, y2, s2); s2 = fmaf(y3, y3, s2);
+        }
+    }
+    c.s_stat[c.half * TILE_ROWS + row] = s1;
+    c.s_stat[(2 + c.half) * TILE_ROWS + row] = s2;
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + c.quad) : "memory");
+    const float S1 = c.s_stat[row] + c.s_stat[TILE_ROWS + row];
+    const float S2 = c.s_stat[2 * TILE_ROWS + row] + c.s_stat[3 * TILE_ROWS + row];
+    const float mean = S1 * (1.f / FD);
+    const float var = fmaxf(S2 * (1.f / FD) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    const bool zero = !live || (zero_rows != nullptr && zero_rows[grow] != 0);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int c0 = c.half * 256 + i * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        float4 r4[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) r4[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float rr[4] = {r4[g].x, r4[g].y, r4[g].z, r4[g].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * g + e;
+                const float y = __uint_as_float(v[j]) + c.s_bias[c0 + j] + rr[e];
+                f[j] = zero ? 0.f : (y - mean) * rstd * c.s_gamma[c0 + j] + c.s_beta[c0 + j];
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(c0 / 8 + g) * GRAN_BYTES + row * 16) = pack8_u4(f + 8 * g);
+    }
+    release_acc(c, 4, 0);
+    publish_a(c);
+}
+
+// x = Emb[token] + pos[t + 1] (decoders.py:107-112); pad flag of the fed token; warp per row.
+__device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) {
+    uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
+    const float* pos = p.word_pos + static_cast<size_t>(p.t + 1) * FD + c.lane * 16;
+    float pv[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(pos) + i);
+        pv[4 * i] = t4.x; pv[4 * i + 1] = t4.y; pv[4 * i + 2] = t4.z; pv[4 * i + 3] = t4.w;
+    }
+    float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS;
+#pragma unroll 2
+    for (int i = 0; i < TILE_ROWS / NW; ++i) {
+        const int row = c.ww * (TILE_ROWS / NW) + i;
+        const int grow = c.r0 + row;
+        float a[16];
+        if (grow < p.R) {
+            const int tok = p.tokens[grow];
+            if (c.lane == 0) pad_t[grow] = (tok == p.pad_idx) ? 1 : 0;
+            const bf16x8* e = reinterpret_cast<const bf16x8*>(p.word_emb + static_cast<size_t>(tok) * FD + c.lane * 16);
+            unpack8(e[0], a);
+            unpack8(e[1], a + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] += pv[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+            *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(2 * c.lane + g) * GRAN_BYTES + row * 16) = pack8_u4(a + 8 * g);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            res[static_cast<size_t>(4 * c.lane + g) * TILE_ROWS + row] = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+    }
+}
+
+// Stateful self-attention of the new token over its beam history (attentions.py:297-304 with the running
+// mask of decoders.py:101-103): warp per row, lanes tile the 512-wide row (4 lanes per head), keys found
+// through the ancestry table, online softmax; output straight into the resident A tile.
+__device__ __forceinline__ void self_attention_phase(WorkerCtx& c, const FusedParams& p, const bf16* cache_l) {
+    constexpr int EPL = 16;
+    const int t = p.t, R = p.R;
+    const size_t row_stride = 3 * FD;
+    const size_t step_stride = static_cast<size_t>(R) * row_stride;
+    const int nkeys = t + 1;
+#pragma unroll 1
+    for (int i = 0; i < TILE_ROWS / NW; ++i) {
+        const int row = c.ww * (TILE_ROWS / NW) + i;
+        const int r = c.r0 + row;
+        if (r >= R) continue;
+        float q[EPL];
+        {
+            const bf16x8* qp = reinterpret_cast<const bf16x8*>(cache_l + t * step_stride + r * row_stride + c.lane * EPL);
+            unpack8(qp[0], q);
+            unpack8(qp[1], q + 8);
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) q[j] *= p.scale;
+        }
+        int slot_lo = 0, slot_hi = 0;       // key slot / pad flag of key index == lane (and lane + 32)
+        int pad_lo = 1, pad_hi = 1;
+        if (c.lane < nkeys) {
+            slot_lo = (c.lane == t) ? r : p.ancestry[static_cast<size_t>(c.lane) * R + r];
+            pad_lo = p.padflag[static_cast<size_t>(c.lane) * R + slot_lo] != 0;
+        }
+        if (c.lane + 32 < nkeys) {
+            slot_hi = (c.lane + 32 == t) ? r : p.ancestry[static_cast<size_t>(c.lane + 32) * R + r];
+            pad_hi = p.padflag[static_cast<size_t>(c.lane + 32) * R + slot_hi] != 0;
+        }
+        float m = -INFINITY, l = 0.f, acc[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+        constexpr int UNROLL = 4;
+        for (int j0 = 0; j0 < nkeys; j0 += UNROLL) {
+            bf16x8 kreg[UNROLL][2], vreg[UNROLL][2];
+            bool pad[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int j = min(j0 + u, nkeys - 1);
+                const int sl = __shfl_sync(0xffffffffu, (j >> 5) ? slot_hi : slot_lo, j & 31);
+                pad[u] = __shfl_sync(0xffffffffu, (j >> 5) ? pad_hi : pad_lo, j & 31) != 0 || (j0 + u >= nkeys);
+                const bf16* base = cache_l + j * step_stride + sl * row_stride + c.lane * EPL;
+                kreg[u][0] = reinterpret_cast<const bf16x8*>(base + FD)[0];
+                kreg[u][1] = reinterpret_cast<const bf16x8*>(base + FD)[1];
+                vreg[u][0] = reinterpret_cast<const bf16x8*>(base + 2 * FD)[0];
+                vreg[u][1] = reinterpret_cast<const bf16x8*>(base + 2 * FD)[1];
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                float kf[EPL];
+                unpack8(kreg[u][0], kf);
+                unpack8(kreg[u][1], kf + 8);
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) s = fmaf(q[j], kf[j], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (pad[u]) continue;  // warp-uniform
+                const float m_new = fmaxf(m, s);
+                const float corr = __expf(m - m_new);
+                const float pr = __expf(s - m_new);
+                l = l * corr + pr;
+                float vf[EPL];
+                unpack8(vreg[u][0], vf);
+                unpack8(vreg[u][1], vf + 8);
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) acc[j] = acc[j] * corr + pr * vf[j];
+                m = m_new;
+            }
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) acc[j] *= inv;
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+            *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(2 * c.lane + g) * GRAN_BYTES + row * 16) = pack8_u4(acc + 8 * g);
+    }
+}
+
+// Cross-attention over the image's cached K|V (decoders.py:23): warp per image, all heads and all of the
+// image's beams at once (lane owns 16 consecutive columns, 4 lanes per head), so every K/V row is read once
+// per step; keys two at a time with the next pair in flight.
+__device__ __forceinline__ void cross_attention_phase(WorkerCtx& c, const FusedParams& p, const bf16* kv_l) {
+    constexpr int EPL = 16;
+    const int beam = p.beam, n = p.n_keys;
+    const int img_lo = c.r0 / beam;
+    const int last_row = min(c.r0 + TILE_ROWS, p.R) - 1;
+    const int img_hi = last_row / beam;
+    const uint4* qg = reinterpret_cast<const uint4*>(p.qg) + static_cast<size_t>(c.tile) * (FD / 8) * TILE_ROWS;
+#pragma unroll 1
+    for (int img = img_lo + c.ww; img <= img_hi; img += NW) {
+        const int row_begin = max(img * beam, c.r0);
+        const int row_end = min(img * beam + beam, last_row + 1);
+        const int nb = row_end - row_begin;
+        const int lr0 = row_begin - c.r0;
+        bf16x8 qreg[MAXB][2];
+#pragma unroll
+        for (int bb = 0; bb < MAXB; ++bb) {
+            if (bb < nb) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint4 u = qg[static_cast<size_t>(2 * c.lane + g) * TILE_ROWS + lr0 + bb];
+                    qreg[bb][g] = *reinterpret_cast<const bf16x8*>(&u);
+                }
+            } else {
+                qreg[bb][0] = qreg[0][0];
+                qreg[bb][1] = qreg[0][1];
+            }
+        }
+        float m[MAXB], l[MAXB], acc[MAXB][EPL];
+#pragma unroll
+        for (int bb = 0; bb < MAXB; ++bb) {
+            m[bb] = -INFINITY;
+            l[bb] = 0.f;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) acc[bb][j] = 0.f;
+        }
+        const bf16* kvb = kv_l + static_cast<size_t>(img) * n * 2 * FD + c.lane * EPL;
+        const uint8_t* mrow = p.enc_mask ? p.enc_mask + static_cast<size_t>(img) * n : nullptr;
+#pragma unroll 1
+        for (int j0 = 0; j0 < n; j0 += 2) {
+            bf16x8 kreg[2][2], vreg[2][2];
+            bool livek[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = j0 + u;
+                livek[u] = j < n && !(mrow && mrow[min(j, n - 1)]);
+                const bf16* base = kvb + static_cast<size_t>(min(j, n - 1)) * 2 * FD;
+                kreg[u][0] = reinterpret_cast<const bf16x8*>(base)[0];
+                kreg[u][1] = reinterpret_cast<const bf16x8*>(base)[1];
+                vreg[u][0] = reinterpret_cast<const bf16x8*>(base + FD)[0];
+                vreg[u][1] = reinterpret_cast<const bf16x8*>(base + FD)[1];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!livek[u]) continue;  // warp-uniform
+                float kf[EPL], vf[EPL];
+                unpack8(kreg[u][0], kf);
+                unpack8(kreg[u][1], kf + 8);
+                unpack8(vreg[u][0], vf);
+                unpack8(vreg[u][1], vf + 8);
+#pragma unroll
+                for (int bb = 0; bb < MAXB; ++bb) {
+                    if (bb >= nb) continue;  // warp-uniform
+                    float qf[EPL];
+                    unpack8(qreg[bb][0], qf);
+                    unpack8(qreg[bb][1], qf + 8);
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) s = fmaf(qf[j], kf[j], s);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s *= p.scale;
+                    const float m_new = fmaxf(m[bb], s);
+                    const float corr = __expf(m[bb] - m_new);
+                    const float pr = __expf(s - m_new);
+                    l[bb] = l[bb] * corr + pr;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) acc[bb][j] = acc[bb][j] * corr + pr * vf[j];
+                    m[bb] = m_new;
+                }
+            }
+        }
+#pragma unroll
+        for (int bb = 0; bb < MAXB; ++bb) {
+            if (bb >= nb) continue;
+            const float inv = l[bb] > 0.f ? 1.f / l[bb] : 0.f;
+            float o[EPL];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) o[j] = acc[bb][j] * inv;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+                *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(2 * c.lane + g) * GRAN_BYTES + (lr0 + bb) * 16) = pack8_u4(o + 8 * g);
+        }
+    }
+}
+
+// Vocabulary projection epilogue (bias-free fc, decoders.py:90,121): fp32 logits + per-32-column-chunk
+// (max, sum exp(x - max)) for beam_chunkmerge_kernel (beam.cu).
+__device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx) {
+    const int b = acquire_acc(c, 2);
+    const int row = c.quad * 32 + c.lane;
+    const int grow = c.r0 + row;
+    float2 st[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int colc = c.half * 128 + i * 32;
+        const int gcol = chunk_idx * 256 + colc;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
+        tmem_ld_wait();
+        const int valid = p.vocab - gcol;  // columns of this 32-chunk inside the vocabulary (warp-uniform)
+        float cm = -INFINITY, cs = 0.f;
+        if (valid >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+            const float cm2 = cm * 1.4426950408889634f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs += exp2f(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -cm2));
+        } else if (valid > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < valid ? __uint_as_float(v[j]) : -INFINITY);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs += j < valid ? __expf(__uint_as_float(v[j]) - cm) : 0.f;
+        }
+        st[i] = make_float2(cm, cs);
+        if (gcol < p.ld_logits) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint4 o[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
+                staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
+            }
+        }
+    }
+    if (grow < p.R) {
+        float4* dst = reinterpret_cast<float4*>(p.part_ms + (static_cast<size_t>(grow) * p.stat_chunks + chunk_idx * 8 + c.half * 4) * 2);
+        dst[0] = make_float4(st[0].x, st[0].y, st[1].x, st[1].y);
+        dst[1] = make_float4(st[2].x, st[2].y, st[3].x, st[3].y);
+    }
+    release_acc(c, 2, b);
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
+    extern __shared__ uint8_t fused_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fused_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* A_buf = smem + OFF_A;
+    uint8_t* B_ring = smem + OFF_B;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    uint64_t* b_full = bars;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* a_full = b_empty + NB;
+    uint64_t* a_empty = a_full + A_SLOTS;
+    uint64_t* acc_full = a_empty + A_SLOTS;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* a_ready = acc_empty + 2;
+    uint64_t* h_ready = a_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int njobs = p.n_layers * 6 + 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w512)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w2)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_vocab)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+            for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NW); }
+            mbar_init(a_ready, NW);
+            mbar_init(h_ready, NW);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < FIRST_WORKER_WARP) {
+    // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
+    // the register limit of each region is unambiguous to ptxas)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer (weights never wait)
+        if (lane == 0) {
+            uint32_t bcount = 0, acount = 0, hphase = 0;
+            const uint8_t* hsrc = reinterpret_cast<const uint8_t*>(p.hbuf) + static_cast<size_t>(tile) * (FDFF / 8) * GRAN_BYTES;
+            for (int ji = 0; ji < njobs; ++ji) {
+                const Job job = get_job(p, ji);
+                const int nch = job.ntiles / job.chunk;
+                for (int c = 0; c < nch; ++c) {
+                    for (int kb = 0; kb < job.kblocks; ++kb) {
+                        for (int j = 0; j < job.chunk; ++j) {
+                            const uint32_t s = bcount % NB;
+                            mbar_wait(&b_empty[s], ((bcount / NB) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
+                            tma_load_2d(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
+                                        job.row0 + (c * job.chunk + j) * 128);
+                            ++bcount;
+                        }
+                        if (job.stream) {
+                            if (kb == 0) {  // the workers have written (and proxy-fenced) the whole hidden tile
+                                mbar_wait(h_ready, hphase);
+                                hphase ^= 1;
+                            }
+                            const uint32_t slot = acount % A_SLOTS;
+                            mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&a_full[slot], A_KB_BYTES);
+                            bulk_load_1d(A_buf + slot * A_KB_BYTES, hsrc + static_cast<size_t>(kb) * A_KB_BYTES, A_KB_BYTES,
+                                         &a_full[slot]);
+                            ++acount;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        pdl_launch_dependents();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_instr_desc(128, 128);
+            const uint32_t lbo = p.desc_swap ? 128u : GRAN_BYTES;
+            const uint32_t sbo = p.desc_swap ? GRAN_BYTES : 128u;
+            uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
+            int toggle = 0;
+            for (int ji = 0; ji < njobs; ++ji) {
+                const Job job = get_job(p, ji);
+                const int nch = job.ntiles / job.chunk;
+                if (!job.stream) {
+                    mbar_wait(a_ready, ar & 1);
+                    ++ar;
+                }
+                tcgen05_fence_after();
+                for (int c = 0; c < nch; ++c) {
+                    int b = 0;
+                    uint32_t colbase = 0;
+                    if (job.chunk == 4) {
+                        mbar_wait(&acc_empty[0], (use0 & 1) ^ 1);
+                        mbar_wait(&acc_empty[1], (use1 & 1) ^ 1);
+                    } else {
+                        b = toggle;
+                        mbar_wait(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
+                        colbase = b * 256;
+                    }
+                    tcgen05_fence_after();
+                    for (int kb = 0; kb < job.kblocks; ++kb) {
+                        uint32_t a_addr;
+                        uint32_t slot = 0;
+                        if (job.stream) {
+                            slot = acount % A_SLOTS;
+                            mbar_wait(&a_full[slot], (acount / A_SLOTS) & 1);
+                            a_addr = smem_u32(A_buf + slot * A_KB_BYTES);
+                        } else {
+                            a_addr = smem_u32(A_buf + kb * A_KB_BYTES);
+                        }
+                        for (int j = 0; j < job.chunk; ++j) {
+                            const uint32_t s = bcount % NB;
+                            mbar_wait(&b_full[s], (bcount / NB) & 1);
+                            tcgen05_fence_after();
+                            const uint64_t b_desc = make_smem_desc(B_ring + s * B_STAGE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint64_t a_desc = make_smem_desc_noswizzle(a_addr + k * 2 * GRAN_BYTES, lbo, sbo);
+                                umma_bf16(tmem_base + colbase + j * 128, a_desc, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&b_empty[s]);
+                            ++bcount;
+                        }
+                        if (job.stream) {
+                            umma_commit(&a_empty[slot]);
+                            ++acount;
+                        }
+                    }
+                    if (job.chunk == 4) {
+                        umma_commit(&acc_full[0]);
+                        umma_commit(&acc_full[1]);
+                        ++use0; ++use1;
+                        toggle = 0;
+                    } else {
+                        umma_commit(&acc_full[b]);
+                        if (b) ++use1; else ++use0;
+                        toggle ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        pdl_launch_dependents();
+    }
+    } else {
+        // ------------------------------------------------------------------ workers
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        WorkerCtx c;
+        c.A_buf = A_buf;
+        c.ww = warp - FIRST_WORKER_WARP;
+        c.quad = warp & 3;
+        c.half = c.ww >> 2;
+        c.lane = lane;
+        c.wtid = threadIdx.x - FIRST_WORKER_WARP * 32;
+        c.stage = smem + OFF_STAGE + c.ww * 32 * STAGE_PITCH;
+        c.s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+        c.s_cbias = reinterpret_cast<float*>(smem + OFF_CBIAS);
+        c.s_gamma = reinterpret_cast<float*>(smem + OFF_GAMMA);
+        c.s_beta = reinterpret_cast<float*>(smem + OFF_BETA);
+        c.s_stat = reinterpret_cast<float*>(smem + OFF_STAT);
+        c.acc_full = acc_full;
+        c.acc_empty = acc_empty;
+        c.a_ready = a_ready;
+        c.h_ready = h_ready;
+        c.tmem_base = tmem_base;
+        c.use0 = c.use1 = 0;
+        c.toggle = 0;
+        c.tile = tile;
+        c.r0 = tile * TILE_ROWS;
+        c.rows_valid_warp = max(0, min(32, p.R - (c.r0 + c.quad * 32)));
+
+        const bool tr = (c.ww == 0 && lane == 0);
+        fstamp(p, tile, 0, tr);
+        pdl_wait();  // tokens / ancestry come from the previous step's selection kernel
+        fstamp(p, tile, 1, tr);
+        embed_phase(c, p);
+        workers_sync();  // the residual tile was written warp-per-row, the epilogues read it thread-per-row
+        publish_a(c);
+
+        uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
+        for (int L = 0; L < p.n_layers; ++L) {
+            const FusedLayerP& W = p.layer[L];
+            bf16* cache_l = p.qkv_cache + static_cast<size_t>(L) * p.T * p.R * 3 * FD;
+            bf16* cache_t = cache_l + static_cast<size_t>(p.t) * p.R * 3 * FD;
+            const int sb = 2 + L * 8;
+            fstamp(p, tile, sb, tr);
+            for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, cache_t, 3 * FD);
+            workers_sync();  // q|k|v of every row of the tile are in the cache
+            fstamp(p, tile, sb + 1, tr);
+            self_attention_phase(c, p, cache_l);
+            publish_a(c);
+            fstamp(p, tile, sb + 2, tr);
+            epilogue_layernorm(c, p, W.b_o1, W.g1, W.be1, nullptr);
+            fstamp(p, tile, sb + 3, tr);
+            for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_QG>(c, p, W.b_q, ch, nullptr, 0);
+            workers_sync();
+            fstamp(p, tile, sb + 4, tr);
+            cross_attention_phase(c, p, p.cross_kv + static_cast<size_t>(L) * p.cross_layer_stride);
+            publish_a(c);
+            fstamp(p, tile, sb + 5, tr);
+            epilogue_layernorm(c, p, W.b_o2, W.g2, W.be2, nullptr);
+            fstamp(p, tile, sb + 6, tr);
+            for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, nullptr, 0);
+            fence_proxy_async();  // hidden tile (global, generic proxy) -> bulk-copy reads (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_ready);
+            fstamp(p, tile, sb + 7, tr);
+            epilogue_layernorm(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
+        }
+        fstamp(p, tile, 2 + p.n_layers * 8, tr);
+        pdl_launch_dependents();
+        const int vchunks = p.vocab_tiles / 2;
+        for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch);
+        fstamp(p, tile, 3 + p.n_layers * 8, tr);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host side
+struct cap_fused_decoder {
+    FusedParams base;
+    void* w512 = nullptr;
+    void* w2 = nullptr;
+    int tiles = 0;
+};
+
+extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out) {
+    CAP_REQUIRE(d && out, "cap_fused_create: null pointer");
+    CAP_REQUIRE(d->d_model == FD && d->heads == FHEADS && d->d_ff == FDFF, "cap_fused_create: needs d_model 512, 8 heads, d_ff 2048");
+    CAP_REQUIRE(d->n_layers >= 1 && d->n_layers <= MAX_FUSED_LAYERS, "cap_fused_create: 1..%d layers", MAX_FUSED_LAYERS);
+    CAP_REQUIRE(d->beam >= 1 && d->beam <= MAXB, "cap_fused_create: beam must be 1..%d", MAXB);
+    CAP_REQUIRE(d->max_rows > 0 && d->vocab > 8 && d->max_len > 0, "cap_fused_create: bad sizes");
+    CAP_REQUIRE(d->ld_logits % 32 == 0 && d->ld_logits >= d->vocab, "cap_fused_create: ld_logits must be a multiple of 32");
+    cap_fused_decoder* f = new cap_fused_decoder();
+    FusedParams& p = f->base;
+    memset(&p, 0, sizeof(p));
+    const int L = d->n_layers;
+    p.n_layers = L;
+    f->tiles = (d->max_rows + TILE_ROWS - 1) / TILE_ROWS;
+    auto fail = [&](int rc) { cap_fused_destroy(f); return rc; };
+    // stacked weight copies: one tensor map covers every K = 512 projection of the model
+    const size_t w512_elems = static_cast<size_t>(L) * W512_ROWS_PER_LAYER * FD;
+    const size_t w2_elems = static_cast<size_t>(L) * FD * FDFF;
+    if (cudaMalloc(&f->w512, w512_elems * 2) != cudaSuccess || cudaMalloc(&f->w2, w2_elems * 2) != cudaSuccess)
+        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cudaMalloc of the stacked weights failed"));
+    for (int l = 0; l < L; ++l) {
+        const cap_fused_layer& w = d->layers[l];
+        const void* srcs[5] = {w.w_qkv, w.w_o1, w.w_q, w.w_o2, w.w_fc1};
+        const int rows[5] = {3 * FD, FD, FD, FD, FDFF};
+        bf16* dst = static_cast<bf16*>(f->w512) + static_cast<size_t>(l) * W512_ROWS_PER_LAYER * FD;
+        for (int i = 0; i < 5; ++i) {
+            if (!srcs[i]) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_create: null weight"));
+            if (cudaMemcpy(dst, srcs[i], static_cast<size_t>(rows[i]) * FD * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
+                return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: weight copy failed"));
+            dst += static_cast<size_t>(rows[i]) * FD;
+        }
+        if (!w.w_fc2 || cudaMemcpy(static_cast<bf16*>(f->w2) + static_cast<size_t>(l) * FD * FDFF, w.w_fc2,
+                                   static_cast<size_t>(FD) * FDFF * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
+            return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: fc2 copy failed"));
+        FusedLayerP& lp = p.layer[l];
+        lp.b_qkv = w.b_qkv; lp.b_o1 = w.b_o1; lp.g1 = w.ln1_g; lp.be1 = w.ln1_b;
+        lp.b_q = w.b_q; lp.b_o2 = w.b_o2; lp.g2 = w.ln2_g; lp.be2 = w.ln2_b;
+        lp.b_w1 = w.b_fc1; lp.b_w2 = w.b_fc2; lp.g3 = w.ln3_g; lp.be3 = w.ln3_b;
+        const float* need[12] = {lp.b_qkv, lp.b_o1, lp.g1, lp.be1, lp.b_q, lp.b_o2, lp.g2, lp.be2, lp.b_w1, lp.b_w2, lp.g3, lp.be3};
+        for (const float* q : need)
+            if (!q) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_create: null bias / LayerNorm parameter"));
+    }
+    int rc = cap_gemm::make_tmap(&p.map_w512, f->w512, L * W512_ROWS_PER_LAYER, FD, FD, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, f->w2, L * FD, FDFF, FDFF, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, d->w_vocab, d->vocab, FD, FD, 128);
+    if (rc != CAP_OK) return fail(rc);
+    p.tokens = d->tokens; p.word_emb = static_cast<const bf16*>(d->word_emb); p.word_pos = d->word_pos; p.pad_idx = d->pad_idx;
+    p.qkv_cache = static_cast<bf16*>(d->qkv_cache); p.ancestry = d->ancestry; p.padflag = d->padflag;
+    p.cross_kv = static_cast<const bf16*>(d->cross_kv); p.cross_layer_stride = d->cross_layer_stride; p.enc_mask = d->enc_mask;
+    p.logits = d->logits; p.ld_logits = d->ld_logits; p.part_ms = d->part_ms;
+    p.vocab = d->vocab;
+    p.vocab_tiles = ((d->vocab + 255) / 256) * 2;
+    p.stat_chunks = ((d->vocab + 255) / 256) * 8;
+    p.T = d->max_len; p.beam = d->beam;
+    p.scale = 1.0f / sqrtf(static_cast<float>(FD / FHEADS));
+    const size_t tiles = f->tiles;
+    void *res = nullptr, *qg = nullptr, *hb = nullptr;
+    if (cudaMalloc(&res, tiles * TILE_ROWS * FD * 4) != cudaSuccess || cudaMalloc(&qg, tiles * TILE_ROWS * FD * 2) != cudaSuccess ||
+        cudaMalloc(&hb, tiles * TILE_ROWS * FDFF * 2) != cudaSuccess) {
+        cudaFree(res); cudaFree(qg); cudaFree(hb);
+        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cudaMalloc of the scratch tiles failed"));
+    }
+    cudaMemset(res, 0, tiles * TILE_ROWS * FD * 4);
+    cudaMemset(qg, 0, tiles * TILE_ROWS * FD * 2);
+    cudaMemset(hb, 0, tiles * TILE_ROWS * FDFF * 2);
+    p.res = static_cast<float*>(res); p.qg = static_cast<bf16*>(qg); p.hbuf = static_cast<bf16*>(hb);
+    if (cudaFuncSetAttribute(decode_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
+    *out = f;
+    return CAP_OK;
+}
+
+extern "C" int cap_fused_destroy(cap_fused_decoder* f) {
+    if (!f) return CAP_OK;
+    cudaFree(f->w512);
+    cudaFree(f->w2);
+    cudaFree(f->base.res);
+    cudaFree(f->base.qg);
+    cudaFree(f->base.hbuf);
+    delete f;
+    return CAP_OK;
+}
+
+static unsigned long long* g_fused_trace = nullptr;
+extern "C" int cap_debug_fused_trace(unsigned long long* device_buffer) {
+    g_fused_trace = device_buffer;
+    return CAP_OK;
+}
+
+extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_keys, cap_stream_t stream) {
+    CAP_REQUIRE(f != nullptr, "cap_fused_decode_step: null handle");
+    FusedParams p = f->base;
+    CAP_REQUIRE(t >= 0 && t < p.T, "cap_fused_decode_step: step %d outside [0,%d)", t, p.T);
+    const int R = B * p.beam;
+    const int tiles = (R + TILE_ROWS - 1) / TILE_ROWS;
+    CAP_REQUIRE(B > 0 && tiles <= f->tiles && n_keys > 0, "cap_fused_decode_step: batch %d exceeds the reservation", B);
+    p.t = t; p.R = R; p.B = B; p.n_keys = n_keys;
+    static const int swap = getenv("OPENVIIC_FUSED_DESC_SWAP") ? atoi(getenv("OPENVIIC_FUSED_DESC_SWAP")) : 0;
+    p.desc_swap = swap;
+    p.trace = g_fused_trace;
+    cap_launch_kernel(decode_step_fused_kernel, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
+                      static_cast<cudaStream_t>(stream), 1, p);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_step_fused_kernel");
+}

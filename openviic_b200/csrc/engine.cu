@@ -14,6 +14,7 @@
 #include "cap_common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -109,6 +110,7 @@ struct cap_engine {
     int64_t* out_ids = nullptr;
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
+    cap_fused_decoder* fused = nullptr;  // one-kernel decode step (decode_fused.cu) when the model is covered
 
     // CUDA graph of a full beam search (begin + T steps + finalize)
     cudaGraphExec_t graph_exec = nullptr;
@@ -288,6 +290,7 @@ extern "C" int cap_engine_destroy(cap_engine* e) {
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->beam_state) cap_beam_destroy(e->beam_state);
+    if (e->fused) cap_fused_destroy(e->fused);
     for (void* p : e->allocations) cudaFree(p);
     delete e;
     return CAP_OK;
@@ -419,13 +422,42 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->res_c, R * lv * d));
     CAP_PROPAGATE(dev_alloc(e, &e->res_mix, R * d));
     CAP_PROPAGATE(dev_alloc(e, &e->buf_y32, rows_max * static_cast<size_t>(std::max(2 * d, hd))));
-    e->ld_logits = (m.vocab + 7) / 8 * 8;
+    e->ld_logits = (m.vocab + 31) / 32 * 32;
     CAP_PROPAGATE(dev_alloc(e, &e->logits, R * e->ld_logits));
     e->vocab_chunks = ((m.vocab + 255) / 256) * 8;
     CAP_PROPAGATE(dev_alloc(e, &e->part_ms, R * e->vocab_chunks * 2));
     CAP_PROPAGATE(dev_alloc(e, &e->out_ids, R * T));
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));
     CAP_PROPAGATE(cap_beam_create(max_batch, beam, T, m.vocab, m.eos_idx, &e->beam_state));
+
+    // Standard decoder at the reference's sizes: the whole decode step runs as one kernel.
+    const char* env = getenv("OPENVIIC_FUSED_DECODE");
+    const bool want_fused = !env || atoi(env) != 0;
+    if (want_fused && m.decoder_kind == CAP_DEC_PLAIN && !m.aoa_dec_self && !m.aoa_dec_cross && d == 512 && m.heads == 8 &&
+        m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && e->vocab_fc.b == nullptr &&
+        e->vocab_chunks <= 512) {
+        std::vector<cap_fused_layer> layers(m.dec_layers);
+        for (int l = 0; l < m.dec_layers; ++l) {
+            const DecoderLayerW& L = e->dec[l];
+            cap_fused_layer& f = layers[l];
+            f.w_qkv = L.self_att.qkv.w; f.b_qkv = L.self_att.qkv.b;
+            f.w_o1 = L.self_att.o.w; f.b_o1 = L.self_att.o.b; f.ln1_g = L.self_att.ln.g; f.ln1_b = L.self_att.ln.b;
+            f.w_q = L.cross_att.q.w; f.b_q = L.cross_att.q.b;
+            f.w_o2 = L.cross_att.o.w; f.b_o2 = L.cross_att.o.b; f.ln2_g = L.cross_att.ln.g; f.ln2_b = L.cross_att.ln.b;
+            f.w_fc1 = L.ffn.fc1.w; f.b_fc1 = L.ffn.fc1.b; f.w_fc2 = L.ffn.fc2.w; f.b_fc2 = L.ffn.fc2.b;
+            f.ln3_g = L.ffn.ln.g; f.ln3_b = L.ffn.ln.b;
+        }
+        cap_fused_desc fd = {};
+        fd.d_model = d; fd.heads = m.heads; fd.d_ff = m.d_ff; fd.n_layers = m.dec_layers; fd.vocab = m.vocab;
+        fd.max_len = T; fd.beam = beam; fd.pad_idx = m.pad_idx; fd.max_rows = static_cast<int>(R);
+        fd.layers = layers.data();
+        fd.w_vocab = e->vocab_fc.w; fd.word_emb = e->word_emb; fd.word_pos = e->word_pos;
+        fd.tokens = cap_beam_tokens(e->beam_state); fd.ancestry = cap_beam_ancestry(e->beam_state);
+        fd.padflag = e->padflag; fd.qkv_cache = e->qkv_cache;
+        fd.cross_kv = e->cross_kv; fd.cross_layer_stride = rows_enc * 2 * hd; fd.enc_mask = e->enc_mask;
+        fd.logits = e->logits; fd.ld_logits = e->ld_logits; fd.part_ms = e->part_ms;
+        CAP_PROPAGATE(cap_fused_create(&fd, &e->fused));
+    }
     return CAP_OK;
 }
 
@@ -525,6 +557,10 @@ extern "C" int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->vocab_chunks > 512)  // vocabularies beyond the merge kernel's reach: full row pass over the logits
         return cap_engine_decode_logits(e, t, stream) || cap_engine_beam_advance(e, t, stream);
+    if (e->fused) {
+        CAP_PROPAGATE(cap_fused_decode_step(e->fused, t, e->cur_batch, e->cur_n, s));
+        return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, e->vocab_chunks, s);
+    }
     bf16* x = nullptr;
     CAP_PROPAGATE(run_decoder_stack(e, t, s, &x));
     const int R = e->cur_batch * e->beam;

@@ -452,6 +452,13 @@ int env_int(const char* name, int fallback) {
 
 }  // namespace
 
+// tensor-map builder for the other tcgen05 kernels of the library (decode_fused.cu)
+namespace cap_gemm {
+int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+    return ::make_tmap(map, base, rows, cols, ld, box_rows);
+}
+}  // namespace cap_gemm
+
 extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bias, void* y, int ldy, int out_dtype,
                           int act, int M, int N, int K, cap_stream_t stream) {
     CAP_REQUIRE(x && w && y, "cap_linear: null pointer");

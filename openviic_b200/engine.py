@@ -153,6 +153,18 @@ class CaptionEngine:
         rows = self.batch * self.reserved[2]
         return _device_view(ptr, (rows, ld.value), torch.float32, self.device)[:, :self.desc.vocab].clone()
 
+    def decode_step(self, t: int):
+        """Production step t: decoder stack (one fused kernel when the model is covered) + vocabulary statistics
+        + beam update."""
+        cabi.call("cap_engine_decode_step", self._h, t, self._stream())
+
+    def logits(self) -> torch.Tensor:
+        """Copy of the (R, V) fp32 logits the last decode step left behind."""
+        ld = C.c_int()
+        ptr = cabi.load_library().cap_engine_logits(self._h, C.byref(ld))
+        rows = self.batch * self.reserved[2]
+        return _device_view(ptr, (rows, ld.value), torch.float32, self.device)[:, :self.desc.vocab].clone()
+
     def beam_advance(self, t: int):
         cabi.call("cap_engine_beam_advance", self._h, t, self._stream())
 
