@@ -13,12 +13,15 @@
 //              256-column TMEM buffers: the epilogue of one 256-column chunk overlaps the MMAs of the next);
 //   warps 4-11: workers -- TMEM epilogues (bias / ReLU / residual + LayerNorm / log-softmax statistics), the two
 //              attention phases on CUDA cores, and the embedding.
-// The activation tile is the RESIDENT A operand: 128 rows x 512 columns of bf16 in shared memory, stored
-// un-swizzled as 16-byte granules [granule (8 columns)][row][16 B] so that a thread-per-row epilogue writes it
-// conflict-free and tcgen05.mma reads it through a no-swizzle K-major descriptor (LBO = 2048, SBO = 128).
-// Only the 2048-wide FFN hidden tile does not fit: it goes through a global scratch buffer in the same granule
-// layout and comes back as the streamed A operand of the second FFN GEMM (one 16 KB bulk copy per k-block).
-// The fp32 residual stream lives in a global scratch buffer in granule layout too (coalesced for thread-per-row).
+// The activation tile is the RESIDENT A operand: 128 rows x 512 columns of bf16 in shared memory as eight
+// K-major SWIZZLE_128B k-blocks (the layout TMA would produce), written directly by the epilogues: a thread
+// per row puts its 16-byte chunk c of k-block kb at kb*16K + row*128 + ((c ^ (row & 7)) << 4), which is
+// bank-conflict-free for a thread-per-row writer and is what the tcgen05.mma descriptor expects.  (A first
+// version kept the tile un-swizzled as 8x16-byte core matrices; it was correct but every MMA took ~4x its
+// floor -- the tensor pipe was busy fetching A -- see profiles/r01_fused_first_ncu.txt.)
+// Only the 2048-wide FFN hidden tile does not fit: it goes through a row-major global scratch buffer and
+// comes back through TMA as the streamed A operand of the second FFN GEMM.  The fp32 residual stream lives in
+// a global scratch buffer in 16-byte-granule layout [granule][row] (coalesced for a thread-per-row reader).
 #include "cap_common.cuh"
 #include "tcgen05_ptx.cuh"
 
@@ -61,7 +64,7 @@ constexpr uint32_t OFF_GAMMA = OFF_CBIAS + FD * 4;
 constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
 constexpr uint32_t OFF_STAT = OFF_BETA + FD * 4;       // [2 (sum, sumsq)][2 halves][128 rows]
 constexpr uint32_t OFF_BARS = OFF_STAT + 4 * TILE_ROWS * 4;
-constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1;
+constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1;
 constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
 constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16 + 1024;  // + alignment slack
 
@@ -73,6 +76,7 @@ struct FusedParams {
     CUtensorMap map_w512;   // [layers * 5120][512]: per layer qkv | self o | cross q | cross o | ffn1
     CUtensorMap map_w2;     // [layers * 512][2048]
     CUtensorMap map_vocab;  // [V][512]
+    CUtensorMap map_h;      // [tiles * 128][2048] FFN hidden scratch
     FusedLayerP layer[MAX_FUSED_LAYERS];
     int n_layers;
     const int32_t* tokens;
@@ -88,15 +92,17 @@ struct FusedParams {
     int n_keys;
     float* res;              // [tiles][128 granules of 4 floats][128 rows][4]   fp32 residual stream
     bf16* qg;                // [tiles][64 granules][128 rows][8]                cross-attention queries
-    bf16* hbuf;              // [tiles][256 granules][128 rows][8]               FFN hidden
+    bf16* hbuf;              // [tiles * 128][2048] row-major                    FFN hidden
     float* logits;
     int ld_logits;
     float* part_ms;          // [R][stat_chunks][2]
     int vocab, vocab_tiles, stat_chunks;
     int t, T, R, B, beam;
     float scale;
-    int desc_swap;           // debug: swap LBO/SBO of the no-swizzle A descriptor
     unsigned long long* trace;  // debug: 64 %globaltimer stamps per CTA (cap_debug_fused_trace), else nullptr
+    int dbg_mma_repeat;      // debug (timing only, wrong results): issue every MMA this many extra times
+    int dbg_ring;            // debug: weight ring depth actually used (1..NB)
+    int dbg_skip;            // debug (timing only): bit 0 = issue no MMAs, bit 1 = load no weight tiles
 };
 
 __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot, bool who) {
@@ -159,6 +165,12 @@ __device__ __forceinline__ void staged_store64(uint8_t* stage, int lane, const u
     __syncwarp();
 }
 
+// byte offset of the 16-byte chunk holding columns [8*chunk, 8*chunk + 8) of `row` inside the resident A tile
+__device__ __forceinline__ uint32_t a_tile_off(int row, int chunk) {
+    return static_cast<uint32_t>(chunk >> 3) * A_KB_BYTES + static_cast<uint32_t>(row) * 128u +
+           (static_cast<uint32_t>((chunk & 7) ^ (row & 7)) << 4);
+}
+
 __device__ __forceinline__ uint4 pack8_u4(const float* f) {
     bf16x8 p = pack8(f);
     return *reinterpret_cast<uint4*>(&p);
@@ -170,7 +182,8 @@ struct WorkerCtx {
     uint8_t* A_buf;
     uint8_t* stage;   // this warp's staging tile
     float *s_bias, *s_cbias, *s_gamma, *s_beta, *s_stat;
-    uint64_t *acc_full, *acc_empty, *a_ready, *h_ready;
+    uint64_t *acc_full, *acc_empty, *a_ready, *h_ready, *ring_free;
+    uint8_t* kv_ring;  // this warp's K|V row ring (inside the weight ring)
     uint32_t tmem_base;
     uint32_t use0, use1;  // completed uses of TMEM buffer 0 / 1 (scalars: no dynamically indexed state)
     int toggle;
@@ -243,11 +256,13 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
         if (KIND == EPI_CACHE) {
             uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
             staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
+        } else if (KIND == EPI_HID) {
+            // row-major scratch [tiles * 128][2048] (whole tiles are allocated: no row guard), re-read by TMA
+            uint8_t* gbase = reinterpret_cast<uint8_t*>(p.hbuf + static_cast<size_t>(c.r0 + c.quad * 32) * FDFF + gcol);
+            staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
         } else {
             // granule layout [tile][granule][row][16 B]: 32 lanes write 512 contiguous bytes per granule
-            const int grans = (KIND == EPI_QG) ? FD / 8 : FDFF / 8;
-            uint4* base = reinterpret_cast<uint4*>(KIND == EPI_QG ? p.qg : p.hbuf) +
-                          (static_cast<size_t>(c.tile) * grans + gcol / 8) * TILE_ROWS + row;
+            uint4* base = reinterpret_cast<uint4*>(p.qg) + (static_cast<size_t>(c.tile) * (FD / 8) + gcol / 8) * TILE_ROWS + row;
 #pragma unroll
             for (int g = 0; g < 4; ++g) base[static_cast<size_t>(g) * TILE_ROWS] = o[g];
         }
@@ -327,7 +342,7 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
             res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(c0 / 8 + g) * GRAN_BYTES + row * 16) = pack8_u4(f + 8 * g);
+            *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
     }
     release_acc(c, 4, 0);
     publish_a(c);
@@ -344,209 +359,277 @@ __device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) 
         pv[4 * i] = t4.x; pv[4 * i + 1] = t4.y; pv[4 * i + 2] = t4.z; pv[4 * i + 3] = t4.w;
     }
     float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS;
-#pragma unroll 2
-    for (int i = 0; i < TILE_ROWS / NW; ++i) {
-        const int row = c.ww * (TILE_ROWS / NW) + i;
-        const int grow = c.r0 + row;
-        float a[16];
+    constexpr int ROWS_PER_WARP = TILE_ROWS / NW;
+    // lane i fetches the token of the warp's row i; rows are then embedded four at a time (eight loads in flight)
+    int mytok = -1;
+    if (c.lane < ROWS_PER_WARP) {
+        const int grow = c.r0 + c.ww * ROWS_PER_WARP + c.lane;
         if (grow < p.R) {
-            const int tok = p.tokens[grow];
-            if (c.lane == 0) pad_t[grow] = (tok == p.pad_idx) ? 1 : 0;
-            const bf16x8* e = reinterpret_cast<const bf16x8*>(p.word_emb + static_cast<size_t>(tok) * FD + c.lane * 16);
-            unpack8(e[0], a);
-            unpack8(e[1], a + 8);
+            mytok = p.tokens[grow];
+            pad_t[grow] = (mytok == p.pad_idx) ? 1 : 0;
+        }
+    }
+#pragma unroll 1
+    for (int i0 = 0; i0 < ROWS_PER_WARP; i0 += 4) {
+        bf16x8 e[4][2];
+        int tk[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] += pv[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = 0.f;
+        for (int u = 0; u < 4; ++u) {
+            tk[u] = __shfl_sync(0xffffffffu, mytok, i0 + u);
+            const bf16x8* ep = reinterpret_cast<const bf16x8*>(p.word_emb + static_cast<size_t>(max(tk[u], 0)) * FD + c.lane * 16);
+            e[u][0] = ep[0];
+            e[u][1] = ep[1];
         }
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
-            *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(2 * c.lane + g) * GRAN_BYTES + row * 16) = pack8_u4(a + 8 * g);
+        for (int u = 0; u < 4; ++u) {
+            const int row = c.ww * ROWS_PER_WARP + i0 + u;
+            float a[16];
+            unpack8(e[u][0], a);
+            unpack8(e[u][1], a + 8);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            res[static_cast<size_t>(4 * c.lane + g) * TILE_ROWS + row] = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+            for (int j = 0; j < 16; ++j) a[j] = tk[u] >= 0 ? a[j] + pv[j] : 0.f;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+                *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, 2 * c.lane + g)) = pack8_u4(a + 8 * g);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                res[static_cast<size_t>(4 * c.lane + g) * TILE_ROWS + row] = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+        }
     }
+}
+
+// ------------------------------------------------------------------------------ streamed K|V rows
+// Both attention phases read 2 KB rows (K | V of one key, contiguous in HBM) that nothing else on the SM
+// needs.  Each worker warp streams them with cp.async through a private 4-slot ring carved out of the weight
+// ring (idle during an attention phase: the producer is gated until the phase ends), three rows in flight
+// while the fourth is consumed -- the loads are decoupled from the arithmetic and cost no registers.
+// Chunk k (16 bytes) of a 1 KB half-row is stored at position k/2 + 32*(k%2): lane l then reads its 16
+// columns as two conflict-free 16-byte accesses (positions l and 32 + l).
+constexpr int KV_SLOTS = 4;
+constexpr uint32_t KV_ROW_BYTES = 2 * FD * 2;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void kv_issue(uint8_t* slot, const bf16* src, int lane) {
+    const uint8_t* g = reinterpret_cast<const uint8_t*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = lane + 32 * i;
+        const int kk = k & 63;
+        const int pos = (k & 64) + (kk >> 1) + ((kk & 1) << 5);
+        cp_async_16(slot + pos * 16, g + k * 16);
+    }
+}
+
+__device__ __forceinline__ void kv_read(const uint8_t* slot, int lane, float* kf, float* vf) {
+    const bf16x8* s8 = reinterpret_cast<const bf16x8*>(slot);
+    unpack8(s8[lane], kf);
+    unpack8(s8[32 + lane], kf + 8);
+    unpack8(s8[64 + lane], vf);
+    unpack8(s8[96 + lane], vf + 8);
 }
 
 // Stateful self-attention of the new token over its beam history (attentions.py:297-304 with the running
 // mask of decoders.py:101-103): warp per row, lanes tile the 512-wide row (4 lanes per head), keys found
-// through the ancestry table, online softmax; output straight into the resident A tile.
+// through the ancestry table, online softmax; output straight into the resident A tile.  The (row, key)
+// pairs of the warp's 16 rows form ONE stream of K|V rows, so the pipeline never drains between rows.
 __device__ __forceinline__ void self_attention_phase(WorkerCtx& c, const FusedParams& p, const bf16* cache_l) {
     constexpr int EPL = 16;
+    constexpr int ROWS_PER_WARP = TILE_ROWS / NW;
     const int t = p.t, R = p.R;
     const size_t row_stride = 3 * FD;
     const size_t step_stride = static_cast<size_t>(R) * row_stride;
     const int nkeys = t + 1;
+    const int row0 = c.ww * ROWS_PER_WARP;
+    const int nrows = max(0, min(ROWS_PER_WARP, R - (c.r0 + row0)));
+    const int items = nrows * nkeys;
+    // slot | pad << 31 of every (row, key) of this warp, gathered with all lanes in parallel
+    int32_t* meta = reinterpret_cast<int32_t*>(c.stage);
+    for (int idx = c.lane; idx < items; idx += 32) {
+        const int i = idx / nkeys, j = idx - i * nkeys;
+        const int r = c.r0 + row0 + i;
+        const int sl = (j == t) ? r : p.ancestry[static_cast<size_t>(j) * R + r];
+        const int pad = p.padflag[static_cast<size_t>(j) * R + sl] != 0;
+        meta[idx] = sl | (pad << 31);
+    }
+    __syncwarp();
+    uint8_t* ring = c.kv_ring;
+    auto src_of = [&](int idx) -> const bf16* {
+        const int i = idx / nkeys, j = idx - i * nkeys;
+        return cache_l + j * step_stride + static_cast<size_t>(meta[idx] & 0x7fffffff) * row_stride + FD;
+    };
+#pragma unroll
+    for (int n = 0; n < KV_SLOTS - 1; ++n) {
+        if (n < items) kv_issue(ring + n * KV_ROW_BYTES, src_of(n), c.lane);
+        cp_async_commit();
+    }
+    float q[EPL], acc[EPL], m = -INFINITY, l = 0.f;
+    int i = 0, j = 0;
 #pragma unroll 1
-    for (int i = 0; i < TILE_ROWS / NW; ++i) {
-        const int row = c.ww * (TILE_ROWS / NW) + i;
-        const int r = c.r0 + row;
-        if (r >= R) continue;
-        float q[EPL];
-        {
-            const bf16x8* qp = reinterpret_cast<const bf16x8*>(cache_l + t * step_stride + r * row_stride + c.lane * EPL);
+    for (int n = 0; n < items; ++n) {
+        if (n + KV_SLOTS - 1 < items) kv_issue(ring + ((n + KV_SLOTS - 1) % KV_SLOTS) * KV_ROW_BYTES, src_of(n + KV_SLOTS - 1), c.lane);
+        cp_async_commit();
+        if (j == 0) {
+            const bf16x8* qp = reinterpret_cast<const bf16x8*>(cache_l + t * step_stride + static_cast<size_t>(c.r0 + row0 + i) * row_stride + c.lane * EPL);
             unpack8(qp[0], q);
             unpack8(qp[1], q + 8);
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) q[j] *= p.scale;
+            for (int e = 0; e < EPL; ++e) { q[e] *= p.scale; acc[e] = 0.f; }
+            m = -INFINITY;
+            l = 0.f;
         }
-        int slot_lo = 0, slot_hi = 0;       // key slot / pad flag of key index == lane (and lane + 32)
-        int pad_lo = 1, pad_hi = 1;
-        if (c.lane < nkeys) {
-            slot_lo = (c.lane == t) ? r : p.ancestry[static_cast<size_t>(c.lane) * R + r];
-            pad_lo = p.padflag[static_cast<size_t>(c.lane) * R + slot_lo] != 0;
+        cp_async_wait<KV_SLOTS - 1>();
+        __syncwarp();  // every lane's copies of item n have landed
+        if (meta[n] >= 0) {  // key not fed <pad> (warp-uniform)
+            float kf[EPL], vf[EPL];
+            kv_read(ring + (n % KV_SLOTS) * KV_ROW_BYTES, c.lane, kf, vf);
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) s = fmaf(q[e], kf[e], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            const float m_new = fmaxf(m, s);
+            const float corr = __expf(m - m_new);
+            const float pr = __expf(s - m_new);
+            l = l * corr + pr;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + pr * vf[e];
+            m = m_new;
         }
-        if (c.lane + 32 < nkeys) {
-            slot_hi = (c.lane + 32 == t) ? r : p.ancestry[static_cast<size_t>(c.lane + 32) * R + r];
-            pad_hi = p.padflag[static_cast<size_t>(c.lane + 32) * R + slot_hi] != 0;
+        __syncwarp();  // slot n % KV_SLOTS may be refilled by the next iteration's issue
+        if (++j == nkeys) {
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[e] *= inv;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+                *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row0 + i, 2 * c.lane + g)) = pack8_u4(acc + 8 * g);
+            j = 0;
+            ++i;
         }
-        float m = -INFINITY, l = 0.f, acc[EPL];
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
-        constexpr int UNROLL = 4;
-        for (int j0 = 0; j0 < nkeys; j0 += UNROLL) {
-            bf16x8 kreg[UNROLL][2], vreg[UNROLL][2];
-            bool pad[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int j = min(j0 + u, nkeys - 1);
-                const int sl = __shfl_sync(0xffffffffu, (j >> 5) ? slot_hi : slot_lo, j & 31);
-                pad[u] = __shfl_sync(0xffffffffu, (j >> 5) ? pad_hi : pad_lo, j & 31) != 0 || (j0 + u >= nkeys);
-                const bf16* base = cache_l + j * step_stride + sl * row_stride + c.lane * EPL;
-                kreg[u][0] = reinterpret_cast<const bf16x8*>(base + FD)[0];
-                kreg[u][1] = reinterpret_cast<const bf16x8*>(base + FD)[1];
-                vreg[u][0] = reinterpret_cast<const bf16x8*>(base + 2 * FD)[0];
-                vreg[u][1] = reinterpret_cast<const bf16x8*>(base + 2 * FD)[1];
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                float kf[EPL];
-                unpack8(kreg[u][0], kf);
-                unpack8(kreg[u][1], kf + 8);
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) s = fmaf(q[j], kf[j], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                if (pad[u]) continue;  // warp-uniform
-                const float m_new = fmaxf(m, s);
-                const float corr = __expf(m - m_new);
-                const float pr = __expf(s - m_new);
-                l = l * corr + pr;
-                float vf[EPL];
-                unpack8(vreg[u][0], vf);
-                unpack8(vreg[u][1], vf + 8);
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) acc[j] = acc[j] * corr + pr * vf[j];
-                m = m_new;
-            }
-        }
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) acc[j] *= inv;
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-            *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(2 * c.lane + g) * GRAN_BYTES + row * 16) = pack8_u4(acc + 8 * g);
     }
+    cp_async_wait<0>();
 }
 
 // Cross-attention over the image's cached K|V (decoders.py:23): warp per image, all heads and all of the
-// image's beams at once (lane owns 16 consecutive columns, 4 lanes per head), so every K/V row is read once
-// per step; keys two at a time with the next pair in flight.
+// image's beams at once (lane owns 16 consecutive columns, 4 lanes per head), so every K/V row crosses HBM
+// once per step; the (image, key) pairs of the warp's images form one stream of K|V rows.
 __device__ __forceinline__ void cross_attention_phase(WorkerCtx& c, const FusedParams& p, const bf16* kv_l) {
     constexpr int EPL = 16;
     const int beam = p.beam, n = p.n_keys;
     const int img_lo = c.r0 / beam;
     const int last_row = min(c.r0 + TILE_ROWS, p.R) - 1;
     const int img_hi = last_row / beam;
+    const int first = img_lo + c.ww;
+    const int nimg = first <= img_hi ? (img_hi - first) / NW + 1 : 0;
+    const int items = nimg * n;
     const uint4* qg = reinterpret_cast<const uint4*>(p.qg) + static_cast<size_t>(c.tile) * (FD / 8) * TILE_ROWS;
-#pragma unroll 1
-    for (int img = img_lo + c.ww; img <= img_hi; img += NW) {
-        const int row_begin = max(img * beam, c.r0);
-        const int row_end = min(img * beam + beam, last_row + 1);
-        const int nb = row_end - row_begin;
-        const int lr0 = row_begin - c.r0;
-        bf16x8 qreg[MAXB][2];
+    uint8_t* ring = c.kv_ring;
+    auto src_of = [&](int idx) -> const bf16* {
+        const int ii = idx / n, j = idx - ii * n;
+        return kv_l + (static_cast<size_t>(first + ii * NW) * n + j) * 2 * FD;
+    };
 #pragma unroll
-        for (int bb = 0; bb < MAXB; ++bb) {
-            if (bb < nb) {
+    for (int k = 0; k < KV_SLOTS - 1; ++k) {
+        if (k < items) kv_issue(ring + k * KV_ROW_BYTES, src_of(k), c.lane);
+        cp_async_commit();
+    }
+    bf16x8 qreg[MAXB][2];
+    float m[MAXB], l[MAXB], acc[MAXB][EPL];
+    uint32_t maskbits = 0;  // bit i: key lane + 32*i of the current image is padding
+    int ii = 0, j = 0, nb = 0, lr0 = 0;
+#pragma unroll 1
+    for (int k = 0; k < items; ++k) {
+        if (k + KV_SLOTS - 1 < items) kv_issue(ring + ((k + KV_SLOTS - 1) % KV_SLOTS) * KV_ROW_BYTES, src_of(k + KV_SLOTS - 1), c.lane);
+        cp_async_commit();
+        if (j == 0) {
+            const int img = first + ii * NW;
+            const int row_begin = max(img * beam, c.r0);
+            nb = min(img * beam + beam, last_row + 1) - row_begin;
+            lr0 = row_begin - c.r0;
+#pragma unroll
+            for (int bb = 0; bb < MAXB; ++bb) {
+                const int lr = lr0 + min(bb, nb - 1);
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const uint4 u = qg[static_cast<size_t>(2 * c.lane + g) * TILE_ROWS + lr0 + bb];
+                    const uint4 u = qg[static_cast<size_t>(2 * c.lane + g) * TILE_ROWS + lr];
                     qreg[bb][g] = *reinterpret_cast<const bf16x8*>(&u);
                 }
-            } else {
-                qreg[bb][0] = qreg[0][0];
-                qreg[bb][1] = qreg[0][1];
+                m[bb] = -INFINITY;
+                l[bb] = 0.f;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) acc[bb][e] = 0.f;
             }
-        }
-        float m[MAXB], l[MAXB], acc[MAXB][EPL];
+            maskbits = 0;
+            if (p.enc_mask != nullptr) {
+                const uint8_t* mrow = p.enc_mask + static_cast<size_t>(img) * n;
 #pragma unroll
-        for (int bb = 0; bb < MAXB; ++bb) {
-            m[bb] = -INFINITY;
-            l[bb] = 0.f;
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) acc[bb][j] = 0.f;
-        }
-        const bf16* kvb = kv_l + static_cast<size_t>(img) * n * 2 * FD + c.lane * EPL;
-        const uint8_t* mrow = p.enc_mask ? p.enc_mask + static_cast<size_t>(img) * n : nullptr;
-#pragma unroll 1
-        for (int j0 = 0; j0 < n; j0 += 2) {
-            bf16x8 kreg[2][2], vreg[2][2];
-            bool livek[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = j0 + u;
-                livek[u] = j < n && !(mrow && mrow[min(j, n - 1)]);
-                const bf16* base = kvb + static_cast<size_t>(min(j, n - 1)) * 2 * FD;
-                kreg[u][0] = reinterpret_cast<const bf16x8*>(base)[0];
-                kreg[u][1] = reinterpret_cast<const bf16x8*>(base)[1];
-                vreg[u][0] = reinterpret_cast<const bf16x8*>(base + FD)[0];
-                vreg[u][1] = reinterpret_cast<const bf16x8*>(base + FD)[1];
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (!livek[u]) continue;  // warp-uniform
-                float kf[EPL], vf[EPL];
-                unpack8(kreg[u][0], kf);
-                unpack8(kreg[u][1], kf + 8);
-                unpack8(vreg[u][0], vf);
-                unpack8(vreg[u][1], vf + 8);
-#pragma unroll
-                for (int bb = 0; bb < MAXB; ++bb) {
-                    if (bb >= nb) continue;  // warp-uniform
-                    float qf[EPL];
-                    unpack8(qreg[bb][0], qf);
-                    unpack8(qreg[bb][1], qf + 8);
-                    float s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < EPL; ++j) s = fmaf(qf[j], kf[j], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s *= p.scale;
-                    const float m_new = fmaxf(m[bb], s);
-                    const float corr = __expf(m[bb] - m_new);
-                    const float pr = __expf(s - m_new);
-                    l[bb] = l[bb] * corr + pr;
-#pragma unroll
-                    for (int j = 0; j < EPL; ++j) acc[bb][j] = acc[bb][j] * corr + pr * vf[j];
-                    m[bb] = m_new;
+                for (int w = 0; w < 4; ++w) {
+                    const int key = c.lane + 32 * w;
+                    if (key < n && mrow[key]) maskbits |= 1u << w;
                 }
             }
         }
+        const bool masked = ((__shfl_sync(0xffffffffu, maskbits, j & 31) >> (j >> 5)) & 1u) != 0;
+        cp_async_wait<KV_SLOTS - 1>();
+        __syncwarp();
+        if (!masked) {  // warp-uniform
+            float kf[EPL], vf[EPL];
+            kv_read(ring + (k % KV_SLOTS) * KV_ROW_BYTES, c.lane, kf, vf);
 #pragma unroll
-        for (int bb = 0; bb < MAXB; ++bb) {
-            if (bb >= nb) continue;
-            const float inv = l[bb] > 0.f ? 1.f / l[bb] : 0.f;
-            float o[EPL];
+            for (int bb = 0; bb < MAXB; ++bb) {
+                if (bb >= nb) continue;  // warp-uniform
+                float qf[EPL];
+                unpack8(qreg[bb][0], qf);
+                unpack8(qreg[bb][1], qf + 8);
+                float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) o[j] = acc[bb][j] * inv;
+                for (int e = 0; e < EPL; ++e) s = fmaf(qf[e], kf[e], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s *= p.scale;
+                const float m_new = fmaxf(m[bb], s);
+                const float corr = __expf(m[bb] - m_new);
+                const float pr = __expf(s - m_new);
+                l[bb] = l[bb] * corr + pr;
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
-                *reinterpret_cast<uint4*>(c.A_buf + static_cast<size_t>(2 * c.lane + g) * GRAN_BYTES + (lr0 + bb) * 16) = pack8_u4(o + 8 * g);
+                for (int e = 0; e < EPL; ++e) acc[bb][e] = acc[bb][e] * corr + pr * vf[e];
+                m[bb] = m_new;
+            }
         }
+        __syncwarp();
+        if (++j == n) {
+#pragma unroll
+            for (int bb = 0; bb < MAXB; ++bb) {
+                if (bb >= nb) continue;
+                const float inv = l[bb] > 0.f ? 1.f / l[bb] : 0.f;
+                float o[EPL];
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) o[e] = acc[bb][e] * inv;
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+                    *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(lr0 + bb, 2 * c.lane + g)) = pack8_u4(o + 8 * g);
+            }
+            j = 0;
+            ++ii;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// end of an attention phase: the resident A tile is complete and the weight ring is handed back
+__device__ __forceinline__ void publish_attention(WorkerCtx& c) {
+    fence_proxy_async();
+    __syncwarp();
+    if (c.lane == 0) {
+        mbar_arrive(c.a_ready);
+        mbar_arrive(c.ring_free);
     }
 }
 
@@ -614,6 +697,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* a_ready = acc_empty + 2;
     uint64_t* h_ready = a_ready + 1;
+    uint64_t* ring_free = h_ready + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
     const int warp = threadIdx.x >> 5;
@@ -625,6 +709,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w512)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w2)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_vocab)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_h)) : "memory");
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -633,6 +718,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NW); }
             mbar_init(a_ready, NW);
             mbar_init(h_ready, NW);
+            mbar_init(ring_free, NW);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -650,19 +736,28 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
         if (lane == 0) {
-            uint32_t bcount = 0, acount = 0, hphase = 0;
-            const uint8_t* hsrc = reinterpret_cast<const uint8_t*>(p.hbuf) + static_cast<size_t>(tile) * (FDFF / 8) * GRAN_BYTES;
+            uint32_t bcount = 0, acount = 0, hphase = 0, rphase = 0;
+            const uint32_t nbr = static_cast<uint32_t>(p.dbg_ring);
             for (int ji = 0; ji < njobs; ++ji) {
                 const Job job = get_job(p, ji);
                 const int nch = job.ntiles / job.chunk;
+                if (ji < p.n_layers * 6 && (ji % 6 == 1 || ji % 6 == 3)) {
+                    // fc_o follows an attention phase, which borrows the weight ring for its K|V rows
+                    mbar_wait(ring_free, rphase);
+                    rphase ^= 1;
+                }
                 for (int c = 0; c < nch; ++c) {
                     for (int kb = 0; kb < job.kblocks; ++kb) {
                         for (int j = 0; j < job.chunk; ++j) {
-                            const uint32_t s = bcount % NB;
-                            mbar_wait(&b_empty[s], ((bcount / NB) & 1) ^ 1);
-                            mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
-                            tma_load_2d(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
-                                        job.row0 + (c * job.chunk + j) * 128);
+                            const uint32_t s = bcount % nbr;
+                            mbar_wait(&b_empty[s], ((bcount / nbr) & 1) ^ 1);
+                            if (p.dbg_skip & 2) {
+                                mbar_arrive(&b_full[s]);
+                            } else {
+                                mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
+                                tma_load_2d(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
+                                            job.row0 + (c * job.chunk + j) * 128);
+                            }
                             ++bcount;
                         }
                         if (job.stream) {
@@ -673,8 +768,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                             const uint32_t slot = acount % A_SLOTS;
                             mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1);
                             mbar_arrive_expect_tx(&a_full[slot], A_KB_BYTES);
-                            bulk_load_1d(A_buf + slot * A_KB_BYTES, hsrc + static_cast<size_t>(kb) * A_KB_BYTES, A_KB_BYTES,
-                                         &a_full[slot]);
+                            tma_load_2d(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
                             ++acount;
                         }
                     }
@@ -687,9 +781,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_instr_desc(128, 128);
-            const uint32_t lbo = p.desc_swap ? 128u : GRAN_BYTES;
-            const uint32_t sbo = p.desc_swap ? GRAN_BYTES : 128u;
             uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
+            const uint32_t nbr = static_cast<uint32_t>(p.dbg_ring);
             int toggle = 0;
             for (int ji = 0; ji < njobs; ++ji) {
                 const Job job = get_job(p, ji);
@@ -712,25 +805,29 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     }
                     tcgen05_fence_after();
                     for (int kb = 0; kb < job.kblocks; ++kb) {
-                        uint32_t a_addr;
+                        const uint8_t* a_tile;
                         uint32_t slot = 0;
                         if (job.stream) {
                             slot = acount % A_SLOTS;
                             mbar_wait(&a_full[slot], (acount / A_SLOTS) & 1);
-                            a_addr = smem_u32(A_buf + slot * A_KB_BYTES);
+                            a_tile = A_buf + slot * A_KB_BYTES;
                         } else {
-                            a_addr = smem_u32(A_buf + kb * A_KB_BYTES);
+                            a_tile = A_buf + kb * A_KB_BYTES;
                         }
+                        const uint64_t a_desc = make_smem_desc(a_tile);
                         for (int j = 0; j < job.chunk; ++j) {
-                            const uint32_t s = bcount % NB;
-                            mbar_wait(&b_full[s], (bcount / NB) & 1);
+                            const uint32_t s = bcount % nbr;
+                            mbar_wait(&b_full[s], (bcount / nbr) & 1);
                             tcgen05_fence_after();
                             const uint64_t b_desc = make_smem_desc(B_ring + s * B_STAGE_BYTES);
+                            if (!(p.dbg_skip & 1))
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                const uint64_t a_desc = make_smem_desc_noswizzle(a_addr + k * 2 * GRAN_BYTES, lbo, sbo);
-                                umma_bf16(tmem_base + colbase + j * 128, a_desc, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                            }
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int rep = 0; rep < p.dbg_mma_repeat; ++rep)
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                    umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
                             umma_commit(&b_empty[s]);
                             ++bcount;
                         }
@@ -775,6 +872,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.acc_empty = acc_empty;
         c.a_ready = a_ready;
         c.h_ready = h_ready;
+        c.ring_free = ring_free;
+        c.kv_ring = B_ring + c.ww * KV_SLOTS * KV_ROW_BYTES;
         c.tmem_base = tmem_base;
         c.use0 = c.use1 = 0;
         c.toggle = 0;
@@ -801,7 +900,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             workers_sync();  // q|k|v of every row of the tile are in the cache
             fstamp(p, tile, sb + 1, tr);
             self_attention_phase(c, p, cache_l);
-            publish_a(c);
+            publish_attention(c);
             fstamp(p, tile, sb + 2, tr);
             epilogue_layernorm(c, p, W.b_o1, W.g1, W.be1, nullptr);
             fstamp(p, tile, sb + 3, tr);
@@ -809,7 +908,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             workers_sync();
             fstamp(p, tile, sb + 4, tr);
             cross_attention_phase(c, p, p.cross_kv + static_cast<size_t>(L) * p.cross_layer_stride);
-            publish_a(c);
+            publish_attention(c);
             fstamp(p, tile, sb + 5, tr);
             epilogue_layernorm(c, p, W.b_o2, W.g2, W.be2, nullptr);
             fstamp(p, tile, sb + 6, tr);
@@ -849,7 +948,7 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     CAP_REQUIRE(d->d_model == FD && d->heads == FHEADS && d->d_ff == FDFF, "cap_fused_create: needs d_model 512, 8 heads, d_ff 2048");
     CAP_REQUIRE(d->n_layers >= 1 && d->n_layers <= MAX_FUSED_LAYERS, "cap_fused_create: 1..%d layers", MAX_FUSED_LAYERS);
     CAP_REQUIRE(d->beam >= 1 && d->beam <= MAXB, "cap_fused_create: beam must be 1..%d", MAXB);
-    CAP_REQUIRE(d->max_rows > 0 && d->vocab > 8 && d->max_len > 0, "cap_fused_create: bad sizes");
+    CAP_REQUIRE(d->max_rows > 0 && d->vocab > 8 && d->max_len > 0 && d->max_len <= 40, "cap_fused_create: bad sizes (max_len <= 40)");
     CAP_REQUIRE(d->ld_logits % 32 == 0 && d->ld_logits >= d->vocab, "cap_fused_create: ld_logits must be a multiple of 32");
     cap_fused_decoder* f = new cap_fused_decoder();
     FusedParams& p = f->base;
@@ -909,6 +1008,8 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     cudaMemset(qg, 0, tiles * TILE_ROWS * FD * 2);
     cudaMemset(hb, 0, tiles * TILE_ROWS * FDFF * 2);
     p.res = static_cast<float*>(res); p.qg = static_cast<bf16*>(qg); p.hbuf = static_cast<bf16*>(hb);
+    rc = cap_gemm::make_tmap(&p.map_h, hb, static_cast<int>(tiles) * TILE_ROWS, FDFF, FDFF, 128);
+    if (rc != CAP_OK) return fail(rc);
     if (cudaFuncSetAttribute(decode_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
@@ -938,11 +1039,15 @@ extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_k
     CAP_REQUIRE(t >= 0 && t < p.T, "cap_fused_decode_step: step %d outside [0,%d)", t, p.T);
     const int R = B * p.beam;
     const int tiles = (R + TILE_ROWS - 1) / TILE_ROWS;
-    CAP_REQUIRE(B > 0 && tiles <= f->tiles && n_keys > 0, "cap_fused_decode_step: batch %d exceeds the reservation", B);
+    CAP_REQUIRE(B > 0 && tiles <= f->tiles && n_keys > 0 && n_keys <= 128, "cap_fused_decode_step: batch %d / %d keys unsupported", B, n_keys);
     p.t = t; p.R = R; p.B = B; p.n_keys = n_keys;
-    static const int swap = getenv("OPENVIIC_FUSED_DESC_SWAP") ? atoi(getenv("OPENVIIC_FUSED_DESC_SWAP")) : 0;
-    p.desc_swap = swap;
     p.trace = g_fused_trace;
+    static const int dbg_rep = getenv("OPENVIIC_FUSED_DBG_MMA_REPEAT") ? atoi(getenv("OPENVIIC_FUSED_DBG_MMA_REPEAT")) : 0;
+    static const int dbg_ring = getenv("OPENVIIC_FUSED_DBG_RING") ? atoi(getenv("OPENVIIC_FUSED_DBG_RING")) : NB;
+    p.dbg_mma_repeat = dbg_rep;
+    static const int dbg_skip = getenv("OPENVIIC_FUSED_DBG_SKIP") ? atoi(getenv("OPENVIIC_FUSED_DBG_SKIP")) : 0;
+    p.dbg_skip = dbg_skip;
+    p.dbg_ring = dbg_ring < 1 ? 1 : (dbg_ring > NB ? NB : dbg_ring);
     cap_launch_kernel(decode_step_fused_kernel, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
                       static_cast<cudaStream_t>(stream), 1, p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);

@@ -434,7 +434,8 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     const char* env = getenv("OPENVIIC_FUSED_DECODE");
     const bool want_fused = !env || atoi(env) != 0;
     if (want_fused && m.decoder_kind == CAP_DEC_PLAIN && !m.aoa_dec_self && !m.aoa_dec_cross && d == 512 && m.heads == 8 &&
-        m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && e->vocab_fc.b == nullptr &&
+        m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && T <= 40 && n_tokens <= 128 &&
+        e->vocab_fc.b == nullptr &&
         e->vocab_chunks <= 512) {
         std::vector<cap_fused_layer> layers(m.dec_layers);
         for (int l = 0; l < m.dec_layers; ++l) {
