@@ -66,7 +66,7 @@ constexpr uint32_t OFF_STAT = OFF_BETA + FD * 4;       // [2 (sum, sumsq)][2 hal
 constexpr uint32_t OFF_BARS = OFF_STAT + 4 * TILE_ROWS * 4;
 constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1;
 constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
-constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16 + 1024;  // + alignment slack
+constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16;
 
 struct FusedLayerP {
     const float *b_qkv, *b_o1, *g1, *be1, *b_q, *b_o2, *g2, *be2, *b_w1, *b_w2, *g3, *be3;
@@ -100,8 +100,6 @@ struct FusedParams {
     int t, T, R, B, beam;
     float scale;
     unsigned long long* trace;  // debug: 64 %globaltimer stamps per CTA (cap_debug_fused_trace), else nullptr
-    int dbg_mma_repeat;      // debug (timing only, wrong results): issue every MMA this many extra times
-    int dbg_ring;            // debug: weight ring depth actually used (1..NB)
     int dbg_skip;            // debug (timing only): bit 0 = issue no MMAs, bit 1 = load no weight tiles
 };
 
@@ -110,6 +108,7 @@ __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot,
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[static_cast<size_t>(tile) * 64 + slot] = t;
+        if (slot == 0 || slot == 1 + 8 * 3 + 2) p.trace[static_cast<size_t>(tile) * 64 + (slot == 0 ? 60 : 61)] = clock64();
     }
 }
 
@@ -220,7 +219,7 @@ __device__ __forceinline__ void release_acc(WorkerCtx& c, int chunk, int b) {
 
 // the resident A tile was written with ordinary stores: make it visible to tcgen05.mma and tell the issuer
 __device__ __forceinline__ void publish_a(WorkerCtx& c) {
-    fence_proxy_async();
+    fence_proxy_async_smem();
     __syncwarp();
     if (c.lane == 0) mbar_arrive(c.a_ready);
 }
@@ -232,17 +231,23 @@ template <int KIND>
 __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
                                                bf16* dst_rowmajor, int ld_rowmajor) {
     // stage this chunk's 256 bias values (double-buffered by chunk parity; see the barrier note below)
+    const bool tr = (KIND == EPI_HID && chunk_idx == 3 && c.ww == 0 && c.lane == 0);
+    fstamp(p, c.tile, 40, tr);
     float* sb = c.s_cbias + (chunk_idx & 1) * 256;
     sb[c.wtid] = __ldg(bias + chunk_idx * 256 + c.wtid);
     workers_sync();  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
+    fstamp(p, c.tile, 41, tr);
     const int b = acquire_acc(c, 2);
+    fstamp(p, c.tile, 42, tr);
     const int row = c.quad * 32 + c.lane;
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const int colc = c.half * 128 + i * 32;
         uint32_t v[32];
+        fstamp(p, c.tile, 48, tr && i == 1);
         tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
         tmem_ld_wait();
+        fstamp(p, c.tile, 49, tr && i == 1);
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -252,6 +257,8 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
         uint4 o[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) o[g] = pack8_u4(f + 8 * g);
+        if (tr && i == 1 && o[0].x == 0x12345678u) fstamp(p, c.tile, 63, true);  // keep the math before the stamp
+        fstamp(p, c.tile, 50, tr && i == 1);
         const int gcol = chunk_idx * 256 + colc;
         if (KIND == EPI_CACHE) {
             uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
@@ -266,8 +273,10 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
 #pragma unroll
             for (int g = 0; g < 4; ++g) base[static_cast<size_t>(g) * TILE_ROWS] = o[g];
         }
+        fstamp(p, c.tile, 43 + i, tr);
     }
     release_acc(c, 2, b);
+    fstamp(p, c.tile, 47, tr);
 }
 
 // Epilogue of an N = 512 projection followed by residual + LayerNorm (attentions.py:308-309,
@@ -625,7 +634,7 @@ __device__ __forceinline__ void cross_attention_phase(WorkerCtx& c, const FusedP
 
 // end of an attention phase: the resident A tile is complete and the weight ring is handed back
 __device__ __forceinline__ void publish_attention(WorkerCtx& c) {
-    fence_proxy_async();
+    fence_proxy_async_smem();
     __syncwarp();
     if (c.lane == 0) {
         mbar_arrive(c.a_ready);
@@ -684,8 +693,10 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
 
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
-    extern __shared__ uint8_t fused_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fused_smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B tiles) comes from the declaration: rounding the address up by hand
+    // goes through an integer and makes every later access a generic LD/ST instead of LDS/STS.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* A_buf = smem + OFF_A;
     uint8_t* B_ring = smem + OFF_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
@@ -735,22 +746,22 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
-        if (lane == 0) {
-            uint32_t bcount = 0, acount = 0, hphase = 0, rphase = 0;
-            const uint32_t nbr = static_cast<uint32_t>(p.dbg_ring);
-            for (int ji = 0; ji < njobs; ++ji) {
-                const Job job = get_job(p, ji);
-                const int nch = job.ntiles / job.chunk;
-                if (ji < p.n_layers * 6 && (ji % 6 == 1 || ji % 6 == 3)) {
-                    // fc_o follows an attention phase, which borrows the weight ring for its K|V rows
-                    mbar_wait(ring_free, rphase);
-                    rphase ^= 1;
-                }
-                for (int c = 0; c < nch; ++c) {
-                    for (int kb = 0; kb < job.kblocks; ++kb) {
-                        for (int j = 0; j < job.chunk; ++j) {
-                            const uint32_t s = bcount % nbr;
-                            mbar_wait(&b_empty[s], ((bcount / nbr) & 1) ^ 1);
+        // The whole warp runs the loop (uniform control flow); one elected lane issues the copies.
+        uint32_t bcount = 0, acount = 0, hphase = 0, rphase = 0;
+        for (int ji = 0; ji < njobs; ++ji) {
+            const Job job = get_job(p, ji);
+            const int nch = job.ntiles / job.chunk;
+            if (ji < p.n_layers * 6 && (ji % 6 == 1 || ji % 6 == 3)) {
+                // fc_o follows an attention phase, which borrows the weight ring for its K|V rows
+                mbar_wait(ring_free, rphase);
+                rphase ^= 1;
+            }
+            for (int c = 0; c < nch; ++c) {
+                for (int kb = 0; kb < job.kblocks; ++kb) {
+                    for (int j = 0; j < job.chunk; ++j) {
+                        const uint32_t s = bcount % NB;
+                        mbar_wait(&b_empty[s], ((bcount / NB) & 1) ^ 1);
+                        if (elect_one_sync()) {
                             if (p.dbg_skip & 2) {
                                 mbar_arrive(&b_full[s]);
                             } else {
@@ -758,98 +769,106 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                                 tma_load_2d(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
                                             job.row0 + (c * job.chunk + j) * 128);
                             }
-                            ++bcount;
                         }
-                        if (job.stream) {
-                            if (kb == 0) {  // the workers have written (and proxy-fenced) the whole hidden tile
-                                mbar_wait(h_ready, hphase);
-                                hphase ^= 1;
-                            }
-                            const uint32_t slot = acount % A_SLOTS;
-                            mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1);
+                        __syncwarp();
+                        ++bcount;
+                    }
+                    if (job.stream) {
+                        if (kb == 0) {  // the workers have written (and proxy-fenced) the whole hidden tile
+                            mbar_wait(h_ready, hphase);
+                            hphase ^= 1;
+                        }
+                        const uint32_t slot = acount % A_SLOTS;
+                        mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1);
+                        if (elect_one_sync()) {
                             mbar_arrive_expect_tx(&a_full[slot], A_KB_BYTES);
                             tma_load_2d(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
-                            ++acount;
                         }
+                        __syncwarp();
+                        ++acount;
                     }
                 }
             }
         }
-        __syncwarp();
         pdl_launch_dependents();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_instr_desc(128, 128);
-            uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
-            const uint32_t nbr = static_cast<uint32_t>(p.dbg_ring);
-            int toggle = 0;
-            for (int ji = 0; ji < njobs; ++ji) {
-                const Job job = get_job(p, ji);
-                const int nch = job.ntiles / job.chunk;
-                if (!job.stream) {
-                    mbar_wait(a_ready, ar & 1);
-                    ++ar;
+        // Uniform control flow for the whole warp; the elected lane issues tcgen05.mma / tcgen05.commit.
+        constexpr uint32_t idesc = make_instr_desc(128, 128);
+        uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
+        int toggle = 0;
+        for (int ji = 0; ji < njobs; ++ji) {
+            const Job job = get_job(p, ji);
+            const int nch = job.ntiles / job.chunk;
+            if (!job.stream) {
+                mbar_wait(a_ready, ar & 1);
+                ++ar;
+            }
+            tcgen05_fence_after();
+            for (int c = 0; c < nch; ++c) {
+                int b = 0;
+                uint32_t colbase = 0;
+                if (job.chunk == 4) {
+                    mbar_wait(&acc_empty[0], (use0 & 1) ^ 1);
+                    mbar_wait(&acc_empty[1], (use1 & 1) ^ 1);
+                } else {
+                    b = toggle;
+                    mbar_wait(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
+                    colbase = b * 256;
                 }
                 tcgen05_fence_after();
-                for (int c = 0; c < nch; ++c) {
-                    int b = 0;
-                    uint32_t colbase = 0;
-                    if (job.chunk == 4) {
-                        mbar_wait(&acc_empty[0], (use0 & 1) ^ 1);
-                        mbar_wait(&acc_empty[1], (use1 & 1) ^ 1);
+                for (int kb = 0; kb < job.kblocks; ++kb) {
+                    const uint8_t* a_tile;
+                    uint32_t slot = 0;
+                    if (job.stream) {
+                        slot = acount % A_SLOTS;
+                        mbar_wait(&a_full[slot], (acount / A_SLOTS) & 1);
+                        a_tile = A_buf + slot * A_KB_BYTES;
                     } else {
-                        b = toggle;
-                        mbar_wait(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
-                        colbase = b * 256;
+                        a_tile = A_buf + kb * A_KB_BYTES;
                     }
-                    tcgen05_fence_after();
-                    for (int kb = 0; kb < job.kblocks; ++kb) {
-                        const uint8_t* a_tile;
-                        uint32_t slot = 0;
-                        if (job.stream) {
-                            slot = acount % A_SLOTS;
-                            mbar_wait(&a_full[slot], (acount / A_SLOTS) & 1);
-                            a_tile = A_buf + slot * A_KB_BYTES;
-                        } else {
-                            a_tile = A_buf + kb * A_KB_BYTES;
-                        }
-                        const uint64_t a_desc = make_smem_desc(a_tile);
-                        for (int j = 0; j < job.chunk; ++j) {
-                            const uint32_t s = bcount % nbr;
-                            mbar_wait(&b_full[s], (bcount / nbr) & 1);
-                            tcgen05_fence_after();
-                            const uint64_t b_desc = make_smem_desc(B_ring + s * B_STAGE_BYTES);
-                            if (!(p.dbg_skip & 1))
-#pragma unroll
-                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                            for (int rep = 0; rep < p.dbg_mma_repeat; ++rep)
+                    const uint64_t a_desc = make_smem_desc(a_tile);
+                    for (int j = 0; j < job.chunk; ++j) {
+                        const uint32_t s = bcount % NB;
+                        mbar_wait(&b_full[s], (bcount / NB) & 1);
+                        tcgen05_fence_after();
+                        const uint64_t b_desc = make_smem_desc(B_ring + s * B_STAGE_BYTES);
+                        if (elect_one_sync()) {
+                            if (!(p.dbg_skip & 1)) {
 #pragma unroll
                                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                    umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
-                            umma_commit(&b_empty[s]);
-                            ++bcount;
+                                    umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                              (kb | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&b_empty[s]);  // stage reusable once these MMAs have read it
                         }
-                        if (job.stream) {
-                            umma_commit(&a_empty[slot]);
-                            ++acount;
-                        }
+                        __syncwarp();
+                        ++bcount;
                     }
+                    if (job.stream) {
+                        if (elect_one_sync()) umma_commit(&a_empty[slot]);
+                        __syncwarp();
+                        ++acount;
+                    }
+                }
+                if (elect_one_sync()) {
                     if (job.chunk == 4) {
                         umma_commit(&acc_full[0]);
                         umma_commit(&acc_full[1]);
-                        ++use0; ++use1;
-                        toggle = 0;
                     } else {
                         umma_commit(&acc_full[b]);
-                        if (b) ++use1; else ++use0;
-                        toggle ^= 1;
                     }
+                }
+                __syncwarp();
+                if (job.chunk == 4) {
+                    ++use0; ++use1;
+                    toggle = 0;
+                } else {
+                    if (b) ++use1; else ++use0;
+                    toggle ^= 1;
                 }
             }
         }
-        __syncwarp();
         pdl_launch_dependents();
     }
     } else {
@@ -1042,12 +1061,14 @@ extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_k
     CAP_REQUIRE(B > 0 && tiles <= f->tiles && n_keys > 0 && n_keys <= 128, "cap_fused_decode_step: batch %d / %d keys unsupported", B, n_keys);
     p.t = t; p.R = R; p.B = B; p.n_keys = n_keys;
     p.trace = g_fused_trace;
-    static const int dbg_rep = getenv("OPENVIIC_FUSED_DBG_MMA_REPEAT") ? atoi(getenv("OPENVIIC_FUSED_DBG_MMA_REPEAT")) : 0;
-    static const int dbg_ring = getenv("OPENVIIC_FUSED_DBG_RING") ? atoi(getenv("OPENVIIC_FUSED_DBG_RING")) : NB;
-    p.dbg_mma_repeat = dbg_rep;
     static const int dbg_skip = getenv("OPENVIIC_FUSED_DBG_SKIP") ? atoi(getenv("OPENVIIC_FUSED_DBG_SKIP")) : 0;
     p.dbg_skip = dbg_skip;
-    p.dbg_ring = dbg_ring < 1 ? 1 : (dbg_ring > NB ? NB : dbg_ring);
+    static bool backoff_set = false;
+    if (!backoff_set) {
+        backoff_set = true;
+        const unsigned int ns = getenv("OPENVIIC_FUSED_DBG_BACKOFF_NS") ? static_cast<unsigned int>(atoi(getenv("OPENVIIC_FUSED_DBG_BACKOFF_NS"))) : 0u;
+        if (ns) cudaMemcpyToSymbol(cap_ptx::g_mbar_backoff_ns, &ns, sizeof(ns));
+    }
     cap_launch_kernel(decode_step_fused_kernel, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
                       static_cast<cudaStream_t>(stream), 1, p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);

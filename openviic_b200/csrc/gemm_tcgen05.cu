@@ -84,8 +84,10 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // alignment from the declaration, not from integer arithmetic (which would turn every shared-memory access
+    // of the epilogue into a generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int stages = p.num_stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.pipe_bytes);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -128,14 +130,17 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(p, 1);
 
+    // Producer and MMA warps run their loops with the WHOLE warp (uniform control flow) and elect one lane for
+    // the TMA / tcgen05 instructions: issued from an `if (lane == 0)` region every tcgen05.mma was wrapped in an
+    // ELECT / R2UR / BRA.U.ANY loop and cost the single thread ~200 cycles (3x the MMA's own 64-cycle floor).
     if (warp == 0) {
-        if (lane == 0) {
-            pdl_wait();  // A (and only A) may still be in flight from the previous kernel
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t phase = (kb / stages) & 1;
-                mbar_wait(&empty_bar[s], phase ^ 1);
-                uint8_t* a_tile = smem + s * STAGE_BYTES;
+        pdl_wait();  // A (and only A) may still be in flight from the previous kernel
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % stages;
+            const uint32_t phase = (kb / stages) & 1;
+            mbar_wait(&empty_bar[s], phase ^ 1);
+            uint8_t* a_tile = smem + s * STAGE_BYTES;
+            if (elect_one_sync()) {
                 if constexpr (CTA2) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // both CTAs' four tiles
                     tma_load_2d_2sm(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
@@ -148,34 +153,39 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
                 if (kb == 0) stamp(p, 2);
             }
+            __syncwarp();
         }
         if constexpr (LN) { __syncwarp(); cluster_sync(); cluster_sync(); }  // the epilogue's two exchanges
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             constexpr uint32_t idesc = make_instr_desc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(&full_bar[s], phase);
-                if (kb == 0) stamp(p, 3);
                 tcgen05_fence_after();
                 const uint8_t* a_tile = smem + s * STAGE_BYTES;
                 const uint64_t a_desc = make_smem_desc(a_tile);
                 const uint64_t b_desc = make_smem_desc(a_tile + A_TILE_BYTES);
+                if (elect_one_sync()) {
+                    if (kb == 0) stamp(p, 3);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                    if constexpr (CTA2)
-                        umma_bf16_2sm(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    else
-                        umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                        if constexpr (CTA2)
+                            umma_bf16_2sm(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    // stage reusable (in both CTAs) once these MMAs have read it
+                    if constexpr (CTA2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+                    if (kb == num_kb - 1) {  // accumulator complete (in both CTAs)
+                        if constexpr (CTA2) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
+                        stamp(p, 4);
+                    }
                 }
-                // stage reusable (in both CTAs) once these MMAs have read it
-                if constexpr (CTA2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+                __syncwarp();
             }
-            // accumulator complete (in both CTAs)
-            if constexpr (CTA2) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
-            stamp(p, 4);
         }
         if constexpr (LN) { __syncwarp(); cluster_sync(); cluster_sync(); }
     } else {

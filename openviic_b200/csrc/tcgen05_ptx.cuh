@@ -22,6 +22,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 
+// debug: nanoseconds to sleep after a failed try_wait (0 = poll again at once)
+static __device__ unsigned int g_mbar_backoff_ns = 0;
+
 // Bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -38,6 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
+        if (g_mbar_backoff_ns) __nanosleep(g_mbar_backoff_ns);
         if (spin == 64) start = clock64();
         if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
     }
@@ -194,8 +198,28 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t smem_addr,
     return desc;
 }
 
+// One lane of the (converged) warp is elected.  tcgen05.mma / tcgen05.commit / TMA are uniform-datapath
+// instructions: guarded by elect.sync, ptxas emits them once with uniform registers.  Guarded by
+// `if (lane == 0)` instead, it wraps every one of them in an ELECT / R2UR / BRA.U.ANY loop over the active
+// lanes, and a single thread then needs ~200 cycles per MMA issue (measured, profiles/README.md).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 %%rx;\n"
+        ".reg .pred %%px;\n"
+        "elect.sync %%rx|%%px, %1;\n"
+        "@%%px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // generic-proxy writes (st.shared / st.global) made visible to the async proxy (tcgen05.mma operand reads, TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// same for shared memory only (the unqualified form costs a MEMBAR.ALL.GPU)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -39,6 +39,12 @@ for t in range(T):
         for tile in (0, tiles // 2):
             st = tr[tile, : len(names) + 1].tolist()
             d = [(st[i + 1] - st[i]) / 1e3 for i in range(len(names))]
+            ep = tr[tile, 40:48].tolist()
+            print("   ffn1 chunk 3 epilogue (ns): bias+sync %d, acquire %d, iters %s, release %d" % (
+                ep[1] - ep[0], ep[2] - ep[1], [ep[k + 1] - ep[k] for k in range(2, 6)], ep[7] - ep[6]))
+            print("   SM clock during the kernel: %.0f MHz" % ((tr[tile, 61] - tr[tile, 60]).item() / max(1, (tr[tile, 27] - tr[tile, 0]).item()) * 1e3))
+            e2 = tr[tile, 48:52].tolist()
+            print("   iter 1: tmem load+wait %d ns, math %d ns, staged store %d ns" % (e2[1] - e2[0], e2[2] - e2[1], ep[4] - e2[2]))
             print(f"t={t} tile={tile} step={ev0.elapsed_time(ev1)*1e3:.0f}us total={sum(d):.0f}us :: " +
                   " ".join(f"{n}={x:.1f}" for n, x in zip(names, d)))
 cabi.call("cap_debug_fused_trace", None)
