@@ -110,6 +110,7 @@ struct cap_engine {
     int64_t* out_ids = nullptr;
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
+    bool fuse_ln = true;                 // Linear + residual + LayerNorm as one cluster kernel (OPENVIIC_LN_FUSED=0: two kernels)
     cap_fused_decoder* fused = nullptr;  // one-kernel decode step (decode_fused.cu) when the model is covered
 
     // CUDA graph of a full beam search (begin + T steps + finalize)
@@ -249,6 +250,18 @@ int run_ln(const float* y32, const float* res32, const Norm& n, const float* pos
                              out32, d, rows, d, s);
 }
 
+// LN(res32 + x.W^T + b): one cluster kernel when the row fits a cluster (d_model 128..1024), else GEMM + LayerNorm
+int run_linear_ln(cap_engine* e, const bf16* x, int ldx, const Linear& l, const float* res32, const Norm& n,
+                  const float* pos, int pos_rows, const uint8_t* zero_rows, bf16* out16, float* out32, int rows,
+                  cudaStream_t s) {
+    const int d = l.out;
+    if (e->fuse_ln && d % 128 == 0 && d <= 1024)
+        return cap_linear_layernorm(x, ldx, l.w, l.b, res32, d, n.g, n.b, 1e-5f, pos, pos_rows, zero_rows, out16, d, out32,
+                                    d, rows, d, l.in, s);
+    CAP_PROPAGATE(run_linear(x, ldx, l, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
+    return run_ln(e->buf_y32, res32, n, pos, pos_rows, zero_rows, out16, out32, rows, d, s);
+}
+
 // AoA: out = Linear_i([q, a]) * sigmoid(Linear_g([q, a]))   (attentions.py:311-315)
 int run_aoa(cap_engine* e, const AttentionW& w, const bf16* queries, const bf16* att_out, bf16* out, float* out32,
             int rows, cudaStream_t s) {
@@ -281,6 +294,7 @@ extern "C" int cap_engine_create(const cap_model_desc* desc, cap_engine** out) {
     }
     cap_engine* e = new cap_engine();
     e->desc = m;
+    if (const char* env = getenv("OPENVIIC_LN_FUSED")) e->fuse_ln = atoi(env) != 0;
     *out = e;
     return CAP_OK;
 }
@@ -430,9 +444,11 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));
     CAP_PROPAGATE(cap_beam_create(max_batch, beam, T, m.vocab, m.eos_idx, &e->beam_state));
 
-    // Standard decoder at the reference's sizes: the whole decode step runs as one kernel.
+    // Standard decoder at the reference's sizes: the whole decode step can run as ONE kernel (decode_fused.cu).
+    // Opt-in (OPENVIIC_FUSED_DECODE=1): parity-green, but at 2.0 ms per step and row tile it only matches the
+    // per-operator path once ~15 batches are in flight; the per-operator path is the default.
     const char* env = getenv("OPENVIIC_FUSED_DECODE");
-    const bool want_fused = !env || atoi(env) != 0;
+    const bool want_fused = env && atoi(env) != 0;
     if (want_fused && m.decoder_kind == CAP_DEC_PLAIN && !m.aoa_dec_self && !m.aoa_dec_cross && d == 512 && m.heads == 8 &&
         m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && T <= 40 && n_tokens <= 128 &&
         e->vocab_fc.b == nullptr &&
@@ -479,8 +495,8 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
 
     // V1: padding mask from the RAW features + cast; projection; E0: LN(x) + pos
     CAP_PROPAGATE(cap_feature_mask_cast(feats, feat_dtype, e->feat_bf16, e->enc_mask, rows, m.d_feature, s));
-    CAP_PROPAGATE(run_linear(e->feat_bf16, m.d_feature, e->vis_proj, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
-    CAP_PROPAGATE(run_ln(e->buf_y32, nullptr, e->enc_ln, e->vis_pos, n, nullptr, e->buf_x, e->res_x, rows, d, s));
+    CAP_PROPAGATE(run_linear_ln(e, e->feat_bf16, m.d_feature, e->vis_proj, nullptr, e->enc_ln, e->vis_pos, n, nullptr,
+                                e->buf_x, e->res_x, rows, s));
     if (m.encoder_kind == CAP_ENC_GEOMETRIC)
         CAP_PROPAGATE(cap_geometry_bias(boxes, e->geo_w, e->geo_b, e->geometry, B, n, m.heads, e->d_g,
                                         m.trig_geometry, s));
@@ -511,12 +527,12 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
         a.B = B; a.H = m.heads; a.nq = n; a.nk = n;
         a.scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
         CAP_PROPAGATE(cap_attention(&a, s));
-        CAP_PROPAGATE(run_linear(e->buf_att, hd, L.att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, e->res_x, L.att.ln, nullptr, 0, nullptr, e->buf_a, e->res_a, rows, d, s));
+        CAP_PROPAGATE(run_linear_ln(e, e->buf_att, hd, L.att.o, e->res_x, L.att.ln, nullptr, 0, nullptr, e->buf_a, e->res_a,
+                                    rows, s));
         if (m.aoa_enc) CAP_PROPAGATE(run_aoa(e, L.att, x, e->buf_a, e->buf_a, e->res_a, rows, s));
         CAP_PROPAGATE(run_linear(e->buf_a, d, L.ffn.fc1, e->buf_h, m.d_ff, CAP_BF16, CAP_ACT_RELU, rows, s));
-        CAP_PROPAGATE(run_linear(e->buf_h, m.d_ff, L.ffn.fc2, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, rows, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, e->res_a, L.ffn.ln, nullptr, 0, e->enc_mask, level_out, e->res_x, rows, d, s));
+        CAP_PROPAGATE(run_linear_ln(e, e->buf_h, m.d_ff, L.ffn.fc2, e->res_a, L.ffn.ln, nullptr, 0, e->enc_mask, level_out,
+                                    e->res_x, rows, s));
         x = level_out;
     }
     // Cross-attention K/V, once per image per decoder layer (and per level for the meshed decoder).
@@ -593,8 +609,8 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
                                  CAP_ACT_NONE, R, s));
         CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd,
                                                 t, R, m.heads, scale, s));
-        CAP_PROPAGATE(run_linear(e->buf_att, hd, L.self_att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, R, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, e->res_x, L.self_att.ln, nullptr, 0, nullptr, e->buf_a, e->res_a, R, d, s));
+        CAP_PROPAGATE(run_linear_ln(e, e->buf_att, hd, L.self_att.o, e->res_x, L.self_att.ln, nullptr, 0, nullptr, e->buf_a,
+                                    e->res_a, R, s));
         if (m.aoa_dec_self) CAP_PROPAGATE(run_aoa(e, L.self_att, x, e->buf_a, e->buf_a, e->res_a, R, s));
         const bf16* sa = e->buf_a;
         // A5 (cross): one q projection shared by every encoder level (same enc_attn weights)
@@ -604,12 +620,17 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
             CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, kv, e->enc_mask, e->buf_att + static_cast<size_t>(i) * R * hd,
                                                      hd, B, beam, n, m.heads, scale, s));
         }
-        CAP_PROPAGATE(run_linear(e->buf_att, hd, L.cross_att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, lv * R, s));
+        if (!(e->fuse_ln && d % 128 == 0 && d <= 1024))
+            CAP_PROPAGATE(run_linear(e->buf_att, hd, L.cross_att.o, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, lv * R, s));
         for (int i = 0; i < lv; ++i) {
             bf16* ci = e->buf_c + static_cast<size_t>(i) * R * d;
             float* ci32 = e->res_c + static_cast<size_t>(i) * R * d;
-            CAP_PROPAGATE(run_ln(e->buf_y32 + static_cast<size_t>(i) * R * d, e->res_a, L.cross_att.ln, nullptr, 0, nullptr,
-                                 ci, ci32, R, d, s));
+            if (e->fuse_ln && d % 128 == 0 && d <= 1024)  // every level adds the same residual (decoders.py:56)
+                CAP_PROPAGATE(run_linear_ln(e, e->buf_att + static_cast<size_t>(i) * R * hd, hd, L.cross_att.o, e->res_a,
+                                            L.cross_att.ln, nullptr, 0, nullptr, ci, ci32, R, s));
+            else
+                CAP_PROPAGATE(run_ln(e->buf_y32 + static_cast<size_t>(i) * R * d, e->res_a, L.cross_att.ln, nullptr, 0,
+                                     nullptr, ci, ci32, R, d, s));
             if (m.aoa_dec_cross) CAP_PROPAGATE(run_aoa(e, L.cross_att, sa, ci, ci, ci32, R, s));
         }
         const bf16* c = e->buf_c;
@@ -630,8 +651,7 @@ int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden) {
         }
         // F1 + zero rows whose input token was <pad> (decoders.py:26)
         CAP_PROPAGATE(run_linear(c, d, L.ffn.fc1, e->buf_h, m.d_ff, CAP_BF16, CAP_ACT_RELU, R, s));
-        CAP_PROPAGATE(run_linear(e->buf_h, m.d_ff, L.ffn.fc2, e->buf_y32, d, CAP_F32, CAP_ACT_NONE, R, s));
-        CAP_PROPAGATE(run_ln(e->buf_y32, c32, L.ffn.ln, nullptr, 0, pad_t, e->buf_x, e->res_x, R, d, s));
+        CAP_PROPAGATE(run_linear_ln(e, e->buf_h, m.d_ff, L.ffn.fc2, c32, L.ffn.ln, nullptr, 0, pad_t, e->buf_x, e->res_x, R, s));
         x = e->buf_x;
     }
     *hidden = x;

@@ -61,6 +61,30 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = 
     return y.reshape(*x.shape[:-1], n)
 
 
+def linear_layernorm(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], gamma: Tensor,
+                     beta: Tensor, eps: float = 1e-5, pos: Optional[Tensor] = None,
+                     zero_rows: Optional[Tensor] = None):
+    """LayerNorm(residual + x @ weight.T + bias) * gamma + beta in ONE kernel (cluster of N/128 CTAs per row tile
+    exchanging row statistics through distributed shared memory).  Returns (bf16 copy, fp32 copy)."""
+    _need_cuda(x, weight, bias, residual, gamma, beta, pos, zero_rows)
+    x2 = _rows(as_bf16(x))
+    w = as_bf16(weight).contiguous()
+    m, k = x2.shape
+    n = w.shape[0]
+    b = None if bias is None else bias.float().contiguous()
+    r2 = None if residual is None else residual.float().reshape(-1, n).contiguous()
+    pos2 = None if pos is None else pos.float().reshape(-1, n).contiguous()
+    zr = None if zero_rows is None else zero_rows.reshape(-1).to(torch.uint8).contiguous()
+    out16 = torch.empty((m, n), device=x.device, dtype=torch.bfloat16)
+    out32 = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    cabi.call("cap_linear_layernorm", x2.data_ptr(), x2.stride(0) if m > 1 else k, w.data_ptr(), _ptr(b), _ptr(r2), n,
+              gamma.float().contiguous().data_ptr(), beta.float().contiguous().data_ptr(), float(eps), _ptr(pos2),
+              0 if pos2 is None else pos2.shape[0], _ptr(zr), out16.data_ptr(), n, out32.data_ptr(), n, m, n, k,
+              _stream())
+    shape = (*x.shape[:-1], n)
+    return out16.reshape(shape), out32.reshape(shape)
+
+
 def add_layernorm(y: Tensor, residual: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float = 1e-5,
                   pos: Optional[Tensor] = None, zero_rows: Optional[Tensor] = None,
                   out_dtype: torch.dtype = torch.float32) -> Tensor:

@@ -63,6 +63,33 @@ def test_add_layernorm(device, rows, d):
     assert torch.equal(out3[~zero], out[~zero])
 
 
+@pytest.mark.parametrize("m,n,k", [(1280, 512, 512), (1280, 512, 2048), (300, 512, 512), (12544, 512, 2048), (77, 256, 64)])
+def test_linear_layernorm_fused(device, m, n, k):
+    """One-kernel Linear + residual + LayerNorm (cluster / DSMEM statistics) against the fp32 composition
+    (attentions.py:308-309, positionwise_feed_forward.py:26) and against the two-kernel CUDA path."""
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).to(device)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(device)
+    b = torch.randn(n, generator=g).to(device)
+    res = torch.randn(m, n, generator=g).to(device)
+    gamma = (1 + 0.1 * torch.randn(n, generator=g)).to(device)
+    beta = (0.1 * torch.randn(n, generator=g)).to(device)
+    zero = (torch.rand(m, generator=g) < 0.1).to(device)
+    o16, o32 = ops.linear_layernorm(x, w, b, res, gamma, beta, zero_rows=zero)
+    ref = torch.nn.functional.layer_norm(res + _bf(x).float() @ _bf(w).float().T + b, (n,), gamma, beta, 1e-5)
+    ref = ref.masked_fill(zero[:, None], 0.0)
+    assert (o32 - ref).abs().max().item() < 2e-4
+    assert (o16.float() - ref).abs().max().item() < TOL_ACT
+    y = ops.linear(x, w, b, out_dtype=torch.float32)
+    two = ops.add_layernorm(y, res, gamma, beta, zero_rows=zero)
+    assert (o32 - two).abs().max().item() < 2e-4
+    # no residual, positional table
+    pos = torch.randn(7, n, generator=g).to(device)
+    o16, o32 = ops.linear_layernorm(x, w, b, None, gamma, beta, pos=pos)
+    ref = torch.nn.functional.layer_norm(_bf(x).float() @ _bf(w).float().T + b, (n,), gamma, beta, 1e-5) + pos[torch.arange(m, device=device) % 7]
+    assert (o32 - ref).abs().max().item() < 2e-4
+
+
 def test_feature_mask_cast(device):
     feats = torch.randn(6, 50, 256)
     feats[1, 30:] = 0
