@@ -218,6 +218,9 @@ typedef struct cap_fused_desc {
     float* logits;                /* fp32 [R][ld_logits], ld_logits % 32 == 0 */
     int ld_logits;
     float* part_ms;               /* fp32 [R][8*ceil(vocab/256)][2] */
+    /* chain mode only (cap_fused_chain), else NULL: */
+    const void* att_in;           /* bf16 [max_rows][d_model]: output of cap_decode_{self,cross}_attention */
+    void* q_out;                  /* bf16 [max_rows][d_model]: queries for cap_decode_cross_attention */
 } cap_fused_desc;
 
 typedef struct cap_fused_decoder cap_fused_decoder;
@@ -226,6 +229,14 @@ int cap_fused_destroy(cap_fused_decoder* f);
 /* Step t for B images (R = B*beam rows, n_keys visual tokens): fills qkv_cache[.][t], padflag[t], logits and
  * part_ms; follow with cap_beam_step_stats. */
 int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_keys, cap_stream_t stream);
+/* The same step as three kinds of GEMM chains with the stand-alone attention kernels in between -- the default
+ * decode path: the chains keep the tensor pipe of "their" SM busy, the attention kernels (low IPC, latency
+ * bound) share SMs with whatever else is in flight instead of monopolising one.  Per step:
+ *   EMBED_QKV(0); for each layer L: cap_decode_self_attention -> SELF_OUT(L) -> cap_decode_cross_attention ->
+ *   FFN(L); then cap_beam_step_stats.  FFN(L) ends with layer L+1's q|k|v projection, FFN(last) with the
+ *   vocabulary projection + chunk statistics. */
+enum cap_fused_chain_kind { CAP_CHAIN_EMBED_QKV = 0, CAP_CHAIN_SELF_OUT = 1, CAP_CHAIN_FFN = 2 };
+int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t, int B, cap_stream_t stream);
 /* Debug: when non-NULL, every later fused step writes %globaltimer stamps (ns) of its phase boundaries into
  * device_buffer[tile*64 + k]: 0 entry, 1 dependencies resolved, then per layer L at 2+8L: layer start,
  * q|k|v stored, self-attention done, LN1 done, cross q stored, cross-attention done, LN2 done, hidden stored;

@@ -64,7 +64,7 @@ constexpr uint32_t OFF_GAMMA = OFF_CBIAS + FD * 4;
 constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
 constexpr uint32_t OFF_STAT = OFF_BETA + FD * 4;       // [2 (sum, sumsq)][2 halves][128 rows]
 constexpr uint32_t OFF_BARS = OFF_STAT + 4 * TILE_ROWS * 4;
-constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1;
+constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1 + 1;
 constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
 constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16;
 
@@ -77,6 +77,7 @@ struct FusedParams {
     CUtensorMap map_w2;     // [layers * 512][2048]
     CUtensorMap map_vocab;  // [V][512]
     CUtensorMap map_h;      // [tiles * 128][2048] FFN hidden scratch
+    CUtensorMap map_att;    // [max_rows][512] attention output of the stand-alone attention kernels (chain mode)
     FusedLayerP layer[MAX_FUSED_LAYERS];
     int n_layers;
     const int32_t* tokens;
@@ -101,6 +102,11 @@ struct FusedParams {
     float scale;
     unsigned long long* trace;  // debug: 64 %globaltimer stamps per CTA (cap_debug_fused_trace), else nullptr
     int dbg_skip;            // debug (timing only): bit 0 = issue no MMAs, bit 1 = load no weight tiles
+    // chain mode: the kernel runs jobs [job_begin, job_end] of the step's GEMM list only; its first A tile is the
+    // embedding (start_embed) or a TMA load of the attention output; the attention itself runs between the chains
+    // as stand-alone kernels that share SMs with everything else in flight
+    int job_begin, job_end, start_embed;
+    bf16* q_out;             // [R][512] cross-attention queries for the stand-alone kernel (chain mode)
 };
 
 __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot, bool who) {
@@ -691,6 +697,9 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
     release_acc(c, 2, b);
 }
 
+// CHAIN = false: the whole step (attention phases on this CTA's CUDA cores).  CHAIN = true: a range of the
+// step's GEMM jobs with their epilogues (see FusedParams::job_begin).
+template <bool CHAIN>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     // 1024-byte alignment (SWIZZLE_128B tiles) comes from the declaration: rounding the address up by hand
@@ -709,12 +718,14 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     uint64_t* a_ready = acc_empty + 2;
     uint64_t* h_ready = a_ready + 1;
     uint64_t* ring_free = h_ready + 1;
+    uint64_t* a_load = ring_free + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
-    const int njobs = p.n_layers * 6 + 1;
+    const int job_lo = CHAIN ? p.job_begin : 0;
+    const int job_hi = CHAIN ? p.job_end : p.n_layers * 6;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w512)) : "memory");
@@ -730,6 +741,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             mbar_init(a_ready, NW);
             mbar_init(h_ready, NW);
             mbar_init(ring_free, NW);
+            mbar_init(a_load, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -743,15 +755,16 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     if (warp < FIRST_WORKER_WARP) {
     // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
     // the register limit of each region is unambiguous to ptxas)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");   // epilogues only: no need
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");                    // to squeeze these warps
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
         // The whole warp runs the loop (uniform control flow); one elected lane issues the copies.
         uint32_t bcount = 0, acount = 0, hphase = 0, rphase = 0;
-        for (int ji = 0; ji < njobs; ++ji) {
+        for (int ji = job_lo; ji <= job_hi; ++ji) {
             const Job job = get_job(p, ji);
             const int nch = job.ntiles / job.chunk;
-            if (ji < p.n_layers * 6 && (ji % 6 == 1 || ji % 6 == 3)) {
+            if (!CHAIN && ji < p.n_layers * 6 && (ji % 6 == 1 || ji % 6 == 3)) {
                 // fc_o follows an attention phase, which borrows the weight ring for its K|V rows
                 mbar_wait(ring_free, rphase);
                 rphase ^= 1;
@@ -797,10 +810,12 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         constexpr uint32_t idesc = make_instr_desc(128, 128);
         uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
         int toggle = 0;
-        for (int ji = 0; ji < njobs; ++ji) {
+        for (int ji = job_lo; ji <= job_hi; ++ji) {
             const Job job = get_job(p, ji);
             const int nch = job.ntiles / job.chunk;
-            if (!job.stream) {
+            if (CHAIN && ji == job_lo && !p.start_embed) {
+                mbar_wait(a_load, 0);   // the chain's first A tile arrives by TMA (warp 2)
+            } else if (!job.stream) {
                 mbar_wait(a_ready, ar & 1);
                 ++ar;
             }
@@ -870,10 +885,22 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             }
         }
         pdl_launch_dependents();
+    } else if (CHAIN && warp == 2) {
+        // ------------------------------------------------------------------ A-tile loader (chain mode)
+        if (!p.start_embed) {
+            pdl_wait();  // the attention kernel that wrote the tile is the stream predecessor
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(a_load, A_SLOTS * A_KB_BYTES);
+                for (int kb = 0; kb < A_SLOTS; ++kb)
+                    tma_load_2d(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, tile * TILE_ROWS);
+            }
+            __syncwarp();
+        }
     }
     } else {
         // ------------------------------------------------------------------ workers
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         WorkerCtx c;
         c.A_buf = A_buf;
         c.ww = warp - FIRST_WORKER_WARP;
@@ -900,6 +927,43 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.r0 = tile * TILE_ROWS;
         c.rows_valid_warp = max(0, min(32, p.R - (c.r0 + c.quad * 32)));
 
+        if constexpr (CHAIN) {
+            pdl_wait();  // everything this chain reads was written by stream predecessors
+            uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
+            if (p.start_embed) {
+                embed_phase(c, p);
+                workers_sync();
+                publish_a(c);
+            }
+            for (int ji = job_lo; ji <= job_hi; ++ji) {
+                if (ji == p.n_layers * 6) {
+                    pdl_launch_dependents();
+                    const int vchunks = p.vocab_tiles / 2;
+                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch);
+                    break;
+                }
+                const int L = ji / 6, k = ji % 6;
+                const FusedLayerP& W = p.layer[L];
+                if (k == 0) {
+                    bf16* cache_t = p.qkv_cache + (static_cast<size_t>(L) * p.T + p.t) * p.R * 3 * FD;
+                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, cache_t, 3 * FD);
+                } else if (k == 1) {
+                    epilogue_layernorm(c, p, W.b_o1, W.g1, W.be1, nullptr);
+                } else if (k == 2) {
+                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, p.q_out, FD);
+                } else if (k == 3) {
+                    epilogue_layernorm(c, p, W.b_o2, W.g2, W.be2, nullptr);
+                } else if (k == 4) {
+                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, nullptr, 0);
+                    fence_proxy_async();  // hidden tile (global, generic proxy) -> TMA reads (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(h_ready);
+                } else {
+                    epilogue_layernorm(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
+                }
+            }
+            pdl_launch_dependents();
+        } else {
         const bool tr = (c.ww == 0 && lane == 0);
         fstamp(p, tile, 0, tr);
         pdl_wait();  // tokens / ancestry come from the previous step's selection kernel
@@ -943,6 +1007,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         const int vchunks = p.vocab_tiles / 2;
         for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch);
         fstamp(p, tile, 3 + p.n_layers * 8, tr);
+            }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -960,6 +1025,7 @@ struct cap_fused_decoder {
     void* w512 = nullptr;
     void* w2 = nullptr;
     int tiles = 0;
+    bool has_att = false;
 };
 
 extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out) {
@@ -1029,7 +1095,14 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     p.res = static_cast<float*>(res); p.qg = static_cast<bf16*>(qg); p.hbuf = static_cast<bf16*>(hb);
     rc = cap_gemm::make_tmap(&p.map_h, hb, static_cast<int>(tiles) * TILE_ROWS, FDFF, FDFF, 128);
     if (rc != CAP_OK) return fail(rc);
-    if (cudaFuncSetAttribute(decode_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+    if (d->att_in) {
+        rc = cap_gemm::make_tmap(&p.map_att, d->att_in, d->max_rows, FD, FD, 128);
+        if (rc != CAP_OK) return fail(rc);
+    }
+    p.q_out = static_cast<bf16*>(d->q_out);
+    f->has_att = d->att_in != nullptr;
+    if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
     return CAP_OK;
@@ -1069,8 +1142,36 @@ extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_k
         const unsigned int ns = getenv("OPENVIIC_FUSED_DBG_BACKOFF_NS") ? static_cast<unsigned int>(atoi(getenv("OPENVIIC_FUSED_DBG_BACKOFF_NS"))) : 0u;
         if (ns) cudaMemcpyToSymbol(cap_ptx::g_mbar_backoff_ns, &ns, sizeof(ns));
     }
-    cap_launch_kernel(decode_step_fused_kernel, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
+    cap_launch_kernel(decode_step_fused_kernel<false>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
                       static_cast<cudaStream_t>(stream), 1, p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_step_fused_kernel");
+}
+
+extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t, int B, cap_stream_t stream) {
+    CAP_REQUIRE(f != nullptr, "cap_fused_chain: null handle");
+    FusedParams p = f->base;
+    CAP_REQUIRE(t >= 0 && t < p.T, "cap_fused_chain: step %d outside [0,%d)", t, p.T);
+    CAP_REQUIRE(chain >= CAP_CHAIN_EMBED_QKV && chain <= CAP_CHAIN_FFN && layer >= 0 && layer < p.n_layers,
+                "cap_fused_chain: bad chain %d / layer %d", chain, layer);
+    CAP_REQUIRE(p.q_out != nullptr && (chain == CAP_CHAIN_EMBED_QKV || f->has_att), "cap_fused_chain: handle has no att_in / q_out buffers");
+    const int R = B * p.beam;
+    const int tiles = (R + TILE_ROWS - 1) / TILE_ROWS;
+    CAP_REQUIRE(B > 0 && tiles <= f->tiles, "cap_fused_chain: batch %d exceeds the reservation", B);
+    p.t = t; p.R = R; p.B = B; p.n_keys = 0;
+    p.trace = nullptr;
+    p.dbg_skip = 0;
+    p.start_embed = 0;
+    if (chain == CAP_CHAIN_EMBED_QKV) {          // x = Emb + pos; q|k|v of layer 0 -> cache
+        CAP_REQUIRE(layer == 0, "cap_fused_chain: the embedding chain belongs to layer 0");
+        p.start_embed = 1; p.job_begin = 0; p.job_end = 0;
+    } else if (chain == CAP_CHAIN_SELF_OUT) {    // self fc_o + LN; cross fc_q -> q_out
+        p.job_begin = layer * 6 + 1; p.job_end = layer * 6 + 2;
+    } else {                                     // cross fc_o + LN; FFN + LN; next layer's q|k|v or the vocabulary
+        p.job_begin = layer * 6 + 3; p.job_end = layer * 6 + 6;
+    }
+    cap_launch_kernel(decode_step_fused_kernel<true>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
+                      static_cast<cudaStream_t>(stream), 1, p);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_step_fused_kernel<chain>");
 }

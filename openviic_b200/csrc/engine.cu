@@ -111,7 +111,8 @@ struct cap_engine {
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
     bool fuse_ln = true;                 // Linear + residual + LayerNorm as one cluster kernel (OPENVIIC_LN_FUSED=0: two kernels)
-    cap_fused_decoder* fused = nullptr;  // one-kernel decode step (decode_fused.cu) when the model is covered
+    cap_fused_decoder* fused = nullptr;  // fused decode step (decode_fused.cu) when the model is covered
+    int fused_mode = 0;                  // 0 per-operator kernels, 1 one kernel per step, 2 GEMM chains + attention kernels
 
     // CUDA graph of a full beam search (begin + T steps + finalize)
     cudaGraphExec_t graph_exec = nullptr;
@@ -444,11 +445,13 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));
     CAP_PROPAGATE(cap_beam_create(max_batch, beam, T, m.vocab, m.eos_idx, &e->beam_state));
 
-    // Standard decoder at the reference's sizes: the whole decode step can run as ONE kernel (decode_fused.cu).
-    // Opt-in (OPENVIIC_FUSED_DECODE=1): parity-green, but at 2.0 ms per step and row tile it only matches the
-    // per-operator path once ~15 batches are in flight; the per-operator path is the default.
+    // Standard decoder at the reference's sizes: the decode step runs on the fused tcgen05 kernel (decode_fused.cu).
+    // OPENVIIC_FUSED_DECODE = 2 (default): three GEMM chains per layer with the stand-alone attention kernels in
+    // between; 1: ONE kernel per step (attention on the CTA's own CUDA cores -- parity-green, but it monopolises
+    // an SM at low IPC during the attention phases); 0: one kernel per operator.
     const char* env = getenv("OPENVIIC_FUSED_DECODE");
-    const bool want_fused = env && atoi(env) != 0;
+    const int mode = env ? atoi(env) : 2;
+    const bool want_fused = mode != 0;
     if (want_fused && m.decoder_kind == CAP_DEC_PLAIN && !m.aoa_dec_self && !m.aoa_dec_cross && d == 512 && m.heads == 8 &&
         m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && T <= 40 && n_tokens <= 128 &&
         e->vocab_fc.b == nullptr &&
@@ -473,7 +476,9 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
         fd.padflag = e->padflag; fd.qkv_cache = e->qkv_cache;
         fd.cross_kv = e->cross_kv; fd.cross_layer_stride = rows_enc * 2 * hd; fd.enc_mask = e->enc_mask;
         fd.logits = e->logits; fd.ld_logits = e->ld_logits; fd.part_ms = e->part_ms;
+        fd.att_in = e->buf_att; fd.q_out = e->buf_q;
         CAP_PROPAGATE(cap_fused_create(&fd, &e->fused));
+        e->fused_mode = mode == 1 ? 1 : 2;
     }
     return CAP_OK;
 }
@@ -574,8 +579,25 @@ extern "C" int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->vocab_chunks > 512)  // vocabularies beyond the merge kernel's reach: full row pass over the logits
         return cap_engine_decode_logits(e, t, stream) || cap_engine_beam_advance(e, t, stream);
-    if (e->fused) {
+    if (e->fused && e->fused_mode == 1) {
         CAP_PROPAGATE(cap_fused_decode_step(e->fused, t, e->cur_batch, e->cur_n, s));
+        return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, e->vocab_chunks, s);
+    }
+    if (e->fused) {
+        const cap_model_desc& m = e->desc;
+        const int hd = e->hd(), T = m.max_len, B = e->cur_batch, R = B * e->beam;
+        const size_t rows_cap = static_cast<size_t>(e->max_batch) * e->n_tokens;
+        const float scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
+        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, B, s));
+        for (int l = 0; l < m.dec_layers; ++l) {
+            const bf16* cache_l = e->qkv_cache + static_cast<size_t>(l) * T * R * 3 * hd;
+            CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd, t,
+                                                    R, m.heads, scale, s));
+            CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, B, s));
+            CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, e->cross_kv + static_cast<size_t>(l) * rows_cap * 2 * hd,
+                                                     e->enc_mask, e->buf_att, hd, B, e->beam, e->cur_n, m.heads, scale, s));
+            CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, B, s));
+        }
         return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, e->vocab_chunks, s);
     }
     bf16* x = nullptr;

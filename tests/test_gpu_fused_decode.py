@@ -20,8 +20,9 @@ TOL_FUSED = 6e-2   # max-abs logits, fused vs per-operator path: same bf16 opera
                    # summation order and a one-pass LayerNorm variance; measured ~1e-2
 
 
-def _engine(model, cfg, vocab, batch, n, beam, device, fused: bool):
-    os.environ["OPENVIIC_FUSED_DECODE"] = "1" if fused else "0"
+def _engine(model, cfg, vocab, batch, n, beam, device, fused):
+    """fused: 0 / False = one kernel per operator, 1 / True = one kernel per step, 2 = GEMM chains + attention kernels."""
+    os.environ["OPENVIIC_FUSED_DECODE"] = str(int(fused))
     try:
         eng = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device)
         eng.reserve(batch, n, beam)
@@ -30,15 +31,16 @@ def _engine(model, cfg, vocab, batch, n, beam, device, fused: bool):
     return eng
 
 
+@pytest.mark.parametrize("mode", [2, 1])
 @pytest.mark.parametrize("name,batch", [("std_grid", 6), ("std_region_A", 16), ("std_grid", 53), ("ort", 5)])
-def test_fused_step_matches_per_operator_path(name, batch, device):
+def test_fused_step_matches_per_operator_path(name, batch, mode, device):
     case, cfg, vocab, model, weights, field, feats, boxes = load_case(name, device)
     beam, T = case["beam"], case["max_len"]
     if batch != case["batch"]:   # several row tiles, images straddling tile boundaries, a ragged last tile
         from openviic_b200 import synthetic
         field, feats, boxes = synthetic.synth_inputs(cfg.MODEL, batch, case["n"], case["seed"])
-    fused = _engine(model, cfg, vocab, batch, case["n"], beam, device, True)
-    plain = _engine(model, cfg, vocab, batch, case["n"], beam, device, False)
+    fused = _engine(model, cfg, vocab, batch, case["n"], beam, device, mode)
+    plain = _engine(model, cfg, vocab, batch, case["n"], beam, device, 0)
     bx = None if boxes is None else boxes.to(device)
     for eng in (fused, plain):
         eng.encode(feats.to(device), bx)
@@ -61,7 +63,7 @@ def test_fused_step_matches_per_operator_path(name, batch, device):
         worst = max(worst, err)
         compared += int(agree.sum())
         assert err < TOL_FUSED, f"step {t}: fused logits differ from the per-operator path by {err}"
-    print(f"[{name} B={batch}] fused vs per-operator: {compared}/{T * batch} image-steps compared, "
+    print(f"[{name} B={batch} mode={mode}] fused vs per-operator: {compared}/{T * batch} image-steps compared, "
           f"max-abs logits diff {worst:.4f}")
     assert compared >= 4 * batch
     ids_f, lp_f = fused.finalize(1)
@@ -71,9 +73,10 @@ def test_fused_step_matches_per_operator_path(name, batch, device):
     assert agree >= 0.6
 
 
-def test_fused_beam_search_against_oracle(device):
+@pytest.mark.parametrize("mode", [2, 1])
+def test_fused_beam_search_against_oracle(mode, device):
     case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_grid", device)
-    eng = _engine(model, cfg, vocab, case["batch"], case["n"], case["beam"], device, True)
+    eng = _engine(model, cfg, vocab, case["batch"], case["n"], case["beam"], device, mode)
     eng.encode(feats.to(device), None)
     ids, lp = eng.beam_search(1, use_graph=False)
     ids2, lp2 = eng.beam_search(1, use_graph=True)   # first graph call captures, second replays
