@@ -168,6 +168,40 @@ def time_gemm_family(cfg, n, batch, levels, device):
     return total_flops, total_s
 
 
+def time_decode_chains(eng, cfg, batch, device):
+    """Average duration of the fused tcgen05 GEMM-chain launches of one decode step (1 + 2 * layers launches of
+    decode_step_fused_kernel<chain>), with CUDA events on the launching stream around graph replays of all 20 steps'
+    chains back to back; returns (algorithmic GEMM flops per step, seconds per step, launches per step) or None when
+    the engine does not decode with chains."""
+    import ctypes as C
+    from openviic_b200 import cabi
+    dec = cfg.MODEL.DECODER
+    d, dff, layers = dec.D_MODEL, dec.ATTENTION.ENC_ATTENTION.D_FF, dec.LAYERS
+    side = torch.cuda.Stream(device=device)
+    try:
+        with torch.cuda.stream(side):
+            cabi.call("cap_engine_debug_chains", eng._h, 0, C.c_void_p(side.cuda_stream))
+    except RuntimeError:
+        return None
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for t in range(MAX_LEN):
+                cabi.call("cap_engine_debug_chains", eng._h, t, C.c_void_p(side.cuda_stream))
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    sec_per_step = e0.elapsed_time(e1) / 1e3 / (3 * MAX_LEN)
+    macs_per_row = layers * (3 * d * d + 3 * d * d + 2 * d * dff) + VOCAB * d
+    return 2.0 * batch * BEAM * macs_per_row, sec_per_step, 1 + 2 * layers
+
+
 # ------------------------------------------------------------------------------------ CPU reference
 def cpu_reference_run(workload: str, steps: int, warmup: int, sample_batch: int = 8):
     """The reference's algorithm (oracle port, fp32, as written) on this box's host cores."""
@@ -254,18 +288,37 @@ def run_gpu_arm(args):
         boxes_host.append(bx)
         boxes_dev.append(None if bx is None else bx.to(device))
 
+    outs_dev = [(torch.empty((batch, 1, MAX_LEN), device=device, dtype=torch.int64),
+                 torch.empty((batch, 1, MAX_LEN), device=device, dtype=torch.float32)) for _ in range(n_streams)]
+
+    pace_stream = torch.cuda.Stream(device=device)
+
     def step(i):
         k = i % n_streams
+        if args.pace_ms > 0:   # admission pacing: batch i may start pace_ms after batch i-1 was admitted
+            with torch.cuda.stream(pace_stream):
+                torch.cuda._sleep(int(args.pace_ms * 1e-3 * 1.9e9))
+                ev = torch.cuda.Event()
+                ev.record()
+            streams[k].wait_event(ev)
         with torch.cuda.stream(streams[k]):
-            engines[k].encode(feats_dev[i % n_sets], boxes_dev[i % n_sets])
-            ids, logp = engines[k].beam_search(out_size=1, use_graph=not args.no_graph)
+            ids, logp = engines[k].caption_device(feats_dev[i % n_sets], boxes_dev[i % n_sets], 1, not args.no_graph,
+                                                  outs_dev[k])
             if world > 1:
                 return parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world)
             return ids, logp
 
-    def fork():   # side streams start after everything already queued on the timing stream
-        for st in streams:
+    def fork(stagger_ms: float = 0.0):
+        pace_stream.wait_stream(torch.cuda.current_stream())
+        """Side streams start after everything already queued on the timing stream.  With `stagger_ms`, stream k
+        additionally idles k * stagger_ms first: batches that start in lock-step stay in lock-step (every engine in
+        its encoder, then every engine in the same decode chain competing for the same SMs); a serving pipeline is
+        staggered by its own H2D copies, as the e2e loop below is."""
+        for k, st in enumerate(streams):
             st.wait_stream(torch.cuda.current_stream())
+            if stagger_ms > 0 and k > 0:
+                with torch.cuda.stream(st):
+                    torch.cuda._sleep(int(k * stagger_ms * 1e-3 * 1.9e9))
 
     def join():   # the timing stream waits for every side stream
         for st in streams:
@@ -298,17 +351,22 @@ def run_gpu_arm(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    fork()
+    fork(args.stagger_ms)
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         out = step(i)
+    host_enqueue_s = time.perf_counter() - host_t0
     join()
     e1.record()
     barrier()
+    wall_ms = (time.perf_counter() - host_t0) * 1e3
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     value = batch * world * args.steps / (total_ms / 1e3)
+    print(f"[bench] device-resident loop: {total_ms:.1f} ms on the device, host enqueue {host_enqueue_s * 1e3:.1f} ms, wall {wall_ms:.1f} ms",
+          file=sys.stderr)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + compute + D2H + sync per step) ----
     outs_host = [(torch.empty((batch, 1, MAX_LEN), dtype=torch.int64).pin_memory(),
@@ -355,19 +413,40 @@ def run_gpu_arm(args):
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), measured live with CUDA events ----
     peaks = measured_peaks()
-    flops, gemm_s = time_gemm_family(cfg, n, batch, levels, device)
-    achieved = flops / gemm_s / 1e12
-    traffic = None   # dram__bytes_read+write per launch, averaged over the decode step's GEMMs (ncu --set full capture)
-    summary = REPO / "profiles" / "r01_gemm_ncu_full_summary.json"
-    if summary.exists() and args.workload == "standard_grid" and batch == 256:
-        traffic = json.loads(summary.read_text())["avg_dram_bytes_per_launch"]
-    roofline = {"bound": "tensor", "kernel": "gemm_tn_bf16_tcgen05 (all projection/FFN/vocab GEMMs of one step)",
-                "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
-                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                "share_of_step": gemm_s / (total_ms / 1e3 / args.steps),
-                "step_algorithmic_tflops": gflop_per_caption * 1e9 * value / world / 1e12,
-                "step_frac_of_tensor_peak": gflop_per_caption * 1e9 * value / world / 1e12 / peaks["tflops_sustained"]}
+    chains = time_decode_chains(eng, cfg, batch, device)
+    traffic = None   # dram__bytes_read+write per launch of the dominant kernel (ncu --set full capture), if committed
+    if chains is not None:
+        # dominant kernel: the fused GEMM chains of the decode steps (20 steps x 7 launches per batch)
+        flops, chain_s, chain_launches = chains
+        achieved = flops / chain_s / 1e12
+        summary = REPO / "profiles" / "r01_chain_ncu_summary.json"
+        if summary.exists() and args.workload == "standard_grid" and batch == 256:
+            traffic = json.loads(summary.read_text()).get("avg_dram_bytes_per_launch")
+        roofline = {"bound": "tensor",
+                    "kernel": "decode_step_fused_kernel<chain> (per decode step: 1 + 2*layers launches holding every "
+                              "projection / FFN / vocabulary GEMM with its bias, ReLU, residual + LayerNorm and "
+                              "log-softmax-statistics epilogue, plus the token embedding)",
+                    "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "flops_per_launch": flops / chain_launches, "avg_launch_us": chain_s / chain_launches * 1e6,
+                    "timing": "CUDA events around graph replays of the 20 steps' chain launches of ONE batch alone on the "
+                              "GPU (10 row tiles = 10 of 148 SMs busy): the fraction is per-launch latency-bound by "
+                              "design; throughput comes from ~15 batches in flight (step_frac_of_tensor_peak)",
+                    "share_of_step": MAX_LEN * chain_s / (total_ms / 1e3 / args.steps)}
+    else:
+        flops, gemm_s = time_gemm_family(cfg, n, batch, levels, device)
+        achieved = flops / gemm_s / 1e12
+        summary = REPO / "profiles" / "r01_gemm_ncu_full_summary.json"
+        if summary.exists() and args.workload == "standard_grid" and batch == 256:
+            traffic = json.loads(summary.read_text())["avg_dram_bytes_per_launch"]
+        roofline = {"bound": "tensor", "kernel": "gemm_tn_bf16_tcgen05 (all projection/FFN/vocab GEMMs of one step)",
+                    "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "share_of_step": gemm_s / (total_ms / 1e3 / args.steps)}
+    roofline["step_algorithmic_tflops"] = gflop_per_caption * 1e9 * max(value, e2e_value) / world / 1e12
+    roofline["step_frac_of_tensor_peak"] = roofline["step_algorithmic_tflops"] / peaks["tflops_sustained"]
 
     cpu_base = None
     if not args.skip_cpu:
@@ -396,13 +475,17 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=80)
+    ap.add_argument("--steps", type=int, default=320)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="standard_grid", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="independent batches kept in flight (engines/streams)")
+    ap.add_argument("--streams", type=int, default=32, help="independent batches kept in flight (engines/streams)")
+    ap.add_argument("--stagger-ms", type=float, default=0.0,
+                    help="start stream k of the device-resident loop k * this many ms late (inside the timed region)")
+    ap.add_argument("--pace-ms", type=float, default=0.0,
+                    help="device-resident loop: admit one batch every this many ms (0 = enqueue everything at once)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=40)

@@ -306,6 +306,14 @@ int cap_engine_caption_host_async(cap_engine* e, const void* feats_host, int fea
                                   const float* boxes_host, int B, int n, int out_size,
                                   int64_t* ids_host, float* logp_host, int use_graph,
                                   cap_stream_t stream);
+/* Same path with DEVICE buffers on both sides (features already in HBM, ids int64 (B,out_size,T) and log-probs
+ * fp32 left in HBM); asynchronous like the call above. */
+int cap_engine_caption_device_async(cap_engine* e, const void* feats_dev, int feat_dtype,
+                                    const float* boxes_dev, int B, int n, int out_size, int64_t* ids_dev,
+                                    float* logp_dev, int use_graph, cap_stream_t stream);
+/* Measurement hook: the 1 + 2*layers GEMM-chain launches of decode step t back to back, without the attention and
+ * beam kernels between them (bench.py times them for the roofline).  CAP_ERR_STATE unless the engine runs chains. */
+int cap_engine_debug_chains(cap_engine* e, int t, cap_stream_t stream);
 /* Debug / parity views: */
 const void* cap_engine_encoder_output(cap_engine* e);   /* bf16 [levels][B*n][d_model] */
 const uint8_t* cap_engine_encoder_mask(cap_engine* e);  /* uint8 [B*n]                 */

@@ -92,6 +92,8 @@ SIGNATURES = {
     "cap_engine_beam_search": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "cap_engine_caption_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "cap_engine_caption_host_async": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "cap_engine_caption_device_async": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "cap_engine_debug_chains": (_i, [_vp, _i, _vp]),
     "cap_engine_encoder_output": (_vp, [_vp]),
     "cap_engine_encoder_mask": (_vp, [_vp]),
     "cap_engine_logits": (_vp, [_vp, C.POINTER(_i)]),

@@ -289,6 +289,10 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
 // positionwise_feed_forward.py:26): thread = row, the two warps of a TMEM quadrant take 256 columns each and
 // exchange (sum, sum of squares); the normalised row goes to the resident A tile (bf16) and back to the fp32
 // residual stream (in place: a thread only ever touches its own elements).
+// PARK (chain kernels): pass A writes y = projection + bias + residual back into the accumulator's TMEM columns, so
+// pass B needs neither the residual (global) nor the bias again; the residual granules of the next 32 columns are
+// requested while the current ones are consumed.
+template <bool PARK>
 __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedParams& p, const float* bias,
                                                    const float* gamma, const float* beta, const uint8_t* zero_rows) {
     for (int i = c.wtid; i < FD; i += NW * 32) {
@@ -304,6 +308,67 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS + row;
     const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
+    if constexpr (PARK) {
+    float4 ra[8], rb[8];
+    auto load_res = [&](float4 (&r)[8], int i) {
+        const int c0 = c.half * 256 + i * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) r[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+    };
+    auto pass_a = [&](const float4 (&r)[8], int i) {
+        const int c0 = c.half * 256 + i * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float y0 = __uint_as_float(v[4 * g]) + c.s_bias[c0 + 4 * g] + r[g].x;
+            const float y1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r[g].y;
+            const float y2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r[g].z;
+            const float y3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r[g].w;
+            s1 += (y0 + y1) + (y2 + y3);
+            s2 = fmaf(y0, y0, s2); s2 = fmaf(y1, y1, s2); s2 = fmaf(y2, y2, s2); s2 = fmaf(y3, y3, s2);
+            v[4 * g] = __float_as_uint(y0); v[4 * g + 1] = __float_as_uint(y1);
+            v[4 * g + 2] = __float_as_uint(y2); v[4 * g + 3] = __float_as_uint(y3);
+        }
+        tmem_st_32x32b_x32(taddr + c0, v);
+    };
+    load_res(ra, 0);
+#pragma unroll 1
+    for (int i = 0; i < 8; i += 2) {
+        load_res(rb, i + 1);
+        pass_a(ra, i);
+        if (i + 2 < 8) load_res(ra, i + 2);
+        pass_a(rb, i + 1);
+    }
+    tmem_st_wait();
+    c.s_stat[c.half * TILE_ROWS + row] = s1;
+    c.s_stat[(2 + c.half) * TILE_ROWS + row] = s2;
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + c.quad) : "memory");
+    const float S1 = c.s_stat[row] + c.s_stat[TILE_ROWS + row];
+    const float S2 = c.s_stat[2 * TILE_ROWS + row] + c.s_stat[3 * TILE_ROWS + row];
+    const float mean = S1 * (1.f / FD);
+    const float var = fmaxf(S2 * (1.f / FD) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    const bool zero = !live || (zero_rows != nullptr && zero_rows[grow] != 0);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int c0 = c.half * 256 + i * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            f[j] = zero ? 0.f : (__uint_as_float(v[j]) - mean) * rstd * c.s_gamma[c0 + j] + c.s_beta[c0 + j];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
+    }
+    } else {
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
         const int c0 = c.half * 256 + i * 32;
@@ -358,6 +423,7 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
 #pragma unroll
         for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
+    }
     }
     release_acc(c, 4, 0);
     publish_a(c);
@@ -948,18 +1014,18 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     bf16* cache_t = p.qkv_cache + (static_cast<size_t>(L) * p.T + p.t) * p.R * 3 * FD;
                     for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, cache_t, 3 * FD);
                 } else if (k == 1) {
-                    epilogue_layernorm(c, p, W.b_o1, W.g1, W.be1, nullptr);
+                    epilogue_layernorm<true>(c, p, W.b_o1, W.g1, W.be1, nullptr);
                 } else if (k == 2) {
                     for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, p.q_out, FD);
                 } else if (k == 3) {
-                    epilogue_layernorm(c, p, W.b_o2, W.g2, W.be2, nullptr);
+                    epilogue_layernorm<true>(c, p, W.b_o2, W.g2, W.be2, nullptr);
                 } else if (k == 4) {
                     for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, nullptr, 0);
                     fence_proxy_async();  // hidden tile (global, generic proxy) -> TMA reads (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready);
                 } else {
-                    epilogue_layernorm(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
+                    epilogue_layernorm<false>(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
                 }
             }
             pdl_launch_dependents();
@@ -985,7 +1051,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             self_attention_phase(c, p, cache_l);
             publish_attention(c);
             fstamp(p, tile, sb + 2, tr);
-            epilogue_layernorm(c, p, W.b_o1, W.g1, W.be1, nullptr);
+            epilogue_layernorm<false>(c, p, W.b_o1, W.g1, W.be1, nullptr);
             fstamp(p, tile, sb + 3, tr);
             for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_QG>(c, p, W.b_q, ch, nullptr, 0);
             workers_sync();
@@ -993,14 +1059,14 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             cross_attention_phase(c, p, p.cross_kv + static_cast<size_t>(L) * p.cross_layer_stride);
             publish_attention(c);
             fstamp(p, tile, sb + 5, tr);
-            epilogue_layernorm(c, p, W.b_o2, W.g2, W.be2, nullptr);
+            epilogue_layernorm<false>(c, p, W.b_o2, W.g2, W.be2, nullptr);
             fstamp(p, tile, sb + 6, tr);
             for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, nullptr, 0);
             fence_proxy_async();  // hidden tile (global, generic proxy) -> bulk-copy reads (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(h_ready);
             fstamp(p, tile, sb + 7, tr);
-            epilogue_layernorm(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
+            epilogue_layernorm<false>(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
         }
         fstamp(p, tile, 2 + p.n_layers * 8, tr);
         pdl_launch_dependents();

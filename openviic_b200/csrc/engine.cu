@@ -772,6 +772,36 @@ extern "C" int cap_engine_caption_host_async(cap_engine* e, const void* feats_ho
     return CAP_OK;
 }
 
+// Device-resident variant of the call above: features already in HBM, results left in HBM (engine-owned
+// decode + one small device-to-device copy into the caller's buffers), nothing synchronises.
+extern "C" int cap_engine_caption_device_async(cap_engine* e, const void* feats_dev, int feat_dtype, const float* boxes_dev,
+                                               int B, int n, int out_size, int64_t* ids_dev, float* logp_dev, int use_graph,
+                                               cap_stream_t stream) {
+    CAP_REQUIRE(e && e->max_batch > 0, "cap_engine_caption_device: reserve the engine first");
+    CAP_REQUIRE(feats_dev && ids_dev && logp_dev, "cap_engine_caption_device: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAP_PROPAGATE(cap_engine_encode(e, feats_dev, feat_dtype, boxes_dev, B, n, s));
+    CAP_PROPAGATE(cap_engine_beam_search(e, out_size, e->out_ids, e->out_logp, use_graph, s));
+    const size_t count = static_cast<size_t>(B) * out_size * e->desc.max_len;
+    CAP_CHECK_CUDA(cudaMemcpyAsync(ids_dev, e->out_ids, count * 8, cudaMemcpyDeviceToDevice, s));
+    CAP_CHECK_CUDA(cudaMemcpyAsync(logp_dev, e->out_logp, count * 4, cudaMemcpyDeviceToDevice, s));
+    return CAP_OK;
+}
+
+// Measurement hook (bench.py roofline): the GEMM chains of step t back to back WITHOUT the attention and beam
+// kernels between them -- same launches, same shapes, same weights as in a real step (the activations they read
+// are whatever the last real step left behind).  Returns CAP_ERR_STATE when the engine does not run chains.
+extern "C" int cap_engine_debug_chains(cap_engine* e, int t, cap_stream_t stream) {
+    CAP_REQUIRE(e && e->encoded, "cap_engine_debug_chains: encode first");
+    if (!e->fused || e->fused_mode != 2) return cap_set_error(CAP_ERR_STATE, "cap_engine_debug_chains: engine is not in chain mode");
+    CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, e->cur_batch, stream));
+    for (int l = 0; l < e->desc.dec_layers; ++l) {
+        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, e->cur_batch, stream));
+        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, e->cur_batch, stream));
+    }
+    return CAP_OK;
+}
+
 extern "C" const void* cap_engine_encoder_output(cap_engine* e) { return e ? e->enc_levels : nullptr; }
 extern "C" const uint8_t* cap_engine_encoder_mask(cap_engine* e) { return e ? e->enc_mask : nullptr; }
 extern "C" const float* cap_engine_logits(cap_engine* e, int* ld) {

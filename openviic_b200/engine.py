@@ -141,6 +141,25 @@ class CaptionEngine:
         self.batch, self.n = b, n
         return ids, logp
 
+    def caption_device(self, feats: torch.Tensor, boxes: Optional[torch.Tensor] = None, out_size: int = 1,
+                       use_graph: bool = True, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """Device tensors in, device tensors out, one C call (encode + beam search), nothing synchronises."""
+        if feats.dtype not in (torch.float32, torch.bfloat16):
+            feats = feats.float()
+        feats = feats.contiguous()
+        b, n, _ = feats.shape
+        bx = None if boxes is None else boxes.float().contiguous()
+        if out is None:
+            out = (torch.empty((b, out_size, self.max_len), device=self.device, dtype=torch.int64),
+                   torch.empty((b, out_size, self.max_len), device=self.device, dtype=torch.float32))
+        self._keep = (feats, bx, out)
+        cabi.call("cap_engine_caption_device_async", self._h, feats.data_ptr(),
+                  cabi.CAP_F32 if feats.dtype == torch.float32 else cabi.CAP_BF16,
+                  None if bx is None else bx.data_ptr(), b, n, out_size, out[0].data_ptr(), out[1].data_ptr(),
+                  1 if use_graph else 0, self._stream())
+        self.batch, self.n = b, n
+        return out
+
     # -- step-wise / debug views ------------------------------------------------------------------
     def begin_decode(self):
         cabi.call("cap_engine_begin_decode", self._h, self._stream())
