@@ -560,6 +560,26 @@ extern "C" int cap_engine_begin_decode(cap_engine* e, cap_stream_t stream) {
 
 namespace {
 int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden);
+
+// Decoder stack + vocabulary projection (logits and chunk statistics) of step t on the fused tcgen05 kernel.
+int run_fused_stack(cap_engine* e, int t, cudaStream_t s) {
+    if (e->fused_mode == 1) return cap_fused_decode_step(e->fused, t, e->cur_batch, e->cur_n, s);
+    const cap_model_desc& m = e->desc;
+    const int hd = e->hd(), T = m.max_len, B = e->cur_batch, R = B * e->beam;
+    const size_t rows_cap = static_cast<size_t>(e->max_batch) * e->n_tokens;
+    const float scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
+    CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, B, s));
+    for (int l = 0; l < m.dec_layers; ++l) {
+        const bf16* cache_l = e->qkv_cache + static_cast<size_t>(l) * T * R * 3 * hd;
+        CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd, t, R,
+                                                m.heads, scale, s));
+        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, B, s));
+        CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, e->cross_kv + static_cast<size_t>(l) * rows_cap * 2 * hd,
+                                                 e->enc_mask, e->buf_att, hd, B, e->beam, e->cur_n, m.heads, scale, s));
+        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, B, s));
+    }
+    return CAP_OK;
+}
 }
 
 extern "C" int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t stream) {
@@ -567,6 +587,7 @@ extern "C" int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t strea
     CAP_REQUIRE(t >= 0 && t < e->desc.max_len, "cap_engine_decode_logits: step %d outside [0,%d)", t, e->desc.max_len);
     bf16* x = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->fused) return run_fused_stack(e, t, s);  // the production stack: the fused kernel leaves the logits behind
     CAP_PROPAGATE(run_decoder_stack(e, t, s, &x));
     // bias-free vocabulary projection (decoders.py:90,121); log-softmax happens in the beam row pass
     return run_linear(x, e->desc.d_model, e->vocab_fc, e->logits, e->ld_logits, CAP_F32, CAP_ACT_NONE,
@@ -579,25 +600,8 @@ extern "C" int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->vocab_chunks > 512)  // vocabularies beyond the merge kernel's reach: full row pass over the logits
         return cap_engine_decode_logits(e, t, stream) || cap_engine_beam_advance(e, t, stream);
-    if (e->fused && e->fused_mode == 1) {
-        CAP_PROPAGATE(cap_fused_decode_step(e->fused, t, e->cur_batch, e->cur_n, s));
-        return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, e->vocab_chunks, s);
-    }
     if (e->fused) {
-        const cap_model_desc& m = e->desc;
-        const int hd = e->hd(), T = m.max_len, B = e->cur_batch, R = B * e->beam;
-        const size_t rows_cap = static_cast<size_t>(e->max_batch) * e->n_tokens;
-        const float scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
-        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, B, s));
-        for (int l = 0; l < m.dec_layers; ++l) {
-            const bf16* cache_l = e->qkv_cache + static_cast<size_t>(l) * T * R * 3 * hd;
-            CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd, t,
-                                                    R, m.heads, scale, s));
-            CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, B, s));
-            CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, e->cross_kv + static_cast<size_t>(l) * rows_cap * 2 * hd,
-                                                     e->enc_mask, e->buf_att, hd, B, e->beam, e->cur_n, m.heads, scale, s));
-            CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, B, s));
-        }
+        CAP_PROPAGATE(run_fused_stack(e, t, s));
         return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, e->vocab_chunks, s);
     }
     bf16* x = nullptr;
