@@ -33,6 +33,9 @@ import torch
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
+# 32 streams on the default 8 hardware work queues serialise falsely (a stream's graph launch waits behind another
+# stream's queued work): measured 54 k -> 73 k captions/s.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "captions_per_sec_beam5_len20"
 UNIT = "captions/s"

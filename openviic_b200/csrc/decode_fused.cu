@@ -765,8 +765,11 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
 
 // CHAIN = false: the whole step (attention phases on this CTA's CUDA cores).  CHAIN = true: a range of the
 // step's GEMM jobs with their epilogues (see FusedParams::job_begin).
+// The chain instantiation is capped at 128 registers per thread (setmaxnreg then moves them: 64 for the control
+// warps, 160 for the epilogue warps): a chain CTA then takes 3/4 of the SM's register file instead of all of it, so
+// it can start on an SM that still hosts a few small CTAs of other streams' kernels, and vice versa.
 template <bool CHAIN>
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
+__global__ void __launch_bounds__(FUSED_THREADS, 1) __maxnreg__(CHAIN ? 128 : 168)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     // 1024-byte alignment (SWIZZLE_128B tiles) comes from the declaration: rounding the address up by hand
     // goes through an integer and makes every later access a generic LD/ST instead of LDS/STS.
@@ -821,7 +824,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     if (warp < FIRST_WORKER_WARP) {
     // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
     // the register limit of each region is unambiguous to ptxas)
-    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");   // epilogues only: no need
+    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");   // epilogues only: no need
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");                    // to squeeze these warps
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
@@ -965,7 +968,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     }
     } else {
         // ------------------------------------------------------------------ workers
-        if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+        if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;" ::: "memory");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         WorkerCtx c;
         c.A_buf = A_buf;
@@ -1236,8 +1239,16 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
     } else {                                     // cross fc_o + LN; FFN + LN; next layer's q|k|v or the vocabulary
         p.job_begin = layer * 6 + 3; p.job_end = layer * 6 + 6;
     }
-    cap_launch_kernel(decode_step_fused_kernel<true>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
-                      static_cast<cudaStream_t>(stream), 1, p);
+    // No programmatic dependent launch for a chain: its CTAs each take a whole SM, and an early-started chain
+    // would hold ten SMs idle in griddepcontrol.wait until the attention kernel before it has drained
+    // (OPENVIIC_CHAIN_PDL=1 restores the early start).
+    static const bool chain_pdl = getenv("OPENVIIC_CHAIN_PDL") && atoi(getenv("OPENVIIC_CHAIN_PDL")) != 0;
+    if (chain_pdl) {
+        cap_launch_kernel(decode_step_fused_kernel<true>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
+                          static_cast<cudaStream_t>(stream), 1, p);
+    } else {
+        decode_step_fused_kernel<true><<<dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_step_fused_kernel<chain>");
 }
