@@ -13,6 +13,8 @@
 // projections (gemm_tcgen05.cu).
 #include "cap_common.cuh"
 
+#include <algorithm>
+
 #include <atomic>
 #include <cstdlib>
 
@@ -380,8 +382,12 @@ decode_self_attention_kernel(const bf16* __restrict__ qkv, const int32_t* __rest
 // EPL consecutive elements of the H*64-wide q/k/v rows (head = l*EPL/64), so every key costs one fully
 // coalesced row read for K and one for V with all 32 lanes busy at any step t; per-head scores are
 // reduced across the 64/EPL lanes of the head with shuffles; softmax is online (single pass over keys).
+// Warps per CTA come from the launch (4 by default).  Fat CTAs (16 warps) put the same rows on a quarter of the SMs:
+// the fused decode chains (decode_fused.cu) need SMs that are otherwise EMPTY, and a thin attention kernel spread
+// over all 148 SMs keeps every one of them "dirty" for its whole duration.
+constexpr int DEC_WARPS_MAX = 16;
 template <int EPL>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS_MAX * 32)
 decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
                                   const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
                                   float scale) {
@@ -389,7 +395,7 @@ decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* _
     constexpr int LANES_PER_HEAD = HEAD_DIM / EPL;
     constexpr int VEC = EPL / 8;  // 16-byte vectors per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * DEC_WARPS + warp;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
     if (r >= R) return;
     const int hd = 32 * EPL;
     const size_t row_stride = static_cast<size_t>(3) * hd;
@@ -436,8 +442,11 @@ decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* _
             const bf16* base = qkv + j * step_stride + sl * row_stride + lane * EPL;
 #pragma unroll
             for (int c = 0; c < VEC; ++c) {
-                kreg[u][c] = reinterpret_cast<const bf16x8*>(base + hd)[c];
-                vreg[u][c] = reinterpret_cast<const bf16x8*>(base + 2 * hd)[c];
+                // cache rows are read once per step: streaming loads (evict-first in L2)
+                const uint4 ku = __ldcs(reinterpret_cast<const uint4*>(base + hd) + c);
+                const uint4 vu = __ldcs(reinterpret_cast<const uint4*>(base + 2 * hd) + c);
+                kreg[u][c] = *reinterpret_cast<const bf16x8*>(&ku);
+                vreg[u][c] = *reinterpret_cast<const bf16x8*>(&vu);
             }
         }
 #pragma unroll
@@ -608,10 +617,14 @@ constexpr int XS_CHUNKS = 4;
 __device__ __forceinline__ uint32_t xs_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 template <int BEAMS>
-__global__ void __launch_bounds__(BEAMS * 32)
+__global__ void __launch_bounds__(BEAMS * XS_CHUNKS * 32)
 decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
                                    const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
                                    float scale) {
+    // warp (beam, chunk): the image's keys are split into XS_CHUNKS row chunks, one bulk copy and one mbarrier each;
+    // a warp starts on its chunk the moment it has landed and the XS_CHUNKS partial softmax states of a beam are
+    // merged through the (by then dead) staging area.  Four times the warps of a warp-per-beam layout: the
+    // dependent exp / FMA chain per key is the long pole of this kernel, not the copy.
     pdl_launch_dependents();
     extern __shared__ __align__(128) uint8_t xs_smem[];
     __shared__ __align__(8) uint64_t bars[XS_CHUNKS];
@@ -619,13 +632,17 @@ decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf
     constexpr int ROW_BYTES = 2 * hd * 2;    // K|V row of one key: 2 KB
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int beam = warp % BEAMS, chunk = warp / BEAMS;
     const int rows_per_chunk = (n + XS_CHUNKS - 1) / XS_CHUNKS;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int c = 0; c < XS_CHUNKS; ++c)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs_smem_u32(&bars[c])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // K/V were projected at encode time, many kernels ago: safe to fetch before the PDL wait below
+        // K/V were projected at encode time, many kernels ago: safe to fetch before the PDL wait below.
+        // Streamed once per step: evict-first, so that 77 MB of K|V per step do not push the weights out of L2.
+        uint64_t stream_policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
         const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + static_cast<size_t>(b) * n * ROW_BYTES;
 #pragma unroll
         for (int c = 0; c < XS_CHUNKS; ++c) {
@@ -636,9 +653,10 @@ decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf
             if (bytes) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
                 asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                         xs_smem_u32(xs_smem + static_cast<size_t>(r0) * ROW_BYTES)),
-                    "l"(reinterpret_cast<uint64_t>(src + static_cast<size_t>(r0) * ROW_BYTES)), "r"(bytes), "r"(bar)
+                    "l"(reinterpret_cast<uint64_t>(src + static_cast<size_t>(r0) * ROW_BYTES)), "r"(bytes), "r"(bar),
+                    "l"(stream_policy)
                     : "memory");
             } else {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -648,26 +666,24 @@ decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf
     pdl_wait();  // q comes from the previous kernel
     __syncthreads();  // barrier inits visible to every waiter
 
-    const int row = b * BEAMS + warp;
+    const int row = b * BEAMS + beam;
     float qf[XW_EPL];
     {
         const bf16x8* qp = reinterpret_cast<const bf16x8*>(q + static_cast<size_t>(row) * ldq + lane * XW_EPL);
         unpack8(qp[0], qf);
         unpack8(qp[1], qf + 8);
 #pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) qf[i] *= scale;
+        for (int i = 0; i < XW_EPL; ++i) qf[i] *= scale * 1.4426950408889634f;  // scores in the log2 domain
     }
     const uint8_t* mrow = key_mask ? key_mask + static_cast<size_t>(b) * n : nullptr;
     float m = -INFINITY, l = 0.f, acc[XW_EPL];
 #pragma unroll
     for (int i = 0; i < XW_EPL; ++i) acc[i] = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < XS_CHUNKS; ++c) {
-        const int r0 = c * rows_per_chunk;
-        const int r1 = min(r0 + rows_per_chunk, n);
-        if (r0 >= r1) break;
-        {   // wait for this chunk (phase 0); bounded spin
-            const uint32_t bar = xs_smem_u32(&bars[c]);
+    const int r0 = chunk * rows_per_chunk;
+    const int r1 = min(r0 + rows_per_chunk, n);
+    if (r0 < r1) {
+        {   // wait for this warp's chunk (phase 0); bounded spin
+            const uint32_t bar = xs_smem_u32(&bars[chunk]);
             uint32_t done = 0;
             for (uint32_t spin = 0; !done; ++spin) {
                 asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
@@ -682,43 +698,77 @@ decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf
             float kf[XW_EPL], vf[XW_EPL];
             unpack8(kp[0], kf);
             unpack8(kp[1], kf + 8);
-            float s = 0.f;
+            float s0 = qf[0] * kf[0], s1 = qf[1] * kf[1], s2 = qf[2] * kf[2], s3 = qf[3] * kf[3];
 #pragma unroll
-            for (int i = 0; i < XW_EPL; ++i) s = fmaf(qf[i], kf[i], s);
+            for (int i = 4; i < XW_EPL; i += 4) {
+                s0 = fmaf(qf[i], kf[i], s0);
+                s1 = fmaf(qf[i + 1], kf[i + 1], s1);
+                s2 = fmaf(qf[i + 2], kf[i + 2], s2);
+                s3 = fmaf(qf[i + 3], kf[i + 3], s3);
+            }
+            float s = (s0 + s1) + (s2 + s3);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             unpack8(vp[0], vf);
             unpack8(vp[1], vf + 8);
             const float m_new = fmaxf(m, s);
-            const float corr = __expf(m - m_new);
-            const float p = __expf(s - m_new);
-            l = l * corr + p;
+            const float corr = exp2f(m - m_new);
+            const float p = exp2f(s - m_new);
+            l = fmaf(l, corr, p);
 #pragma unroll
-            for (int i = 0; i < XW_EPL; ++i) acc[i] = acc[i] * corr + p * vf[i];
+            for (int i = 0; i < XW_EPL; ++i) acc[i] = fmaf(p, vf[i], acc[i] * corr);
             m = m_new;
         }
     }
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    float o[XW_EPL];
+    // merge the XS_CHUNKS partial states of each beam; the staging area is dead once every warp is past its keys
+    __syncthreads();
+    float* part = reinterpret_cast<float*>(xs_smem);                  // [warp][lane][XW_EPL + 2]
+    float* mine = part + (static_cast<size_t>(warp) * 32 + lane) * (XW_EPL + 2);
 #pragma unroll
-    for (int i = 0; i < XW_EPL; ++i) o[i] = acc[i] * inv;
-    bf16* orow = out + static_cast<size_t>(row) * ldo + lane * XW_EPL;
-    reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
-    reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
+    for (int i = 0; i < XW_EPL; ++i) mine[i] = acc[i];
+    mine[XW_EPL] = m;
+    mine[XW_EPL + 1] = l;
+    __syncthreads();
+    if (chunk == 0) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < XS_CHUNKS; ++c)
+            mx = fmaxf(mx, part[(static_cast<size_t>(c * BEAMS + beam) * 32 + lane) * (XW_EPL + 2) + XW_EPL]);
+        float lsum = 0.f, o[XW_EPL];
+#pragma unroll
+        for (int i = 0; i < XW_EPL; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < XS_CHUNKS; ++c) {
+            const float* pc = part + (static_cast<size_t>(c * BEAMS + beam) * 32 + lane) * (XW_EPL + 2);
+            const float mc = pc[XW_EPL];
+            const float f = (mc == -INFINITY) ? 0.f : exp2f(mc - mx);
+            lsum = fmaf(pc[XW_EPL + 1], f, lsum);
+#pragma unroll
+            for (int i = 0; i < XW_EPL; ++i) o[i] = fmaf(pc[i], f, o[i]);
+        }
+        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+#pragma unroll
+        for (int i = 0; i < XW_EPL; ++i) o[i] *= inv;
+        bf16* orow = out + static_cast<size_t>(row) * ldo + lane * XW_EPL;
+        reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
+        reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
+    }
 }
 
 template <int BEAMS>
 int launch_cross_smem(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
                       float scale, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(n) * 2048;
+    // K|V staging; the partial-state merge (XS_CHUNKS * BEAMS warps x 32 lanes x 18 floats) reuses it
+    const size_t smem = std::max(static_cast<size_t>(n) * 2048,
+                                 static_cast<size_t>(XS_CHUNKS) * BEAMS * 32 * (XW_EPL + 2) * sizeof(float));
     static bool attr_done = false;
     if (!attr_done) {
         CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_smem_kernel<BEAMS>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
         attr_done = true;
     }
-    CAP_LAUNCH((decode_cross_attention_smem_kernel<BEAMS>), B, BEAMS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n,
-               scale);
+    CAP_LAUNCH((decode_cross_attention_smem_kernel<BEAMS>), B, BEAMS * XS_CHUNKS * 32, smem, stream, q, ldq, kv, key_mask,
+               out, ldo, n, scale);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_cross_attention_smem_kernel");
 }
@@ -844,13 +894,18 @@ extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestr
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bf16* cache = static_cast<const bf16*>(qkv);
     bf16* o = static_cast<bf16*>(out);
-    const int wide_blocks = (R + DEC_WARPS - 1) / DEC_WARPS;
+    static const int self_warps = [] {
+        const char* v = getenv("OPENVIIC_SELF_WARPS");
+        const int w = v ? atoi(v) : DEC_WARPS;
+        return w < 1 ? 1 : (w > DEC_WARPS_MAX ? DEC_WARPS_MAX : w);
+    }();
+    const int wide_blocks = (R + self_warps - 1) / self_warps;
     if (H == 8 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_wide_kernel<16>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
+        CAP_LAUNCH((decode_self_attention_wide_kernel<16>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else if (H == 4 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_wide_kernel<8>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
+        CAP_LAUNCH((decode_self_attention_wide_kernel<8>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else if (H == 16 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_wide_kernel<32>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
+        CAP_LAUNCH((decode_self_attention_wide_kernel<32>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else {
         const int items = R * H;
         CAP_LAUNCH((decode_self_attention_kernel), (items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, H, scale);

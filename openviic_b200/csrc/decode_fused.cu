@@ -154,6 +154,7 @@ __device__ __forceinline__ Job get_job(const FusedParams& p, int ji) {
 
 // 64 bytes per lane (the lane's row) -> global rows, through the warp's staging tile: every store instruction
 // then covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
+template <bool STREAMING = false>
 __device__ __forceinline__ void staged_store64(uint8_t* stage, int lane, const uint4 (&v)[4], uint8_t* gbase,
                                                size_t row_stride, int rows_valid) {
     uint8_t* mine = stage + lane * STAGE_PITCH;
@@ -165,7 +166,10 @@ __device__ __forceinline__ void staged_store64(uint8_t* stage, int lane, const u
         const int idx = it * 32 + lane;
         const int rr = idx >> 2, part = idx & 3;
         const uint4 x = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + part * 16);
-        if (rr < rows_valid) *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(rr) * row_stride + part * 16) = x;
+        if (rr < rows_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(rr) * row_stride + part * 16);
+            if (STREAMING) __stcs(dst, x); else *dst = x;   // logits are written once and almost never read back
+        }
     }
     __syncwarp();
 }
@@ -751,7 +755,7 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
                 for (int g = 0; g < 4; ++g)
                     o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
                 uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
-                staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
+                staged_store64<true>(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
             }
         }
     }
@@ -830,6 +834,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         // ------------------------------------------------------------------ producer (weights never wait)
         // The whole warp runs the loop (uniform control flow); one elected lane issues the copies.
         uint32_t bcount = 0, acount = 0, hphase = 0, rphase = 0;
+        const uint64_t keep_policy = l2_policy_evict_last();   // weights: shared by every tile of every batch in flight
         for (int ji = job_lo; ji <= job_hi; ++ji) {
             const Job job = get_job(p, ji);
             const int nch = job.ntiles / job.chunk;
@@ -848,8 +853,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                                 mbar_arrive(&b_full[s]);
                             } else {
                                 mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
-                                tma_load_2d(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
-                                            job.row0 + (c * job.chunk + j) * 128);
+                                tma_load_2d_hint(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
+                                                 job.row0 + (c * job.chunk + j) * 128, keep_policy);
                             }
                         }
                         __syncwarp();

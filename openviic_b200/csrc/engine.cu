@@ -251,6 +251,13 @@ int run_ln(const float* y32, const float* res32, const Norm& n, const float* pos
                              out32, d, rows, d, s);
 }
 
+// timing-only ablations (results are wrong): OPENVIIC_DBG_ABLATE bit 0 = no decode self-attention kernels,
+// bit 1 = no encoder layers, bit 2 = no decode chains, bit 3 = no decode cross-attention kernels
+int dbg_ablate() {
+    static const int v = getenv("OPENVIIC_DBG_ABLATE") ? atoi(getenv("OPENVIIC_DBG_ABLATE")) : 0;
+    return v;
+}
+
 // LN(res32 + x.W^T + b): one cluster kernel when the row fits a cluster (d_model 128..1024), else GEMM + LayerNorm
 int run_linear_ln(cap_engine* e, const bf16* x, int ldx, const Linear& l, const float* res32, const Norm& n,
                   const float* pos, int pos_rows, const uint8_t* zero_rows, bf16* out16, float* out32, int rows,
@@ -507,7 +514,7 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
                                         m.trig_geometry, s));
 
     const bf16* x = e->buf_x;
-    for (int l = 0; l < m.enc_layers; ++l) {
+    for (int l = 0; l < ((dbg_ablate() & 2) ? 0 : m.enc_layers); ++l) {
         const EncoderLayerW& L = e->enc[l];
         bf16* level_out = e->enc_levels + static_cast<size_t>(l) * rows_cap * d;
         CAP_PROPAGATE(run_linear(x, d, L.att.qkv, e->buf_qkv, 3 * hd, CAP_BF16, CAP_ACT_NONE, rows, s));
@@ -561,6 +568,7 @@ extern "C" int cap_engine_begin_decode(cap_engine* e, cap_stream_t stream) {
 namespace {
 int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden);
 
+
 // Decoder stack + vocabulary projection (logits and chunk statistics) of step t on the fused tcgen05 kernel.
 int run_fused_stack(cap_engine* e, int t, cudaStream_t s) {
     if (e->fused_mode == 1) return cap_fused_decode_step(e->fused, t, e->cur_batch, e->cur_n, s);
@@ -568,15 +576,32 @@ int run_fused_stack(cap_engine* e, int t, cudaStream_t s) {
     const int hd = e->hd(), T = m.max_len, B = e->cur_batch, R = B * e->beam;
     const size_t rows_cap = static_cast<size_t>(e->max_batch) * e->n_tokens;
     const float scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
-    CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, B, s));
+    const int ab = dbg_ablate();
+    if (!(ab & 4)) CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, B, s));
     for (int l = 0; l < m.dec_layers; ++l) {
         const bf16* cache_l = e->qkv_cache + static_cast<size_t>(l) * T * R * 3 * hd;
-        CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd, t, R,
-                                                m.heads, scale, s));
-        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, B, s));
-        CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, e->cross_kv + static_cast<size_t>(l) * rows_cap * 2 * hd,
-                                                 e->enc_mask, e->buf_att, hd, B, e->beam, e->cur_n, m.heads, scale, s));
-        CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, B, s));
+        if (!(ab & 1))
+            CAP_PROPAGATE(cap_decode_self_attention(cache_l, cap_beam_ancestry(e->beam_state), e->padflag, e->buf_att, hd, t,
+                                                    R, m.heads, scale, s));
+        if (!(ab & 4)) CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, B, s));
+        if (!(ab & 8)) {
+            const bf16* kv = e->cross_kv + static_cast<size_t>(l) * rows_cap * 2 * hd;
+            static const bool cross_mma = getenv("OPENVIIC_CROSS_MMA") && atoi(getenv("OPENVIIC_CROSS_MMA")) != 0;
+            if (cross_mma) {  // the image's beams as the queries of a batched tensor-core attention (nq = beam)
+                cap_attention_args a = {};
+                a.q = e->buf_q; a.k = kv; a.v = kv + hd; a.out = e->buf_att;
+                a.q_bs = a.o_bs = static_cast<int64_t>(e->beam) * hd;
+                a.k_bs = a.v_bs = static_cast<int64_t>(e->cur_n) * 2 * hd;
+                a.ldq = a.ldo = hd; a.ldk = a.ldv = 2 * hd;
+                a.mask = e->enc_mask; a.mask_bs = e->cur_n; a.mask_qs = 0;
+                a.B = B; a.H = m.heads; a.nq = e->beam; a.nk = e->cur_n; a.scale = scale;
+                CAP_PROPAGATE(cap_attention(&a, s));
+            } else {
+                CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, kv, e->enc_mask, e->buf_att, hd, B, e->beam, e->cur_n,
+                                                         m.heads, scale, s));
+            }
+        }
+        if (!(ab & 4)) CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, B, s));
     }
     return CAP_OK;
 }
