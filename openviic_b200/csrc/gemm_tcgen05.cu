@@ -134,6 +134,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     // the TMA / tcgen05 instructions: issued from an `if (lane == 0)` region every tcgen05.mma was wrapped in an
     // ELECT / R2UR / BRA.U.ANY loop and cost the single thread ~200 cycles (3x the MMA's own 64-cycle floor).
     if (warp == 0) {
+        const uint64_t keep_policy = l2_policy_evict_last();  // weights stay in L2 across the batches in flight
         pdl_wait();  // A (and only A) may still be in flight from the previous kernel
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % stages;
@@ -144,12 +145,12 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 if constexpr (CTA2) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // both CTAs' four tiles
                     tma_load_2d_2sm(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
-                    tma_load_2d_2sm(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K,
-                                    n0 + static_cast<int>(rank) * B_ROWS);
+                    tma_load_2d_2sm_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K,
+                                         n0 + static_cast<int>(rank) * B_ROWS, keep_policy);
                 } else {
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
-                    tma_load_2d(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+                    tma_load_2d_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0, keep_policy);  // weights
                 }
                 if (kb == 0) stamp(p, 2);
             }
