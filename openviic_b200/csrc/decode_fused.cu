@@ -64,7 +64,9 @@ constexpr uint32_t OFF_GAMMA = OFF_CBIAS + FD * 4;
 constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
 constexpr uint32_t OFF_STAT = OFF_BETA + FD * 4;       // [2 (sum, sumsq)][2 halves][128 rows]
 constexpr uint32_t OFF_BARS = OFF_STAT + 4 * TILE_ROWS * 4;
-constexpr int NUM_BARS = 2 * NB + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1 + 1;
+constexpr int NB_PAIR = 8;            // CTA pairs stage HALF of every weight tile: the same 64 KB hold 8 k-block stages
+constexpr uint32_t B_STAGE_BYTES_PAIR = 64 * 64 * 2;
+constexpr int NUM_BARS = 2 * NB_PAIR + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1 + 1;
 constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
 constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16;
 
@@ -78,6 +80,7 @@ struct FusedParams {
     CUtensorMap map_vocab;  // [V][512]
     CUtensorMap map_h;      // [tiles * 128][2048] FFN hidden scratch
     CUtensorMap map_att;    // [max_rows][512] attention output of the stand-alone attention kernels (chain mode)
+    CUtensorMap map_w512_h, map_w2_h, map_vocab_h;   // the three weight maps with 64-row boxes (CTA pairs)
     FusedLayerP layer[MAX_FUSED_LAYERS];
     int n_layers;
     const int32_t* tokens;
@@ -120,6 +123,7 @@ __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot,
 
 struct Job {
     const CUtensorMap* map;
+    const CUtensorMap* map_half;   // same matrix, 64-row boxes
     int row0, ntiles, kblocks, chunk;
     bool stream;
 };
@@ -129,8 +133,10 @@ __device__ __forceinline__ Job get_job(const FusedParams& p, int ji) {
     j.kblocks = FD / BLOCK_K;
     j.stream = false;
     j.map = &p.map_w512;
+    j.map_half = &p.map_w512_h;
     if (ji == p.n_layers * 6) {
         j.map = &p.map_vocab;
+        j.map_half = &p.map_vocab_h;
         j.row0 = 0;
         j.ntiles = p.vocab_tiles;
         j.chunk = 2;
@@ -145,7 +151,7 @@ __device__ __forceinline__ Job get_job(const FusedParams& p, int ji) {
         case 3: j.row0 = base + 2560; j.ntiles = 4; j.chunk = 4; break;       // cross fc_o (+ LN)
         case 4: j.row0 = base + 3072; j.ntiles = 16; j.chunk = 2; break;      // fc1 (+ ReLU)
         default:
-            j.map = &p.map_w2; j.row0 = L * FD; j.ntiles = 4; j.chunk = 4; j.kblocks = FDFF / BLOCK_K;
+            j.map = &p.map_w2; j.map_half = &p.map_w2_h; j.row0 = L * FD; j.ntiles = 4; j.chunk = 4; j.kblocks = FDFF / BLOCK_K;
             j.stream = true;                                                  // fc2 (+ LN), A = hidden tile
             break;
     }
@@ -193,6 +199,7 @@ struct WorkerCtx {
     float *s_bias, *s_cbias, *s_gamma, *s_beta, *s_stat;
     uint64_t *acc_full, *acc_empty, *a_ready, *h_ready, *ring_free;
     uint8_t* kv_ring;  // this warp's K|V row ring (inside the weight ring)
+    bool pair_peer;    // CTA pair, and this CTA is not the leader: consumer-side barriers live in the leader CTA
     uint32_t tmem_base;
     uint32_t use0, use1;  // completed uses of TMEM buffer 0 / 1 (scalars: no dynamically indexed state)
     int toggle;
@@ -217,11 +224,16 @@ __device__ __forceinline__ void release_acc(WorkerCtx& c, int chunk, int b) {
     tcgen05_fence_before();
     __syncwarp();
     if (chunk == 4) {
-        if (c.lane == 0) { mbar_arrive(&c.acc_empty[0]); mbar_arrive(&c.acc_empty[1]); }
+        if (c.lane == 0) {
+            if (c.pair_peer) { mbar_arrive_remote(&c.acc_empty[0], 0); mbar_arrive_remote(&c.acc_empty[1], 0); }
+            else { mbar_arrive(&c.acc_empty[0]); mbar_arrive(&c.acc_empty[1]); }
+        }
         c.use0++; c.use1++;
         c.toggle = 0;
     } else {
-        if (c.lane == 0) mbar_arrive(&c.acc_empty[b]);
+        if (c.lane == 0) {
+            if (c.pair_peer) mbar_arrive_remote(&c.acc_empty[b], 0); else mbar_arrive(&c.acc_empty[b]);
+        }
         if (b) c.use1++; else c.use0++;
         c.toggle ^= 1;
     }
@@ -231,7 +243,9 @@ __device__ __forceinline__ void release_acc(WorkerCtx& c, int chunk, int b) {
 __device__ __forceinline__ void publish_a(WorkerCtx& c) {
     fence_proxy_async_smem();
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(c.a_ready);
+    if (c.lane == 0) {
+        if (c.pair_peer) mbar_arrive_remote(c.a_ready, 0); else mbar_arrive(c.a_ready);
+    }
 }
 
 enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
@@ -772,9 +786,18 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
 // The chain instantiation is capped at 128 registers per thread (setmaxnreg then moves them: 64 for the control
 // warps, 160 for the epilogue warps): a chain CTA then takes 3/4 of the SM's register file instead of all of it, so
 // it can start on an SM that still hosts a few small CTAs of other streams' kernels, and vice versa.
-template <bool CHAIN>
+// PAIR (chains only): two CTAs of a cluster, each with its own 128-row tile, share every weight tile -- each
+// stages HALF of it (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared
+// memories and both CTAs drain their own accumulator rows.  A ring byte then feeds 256 rows instead of 128: the
+// same 64 KB ring keeps 8 k-block stages in flight instead of 4 (the chains are bound by that ring's latency).
+template <bool CHAIN, bool PAIR = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) __maxnreg__(CHAIN ? 128 : 168)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
+    static_assert(CHAIN || !PAIR, "CTA pairs exist for the chain kernels only");
+    constexpr int NBX = PAIR ? NB_PAIR : NB;
+    constexpr uint32_t BST = PAIR ? B_STAGE_BYTES_PAIR : B_STAGE_BYTES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     // 1024-byte alignment (SWIZZLE_128B tiles) comes from the declaration: rounding the address up by hand
     // goes through an integer and makes every later access a generic LD/ST instead of LDS/STS.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -783,8 +806,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     uint8_t* B_ring = smem + OFF_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint64_t* b_full = bars;
-    uint64_t* b_empty = b_full + NB;
-    uint64_t* a_full = b_empty + NB;
+    uint64_t* b_empty = b_full + NB_PAIR;
+    uint64_t* a_full = b_empty + NB_PAIR;
     uint64_t* a_empty = a_full + A_SLOTS;
     uint64_t* acc_full = a_empty + A_SLOTS;
     uint64_t* acc_empty = acc_full + 2;
@@ -808,20 +831,21 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+            constexpr int consumers = PAIR ? 2 * NW : NW;   // pair: the leader's barriers hear both CTAs' workers
+            for (int s = 0; s < NBX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
             for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NW); }
-            mbar_init(a_ready, NW);
+            for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], consumers); }
+            mbar_init(a_ready, consumers);
             mbar_init(h_ready, NW);
             mbar_init(ring_free, NW);
             mbar_init(a_load, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_slot);
+        if constexpr (PAIR) tmem_alloc_2sm<512>(tmem_slot); else tmem_alloc<512>(tmem_slot);
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync(); else __syncthreads();   // pair: the peer's barriers exist before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -846,10 +870,16 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             for (int c = 0; c < nch; ++c) {
                 for (int kb = 0; kb < job.kblocks; ++kb) {
                     for (int j = 0; j < job.chunk; ++j) {
-                        const uint32_t s = bcount % NB;
-                        mbar_wait(&b_empty[s], ((bcount / NB) & 1) ^ 1);
+                        const uint32_t s = bcount % NBX;
+                        mbar_wait(&b_empty[s], ((bcount / NBX) & 1) ^ 1);
                         if (elect_one_sync()) {
-                            if (p.dbg_skip & 2) {
+                            if constexpr (PAIR) {
+                                // both CTAs signal the LEADER's barrier, which expects the two halves of the tile
+                                if (leader) mbar_arrive_expect_tx(&b_full[s], 2 * BST);
+                                tma_load_2d_2sm_hint(B_ring + s * BST, job.map_half, &b_full[s], kb * BLOCK_K,
+                                                     job.row0 + (c * job.chunk + j) * 128 + static_cast<int>(rank) * 64,
+                                                     keep_policy);
+                            } else if (p.dbg_skip & 2) {
                                 mbar_arrive(&b_full[s]);
                             } else {
                                 mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
@@ -868,8 +898,13 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                         const uint32_t slot = acount % A_SLOTS;
                         mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1);
                         if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(&a_full[slot], A_KB_BYTES);
-                            tma_load_2d(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
+                            if constexpr (PAIR) {
+                                if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * A_KB_BYTES);
+                                tma_load_2d_2sm(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
+                            } else {
+                                mbar_arrive_expect_tx(&a_full[slot], A_KB_BYTES);
+                                tma_load_2d(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
+                            }
                         }
                         __syncwarp();
                         ++acount;
@@ -878,10 +913,16 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             }
         }
         pdl_launch_dependents();
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 && leader) {
+        // ------------------------------------------------------------------ MMA issuer (pair: the leader's only)
         // Uniform control flow for the whole warp; the elected lane issues tcgen05.mma / tcgen05.commit.
-        constexpr uint32_t idesc = make_instr_desc(128, 128);
+        constexpr uint32_t idesc = make_instr_desc(PAIR ? 256 : 128, 128);
+        auto wait_consumers = [](uint64_t* bar, uint32_t parity) {
+            if constexpr (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+        };
+        auto commit = [](uint64_t* bar) {
+            if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar);
+        };
         uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
         int toggle = 0;
         for (int ji = job_lo; ji <= job_hi; ++ji) {
@@ -890,7 +931,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             if (CHAIN && ji == job_lo && !p.start_embed) {
                 mbar_wait(a_load, 0);   // the chain's first A tile arrives by TMA (warp 2)
             } else if (!job.stream) {
-                mbar_wait(a_ready, ar & 1);
+                wait_consumers(a_ready, ar & 1);
                 ++ar;
             }
             tcgen05_fence_after();
@@ -898,11 +939,11 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                 int b = 0;
                 uint32_t colbase = 0;
                 if (job.chunk == 4) {
-                    mbar_wait(&acc_empty[0], (use0 & 1) ^ 1);
-                    mbar_wait(&acc_empty[1], (use1 & 1) ^ 1);
+                    wait_consumers(&acc_empty[0], (use0 & 1) ^ 1);
+                    wait_consumers(&acc_empty[1], (use1 & 1) ^ 1);
                 } else {
                     b = toggle;
-                    mbar_wait(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
+                    wait_consumers(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
                     colbase = b * 256;
                 }
                 tcgen05_fence_after();
@@ -918,34 +959,39 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     }
                     const uint64_t a_desc = make_smem_desc(a_tile);
                     for (int j = 0; j < job.chunk; ++j) {
-                        const uint32_t s = bcount % NB;
-                        mbar_wait(&b_full[s], (bcount / NB) & 1);
+                        const uint32_t s = bcount % NBX;
+                        mbar_wait(&b_full[s], (bcount / NBX) & 1);
                         tcgen05_fence_after();
-                        const uint64_t b_desc = make_smem_desc(B_ring + s * B_STAGE_BYTES);
+                        const uint64_t b_desc = make_smem_desc(B_ring + s * BST);
                         if (elect_one_sync()) {
                             if (!(p.dbg_skip & 1)) {
 #pragma unroll
-                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                    umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                              (kb | k) != 0 ? 1u : 0u);
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                    if constexpr (PAIR)
+                                        umma_bf16_2sm(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                                      (kb | k) != 0 ? 1u : 0u);
+                                    else
+                                        umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                                  (kb | k) != 0 ? 1u : 0u);
+                                }
                             }
-                            umma_commit(&b_empty[s]);  // stage reusable once these MMAs have read it
+                            commit(&b_empty[s]);  // stage reusable (in both CTAs) once these MMAs have read it
                         }
                         __syncwarp();
                         ++bcount;
                     }
                     if (job.stream) {
-                        if (elect_one_sync()) umma_commit(&a_empty[slot]);
+                        if (elect_one_sync()) commit(&a_empty[slot]);
                         __syncwarp();
                         ++acount;
                     }
                 }
                 if (elect_one_sync()) {
                     if (job.chunk == 4) {
-                        umma_commit(&acc_full[0]);
-                        umma_commit(&acc_full[1]);
+                        commit(&acc_full[0]);
+                        commit(&acc_full[1]);
                     } else {
-                        umma_commit(&acc_full[b]);
+                        commit(&acc_full[b]);
                     }
                 }
                 __syncwarp();
@@ -964,9 +1010,15 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         if (!p.start_embed) {
             pdl_wait();  // the attention kernel that wrote the tile is the stream predecessor
             if (elect_one_sync()) {
-                mbar_arrive_expect_tx(a_load, A_SLOTS * A_KB_BYTES);
-                for (int kb = 0; kb < A_SLOTS; ++kb)
-                    tma_load_2d(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, tile * TILE_ROWS);
+                if constexpr (PAIR) {
+                    if (leader) mbar_arrive_expect_tx(a_load, 2 * A_SLOTS * A_KB_BYTES);
+                    for (int kb = 0; kb < A_SLOTS; ++kb)
+                        tma_load_2d_2sm(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, tile * TILE_ROWS);
+                } else {
+                    mbar_arrive_expect_tx(a_load, A_SLOTS * A_KB_BYTES);
+                    for (int kb = 0; kb < A_SLOTS; ++kb)
+                        tma_load_2d(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, tile * TILE_ROWS);
+                }
             }
             __syncwarp();
         }
@@ -994,6 +1046,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.h_ready = h_ready;
         c.ring_free = ring_free;
         c.kv_ring = B_ring + c.ww * KV_SLOTS * KV_ROW_BYTES;
+        c.pair_peer = PAIR && !leader;
         c.tmem_base = tmem_base;
         c.use0 = c.use1 = 0;
         c.toggle = 0;
@@ -1084,10 +1137,10 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync(); else __syncthreads();   // pair: the leader's MMAs read the peer's shared memory
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (PAIR) tmem_dealloc_2sm<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -1114,7 +1167,7 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     memset(&p, 0, sizeof(p));
     const int L = d->n_layers;
     p.n_layers = L;
-    f->tiles = (d->max_rows + TILE_ROWS - 1) / TILE_ROWS;
+    f->tiles = ((d->max_rows + TILE_ROWS - 1) / TILE_ROWS + 1) / 2 * 2;   // even: CTA pairs; scratch tiles exist for a dummy partner
     auto fail = [&](int rc) { cap_fused_destroy(f); return rc; };
     // stacked weight copies: one tensor map covers every K = 512 projection of the model
     const size_t w512_elems = static_cast<size_t>(L) * W512_ROWS_PER_LAYER * FD;
@@ -1146,6 +1199,9 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     int rc = cap_gemm::make_tmap(&p.map_w512, f->w512, L * W512_ROWS_PER_LAYER, FD, FD, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, f->w2, L * FD, FDFF, FDFF, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, d->w_vocab, d->vocab, FD, FD, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, f->w512, L * W512_ROWS_PER_LAYER, FD, FD, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, f->w2, L * FD, FDFF, FDFF, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab_h, d->w_vocab, d->vocab, FD, FD, 64);
     if (rc != CAP_OK) return fail(rc);
     p.tokens = d->tokens; p.word_emb = static_cast<const bf16*>(d->word_emb); p.word_pos = d->word_pos; p.pad_idx = d->pad_idx;
     p.qkv_cache = static_cast<bf16*>(d->qkv_cache); p.ancestry = d->ancestry; p.padflag = d->padflag;
@@ -1176,7 +1232,8 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     p.q_out = static_cast<bf16*>(d->q_out);
     f->has_att = d->att_in != nullptr;
     if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
     return CAP_OK;
@@ -1210,12 +1267,6 @@ extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_k
     p.trace = g_fused_trace;
     static const int dbg_skip = getenv("OPENVIIC_FUSED_DBG_SKIP") ? atoi(getenv("OPENVIIC_FUSED_DBG_SKIP")) : 0;
     p.dbg_skip = dbg_skip;
-    static bool backoff_set = false;
-    if (!backoff_set) {
-        backoff_set = true;
-        const unsigned int ns = getenv("OPENVIIC_FUSED_DBG_BACKOFF_NS") ? static_cast<unsigned int>(atoi(getenv("OPENVIIC_FUSED_DBG_BACKOFF_NS"))) : 0u;
-        if (ns) cudaMemcpyToSymbol(cap_ptx::g_mbar_backoff_ns, &ns, sizeof(ns));
-    }
     cap_launch_kernel(decode_step_fused_kernel<false>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
                       static_cast<cudaStream_t>(stream), 1, p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1245,12 +1296,24 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         p.job_begin = layer * 6 + 3; p.job_end = layer * 6 + 6;
     }
     // No programmatic dependent launch for a chain: its CTAs each take a whole SM, and an early-started chain
-    // would hold ten SMs idle in griddepcontrol.wait until the attention kernel before it has drained
-    // (OPENVIIC_CHAIN_PDL=1 restores the early start).
-    static const bool chain_pdl = getenv("OPENVIIC_CHAIN_PDL") && atoi(getenv("OPENVIIC_CHAIN_PDL")) != 0;
-    if (chain_pdl) {
-        cap_launch_kernel(decode_step_fused_kernel<true>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
-                          static_cast<cudaStream_t>(stream), 1, p);
+    // would hold them idle in griddepcontrol.wait until the attention kernel before it has drained.
+    // CTA pairs (OPENVIIC_CHAIN_PAIR=0: single CTAs): clusters of two adjacent tiles, the second CTA of the last
+    // pair is a dummy when the tile count is odd (every access of it is guarded by the row count).
+    static const bool use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
+    if (use_pairs) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((tiles + 1) / 2 * 2);
+        cfg.blockDim = dim3(FUSED_THREADS);
+        cfg.dynamicSmemBytes = FUSED_SMEM;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
     } else {
         decode_step_fused_kernel<true><<<dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     }

@@ -22,9 +22,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 
-// debug: nanoseconds to sleep after a failed try_wait (0 = poll again at once)
-static __device__ unsigned int g_mbar_backoff_ns = 0;
-
 // Bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -41,10 +38,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (g_mbar_backoff_ns) __nanosleep(g_mbar_backoff_ns);
         if (spin == 64) start = clock64();
         if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
     }
+}
+
+// same, acquiring at cluster scope: the arrivals come from the peer CTA of a pair (remote mbarrier.arrive)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long start = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (spin == 64) start = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
+    }
+}
+
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
