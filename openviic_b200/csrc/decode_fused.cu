@@ -468,19 +468,20 @@ __device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) 
             pad_t[grow] = (mytok == p.pad_idx) ? 1 : 0;
         }
     }
+    constexpr int EMB_ROWS = 8;   // rows embedded per round: 16 independent 16-byte loads in flight per lane
 #pragma unroll 1
-    for (int i0 = 0; i0 < ROWS_PER_WARP; i0 += 4) {
-        bf16x8 e[4][2];
-        int tk[4];
+    for (int i0 = 0; i0 < ROWS_PER_WARP; i0 += EMB_ROWS) {
+        bf16x8 e[EMB_ROWS][2];
+        int tk[EMB_ROWS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < EMB_ROWS; ++u) {
             tk[u] = __shfl_sync(0xffffffffu, mytok, i0 + u);
             const bf16x8* ep = reinterpret_cast<const bf16x8*>(p.word_emb + static_cast<size_t>(max(tk[u], 0)) * FD + c.lane * 16);
             e[u][0] = ep[0];
             e[u][1] = ep[1];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < EMB_ROWS; ++u) {
             const int row = c.ww * ROWS_PER_WARP + i0 + u;
             float a[16];
             unpack8(e[u][0], a);
@@ -852,7 +853,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     if (warp < FIRST_WORKER_WARP) {
     // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
     // the register limit of each region is unambiguous to ptxas)
-    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");   // epilogues only: no need
+    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // epilogues only: no need
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");                    // to squeeze these warps
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
@@ -1025,7 +1026,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     }
     } else {
         // ------------------------------------------------------------------ workers
-        if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;" ::: "memory");
+        if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         WorkerCtx c;
         c.A_buf = A_buf;
