@@ -237,6 +237,11 @@ int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_keys, cap_st
  *   vocabulary projection + chunk statistics. */
 enum cap_fused_chain_kind { CAP_CHAIN_EMBED_QKV = 0, CAP_CHAIN_SELF_OUT = 1, CAP_CHAIN_FFN = 2 };
 int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t, int B, cap_stream_t stream);
+/* By default the vocabulary epilogue of the chains stores only the 32-column groups of logits that can contain one
+ * of a row's `beam` best candidates (cap_beam_step_stats reads nothing else); on != 0 stores every logit (debug
+ * views, cap_engine_decode_logits; OPENVIIC_FULL_LOGITS=1 sets it at creation). */
+int cap_fused_set_full_logits(cap_fused_decoder* f, int on);
+int cap_fused_get_full_logits(cap_fused_decoder* f);
 /* Debug: when non-NULL, every later fused step writes %globaltimer stamps (ns) of its phase boundaries into
  * device_buffer[tile*64 + k]: 0 entry, 1 dependencies resolved, then per layer L at 2+8L: layer start,
  * q|k|v stored, self-attention done, LN1 done, cross q stored, cross-attention done, LN2 done, hidden stored;

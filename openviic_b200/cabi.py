@@ -78,6 +78,8 @@ SIGNATURES = {
     "cap_fused_destroy": (_i, [_vp]),
     "cap_fused_decode_step": (_i, [_vp, _i, _i, _i, _vp]),
     "cap_debug_fused_trace": (_i, [_vp]),
+    "cap_fused_set_full_logits": (_i, [_vp, _i]),
+    "cap_fused_get_full_logits": (_i, [_vp]),
     "cap_fused_chain": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "cap_linear_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cap_engine_create": (_i, [C.POINTER(ModelDesc), C.POINTER(_vp)]),

@@ -110,6 +110,7 @@ struct FusedParams {
     // as stand-alone kernels that share SMs with everything else in flight
     int job_begin, job_end, start_embed;
     bf16* q_out;             // [R][512] cross-attention queries for the stand-alone kernel (chain mode)
+    int sparse_logits;       // 1: store only the 32-column groups that can hold one of the row's top-5 candidates
 };
 
 __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot, bool who) {
@@ -735,7 +736,11 @@ __device__ __forceinline__ void publish_attention(WorkerCtx& c) {
 
 // Vocabulary projection epilogue (bias-free fc, decoders.py:90,121): fp32 logits + per-32-column-chunk
 // (max, sum exp(x - max)) for beam_chunkmerge_kernel (beam.cu).
-__device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx) {
+// Sparse mode: the selection (beam_chunkmerge_kernel) reads back only the `beam` <= 5 groups of 32 columns with
+// the largest maxima of a row.  A thread (= row, one half of every chunk) keeps the five largest group maxima it
+// has seen; a group is stored only if its maximum reaches the fifth of them -- every group of the row's final
+// top five passes that test when it is produced, and ~85 % of the 52 MB of logits per step are never written.
+__device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx, float (&top)[5]) {
     const int b = acquire_acc(c, 2);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
@@ -763,14 +768,30 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
         }
         st[i] = make_float2(cm, cs);
         if (gcol < p.ld_logits) {
+            if (p.sparse_logits) {
+                const bool keep = cm >= top[4] && grow < p.R;
+                float x = cm;   // insert into the descending top five
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint4 o[4];
+                for (int k = 0; k < 5; ++k) {
+                    const float hi = fmaxf(top[k], x);
+                    x = fminf(top[k], x);
+                    top[k] = hi;
+                }
+                if (keep) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.logits + static_cast<size_t>(grow) * p.ld_logits + gcol);
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
-                uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
-                staged_store64<true>(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
+                    for (int g = 0; g < 8; ++g) __stcs(dst + g, make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint4 o[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
+                    uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
+                    staged_store64<true>(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
+                }
             }
         }
     }
@@ -1067,7 +1088,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                 if (ji == p.n_layers * 6) {
                     pdl_launch_dependents();
                     const int vchunks = p.vocab_tiles / 2;
-                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch);
+                    float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
                     break;
                 }
                 const int L = ji / 6, k = ji % 6;
@@ -1133,7 +1155,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         fstamp(p, tile, 2 + p.n_layers * 8, tr);
         pdl_launch_dependents();
         const int vchunks = p.vocab_tiles / 2;
-        for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch);
+        float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
         fstamp(p, tile, 3 + p.n_layers * 8, tr);
             }
     }
@@ -1154,6 +1177,7 @@ struct cap_fused_decoder {
     void* w2 = nullptr;
     int tiles = 0;
     bool has_att = false;
+    bool full_logits = false;   // debug / parity: every logit is stored (cap_fused_set_full_logits, OPENVIIC_FULL_LOGITS)
 };
 
 extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out) {
@@ -1232,6 +1256,7 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     }
     p.q_out = static_cast<bf16*>(d->q_out);
     f->has_att = d->att_in != nullptr;
+    f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
     if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
@@ -1239,6 +1264,14 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     *out = f;
     return CAP_OK;
 }
+
+extern "C" int cap_fused_set_full_logits(cap_fused_decoder* f, int on) {
+    CAP_REQUIRE(f != nullptr, "cap_fused_set_full_logits: null handle");
+    f->full_logits = on != 0;
+    return CAP_OK;
+}
+
+extern "C" int cap_fused_get_full_logits(cap_fused_decoder* f) { return f && f->full_logits ? 1 : 0; }
 
 extern "C" int cap_fused_destroy(cap_fused_decoder* f) {
     if (!f) return CAP_OK;
@@ -1285,6 +1318,7 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
     const int tiles = (R + TILE_ROWS - 1) / TILE_ROWS;
     CAP_REQUIRE(B > 0 && tiles <= f->tiles, "cap_fused_chain: batch %d exceeds the reservation", B);
     p.t = t; p.R = R; p.B = B; p.n_keys = 0;
+    p.sparse_logits = (f->full_logits || p.beam > 5) ? 0 : 1;
     p.trace = nullptr;
     p.dbg_skip = 0;
     p.start_embed = 0;

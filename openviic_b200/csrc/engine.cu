@@ -612,7 +612,13 @@ extern "C" int cap_engine_decode_logits(cap_engine* e, int t, cap_stream_t strea
     CAP_REQUIRE(t >= 0 && t < e->desc.max_len, "cap_engine_decode_logits: step %d outside [0,%d)", t, e->desc.max_len);
     bf16* x = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (e->fused) return run_fused_stack(e, t, s);  // the production stack: the fused kernel leaves the logits behind
+    if (e->fused) {  // the production stack; this debug entry point wants EVERY logit stored
+        const int was = cap_fused_get_full_logits(e->fused);
+        cap_fused_set_full_logits(e->fused, 1);
+        const int rc = run_fused_stack(e, t, s);
+        cap_fused_set_full_logits(e->fused, was);
+        return rc;
+    }
     CAP_PROPAGATE(run_decoder_stack(e, t, s, &x));
     // bias-free vocabulary projection (decoders.py:90,121); log-softmax happens in the beam row pass
     return run_linear(x, e->desc.d_model, e->vocab_fc, e->logits, e->ld_logits, CAP_F32, CAP_ACT_NONE,

@@ -20,14 +20,16 @@ TOL_FUSED = 6e-2   # max-abs logits, fused vs per-operator path: same bf16 opera
                    # summation order and a one-pass LayerNorm variance; measured ~1e-2
 
 
-def _engine(model, cfg, vocab, batch, n, beam, device, fused):
+def _engine(model, cfg, vocab, batch, n, beam, device, fused, full_logits=True):
     """fused: 0 / False = one kernel per operator, 1 / True = one kernel per step, 2 = GEMM chains + attention kernels."""
     os.environ["OPENVIIC_FUSED_DECODE"] = str(int(fused))
+    os.environ["OPENVIIC_FULL_LOGITS"] = "1" if full_logits else "0"   # the step-wise comparison reads whole rows
     try:
         eng = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device)
         eng.reserve(batch, n, beam)
     finally:
         os.environ.pop("OPENVIIC_FUSED_DECODE", None)
+        os.environ.pop("OPENVIIC_FULL_LOGITS", None)
     return eng
 
 
@@ -76,7 +78,7 @@ def test_fused_step_matches_per_operator_path(name, batch, mode, device):
 @pytest.mark.parametrize("mode", [2, 1])
 def test_fused_beam_search_against_oracle(mode, device):
     case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_grid", device)
-    eng = _engine(model, cfg, vocab, case["batch"], case["n"], case["beam"], device, mode)
+    eng = _engine(model, cfg, vocab, case["batch"], case["n"], case["beam"], device, mode, full_logits=False)
     eng.encode(feats.to(device), None)
     ids, lp = eng.beam_search(1, use_graph=False)
     ids2, lp2 = eng.beam_search(1, use_graph=True)   # first graph call captures, second replays
