@@ -252,14 +252,19 @@ __device__ __forceinline__ void publish_a(WorkerCtx& c) {
 enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
 
 // Epilogue of one 256-column chunk of a plain projection: + bias (ReLU for the hidden layer), bf16, to global.
+// `bias_reg` carries this thread's bias value of the chunk across calls: the value of chunk c + 1 is requested
+// while chunk c is drained, so the global-load latency is off the per-chunk critical path (n_chunks = chunks of
+// the job; the first chunk of a job loads its own value).
 template <int KIND>
 __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
-                                               bf16* dst_rowmajor, int ld_rowmajor) {
+                                               int n_chunks, float& bias_reg, bf16* dst_rowmajor, int ld_rowmajor) {
     // stage this chunk's 256 bias values (double-buffered by chunk parity; see the barrier note below)
     const bool tr = (KIND == EPI_HID && chunk_idx == 3 && c.ww == 0 && c.lane == 0);
     fstamp(p, c.tile, 40, tr);
     float* sb = c.s_cbias + (chunk_idx & 1) * 256;
-    sb[c.wtid] = __ldg(bias + chunk_idx * 256 + c.wtid);
+    if (chunk_idx == 0) bias_reg = __ldg(bias + c.wtid);
+    sb[c.wtid] = bias_reg;
+    if (chunk_idx + 1 < n_chunks) bias_reg = __ldg(bias + (chunk_idx + 1) * 256 + c.wtid);
     workers_sync();  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
     fstamp(p, c.tile, 41, tr);
     const int b = acquire_acc(c, 2);
@@ -1076,6 +1081,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.r0 = tile * TILE_ROWS;
         c.rows_valid_warp = max(0, min(32, p.R - (c.r0 + c.quad * 32)));
 
+        float bias_reg = 0.f;
         if constexpr (CHAIN) {
             pdl_wait();  // everything this chain reads was written by stream predecessors
             uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
@@ -1096,15 +1102,15 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                 const FusedLayerP& W = p.layer[L];
                 if (k == 0) {
                     bf16* cache_t = p.qkv_cache + (static_cast<size_t>(L) * p.T + p.t) * p.R * 3 * FD;
-                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, cache_t, 3 * FD);
+                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
                 } else if (k == 1) {
                     epilogue_layernorm<true>(c, p, W.b_o1, W.g1, W.be1, nullptr);
                 } else if (k == 2) {
-                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, p.q_out, FD);
+                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, 2, bias_reg, p.q_out, FD);
                 } else if (k == 3) {
                     epilogue_layernorm<true>(c, p, W.b_o2, W.g2, W.be2, nullptr);
                 } else if (k == 4) {
-                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, nullptr, 0);
+                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
                     fence_proxy_async();  // hidden tile (global, generic proxy) -> TMA reads (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready);
@@ -1129,7 +1135,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             bf16* cache_t = cache_l + static_cast<size_t>(p.t) * p.R * 3 * FD;
             const int sb = 2 + L * 8;
             fstamp(p, tile, sb, tr);
-            for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, cache_t, 3 * FD);
+            for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
             workers_sync();  // q|k|v of every row of the tile are in the cache
             fstamp(p, tile, sb + 1, tr);
             self_attention_phase(c, p, cache_l);
@@ -1137,7 +1143,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             fstamp(p, tile, sb + 2, tr);
             epilogue_layernorm<false>(c, p, W.b_o1, W.g1, W.be1, nullptr);
             fstamp(p, tile, sb + 3, tr);
-            for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_QG>(c, p, W.b_q, ch, nullptr, 0);
+            for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_QG>(c, p, W.b_q, ch, 2, bias_reg, nullptr, 0);
             workers_sync();
             fstamp(p, tile, sb + 4, tr);
             cross_attention_phase(c, p, p.cross_kv + static_cast<size_t>(L) * p.cross_layer_stride);
@@ -1145,7 +1151,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             fstamp(p, tile, sb + 5, tr);
             epilogue_layernorm<false>(c, p, W.b_o2, W.g2, W.be2, nullptr);
             fstamp(p, tile, sb + 6, tr);
-            for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, nullptr, 0);
+            for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
             fence_proxy_async();  // hidden tile (global, generic proxy) -> bulk-copy reads (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(h_ready);
