@@ -1183,6 +1183,7 @@ struct cap_fused_decoder {
     void* w2 = nullptr;
     int tiles = 0;
     bool has_att = false;
+    bool use_pairs = true;      // CTA pairs (OPENVIIC_CHAIN_PAIR=0 at creation: single CTAs)
     bool full_logits = false;   // debug / parity: every logit is stored (cap_fused_set_full_logits, OPENVIIC_FULL_LOGITS)
 };
 
@@ -1263,6 +1264,7 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     p.q_out = static_cast<bf16*>(d->q_out);
     f->has_att = d->att_in != nullptr;
     f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
+    f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
     if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
@@ -1340,8 +1342,7 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
     // would hold them idle in griddepcontrol.wait until the attention kernel before it has drained.
     // CTA pairs (OPENVIIC_CHAIN_PAIR=0: single CTAs): clusters of two adjacent tiles, the second CTA of the last
     // pair is a dummy when the tile count is odd (every access of it is guarded by the row count).
-    static const bool use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
-    if (use_pairs) {
+    if (f->use_pairs) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((tiles + 1) / 2 * 2);
         cfg.blockDim = dim3(FUSED_THREADS);

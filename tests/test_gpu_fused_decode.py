@@ -92,3 +92,43 @@ def test_fused_beam_search_against_oracle(mode, device):
     assert same.float().mean().item() >= 0.5
     d = (lp.cpu().view(ref_lp.shape) - ref_lp).abs()[same]
     assert d.numel() == 0 or d.max().item() < 9e-2
+
+
+@pytest.mark.parametrize("env", [{"OPENVIIC_CHAIN_PAIR": "0"}, {"OPENVIIC_FULL_LOGITS": "1"}, {}])
+def test_chain_variants_agree(env, device):
+    """Single-CTA chains vs CTA pairs, sparse vs full logits stores: identical captions and log-probs (the same
+    arithmetic in the same order; only the staging of weights and the set of stored logits differ)."""
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_region_A", device)
+
+    def run(extra):
+        old = {k: os.environ.get(k) for k in extra}
+        os.environ.update(extra)
+        try:
+            eng = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device)
+            eng.reserve(case["batch"], case["n"], case["beam"])
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        out = eng.caption_device(feats.to(device), None, out_size=case["beam"], use_graph=False)
+        torch.cuda.synchronize()
+        return out[0].clone(), out[1].clone()
+
+    # both switches are read when the engine is created
+    ids_ref, lp_ref = run({})
+    ids, lp = run(env)
+    assert torch.equal(ids, ids_ref)
+    assert torch.equal(lp, lp_ref)
+
+
+def test_device_and_host_entry_points_agree(device):
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_grid", device)
+    eng = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device)
+    eng.reserve(case["batch"], case["n"], case["beam"])
+    for use_graph in (False, True, True):
+        ids_d, lp_d = eng.caption_device(feats.to(device), None, out_size=1, use_graph=use_graph)
+        torch.cuda.synchronize()
+        ids_h, lp_h = eng.caption_host(feats.pin_memory(), None, out_size=1, use_graph=use_graph)
+        assert torch.equal(ids_d.cpu(), ids_h) and torch.equal(lp_d.cpu(), lp_h)
