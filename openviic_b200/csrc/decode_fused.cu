@@ -45,6 +45,13 @@ constexpr int TILE_ROWS = 128;
 constexpr int NW = 8;                // worker warps
 constexpr int FIRST_WORKER_WARP = 4;  // warps 0-3 form the control warpgroup (producer, MMA issuer, two idle)
 constexpr int FUSED_THREADS = (FIRST_WORKER_WARP + NW) * 32;
+// Worker warps of the chain kernels: 8 or 16 (the epilogues are written for both).  Measured: 16 warps (4 per
+// scheduler, 96 registers per thread) are no faster than 8 (84.3 k vs 83.6 k captions/s) -- the chains are paced by
+// the weight ring and the shared-memory traffic of the MMAs, not by epilogue instruction latency -- so 8 it is.
+constexpr int NW_CHAIN = 8;
+constexpr int CHAIN_THREADS = (FIRST_WORKER_WARP + NW_CHAIN) * 32;
+constexpr int CHAIN_MAXNREG = NW_CHAIN == 16 ? 96 : 128;
+constexpr int STAGE_PITCH_CHAIN = 48;  // 16-warp staging: 32 rows x 32 B (+16 B skew) per warp
 constexpr int NB = 4;                // weight ring stages
 constexpr uint32_t B_STAGE_BYTES = 128 * 64 * 2;   // one 128-row x 64-column weight tile
 constexpr uint32_t A_KB_BYTES = 128 * 64 * 2;      // one k-block of the A operand (8 granules)
@@ -58,12 +65,17 @@ constexpr int W512_ROWS_PER_LAYER = 3 * FD + FD + FD + FD + FDFF;  // qkv | o1 |
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_B = OFF_A + A_SLOTS * A_KB_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_B + NB * B_STAGE_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_STAGE + NW * 32 * STAGE_PITCH;
+constexpr uint32_t STAGE_BYTES_ALL = NW_CHAIN * 32 * STAGE_PITCH_CHAIN > NW * 32 * STAGE_PITCH ? NW_CHAIN * 32 * STAGE_PITCH_CHAIN
+                                                                                             : NW * 32 * STAGE_PITCH;
+constexpr uint32_t OFF_BIAS = OFF_STAGE + STAGE_BYTES_ALL;
 constexpr uint32_t OFF_CBIAS = OFF_BIAS + FD * 4;     // [2][256] chunk biases of the plain projections
 constexpr uint32_t OFF_GAMMA = OFF_CBIAS + FD * 4;
 constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
-constexpr uint32_t OFF_STAT = OFF_BETA + FD * 4;       // [2 (sum, sumsq)][2 halves][128 rows]
-constexpr uint32_t OFF_BARS = OFF_STAT + 4 * TILE_ROWS * 4;
+// LayerNorm row statistics [2 (sum, sumsq)][column groups <= 4][128 rows] alias the staging tiles: the LN epilogue
+// stages nothing, and a workers_sync separates it from the chunk epilogues on both sides
+constexpr uint32_t OFF_STAT = OFF_STAGE;
+static_assert(2 * 4 * TILE_ROWS * 4 <= STAGE_BYTES_ALL, "row statistics must fit the staging area");
+constexpr uint32_t OFF_BARS = OFF_BETA + FD * 4;
 constexpr int NB_PAIR = 8;            // CTA pairs stage HALF of every weight tile: the same 64 KB hold 8 k-block stages
 constexpr uint32_t B_STAGE_BYTES_PAIR = 64 * 64 * 2;
 constexpr int NUM_BARS = 2 * NB_PAIR + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1 + 1;
@@ -187,12 +199,45 @@ __device__ __forceinline__ uint32_t a_tile_off(int row, int chunk) {
            (static_cast<uint32_t>((chunk & 7) ^ (row & 7)) << 4);
 }
 
+// 16-warp layout: 32 bytes per lane and pass (every store instruction covers 16 rows x 32 contiguous bytes)
+template <bool STREAMING = false>
+__device__ __forceinline__ void staged_store32(uint8_t* stage, int lane, const uint4& v0, const uint4& v1, uint8_t* gbase,
+                                               size_t row_stride, int rows_valid) {
+    uint8_t* mine = stage + lane * STAGE_PITCH_CHAIN;
+    *reinterpret_cast<uint4*>(mine) = v0;
+    *reinterpret_cast<uint4*>(mine + 16) = v1;
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int idx = it * 32 + lane;
+        const int rr = idx >> 1, part = idx & 1;
+        const uint4 x = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH_CHAIN + part * 16);
+        if (rr < rows_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(rr) * row_stride + part * 16);
+            if (STREAMING) __stcs(dst, x); else *dst = x;
+        }
+    }
+    __syncwarp();
+}
+
+// 64 bytes per lane to global rows through the warp's staging tile, in the layout of the kernel's warp count
+template <bool STREAMING = false>
+__device__ __forceinline__ void staged_store(bool wide, uint8_t* stage, int lane, const uint4 (&v)[4], uint8_t* gbase,
+                                             size_t row_stride, int rows_valid) {
+    if (wide) {
+        staged_store64<STREAMING>(stage, lane, v, gbase, row_stride, rows_valid);
+    } else {
+        staged_store32<STREAMING>(stage, lane, v[0], v[1], gbase, row_stride, rows_valid);
+        staged_store32<STREAMING>(stage, lane, v[2], v[3], gbase + 32, row_stride, rows_valid);
+    }
+}
+
 __device__ __forceinline__ uint4 pack8_u4(const float* f) {
     bf16x8 p = pack8(f);
     return *reinterpret_cast<uint4*>(&p);
 }
 
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
+__device__ __forceinline__ void workers_sync(int nw) { asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory"); }
 
 struct WorkerCtx {
     uint8_t* A_buf;
@@ -205,6 +250,7 @@ struct WorkerCtx {
     uint32_t use0, use1;  // completed uses of TMEM buffer 0 / 1 (scalars: no dynamically indexed state)
     int toggle;
     int ww, quad, half, lane, wtid;
+    int nw, nsub;   // worker warps of this kernel (8 or 16) and column groups per TMEM quadrant (nw / 4); half = ww / 4 in [0, nsub)
     int tile, r0, rows_valid_warp;  // rows of this warp's TMEM quadrant that exist (0..32)
 };
 
@@ -262,17 +308,21 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
     const bool tr = (KIND == EPI_HID && chunk_idx == 3 && c.ww == 0 && c.lane == 0);
     fstamp(p, c.tile, 40, tr);
     float* sb = c.s_cbias + (chunk_idx & 1) * 256;
-    if (chunk_idx == 0) bias_reg = __ldg(bias + c.wtid);
-    sb[c.wtid] = bias_reg;
-    if (chunk_idx + 1 < n_chunks) bias_reg = __ldg(bias + (chunk_idx + 1) * 256 + c.wtid);
-    workers_sync();  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
+    if (c.wtid < 256) {
+        if (chunk_idx == 0) bias_reg = __ldg(bias + c.wtid);
+        sb[c.wtid] = bias_reg;
+        if (chunk_idx + 1 < n_chunks) bias_reg = __ldg(bias + (chunk_idx + 1) * 256 + c.wtid);
+    }
+    workers_sync(c.nw);  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
     fstamp(p, c.tile, 41, tr);
     const int b = acquire_acc(c, 2);
     fstamp(p, c.tile, 42, tr);
     const int row = c.quad * 32 + c.lane;
+    const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains (4 with 8 warps, 2 with 16)
+    const bool wide = c.nw == NW;
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int colc = c.half * 128 + i * 32;
+    for (int i = 0; i < groups; ++i) {
+        const int colc = (c.half * groups + i) * 32;
         uint32_t v[32];
         fstamp(p, c.tile, 48, tr && i == 1);
         tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
@@ -292,11 +342,11 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
         const int gcol = chunk_idx * 256 + colc;
         if (KIND == EPI_CACHE) {
             uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
-            staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
+            staged_store(wide, c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
         } else if (KIND == EPI_HID) {
             // row-major scratch [tiles * 128][2048] (whole tiles are allocated: no row guard), re-read by TMA
             uint8_t* gbase = reinterpret_cast<uint8_t*>(p.hbuf + static_cast<size_t>(c.r0 + c.quad * 32) * FDFF + gcol);
-            staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
+            staged_store(wide, c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
         } else {
             // granule layout [tile][granule][row][16 B]: 32 lanes write 512 contiguous bytes per granule
             uint4* base = reinterpret_cast<uint4*>(p.qg) + (static_cast<size_t>(c.tile) * (FD / 8) + gcol / 8) * TILE_ROWS + row;
@@ -319,12 +369,12 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
 template <bool PARK>
 __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedParams& p, const float* bias,
                                                    const float* gamma, const float* beta, const uint8_t* zero_rows) {
-    for (int i = c.wtid; i < FD; i += NW * 32) {
+    for (int i = c.wtid; i < FD; i += c.nw * 32) {
         c.s_bias[i] = __ldg(bias + i);
         c.s_gamma[i] = __ldg(gamma + i);
         c.s_beta[i] = __ldg(beta + i);
     }
-    workers_sync();
+    workers_sync(c.nw);
     acquire_acc(c, 4);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
@@ -333,16 +383,15 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
     if constexpr (PARK) {
-    float4 ra[8], rb[8];
-    auto load_res = [&](float4 (&r)[8], int i) {
-        const int c0 = c.half * 256 + i * 32;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) r[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
-    };
-    auto pass_a = [&](const float4 (&r)[8], int i) {
-        const int c0 = c.half * 256 + i * 32;
+    const int groups = 16 / c.nsub;   // 32-column groups of the 512-wide row this warp owns (8 or 4)
+#pragma unroll 1
+    for (int i = 0; i < groups; ++i) {
+        const int c0 = (c.half * groups + i) * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
+        float4 r[8];   // requested while the TMEM load is in flight
+#pragma unroll
+        for (int g = 0; g < 8; ++g) r[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -356,28 +405,23 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
             v[4 * g + 2] = __float_as_uint(y2); v[4 * g + 3] = __float_as_uint(y3);
         }
         tmem_st_32x32b_x32(taddr + c0, v);
-    };
-    load_res(ra, 0);
-#pragma unroll 1
-    for (int i = 0; i < 8; i += 2) {
-        load_res(rb, i + 1);
-        pass_a(ra, i);
-        if (i + 2 < 8) load_res(ra, i + 2);
-        pass_a(rb, i + 1);
     }
     tmem_st_wait();
     c.s_stat[c.half * TILE_ROWS + row] = s1;
-    c.s_stat[(2 + c.half) * TILE_ROWS + row] = s2;
-    asm volatile("bar.sync %0, 64;" ::"r"(2 + c.quad) : "memory");
-    const float S1 = c.s_stat[row] + c.s_stat[TILE_ROWS + row];
-    const float S2 = c.s_stat[2 * TILE_ROWS + row] + c.s_stat[3 * TILE_ROWS + row];
+    c.s_stat[(4 + c.half) * TILE_ROWS + row] = s2;
+    asm volatile("bar.sync %0, %1;" ::"r"(2 + c.quad), "r"(c.nsub * 32) : "memory");  // the quadrant's column groups
+    float S1 = 0.f, S2 = 0.f;
+    for (int k = 0; k < c.nsub; ++k) {
+        S1 += c.s_stat[k * TILE_ROWS + row];
+        S2 += c.s_stat[(4 + k) * TILE_ROWS + row];
+    }
     const float mean = S1 * (1.f / FD);
     const float var = fmaxf(S2 * (1.f / FD) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
     const bool zero = !live || (zero_rows != nullptr && zero_rows[grow] != 0);
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        const int c0 = c.half * 256 + i * 32;
+    for (int i = 0; i < groups; ++i) {
+        const int c0 = (c.half * groups + i) * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
@@ -464,8 +508,8 @@ __device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) 
         pv[4 * i] = t4.x; pv[4 * i + 1] = t4.y; pv[4 * i + 2] = t4.z; pv[4 * i + 3] = t4.w;
     }
     float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS;
-    constexpr int ROWS_PER_WARP = TILE_ROWS / NW;
-    // lane i fetches the token of the warp's row i; rows are then embedded four at a time (eight loads in flight)
+    const int ROWS_PER_WARP = TILE_ROWS / c.nw;
+    // lane i fetches the token of the warp's row i; rows are then embedded a few at a time (many loads in flight)
     int mytok = -1;
     if (c.lane < ROWS_PER_WARP) {
         const int grow = c.r0 + c.ww * ROWS_PER_WARP + c.lane;
@@ -474,7 +518,7 @@ __device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) 
             pad_t[grow] = (mytok == p.pad_idx) ? 1 : 0;
         }
     }
-    constexpr int EMB_ROWS = 8;   // rows embedded per round: 16 independent 16-byte loads in flight per lane
+    constexpr int EMB_ROWS = 4;   // rows embedded per round: 8 independent 16-byte loads in flight per lane
 #pragma unroll 1
     for (int i0 = 0; i0 < ROWS_PER_WARP; i0 += EMB_ROWS) {
         bf16x8 e[EMB_ROWS][2];
@@ -749,10 +793,11 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
     const int b = acquire_acc(c, 2);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
-    float2 st[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int colc = c.half * 128 + i * 32;
+    const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains
+    const bool wide = c.nw == NW;
+#pragma unroll 1
+    for (int i = 0; i < groups; ++i) {
+        const int colc = (c.half * groups + i) * 32;
         const int gcol = chunk_idx * 256 + colc;
         uint32_t v[32];
         tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
@@ -771,7 +816,9 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
 #pragma unroll
             for (int j = 0; j < 32; ++j) cs += j < valid ? __expf(__uint_as_float(v[j]) - cm) : 0.f;
         }
-        st[i] = make_float2(cm, cs);
+        if (grow < p.R)
+            *reinterpret_cast<float2*>(p.part_ms + (static_cast<size_t>(grow) * p.stat_chunks + chunk_idx * 8 + colc / 32) * 2) =
+                make_float2(cm, cs);
         if (gcol < p.ld_logits) {
             if (p.sparse_logits) {
                 const bool keep = cm >= top[4] && grow < p.R;
@@ -795,15 +842,10 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
                     for (int g = 0; g < 4; ++g)
                         o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
                     uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
-                    staged_store64<true>(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
+                    staged_store<true>(wide, c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
                 }
             }
         }
-    }
-    if (grow < p.R) {
-        float4* dst = reinterpret_cast<float4*>(p.part_ms + (static_cast<size_t>(grow) * p.stat_chunks + chunk_idx * 8 + c.half * 4) * 2);
-        dst[0] = make_float4(st[0].x, st[0].y, st[1].x, st[1].y);
-        dst[1] = make_float4(st[2].x, st[2].y, st[3].x, st[3].y);
     }
     release_acc(c, 2, b);
 }
@@ -818,8 +860,9 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
 // memories and both CTAs drain their own accumulator rows.  A ring byte then feeds 256 rows instead of 128: the
 // same 64 KB ring keeps 8 k-block stages in flight instead of 4 (the chains are bound by that ring's latency).
 template <bool CHAIN, bool PAIR = false>
-__global__ void __launch_bounds__(FUSED_THREADS, 1) __maxnreg__(CHAIN ? 128 : 168)
+__global__ void __launch_bounds__(CHAIN ? CHAIN_THREADS : FUSED_THREADS, 1) __maxnreg__(CHAIN ? CHAIN_MAXNREG : 168)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
+    constexpr int NWK = CHAIN ? NW_CHAIN : NW;   // worker warps of this instantiation
     static_assert(CHAIN || !PAIR, "CTA pairs exist for the chain kernels only");
     constexpr int NBX = PAIR ? NB_PAIR : NB;
     constexpr uint32_t BST = PAIR ? B_STAGE_BYTES_PAIR : B_STAGE_BYTES;
@@ -858,13 +901,13 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     }
     if (warp == 1) {
         if (lane == 0) {
-            constexpr int consumers = PAIR ? 2 * NW : NW;   // pair: the leader's barriers hear both CTAs' workers
+            constexpr int consumers = PAIR ? 2 * NWK : NWK;   // pair: the leader's barriers hear both CTAs' workers
             for (int s = 0; s < NBX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
             for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
             for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], consumers); }
             mbar_init(a_ready, consumers);
-            mbar_init(h_ready, NW);
-            mbar_init(ring_free, NW);
+            mbar_init(h_ready, NWK);
+            mbar_init(ring_free, NWK);
             mbar_init(a_load, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -879,7 +922,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     if (warp < FIRST_WORKER_WARP) {
     // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
     // the register limit of each region is unambiguous to ptxas)
-    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // epilogues only: no need
+    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // 128 x 40 + 512 x 104 regs
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");                    // to squeeze these warps
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
@@ -1052,7 +1095,8 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     }
     } else {
         // ------------------------------------------------------------------ workers
-        if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
+        if constexpr (CHAIN && NW_CHAIN == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
+        else if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         WorkerCtx c;
         c.A_buf = A_buf;
@@ -1061,7 +1105,9 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.half = c.ww >> 2;
         c.lane = lane;
         c.wtid = threadIdx.x - FIRST_WORKER_WARP * 32;
-        c.stage = smem + OFF_STAGE + c.ww * 32 * STAGE_PITCH;
+        c.nw = NWK;
+        c.nsub = NWK / 4;
+        c.stage = smem + OFF_STAGE + c.ww * 32 * (NWK == NW ? STAGE_PITCH : STAGE_PITCH_CHAIN);   // matches staged_store's `wide`
         c.s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
         c.s_cbias = reinterpret_cast<float*>(smem + OFF_CBIAS);
         c.s_gamma = reinterpret_cast<float*>(smem + OFF_GAMMA);
@@ -1087,7 +1133,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
             if (p.start_embed) {
                 embed_phase(c, p);
-                workers_sync();
+                workers_sync(c.nw);
                 publish_a(c);
             }
             for (int ji = job_lo; ji <= job_hi; ++ji) {
@@ -1115,7 +1161,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready);
                 } else {
-                    epilogue_layernorm<false>(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
+                    epilogue_layernorm<true>(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
                 }
             }
             pdl_launch_dependents();
@@ -1125,7 +1171,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         pdl_wait();  // tokens / ancestry come from the previous step's selection kernel
         fstamp(p, tile, 1, tr);
         embed_phase(c, p);
-        workers_sync();  // the residual tile was written warp-per-row, the epilogues read it thread-per-row
+        workers_sync(c.nw);  // the residual tile was written warp-per-row, the epilogues read it thread-per-row
         publish_a(c);
 
         uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
@@ -1136,7 +1182,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             const int sb = 2 + L * 8;
             fstamp(p, tile, sb, tr);
             for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
-            workers_sync();  // q|k|v of every row of the tile are in the cache
+            workers_sync(c.nw);  // q|k|v of every row of the tile are in the cache
             fstamp(p, tile, sb + 1, tr);
             self_attention_phase(c, p, cache_l);
             publish_attention(c);
@@ -1144,7 +1190,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
             epilogue_layernorm<false>(c, p, W.b_o1, W.g1, W.be1, nullptr);
             fstamp(p, tile, sb + 3, tr);
             for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_QG>(c, p, W.b_q, ch, 2, bias_reg, nullptr, 0);
-            workers_sync();
+            workers_sync(c.nw);
             fstamp(p, tile, sb + 4, tr);
             cross_attention_phase(c, p, p.cross_kv + static_cast<size_t>(L) * p.cross_layer_stride);
             publish_attention(c);
@@ -1345,7 +1391,7 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
     if (f->use_pairs) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((tiles + 1) / 2 * 2);
-        cfg.blockDim = dim3(FUSED_THREADS);
+        cfg.blockDim = dim3(CHAIN_THREADS);
         cfg.dynamicSmemBytes = FUSED_SMEM;
         cfg.stream = static_cast<cudaStream_t>(stream);
         cudaLaunchAttribute attr[1];
@@ -1357,7 +1403,7 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
     } else {
-        decode_step_fused_kernel<true><<<dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+        decode_step_fused_kernel<true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_step_fused_kernel<chain>");
