@@ -499,14 +499,14 @@ template <int BEAMS>
 __global__ void __launch_bounds__(XW_WARPS * 32)
 decode_cross_attention_wide_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
                                    const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
-                                   float scale) {
+                                   float scale, int n_images) {
     pdl_prologue();
     extern __shared__ __align__(16) float xw_smem[];
     float* s_acc = xw_smem;                                             // [WARPS][BEAMS][32][EPL]
     float* s_m = s_acc + XW_WARPS * BEAMS * 32 * XW_EPL;                // [WARPS][BEAMS][32]
     float* s_l = s_m + XW_WARPS * BEAMS * 32;                           // [WARPS][BEAMS][32]
-    const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = blockIdx.x; b < n_images; b += gridDim.x) {   // grid-stride over images (grid < images: fewer SMs touched)
     constexpr int hd = 32 * XW_EPL;
     const bf16* kvb = kv + static_cast<size_t>(b) * n * 2 * hd + lane * XW_EPL;
     const uint8_t* mrow = key_mask ? key_mask + static_cast<size_t>(b) * n : nullptr;
@@ -604,6 +604,8 @@ decode_cross_attention_wide_kernel(const bf16* __restrict__ q, int ldq, const bf
         bf16* orow = out + static_cast<size_t>(b * BEAMS + bb) * ldo + lane * XW_EPL;
         reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
         reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
+    }
+    __syncthreads();  // the merge buffers are reused by the next image
     }
 }
 
@@ -783,7 +785,10 @@ int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_done = true;
     }
-    CAP_LAUNCH((decode_cross_attention_wide_kernel<BEAMS>), B, XW_WARPS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n, scale);
+    static const int max_grid = getenv("OPENVIIC_CROSS_GRID") ? atoi(getenv("OPENVIIC_CROSS_GRID")) : 0;
+    const int grid = (max_grid > 0 && max_grid < B) ? max_grid : B;
+    CAP_LAUNCH((decode_cross_attention_wide_kernel<BEAMS>), grid, XW_WARPS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n,
+               scale, B);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_cross_attention_wide_kernel");
 }

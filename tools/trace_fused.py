@@ -1,5 +1,9 @@
-"""Phase timing of the fused decode step (cap_debug_fused_trace) at the bench workload."""
+"""Phase timing of the ONE-KERNEL-PER-STEP variant of the fused decode step (OPENVIIC_FUSED_DECODE=1,
+cap_debug_fused_trace) at the bench workload; the default chain mode is profiled with ncu (tools/one_batch.py)."""
+import os
 import sys
+
+os.environ["OPENVIIC_FUSED_DECODE"] = "1"
 from pathlib import Path
 
 import torch
