@@ -28,6 +28,8 @@ import threading
 import time
 from pathlib import Path
 
+RESULT_OUT = sys.stdout   # main() re-points it at the original stdout before diverting fd 1 to stderr
+
 import torch
 
 REPO = Path(__file__).resolve().parent
@@ -245,7 +247,7 @@ def run_reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -253,6 +255,12 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import torch.distributed as dist
     from openviic_b200 import cabi, parallel, synthetic
+
+    t_start = time.perf_counter()
+
+    def progress(what):   # stderr breadcrumbs: a multi-rank run that stalls shows where
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_start:6.1f}s] {what}", file=sys.stderr, flush=True)
 
     rank, world, local_rank = parallel.init_distributed()
     if not torch.cuda.is_available():
@@ -275,6 +283,7 @@ def run_gpu_arm(args):
         extra.reserve(batch, n, BEAM)
         engines.append(extra)
     streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
+    progress(f"{n_streams} engines ready (world {world})")
     needs_boxes = synthetic.needs_boxes(cfg.MODEL)
 
     # Rotating input sets: 4 x (B,n,2048) bf16 = 4 x 51 MB > 126 MB L2, so no step finds its input cached
@@ -305,11 +314,20 @@ def run_gpu_arm(args):
                 ev.record()
             streams[k].wait_event(ev)
         with torch.cuda.stream(streams[k]):
-            ids, logp = engines[k].caption_device(feats_dev[i % n_sets], boxes_dev[i % n_sets], 1, not args.no_graph,
-                                                  outs_dev[k])
-            if world > 1:
-                return parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world)
-            return ids, logp
+            return engines[k].caption_device(feats_dev[i % n_sets], boxes_dev[i % n_sets], 1, not args.no_graph,
+                                             outs_dev[k])
+
+    def final_gather():
+        """N > 1: the path's only collective -- ONE all-gather of caption ids / log-probs (the last batch of every
+        stream) on the timing stream, after every side stream has been joined.  It is deliberately not issued per
+        step from the 32 side streams: a NCCL kernel waits for its peers on the other GPUs, and with many streams
+        sharing the hardware work queues a per-stream collective can end up queued behind work that (on another
+        rank) waits for it -- the 8-GPU run of the per-step variant did not finish."""
+        if world == 1:
+            return None
+        ids = torch.stack([o[0].squeeze(1) for o in outs_dev]).reshape(-1, MAX_LEN)
+        logp = torch.stack([o[1].squeeze(1) for o in outs_dev]).reshape(-1, MAX_LEN)
+        return parallel.gather_captions(ids, logp, ids.shape[0] * world)
 
     def fork(stagger_ms: float = 0.0):
         pace_stream.wait_stream(torch.cuda.current_stream())
@@ -351,7 +369,9 @@ def run_gpu_arm(args):
             engines[k].beam_search(out_size=1, use_graph=False)
     for i in range(max(3, args.warmup) * n_streams):
         step(i)
+    progress("warm-up enqueued")
     barrier()
+    progress("warm-up done, timing")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     fork(args.stagger_ms)
@@ -360,6 +380,7 @@ def run_gpu_arm(args):
         out = step(i)
     host_enqueue_s = time.perf_counter() - host_t0
     join()
+    gathered = final_gather()
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - host_t0) * 1e3
@@ -375,32 +396,32 @@ def run_gpu_arm(args):
     outs_host = [(torch.empty((batch, 1, MAX_LEN), dtype=torch.int64).pin_memory(),
                   torch.empty((batch, 1, MAX_LEN), dtype=torch.float32).pin_memory()) for _ in range(n_streams)]
 
-    gathered_host = [(torch.empty((batch * world, MAX_LEN), dtype=torch.int64).pin_memory(),
-                      torch.empty((batch * world, MAX_LEN), dtype=torch.float32).pin_memory()) for _ in range(n_streams)]
+    gathered_host = (torch.empty((n_streams * batch * world, MAX_LEN), dtype=torch.int64).pin_memory(),
+                     torch.empty((n_streams * batch * world, MAX_LEN), dtype=torch.float32).pin_memory())
 
     def e2e_step(i):
+        # the C-ABI host entry point: H2D + path + D2H of this rank's captions, enqueued by one call
         k = i % n_streams
         with torch.cuda.stream(streams[k]):
-            if world == 1:   # the C-ABI host entry point: H2D + path + D2H enqueued by one call
-                engines[k].caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph,
-                                        outs_host[k], sync=False)
-                return
-            # N > 1: same copies, plus the all-gather of ids between the search and the D2H copy; nothing
-            # blocks the host, so the ranks' batches stay pipelined
-            f = feats_host[i % n_sets].to(device, non_blocking=True)
-            bx = boxes_host[i % n_sets].to(device, non_blocking=True) if needs_boxes else None
-            engines[k].encode(f, bx)
-            ids, logp = engines[k].beam_search(out_size=1, use_graph=not args.no_graph)
-            all_ids, all_lp = parallel.gather_captions(ids.squeeze(1), logp.squeeze(1), batch * world)
-            gathered_host[k][0].copy_(all_ids, non_blocking=True)
-            gathered_host[k][1].copy_(all_lp, non_blocking=True)
+            engines[k].caption_host(feats_host[i % n_sets], boxes_host[i % n_sets], 1, not args.no_graph, outs_host[k],
+                                    sync=False)
 
+    progress("device-resident loop done")
     for i in range(3 * n_streams):
         e2e_step(i)
     barrier()
+    progress("e2e warm-up done, timing")
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(i)
+    if world > 1:   # the final gather of the ranks' captions, from the host buffers the loop has just filled
+        torch.cuda.synchronize()
+        for k in range(n_streams):
+            outs_dev[k][0].copy_(outs_host[k][0], non_blocking=True)
+            outs_dev[k][1].copy_(outs_host[k][1], non_blocking=True)
+        all_ids, all_lp = final_gather()
+        gathered_host[0].copy_(all_ids, non_blocking=True)
+        gathered_host[1].copy_(all_lp, non_blocking=True)
     barrier()   # every stream drained: all ids / log-probs are in host memory
     e2e_elapsed = time.perf_counter() - t0
     clocks.__exit__(None, None, None)
@@ -411,6 +432,7 @@ def run_gpu_arm(args):
     h2d = feats_host[0].numel() * feats_host[0].element_size() + (boxes_host[0].numel() * 4 if needs_boxes else 0)
     d2h = batch * MAX_LEN * (8 + 4)
 
+    progress("e2e loop done")
     if rank != 0:
         return 0
 
@@ -466,12 +488,13 @@ def run_gpu_arm(args):
                    "pipelining": f"{n_streams} independent batches in flight on {n_streams} streams/engines", "weights": "synthetic seed 1234 (openviic_b200/synthetic.py)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_features": "bf16 pinned",
-                "api": "cap_engine_caption_host_async" if world == 1 else "pinned H2D + engine + NCCL all-gather + D2H"},
+                "api": "cap_engine_caption_host_async" if world == 1 else
+                "cap_engine_caption_host_async per rank + one final NCCL all-gather of the caption ids"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -493,6 +516,12 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=40)
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything a library writes to file descriptor 1 from here
+    # on (NCCL prints its version banner there on rank 0) goes to stderr instead
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
     try:

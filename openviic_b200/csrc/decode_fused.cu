@@ -1355,8 +1355,8 @@ extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_k
     p.trace = g_fused_trace;
     static const int dbg_skip = getenv("OPENVIIC_FUSED_DBG_SKIP") ? atoi(getenv("OPENVIIC_FUSED_DBG_SKIP")) : 0;
     p.dbg_skip = dbg_skip;
-    cap_launch_kernel(decode_step_fused_kernel<false>, dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM,
-                      static_cast<cudaStream_t>(stream), 1, p);
+    // plain launch (no programmatic dependent launch), for the reason given in cap_fused_chain below
+    decode_step_fused_kernel<false><<<dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_step_fused_kernel");
 }
