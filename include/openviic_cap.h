@@ -328,6 +328,31 @@ cap_beam* cap_engine_beam(cap_engine* e);
  * device_buffer[cta*8 + k]: 0 entry, 1 prologue done, 2 first TMA issued, 3 first stage landed,
  * 4 last MMA committed, 5 accumulator visible to the epilogue, 6 stores issued, 7 TMEM freed. */
 int cap_debug_gemm_trace(unsigned long long* device_buffer);
+/* ------------------------------------------------------------------------------------------------
+ * Host glue either side of the path.  Plain host code: no GPU, no stream.
+ * ------------------------------------------------------------------------------------------------ */
+/* Collate: image i contributes n_rows[i] rows of D floats at rows[i]; the batch is (B, n_max, D), short images
+ * zero-padded at the end -- InstanceList.__init__ / pad_values (reference utils/instance.py:32-55, 156-171)
+ * writing directly into the buffer the H2D copy reads (pinned for full speed).  The bf16 variant rounds to
+ * nearest even exactly as torch's .to(torch.bfloat16); `threads` host threads share the rows. */
+int cap_host_collate_bf16(const float* const* rows, const int32_t* n_rows, int B, int n_max, int D,
+                          uint16_t* out, int threads);
+int cap_host_collate_f32(const float* const* rows, const int32_t* n_rows, int B, int n_max, int D,
+                         float* out, int threads);
+/* Vocabulary for ids -> text: word i is words[offsets[i] .. offsets[i+1]) (UTF-8, n_words + 1 offsets);
+ * is_special[i] != 0 marks pad / bos / eos / unk (reference data_utils/vocab.py:41,66). */
+typedef struct cap_vocab cap_vocab;
+int cap_vocab_create(const char* words, const int64_t* offsets, int64_t n_words, const uint8_t* is_special,
+                     int64_t eos_idx, cap_vocab** out);
+int cap_vocab_destroy(cap_vocab* v);
+/* Vocab.decode_caption(ids, join_words=True) (reference data_utils/vocab.py:104-122): per caption the
+ * non-special words up to the first eos, joined by one space; captions are written back to back, each followed
+ * by '\n'.  collapse_repeats != 0 also drops a word equal to the word before it -- the itertools.groupby pass
+ * of the trainers (reference trainers/vi_trainer.py:251).  *out_bytes receives the bytes needed; if that exceeds
+ * out_capacity nothing is written and CAP_ERR_INVALID is returned.  An id outside [0, n_words) is an error
+ * (the reference raises IndexError). */
+int cap_vocab_decode(const cap_vocab* v, const int64_t* ids, int64_t n_captions, int T, int collapse_repeats,
+                     char* out, int64_t out_capacity, int64_t* out_bytes);
 /* Kernels launched by this library since load (all entry points); for bench.py's gpu_launches. */
 int64_t cap_launch_count(void);
 

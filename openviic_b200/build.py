@@ -28,16 +28,19 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]   # csrc/*.cpp: host-only code, compiled by g++
+
+
 def _sources():
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    for path in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "openviic_cap.h"]):
+    for path in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "openviic_cap.h"]):
         h.update(path.name.encode())
         h.update(path.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + HOST_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -60,9 +63,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in _sources():
         obj = obj_dir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
+        if src.suffix == ".cpp":
+            cuda_include = str(Path(nvcc).resolve().parent.parent / "include")
+            cmd = [shutil.which("g++") or "g++", *HOST_FLAGS, "-I", cuda_include, "-c", str(src), "-o", str(obj)]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, proc in procs:

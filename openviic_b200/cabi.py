@@ -96,6 +96,11 @@ SIGNATURES = {
     "cap_engine_caption_host_async": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "cap_engine_caption_device_async": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "cap_engine_debug_chains": (_i, [_vp, _i, _vp]),
+    "cap_host_collate_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "cap_host_collate_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "cap_vocab_create": (_i, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_vp)]),
+    "cap_vocab_destroy": (_i, [_vp]),
+    "cap_vocab_decode": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i64, C.POINTER(_i64)]),
     "cap_engine_encoder_output": (_vp, [_vp]),
     "cap_engine_encoder_mask": (_vp, [_vp]),
     "cap_engine_logits": (_vp, [_vp, C.POINTER(_i)]),
