@@ -474,7 +474,7 @@ def run_gpu_arm(args):
     roofline["step_frac_of_tensor_peak"] = roofline["step_algorithmic_tflops"] / peaks["tflops_sustained"]
 
     cpu_base = None
-    if not args.skip_cpu:
+    if not args.skip_cpu and world == 1:   # the CPU baseline is an N=1 figure (rank 0, host cores otherwise idle)
         cpu_base, _ = cpu_reference_run(args.workload, steps=args.cpu_steps, warmup=1, sample_batch=args.cpu_batch)
 
     line = {
