@@ -353,6 +353,26 @@ int cap_vocab_destroy(cap_vocab* v);
  * (the reference raises IndexError). */
 int cap_vocab_decode(const cap_vocab* v, const int64_t* ids, int64_t n_captions, int T, int collapse_repeats,
                      char* out, int64_t out_capacity, int64_t* out_bytes);
+/* CIDEr-D: the self-critical reward and the evaluation loop's CIDEr -- reference
+ * evaluation/cider/cider_scorer.py:9-167, evaluation/cider/cider.py:12-38, trainers/vi_trainer.py:137-145.  Captions are
+ * int32 word-id sequences in ragged form: caption j is tokens[caption_offsets[j] .. caption_offsets[j+1]).
+ *   cap_cider_set_corpus: image i owns captions [image_offsets[i], image_offsets[i+1]); counts in how many images each
+ *     n-gram occurs (Cider(gts), cider.py:22-26).  ref_len = log(number of images) and log_table[c] = log(c) come
+ *     from the caller so that they are the caller's (numpy's) logarithms; log_table may be NULL (libm's log).
+ *   cap_cider_score: hypothesis i is scored against reference captions [ref_group_offsets[i], ref_group_offsets[i+1])
+ *     (at least one); scores[i] is the reference's per-image CIDEr-D (x10).  Without a corpus the batch's reference
+ *     groups are the documents and batch_ref_len / log_table apply (Cider(), cider.py:19-21).  Doubles throughout. */
+typedef struct cap_cider cap_cider;
+int cap_cider_create(int n, double sigma, cap_cider** out);
+int cap_cider_destroy(cap_cider* c);
+int cap_cider_set_corpus(cap_cider* c, const int32_t* tokens, const int64_t* caption_offsets,
+                         const int64_t* image_offsets, int64_t n_images, double ref_len,
+                         const double* log_table, int64_t log_table_len);
+int64_t cap_cider_max_doc_freq(const cap_cider* c);
+int cap_cider_score(const cap_cider* c, const int32_t* hyp_tokens, const int64_t* hyp_offsets, int64_t n_hyp,
+                    const int32_t* ref_tokens, const int64_t* ref_caption_offsets,
+                    const int64_t* ref_group_offsets, double batch_ref_len, const double* log_table,
+                    int64_t log_table_len, double* scores, int threads);
 /* Kernels launched by this library since load (all entry points); for bench.py's gpu_launches. */
 int64_t cap_launch_count(void);
 

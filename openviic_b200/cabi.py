@@ -101,6 +101,11 @@ SIGNATURES = {
     "cap_vocab_create": (_i, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_vp)]),
     "cap_vocab_destroy": (_i, [_vp]),
     "cap_vocab_decode": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i64, C.POINTER(_i64)]),
+    "cap_cider_create": (_i, [_i, C.c_double, C.POINTER(_vp)]),
+    "cap_cider_destroy": (_i, [_vp]),
+    "cap_cider_set_corpus": (_i, [_vp, _vp, _vp, _vp, _i64, C.c_double, _vp, _i64]),
+    "cap_cider_max_doc_freq": (_i64, [_vp]),
+    "cap_cider_score": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_double, _vp, _i64, _vp, _i]),
     "cap_engine_encoder_output": (_vp, [_vp]),
     "cap_engine_encoder_mask": (_vp, [_vp]),
     "cap_engine_logits": (_vp, [_vp, C.POINTER(_i)]),

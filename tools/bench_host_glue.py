@@ -59,6 +59,35 @@ def reference_decode(vocab, ids):
     return out
 
 
+def cider_leg(rng, threads, repeat):
+    """The self-critical reward of one step: 64 images x beam 5 hypotheses, 5 references each, document frequencies
+    from a 10 000-image corpus.  The reference leg runs the reference's own evaluation/cider when /root/reference
+    (or $OPENVIIC_REFERENCE) exists -- build container only."""
+    from openviic_b200.evaluation import Cider
+    words = [f"w{i}" for i in range(3000)]
+    p = 1.0 / np.arange(1, len(words) + 1)
+    p /= p.sum()
+    corpus = {str(i): [" ".join(rng.choice(words, size=rng.integers(6, 18), p=p)) for _ in range(5)] for i in range(10000)}
+    images, beam = 64, 5
+    gts = {str(i): corpus[str(i // beam)] for i in range(images * beam)}
+    res = {str(i): [" ".join(rng.choice(words, size=rng.integers(6, 18), p=p))] for i in range(images * beam)}
+    ours = Cider(corpus, threads=threads)
+    got = ours.compute_score(gts, res)[1]
+    t_native = best_of(lambda: ours.compute_score(gts, res), repeat)
+    out = {"workload": "320 hypotheses x 5 references, 10 000-image corpus", "native_hypotheses_per_s": len(res) / t_native}
+    ref_root = Path(os.environ.get("OPENVIIC_REFERENCE", "/root/reference"))
+    if ref_root.exists():
+        sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle" / "ref_harness" / "shims"))
+        sys.path.insert(0, str(ref_root))
+        from evaluation.cider import Cider as RefCider
+        ref = RefCider(corpus)
+        want = ref.compute_score(gts, res)[1]
+        assert np.abs(want - got).max() <= 1e-12
+        t_ref = best_of(lambda: ref.compute_score(gts, res), 3)
+        out.update({"reference_hypotheses_per_s": len(res) / t_ref, "speedup": t_ref / t_native})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
@@ -90,6 +119,8 @@ def main():
     d_native = best_of(lambda: vocab.decode_predictions(ids), args.repeat * 5)
     d_ref = best_of(lambda: reference_decode(vocab, ids), args.repeat)
 
+    cider = cider_leg(rng, threads, args.repeat)
+
     in_bytes = int(sum(r.nbytes for r in rows))
     print(json.dumps({
         "workload": f"{args.batch} images x <= {args.rows} rows x {args.width} fp32 -> bf16 batch; {args.batch} x 20 ids -> text, V 10201",
@@ -98,6 +129,7 @@ def main():
                     "native_gb_per_s_read": in_bytes / t_native / 1e9, "speedup": t_ref / t_native},
         "decode": {"native_captions_per_s": args.batch / d_native, "reference_procedure_captions_per_s": args.batch / d_ref,
                    "speedup": d_ref / d_native},
+        "cider": cider,
     }))
 
 
