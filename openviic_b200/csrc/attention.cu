@@ -775,6 +775,164 @@ int launch_cross_smem(const bf16* q, int ldq, const bf16* kv, const uint8_t* key
     return cap_check_launch("decode_cross_attention_smem_kernel");
 }
 
+// Decode-step cross-attention on the warp-level tensor path (opt-in: OPENVIIC_CROSS_TC=1; H = 8): one CTA per image,
+// one warp per head.  The image's K|V rows are bulk-copied (one cp.async.bulk per 2 KB row, all in flight at once)
+// into shared memory rows of pitch 2 KB + 16 B, which makes both fragment access patterns conflict-free: K as the
+// col-major B operand of S = Q.K^T by 32-bit loads (lanes of a quad-group walk rows, pitch = 4 banks), V as the B
+// operand of O = P.V by ldmatrix.trans (8 rows x 16 B, pitch = one 16-byte bank group).  The image's beams are rows
+// 0..BEAMS-1 of the m16 tile (rows BEAMS..15 are zero: 11/16 of the MMA is padding, still ~7x fewer instructions than
+// the CUDA-core kernel above, whose per-key unpack / FMA / exp chain is issue-bound); keys past n read one shared
+// zero row.  S accumulators become the P operand in registers (bf16), softmax in fp32 in the log2 domain.
+constexpr int XT_PITCH = 2048 + 16;   // bytes per staged K|V row
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <int NT>   // 8-key tiles: 7 (n <= 56) or 13 (n <= 104)
+__global__ void __launch_bounds__(256)
+decode_cross_attention_tc_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
+                                 const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int beams, int n,
+                                 float scale) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) uint8_t xt_smem[];     // [n + 1][XT_PITCH] (last row zero), then NT*8 mask bytes
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    uint8_t* zero_row = xt_smem + static_cast<size_t>(n) * XT_PITCH;
+    uint8_t* smask = zero_row + XT_PITCH;
+    const uint32_t bar_addr = xs_smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(static_cast<uint32_t>(n) * 2048u)
+                     : "memory");
+    }
+    for (int i = threadIdx.x; i < XT_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zero_row)[i] = 0u;
+    for (int j = threadIdx.x; j < NT * 8; j += blockDim.x) smask[j] = (j >= n || (key_mask && key_mask[static_cast<size_t>(b) * n + j])) ? 1 : 0;
+    __syncthreads();   // barrier armed before any copy can complete on it; zero row and mask visible
+    if (threadIdx.x < n) {   // K|V were projected at encode time: safe to fetch before the PDL wait
+        uint64_t stream_policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + (static_cast<size_t>(b) * n + threadIdx.x) * 2048;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                xs_smem_u32(xt_smem + static_cast<size_t>(threadIdx.x) * XT_PITCH)),
+            "l"(reinterpret_cast<uint64_t>(src)), "r"(2048u), "r"(bar_addr), "l"(stream_policy)
+            : "memory");
+    }
+    pdl_wait();   // q comes from the previous kernel
+
+    const int h = warp;
+    // A operand: rows g < beams of the image's queries, head h; rows 8..15 of the tile are zero
+    uint32_t qa[4][4];
+    {
+        const bf16* qrow = q + static_cast<size_t>(b * beams + (g < beams ? g : 0)) * ldq + h * HEAD_DIM + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t lo = *reinterpret_cast<const uint32_t*>(qrow + ks * 16);
+            const uint32_t hi = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8);
+            qa[ks][0] = g < beams ? lo : 0u;
+            qa[ks][1] = 0u;
+            qa[ks][2] = g < beams ? hi : 0u;
+            qa[ks][3] = 0u;
+        }
+    }
+    {   // all rows landed (phase 0); bounded spin
+        uint32_t done = 0;
+        for (uint32_t spin = 0; !done; ++spin) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(bar_addr) : "memory");
+            if (spin > (1u << 26)) __trap();
+        }
+    }
+    // S = Q.K^T
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const int key = nt * 8 + g;
+        const uint8_t* krow = (key < n ? xt_smem + static_cast<size_t>(key) * XT_PITCH : zero_row) + h * (HEAD_DIM * 2) + 4 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(krow + ks * 32),
+                           *reinterpret_cast<const uint32_t*>(krow + ks * 32 + 16));
+    }
+    // softmax over the keys of row g (log2 domain); a quad holds one row
+    const float sc = scale * 1.4426950408889634f;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float x = smask[nt * 8 + 2 * t + e] ? -INFINITY : s[nt][e] * sc;
+            s[nt][e] = x;
+            mx = fmaxf(mx, x);
+        }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float p = (mx == -INFINITY) ? 0.f : exp2f(s[nt][e] - mx);
+            s[nt][e] = p;
+            sum += p;
+        }
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    // O = P.V : two 8-key score tiles are the A operand of one 16-key step; V fragments by ldmatrix.trans
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    const int mi = lane >> 3, mr = lane & 7;   // this lane addresses row mr of 8x8 matrix mi of an x4 load
+#pragma unroll
+    for (int kk = 0; kk < (NT + 1) / 2; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = 0u;
+        pa[2] = (2 * kk + 1 < NT) ? pack_bf16x2(s[2 * kk + 1 < NT ? 2 * kk + 1 : 0][0], s[2 * kk + 1 < NT ? 2 * kk + 1 : 0][1]) : 0u;
+        pa[3] = 0u;
+        const int key = kk * 16 + (mi & 1) * 8 + mr;
+        const uint8_t* vrow = (key < n ? xt_smem + static_cast<size_t>(key) * XT_PITCH : zero_row) + 1024 + h * (HEAD_DIM * 2) +
+                              (mi >> 1) * 16;
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {   // dims (2 dp) * 8 .. +15: matrices 0/1 = keys lo/hi of tile 2 dp, 2/3 of tile 2 dp + 1
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, xs_smem_u32(vrow + dp * 32));
+            mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
+            mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+        }
+    }
+    if (g < beams) {
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        bf16* orow = out + static_cast<size_t>(b * beams + g) * ldo + h * HEAD_DIM + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+            *reinterpret_cast<bf162*>(orow + dt * 8) = __floats2bfloat162_rn(o[dt][0] * inv, o[dt][1] * inv);
+    }
+}
+
+template <int NT>
+int launch_cross_tc(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int beams,
+                    int n, float scale, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(n + 1) * XT_PITCH + NT * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
+        attr_done = true;
+    }
+    CAP_LAUNCH((decode_cross_attention_tc_kernel<NT>), B, 256, smem, stream, q, ldq, kv, key_mask, out, ldo, beams, n, scale);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_cross_attention_tc_kernel");
+}
+
 template <int BEAMS>
 int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
                       float scale, cudaStream_t stream) {
@@ -858,6 +1016,12 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
         bf16* op = static_cast<bf16*>(out);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         static const bool no_bulk = getenv("OPENVIIC_CROSS_NO_BULK") != nullptr;
+        const char* tc_env = getenv("OPENVIIC_CROSS_TC");   // read per call: a probe compares both paths in one process
+        const bool tensor_path = tc_env && atoi(tc_env) != 0;
+        if (tensor_path && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
+            if (n <= 56) return launch_cross_tc<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
+            return launch_cross_tc<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
+        }
         if (!no_bulk && static_cast<size_t>(n) * 2048 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
             switch (beam) {  // bulk-staged variant: the image's K|V block lives in shared memory
                 case 1: return launch_cross_smem<1>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
