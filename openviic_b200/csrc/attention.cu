@@ -487,6 +487,131 @@ decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* _
     }
 }
 
+// Decode-step self-attention, split-key variant (opt-in: OPENVIIC_SELF_SPLIT=1; H = 8): SS_SPLITS warps share the
+// keys of one row, each warp has ALL of its keys' K and V vectors in flight at once (<= SS_KEYS keys per round, one
+// round for T <= SS_SPLITS * SS_KEYS = 20 steps) instead of walking the history four keys at a time, and softmax is
+// two-pass within a round (scores, max, then weights: no rescale of the accumulator per key).  The warp-per-row
+// kernel above is latency-bound: (t+1)/4 dependent rounds of HBM latency per launch.  The partial (max, sum,
+// accumulator) states of a row's warps are merged through shared memory, flash-decoding style.
+constexpr int SS_SPLITS = 4;
+constexpr int SS_KEYS = 5;
+constexpr int SS_ROWS = 2;                      // rows per CTA: SS_ROWS * SS_SPLITS warps
+constexpr int SS_EPL = 16;                      // elements per lane (H = 8: 4 lanes per head)
+
+__global__ void __launch_bounds__(SS_ROWS * SS_SPLITS * 32)
+decode_self_attention_split_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
+                                   const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
+                                   float scale) {
+    pdl_prologue();
+    __shared__ __align__(16) float part[SS_ROWS * SS_SPLITS * 32 * (SS_EPL + 2)];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = warp % SS_SPLITS;
+    const int r = blockIdx.x * SS_ROWS + warp / SS_SPLITS;
+    constexpr int hd = 32 * SS_EPL;
+    const size_t row_stride = static_cast<size_t>(3) * hd;
+    const size_t step_stride = static_cast<size_t>(R) * row_stride;
+    const int nkeys = t + 1;
+    const int per_split = (nkeys + SS_SPLITS - 1) / SS_SPLITS;
+    const int j_begin = split * per_split;
+    const int j_end = min(nkeys, j_begin + per_split);
+
+    float m = -INFINITY, l = 0.f, acc[SS_EPL];
+#pragma unroll
+    for (int i = 0; i < SS_EPL; ++i) acc[i] = 0.f;
+    if (r < R && j_begin < j_end) {
+        float q[SS_EPL];
+        {
+            const bf16x8* qp = reinterpret_cast<const bf16x8*>(qkv + t * step_stride + r * row_stride + lane * SS_EPL);
+            unpack8(qp[0], q);
+            unpack8(qp[1], q + 8);
+#pragma unroll
+            for (int i = 0; i < SS_EPL; ++i) q[i] *= scale * 1.4426950408889634f;   // scores in the log2 domain
+        }
+        for (int j0 = j_begin; j0 < j_end; j0 += SS_KEYS) {
+            uint4 kreg[SS_KEYS][2], vreg[SS_KEYS][2];
+            bool live[SS_KEYS];
+#pragma unroll
+            for (int u = 0; u < SS_KEYS; ++u) {   // every key of the round in flight before the first use
+                const int j = min(j0 + u, j_end - 1);
+                const int sl = (j == t) ? r : ancestry[static_cast<size_t>(j) * R + r];
+                live[u] = (j0 + u < j_end) && padflag[static_cast<size_t>(j) * R + sl] == 0;
+                const bf16* base = qkv + j * step_stride + sl * row_stride + lane * SS_EPL;
+                kreg[u][0] = __ldcs(reinterpret_cast<const uint4*>(base + hd));
+                kreg[u][1] = __ldcs(reinterpret_cast<const uint4*>(base + hd) + 1);
+                vreg[u][0] = __ldcs(reinterpret_cast<const uint4*>(base + 2 * hd));
+                vreg[u][1] = __ldcs(reinterpret_cast<const uint4*>(base + 2 * hd) + 1);
+            }
+            float sc[SS_KEYS], m_round = m;
+#pragma unroll
+            for (int u = 0; u < SS_KEYS; ++u) {
+                float kf[SS_EPL];
+                unpack8(*reinterpret_cast<const bf16x8*>(&kreg[u][0]), kf);
+                unpack8(*reinterpret_cast<const bf16x8*>(&kreg[u][1]), kf + 8);
+                float s0 = q[0] * kf[0], s1 = q[1] * kf[1], s2 = q[2] * kf[2], s3 = q[3] * kf[3];
+#pragma unroll
+                for (int i = 4; i < SS_EPL; i += 4) {
+                    s0 = fmaf(q[i], kf[i], s0);
+                    s1 = fmaf(q[i + 1], kf[i + 1], s1);
+                    s2 = fmaf(q[i + 2], kf[i + 2], s2);
+                    s3 = fmaf(q[i + 3], kf[i + 3], s3);
+                }
+                float x = (s0 + s1) + (s2 + s3);
+                x += __shfl_xor_sync(0xffffffffu, x, 2);
+                x += __shfl_xor_sync(0xffffffffu, x, 1);
+                sc[u] = live[u] ? x : -INFINITY;
+                m_round = fmaxf(m_round, sc[u]);
+            }
+            if (m_round == -INFINITY) continue;   // nothing live yet (warp-uniform per head group: every lane agrees on live[])
+            const float corr = exp2f(m - m_round);    // exp2(-inf) = 0 on the first live round
+            l *= corr;
+#pragma unroll
+            for (int i = 0; i < SS_EPL; ++i) acc[i] *= corr;
+#pragma unroll
+            for (int u = 0; u < SS_KEYS; ++u) {
+                const float p = exp2f(sc[u] - m_round);   // 0 for masked keys
+                l += p;
+                float vf[SS_EPL];
+                unpack8(*reinterpret_cast<const bf16x8*>(&vreg[u][0]), vf);
+                unpack8(*reinterpret_cast<const bf16x8*>(&vreg[u][1]), vf + 8);
+#pragma unroll
+                for (int i = 0; i < SS_EPL; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+            }
+            m = m_round;
+        }
+    }
+    float* mine = part + (static_cast<size_t>(warp) * 32 + lane) * (SS_EPL + 2);
+#pragma unroll
+    for (int i = 0; i < SS_EPL; ++i) mine[i] = acc[i];
+    mine[SS_EPL] = m;
+    mine[SS_EPL + 1] = l;
+    __syncthreads();
+    if (split == 0 && r < R) {
+        const float* row_part = part + (static_cast<size_t>(warp) * 32 + lane) * (SS_EPL + 2);   // this row's split 0
+        constexpr int SPLIT_STRIDE = 32 * (SS_EPL + 2);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < SS_SPLITS; ++c) mx = fmaxf(mx, row_part[c * SPLIT_STRIDE + SS_EPL]);
+        float lsum = 0.f, o[SS_EPL];
+#pragma unroll
+        for (int i = 0; i < SS_EPL; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < SS_SPLITS; ++c) {
+            const float* pc = row_part + c * SPLIT_STRIDE;
+            const float mc = pc[SS_EPL];
+            const float f = (mc == -INFINITY) ? 0.f : exp2f(mc - mx);
+            lsum = fmaf(pc[SS_EPL + 1], f, lsum);
+#pragma unroll
+            for (int i = 0; i < SS_EPL; ++i) o[i] = fmaf(pc[i], f, o[i]);
+        }
+        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+#pragma unroll
+        for (int i = 0; i < SS_EPL; ++i) o[i] *= inv;
+        bf16* orow = out + static_cast<size_t>(r) * ldo + lane * SS_EPL;
+        reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
+        reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
+    }
+}
+
 // Decode-step cross-attention, wide variant (H = 8): one CTA per image, its 4 warps split the image's
 // keys round-robin, every warp serves ALL `BEAMS` rows of the image and all heads at once (lane l owns
 // 16 consecutive elements of the 512-wide rows, 4 lanes per head), so each K/V row is read from HBM
@@ -1069,7 +1194,11 @@ extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestr
         return w < 1 ? 1 : (w > DEC_WARPS_MAX ? DEC_WARPS_MAX : w);
     }();
     const int wide_blocks = (R + self_warps - 1) / self_warps;
-    if (H == 8 && ldo % 8 == 0) {
+    const char* split_env = getenv("OPENVIIC_SELF_SPLIT");   // read per call: a probe compares both paths in one process
+    if (split_env && atoi(split_env) != 0 && H == 8 && ldo % 8 == 0) {
+        CAP_LAUNCH((decode_self_attention_split_kernel), (R + SS_ROWS - 1) / SS_ROWS, SS_ROWS * SS_SPLITS * 32, 0, s, cache,
+                   ancestry, padflag, o, ldo, t, R, scale);
+    } else if (H == 8 && ldo % 8 == 0) {
         CAP_LAUNCH((decode_self_attention_wide_kernel<16>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
     } else if (H == 4 && ldo % 8 == 0) {
         CAP_LAUNCH((decode_self_attention_wide_kernel<8>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);

@@ -1,8 +1,9 @@
-"""GPU probe (not collected by pytest): the opt-in tensor-core decode cross-attention (OPENVIIC_CROSS_TC=1,
-decode_cross_attention_tc_kernel) against the default kernel and a torch fp32 reference -- numerics at several
-shapes, launch time at the bench shape, and captions / throughput of a whole beam search with the switch on.
+"""GPU probe (not collected by pytest): the two opt-in decode attention kernels against the default ones --
+the tensor-core cross-attention (OPENVIIC_CROSS_TC=1, decode_cross_attention_tc_kernel) and the split-key
+self-attention (OPENVIIC_SELF_SPLIT=1, decode_self_attention_split_kernel): numerics at several shapes, launch time
+at the bench shape, and captions / latency of a whole beam search with each switch on.
 
-    python tests/gpu_scripts/probe_cross_tc.py
+    python tests/gpu_scripts/probe_attention_variants.py
 """
 import ctypes as C
 import os
@@ -69,17 +70,20 @@ def main():
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (25 * len(sets))
         print(f"tensor_path={tensor_path}: {us:.2f} us per launch back to back, {B * n * 2048 / us / 1e3:.0f} GB/s of K|V")
-    # whole path: captions with the switch on vs off (eager: the switch is read per launch; graphs bake it in)
+    self_attention_part(dev, g)
+    # whole path: captions with the switches on vs off (both are read per launch; CUDA graphs bake them in at capture)
     cfg, vocab, model, _ = bench.build_model("standard_grid", dev)
     feats = synthetic.synth_features(256, 49, 2048, 1, False).to(torch.bfloat16).to(dev)
     outs = {}
-    for tensor_path in (False, True):
-        os.environ["OPENVIIC_CROSS_TC"] = "1" if tensor_path else "0"
+    for name, env in [("default", {}), ("cross_tc", {"OPENVIIC_CROSS_TC": "1"}), ("self_split", {"OPENVIIC_SELF_SPLIT": "1"}),
+                      ("both", {"OPENVIIC_CROSS_TC": "1", "OPENVIIC_SELF_SPLIT": "1"})]:
+        os.environ["OPENVIIC_CROSS_TC"] = env.get("OPENVIIC_CROSS_TC", "0")
+        os.environ["OPENVIIC_SELF_SPLIT"] = env.get("OPENVIIC_SELF_SPLIT", "0")
         eng = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), dev)
         eng.reserve(256, 49, 5)
         ids, lp = eng.caption_device(feats, None, 1, use_graph=False)
         torch.cuda.synchronize()
-        outs[tensor_path] = (ids.clone(), lp.clone())
+        outs[name] = (ids.clone(), lp.clone())
         eng.caption_device(feats, None, 1, use_graph=True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -88,12 +92,49 @@ def main():
             eng.caption_device(feats, None, 1, use_graph=True)
         e1.record()
         torch.cuda.synchronize()
-        print(f"tensor_path={tensor_path}: one batch alone {e0.elapsed_time(e1) / 10:.3f} ms (graph)")
+        same = (outs["default"][0] == ids).all(-1)
+        print(f"{name}: one batch alone {e0.elapsed_time(e1) / 10:.3f} ms (graph); captions identical to default "
+              f"{same.float().mean().item():.2%}, max log-prob diff on those "
+              f"{(outs['default'][1] - lp).abs()[same].max().item():.4f}")
         eng.close()
-    same = (outs[False][0] == outs[True][0]).all(-1).float().mean().item()
-    print(f"captions identical with / without the tensor path: {same:.2%}; "
-          f"max log-prob diff on identical captions "
-          f"{(outs[False][1] - outs[True][1]).abs()[(outs[False][0] == outs[True][0]).all(-1)].max().item():.4f}")
+    os.environ["OPENVIIC_CROSS_TC"] = os.environ["OPENVIIC_SELF_SPLIT"] = "0"
+
+
+def self_attention_part(dev, g):
+    H, hd, T = 8, 512, 20
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for B, beam in [(7, 5), (256, 5)]:
+        R = B * beam
+        qkv = torch.randn(T, R, 3 * hd, generator=g).to(torch.bfloat16).to(dev)
+        anc = torch.empty(T, R, dtype=torch.int32)
+        for tt in range(T):
+            anc[tt] = (torch.arange(R) // beam) * beam + torch.randint(0, beam, (R,), generator=g)
+        pad = torch.rand(T, R, generator=g) < 0.2
+        pad[0] = False
+        anc_d, pad_d = anc.to(dev), pad.to(torch.uint8).to(dev)
+        for t in (0, 1, 4, 9, 19):
+            outs = []
+            for split in ("0", "1"):
+                os.environ["OPENVIIC_SELF_SPLIT"] = split
+                out = torch.empty(R, hd, dtype=torch.bfloat16, device=dev)
+                cabi.call("cap_decode_self_attention", qkv.data_ptr(), anc_d.data_ptr(), pad_d.data_ptr(), out.data_ptr(),
+                          hd, t, R, H, 0.125, stream)
+                torch.cuda.synchronize()
+                outs.append(out.float())
+            line = f"self-attention B={B} t={t}: split vs default max-abs diff {(outs[0] - outs[1]).abs().max().item():.4f}"
+            if B == 256:   # launch time, back to back (the 157 MB cache of one engine does not stay in L2 with 32 engines; here it may)
+                for split in ("0", "1"):
+                    os.environ["OPENVIIC_SELF_SPLIT"] = split
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(50):
+                        cabi.call("cap_decode_self_attention", qkv.data_ptr(), anc_d.data_ptr(), pad_d.data_ptr(),
+                                  out.data_ptr(), hd, t, R, H, 0.125, stream)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    line += f"; split={split} {e0.elapsed_time(e1) * 1e3 / 50:.2f} us"
+            print(line)
+    os.environ["OPENVIIC_SELF_SPLIT"] = "0"
 
 
 if __name__ == "__main__":
