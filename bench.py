@@ -207,6 +207,48 @@ def time_decode_chains(eng, cfg, batch, device):
     return 2.0 * batch * BEAM * macs_per_row, sec_per_step, 1 + 2 * layers
 
 
+def time_decode_chains_saturated(engines, streams):
+    """The same chain launches with the whole GPU busy: every engine's 20 steps of chains replayed concurrently on its
+    own stream (one batch alone keeps 10 of 148 SMs busy).  Returns the effective seconds per (engine, step), i.e.
+    elapsed / (engines x steps), or None if anything about the extra measurement fails (it must not take the bench
+    line down with it)."""
+    import ctypes as C
+    from openviic_b200 import cabi
+    try:
+        graphs = []
+        for eng, st in zip(engines, streams):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(st):
+                cabi.call("cap_engine_debug_chains", eng._h, 0, C.c_void_p(st.cuda_stream))
+            torch.cuda.synchronize()
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(graph, stream=st):
+                    for t in range(MAX_LEN):
+                        cabi.call("cap_engine_debug_chains", eng._h, t, C.c_void_p(st.cuda_stream))
+            graphs.append(graph)
+        reps = 3
+        elapsed = None
+        for timed in (False, True):   # one untimed round first
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for st in streams:
+                st.wait_stream(torch.cuda.current_stream())
+            for _ in range(reps if timed else 1):
+                for graph, st in zip(graphs, streams):
+                    with torch.cuda.stream(st):
+                        graph.replay()
+            for st in streams:
+                torch.cuda.current_stream().wait_stream(st)
+            e1.record()
+            torch.cuda.synchronize()
+            elapsed = e0.elapsed_time(e1) / 1e3
+        return elapsed / (reps * MAX_LEN * len(engines))
+    except Exception as err:   # noqa: BLE001 -- an optional extra figure
+        print(f"[bench] saturated chain timing skipped: {err}", file=sys.stderr)
+        return None
+
+
 # ------------------------------------------------------------------------------------ CPU reference
 def cpu_reference_run(workload: str, steps: int, warmup: int, sample_batch: int = 8):
     """The reference's algorithm (oracle port, fp32, as written) on this box's host cores."""
@@ -459,6 +501,13 @@ def run_gpu_arm(args):
                               "GPU (10 row tiles = 10 of 148 SMs busy): the fraction is per-launch latency-bound by "
                               "design; throughput comes from ~15 batches in flight (step_frac_of_tensor_peak)",
                     "share_of_step": MAX_LEN * chain_s / (total_ms / 1e3 / args.steps)}
+        sat_s = time_decode_chains_saturated(engines, streams) if n_streams > 1 else None
+        if sat_s:   # the kernel with all SMs busy: what the throughput figure is made of
+            roofline["achieved_saturated"] = flops / sat_s / 1e12
+            roofline["frac_saturated"] = roofline["achieved_saturated"] / peaks["tflops_sustained"]
+            roofline["saturated_timing"] = (f"CUDA events around the same chain launches of {n_streams} batches replayed "
+                                            f"concurrently on {n_streams} streams; flops of one batch-step / (elapsed / "
+                                            f"({n_streams} x {MAX_LEN} steps))")
     else:
         flops, gemm_s = time_gemm_family(cfg, n, batch, levels, device)
         achieved = flops / gemm_s / 1e12
