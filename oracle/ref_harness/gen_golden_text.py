@@ -9,6 +9,8 @@ section 8f row 2 -- the code either side of the caption path:
   * the evaluation loop's duplicate collapse, ``' '.join(k for k, g in itertools.groupby(words))``
     (reference trainers/vi_trainer.py:251) -- re-stated here in one line because it is inlined in the trainer
   * ``InstanceList`` collate of ragged per-image features (reference utils/instance.py:32-55,156-171)
+  * ``FeatureDataset`` / ``DictionaryDataset`` over an annotation JSON + per-image ``.npy`` feature dicts
+    (reference data_utils/dataset.py:12-132), and a collated ``DictionaryDataset`` batch
 
 Everything recorded is an OUTPUT OF THE REFERENCE; the inputs (annotation files, id matrices, feature rows) are
 stored next to it so that the tests rebuild them without the reference.
@@ -35,6 +37,7 @@ sys.path.insert(0, str(HERE / "shims"))
 sys.path.insert(0, str(REFERENCE))
 
 import builders  # noqa: E402,F401  (must come first: data_utils.vocab <-> trainers import each other)
+from data_utils.dataset import DictionaryDataset as RefDictionaryDataset, FeatureDataset as RefFeatureDataset  # noqa: E402
 from data_utils.utils import collate_fn as ref_collate_fn, preprocess_caption as ref_preprocess  # noqa: E402
 from data_utils.vocab import Vocab as RefVocab  # noqa: E402
 from utils.instance import Instance as RefInstance  # noqa: E402
@@ -132,6 +135,43 @@ def main() -> None:
     arrays["collate_boxes_out"] = batch.region_boxes.numpy()
     golden["collate_filenames"] = list(batch.filename)
     golden["collate_batch_size"] = int(batch.batch_size)
+
+    # datasets: 4 images (ids not in order, one without captions last), 7 annotations, per-image .npy feature dicts
+    feat_dir = tmp / "features"
+    feat_dir.mkdir()
+    image_ids = [17, 3, 42, 8]
+    rows_per_image = [6, 9, 4, 9]
+    images = [{"id": i, "file_name": f"{i:06d}.jpg"} for i in image_ids]
+    ann_images = [17, 3, 17, 42, 3, 17, 42]
+    annotations = [{"image_id": i, "caption": TRAIN[k]} for k, i in enumerate(ann_images)]
+    ds_json = str(tmp / "dataset.json")
+    with open(ds_json, "w", encoding="utf-8") as fh:
+        json.dump({"images": images, "annotations": annotations}, fh, ensure_ascii=False)
+    ds_feats, ds_boxes = {}, {}
+    for i, n in zip(image_ids, rows_per_image):
+        ds_feats[i] = rng.standard_normal((n, 16)).astype(np.float32)
+        ds_boxes[i] = rng.random((n, 4)).astype(np.float32)
+        np.save(feat_dir / f"{i}.npy", {"region_features": ds_feats[i], "region_boxes": ds_boxes[i]}, allow_pickle=True)
+    ds_cfg = CfgNode({"FEATURE_PATH": {"FEATURES": str(feat_dir)}})
+    fds = RefFeatureDataset(ds_json, vocab, ds_cfg)          # `vocab`: the MIN_FREQ 2 vocabulary built above
+    samples = [fds[i] for i in range(len(fds))]
+    dds = RefDictionaryDataset(ds_json, vocab, ds_cfg)
+    dict_batch = ref_collate_fn([dds[i] for i in range(len(dds))])
+    golden["dataset"] = {
+        "images": images, "annotations": annotations, "rows_per_image": rows_per_image,
+        "feature_len": len(fds), "feature_captions": fds.captions, "feature_fields": [list(s.keys()) for s in samples],
+        "dictionary_len": len(dds), "dictionary_image_ids": list(dds.image_ids), "dictionary_filenames": list(dds.filenames),
+        "dictionary_captions": dds.captions_with_image,
+        "batch_fields": list(dict_batch.keys()), "batch_filename": list(dict_batch.filename),
+        "batch_captions": list(dict_batch.captions), "batch_size": int(dict_batch.batch_size),
+    }
+    arrays["dataset_feats_in"] = np.concatenate([ds_feats[i] for i in image_ids], 0)
+    arrays["dataset_boxes_in"] = np.concatenate([ds_boxes[i] for i in image_ids], 0)
+    arrays["dataset_caption_tokens"] = torch.stack([s.caption_tokens for s in samples]).numpy()
+    arrays["dataset_shifted_tokens"] = torch.stack([s.shifted_right_caption_tokens for s in samples]).numpy()
+    arrays["dataset_sample_rows"] = np.array([s.region_features.shape[0] for s in samples])
+    arrays["dataset_batch_feats"] = dict_batch.region_features.numpy()
+    arrays["dataset_batch_boxes"] = dict_batch.region_boxes.numpy()
 
     out_dir = REPO / "tests" / "golden"
     with open(out_dir / "text_glue.json", "w", encoding="utf-8") as fh:

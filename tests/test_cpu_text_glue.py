@@ -173,3 +173,57 @@ def test_bf16_rounding_is_torchs(width, cap_lib):
     nan = torch.isnan(want)
     assert torch.equal(got_bits[~nan], want_bits[~nan])
     assert torch.isnan(out[0][nan]).all()
+
+
+def _dataset_fixture(golden, tmp_path):
+    """The annotation JSON and the per-image .npy feature dicts the golden generator fed to the reference."""
+    g, arrays = golden
+    d = g["dataset"]
+    feat_dir = tmp_path / "features"
+    feat_dir.mkdir()
+    bounds = np.cumsum([0] + d["rows_per_image"])
+    for k, image in enumerate(d["images"]):
+        np.save(feat_dir / f"{image['id']}.npy",
+                {"region_features": arrays["dataset_feats_in"][bounds[k]:bounds[k + 1]],
+                 "region_boxes": arrays["dataset_boxes_in"][bounds[k]:bounds[k + 1]]}, allow_pickle=True)
+    json_path = tmp_path / "dataset.json"
+    with open(json_path, "w", encoding="utf-8") as fh:
+        json.dump({"images": d["images"], "annotations": d["annotations"]}, fh, ensure_ascii=False)
+    vocab = Vocab(_vocab_config(tmp_path, g["annotations"], 2))     # the generator used the MIN_FREQ 2 vocabulary
+    return d, arrays, str(json_path), vocab, CfgNode({"FEATURE_PATH": {"FEATURES": str(feat_dir)}})
+
+
+def test_feature_dataset_matches_reference(golden, tmp_path):
+    from openviic_b200.data_utils import FeatureDataset
+    d, arrays, json_path, vocab, cfg = _dataset_fixture(golden, tmp_path)
+    ds = FeatureDataset(json_path, vocab, cfg)
+    assert len(ds) == d["feature_len"]
+    assert ds.captions == d["feature_captions"]
+    samples = [ds[i] for i in range(len(ds))]
+    assert [list(s.keys()) for s in samples] == d["feature_fields"]
+    assert np.array_equal(torch.stack([s.caption_tokens for s in samples]).numpy(), arrays["dataset_caption_tokens"])
+    assert np.array_equal(torch.stack([s.shifted_right_caption_tokens for s in samples]).numpy(),
+                          arrays["dataset_shifted_tokens"])
+    assert [s.region_features.shape[0] for s in samples] == arrays["dataset_sample_rows"].tolist()
+    assert not (torch.stack([s.caption_tokens for s in samples]) == vocab.eos_idx).any()
+
+
+def test_dictionary_dataset_and_its_batches_match_reference(golden, tmp_path, cap_lib):
+    from openviic_b200.data_utils import DictionaryDataset
+    d, arrays, json_path, vocab, cfg = _dataset_fixture(golden, tmp_path)
+    ds = DictionaryDataset(json_path, vocab, cfg)
+    assert len(ds) == d["dictionary_len"]
+    assert list(ds.image_ids) == d["dictionary_image_ids"]
+    assert list(ds.filenames) == d["dictionary_filenames"]
+    assert ds.captions_with_image == d["dictionary_captions"]
+    samples = [ds[i] for i in range(len(ds))]
+    batch = collate_fn(samples)                                      # the reference's batch
+    assert list(batch.keys()) == d["batch_fields"] and batch.batch_size == d["batch_size"]
+    assert list(batch.filename) == d["batch_filename"] and list(batch.captions) == d["batch_captions"]
+    assert np.array_equal(batch.region_features.numpy(), arrays["dataset_batch_feats"])
+    assert np.array_equal(batch.region_boxes.numpy(), arrays["dataset_batch_boxes"])
+    # the fast path: the same samples through the native collate (bf16 features, fp32 boxes, pinned when a GPU is present)
+    batcher = FeatureBatcher(max_batch=8, max_rows=16, width=16, box_width=4)
+    feats, boxes = batcher.collate([s.region_features for s in samples], [s.region_boxes for s in samples])
+    assert torch.equal(feats, torch.from_numpy(arrays["dataset_batch_feats"]).to(torch.bfloat16))
+    assert torch.equal(boxes, torch.from_numpy(arrays["dataset_batch_boxes"]))
