@@ -67,3 +67,52 @@ class CaptionPredictor:
     def last_log_probs(self, batch: int) -> torch.Tensor:
         """(batch, T) per-token log-probs of the last collected batch's captions."""
         return self._logp[:batch, 0].clone()
+
+
+def _batches(dataset, batch_size: int):
+    for start in range(0, len(dataset), batch_size):
+        yield [dataset[i] for i in range(start, min(start + batch_size, len(dataset)))]
+
+
+def get_predictions(predictor, dataset, batch_size: int, get_scores: bool = True) -> dict:
+    """The test-set loop of the reference (trainers/vi_trainer.py:229-276) over a ``DictionaryDataset``: per batch
+    ``{"image_id", "filename", "gens", "gts"}`` with keys ``"<batch>_<index>"``, plus the corpus scores.
+
+    Feature loading of batch k+1 runs while batch k is on the GPU (``submit`` returns at once).  Differences, on
+    purpose: ``image_id`` holds the dataset's ids (the reference's ``items.image_id`` is always ``None`` because its
+    samples carry no such field), and of the reference's four metrics only CIDEr is computed (the others shell out to
+    Java tools).  ``predictor`` needs ``submit(features, boxes)`` / ``collect()`` (``CaptionPredictor``)."""
+    from .evaluation import Cider
+    results, overall_gens, overall_gts = [], {}, {}
+    pending = None
+
+    def finish(entry):
+        it, samples, ids = entry
+        texts = predictor.collect()
+        gens = {"%d_%d" % (it, i): text for i, text in enumerate(texts)}
+        gts = {"%d_%d" % (it, i): s.captions for i, s in enumerate(samples)}
+        overall_gens.update({k: [v] for k, v in gens.items()})
+        overall_gts.update(gts)
+        results.append({"image_id": ids, "filename": [s.filename for s in samples], "gens": gens, "gts": gts})
+
+    for it, samples in enumerate(_batches(dataset, batch_size)):      # loading batch `it` overlaps batch `it - 1`
+        field = "region_features" if "region_features" in samples[0] else "grid_features"
+        feats = [s[field] for s in samples]
+        boxes = [s["region_boxes"] for s in samples] if "region_boxes" in samples[0] else None
+        if pending is not None:
+            finish(pending)
+        predictor.submit(feats, boxes)
+        start = it * batch_size
+        pending = (it, samples, list(dataset.image_ids[start:start + len(samples)]))
+    if pending is not None:
+        finish(pending)
+    scores = {}
+    if get_scores and overall_gts:
+        scores["CIDEr"] = float(Cider().compute_score(overall_gts, overall_gens)[0])
+    return {"results": results, **scores}
+
+
+def evaluate_metrics(predictor, dataset, batch_size: int) -> dict:
+    """The validation loop of the reference (trainers/vi_trainer.py:78-98): corpus scores only."""
+    out = get_predictions(predictor, dataset, batch_size, get_scores=True)
+    return {k: v for k, v in out.items() if k != "results"}

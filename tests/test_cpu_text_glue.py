@@ -227,3 +227,54 @@ def test_dictionary_dataset_and_its_batches_match_reference(golden, tmp_path, ca
     feats, boxes = batcher.collate([s.region_features for s in samples], [s.region_boxes for s in samples])
     assert torch.equal(feats, torch.from_numpy(arrays["dataset_batch_feats"]).to(torch.bfloat16))
     assert torch.equal(boxes, torch.from_numpy(arrays["dataset_batch_boxes"]))
+
+
+def test_get_predictions_loop_with_a_scripted_predictor(golden, tmp_path, cap_lib):
+    """The evaluation loop's bookkeeping (keys, grouping, overlap protocol, CIDEr over the whole set) with a scripted
+    stand-in for the GPU predictor; the GPU leg is tests/test_gpu_predict.py."""
+    import itertools as it_
+    from openviic_b200.data_utils import DictionaryDataset
+    from openviic_b200.evaluation import Cider
+    from openviic_b200.predict import evaluate_metrics, get_predictions
+    d, arrays, json_path, vocab, cfg = _dataset_fixture(golden, tmp_path)
+    ds = DictionaryDataset(json_path, vocab, cfg)
+
+    class Scripted:
+        def __init__(self):
+            self.inflight, self.calls = None, []
+
+        def submit(self, features, boxes):
+            assert self.inflight is None and boxes is not None and len(boxes) == len(features)
+            assert all(f.shape[0] == b.shape[0] for f, b in zip(features, boxes))
+            self.calls.append(len(features))
+            self.inflight = ["caption with %d rows" % f.shape[0] for f in features]
+
+        def collect(self):
+            out, self.inflight = self.inflight, None
+            return out
+
+    pred = Scripted()
+    out = get_predictions(pred, ds, batch_size=3, get_scores=False)   # image 8 has no reference captions
+    assert "CIDEr" not in out
+    assert pred.calls == [3, 1] and pred.inflight is None
+    assert [r["image_id"] for r in out["results"]] == [d["dictionary_image_ids"][:3], d["dictionary_image_ids"][3:]]
+    assert out["results"][0]["filename"] == d["dictionary_filenames"][:3]
+    assert list(out["results"][0]["gens"]) == ["0_0", "0_1", "0_2"] and list(out["results"][1]["gts"]) == ["1_0"]
+    assert out["results"][0]["gens"]["0_1"] == "caption with %d rows" % d["rows_per_image"][1]
+    assert out["results"][0]["gts"]["0_0"] == d["dictionary_captions"][0]
+    # an image without reference captions cannot be scored (the reference's scorer divides by zero there): drop it
+    scored = [i for i, caps in enumerate(d["dictionary_captions"]) if caps]
+
+    class Subset:
+        image_ids = [ds.image_ids[i] for i in scored]
+
+        def __len__(self):
+            return len(scored)
+
+        def __getitem__(self, i):
+            return ds[scored[i]]
+
+    scores = evaluate_metrics(Scripted(), Subset(), batch_size=2)
+    gts = {"%d_%d" % (k // 2, k % 2): d["dictionary_captions"][i] for k, i in enumerate(scored)}
+    gens = {"%d_%d" % (k // 2, k % 2): ["caption with %d rows" % d["rows_per_image"][i]] for k, i in enumerate(scored)}
+    assert scores == {"CIDEr": float(Cider().compute_score(gts, gens)[0])}
