@@ -320,8 +320,10 @@ def run_gpu_arm(args):
     from openviic_b200 import CaptionEngine
     n_streams = max(1, args.streams)
     engines = [eng]
+    host_weights = {k: v.detach().to("cpu", torch.float32) if torch.is_tensor(v) and v.dtype.is_floating_point else v
+                    for k, v in model.state_dict().items()}   # one device-to-host pass, not one per engine
     for _ in range(n_streams - 1):
-        extra = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), device)
+        extra = CaptionEngine(cfg.MODEL, vocab, host_weights, device)
         extra.reserve(batch, n, BEAM)
         engines.append(extra)
     streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
