@@ -26,8 +26,8 @@ step bench_both 300 env OPENVIIC_CROSS_TC=1 OPENVIIC_SELF_SPLIT=1 python bench.p
 step ncu_launches_variants 400 env OPENVIIC_CROSS_TC=1 OPENVIIC_SELF_SPLIT=1 ncu --metrics gpu__time_duration.sum \
     --clock-control none -c 800 --csv --log-file $OUT/r02_launches_variants.csv python tools/one_batch.py
 # 5. full captures of the two decode attention kernels (default and variant) for the roofline of the HBM-bound part
-step ncu_attention_default 500 ncu --set full --clock-control none --import-source on -k regex:decode_.*attention -c 12 \
+step ncu_attention_default 500 ncu --set full --clock-control none --import-source on -k regex:decode_.*attention --launch-skip 100 -c 12 \
     -o $OUT/r02_attention_default python tools/one_batch.py
 step ncu_attention_variants 500 env OPENVIIC_CROSS_TC=1 OPENVIIC_SELF_SPLIT=1 ncu --set full --clock-control none \
-    --import-source on -k regex:decode_.*attention -c 12 -o $OUT/r02_attention_variants python tools/one_batch.py
+    --import-source on -k regex:decode_.*attention --launch-skip 100 -c 12 -o $OUT/r02_attention_variants python tools/one_batch.py
 cat $OUT/r2_first_call.log
