@@ -1373,7 +1373,7 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
     CAP_REQUIRE(B > 0 && tiles <= f->tiles, "cap_fused_chain: batch %d exceeds the reservation", B);
     p.t = t; p.R = R; p.B = B; p.n_keys = 0;
     p.sparse_logits = (f->full_logits || p.beam > 5) ? 0 : 1;
-    p.trace = nullptr;
+    p.trace = g_fused_trace;   // debug (cap_debug_fused_trace): the epilogue stamps of fc1's chunk 3, else nullptr
     p.dbg_skip = 0;
     p.start_embed = 0;
     if (chain == CAP_CHAIN_EMBED_QKV) {          // x = Emb + pos; q|k|v of layer 0 -> cache
