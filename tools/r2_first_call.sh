@@ -16,6 +16,7 @@ step tests_predict 400 python -m pytest tests/test_gpu_predict.py -x -q
 step tests_gpu 900 python -m pytest tests -x -q -m gpu
 # 2. the default bench line (new: saturated roofline figure, breadcrumbs on stderr)
 step bench_default 400 python bench.py
+step trace_chain 300 python tools/trace_chain.py
 # 3. the opt-in attention kernels: numerics + launch times, then the suite and the bench with both switches on
 step probe_attention 400 python tests/gpu_scripts/probe_attention_variants.py
 step tests_gpu_variants 900 env OPENVIIC_CROSS_TC=1 OPENVIIC_SELF_SPLIT=1 python -m pytest tests -x -q -m gpu
