@@ -70,10 +70,12 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:   # N > 1: only rank 0 reports clocks; seven more pollers would only add driver-lock noise
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -405,7 +407,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     launches_per_step = cabi.launch_count() - c0
 
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=rank == 0)
     clocks.__enter__()
     for k in range(1, n_streams):   # warm every engine eagerly once (sets kernel attributes before capture)
         with torch.cuda.stream(streams[k]):
