@@ -301,7 +301,9 @@ enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
 // `bias_reg` carries this thread's bias value of the chunk across calls: the value of chunk c + 1 is requested
 // while chunk c is drained, so the global-load latency is off the per-chunk critical path (n_chunks = chunks of
 // the job; the first chunk of a job loads its own value).
-template <int KIND>
+// EPI = 1 (opt-in chain instantiation, 8 worker warps): the four tcgen05.ld of a warp are software-pipelined -- group
+// i + 1 is requested before the math and stores of group i -- and the chunk bias comes in as float4.
+template <int KIND, int EPI = 0>
 __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
                                                int n_chunks, float& bias_reg, bf16* dst_rowmajor, int ld_rowmajor) {
     // stage this chunk's 256 bias values (double-buffered by chunk parity; see the barrier note below)
@@ -318,6 +320,48 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
     const int b = acquire_acc(c, 2);
     fstamp(p, c.tile, 42, tr);
     const int row = c.quad * 32 + c.lane;
+    if constexpr (EPI == 1) {
+        uint32_t v[2][32];
+        const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
+        tmem_ld_32x32b_x32(tbase, v[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int colc = c.half * 128 + i * 32;
+            tmem_ld_wait();                                                     // group i has landed ...
+            if (i + 1 < 4) tmem_ld_32x32b_x32(tbase + (i + 1) * 32, v[(i + 1) & 1]);   // ... group i + 1 flies during its math
+            float f[32];
+            const float4* sb4 = reinterpret_cast<const float4*>(sb + colc);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = sb4[j4];
+                f[4 * j4] = __uint_as_float(v[i & 1][4 * j4]) + b4.x;
+                f[4 * j4 + 1] = __uint_as_float(v[i & 1][4 * j4 + 1]) + b4.y;
+                f[4 * j4 + 2] = __uint_as_float(v[i & 1][4 * j4 + 2]) + b4.z;
+                f[4 * j4 + 3] = __uint_as_float(v[i & 1][4 * j4 + 3]) + b4.w;
+            }
+            if (KIND == EPI_HID) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g] = pack8_u4(f + 8 * g);
+            const int gcol = chunk_idx * 256 + colc;
+            if (KIND == EPI_CACHE) {
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
+                staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
+            } else if (KIND == EPI_HID) {
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(p.hbuf + static_cast<size_t>(c.r0 + c.quad * 32) * FDFF + gcol);
+                staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
+            } else {
+                uint4* base = reinterpret_cast<uint4*>(p.qg) + (static_cast<size_t>(c.tile) * (FD / 8) + gcol / 8) * TILE_ROWS + row;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) base[static_cast<size_t>(g) * TILE_ROWS] = o[g];
+            }
+        }
+        release_acc(c, 2, b);
+        return;
+    }
     const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains (4 with 8 warps, 2 with 16)
     const bool wide = c.nw == NW;
 #pragma unroll 1
@@ -789,19 +833,46 @@ __device__ __forceinline__ void publish_attention(WorkerCtx& c) {
 // the largest maxima of a row.  A thread (= row, one half of every chunk) keeps the five largest group maxima it
 // has seen; a group is stored only if its maximum reaches the fifth of them -- every group of the row's final
 // top five passes that test when it is produced, and ~85 % of the 52 MB of logits per step are never written.
+// (the per-group body is vocab_group below; EPI = 1 requests the TMEM load of group i + 1 before it handles group i)
+__device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, int chunk_idx, int colc, int grow, bool wide,
+                                            const uint32_t (&v)[32], float (&top)[5]);
+
+template <int EPI = 0>
 __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx, float (&top)[5]) {
     const int b = acquire_acc(c, 2);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
     const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains
     const bool wide = c.nw == NW;
+    if constexpr (EPI == 1) {   // 8 worker warps: four groups, TMEM loads one group ahead of the statistics
+        uint32_t v[2][32];
+        const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
+        tmem_ld_32x32b_x32(tbase, v[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            tmem_ld_wait();
+            if (i + 1 < 4) tmem_ld_32x32b_x32(tbase + (i + 1) * 32, v[(i + 1) & 1]);
+            vocab_group(c, p, chunk_idx, c.half * 128 + i * 32, grow, true, v[i & 1], top);
+        }
+        release_acc(c, 2, b);
+        return;
+    }
 #pragma unroll 1
     for (int i = 0; i < groups; ++i) {
         const int colc = (c.half * groups + i) * 32;
-        const int gcol = chunk_idx * 256 + colc;
         uint32_t v[32];
         tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
         tmem_ld_wait();
+        vocab_group(c, p, chunk_idx, colc, grow, wide, v, top);
+    }
+    release_acc(c, 2, b);
+}
+
+// statistics + (sparse) store of one 32-column group of the vocabulary projection
+__device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, int chunk_idx, int colc, int grow, bool wide,
+                                            const uint32_t (&v)[32], float (&top)[5]) {
+    {
+        const int gcol = chunk_idx * 256 + colc;
         const int valid = p.vocab - gcol;  // columns of this 32-chunk inside the vocabulary (warp-uniform)
         float cm = -INFINITY, cs = 0.f;
         if (valid >= 32) {
@@ -847,7 +918,6 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
             }
         }
     }
-    release_acc(c, 2, b);
 }
 
 // CHAIN = false: the whole step (attention phases on this CTA's CUDA cores).  CHAIN = true: a range of the
@@ -859,9 +929,11 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
 // stages HALF of it (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared
 // memories and both CTAs drain their own accumulator rows.  A ring byte then feeds 256 rows instead of 128: the
 // same 64 KB ring keeps 8 k-block stages in flight instead of 4 (the chains are bound by that ring's latency).
-template <bool CHAIN, bool PAIR = false>
+// EPI (chains only, opt-in through OPENVIIC_CHAIN_EPI=1): epilogues with software-pipelined TMEM loads.
+template <bool CHAIN, bool PAIR = false, int EPI = 0>
 __global__ void __launch_bounds__(CHAIN ? CHAIN_THREADS : FUSED_THREADS, 1) __maxnreg__(CHAIN ? CHAIN_MAXNREG : 168)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
+    static_assert(EPI == 0 || (CHAIN && NW_CHAIN == 8), "the pipelined epilogues are written for the 8-warp chain kernels");
     constexpr int NWK = CHAIN ? NW_CHAIN : NW;   // worker warps of this instantiation
     static_assert(CHAIN || !PAIR, "CTA pairs exist for the chain kernels only");
     constexpr int NBX = PAIR ? NB_PAIR : NB;
@@ -1141,22 +1213,22 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     pdl_launch_dependents();
                     const int vchunks = p.vocab_tiles / 2;
                     float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
+                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk<EPI>(c, p, ch, top);
                     break;
                 }
                 const int L = ji / 6, k = ji % 6;
                 const FusedLayerP& W = p.layer[L];
                 if (k == 0) {
                     bf16* cache_t = p.qkv_cache + (static_cast<size_t>(L) * p.T + p.t) * p.R * 3 * FD;
-                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
+                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE, EPI>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
                 } else if (k == 1) {
                     epilogue_layernorm<true>(c, p, W.b_o1, W.g1, W.be1, nullptr);
                 } else if (k == 2) {
-                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, 2, bias_reg, p.q_out, FD);
+                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE, EPI>(c, p, W.b_q, ch, 2, bias_reg, p.q_out, FD);
                 } else if (k == 3) {
                     epilogue_layernorm<true>(c, p, W.b_o2, W.g2, W.be2, nullptr);
                 } else if (k == 4) {
-                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
+                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID, EPI>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
                     fence_proxy_async();  // hidden tile (global, generic proxy) -> TMA reads (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready);
@@ -1230,6 +1302,7 @@ struct cap_fused_decoder {
     int tiles = 0;
     bool has_att = false;
     bool use_pairs = true;      // CTA pairs (OPENVIIC_CHAIN_PAIR=0 at creation: single CTAs)
+    bool epi_pipelined = false; // experimental epilogues with software-pipelined TMEM loads (OPENVIIC_CHAIN_EPI=1 at creation)
     bool full_logits = false;   // debug / parity: every logit is stored (cap_fused_set_full_logits, OPENVIIC_FULL_LOGITS)
 };
 
@@ -1311,9 +1384,12 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     f->has_att = d->att_in != nullptr;
     f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
     f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
+    f->epi_pipelined = getenv("OPENVIIC_CHAIN_EPI") && atoi(getenv("OPENVIIC_CHAIN_EPI")) == 1;
     if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
     return CAP_OK;
@@ -1401,7 +1477,10 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
+        if (f->epi_pipelined) cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true, 1>, p);
+        else cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
+    } else if (f->epi_pipelined) {
+        decode_step_fused_kernel<true, false, 1><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     } else {
         decode_step_fused_kernel<true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     }
