@@ -302,7 +302,9 @@ enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
 // while chunk c is drained, so the global-load latency is off the per-chunk critical path (n_chunks = chunks of
 // the job; the first chunk of a job loads its own value).
 // EPI = 1 (opt-in chain instantiation, 8 worker warps): the four tcgen05.ld of a warp are software-pipelined -- group
-// i + 1 is requested before the math and stores of group i -- and the chunk bias comes in as float4.
+// i + 1 is requested before the math and stores of group i -- and the chunk bias comes in as float4.  EPI = 2: the
+// same, and the bf16 rows go to global memory straight from registers instead of through the warp's staging tile
+// (less shared-memory traffic next to the MMA's operand reads, more store sectors).
 template <int KIND, int EPI = 0>
 __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
                                                int n_chunks, float& bias_reg, bf16* dst_rowmajor, int ld_rowmajor) {
@@ -320,7 +322,7 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
     const int b = acquire_acc(c, 2);
     fstamp(p, c.tile, 42, tr);
     const int row = c.quad * 32 + c.lane;
-    if constexpr (EPI == 1) {
+    if constexpr (EPI >= 1) {
         uint32_t v[2][32];
         const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
         tmem_ld_32x32b_x32(tbase, v[0]);
@@ -349,10 +351,24 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
             const int gcol = chunk_idx * 256 + colc;
             if (KIND == EPI_CACHE) {
                 uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
-                staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
+                if constexpr (EPI == 2) {   // straight from registers: 32 rows x 16 B per store instruction, no staging tile
+                    if (c.lane < c.rows_valid_warp) {
+                        uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(c.lane) * ld_rowmajor * 2);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) dst[g] = o[g];
+                    }
+                } else {
+                    staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
+                }
             } else if (KIND == EPI_HID) {
                 uint8_t* gbase = reinterpret_cast<uint8_t*>(p.hbuf + static_cast<size_t>(c.r0 + c.quad * 32) * FDFF + gcol);
-                staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
+                if constexpr (EPI == 2) {
+                    uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(c.lane) * FDFF * 2);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[g] = o[g];
+                } else {
+                    staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
+                }
             } else {
                 uint4* base = reinterpret_cast<uint4*>(p.qg) + (static_cast<size_t>(c.tile) * (FD / 8) + gcol / 8) * TILE_ROWS + row;
 #pragma unroll
@@ -844,7 +860,7 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
     const int grow = c.r0 + row;
     const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains
     const bool wide = c.nw == NW;
-    if constexpr (EPI == 1) {   // 8 worker warps: four groups, TMEM loads one group ahead of the statistics
+    if constexpr (EPI >= 1) {   // 8 worker warps: four groups, TMEM loads one group ahead of the statistics
         uint32_t v[2][32];
         const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
         tmem_ld_32x32b_x32(tbase, v[0]);
@@ -929,11 +945,12 @@ __device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, 
 // stages HALF of it (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared
 // memories and both CTAs drain their own accumulator rows.  A ring byte then feeds 256 rows instead of 128: the
 // same 64 KB ring keeps 8 k-block stages in flight instead of 4 (the chains are bound by that ring's latency).
-// EPI (chains only, opt-in through OPENVIIC_CHAIN_EPI=1): epilogues with software-pipelined TMEM loads.
+// EPI (chains only, opt-in through OPENVIIC_CHAIN_EPI=1 / 2): epilogues with software-pipelined TMEM loads (2: and
+// direct register-to-global stores).
 template <bool CHAIN, bool PAIR = false, int EPI = 0>
 __global__ void __launch_bounds__(CHAIN ? CHAIN_THREADS : FUSED_THREADS, 1) __maxnreg__(CHAIN ? CHAIN_MAXNREG : 168)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
-    static_assert(EPI == 0 || (CHAIN && NW_CHAIN == 8), "the pipelined epilogues are written for the 8-warp chain kernels");
+    static_assert(EPI == 0 || ((EPI == 1 || EPI == 2) && CHAIN && NW_CHAIN == 8), "the pipelined epilogues are written for the 8-warp chain kernels");
     constexpr int NWK = CHAIN ? NW_CHAIN : NW;   // worker warps of this instantiation
     static_assert(CHAIN || !PAIR, "CTA pairs exist for the chain kernels only");
     constexpr int NBX = PAIR ? NB_PAIR : NB;
@@ -1302,7 +1319,7 @@ struct cap_fused_decoder {
     int tiles = 0;
     bool has_att = false;
     bool use_pairs = true;      // CTA pairs (OPENVIIC_CHAIN_PAIR=0 at creation: single CTAs)
-    bool epi_pipelined = false; // experimental epilogues with software-pipelined TMEM loads (OPENVIIC_CHAIN_EPI=1 at creation)
+    int epi_variant = 0;        // experimental epilogues (OPENVIIC_CHAIN_EPI=1 / 2 at creation): pipelined TMEM loads / + direct stores
     bool full_logits = false;   // debug / parity: every logit is stored (cap_fused_set_full_logits, OPENVIIC_FULL_LOGITS)
 };
 
@@ -1384,12 +1401,15 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     f->has_att = d->att_in != nullptr;
     f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
     f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
-    f->epi_pipelined = getenv("OPENVIIC_CHAIN_EPI") && atoi(getenv("OPENVIIC_CHAIN_EPI")) == 1;
+    f->epi_variant = getenv("OPENVIIC_CHAIN_EPI") ? atoi(getenv("OPENVIIC_CHAIN_EPI")) : 0;
+    if (f->epi_variant < 0 || f->epi_variant > 2) f->epi_variant = 0;
     if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
     return CAP_OK;
@@ -1477,10 +1497,13 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (f->epi_pipelined) cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true, 1>, p);
+        if (f->epi_variant == 1) cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true, 1>, p);
+        else if (f->epi_variant == 2) cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true, 2>, p);
         else cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
-    } else if (f->epi_pipelined) {
+    } else if (f->epi_variant == 1) {
         decode_step_fused_kernel<true, false, 1><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    } else if (f->epi_variant == 2) {
+        decode_step_fused_kernel<true, false, 2><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     } else {
         decode_step_fused_kernel<true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     }

@@ -26,6 +26,8 @@ step bench_both 300 env OPENVIIC_CROSS_TC=1 OPENVIIC_SELF_SPLIT=1 python bench.p
 # 3b. the chain kernels with software-pipelined TMEM loads in the epilogues (separate instantiation, read at engine creation)
 step tests_fused_epi 600 env OPENVIIC_CHAIN_EPI=1 python -m pytest tests/test_gpu_fused_decode.py tests/test_gpu_engine.py -x -q
 step bench_chain_epi 300 env OPENVIIC_CHAIN_EPI=1 python bench.py --skip-cpu
+step tests_fused_epi2 600 env OPENVIIC_CHAIN_EPI=2 python -m pytest tests/test_gpu_fused_decode.py tests/test_gpu_engine.py -x -q
+step bench_chain_epi2 300 env OPENVIIC_CHAIN_EPI=2 python bench.py --skip-cpu
 # 4. launch list of one batch with the variants on (share of the step per kernel), only after the runs above passed
 step ncu_launches_variants 400 env OPENVIIC_CROSS_TC=1 OPENVIIC_SELF_SPLIT=1 ncu --metrics gpu__time_duration.sum \
     --clock-control none -c 800 --csv --log-file $OUT/r02_launches_variants.csv python tools/one_batch.py
