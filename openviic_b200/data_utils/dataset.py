@@ -3,93 +3,91 @@
 
 On disk, as the reference expects it: one COCO-style JSON (``images`` with ``id`` / ``file_name``, ``annotations``
 with ``image_id`` / ``caption``) and one ``{image_id}.npy`` per image under ``config.FEATURE_PATH.FEATURES`` holding a
-pickled dict of arrays (``region_features`` (n, D), ``region_boxes`` (n, 4), ``grid_features`` ...), read with
-``np.load(..., allow_pickle=True)[()]``.  Samples are ``Instance`` objects; batches are built by
-``data_utils.collate_fn`` (the reference's) or, on the fast path, by ``FeatureBatcher`` from the per-image arrays.
+pickled dict of arrays (``region_features`` (n, D), ``region_boxes`` (n, 4), ``grid_features`` ...).  Samples are
+``Instance`` objects with the reference's field names and order; batches are built by ``data_utils.collate_fn`` (the
+reference's) or, on the fast path, by ``FeatureBatcher`` from the per-image arrays.
 """
 
 from __future__ import annotations
 
 import json
-import os
-from typing import Any, Dict, List, Tuple
+from pathlib import Path
+from typing import Any, Dict, List
 
 import numpy as np
 import torch
-from torch.utils import data
+from torch.utils.data import Dataset
 
 from ..utils.instance import Instance
 from .utils import preprocess_caption
 
 
-def _load_features(root: str, image_id) -> Dict[str, Any]:
-    return np.load(os.path.join(root, f"{image_id}.npy"), allow_pickle=True)[()]
-
-
-class FeatureDataset(data.Dataset):
-    """One sample per ANNOTATION: teacher-forcing tokens + the image's features (XE training / validation loss)."""
+class _AnnotatedFeatures(Dataset):
+    """What both datasets share: the parsed annotation file, the vocabulary and the per-image feature files."""
 
     def __init__(self, json_path: str, vocab, config) -> None:
         super().__init__()
-        with open(json_path, "r", encoding="utf-8") as fh:
-            json_data = json.load(fh)
         self.vocab = vocab
-        self.annotations = self.load_json(json_data)
         self.image_features_path = config.FEATURE_PATH.FEATURES
+        with open(json_path, encoding="utf-8") as fh:
+            self._index(json.load(fh))
 
-    def load_json(self, json_data: Dict) -> List[Dict]:
-        # the reference scans the image list per annotation (data_utils/dataset.py:29-42); an id -> file name table
-        # gives the same records (an annotation whose image is missing raises KeyError here; the reference silently
-        # repeats the previous annotation)
-        filenames = {}
-        for image in json_data["images"]:
-            filenames.setdefault(image["id"], image["file_name"])
-        return [{"caption": preprocess_caption(ann["caption"], self.vocab.tokenizer),
-                 "image_id": ann["image_id"],
-                 "filename": filenames[ann["image_id"]]} for ann in json_data["annotations"]]
+    def _index(self, json_data: Dict) -> None:
+        raise NotImplementedError
+
+    def _words(self, caption: str) -> List[str]:
+        return preprocess_caption(caption, self.vocab.tokenizer)
 
     def load_features(self, image_id) -> Dict[str, Any]:
-        return _load_features(self.image_features_path, image_id)
+        """The pickled dict of arrays of one image (``np.save(path, {...})``; ``[()]`` unwraps the 0-d object array)."""
+        return np.load(Path(self.image_features_path) / f"{image_id}.npy", allow_pickle=True)[()]
+
+
+class FeatureDataset(_AnnotatedFeatures):
+    """One sample per ANNOTATION: teacher-forcing tokens + the image's features (XE training / validation loss)."""
+
+    def _index(self, json_data: Dict) -> None:
+        self.annotations = self.load_json(json_data)
+
+    def load_json(self, json_data: Dict) -> List[Dict]:
+        # the reference scans the image list once per annotation (data_utils/dataset.py:29-42); one id -> file name
+        # table gives the same records.  An annotation whose image is missing raises KeyError here -- the reference
+        # silently repeats the previous record.
+        file_of = {}
+        for image in json_data["images"]:
+            file_of.setdefault(image["id"], image["file_name"])
+        return [dict(caption=self._words(a["caption"]), image_id=a["image_id"], filename=file_of[a["image_id"]])
+                for a in json_data["annotations"]]
 
     @property
     def captions(self) -> List[List[str]]:
-        return [ann["caption"] for ann in self.annotations]
-
-    def __getitem__(self, idx: int) -> Instance:
-        item = self.annotations[idx]
-        caption = self.vocab.encode_caption(item["caption"])
-        shifted = torch.full_like(caption, self.vocab.padding_idx)
-        shifted[:-1] = caption[1:]
-        caption = torch.where(caption == self.vocab.eos_idx, self.vocab.padding_idx, caption)   # the input never holds eos
-        return Instance(caption_tokens=caption, shifted_right_caption_tokens=shifted, **self.load_features(item["image_id"]))
+        return [record["caption"] for record in self.annotations]
 
     def __len__(self) -> int:
         return len(self.annotations)
 
+    def __getitem__(self, idx: int) -> Instance:
+        record = self.annotations[idx]
+        pad, eos = self.vocab.padding_idx, self.vocab.eos_idx
+        tokens = self.vocab.encode_caption(record["caption"])          # bos w1 .. wk eos pad ...
+        targets = torch.cat([tokens[1:], tokens.new_full((1,), pad)])   # w1 .. wk eos pad ... pad
+        inputs = tokens.masked_fill(tokens == eos, pad)                 # the decoder input never holds eos
+        return Instance(caption_tokens=inputs, shifted_right_caption_tokens=targets,
+                        **self.load_features(record["image_id"]))
 
-class DictionaryDataset(data.Dataset):
+
+class DictionaryDataset(_AnnotatedFeatures):
     """One sample per IMAGE with all of its reference captions (evaluation, self-critical training)."""
 
-    def __init__(self, json_path: str, vocab, config) -> None:
-        super().__init__()
-        with open(json_path, "r", encoding="utf-8") as fh:
-            json_data = json.load(fh)
-        self.vocab = vocab
+    def _index(self, json_data: Dict) -> None:
         self.image_ids, self.filenames, self.captions_with_image = self.load_json(json_data)
-        self.image_features_path = config.FEATURE_PATH.FEATURES
 
-    def load_json(self, json_data: Dict) -> Tuple[List, List[str], List[List[str]]]:
-        examples: Dict[Any, List[str]] = {}
-        filenames: Dict[Any, str] = {}
-        for image in json_data["images"]:
-            examples[image["id"]] = []
-            filenames[image["id"]] = image["file_name"]
+    def load_json(self, json_data: Dict):
+        by_image: Dict[Any, List[str]] = {image["id"]: [] for image in json_data["images"]}
+        file_of = {image["id"]: image["file_name"] for image in json_data["images"]}
         for ann in json_data["annotations"]:
-            examples[ann["image_id"]].append(" ".join(preprocess_caption(ann["caption"], self.vocab.tokenizer)))
-        return list(examples.keys()), list(filenames.values()), list(examples.values())
-
-    def load_features(self, image_id) -> Dict[str, Any]:
-        return _load_features(self.image_features_path, image_id)
+            by_image[ann["image_id"]].append(" ".join(self._words(ann["caption"])))
+        return list(by_image), list(file_of.values()), list(by_image.values())
 
     def __len__(self) -> int:
         return len(self.image_ids)
