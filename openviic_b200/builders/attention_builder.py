@@ -1,9 +1,3 @@
-"""META_ATTENTION registry + builder (reference: builders/attention_builder.py:3-8)."""
+"""Reference import path ``builders.attention_builder``; defined in ``builders/__init__.py``."""
 
-from .registry import Registry
-
-META_ATTENTION = Registry("META_ATTENTION")
-
-
-def build_attention(config):
-    return META_ATTENTION.get(config.ARCHITECTURE)(config)
+from . import META_ATTENTION, build_attention  # noqa: F401

@@ -1,9 +1,3 @@
-"""META_DECODER registry + builder (reference: builders/decoder_builder.py:3-8)."""
+"""Reference import path ``builders.decoder_builder``; defined in ``builders/__init__.py``."""
 
-from .registry import Registry
-
-META_DECODER = Registry("META_DECODER")
-
-
-def build_decoder(config, vocab):
-    return META_DECODER.get(config.ARCHITECTURE)(config, vocab)
+from . import META_DECODER, build_decoder  # noqa: F401

@@ -1,9 +1,3 @@
-"""META_ENCODER registry + builder (reference: builders/encoder_builder.py:3-8)."""
+"""Reference import path ``builders.encoder_builder``; defined in ``builders/__init__.py``."""
 
-from .registry import Registry
-
-META_ENCODER = Registry("META_ENCODER")
-
-
-def build_encoder(config):
-    return META_ENCODER.get(config.ARCHITECTURE)(config)
+from . import META_ENCODER, build_encoder  # noqa: F401

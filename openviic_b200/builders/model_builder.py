@@ -1,12 +1,3 @@
-"""META_ARCHITECTURE registry + builder (reference: builders/model_builder.py:4-10)."""
+"""Reference import path ``builders.model_builder``; defined in ``builders/__init__.py``."""
 
-import torch
-
-from .registry import Registry
-
-META_ARCHITECTURE = Registry("ARCHITECTURE")
-
-
-def build_model(config, vocab):
-    model = META_ARCHITECTURE.get(config.ARCHITECTURE)(config, vocab)
-    return model.to(torch.device(config.DEVICE))
+from . import META_ARCHITECTURE, build_model  # noqa: F401

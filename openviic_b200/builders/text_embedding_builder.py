@@ -1,9 +1,3 @@
-"""META_TEXT_EMBEDDING registry + builder (reference: builders/text_embedding_builder.py:3-8)."""
+"""Reference import path ``builders.text_embedding_builder``; defined in ``builders/__init__.py``."""
 
-from .registry import Registry
-
-META_TEXT_EMBEDDING = Registry("META_TEXT_EMBEDDING")
-
-
-def build_text_embedding(config, vocab):
-    return META_TEXT_EMBEDDING.get(config.ARCHITECTURE)(config, vocab)
+from . import META_TEXT_EMBEDDING, build_text_embedding  # noqa: F401

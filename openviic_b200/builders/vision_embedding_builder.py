@@ -1,9 +1,3 @@
-"""META_VISION_EMBEDDING registry + builder (reference: builders/vision_embedding_builder.py:3-8)."""
+"""Reference import path ``builders.vision_embedding_builder``; defined in ``builders/__init__.py``."""
 
-from .registry import Registry
-
-META_VISION_EMBEDDING = Registry("META_VISION_EMBEDDING")
-
-
-def build_vision_embedding(config):
-    return META_VISION_EMBEDDING.get(config.ARCHITECTURE)(config)
+from . import META_VISION_EMBEDDING, build_vision_embedding  # noqa: F401

@@ -1,13 +1,18 @@
-"""Stateful module container: the decode-state registry beam search reorders.
+"""Stateful module container: the decode-state registry that beam search reorders.
 
-Same API as the reference's models/modules/containers.py:5-78 (``register_state``, ``states``,
-``apply_to_states``, ``enable/disable_statefulness``, ``statefulness``).  States are registered
-buffers, so they also appear in ``state_dict()`` exactly like the reference's.
+API of the reference's models/modules/containers.py:5-78 -- ``register_state``, ``states``, ``apply_to_states``,
+``enable_statefulness`` / ``disable_statefulness``, the ``statefulness`` context manager, ``_is_stateful`` -- on a
+different mechanism: every container keeps one ordered table ``name -> pristine default``, and one generator walks
+the container tree (a container, then its container children depth-first in registration order; plain
+``nn.Module`` children and everything below them are skipped, as in the reference).  All operations are loops
+over that walk.  States are registered buffers, so they appear in ``state_dict()`` exactly like the reference's.
 """
 
 from __future__ import annotations
 
+from collections import OrderedDict
 from contextlib import contextmanager
+from typing import Iterator, Optional
 
 from torch import nn
 
@@ -16,51 +21,47 @@ class Module(nn.Module):
     def __init__(self):
         super().__init__()
         self._is_stateful = False
-        self._state_names = []
-        self._state_defaults = dict()
+        self._decode_states = OrderedDict()   # state name -> default value (a detached copy, or None)
 
-    def register_state(self, name: str, default):
-        self._state_names.append(name)
-        self._state_defaults[name] = None if default is None else default.clone().detach()
+    def register_state(self, name: str, default) -> None:
+        self._decode_states[name] = default if default is None else default.detach().clone()
         self.register_buffer(name, default)
 
-    def _stateful_children(self):
-        return (m for m in self.children() if isinstance(m, Module))
+    def _state_owners(self) -> Iterator["Module"]:
+        yield self
+        for child in self.children():
+            if isinstance(child, Module):
+                yield from child._state_owners()
 
     def states(self):
-        for name in self._state_names:
-            yield self._buffers[name]
-        for child in self._stateful_children():
-            yield from child.states()
+        for owner in self._state_owners():
+            for name in owner._decode_states:
+                yield owner._buffers[name]
 
-    def apply_to_states(self, fn):
-        for name in self._state_names:
-            self._buffers[name] = fn(self._buffers[name])
-        for child in self._stateful_children():
-            child.apply_to_states(fn)
+    def apply_to_states(self, fn) -> None:
+        """``state = fn(state)`` for every state of the tree, in the order ``states()`` yields them."""
+        for owner in self._state_owners():
+            for name in owner._decode_states:
+                owner._buffers[name] = fn(owner._buffers[name])
 
-    def _fresh_state(self, name: str):
-        default = self._state_defaults[name]
-        if default is None:
-            return None
-        return default.clone().detach().to(self._buffers[name].device)
+    def _load_defaults(self, batch_size: Optional[int]) -> None:
+        """Every state back to its default -- broadcast over a leading batch dimension when ``batch_size`` is given
+        (decode mode), as registered otherwise."""
+        for owner in self._state_owners():
+            for name, default in owner._decode_states.items():
+                value = None
+                if default is not None:
+                    value = default.detach().clone().to(owner._buffers[name].device)
+                    if batch_size is not None:
+                        value = value.unsqueeze(0).expand(batch_size, *value.shape).contiguous()
+                owner._buffers[name] = value
+            owner._is_stateful = batch_size is not None
 
-    def enable_statefulness(self, batch_size: int):
-        for child in self._stateful_children():
-            child.enable_statefulness(batch_size)
-        for name in self._state_names:
-            state = self._fresh_state(name)
-            if state is not None:
-                state = state.unsqueeze(0).expand([batch_size] + list(state.shape)).contiguous()
-            self._buffers[name] = state
-        self._is_stateful = True
+    def enable_statefulness(self, batch_size: int) -> None:
+        self._load_defaults(batch_size)
 
-    def disable_statefulness(self):
-        for child in self._stateful_children():
-            child.disable_statefulness()
-        for name in self._state_names:
-            self._buffers[name] = self._fresh_state(name)
-        self._is_stateful = False
+    def disable_statefulness(self) -> None:
+        self._load_defaults(None)
 
     @contextmanager
     def statefulness(self, batch_size: int):

@@ -1,0 +1,1 @@
+"""CPU restatement of the reference algorithm -- TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py CPU legs)."""
