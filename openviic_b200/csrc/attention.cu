@@ -1076,8 +1076,171 @@ int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key
     return cap_check_launch("decode_cross_attention_wide_kernel");
 }
 
+// Encoder self-attention with the whole image in shared memory (opt-in: OPENVIIC_ENC_TC=1; plain scaled dot-product,
+// H = 8, fused q|k|v rows, n <= 64): one CTA per image, one warp per head.  The image's n rows of q|k|v (3 KB each,
+// contiguous in the fused projection output) are bulk-copied once into rows of pitch 3 KB + 16 B; every warp then
+// walks the 16-query tiles of its head: S = Q.K^T with A and B fragments by conflict-free 32-bit loads, fp32 softmax
+// on the accumulator fragments (two query rows per lane), O = P.V with V fragments by ldmatrix.trans.
+// attention_mma_kernel above runs one CTA per (image, head) and gathers 128-byte slices of 3 KB rows for K, V and
+// Q separately: 2048 small CTAs per launch at config B against 256 here, each HBM byte requested once.
+constexpr int ET_PITCH = 3072 + 16;
+
+template <int NT>   // 8-key tiles: 7 (n <= 56) or 8 (n <= 64)
+__global__ void __launch_bounds__(256)
+encoder_self_attention_tc_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ key_mask, bf16* __restrict__ out,
+                                 int ldo, int n, float scale) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) uint8_t et_smem[];     // [n + 1][ET_PITCH] (last row zero), then NT*8 mask bytes
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    uint8_t* zero_row = et_smem + static_cast<size_t>(n) * ET_PITCH;
+    uint8_t* smask = zero_row + ET_PITCH;
+    const uint32_t bar_addr = xs_smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(static_cast<uint32_t>(n) * 3072u)
+                     : "memory");
+    }
+    for (int i = threadIdx.x; i < ET_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zero_row)[i] = 0u;
+    for (int j = threadIdx.x; j < NT * 8; j += blockDim.x) smask[j] = (j >= n || (key_mask && key_mask[static_cast<size_t>(b) * n + j])) ? 1 : 0;
+    pdl_wait();        // q|k|v come from the projection kernel right before this one
+    __syncthreads();   // barrier armed before any copy can complete on it; zero row and mask visible
+    if (threadIdx.x < n) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) + (static_cast<size_t>(b) * n + threadIdx.x) * 3072;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         xs_smem_u32(et_smem + static_cast<size_t>(threadIdx.x) * ET_PITCH)),
+                     "l"(reinterpret_cast<uint64_t>(src)), "r"(3072u), "r"(bar_addr)
+                     : "memory");
+    }
+    {   // all rows landed (phase 0); bounded spin
+        uint32_t done = 0;
+        for (uint32_t spin = 0; !done; ++spin) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(bar_addr) : "memory");
+            if (spin > (1u << 26)) __trap();
+        }
+    }
+    const int h = warp;
+    const float sc = scale * 1.4426950408889634f;   // scores in the log2 domain
+    const int mi = lane >> 3, mr = lane & 7;        // ldmatrix: this lane addresses row mr of 8x8 matrix mi
+    for (int q0 = 0; q0 < n; q0 += 16) {
+        const int ra = q0 + g, rb = ra + 8;
+        const uint8_t* qa_row = (ra < n ? et_smem + static_cast<size_t>(ra) * ET_PITCH : zero_row) + h * (HEAD_DIM * 2) + 4 * t;
+        const uint8_t* qb_row = (rb < n ? et_smem + static_cast<size_t>(rb) * ET_PITCH : zero_row) + h * (HEAD_DIM * 2) + 4 * t;
+        uint32_t qa[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(qa_row + ks * 32);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qb_row + ks * 32);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(qa_row + ks * 32 + 16);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(qb_row + ks * 32 + 16);
+        }
+        float s[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            const int key = nt * 8 + g;
+            const uint8_t* krow = (key < n ? et_smem + static_cast<size_t>(key) * ET_PITCH : zero_row) + 1024 + h * (HEAD_DIM * 2) + 4 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(krow + ks * 32),
+                               *reinterpret_cast<const uint32_t*>(krow + ks * 32 + 16));
+        }
+        float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x = smask[nt * 8 + 2 * t + (e & 1)] ? -INFINITY : s[nt][e] * sc;
+                s[nt][e] = x;
+                if (e < 2) ma = fmaxf(ma, x); else mb = fmaxf(mb, x);
+            }
+        }
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+        float suma = 0.f, sumb = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float m = e < 2 ? ma : mb;
+                const float p = (m == -INFINITY) ? 0.f : exp2f(s[nt][e] - m);
+                s[nt][e] = p;
+                if (e < 2) suma += p; else sumb += p;
+            }
+        }
+        suma += __shfl_xor_sync(0xffffffffu, suma, 1);
+        suma += __shfl_xor_sync(0xffffffffu, suma, 2);
+        sumb += __shfl_xor_sync(0xffffffffu, sumb, 1);
+        sumb += __shfl_xor_sync(0xffffffffu, sumb, 2);
+        float o[8][4];
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < (NT + 1) / 2; ++kk) {
+            constexpr int LAST = NT - 1;
+            const int hi = 2 * kk + 1 <= LAST ? 2 * kk + 1 : LAST;   // clamp keeps the index constant-foldable
+            const bool has_hi = 2 * kk + 1 <= LAST;
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = has_hi ? pack_bf16x2(s[hi][0], s[hi][1]) : 0u;
+            pa[3] = has_hi ? pack_bf16x2(s[hi][2], s[hi][3]) : 0u;
+            const int key = kk * 16 + (mi & 1) * 8 + mr;
+            const uint8_t* vrow = (key < n ? et_smem + static_cast<size_t>(key) * ET_PITCH : zero_row) + 2048 + h * (HEAD_DIM * 2) +
+                                  (mi >> 1) * 16;
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t vb[4];
+                ldmatrix_x4_trans(vb, xs_smem_u32(vrow + dp * 32));
+                mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+            }
+        }
+        const float inva = suma > 0.f ? 1.f / suma : 0.f;
+        const float invb = sumb > 0.f ? 1.f / sumb : 0.f;
+        bf16* oa = out + (static_cast<size_t>(b) * n + ra) * ldo + h * HEAD_DIM + 2 * t;
+        bf16* ob = out + (static_cast<size_t>(b) * n + rb) * ldo + h * HEAD_DIM + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            if (ra < n) *reinterpret_cast<bf162*>(oa + dt * 8) = __floats2bfloat162_rn(o[dt][0] * inva, o[dt][1] * inva);
+            if (rb < n) *reinterpret_cast<bf162*>(ob + dt * 8) = __floats2bfloat162_rn(o[dt][2] * invb, o[dt][3] * invb);
+        }
+    }
+}
+
+template <int NT>
+int launch_encoder_tc(const AttnDev& a, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(a.nk + 1) * ET_PITCH + NT * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAP_CHECK_CUDA(cudaFuncSetAttribute(encoder_self_attention_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
+        attr_done = true;
+    }
+    CAP_LAUNCH((encoder_self_attention_tc_kernel<NT>), a.B, 256, smem, stream, a.q, a.mask, a.out, a.ldo, a.nk, a.scale);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("encoder_self_attention_tc_kernel");
+}
+
 int launch_attention(const AttnDev& a, cudaStream_t stream) {
     const int nk_all = a.nk + a.n_mem;
+    {   // opt-in: whole-image encoder self-attention (plain attention over fused q|k|v rows, one CTA per image)
+        const char* enc_tc = getenv("OPENVIIC_ENC_TC");   // read per call: a probe compares both paths in one process
+        const int hd = a.H * HEAD_DIM;
+        if (enc_tc && atoi(enc_tc) != 0 && a.H == 8 && a.geometry == nullptr && a.n_mem == 0 && a.nq == a.nk && a.nk <= 64 &&
+            a.k == a.q + hd && a.v == a.q + 2 * hd && a.ldq == 3 * hd && a.ldk == 3 * hd && a.ldv == 3 * hd &&
+            a.q_bs == static_cast<long long>(a.nk) * 3 * hd && a.o_bs == static_cast<long long>(a.nk) * a.ldo &&
+            (a.mask == nullptr || (a.mask_qs == 0 && a.mask_bs == a.nk)) && a.ldo % 2 == 0 &&
+            (reinterpret_cast<uintptr_t>(a.q) & 15) == 0) {
+            return a.nk <= 56 ? launch_encoder_tc<7>(a, stream) : launch_encoder_tc<8>(a, stream);
+        }
+    }
     static const bool force_simt = getenv("OPENVIIC_ATTENTION_SIMT") != nullptr;
     if (nk_all <= 128 && !force_simt) {  // tensor-core variant
         dim3 grid((a.nq + MMA_Q_TILE - 1) / MMA_Q_TILE, a.H, a.B);

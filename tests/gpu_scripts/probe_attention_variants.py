@@ -1,6 +1,7 @@
 """GPU probe (not collected by pytest): the two opt-in decode attention kernels against the default ones --
-the tensor-core cross-attention (OPENVIIC_CROSS_TC=1, decode_cross_attention_tc_kernel) and the split-key
-self-attention (OPENVIIC_SELF_SPLIT=1, decode_self_attention_split_kernel): numerics at several shapes, launch time
+the tensor-core cross-attention (OPENVIIC_CROSS_TC=1, decode_cross_attention_tc_kernel), the split-key
+self-attention (OPENVIIC_SELF_SPLIT=1, decode_self_attention_split_kernel) and the whole-image encoder self-attention
+(OPENVIIC_ENC_TC=1, encoder_self_attention_tc_kernel): numerics at several shapes, launch time
 at the bench shape, and captions / latency of a whole beam search with each switch on.
 
     python tests/gpu_scripts/probe_attention_variants.py
@@ -71,14 +72,16 @@ def main():
         us = e0.elapsed_time(e1) * 1e3 / (25 * len(sets))
         print(f"tensor_path={tensor_path}: {us:.2f} us per launch back to back, {B * n * 2048 / us / 1e3:.0f} GB/s of K|V")
     self_attention_part(dev, g)
+    encoder_attention_part(dev, g)
     # whole path: captions with the switches on vs off (both are read per launch; CUDA graphs bake them in at capture)
     cfg, vocab, model, _ = bench.build_model("standard_grid", dev)
     feats = synthetic.synth_features(256, 49, 2048, 1, False).to(torch.bfloat16).to(dev)
     outs = {}
     for name, env in [("default", {}), ("cross_tc", {"OPENVIIC_CROSS_TC": "1"}), ("self_split", {"OPENVIIC_SELF_SPLIT": "1"}),
-                      ("both", {"OPENVIIC_CROSS_TC": "1", "OPENVIIC_SELF_SPLIT": "1"})]:
-        os.environ["OPENVIIC_CROSS_TC"] = env.get("OPENVIIC_CROSS_TC", "0")
-        os.environ["OPENVIIC_SELF_SPLIT"] = env.get("OPENVIIC_SELF_SPLIT", "0")
+                      ("enc_tc", {"OPENVIIC_ENC_TC": "1"}),
+                      ("all", {"OPENVIIC_CROSS_TC": "1", "OPENVIIC_SELF_SPLIT": "1", "OPENVIIC_ENC_TC": "1"})]:
+        for key in ("OPENVIIC_CROSS_TC", "OPENVIIC_SELF_SPLIT", "OPENVIIC_ENC_TC"):
+            os.environ[key] = env.get(key, "0")
         eng = CaptionEngine(cfg.MODEL, vocab, model.state_dict(), dev)
         eng.reserve(256, 49, 5)
         ids, lp = eng.caption_device(feats, None, 1, use_graph=False)
@@ -97,7 +100,40 @@ def main():
               f"{same.float().mean().item():.2%}, max log-prob diff on those "
               f"{(outs['default'][1] - lp).abs()[same].max().item():.4f}")
         eng.close()
-    os.environ["OPENVIIC_CROSS_TC"] = os.environ["OPENVIIC_SELF_SPLIT"] = "0"
+    os.environ["OPENVIIC_CROSS_TC"] = os.environ["OPENVIIC_SELF_SPLIT"] = os.environ["OPENVIIC_ENC_TC"] = "0"
+
+
+def encoder_attention_part(dev, g):
+    """Whole-image encoder self-attention (OPENVIIC_ENC_TC=1) against the per-(image, head) kernel, through ops.attention
+    on slices of a fused q|k|v tensor (the layout the engine's encoder uses)."""
+    from openviic_b200 import ops
+    H, hd = 8, 512
+    for B, n in [(5, 49), (3, 50), (4, 37), (2, 57), (2, 64), (256, 49)]:
+        qkv = torch.randn(B, n, 3 * hd, generator=g).to(torch.bfloat16).to(dev)
+        mask = torch.zeros(B, 1, 1, n, dtype=torch.bool)
+        mask[B // 2, ..., n // 2:] = True
+        mask[0, ..., 0] = True
+        mask = mask.to(dev)
+        q, k, v = qkv[..., :hd], qkv[..., hd:2 * hd], qkv[..., 2 * hd:]
+        qf, kf, vf = (x.float().view(B, n, H, 64).transpose(1, 2) for x in (q, k, v))
+        sc = (qf @ kf.transpose(-1, -2)) * 0.125
+        ref = (torch.softmax(sc.masked_fill(mask, float("-inf")), -1) @ vf).transpose(1, 2).reshape(B, n, hd)
+        line = f"encoder attention B={B} n={n}:"
+        for flag in ("0", "1"):
+            os.environ["OPENVIIC_ENC_TC"] = flag
+            out = ops.attention(q, k, v, H, mask=mask)
+            torch.cuda.synchronize()
+            line += f" enc_tc={flag} max-abs err {(out.float() - ref).abs().max().item():.4f}"
+            if B == 256:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(50):
+                    ops.attention(q, k, v, H, mask=mask)
+                e1.record()
+                torch.cuda.synchronize()
+                line += f" ({e0.elapsed_time(e1) * 1e3 / 50:.2f} us per call incl. host)"
+        print(line)
+    os.environ["OPENVIIC_ENC_TC"] = "0"
 
 
 def self_attention_part(dev, g):
