@@ -158,3 +158,29 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(cabi, "LIB_PATH", tmp_path / "libopenviic_cap.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cabi.load_library()
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """`bench.py --impl reference`: stdout carries one JSON object with the contract's keys (the GPU arm prints the same
+    shape); anything else the run prints goes to stderr."""
+    proc = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--cpu-batch", "2"], capture_output=True, text=True, cwd=REPO, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "captions_per_sec_beam5_len20" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_gpu_arm_refuses_to_run_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    proc = subprocess.run([sys.executable, str(REPO / "bench.py"), "--steps", "1"], capture_output=True, text=True, cwd=REPO,
+                          timeout=600)
+    assert proc.returncode != 0 and proc.stdout.strip() == ""
+    assert "no CPU fallback" in proc.stderr
