@@ -415,26 +415,45 @@ def run_gpu_arm(args):
             engines[k].beam_search(out_size=1, use_graph=False)
     for i in range(max(3, args.warmup) * n_streams):
         step(i)
+    join()
+    final_gather()   # the collective is warm (communicator channels, allocator blocks) before the timed region
     progress("warm-up enqueued")
     barrier()
-    progress("warm-up done, timing")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fork(args.stagger_ms)
-    host_t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = step(i)
-    host_enqueue_s = time.perf_counter() - host_t0
-    join()
-    gathered = final_gather()
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - host_t0) * 1e3
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    value = batch * world * args.steps / (total_ms / 1e3)
+
+    def timed_pass(passes):
+        """`passes` x K steps inside ONE region bracketed by barrier + synchronize, CUDA events on the timing
+        stream, max over ranks.  Returns (device ms, host enqueue s, wall ms)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fork(args.stagger_ms)
+        host_t0 = time.perf_counter()
+        for i in range(args.steps * passes):
+            step(i)
+        enqueue_s = time.perf_counter() - host_t0
+        join()
+        final_gather()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - host_t0) * 1e3
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), enqueue_s, wall
+
+    # K steps at ~3 ms each is a region of tens of milliseconds: launch ramp, the final gather and event jitter
+    # would be a visible part of it.  One untimed calibration pass, then the K steps are repeated `passes` times
+    # inside one timed region of >= --min-timed-ms; ms_per_step = region / (K x passes).
+    calib_ms, _, _ = timed_pass(1)
+    passes = max(1, int(-(-args.min_timed_ms // max(calib_ms, 1e-3)))) if args.min_timed_ms > 0 else 1
+    if world > 1:   # every rank must run the same number of passes
+        pt = torch.tensor([passes], device=device)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        passes = int(pt.item())
+    progress(f"warm-up done (calibration pass {calib_ms:.1f} ms), timing {passes} x {args.steps} steps")
+    total_ms, host_enqueue_s, wall_ms = timed_pass(passes)
+    steps_timed = args.steps * passes
+    value = batch * world * steps_timed / (total_ms / 1e3)
     print(f"[bench] device-resident loop: {total_ms:.1f} ms on the device, host enqueue {host_enqueue_s * 1e3:.1f} ms, wall {wall_ms:.1f} ms",
           file=sys.stderr)
 
@@ -458,7 +477,7 @@ def run_gpu_arm(args):
     barrier()
     progress("e2e warm-up done, timing")
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps_timed):
         e2e_step(i)
     if world > 1:   # the final gather of the ranks' captions, from the host buffers the loop has just filled
         torch.cuda.synchronize()
@@ -474,7 +493,7 @@ def run_gpu_arm(args):
     e2e_s = torch.tensor([e2e_elapsed], device=device)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = batch * world * args.steps / float(e2e_s.item())
+    e2e_value = batch * world * steps_timed / float(e2e_s.item())
     h2d = feats_host[0].numel() * feats_host[0].element_size() + (boxes_host[0].numel() * 4 if needs_boxes else 0)
     d2h = batch * MAX_LEN * (8 + 4)
 
@@ -504,7 +523,7 @@ def run_gpu_arm(args):
                     "timing": "CUDA events around graph replays of the 20 steps' chain launches of ONE batch alone on the "
                               "GPU (10 row tiles = 10 of 148 SMs busy): the fraction is per-launch latency-bound by "
                               "design; throughput comes from ~15 batches in flight (step_frac_of_tensor_peak)",
-                    "share_of_step": MAX_LEN * chain_s / (total_ms / 1e3 / args.steps)}
+                    "share_of_step": MAX_LEN * chain_s / (total_ms / 1e3 / steps_timed)}
         sat_s = time_decode_chains_saturated(engines, streams) if n_streams > 1 else None
         if sat_s:   # the kernel with all SMs busy: what the throughput figure is made of
             roofline["achieved_saturated"] = flops / sat_s / 1e12
@@ -522,7 +541,7 @@ def run_gpu_arm(args):
                     "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                    "share_of_step": gemm_s / (total_ms / 1e3 / args.steps)}
+                    "share_of_step": gemm_s / (total_ms / 1e3 / steps_timed)}
     roofline["step_algorithmic_tflops"] = gflop_per_caption * 1e9 * max(value, e2e_value) / world / 1e12
     roofline["step_frac_of_tensor_peak"] = roofline["step_algorithmic_tflops"] / peaks["tflops_sustained"]
 
@@ -532,18 +551,21 @@ def run_gpu_arm(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / steps_timed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{yaml_name}: {n} visual tokens x 2048, beam {BEAM}, len {MAX_LEN}, V {VOCAB}, "
                                f"batch {batch}/GPU", "global_batch": batch * world, "parallelism": f"dp{world}",
                    "l2": f"{n_sets} rotating input batches ({n_sets} x {h2d / 1e6:.0f} MB > 126 MB L2); step working set > L2",
+                   "timed_region": f"{args.steps} steps x {passes} passes = {steps_timed} steps in one region of {total_ms:.0f} ms "
+                                   f"(>= {args.min_timed_ms:.0f} ms so that ramp-up and the final gather do not dominate)",
+                   "timed_passes": passes,
                    "cuda_graph": not args.no_graph, "streams": n_streams,
                    "pipelining": f"{n_streams} independent batches in flight on {n_streams} streams/engines", "weights": "synthetic seed 1234 (openviic_b200/synthetic.py)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_features": "bf16 pinned",
                 "api": "cap_engine_caption_host_async" if world == 1 else
                 "cap_engine_caption_host_async per rank + one final NCCL all-gather of the caption ids"},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches": int(launches_per_step * steps_timed),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks.summary(),
     }
@@ -565,6 +587,8 @@ def main():
                     help="start stream k of the device-resident loop k * this many ms late (inside the timed region)")
     ap.add_argument("--pace-ms", type=float, default=0.0,
                     help="device-resident loop: admit one batch every this many ms (0 = enqueue everything at once)")
+    ap.add_argument("--min-timed-ms", type=float, default=500.0,
+                    help="repeat the K steps inside the timed region until it lasts at least this long (0 = exactly K steps)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=40)
@@ -578,11 +602,16 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
     try:
-        return run_gpu_arm(args)
-    finally:
-        import torch.distributed as dist
-        if dist.is_initialized():
-            dist.destroy_process_group()
+        rc = run_gpu_arm(args)
+    except BaseException:   # noqa: BLE001 -- a rank that fails must not leave its peers parked in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)   # no destructors, no communicator teardown: torchrun sees the exit and stops the other ranks
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    return rc
 
 
 if __name__ == "__main__":

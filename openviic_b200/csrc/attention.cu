@@ -888,12 +888,8 @@ int launch_cross_smem(const bf16* q, int ldq, const bf16* kv, const uint8_t* key
     // K|V staging; the partial-state merge (XS_CHUNKS * BEAMS warps x 32 lanes x 18 floats) reuses it
     const size_t smem = std::max(static_cast<size_t>(n) * 2048,
                                  static_cast<size_t>(XS_CHUNKS) * BEAMS * 32 * (XW_EPL + 2) * sizeof(float));
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_smem_kernel<BEAMS>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-        attr_done = true;
-    }
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_smem_kernel<BEAMS>, 208 * 1024));
     CAP_LAUNCH((decode_cross_attention_smem_kernel<BEAMS>), B, BEAMS * XS_CHUNKS * 32, smem, stream, q, ldq, kv, key_mask,
                out, ldo, n, scale);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1047,12 +1043,8 @@ template <int NT>
 int launch_cross_tc(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int beams,
                     int n, float scale, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(n + 1) * XT_PITCH + NT * 8;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            220 * 1024));
-        attr_done = true;
-    }
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_tc_kernel<NT>, 220 * 1024));
     CAP_LAUNCH((decode_cross_attention_tc_kernel<NT>), B, 256, smem, stream, q, ldq, kv, key_mask, out, ldo, beams, n, scale);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_cross_attention_tc_kernel");
@@ -1062,12 +1054,8 @@ template <int BEAMS>
 int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
                       float scale, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(XW_WARPS) * BEAMS * 32 * (XW_EPL + 2) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(decode_cross_attention_wide_kernel<BEAMS>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_done = true;
-    }
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_wide_kernel<BEAMS>, 64 * 1024));
     static const int max_grid = getenv("OPENVIIC_CROSS_GRID") ? atoi(getenv("OPENVIIC_CROSS_GRID")) : 0;
     const int grid = (max_grid > 0 && max_grid < B) ? max_grid : B;
     CAP_LAUNCH((decode_cross_attention_wide_kernel<BEAMS>), grid, XW_WARPS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n,
@@ -1217,12 +1205,8 @@ encoder_self_attention_tc_kernel(const bf16* __restrict__ qkv, const uint8_t* __
 template <int NT>
 int launch_encoder_tc(const AttnDev& a, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(a.nk + 1) * ET_PITCH + NT * 8;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(encoder_self_attention_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            220 * 1024));
-        attr_done = true;
-    }
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, encoder_self_attention_tc_kernel<NT>, 220 * 1024));
     CAP_LAUNCH((encoder_self_attention_tc_kernel<NT>), a.B, 256, smem, stream, a.q, a.mask, a.out, a.ldo, a.nk, a.scale);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("encoder_self_attention_tc_kernel");
@@ -1253,11 +1237,8 @@ int launch_attention(const AttnDev& a, cudaStream_t stream) {
     }
     const size_t smem = static_cast<size_t>(nk_all) * (K_STRIDE + HEAD_DIM) * 2 + ATT_WARPS * HEAD_DIM * 4 +
                         ATT_WARPS * MAX_KEYS * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_done = true;
-    }
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, attention_kernel, 64 * 1024));
     dim3 grid((a.nq + Q_TILE - 1) / Q_TILE, a.H, a.B);
     CAP_LAUNCH((attention_kernel), grid, ATT_THREADS, smem, stream, a);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);

@@ -578,7 +578,9 @@ extern "C" int cap_beam_reset(cap_beam* h, int batch, int bos_idx, cap_stream_t 
     CAP_REQUIRE(batch > 0 && batch <= h->max_batch, "cap_beam_reset: batch %d outside (0,%d]", batch, h->max_batch);
     h->dev.batch = batch;  // the [T][R] tables are laid out for the CURRENT R = batch*beam
     const int R = batch * h->dev.beam;
-    CAP_LAUNCH((beam_reset_kernel), (R + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), h->dev, bos_idx);
+    // serialising launch: every later decode kernel may start early (PDL) and some prefetch the encode-time cross K|V
+    // before their griddepcontrol.wait -- the encoder's GEMMs must have COMPLETED before the first decode kernel runs
+    CAP_LAUNCH_SERIAL((beam_reset_kernel), (R + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), h->dev, bos_idx);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("beam_reset_kernel");
 }
@@ -592,12 +594,8 @@ extern "C" int cap_beam_step(cap_beam* h, int t, const float* scores, int ld, in
     const int R = d.batch * d.beam;
     const size_t row_bytes = static_cast<size_t>(d.vocab) * 4;
     const int stage = row_bytes <= 160 * 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAP_CHECK_CUDA(cudaFuncSetAttribute(beam_rowpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            160 * 1024));
-        attr_done = true;
-    }
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, beam_rowpass_kernel, 160 * 1024));
     const int items = (d.vocab + ROW_THREADS - 1) / ROW_THREADS;
     if (items <= 4)
         CAP_LAUNCH((beam_rowpass_reg_kernel<4>), R, ROW_THREADS, 0, s, d, scores, ld, is_logprob, t);

@@ -50,7 +50,7 @@ int cap_set_error(int code, const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------
 bool cap_pdl_enabled();
 
-template <typename Kernel, typename... Args>
+template <bool PDL = true, typename Kernel, typename... Args>
 inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
                               Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -60,7 +60,7 @@ inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem,
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int n = 0;
-    if (cap_pdl_enabled()) {
+    if (PDL && cap_pdl_enabled()) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
@@ -79,6 +79,27 @@ inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem,
 
 #define CAP_LAUNCH(kernel, grid, block, smem, stream, ...) \
     cap_launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__)
+// Full stream serialisation (no programmatic dependent launch): the kernel starts only after everything before it on
+// the stream has COMPLETED.  Used as the fence between phases whose later kernels prefetch data before their own
+// griddepcontrol.wait (the decode cross-attention fetches the encode-time K|V early).
+#define CAP_LAUNCH_SERIAL(kernel, grid, block, smem, stream, ...) \
+    cap_launch_kernel<false>(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__)
+
+// Opt-in to > 48 KB of dynamic shared memory: the attribute is PER DEVICE, and entry points may be called from several
+// host threads, so the "already done" flag is one atomic bit per device ordinal (setting it twice is harmless).
+struct cap_device_once {
+    unsigned long long done = 0;
+};
+template <typename Kernel>
+inline int cap_opt_in_smem(cap_device_once& once, Kernel kernel, int bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&once.done, __ATOMIC_ACQUIRE) & bit) return CAP_OK;
+    CAP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    __atomic_fetch_or(&once.done, bit, __ATOMIC_RELEASE);
+    return CAP_OK;
+}
 
 static inline int cap_check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

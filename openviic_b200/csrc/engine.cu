@@ -117,7 +117,7 @@ struct cap_engine {
     // CUDA graph of a full beam search (begin + T steps + finalize)
     cudaGraphExec_t graph_exec = nullptr;
     cudaStream_t capture_stream = nullptr;  // the legacy default stream cannot be captured: capture here, replay anywhere
-    int graph_batch = 0, graph_out_size = 0;
+    int graph_batch = 0, graph_n = 0, graph_out_size = 0;   // the captured launches bake B, n and out_size into their arguments
     int64_t* graph_ids = nullptr;
     float* graph_logp = nullptr;
     bool warmed = false;
@@ -630,7 +630,10 @@ extern "C" int cap_engine_decode_step(cap_engine* e, int t, cap_stream_t stream)
     CAP_REQUIRE(t >= 0 && t < e->desc.max_len, "cap_engine_decode_step: step %d outside [0,%d)", t, e->desc.max_len);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->vocab_chunks > 512)  // vocabularies beyond the merge kernel's reach: full row pass over the logits
-        return cap_engine_decode_logits(e, t, stream) || cap_engine_beam_advance(e, t, stream);
+    {
+        CAP_PROPAGATE(cap_engine_decode_logits(e, t, stream));
+        return cap_engine_beam_advance(e, t, stream);
+    }
     if (e->fused) {
         CAP_PROPAGATE(run_fused_stack(e, t, s));
         return cap_beam_step_stats(e->beam_state, t, e->logits, e->ld_logits, e->part_ms, e->vocab_chunks, s);
@@ -740,8 +743,8 @@ extern "C" int cap_engine_beam_search(cap_engine* e, int out_size, int64_t* ids,
         e->warmed = true;
         return run_search_eager(e, out_size, ids, logp, s);
     }
-    const bool hit = e->graph_exec && e->graph_batch == e->cur_batch && e->graph_out_size == out_size &&
-                     e->graph_ids == ids && e->graph_logp == logp;
+    const bool hit = e->graph_exec && e->graph_batch == e->cur_batch && e->graph_n == e->cur_n &&
+                     e->graph_out_size == out_size && e->graph_ids == ids && e->graph_logp == logp;
     if (!hit) {
         if (e->graph_exec) {
             cudaGraphExecDestroy(e->graph_exec);
@@ -762,6 +765,7 @@ extern "C" int cap_engine_beam_search(cap_engine* e, int out_size, int64_t* ids,
         cudaGraphDestroy(graph);
         if (inst != cudaSuccess) return cap_set_error(CAP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(inst));
         e->graph_batch = e->cur_batch;
+        e->graph_n = e->cur_n;
         e->graph_out_size = out_size;
         e->graph_ids = ids;
         e->graph_logp = logp;

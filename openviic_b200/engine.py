@@ -50,6 +50,26 @@ def model_desc(model_cfg, vocab) -> cabi.ModelDesc:
         eos_idx=vocab.eos_idx)
 
 
+def _feat_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return cabi.CAP_F32
+    if t.dtype == torch.bfloat16:
+        return cabi.CAP_BF16
+    raise TypeError(f"features must be float32 or bfloat16, got {t.dtype}")
+
+
+def _check_out(out, b: int, out_size: int, max_len: int, where: str, device=None):
+    """(ids int64, log-probs float32), both contiguous (b, out_size, max_len): the C side writes exactly that many."""
+    ids, logp = out
+    for t, dt, name in ((ids, torch.int64, "ids"), (logp, torch.float32, "log-probs")):
+        if t.dtype != dt or not t.is_contiguous() or t.numel() != b * out_size * max_len:
+            raise ValueError(f"{where}: output {name} must be a contiguous {dt} tensor of {b}x{out_size}x{max_len} elements")
+        if device is None and t.is_cuda:
+            raise ValueError(f"{where}: output {name} must live in host memory")
+        if device is not None and t.device != device:
+            raise ValueError(f"{where}: output {name} must live on {device}")
+
+
 class CaptionEngine:
     """One engine per GPU / rank: weights as bf16, workspaces, KV caches, beam state, CUDA graph."""
 
@@ -57,6 +77,8 @@ class CaptionEngine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("CaptionEngine needs a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:   # "cuda" -> the current device, so that tensor.device comparisons are exact
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.desc = model_desc(model_cfg, vocab)
         self.max_len = vocab.max_caption_length
         self._h = C.c_void_p()
@@ -98,29 +120,44 @@ class CaptionEngine:
     # -- the path ---------------------------------------------------------------------------
     def encode(self, feats: torch.Tensor, boxes: Optional[torch.Tensor] = None):
         """feats (B,n,D_FEATURE) fp32/bf16 on the device [+ boxes (B,n,4) fp32]."""
+        feats, bx = self._device_inputs(feats, boxes)
+        b, n, _ = feats.shape
+        self._keep = (feats, bx)
+        with torch.cuda.device(self.device):
+            cabi.call("cap_engine_encode", self._h, feats.data_ptr(), _feat_dtype(feats),
+                      None if bx is None else bx.data_ptr(), b, n, self._stream())
+        self.batch, self.n = b, n
+
+    def _device_inputs(self, feats: torch.Tensor, boxes: Optional[torch.Tensor]):
+        """Features as contiguous fp32 / bf16 and boxes as contiguous fp32 (B,n,4) on this engine's device."""
+        if feats.device != self.device:
+            raise ValueError(f"features live on {feats.device}, the engine on {self.device}")
+        if feats.dim() != 3 or feats.shape[2] != self.desc.d_feature:
+            raise ValueError(f"features must be (B, n, {self.desc.d_feature}), got {tuple(feats.shape)}")
         if feats.dtype not in (torch.float32, torch.bfloat16):
             feats = feats.float()
         feats = feats.contiguous()
-        b, n, _ = feats.shape
-        bx = None if boxes is None else boxes.float().contiguous()
-        self._keep = (feats, bx)
-        cabi.call("cap_engine_encode", self._h, feats.data_ptr(),
-                  cabi.CAP_F32 if feats.dtype == torch.float32 else cabi.CAP_BF16,
-                  None if bx is None else bx.data_ptr(), b, n, self._stream())
-        self.batch, self.n = b, n
+        bx = None
+        if boxes is not None:
+            if boxes.device != self.device or tuple(boxes.shape) != (feats.shape[0], feats.shape[1], 4):
+                raise ValueError("boxes must be (B, n, 4) on the engine's device")
+            bx = boxes.float().contiguous()
+        return feats, bx
 
     def beam_search(self, out_size: int = 1, use_graph: bool = True):
         ids = torch.empty((self.batch, out_size, self.max_len), device=self.device, dtype=torch.int64)
         logp = torch.empty((self.batch, out_size, self.max_len), device=self.device, dtype=torch.float32)
         if use_graph:  # graph replay needs stable output addresses: decode into engine-owned buffers
-            key = (self.batch, out_size)
+            key = (self.batch, self.n, out_size)
             if getattr(self, "_graph_out", {}).get("key") != key:
                 self._graph_out = {"key": key, "ids": ids, "logp": logp}
             g = self._graph_out
-            cabi.call("cap_engine_beam_search", self._h, out_size, g["ids"].data_ptr(), g["logp"].data_ptr(), 1,
-                      self._stream())
+            with torch.cuda.device(self.device):
+                cabi.call("cap_engine_beam_search", self._h, out_size, g["ids"].data_ptr(), g["logp"].data_ptr(), 1,
+                          self._stream())
             return g["ids"].clone(), g["logp"].clone()
-        cabi.call("cap_engine_beam_search", self._h, out_size, ids.data_ptr(), logp.data_ptr(), 0, self._stream())
+        with torch.cuda.device(self.device):
+            cabi.call("cap_engine_beam_search", self._h, out_size, ids.data_ptr(), logp.data_ptr(), 0, self._stream())
         return ids, logp
 
     def caption_host(self, feats_host: torch.Tensor, boxes_host: Optional[torch.Tensor] = None, out_size: int = 1,
@@ -128,35 +165,43 @@ class CaptionEngine:
                      sync: bool = True):
         """End to end from HOST tensors (pin them for full PCIe speed) to HOST ids / log-probs.
         ``sync=False`` returns right after enqueueing (synchronise the current stream before reading)."""
+        if feats_host.is_cuda or feats_host.dim() != 3 or feats_host.shape[2] != self.desc.d_feature:
+            raise ValueError(f"caption_host: features must be a host tensor (B, n, {self.desc.d_feature})")
+        if feats_host.dtype not in (torch.float32, torch.bfloat16):   # any other dtype would be reinterpreted bit-wise
+            feats_host = feats_host.float()
+        feats_host = feats_host.contiguous()
         b, n, _ = feats_host.shape
+        if boxes_host is not None:
+            if boxes_host.is_cuda or tuple(boxes_host.shape) != (b, n, 4):
+                raise ValueError("caption_host: boxes must be a host tensor (B, n, 4)")
+            boxes_host = boxes_host.float().contiguous()
         if out is None:
             out = (torch.empty((b, out_size, self.max_len), dtype=torch.int64).pin_memory(),
                    torch.empty((b, out_size, self.max_len), dtype=torch.float32).pin_memory())
+        _check_out(out, b, out_size, self.max_len, "caption_host")
         ids, logp = out
+        self._keep_host = (feats_host, boxes_host, out)   # the async copies read / write these after the call returns
         with torch.cuda.device(self.device):
             cabi.call("cap_engine_caption_host" if sync else "cap_engine_caption_host_async", self._h, feats_host.data_ptr(),
-                      cabi.CAP_F32 if feats_host.dtype == torch.float32 else cabi.CAP_BF16,
-                      None if boxes_host is None else boxes_host.data_ptr(), b, n, out_size, ids.data_ptr(),
-                      logp.data_ptr(), 1 if use_graph else 0, self._stream())
+                      _feat_dtype(feats_host), None if boxes_host is None else boxes_host.data_ptr(), b, n, out_size,
+                      ids.data_ptr(), logp.data_ptr(), 1 if use_graph else 0, self._stream())
         self.batch, self.n = b, n
         return ids, logp
 
     def caption_device(self, feats: torch.Tensor, boxes: Optional[torch.Tensor] = None, out_size: int = 1,
                        use_graph: bool = True, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """Device tensors in, device tensors out, one C call (encode + beam search), nothing synchronises."""
-        if feats.dtype not in (torch.float32, torch.bfloat16):
-            feats = feats.float()
-        feats = feats.contiguous()
+        feats, bx = self._device_inputs(feats, boxes)
         b, n, _ = feats.shape
-        bx = None if boxes is None else boxes.float().contiguous()
         if out is None:
             out = (torch.empty((b, out_size, self.max_len), device=self.device, dtype=torch.int64),
                    torch.empty((b, out_size, self.max_len), device=self.device, dtype=torch.float32))
+        _check_out(out, b, out_size, self.max_len, "caption_device", self.device)
         self._keep = (feats, bx, out)
-        cabi.call("cap_engine_caption_device_async", self._h, feats.data_ptr(),
-                  cabi.CAP_F32 if feats.dtype == torch.float32 else cabi.CAP_BF16,
-                  None if bx is None else bx.data_ptr(), b, n, out_size, out[0].data_ptr(), out[1].data_ptr(),
-                  1 if use_graph else 0, self._stream())
+        with torch.cuda.device(self.device):
+            cabi.call("cap_engine_caption_device_async", self._h, feats.data_ptr(), _feat_dtype(feats),
+                      None if bx is None else bx.data_ptr(), b, n, out_size, out[0].data_ptr(), out[1].data_ptr(),
+                      1 if use_graph else 0, self._stream())
         self.batch, self.n = b, n
         return out
 

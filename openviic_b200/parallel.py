@@ -8,15 +8,17 @@ its own engine; the only exchange is one final all-gather of the caption ids (an
 from __future__ import annotations
 
 import os
+from datetime import timedelta
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 
-def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+def init_distributed(backend: Optional[str] = None, timeout_s: float = 120.0) -> Tuple[int, int, int]:
     """(rank, world_size, local_rank) from the torchrun environment; initialises the process group
-    when WORLD_SIZE > 1 (NCCL on GPUs, gloo otherwise)."""
+    when WORLD_SIZE > 1 (NCCL on GPUs, gloo otherwise).  `timeout_s` bounds every collective: a rank whose
+    peer died raises after that long instead of waiting in a barrier until somebody kills the job."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -29,10 +31,10 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
             # bind the communicator to this rank's GPU and create it now (not lazily at the first collective,
             # which would otherwise happen in the middle of the pipelined work)
             torch.cuda.set_device(local_rank)
-            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=timedelta(seconds=timeout_s),
                                     device_id=torch.device("cuda", local_rank))
         else:
-            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=timedelta(seconds=timeout_s))
     return rank, world, local_rank
 
 
