@@ -201,6 +201,13 @@ typedef struct cap_fused_layer {
     const float *b_fc1, *b_fc2, *ln3_g, *ln3_b;            /* feed-forward */
 } cap_fused_layer;
 
+/* Stacked bf16 copies of the decoder's projection weights (one TMA tensor map then serves every GEMM of a chain).
+ * A set built once can back any number of handles (cap_fused_desc::stacked): engines that pipeline independent
+ * batches stream the same addresses, which stay L2-resident.  The caller keeps it alive while a handle uses it. */
+typedef struct cap_fused_weights cap_fused_weights;
+int cap_fused_weights_create(const cap_fused_layer* layers, int n_layers, cap_fused_weights** out);
+int cap_fused_weights_destroy(cap_fused_weights* w);
+
 typedef struct cap_fused_desc {
     int d_model, heads, d_ff, n_layers, vocab, max_len, beam, pad_idx;
     int max_rows;                 /* max_batch * beam */
@@ -221,6 +228,7 @@ typedef struct cap_fused_desc {
     /* chain mode only (cap_fused_chain), else NULL: */
     const void* att_in;           /* bf16 [max_rows][d_model]: output of cap_decode_{self,cross}_attention */
     void* q_out;                  /* bf16 [max_rows][d_model]: queries for cap_decode_cross_attention */
+    const cap_fused_weights* stacked; /* NULL: the handle builds and owns its own stacked copies of `layers` */
 } cap_fused_desc;
 
 typedef struct cap_fused_decoder cap_fused_decoder;
@@ -273,6 +281,11 @@ typedef struct cap_engine cap_engine;
 
 int cap_engine_create(const cap_model_desc* desc, cap_engine** out);
 int cap_engine_destroy(cap_engine* e);
+/* A further engine over the SAME device weights as `parent` (which must be finalized): no upload, no copy -- only
+ * its own workspaces, caches, beam state and CUDA graph after cap_engine_reserve.  Engines that caption independent
+ * batches concurrently on several streams are created this way: one 48 MB weight set stays L2-resident instead of one
+ * per engine.  The weights live until the last engine referencing them is destroyed. */
+int cap_engine_create_shared(cap_engine* parent, cap_engine** out);
 /* Upload one state_dict entry (fp32, HOST memory) under its reference name, e.g.
  * "encoder.layers.0.mhatt.attention.fc_q.weight".  Unknown names are an error. */
 int cap_engine_load_weight(cap_engine* e, const char* name, const float* data_host,
@@ -324,6 +337,11 @@ const void* cap_engine_encoder_output(cap_engine* e);   /* bf16 [levels][B*n][d_
 const uint8_t* cap_engine_encoder_mask(cap_engine* e);  /* uint8 [B*n]                 */
 const float* cap_engine_logits(cap_engine* e, int* ld); /* fp32 [R][ld]                */
 cap_beam* cap_engine_beam(cap_engine* e);
+/* Fault records: every bounded device-side wait (mbarrier waits of the tcgen05 / TMA kernels) that times out records
+ * its source line in pinned host memory before it traps, so the cause of an "unspecified launch failure" can be read
+ * AFTER the CUDA context has died.  Copies up to max_records source lines and returns the number of distinct waits
+ * that timed out (0: none ever did). */
+int cap_fault_records(unsigned int* out, int max_records);
 /* Debug: when non-NULL, every later cap_linear writes 8 %globaltimer stamps (ns) per CTA into
  * device_buffer[cta*8 + k]: 0 entry, 1 prologue done, 2 first TMA issued, 3 first stage landed,
  * 4 last MMA committed, 5 accumulator visible to the epilogue, 6 stores issued, 7 TMEM freed. */

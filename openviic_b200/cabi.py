@@ -50,6 +50,7 @@ SIGNATURES = {
     "cap_last_error": (C.c_char_p, []),
     "cap_launch_count": (_i64, []),
     "cap_debug_gemm_trace": (_i, [_vp]),
+    "cap_fault_records": (_i, [_vp, _i]),
     "cap_linear": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_linear_simt": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_add_layernorm": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
@@ -74,6 +75,8 @@ SIGNATURES = {
     "cap_beam_ancestry": (_vp, [_vp]),
     "cap_beam_seq_logprob": (_vp, [_vp]),
     "cap_beam_parents": (_vp, [_vp]),
+    "cap_fused_weights_create": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "cap_fused_weights_destroy": (_i, [_vp]),
     "cap_fused_create": (_i, [_vp, C.POINTER(_vp)]),
     "cap_fused_destroy": (_i, [_vp]),
     "cap_fused_decode_step": (_i, [_vp, _i, _i, _i, _vp]),
@@ -84,6 +87,7 @@ SIGNATURES = {
     "cap_linear_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cap_engine_create": (_i, [C.POINTER(ModelDesc), C.POINTER(_vp)]),
     "cap_engine_destroy": (_i, [_vp]),
+    "cap_engine_create_shared": (_i, [_vp, C.POINTER(_vp)]),
     "cap_engine_load_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
     "cap_engine_finalize": (_i, [_vp]),
     "cap_engine_reserve": (_i, [_vp, _i, _i, _i]),
@@ -113,7 +117,8 @@ SIGNATURES = {
 }
 
 # entry points whose int return value is an error code
-_STATUS_FUNCS = {name for name, (res, _) in SIGNATURES.items() if res is _i and name != "cap_abi_version"}
+_STATUS_FUNCS = {name for name, (res, _) in SIGNATURES.items()
+                 if res is _i and name not in ("cap_abi_version", "cap_fault_records", "cap_fused_get_full_logits")}
 
 _lib: Optional[C.CDLL] = None
 
@@ -150,3 +155,11 @@ def call(name: str, *args):
 
 def launch_count() -> int:
     return int(load_library().cap_launch_count())
+
+
+def fault_records():
+    """Source lines (in their .cu file) of the device-side waits that timed out; readable after the CUDA context has
+    faulted.  Empty: no bounded wait ever timed out, i.e. a fault had another cause."""
+    buf = (C.c_uint * 64)()
+    n = int(load_library().cap_fault_records(buf, 64))
+    return [int(r) for r in buf[:min(n, 64)]]

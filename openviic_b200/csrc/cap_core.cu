@@ -32,3 +32,45 @@ extern "C" int cap_abi_version(void) { return CAP_ABI_VERSION; }
 extern "C" const char* cap_last_error(void) { return g_last_error; }
 
 extern "C" int64_t cap_launch_count(void) { return static_cast<int64_t>(g_cap_launches.load()); }
+
+// ---- fault records (see tcgen05_ptx.cuh) -----------------------------------------------------------------------
+// 64 bytes of header + 64 32-bit records (slot = source line & 63, value = source line), in pinned host memory that
+// every device of the process can write (portable + mapped); readable after a sticky CUDA error.
+namespace {
+unsigned long long* g_fault_host = nullptr;
+}
+
+extern "C" unsigned long long* cap_fault_buffer_device() {
+    static const bool ok = [] {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 4096, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        memset(p, 0, 4096);
+        g_fault_host = static_cast<unsigned long long*>(p);
+        return true;
+    }();
+    if (!ok) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, g_fault_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return static_cast<unsigned long long*>(d);
+}
+
+// Copies the non-empty fault records (source lines of the waits that timed out) into out, at most max_records, and
+// returns their number (0 = no wait ever timed out).  Works after the CUDA context has faulted.
+extern "C" int cap_fault_records(unsigned int* out, int max_records) {
+    if (g_fault_host == nullptr) return 0;
+    const unsigned int* slots = reinterpret_cast<const unsigned int*>(g_fault_host) + 16;
+    int n = 0;
+    for (int i = 0; i < 64; ++i) {
+        const unsigned int r = __atomic_load_n(slots + i, __ATOMIC_ACQUIRE);
+        if (r == 0) continue;
+        if (n < max_records) out[n] = r;
+        ++n;
+    }
+    return n;
+}

@@ -301,11 +301,10 @@ enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
 // `bias_reg` carries this thread's bias value of the chunk across calls: the value of chunk c + 1 is requested
 // while chunk c is drained, so the global-load latency is off the per-chunk critical path (n_chunks = chunks of
 // the job; the first chunk of a job loads its own value).
-// EPI = 1 (opt-in chain instantiation, 8 worker warps): the four tcgen05.ld of a warp are software-pipelined -- group
-// i + 1 is requested before the math and stores of group i -- and the chunk bias comes in as float4.  EPI = 2: the
-// same, and the bf16 rows go to global memory straight from registers instead of through the warp's staging tile
-// (less shared-memory traffic next to the MMA's operand reads, more store sectors).
-template <int KIND, int EPI = 0>
+// (Measured in round 2 and removed: software-pipelining the four tcgen05.ld of a warp one group ahead of the math
+// changed nothing -- 84.5 k vs 85.2 k captions/s -- and storing the bf16 rows straight from registers instead of
+// through the staging tile was slower, 81.9 k: the store sectors cost more than the shared-memory round trip.)
+template <int KIND>
 __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
                                                int n_chunks, float& bias_reg, bf16* dst_rowmajor, int ld_rowmajor) {
     // stage this chunk's 256 bias values (double-buffered by chunk parity; see the barrier note below)
@@ -322,62 +321,6 @@ __device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& 
     const int b = acquire_acc(c, 2);
     fstamp(p, c.tile, 42, tr);
     const int row = c.quad * 32 + c.lane;
-    if constexpr (EPI >= 1) {
-        uint32_t v[2][32];
-        const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
-        tmem_ld_32x32b_x32(tbase, v[0]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int colc = c.half * 128 + i * 32;
-            tmem_ld_wait();                                                     // group i has landed ...
-            if (i + 1 < 4) tmem_ld_32x32b_x32(tbase + (i + 1) * 32, v[(i + 1) & 1]);   // ... group i + 1 flies during its math
-            float f[32];
-            const float4* sb4 = reinterpret_cast<const float4*>(sb + colc);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b4 = sb4[j4];
-                f[4 * j4] = __uint_as_float(v[i & 1][4 * j4]) + b4.x;
-                f[4 * j4 + 1] = __uint_as_float(v[i & 1][4 * j4 + 1]) + b4.y;
-                f[4 * j4 + 2] = __uint_as_float(v[i & 1][4 * j4 + 2]) + b4.z;
-                f[4 * j4 + 3] = __uint_as_float(v[i & 1][4 * j4 + 3]) + b4.w;
-            }
-            if (KIND == EPI_HID) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            uint4 o[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) o[g] = pack8_u4(f + 8 * g);
-            const int gcol = chunk_idx * 256 + colc;
-            if (KIND == EPI_CACHE) {
-                uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
-                if constexpr (EPI == 2) {   // straight from registers: 32 rows x 16 B per store instruction, no staging tile
-                    if (c.lane < c.rows_valid_warp) {
-                        uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(c.lane) * ld_rowmajor * 2);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) dst[g] = o[g];
-                    }
-                } else {
-                    staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
-                }
-            } else if (KIND == EPI_HID) {
-                uint8_t* gbase = reinterpret_cast<uint8_t*>(p.hbuf + static_cast<size_t>(c.r0 + c.quad * 32) * FDFF + gcol);
-                if constexpr (EPI == 2) {
-                    uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(c.lane) * FDFF * 2);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) dst[g] = o[g];
-                } else {
-                    staged_store64(c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
-                }
-            } else {
-                uint4* base = reinterpret_cast<uint4*>(p.qg) + (static_cast<size_t>(c.tile) * (FD / 8) + gcol / 8) * TILE_ROWS + row;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) base[static_cast<size_t>(g) * TILE_ROWS] = o[g];
-            }
-        }
-        release_acc(c, 2, b);
-        return;
-    }
     const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains (4 with 8 warps, 2 with 16)
     const bool wide = c.nw == NW;
 #pragma unroll 1
@@ -849,30 +792,16 @@ __device__ __forceinline__ void publish_attention(WorkerCtx& c) {
 // the largest maxima of a row.  A thread (= row, one half of every chunk) keeps the five largest group maxima it
 // has seen; a group is stored only if its maximum reaches the fifth of them -- every group of the row's final
 // top five passes that test when it is produced, and ~85 % of the 52 MB of logits per step are never written.
-// (the per-group body is vocab_group below; EPI = 1 requests the TMEM load of group i + 1 before it handles group i)
+// (the per-group body is vocab_group below)
 __device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, int chunk_idx, int colc, int grow, bool wide,
                                             const uint32_t (&v)[32], float (&top)[5]);
 
-template <int EPI = 0>
 __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx, float (&top)[5]) {
     const int b = acquire_acc(c, 2);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
     const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains
     const bool wide = c.nw == NW;
-    if constexpr (EPI >= 1) {   // 8 worker warps: four groups, TMEM loads one group ahead of the statistics
-        uint32_t v[2][32];
-        const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
-        tmem_ld_32x32b_x32(tbase, v[0]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            tmem_ld_wait();
-            if (i + 1 < 4) tmem_ld_32x32b_x32(tbase + (i + 1) * 32, v[(i + 1) & 1]);
-            vocab_group(c, p, chunk_idx, c.half * 128 + i * 32, grow, true, v[i & 1], top);
-        }
-        release_acc(c, 2, b);
-        return;
-    }
 #pragma unroll 1
     for (int i = 0; i < groups; ++i) {
         const int colc = (c.half * groups + i) * 32;
@@ -945,12 +874,9 @@ __device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, 
 // stages HALF of it (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared
 // memories and both CTAs drain their own accumulator rows.  A ring byte then feeds 256 rows instead of 128: the
 // same 64 KB ring keeps 8 k-block stages in flight instead of 4 (the chains are bound by that ring's latency).
-// EPI (chains only, opt-in through OPENVIIC_CHAIN_EPI=1 / 2): epilogues with software-pipelined TMEM loads (2: and
-// direct register-to-global stores).
-template <bool CHAIN, bool PAIR = false, int EPI = 0>
+template <bool CHAIN, bool PAIR = false>
 __global__ void __launch_bounds__(CHAIN ? CHAIN_THREADS : FUSED_THREADS, 1) __maxnreg__(CHAIN ? CHAIN_MAXNREG : 168)
 decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
-    static_assert(EPI == 0 || ((EPI == 1 || EPI == 2) && CHAIN && NW_CHAIN == 8), "the pipelined epilogues are written for the 8-warp chain kernels");
     constexpr int NWK = CHAIN ? NW_CHAIN : NW;   // worker warps of this instantiation
     static_assert(CHAIN || !PAIR, "CTA pairs exist for the chain kernels only");
     constexpr int NBX = PAIR ? NB_PAIR : NB;
@@ -1076,9 +1002,10 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         // ------------------------------------------------------------------ MMA issuer (pair: the leader's only)
         // Uniform control flow for the whole warp; the elected lane issues tcgen05.mma / tcgen05.commit.
         constexpr uint32_t idesc = make_instr_desc(PAIR ? 256 : 128, 128);
-        auto wait_consumers = [](uint64_t* bar, uint32_t parity) {
-            if constexpr (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+        auto wait_consumers_at = [](uint64_t* bar, uint32_t parity, int line) {
+            if constexpr (PAIR) mbar_wait_cluster_impl(bar, parity, line); else mbar_wait_impl(bar, parity, line);
         };
+#define wait_consumers(bar, parity) wait_consumers_at(bar, parity, __LINE__)
         auto commit = [](uint64_t* bar) {
             if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar);
         };
@@ -1163,6 +1090,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                 }
             }
         }
+#undef wait_consumers
         pdl_launch_dependents();
     } else if (CHAIN && warp == 2) {
         // ------------------------------------------------------------------ A-tile loader (chain mode)
@@ -1230,22 +1158,22 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     pdl_launch_dependents();
                     const int vchunks = p.vocab_tiles / 2;
                     float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk<EPI>(c, p, ch, top);
+                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
                     break;
                 }
                 const int L = ji / 6, k = ji % 6;
                 const FusedLayerP& W = p.layer[L];
                 if (k == 0) {
                     bf16* cache_t = p.qkv_cache + (static_cast<size_t>(L) * p.T + p.t) * p.R * 3 * FD;
-                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE, EPI>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
+                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
                 } else if (k == 1) {
                     epilogue_layernorm<true>(c, p, W.b_o1, W.g1, W.be1, nullptr);
                 } else if (k == 2) {
-                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE, EPI>(c, p, W.b_q, ch, 2, bias_reg, p.q_out, FD);
+                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, 2, bias_reg, p.q_out, FD);
                 } else if (k == 3) {
                     epilogue_layernorm<true>(c, p, W.b_o2, W.g2, W.be2, nullptr);
                 } else if (k == 4) {
-                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID, EPI>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
+                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
                     fence_proxy_async();  // hidden tile (global, generic proxy) -> TMA reads (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready);
@@ -1312,14 +1240,60 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
-struct cap_fused_decoder {
-    FusedParams base;
+// Stacked bf16 copies of a decoder's projection weights: [layers * 5120][512] (q|k|v, self fc_o, cross fc_q, cross
+// fc_o, fc1 per layer) and [layers * 512][2048] (fc2), so that one TMA tensor map serves every GEMM of a chain.
+// One set can serve any number of handles (cap_fused_desc::stacked): engines that pipeline independent batches then
+// stream the SAME addresses, which the evict_last hint keeps L2-resident.
+struct cap_fused_weights {
     void* w512 = nullptr;
     void* w2 = nullptr;
+    int n_layers = 0;
+};
+
+extern "C" int cap_fused_weights_destroy(cap_fused_weights* w) {
+    if (!w) return CAP_OK;
+    cudaFree(w->w512);
+    cudaFree(w->w2);
+    delete w;
+    return CAP_OK;
+}
+
+extern "C" int cap_fused_weights_create(const cap_fused_layer* layers, int n_layers, cap_fused_weights** out) {
+    CAP_REQUIRE(layers && out, "cap_fused_weights_create: null pointer");
+    CAP_REQUIRE(n_layers >= 1 && n_layers <= MAX_FUSED_LAYERS, "cap_fused_weights_create: 1..%d layers", MAX_FUSED_LAYERS);
+    cap_fused_weights* f = new cap_fused_weights();
+    f->n_layers = n_layers;
+    auto fail = [&](int rc) { cap_fused_weights_destroy(f); return rc; };
+    const size_t w512_elems = static_cast<size_t>(n_layers) * W512_ROWS_PER_LAYER * FD;
+    const size_t w2_elems = static_cast<size_t>(n_layers) * FD * FDFF;
+    if (cudaMalloc(&f->w512, w512_elems * 2) != cudaSuccess || cudaMalloc(&f->w2, w2_elems * 2) != cudaSuccess)
+        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_weights_create: cudaMalloc of the stacked weights failed"));
+    for (int l = 0; l < n_layers; ++l) {
+        const cap_fused_layer& w = layers[l];
+        const void* srcs[5] = {w.w_qkv, w.w_o1, w.w_q, w.w_o2, w.w_fc1};
+        const int rows[5] = {3 * FD, FD, FD, FD, FDFF};
+        bf16* dst = static_cast<bf16*>(f->w512) + static_cast<size_t>(l) * W512_ROWS_PER_LAYER * FD;
+        for (int i = 0; i < 5; ++i) {
+            if (!srcs[i]) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_weights_create: null weight"));
+            if (cudaMemcpy(dst, srcs[i], static_cast<size_t>(rows[i]) * FD * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
+                return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_weights_create: weight copy failed"));
+            dst += static_cast<size_t>(rows[i]) * FD;
+        }
+        if (!w.w_fc2 || cudaMemcpy(static_cast<bf16*>(f->w2) + static_cast<size_t>(l) * FD * FDFF, w.w_fc2,
+                                   static_cast<size_t>(FD) * FDFF * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
+            return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_weights_create: fc2 copy failed"));
+    }
+    *out = f;
+    return CAP_OK;
+}
+
+struct cap_fused_decoder {
+    FusedParams base;
+    cap_fused_weights* stacked = nullptr;   // the stacked weights the tensor maps point into
+    bool owns_stacked = false;              // false: cap_fused_desc::stacked, owned by the caller
     int tiles = 0;
     bool has_att = false;
     bool use_pairs = true;      // CTA pairs (OPENVIIC_CHAIN_PAIR=0 at creation: single CTAs)
-    int epi_variant = 0;        // experimental epilogues (OPENVIIC_CHAIN_EPI=1 / 2 at creation): pipelined TMEM loads / + direct stores
     bool full_logits = false;   // debug / parity: every logit is stored (cap_fused_set_full_logits, OPENVIIC_FULL_LOGITS)
 };
 
@@ -1330,6 +1304,8 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     CAP_REQUIRE(d->beam >= 1 && d->beam <= MAXB, "cap_fused_create: beam must be 1..%d", MAXB);
     CAP_REQUIRE(d->max_rows > 0 && d->vocab > 8 && d->max_len > 0 && d->max_len <= 40, "cap_fused_create: bad sizes (max_len <= 40)");
     CAP_REQUIRE(d->ld_logits % 32 == 0 && d->ld_logits >= d->vocab, "cap_fused_create: ld_logits must be a multiple of 32");
+    CAP_REQUIRE(d->stacked == nullptr || d->stacked->n_layers == d->n_layers, "cap_fused_create: stacked weights of another model");
+    CAP_PROPAGATE(install_fault_buffer());
     cap_fused_decoder* f = new cap_fused_decoder();
     FusedParams& p = f->base;
     memset(&p, 0, sizeof(p));
@@ -1337,25 +1313,15 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     p.n_layers = L;
     f->tiles = ((d->max_rows + TILE_ROWS - 1) / TILE_ROWS + 1) / 2 * 2;   // even: CTA pairs; scratch tiles exist for a dummy partner
     auto fail = [&](int rc) { cap_fused_destroy(f); return rc; };
-    // stacked weight copies: one tensor map covers every K = 512 projection of the model
-    const size_t w512_elems = static_cast<size_t>(L) * W512_ROWS_PER_LAYER * FD;
-    const size_t w2_elems = static_cast<size_t>(L) * FD * FDFF;
-    if (cudaMalloc(&f->w512, w512_elems * 2) != cudaSuccess || cudaMalloc(&f->w2, w2_elems * 2) != cudaSuccess)
-        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cudaMalloc of the stacked weights failed"));
+    if (d->stacked) {
+        f->stacked = const_cast<cap_fused_weights*>(d->stacked);
+    } else {
+        const int rc0 = cap_fused_weights_create(d->layers, L, &f->stacked);
+        if (rc0 != CAP_OK) return fail(rc0);
+        f->owns_stacked = true;
+    }
     for (int l = 0; l < L; ++l) {
         const cap_fused_layer& w = d->layers[l];
-        const void* srcs[5] = {w.w_qkv, w.w_o1, w.w_q, w.w_o2, w.w_fc1};
-        const int rows[5] = {3 * FD, FD, FD, FD, FDFF};
-        bf16* dst = static_cast<bf16*>(f->w512) + static_cast<size_t>(l) * W512_ROWS_PER_LAYER * FD;
-        for (int i = 0; i < 5; ++i) {
-            if (!srcs[i]) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_create: null weight"));
-            if (cudaMemcpy(dst, srcs[i], static_cast<size_t>(rows[i]) * FD * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
-                return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: weight copy failed"));
-            dst += static_cast<size_t>(rows[i]) * FD;
-        }
-        if (!w.w_fc2 || cudaMemcpy(static_cast<bf16*>(f->w2) + static_cast<size_t>(l) * FD * FDFF, w.w_fc2,
-                                   static_cast<size_t>(FD) * FDFF * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
-            return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: fc2 copy failed"));
         FusedLayerP& lp = p.layer[l];
         lp.b_qkv = w.b_qkv; lp.b_o1 = w.b_o1; lp.g1 = w.ln1_g; lp.be1 = w.ln1_b;
         lp.b_q = w.b_q; lp.b_o2 = w.b_o2; lp.g2 = w.ln2_g; lp.be2 = w.ln2_b;
@@ -1364,11 +1330,13 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
         for (const float* q : need)
             if (!q) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_create: null bias / LayerNorm parameter"));
     }
-    int rc = cap_gemm::make_tmap(&p.map_w512, f->w512, L * W512_ROWS_PER_LAYER, FD, FD, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, f->w2, L * FD, FDFF, FDFF, 128);
+    void* const w512 = f->stacked->w512;
+    void* const w2 = f->stacked->w2;
+    int rc = cap_gemm::make_tmap(&p.map_w512, w512, L * W512_ROWS_PER_LAYER, FD, FD, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, w2, L * FD, FDFF, FDFF, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, d->w_vocab, d->vocab, FD, FD, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, f->w512, L * W512_ROWS_PER_LAYER, FD, FD, 64);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, f->w2, L * FD, FDFF, FDFF, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, w512, L * W512_ROWS_PER_LAYER, FD, FD, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, w2, L * FD, FDFF, FDFF, 64);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab_h, d->w_vocab, d->vocab, FD, FD, 64);
     if (rc != CAP_OK) return fail(rc);
     p.tokens = d->tokens; p.word_emb = static_cast<const bf16*>(d->word_emb); p.word_pos = d->word_pos; p.pad_idx = d->pad_idx;
@@ -1401,15 +1369,9 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     f->has_att = d->att_in != nullptr;
     f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
     f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
-    f->epi_variant = getenv("OPENVIIC_CHAIN_EPI") ? atoi(getenv("OPENVIIC_CHAIN_EPI")) : 0;
-    if (f->epi_variant < 0 || f->epi_variant > 2) f->epi_variant = 0;
     if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
     return CAP_OK;
@@ -1425,8 +1387,7 @@ extern "C" int cap_fused_get_full_logits(cap_fused_decoder* f) { return f && f->
 
 extern "C" int cap_fused_destroy(cap_fused_decoder* f) {
     if (!f) return CAP_OK;
-    cudaFree(f->w512);
-    cudaFree(f->w2);
+    if (f->owns_stacked) cap_fused_weights_destroy(f->stacked);
     cudaFree(f->base.res);
     cudaFree(f->base.qg);
     cudaFree(f->base.hbuf);
@@ -1497,13 +1458,7 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (f->epi_variant == 1) cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true, 1>, p);
-        else if (f->epi_variant == 2) cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true, 2>, p);
-        else cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
-    } else if (f->epi_variant == 1) {
-        decode_step_fused_kernel<true, false, 1><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
-    } else if (f->epi_variant == 2) {
-        decode_step_fused_kernel<true, false, 2><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+        cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
     } else {
         decode_step_fused_kernel<true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     }

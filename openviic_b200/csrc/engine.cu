@@ -16,10 +16,25 @@
 #include <cmath>
 #include <cstdlib>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
 namespace {
+
+// Device weights (bf16 projections, fp32 biases / LayerNorm parameters / tables).  One set serves every engine
+// created from the same parent (cap_engine_create_shared): N engines pipelining N batches then read ONE copy of the
+// weights -- 48 MB that stay L2-resident under the evict_last hints -- instead of N distinct address ranges.
+struct WeightOwner {
+    std::vector<void*> allocations;
+    cap_fused_weights* stacked = nullptr;   // stacked chain weights (decode_fused.cu), built by the first engine that reserves
+    std::mutex lock;
+    ~WeightOwner() {
+        if (stacked) cap_fused_weights_destroy(stacked);
+        for (void* p : allocations) cudaFree(p);
+    }
+};
 
 struct HostTensor {
     std::vector<float> data;
@@ -68,7 +83,9 @@ struct DecoderLayerW {
 struct cap_engine {
     cap_model_desc desc;
     std::map<std::string, HostTensor> host;
-    std::vector<void*> allocations;
+    std::vector<void*> allocations;            // workspaces, caches (this engine's own)
+    std::shared_ptr<WeightOwner> weights;      // device weights, possibly shared with sibling engines
+    bool alloc_weights = false;                // dev_alloc target: the weight set (finalize) or the workspaces (reserve)
     bool finalized = false;
 
     // weights
@@ -135,7 +152,7 @@ int dev_alloc(cap_engine* e, T** out, size_t count) {
     if (err != cudaSuccess)
         return cap_set_error(CAP_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
                              cudaGetErrorString(err));
-    e->allocations.push_back(p);
+    (e->alloc_weights ? e->weights->allocations : e->allocations).push_back(p);
     *out = static_cast<T*>(p);
     return CAP_OK;
 }
@@ -302,7 +319,27 @@ extern "C" int cap_engine_create(const cap_model_desc* desc, cap_engine** out) {
     }
     cap_engine* e = new cap_engine();
     e->desc = m;
+    e->weights = std::make_shared<WeightOwner>();
     if (const char* env = getenv("OPENVIIC_LN_FUSED")) e->fuse_ln = atoi(env) != 0;
+    *out = e;
+    return CAP_OK;
+}
+
+// A second engine over the SAME device weights (no upload, no copy): its own workspaces, caches, beam state and CUDA
+// graph, so that it can caption another batch concurrently on another stream.  The weight set lives until the last
+// engine that references it is destroyed; `parent` itself may be destroyed first.
+extern "C" int cap_engine_create_shared(cap_engine* parent, cap_engine** out) {
+    CAP_REQUIRE(parent && out, "cap_engine_create_shared: null pointer");
+    CAP_REQUIRE(parent->finalized, "cap_engine_create_shared: finalize the parent first");
+    cap_engine* e = new cap_engine();
+    e->desc = parent->desc;
+    e->weights = parent->weights;
+    e->fuse_ln = parent->fuse_ln;
+    e->vis_proj = parent->vis_proj; e->vocab_fc = parent->vocab_fc; e->enc_ln = parent->enc_ln;
+    e->enc = parent->enc; e->dec = parent->dec;
+    e->geo_w = parent->geo_w; e->geo_b = parent->geo_b; e->d_g = parent->d_g;
+    e->word_emb = parent->word_emb; e->word_pos = parent->word_pos;
+    e->finalized = true;
     *out = e;
     return CAP_OK;
 }
@@ -338,6 +375,8 @@ extern "C" int cap_engine_finalize(cap_engine* e) {
     CAP_REQUIRE(!e->finalized, "cap_engine_finalize: called twice");
     const cap_model_desc& m = e->desc;
     const int d = m.d_model;
+    e->alloc_weights = true;
+    struct Reset { cap_engine* e; ~Reset() { e->alloc_weights = false; } } reset{e};
     CAP_PROPAGATE(make_linear(e, {"vision_embedding.proj"}, m.d_feature, true, &e->vis_proj));
     CAP_PROPAGATE(make_norm(e, "encoder.layer_norm", d, &e->enc_ln));
     e->enc.resize(m.enc_layers);
@@ -484,6 +523,11 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
         fd.cross_kv = e->cross_kv; fd.cross_layer_stride = rows_enc * 2 * hd; fd.enc_mask = e->enc_mask;
         fd.logits = e->logits; fd.ld_logits = e->ld_logits; fd.part_ms = e->part_ms;
         fd.att_in = e->buf_att; fd.q_out = e->buf_q;
+        {   // one stacked copy of the chain weights per weight set, shared by every engine over it
+            std::lock_guard<std::mutex> guard(e->weights->lock);
+            if (!e->weights->stacked) CAP_PROPAGATE(cap_fused_weights_create(layers.data(), m.dec_layers, &e->weights->stacked));
+            fd.stacked = e->weights->stacked;
+        }
         CAP_PROPAGATE(cap_fused_create(&fd, &e->fused));
         e->fused_mode = mode == 1 ? 1 : 2;
     }

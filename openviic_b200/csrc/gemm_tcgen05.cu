@@ -433,6 +433,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
     static cap_device_once smem_once;
     CAP_PROPAGATE(cap_opt_in_smem(smem_once, gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, 200 * 1024));
+    CAP_PROPAGATE(install_fault_buffer());
     const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     if constexpr (CTA2) {
         cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, dim3((tiles_m + 1) / 2 * 2, tiles_n),

@@ -22,11 +22,53 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 
-// Bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// ---- fault records -------------------------------------------------------------------------------------------
+// A bounded wait that times out traps (reported by CUDA as "unspecified launch failure", after which device memory is
+// unreadable).  Before trapping it leaves a record in a pinned, device-mapped HOST buffer (cap_fault_buffer_device in
+// cap_core.cu): WHICH wait it was (the source line of the mbar_wait).  The host can read that buffer after the context
+// has died (cap_fault_records).  One pointer per translation unit, installed per device.
+static __device__ unsigned long long* g_fault_buf = nullptr;
+
+// Deliberately tiny -- one 32-bit store of an immediate (the source line) into the slot line & 63: a record that also
+// carried blockIdx / threadIdx cost the chain kernels 36 bytes of register spills at their 128-register cap.
+static __device__ __forceinline__ void fault_record_and_trap(int line, uint32_t parity) {
+    unsigned long long* buf = g_fault_buf;
+    if (buf != nullptr) {
+        reinterpret_cast<volatile uint32_t*>(buf)[16 + (line & 63)] = static_cast<uint32_t>(line);   // immediate operands only
+        __threadfence_system();
+    }
+    __trap();
+}
+
+// host side: point this translation unit's g_fault_buf at the process-wide buffer, once per device
+}  // namespace cap_ptx
+extern "C" unsigned long long* cap_fault_buffer_device();
+namespace cap_ptx {
+static inline int install_fault_buffer() {
+    static cap_device_once once;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&once.done, __ATOMIC_ACQUIRE) & bit) return CAP_OK;
+    unsigned long long* p = cap_fault_buffer_device();
+    if (p != nullptr) CAP_CHECK_CUDA(cudaMemcpyToSymbol(g_fault_buf, &p, sizeof(p)));
+    __atomic_fetch_or(&once.done, bit, __ATOMIC_RELEASE);
+    return CAP_OK;
+}
+
+// Bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The bound is wall time
+// (%globaltimer, 10 s), not SM cycles: a CTA can legitimately wait long when the GPU is shared or throttled.
+constexpr uint32_t WAIT_LIMIT_TICKS = 10000;   // ticks of 2^20 ns (~1.05 ms): ~10.5 s
+__device__ __forceinline__ uint32_t global_ticks() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return static_cast<uint32_t>(t >> 20);
+}
+
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, int line) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    long long start = 0;
+    uint32_t start = 0;
     for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n"
@@ -38,16 +80,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (spin == 64) start = clock64();
-        if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
+        if (spin == 64) start = global_ticks();
+        if (spin > 64 && (spin & 1023) == 0 && global_ticks() - start > WAIT_LIMIT_TICKS) fault_record_and_trap(line, parity);
     }
 }
 
 // same, acquiring at cluster scope: the arrivals come from the peer CTA of a pair (remote mbarrier.arrive)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster_impl(uint64_t* bar, uint32_t parity, int line) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    long long start = 0;
+    uint32_t start = 0;
     for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n"
@@ -59,10 +101,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (spin == 64) start = clock64();
-        if (spin > 64 && (spin & 1023) == 0 && clock64() - start > 4000000000LL) __trap();
+        if (spin == 64) start = global_ticks();
+        if (spin > 64 && (spin & 1023) == 0 && global_ticks() - start > WAIT_LIMIT_TICKS) fault_record_and_trap(line, parity);
     }
 }
+#define mbar_wait(bar, parity) mbar_wait_impl(bar, parity, __LINE__)
+#define mbar_wait_cluster(bar, parity) mbar_wait_cluster_impl(bar, parity, __LINE__)
 
 // arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster (release at cluster scope)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {

@@ -73,7 +73,10 @@ def _check_out(out, b: int, out_size: int, max_len: int, where: str, device=None
 class CaptionEngine:
     """One engine per GPU / rank: weights as bf16, workspaces, KV caches, beam state, CUDA graph."""
 
-    def __init__(self, model_cfg, vocab, state_dict: Dict[str, torch.Tensor], device="cuda"):
+    def __init__(self, model_cfg, vocab, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda",
+                 share_weights_with: Optional["CaptionEngine"] = None):
+        """``share_weights_with``: another engine of the same model on the same device whose device weights this one
+        uses (``state_dict`` is then ignored): no upload, and concurrent engines read one L2-resident weight set."""
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("CaptionEngine needs a CUDA device (there is no CPU fallback)")
@@ -83,6 +86,12 @@ class CaptionEngine:
         self.max_len = vocab.max_caption_length
         self._h = C.c_void_p()
         self.reserved: Optional[Tuple[int, int, int]] = None
+        if share_weights_with is not None:
+            if share_weights_with.device != self.device:
+                raise ValueError("share_weights_with: the parent engine lives on another device")
+            with torch.cuda.device(self.device):
+                cabi.call("cap_engine_create_shared", share_weights_with._h, C.byref(self._h))
+            return
         with torch.cuda.device(self.device):
             cabi.call("cap_engine_create", C.byref(self.desc), C.byref(self._h))
             for name, tensor in state_dict.items():
@@ -92,6 +101,18 @@ class CaptionEngine:
                 shape = (C.c_int64 * host.dim())(*host.shape)
                 cabi.call("cap_engine_load_weight", self._h, name.encode(), host.data_ptr(), shape, host.dim())
             cabi.call("cap_engine_finalize", self._h)
+
+    def clone(self) -> "CaptionEngine":
+        """A further engine over this engine's device weights, reserved like this one: for captioning independent
+        batches concurrently on several streams."""
+        other = CaptionEngine.__new__(CaptionEngine)
+        other.device, other.desc, other.max_len = self.device, self.desc, self.max_len
+        other._h, other.reserved = C.c_void_p(), None
+        with torch.cuda.device(self.device):
+            cabi.call("cap_engine_create_shared", self._h, C.byref(other._h))
+        if self.reserved is not None:
+            other.reserve(*self.reserved)
+        return other
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):

@@ -41,16 +41,3 @@ def make_items(field, feats, boxes, device):
     if boxes is not None:
         items.set("region_boxes", boxes.to(device))
     return items
-
-
-def explain_caption_mismatches(ids, ref_ids, ref_trace_logits, tol):
-    """Every caption must either equal the reference's or diverge first at a near-tie.
-
-    Returns (n_equal, n_total, worst_gap).  ``worst_gap`` is the largest reference log-prob gap
-    between the reference's token and ours at the first divergence of a mismatching caption.
-    """
-    n_equal, worst = 0, 0.0
-    for b in range(ids.shape[0]):
-        if np.array_equal(ids[b], ref_ids[b]):
-            n_equal += 1
-    return n_equal, ids.shape[0], worst

@@ -13,9 +13,6 @@ step() {   # step <name> <timeout-seconds> <command...>
     timeout "$limit" "$@" > "$OUT/$name.out" 2> "$OUT/$name.err"
     echo "   rc=$? $(( $(date +%s) - t0 ))s ($(tail -c 400 "$OUT/$name.out" | tr '\n' ' '))" | tee -a $LOG
 }
-export CUDA_ENABLE_COREDUMP_ON_EXCEPTION=1
-export CUDA_COREDUMP_FILE=$PWD/$OUT/core_%h_%p
-export CUDA_COREDUMP_GENERATION_FLAGS=skip_global_memory,skip_shared_memory,skip_local_memory,skip_constbank_memory
 step tests_gpu 600 python -m pytest tests -x -q -m gpu
 step stress_default 400 python tools/stress.py --iters 150 --seconds 120
 step bench_default 300 python bench.py --steps 20 --warmup 5

@@ -22,7 +22,7 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import bench
-from openviic_b200 import CaptionEngine, synthetic
+from openviic_b200 import synthetic
 
 
 def main():
@@ -40,13 +40,7 @@ def main():
     batch = args.batch or per_gpu_batch
     cfg, vocab, model, weights = bench.build_model(args.workload, dev)
     eng0 = model.engine(batch, n, bench.BEAM)
-    host_weights = {k: v.detach().to("cpu", torch.float32) if torch.is_tensor(v) and v.dtype.is_floating_point else v
-                    for k, v in model.state_dict().items()}
-    engines = [eng0]
-    for _ in range(args.streams - 1):
-        e = CaptionEngine(cfg.MODEL, vocab, host_weights, dev)
-        e.reserve(batch, n, bench.BEAM)
-        engines.append(e)
+    engines = [eng0] + [eng0.clone() for _ in range(args.streams - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)]
     needs_boxes = synthetic.needs_boxes(cfg.MODEL)
     n_sets = 4
@@ -103,7 +97,8 @@ def main():
             if args.seconds > 0 and time.perf_counter() - t0 > args.seconds:
                 break
     except RuntimeError as err:   # a CUDA fault is sticky: report and leave
-        fault = f"iteration {done}: {err}"
+        from openviic_b200 import cabi
+        fault = f"iteration {done}: {err}; timed-out waits at source lines {cabi.fault_records()}"
     out = {"tool": "stress", "workload": args.workload, "batch": batch, "streams": args.streams, "iters_done": done,
            "captions_checked": done * args.streams * batch, "mismatches": len(mism), "first_mismatches": mism[:8],
            "fault": fault, "seconds": time.perf_counter() - t0,
