@@ -1036,6 +1036,203 @@ int launch_cross_tc(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_m
     return cap_check_launch("decode_cross_attention_tc_kernel");
 }
 
+// Decode-step cross-attention, streamed (default since round 2; H = 8).  The tensor-path kernel above runs one CTA
+// per image: load 100 KB, wait, compute, exit -- nothing overlaps inside a CTA, and its 256 CTAs hold 200 KB of
+// shared memory on 128 SMs for the whole launch (12 us for 25.7 MB of K|V = 2.1 TB/s alone on the GPU).  Here a CTA is
+// a small pipeline: a PRODUCER warp streams image after image into a ring of shared-memory stages (one cp.async.bulk
+// per 2 KB K|V row, one mbarrier phase per image), eight CONSUMER warps (one per head) run the same mma.sync
+// arithmetic on the stage that has landed while the next image is in flight, and hand the stage back through an
+// "empty" barrier.  A quarter of the CTAs (4 images each) then move the same bytes: the launch costs a fraction of
+// the SM-time, which is what the pipelined regime (32 batches in flight) is short of.
+constexpr int XA_CONSUMERS = 8;                       // one warp per head
+constexpr int XA_THREADS = (XA_CONSUMERS + 1) * 32;   // + the producer warp
+constexpr int XA_MAX_STAGES = 4;
+constexpr int XA_IMAGES_PER_CTA = 4;
+
+template <int NT>   // 8-key tiles: 7 (n <= 56) or 13 (n <= 104)
+__global__ void __launch_bounds__(XA_THREADS, 1)
+decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
+                                     const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int beams, int n,
+                                     float scale, int n_images, int stages, uint32_t stage_bytes) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) uint8_t xa_smem[];   // [stages][n rows at XT_PITCH], zero row, [stages][NT*8] mask, barriers
+    uint8_t* zero_row = xa_smem + static_cast<size_t>(stages) * stage_bytes;
+    uint8_t* smask = zero_row + XT_PITCH;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smask + XA_MAX_STAGES * NT * 8);
+    uint64_t* empty = full + XA_MAX_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            cap_ptx::mbar_init(&full[s], 1);
+            cap_ptx::mbar_init(&empty[s], XA_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < XT_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zero_row)[i] = 0u;
+    __syncthreads();
+
+    if (warp == XA_CONSUMERS) {
+        // ------------------------------------------------------------------ producer
+        // K|V were projected at encode time and a serialising launch separates encode from decode: safe to stream
+        // before (without) the PDL wait.  Read once per step: evict-first, the weights keep their place in L2.
+        const uint64_t stream_policy = cap_ptx::l2_policy_evict_first();
+        int it = 0;
+        for (int img = blockIdx.x; img < n_images; img += gridDim.x, ++it) {
+            const int s = it % stages;
+            const uint32_t use = static_cast<uint32_t>(it / stages);
+            if (use > 0) cap_ptx::mbar_wait(&empty[s], (use - 1) & 1);   // every consumer is done with the stage's last image
+            uint8_t* mk = smask + s * NT * 8;
+            for (int j = lane; j < NT * 8; j += 32)
+                mk[j] = (j >= n || (key_mask != nullptr && key_mask[static_cast<size_t>(img) * n + j])) ? 1 : 0;
+            __syncwarp();
+            if (lane == 0) cap_ptx::mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(n) * 2048u);   // release: mask visible
+            __syncwarp();
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + static_cast<size_t>(img) * n * 2048;
+            uint8_t* dst = xa_smem + static_cast<size_t>(s) * stage_bytes;
+            for (int r = lane; r < n; r += 32)
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                        xs_smem_u32(dst + static_cast<size_t>(r) * XT_PITCH)),
+                    "l"(reinterpret_cast<uint64_t>(src + static_cast<size_t>(r) * 2048)), "r"(2048u), "r"(xs_smem_u32(&full[s])),
+                    "l"(stream_policy)
+                    : "memory");
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers: warp = head
+    const int g = lane >> 2, t = lane & 3;
+    const int h = warp;
+    const float sc = scale * 1.4426950408889634f;
+    const int mi = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of 8x8 matrix mi of an x4 load
+    pdl_wait();   // q comes from the previous kernel; out is read by nothing that is still running
+    // A operand of S = Q.K^T: rows g < beams of the image's queries, head h; rows 8..15 of the m16 tile are zero
+    auto load_q = [&](int img, uint32_t (&qa)[4][4]) {
+        const bf16* qrow = q + static_cast<size_t>(img * beams + (g < beams ? g : 0)) * ldq + h * HEAD_DIM + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t lo = *reinterpret_cast<const uint32_t*>(qrow + ks * 16);
+            const uint32_t hi = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8);
+            qa[ks][0] = g < beams ? lo : 0u;
+            qa[ks][1] = 0u;
+            qa[ks][2] = g < beams ? hi : 0u;
+            qa[ks][3] = 0u;
+        }
+    };
+    uint32_t qa[4][4];
+    if (blockIdx.x < n_images) load_q(blockIdx.x, qa);
+    int it = 0;
+    for (int img = blockIdx.x; img < n_images; img += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t use = static_cast<uint32_t>(it / stages);
+        uint32_t qn[4][4];   // the next image's queries are requested before this image's arithmetic
+        const int next = img + gridDim.x;
+        if (next < n_images) load_q(next, qn);
+        cap_ptx::mbar_wait(&full[s], use & 1);
+        const uint8_t* st = xa_smem + static_cast<size_t>(s) * stage_bytes;
+        const uint8_t* mk = smask + s * NT * 8;
+        // S = Q.K^T
+        float sv[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            sv[nt][0] = sv[nt][1] = sv[nt][2] = sv[nt][3] = 0.f;
+            const int key = nt * 8 + g;
+            const uint8_t* krow = (key < n ? st + static_cast<size_t>(key) * XT_PITCH : zero_row) + h * (HEAD_DIM * 2) + 4 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_16816(sv[nt], qa[ks], *reinterpret_cast<const uint32_t*>(krow + ks * 32),
+                               *reinterpret_cast<const uint32_t*>(krow + ks * 32 + 16));
+        }
+        // softmax over the keys of row g (log2 domain); a quad holds one row
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float x = mk[nt * 8 + 2 * t + e] ? -INFINITY : sv[nt][e] * sc;
+                sv[nt][e] = x;
+                mx = fmaxf(mx, x);
+            }
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float p = (mx == -INFINITY) ? 0.f : exp2f(sv[nt][e] - mx);
+                sv[nt][e] = p;
+                sum += p;
+            }
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        // O = P.V : two 8-key score tiles are the A operand of one 16-key step; V fragments by ldmatrix.trans
+        float o[8][4];
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < (NT + 1) / 2; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(sv[2 * kk][0], sv[2 * kk][1]);
+            pa[1] = 0u;
+            pa[2] = (2 * kk + 1 < NT) ? pack_bf16x2(sv[2 * kk + 1 < NT ? 2 * kk + 1 : 0][0], sv[2 * kk + 1 < NT ? 2 * kk + 1 : 0][1]) : 0u;
+            pa[3] = 0u;
+            const int key = kk * 16 + (mi & 1) * 8 + mr;
+            const uint8_t* vrow = (key < n ? st + static_cast<size_t>(key) * XT_PITCH : zero_row) + 1024 + h * (HEAD_DIM * 2) +
+                                  (mi >> 1) * 16;
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t vb[4];
+                ldmatrix_x4_trans(vb, xs_smem_u32(vrow + dp * 32));
+                mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+            }
+        }
+        __syncwarp();   // every lane's shared-memory reads of the stage are done
+        if (lane == 0) cap_ptx::mbar_arrive(&empty[s]);
+        if (g < beams) {
+            const float inv = sum > 0.f ? 1.f / sum : 0.f;
+            bf16* orow = out + static_cast<size_t>(img * beams + g) * ldo + h * HEAD_DIM + 2 * t;
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt)
+                *reinterpret_cast<bf162*>(orow + dt * 8) = __floats2bfloat162_rn(o[dt][0] * inv, o[dt][1] * inv);
+        }
+        if (next < n_images) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                qa[ks][0] = qn[ks][0];
+                qa[ks][2] = qn[ks][2];
+            }
+        }
+    }
+}
+
+template <int NT>
+int launch_cross_stream(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int beams,
+                        int n, float scale, cudaStream_t stream) {
+    const uint32_t stage_bytes = static_cast<uint32_t>(n) * XT_PITCH;
+    const size_t fixed = XT_PITCH + XA_MAX_STAGES * NT * 8 + 2 * XA_MAX_STAGES * 8;
+    const size_t budget = 226 * 1024;
+    int stages = static_cast<int>((budget - fixed) / stage_bytes);
+    if (stages < 1) return cap_set_error(CAP_ERR_INVALID, "cap_decode_cross_attention: %d keys do not fit shared memory", n);
+    static const int env_stages = getenv("OPENVIIC_XATTN_STAGES") ? atoi(getenv("OPENVIIC_XATTN_STAGES")) : 0;   // tuning
+    static const int env_per_cta = getenv("OPENVIIC_XATTN_IMAGES") ? atoi(getenv("OPENVIIC_XATTN_IMAGES")) : 0;
+    stages = std::min(stages, env_stages > 0 ? env_stages : XA_MAX_STAGES);
+    const int per_cta = env_per_cta > 0 ? env_per_cta : (stages > 1 ? XA_IMAGES_PER_CTA : 1);
+    const int grid = std::max(1, (B + per_cta - 1) / per_cta);
+    stages = std::min(stages, (B + grid - 1) / grid);   // never more stages than images per CTA
+    const size_t smem = static_cast<size_t>(stages) * stage_bytes + fixed;
+    static cap_device_once smem_once;
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_stream_kernel<NT>, 227 * 1024));
+    CAP_PROPAGATE(cap_ptx::install_fault_buffer());
+    CAP_LAUNCH((decode_cross_attention_stream_kernel<NT>), grid, XA_THREADS, smem, stream, q, ldq, kv, key_mask, out, ldo, beams,
+               n, scale, B, stages, stage_bytes);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("decode_cross_attention_stream_kernel");
+}
+
 template <int BEAMS>
 int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
                       float scale, cudaStream_t stream) {
@@ -1265,7 +1462,12 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         static const bool no_bulk = getenv("OPENVIIC_CROSS_NO_BULK") != nullptr;
         const char* tc_env = getenv("OPENVIIC_CROSS_TC");   // read per call: a probe compares both paths in one process
-        const bool tensor_path = !(tc_env && atoi(tc_env) == 0);   // default since round 2: 85.2 k -> 96.1 k captions/s
+        const int tc_mode = tc_env ? atoi(tc_env) : 2;   // 0 CUDA cores, 1 tensor path one CTA per image, 2 streamed (default)
+        const bool tensor_path = tc_mode != 0;
+        if (tc_mode == 2 && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
+            if (n <= 56) return launch_cross_stream<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
+            return launch_cross_stream<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
+        }
         if (tensor_path && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
             if (n <= 56) return launch_cross_tc<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
             return launch_cross_tc<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
