@@ -39,7 +39,7 @@ extern "C" {
 typedef void* cap_stream_t; /* cudaStream_t */
 
 enum cap_dtype { CAP_BF16 = 0, CAP_F32 = 1 };
-enum cap_activation { CAP_ACT_NONE = 0, CAP_ACT_RELU = 1, CAP_ACT_SIGMOID = 2 };
+enum cap_activation { CAP_ACT_NONE = 0, CAP_ACT_RELU = 1, CAP_ACT_SIGMOID = 2, CAP_ACT_LEAKY_RELU = 3 /* slope 0.01 */ };
 
 int cap_abi_version(void);
 const char* cap_last_error(void);
@@ -133,6 +133,11 @@ int cap_decode_self_attention(const void* qkv, const int32_t* ancestry, const ui
 int cap_decode_cross_attention(const void* q, int ldq, const void* kv, const uint8_t* key_mask,
                                void* out, int ldo, int B, int beam, int n, int H, float scale,
                                cap_stream_t stream);
+/* The same queries over `levels` encoder levels in one launch (MeshedDecoderLayer, decoders.py:55-57): level i reads
+ * kv + i * kv_level_stride elements and writes out + i * out_level_stride elements. */
+int cap_decode_cross_attention_levels(const void* q, int ldq, const void* kv, size_t kv_level_stride,
+                                      const uint8_t* key_mask, void* out, int ldo, size_t out_level_stride, int B,
+                                      int beam, int n, int H, int levels, float scale, cap_stream_t stream);
 
 /* x[r,:] = word_emb[token[r],:] + pos_table[position,:] (bf16 out); padflag_out[r] = token==pad.
  * Replaces models/modules/decoders.py:105-112 (stateful: position = t+1 for every row). */
@@ -187,18 +192,22 @@ const float* cap_beam_seq_logprob(cap_beam* h); /* [R]                          
 const int32_t* cap_beam_parents(cap_beam* h);   /* [R]    selected_beam of the last step     */
 
 /* ------------------------------------------------------------------------------------------
- * Fused decode step (csrc/decode_fused.cu): ONE kernel per BaseTransformer.step of the standard
- * Decoder (decoders.py:95-123 at nq = 1) -- every CTA carries a tile of 128 beam rows through
- * embedding, all DecoderLayers (decoders.py:21-28) and the vocabulary projection with its
- * log-softmax chunk statistics.  All pointers are DEVICE memory owned by the caller (the engine);
- * the handle owns stacked copies of the weights and its scratch tiles.  Needs d_model 512, 8 heads,
- * d_ff 2048, beam <= 5, bias-free vocabulary projection.
+ * GEMM chains of a decode step (csrc/decode_fused.cu): BaseTransformer.step of the standard Decoder and of the
+ * MeshedDecoder (decoders.py:95-123, 145-173 at nq = 1) as 1 + 2 * layers launches per step -- every CTA (pair)
+ * carries a tile of 128 beam rows through a list of projection GEMMs with fused epilogues (bias, ReLU, residual +
+ * LayerNorm, meshed gates + mix, vocabulary log-softmax statistics), the stand-alone attention kernels run between
+ * the chains.  All pointers are DEVICE memory owned by the caller (the engine); the handle owns its scratch tiles and
+ * (unless `stacked` is given) stacked copies of the weights.  Needs d_model 512, 8 heads, d_ff 2048, beam <= 5,
+ * bias-free vocabulary projection; the meshed decoder with 3 encoder levels.
  * ------------------------------------------------------------------------------------------ */
 typedef struct cap_fused_layer {
     const void *w_qkv, *w_o1, *w_q, *w_o2, *w_fc1, *w_fc2; /* bf16 [out,in]: self q|k|v, self fc_o, cross fc_q, cross fc_o, fc1, fc2 */
     const float *b_qkv, *b_o1, *ln1_g, *ln1_b;             /* self-attention biases + its LayerNorm */
     const float *b_q, *b_o2, *ln2_g, *ln2_b;               /* cross-attention */
     const float *b_fc1, *b_fc2, *ln3_g, *ln3_b;            /* feed-forward */
+    int n_levels;                                          /* 0: DecoderLayer; 3: MeshedDecoderLayer (decoders.py:31-73) */
+    const void* w_alpha[3];                                /* bf16 [d_model, 2 * d_model]: fc_alphas.i over [self_att ; enc_att_i] */
+    const float* b_alpha[3];
 } cap_fused_layer;
 
 /* Stacked bf16 copies of the decoder's projection weights (one TMA tensor map then serves every GEMM of a chain).
@@ -216,17 +225,12 @@ typedef struct cap_fused_desc {
     const void* word_emb;         /* bf16 [vocab, d_model] */
     const float* word_pos;        /* fp32 [max_len + 1, d_model] */
     const int32_t* tokens;        /* [R]    cap_beam_tokens */
-    const int32_t* ancestry;      /* [T][R] cap_beam_ancestry */
     uint8_t* padflag;             /* [T][R] written at step t, read at later steps */
     void* qkv_cache;              /* bf16 [layers][T][R][3*d_model] */
-    const void* cross_kv;         /* bf16, layer l at + l*cross_layer_stride elements: [B][n][K|V] */
-    size_t cross_layer_stride;
-    const uint8_t* enc_mask;      /* [B][n] key padding */
     float* logits;                /* fp32 [R][ld_logits], ld_logits % 32 == 0 */
     int ld_logits;
     float* part_ms;               /* fp32 [R][8*ceil(vocab/256)][2] */
-    /* chain mode only (cap_fused_chain), else NULL: */
-    const void* att_in;           /* bf16 [max_rows][d_model]: output of cap_decode_{self,cross}_attention */
+    const void* att_in;           /* bf16 [max(levels,1)][max_rows][d_model]: outputs of cap_decode_{self,cross}_attention */
     void* q_out;                  /* bf16 [max_rows][d_model]: queries for cap_decode_cross_attention */
     const cap_fused_weights* stacked; /* NULL: the handle builds and owns its own stacked copies of `layers` */
 } cap_fused_desc;
@@ -234,15 +238,13 @@ typedef struct cap_fused_desc {
 typedef struct cap_fused_decoder cap_fused_decoder;
 int cap_fused_create(const cap_fused_desc* desc, cap_fused_decoder** out);
 int cap_fused_destroy(cap_fused_decoder* f);
-/* Step t for B images (R = B*beam rows, n_keys visual tokens): fills qkv_cache[.][t], padflag[t], logits and
- * part_ms; follow with cap_beam_step_stats. */
-int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_keys, cap_stream_t stream);
-/* The same step as three kinds of GEMM chains with the stand-alone attention kernels in between -- the default
- * decode path: the chains keep the tensor pipe of "their" SM busy, the attention kernels (low IPC, latency
- * bound) share SMs with whatever else is in flight instead of monopolising one.  Per step:
- *   EMBED_QKV(0); for each layer L: cap_decode_self_attention -> SELF_OUT(L) -> cap_decode_cross_attention ->
- *   FFN(L); then cap_beam_step_stats.  FFN(L) ends with layer L+1's q|k|v projection, FFN(last) with the
- *   vocabulary projection + chunk statistics. */
+/* One chain of step t for B images (R = B*beam rows).  Per step:
+ *   EMBED_QKV(0); for each layer L: cap_decode_self_attention -> SELF_OUT(L) -> cap_decode_cross_attention (one per
+ *   encoder level, level i into att_in[i]) -> FFN(L); then cap_beam_step_stats.
+ * EMBED_QKV: x = Emb[token] + pos, q|k|v of layer 0 into the cache slot of step t.  SELF_OUT(L): self fc_o + LN,
+ * cross fc_q -> q_out (meshed: + the gates' self-attention part).  FFN(L): cross fc_o + LN (meshed: per level, then
+ * gate and mix), fc1, fc2 + LN, and layer L+1's q|k|v projection or, after the last layer, the vocabulary projection
+ * with its chunk statistics. */
 enum cap_fused_chain_kind { CAP_CHAIN_EMBED_QKV = 0, CAP_CHAIN_SELF_OUT = 1, CAP_CHAIN_FFN = 2 };
 int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t, int B, cap_stream_t stream);
 /* By default the vocabulary epilogue of the chains stores only the 32-column groups of logits that can contain one
@@ -250,10 +252,13 @@ int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t, int B, ca
  * views, cap_engine_decode_logits; OPENVIIC_FULL_LOGITS=1 sets it at creation). */
 int cap_fused_set_full_logits(cap_fused_decoder* f, int on);
 int cap_fused_get_full_logits(cap_fused_decoder* f);
-/* Debug: when non-NULL, every later fused step writes %globaltimer stamps (ns) of its phase boundaries into
- * device_buffer[tile*64 + k]: 0 entry, 1 dependencies resolved, then per layer L at 2+8L: layer start,
- * q|k|v stored, self-attention done, LN1 done, cross q stored, cross-attention done, LN2 done, hidden stored;
- * 2+8*layers: last LN done, 3+8*layers: vocabulary epilogue done. */
+/* Debug: when non-NULL (3 * 6 * 64 * 64 words of device memory), every later chain launch runs a tracing
+ * instantiation that writes, for chain kind c and layer l, into region (c * 6 + l) * 4096 + tile * 64 + k:
+ *   k = 0..4   issuer warp, SM clock cycles: total, waiting for weight stages, for free accumulators (epilogues),
+ *              for the A tile, for streamed A blocks;
+ *   k = 8..10  producer warp: total, waiting for free ring stages, for the hidden tile / free A slots;
+ *   k = 40..47 %globaltimer stamps (ns) of the epilogue of fc1's fourth 256-column chunk: entry, bias staged,
+ *              accumulator ready, the four 32-column groups stored, accumulator released. */
 int cap_debug_fused_trace(unsigned long long* device_buffer);
 
 /* ------------------------------------------------------------------------------------------

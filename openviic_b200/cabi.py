@@ -13,7 +13,7 @@ from typing import Optional
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libopenviic_cap.so"
 
 CAP_BF16, CAP_F32 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_LEAKY_RELU = 0, 1, 2, 3
 ENC_PLAIN, ENC_MULTILEVEL, ENC_GEOMETRIC = 0, 1, 2
 ATT_SDPA, ATT_GEOMETRY, ATT_MEMORY = 0, 1, 2
 DEC_PLAIN, DEC_MESHED = 0, 1
@@ -59,6 +59,7 @@ SIGNATURES = {
     "cap_attention": (_i, [C.POINTER(AttentionArgs), _vp]),
     "cap_decode_self_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "cap_decode_cross_attention": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cap_decode_cross_attention_levels": (_i, [_vp, _i, _vp, C.c_size_t, _vp, _vp, _i, C.c_size_t, _i, _i, _i, _i, _i, _f, _vp]),
     "cap_embed_tokens": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "cap_meshed_mix": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "cap_aoa_gate": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
@@ -79,7 +80,6 @@ SIGNATURES = {
     "cap_fused_weights_destroy": (_i, [_vp]),
     "cap_fused_create": (_i, [_vp, C.POINTER(_vp)]),
     "cap_fused_destroy": (_i, [_vp]),
-    "cap_fused_decode_step": (_i, [_vp, _i, _i, _i, _vp]),
     "cap_debug_fused_trace": (_i, [_vp]),
     "cap_fused_set_full_logits": (_i, [_vp, _i]),
     "cap_fused_get_full_logits": (_i, [_vp]),

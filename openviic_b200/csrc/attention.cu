@@ -1053,8 +1053,12 @@ template <int NT>   // 8-key tiles: 7 (n <= 56) or 13 (n <= 104)
 __global__ void __launch_bounds__(XA_THREADS, 1)
 decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
                                      const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int beams, int n,
-                                     float scale, int n_images, int stages, uint32_t stage_bytes) {
+                                     float scale, int n_images, int stages, uint32_t stage_bytes, int levels,
+                                     size_t kv_level_stride, size_t out_level_stride) {
+    // `levels` > 1 (meshed decoder, decoders.py:55-57): the same queries attend to the K|V of several encoder levels;
+    // virtual image v = level * n_images + image reads kv + level * kv_level_stride, writes out + level * out_level_stride
     pdl_launch_dependents();
+    const int n_virtual = n_images * levels;
     extern __shared__ __align__(128) uint8_t xa_smem[];   // [stages][n rows at XT_PITCH], zero row, [stages][NT*8] mask, barriers
     uint8_t* zero_row = xa_smem + static_cast<size_t>(stages) * stage_bytes;
     uint8_t* smask = zero_row + XT_PITCH;
@@ -1077,7 +1081,8 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
         // before (without) the PDL wait.  Read once per step: evict-first, the weights keep their place in L2.
         const uint64_t stream_policy = cap_ptx::l2_policy_evict_first();
         int it = 0;
-        for (int img = blockIdx.x; img < n_images; img += gridDim.x, ++it) {
+        for (int vi = blockIdx.x; vi < n_virtual; vi += gridDim.x, ++it) {
+            const int img = vi % n_images, lvl = vi / n_images;
             const int s = it % stages;
             const uint32_t use = static_cast<uint32_t>(it / stages);
             if (use > 0) cap_ptx::mbar_wait(&empty[s], (use - 1) & 1);   // every consumer is done with the stage's last image
@@ -1087,7 +1092,7 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
             __syncwarp();
             if (lane == 0) cap_ptx::mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(n) * 2048u);   // release: mask visible
             __syncwarp();
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + static_cast<size_t>(img) * n * 2048;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(kv + lvl * kv_level_stride) + static_cast<size_t>(img) * n * 2048;
             uint8_t* dst = xa_smem + static_cast<size_t>(s) * stage_bytes;
             for (int r = lane; r < n; r += 32)
                 asm volatile(
@@ -1120,14 +1125,15 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
         }
     };
     uint32_t qa[4][4];
-    if (blockIdx.x < n_images) load_q(blockIdx.x, qa);
+    if (blockIdx.x < n_virtual) load_q(blockIdx.x % n_images, qa);
     int it = 0;
-    for (int img = blockIdx.x; img < n_images; img += gridDim.x, ++it) {
+    for (int vi = blockIdx.x; vi < n_virtual; vi += gridDim.x, ++it) {
+        const int img = vi % n_images, lvl = vi / n_images;
         const int s = it % stages;
         const uint32_t use = static_cast<uint32_t>(it / stages);
         uint32_t qn[4][4];   // the next image's queries are requested before this image's arithmetic
-        const int next = img + gridDim.x;
-        if (next < n_images) load_q(next, qn);
+        const int next = vi + gridDim.x;
+        if (next < n_virtual) load_q(next % n_images, qn);
         cap_ptx::mbar_wait(&full[s], use & 1);
         const uint8_t* st = xa_smem + static_cast<size_t>(s) * stage_bytes;
         const uint8_t* mk = smask + s * NT * 8;
@@ -1194,12 +1200,12 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
         if (lane == 0) cap_ptx::mbar_arrive(&empty[s]);
         if (g < beams) {
             const float inv = sum > 0.f ? 1.f / sum : 0.f;
-            bf16* orow = out + static_cast<size_t>(img * beams + g) * ldo + h * HEAD_DIM + 2 * t;
+            bf16* orow = out + lvl * out_level_stride + static_cast<size_t>(img * beams + g) * ldo + h * HEAD_DIM + 2 * t;
 #pragma unroll
             for (int dt = 0; dt < 8; ++dt)
                 *reinterpret_cast<bf162*>(orow + dt * 8) = __floats2bfloat162_rn(o[dt][0] * inv, o[dt][1] * inv);
         }
-        if (next < n_images) {
+        if (next < n_virtual) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 qa[ks][0] = qn[ks][0];
@@ -1211,7 +1217,8 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
 
 template <int NT>
 int launch_cross_stream(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int beams,
-                        int n, float scale, cudaStream_t stream) {
+                        int n, float scale, cudaStream_t stream, int levels = 1, size_t kv_level_stride = 0,
+                        size_t out_level_stride = 0) {
     const uint32_t stage_bytes = static_cast<uint32_t>(n) * XT_PITCH;
     const size_t fixed = XT_PITCH + XA_MAX_STAGES * NT * 8 + 2 * XA_MAX_STAGES * 8;
     const size_t budget = 226 * 1024;
@@ -1221,14 +1228,15 @@ int launch_cross_stream(const bf16* q, int ldq, const bf16* kv, const uint8_t* k
     static const int env_per_cta = getenv("OPENVIIC_XATTN_IMAGES") ? atoi(getenv("OPENVIIC_XATTN_IMAGES")) : 0;
     stages = std::min(stages, env_stages > 0 ? env_stages : XA_MAX_STAGES);
     const int per_cta = env_per_cta > 0 ? env_per_cta : (stages > 1 ? XA_IMAGES_PER_CTA : 1);
-    const int grid = std::max(1, (B + per_cta - 1) / per_cta);
-    stages = std::min(stages, (B + grid - 1) / grid);   // never more stages than images per CTA
+    const int n_virtual = B * levels;
+    const int grid = std::max(1, (n_virtual + per_cta - 1) / per_cta);
+    stages = std::min(stages, (n_virtual + grid - 1) / grid);   // never more stages than images per CTA
     const size_t smem = static_cast<size_t>(stages) * stage_bytes + fixed;
     static cap_device_once smem_once;
     CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_stream_kernel<NT>, 227 * 1024));
     CAP_PROPAGATE(cap_ptx::install_fault_buffer());
     CAP_LAUNCH((decode_cross_attention_stream_kernel<NT>), grid, XA_THREADS, smem, stream, q, ldq, kv, key_mask, out, ldo, beams,
-               n, scale, B, stages, stage_bytes);
+               n, scale, B, stages, stage_bytes, levels, kv_level_stride, out_level_stride);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_cross_attention_stream_kernel");
 }
@@ -1503,6 +1511,30 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
     a.B = B; a.H = H; a.nq = beam; a.nk = n;
     a.scale = scale;
     return launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+// Cross-attention of the same queries over several encoder levels in one launch (MeshedDecoderLayer, decoders.py:55-57):
+// level i reads kv + i * kv_level_stride elements ([B][n][K|V]) and writes out + i * out_level_stride elements.
+extern "C" int cap_decode_cross_attention_levels(const void* q, int ldq, const void* kv, size_t kv_level_stride,
+                                                 const uint8_t* key_mask, void* out, int ldo, size_t out_level_stride, int B,
+                                                 int beam, int n, int H, int levels, float scale, cap_stream_t stream) {
+    CAP_REQUIRE(q && kv && out, "cap_decode_cross_attention_levels: null pointer");
+    CAP_REQUIRE(B > 0 && beam > 0 && n > 0 && n <= MAX_KEYS && H > 0 && levels >= 1, "cap_decode_cross_attention_levels: bad shape");
+    const char* tc_env = getenv("OPENVIIC_CROSS_TC");
+    const bool streamed = (tc_env ? atoi(tc_env) : 2) == 2;
+    if (streamed && H == 8 && beam <= 8 && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0 &&
+        (kv_level_stride * 2) % 16 == 0) {
+        const bf16* qp = static_cast<const bf16*>(q);
+        const bf16* kvp = static_cast<const bf16*>(kv);
+        bf16* op = static_cast<bf16*>(out);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (n <= 56) return launch_cross_stream<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s, levels, kv_level_stride, out_level_stride);
+        return launch_cross_stream<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s, levels, kv_level_stride, out_level_stride);
+    }
+    for (int i = 0; i < levels; ++i)   // other shapes: one launch per level
+        CAP_PROPAGATE(cap_decode_cross_attention(q, ldq, static_cast<const bf16*>(kv) + i * kv_level_stride, key_mask,
+                                                 static_cast<bf16*>(out) + i * out_level_stride, ldo, B, beam, n, H, scale, stream));
+    return CAP_OK;
 }
 
 extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestry, const uint8_t* padflag, void* out,

@@ -1,27 +1,39 @@
-// One decode step of the standard caption decoder as ONE kernel: every CTA owns a tile of 128 beam rows and
-// carries it through token embedding, the decoder layers (decoders.py:21-28: self-attention, cross-attention,
-// position-wise feed-forward, each followed by residual + LayerNorm) and the vocabulary projection with its
-// log-softmax chunk statistics (decoders.py:121-123).  Rows never interact inside a step (beams interact only
-// in the selection, beam.cu), so there is no grid-wide dependency: nothing but the weights is shared between
-// CTAs, and the ~37 dependent launches of the per-operator path collapse into one.
+// GEMM chains of a caption decode step on tcgen05: a CTA (or a pair of CTAs) owns a tile of 128 beam rows and carries
+// it through a LIST OF JOBS -- projection GEMMs with their epilogues (bias / ReLU / residual + LayerNorm / meshed gates
+// / log-softmax chunk statistics) -- without the activations leaving the SM between them.  Rows never interact inside
+// a step (beams interact only in the selection, beam.cu), so there is no grid-wide dependency: nothing but the weights
+// is shared between CTAs.  The attention kernels (attention.cu) run between the chains.
+//
+// Reference operators covered by the job lists (cap_fused_chain builds them):
+//   token embedding                        decoders.py:105-112
+//   q|k|v, fc_o + residual + LayerNorm     attentions.py:44-58, 296-309
+//   cross fc_q                             attentions.py:51 (queries of decoders.py:23,56)
+//   meshed gates + mix                     decoders.py:55-67   (MeshedDecoderLayer)
+//   fc1 -> ReLU -> fc2 + residual + LN     positionwise_feed_forward.py:23-28, zero rows fed <pad> decoders.py:26
+//   vocabulary projection (+ statistics)   decoders.py:90,121-123
 //
 // Structure of a CTA (384 threads; setmaxnreg moves registers from the control warpgroup to the workers):
-//   warp 0   : producer -- streams 128x64 weight tiles (TMA, SWIZZLE_128B) through a 4-stage ring, for ALL the
-//              step's GEMMs back to back: weights do not depend on activations, so the ring is refilled while
-//              the workers are still in an epilogue or an attention phase;
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x128x16, fp32 accumulators in two
-//              256-column TMEM buffers: the epilogue of one 256-column chunk overlaps the MMAs of the next);
-//   warps 4-11: workers -- TMEM epilogues (bias / ReLU / residual + LayerNorm / log-softmax statistics), the two
-//              attention phases on CUDA cores, and the embedding.
-// The activation tile is the RESIDENT A operand: 128 rows x 512 columns of bf16 in shared memory as eight
-// K-major SWIZZLE_128B k-blocks (the layout TMA would produce), written directly by the epilogues: a thread
-// per row puts its 16-byte chunk c of k-block kb at kb*16K + row*128 + ((c ^ (row & 7)) << 4), which is
-// bank-conflict-free for a thread-per-row writer and is what the tcgen05.mma descriptor expects.  (A first
-// version kept the tile un-swizzled as 8x16-byte core matrices; it was correct but every MMA took ~4x its
-// floor -- the tensor pipe was busy fetching A -- see profiles/r01_fused_first_ncu.txt.)
-// Only the 2048-wide FFN hidden tile does not fit: it goes through a row-major global scratch buffer and
-// comes back through TMA as the streamed A operand of the second FFN GEMM.  The fp32 residual stream lives in
-// a global scratch buffer in 16-byte-granule layout [granule][row] (coalesced for a thread-per-row reader).
+//   warp 0   : producer -- streams weight tiles (TMA, SWIZZLE_128B) through a ring for ALL the chain's GEMMs back to
+//              back: weights do not depend on activations, so the ring is refilled while the workers are in an epilogue;
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (UMMA 128x128x16 / 256x128x16 for CTA pairs, fp32 accumulators in
+//              two 256-column TMEM buffers: the epilogue of one 256-column chunk overlaps the MMAs of the next);
+//   warp 2   : A-tile loader -- attention outputs arrive by TMA (the chain's first tile, and mid-chain tiles of the
+//              meshed decoder's encoder levels);
+//   warps 4-11: workers -- the epilogues and the embedding.
+// The activation tile is the RESIDENT A operand: 128 rows x 512 columns of bf16 in shared memory as eight K-major
+// SWIZZLE_128B k-blocks (the layout TMA would produce), written directly by the epilogues: a thread per row puts its
+// 16-byte chunk c of k-block kb at kb*16K + row*128 + ((c ^ (row & 7)) << 4), which is bank-conflict-free for a
+// thread-per-row writer and is what the tcgen05.mma descriptor expects.  Only the 2048-wide FFN hidden tile does not
+// fit: it goes through a row-major global scratch buffer and comes back through TMA as the streamed A operand of the
+// second FFN GEMM.  The fp32 residual stream (and the meshed decoder's fp32 side streams) live in global scratch
+// buffers in 16-byte-granule layout [granule][row] (coalesced for a thread-per-row reader; L2-resident).
+// CTA pairs: two CTAs of a cluster, each with its own 128-row tile, share every weight tile -- each stages HALF of it
+// (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared memories and both CTAs
+// drain their own accumulator rows: the same 64 KB ring keeps 8 k-block stages in flight instead of 4.
+//
+// (Removed in round 2, after measurement: the one-kernel-per-step mode that also ran both attention phases on the
+// CTA's CUDA cores -- parity-green but 2.4x slower per tile than chains + stand-alone attention, because a chain CTA
+// owns its SM and its low-IPC attention phases idled the tensor pipe; and two epilogue variants, see epilogue_store.)
 #include "cap_common.cuh"
 #include "tcgen05_ptx.cuh"
 
@@ -42,87 +54,103 @@ constexpr int FD = 512;              // d_model = heads * d_k
 constexpr int FDFF = 2048;           // feed-forward width
 constexpr int FHEADS = 8;
 constexpr int TILE_ROWS = 128;
-constexpr int NW = 8;                // worker warps
-constexpr int FIRST_WORKER_WARP = 4;  // warps 0-3 form the control warpgroup (producer, MMA issuer, two idle)
-constexpr int FUSED_THREADS = (FIRST_WORKER_WARP + NW) * 32;
-// Worker warps of the chain kernels: 8 or 16 (the epilogues are written for both).  Measured: 16 warps (4 per
-// scheduler, 96 registers per thread) are no faster than 8 (84.3 k vs 83.6 k captions/s) -- the chains are paced by
-// the weight ring and the shared-memory traffic of the MMAs, not by epilogue instruction latency -- so 8 it is.
-constexpr int NW_CHAIN = 8;
-constexpr int CHAIN_THREADS = (FIRST_WORKER_WARP + NW_CHAIN) * 32;
-constexpr int CHAIN_MAXNREG = NW_CHAIN == 16 ? 96 : 128;
-constexpr int STAGE_PITCH_CHAIN = 48;  // 16-warp staging: 32 rows x 32 B (+16 B skew) per warp
-constexpr int NB = 4;                // weight ring stages
+constexpr int NW = 8;                // worker warps (16 were measured no faster: the chains are paced by the weight ring)
+constexpr int FIRST_WORKER_WARP = 4;  // warps 0-3 form the control warpgroup (producer, MMA issuer, A loader, one idle)
+constexpr int CHAIN_THREADS = (FIRST_WORKER_WARP + NW) * 32;
+constexpr int CHAIN_MAXNREG = 128;
+constexpr int NB = 4;                // weight ring stages (single CTAs)
 constexpr uint32_t B_STAGE_BYTES = 128 * 64 * 2;   // one 128-row x 64-column weight tile
-constexpr uint32_t A_KB_BYTES = 128 * 64 * 2;      // one k-block of the A operand (8 granules)
-constexpr uint32_t GRAN_BYTES = TILE_ROWS * 16;    // one 16-byte granule column of all 128 rows
+constexpr uint32_t A_KB_BYTES = 128 * 64 * 2;      // one k-block of the A operand
 constexpr int A_SLOTS = 8;           // k-blocks of the resident A tile = slots of the streamed-A ring
 constexpr int STAGE_PITCH = 80;      // per-warp store staging: 32 rows x 64 B (+16 B skew)
-constexpr int MAXB = 5;              // beams served per image by the cross-attention phase
+constexpr int MAXB = 5;              // beams per image the sparse-logits bookkeeping is written for
 constexpr int MAX_FUSED_LAYERS = 6;
-constexpr int W512_ROWS_PER_LAYER = 3 * FD + FD + FD + FD + FDFF;  // qkv | o1 | q | o2 | w1 (all K = 512)
+constexpr int MAX_LEVELS = 3;        // encoder levels of the meshed decoder
+constexpr int MAX_JOBS = 12;         // jobs of one chain launch
 
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_B = OFF_A + A_SLOTS * A_KB_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_B + NB * B_STAGE_BYTES;
-constexpr uint32_t STAGE_BYTES_ALL = NW_CHAIN * 32 * STAGE_PITCH_CHAIN > NW * 32 * STAGE_PITCH ? NW_CHAIN * 32 * STAGE_PITCH_CHAIN
-                                                                                             : NW * 32 * STAGE_PITCH;
+constexpr uint32_t STAGE_BYTES_ALL = NW * 32 * STAGE_PITCH;
 constexpr uint32_t OFF_BIAS = OFF_STAGE + STAGE_BYTES_ALL;
 constexpr uint32_t OFF_CBIAS = OFF_BIAS + FD * 4;     // [2][256] chunk biases of the plain projections
 constexpr uint32_t OFF_GAMMA = OFF_CBIAS + FD * 4;
 constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
-// LayerNorm row statistics [2 (sum, sumsq)][column groups <= 4][128 rows] alias the staging tiles: the LN epilogue
-// stages nothing, and a workers_sync separates it from the chunk epilogues on both sides
+// LayerNorm row statistics [2 (sum, sumsq)][2 halves][128 rows] alias the staging tiles: the LN epilogue stages
+// nothing, and a workers_sync separates it from the chunk epilogues on both sides
 constexpr uint32_t OFF_STAT = OFF_STAGE;
-static_assert(2 * 4 * TILE_ROWS * 4 <= STAGE_BYTES_ALL, "row statistics must fit the staging area");
+static_assert(2 * 2 * TILE_ROWS * 4 <= STAGE_BYTES_ALL, "row statistics must fit the staging area");
 constexpr uint32_t OFF_BARS = OFF_BETA + FD * 4;
 constexpr int NB_PAIR = 8;            // CTA pairs stage HALF of every weight tile: the same 64 KB hold 8 k-block stages
 constexpr uint32_t B_STAGE_BYTES_PAIR = 64 * 64 * 2;
-constexpr int NUM_BARS = 2 * NB_PAIR + 2 * A_SLOTS + 2 + 2 + 1 + 1 + 1 + 1;
+constexpr int NUM_BARS = 2 * NB_PAIR + 2 * A_SLOTS + 2 + 2 + 4;
 constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
 constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16;
 
-struct FusedLayerP {
-    const float *b_qkv, *b_o1, *g1, *be1, *b_q, *b_o2, *g2, *be2, *b_w1, *b_w2, *g3, *be3;
+// ---- jobs ---------------------------------------------------------------------------------------------------
+enum JobEpi : int {
+    JE_STORE = 0,   // + bias (+ ReLU) -> bf16 rows at dst, 256-column chunks
+    JE_LN = 1,      // N = 512: + bias + residual (res_in) -> LayerNorm -> resident A tile (bf16) + res_out (fp32) [zero rows]
+    JE_VOCAB = 2,   // bias-free: fp32 logits (sparse) + per-32-column (max, sum exp) statistics
+    JE_F32 = 3,     // raw fp32 accumulators -> side stream `aux` in granule layout (the meshed gates' s-part)
+    JE_ALPHA = 4    // N = 512: sigmoid(acc + bias + aux[level]) * c (res_in) accumulated into the mix stream (res_out);
+                    //          last level: scaled by 1/sqrt(levels) -> resident A tile + residual stream
+};
+enum JobASrc : int { JA_RESIDENT = 0, JA_TMA_TILE = 1, JA_STREAM_HIDDEN = 2 };
+enum JobFlags : int {
+    JF_RELU = 1, JF_WHOLE_TILES = 2, JF_HIDDEN_DONE = 4, JF_LAST_LEVEL = 8, JF_FIRST_LEVEL = 16,
+    JF_WAIT_A = 32   // the resident A tile is (re)written just before this job: the issuer waits for the workers' publish
+};
+
+struct JobDesc {
+    int wmap;        // weight tensor map: 0 K = 512 stack, 1 fc2 stack (K = 2048), 2 vocabulary
+    int row0;        // first weight row of the job inside that stack
+    int ntiles;      // 128-row weight tiles (N / 128)
+    int kblocks;     // K / 64
+    int chunk;       // n-tiles per accumulator pass: 2 (one 256-column TMEM buffer) or 4 (both)
+    int a_src;       // JobASrc
+    int att_row0;    // JA_TMA_TILE: first row of this job's tile source in the att_in tensor map (level * max_rows)
+    int epi;         // JobEpi
+    int flags;       // JobFlags
+    int aux_col0;    // JE_ALPHA: first column of this level's gate inside the aux stream
+    int ld_dst;      // JE_STORE: destination row pitch (elements)
+    int pad_;
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    bf16* dst;               // JE_STORE
+    const float* res_in;     // JE_LN residual / JE_ALPHA c stream   (granule layout, per tile)
+    float* res_out;          // JE_LN output stream / JE_ALPHA mix or final stream
+    const uint8_t* zero_rows;  // JE_LN: rows to zero (fed <pad>), or nullptr
 };
 
 struct FusedParams {
-    CUtensorMap map_w512;   // [layers * 5120][512]: per layer qkv | self o | cross q | cross o | ffn1
+    CUtensorMap map_w512;   // [layers * rows_per_layer][512]: the model's K = 512 projections stacked
     CUtensorMap map_w2;     // [layers * 512][2048]
     CUtensorMap map_vocab;  // [V][512]
     CUtensorMap map_h;      // [tiles * 128][2048] FFN hidden scratch
-    CUtensorMap map_att;    // [max_rows][512] attention output of the stand-alone attention kernels (chain mode)
+    CUtensorMap map_att;    // [levels * max_rows][512] attention outputs of the stand-alone attention kernels
     CUtensorMap map_w512_h, map_w2_h, map_vocab_h;   // the three weight maps with 64-row boxes (CTA pairs)
-    FusedLayerP layer[MAX_FUSED_LAYERS];
-    int n_layers;
+    JobDesc jobs[MAX_JOBS];
+    int n_jobs;
+    int start_embed;         // the chain starts with x = Emb[token] + pos (its first job reads the resident tile)
     const int32_t* tokens;
     const bf16* word_emb;
     const float* word_pos;
     int pad_idx;
-    bf16* qkv_cache;         // [layers][T][R][1536]
-    const int32_t* ancestry; // [T][R]
     uint8_t* padflag;        // [T][R]
-    const bf16* cross_kv;    // layer l at cross_kv + l * cross_layer_stride: [B][n][K(512) | V(512)]
-    size_t cross_layer_stride;
-    const uint8_t* enc_mask; // [B][n]
-    int n_keys;
     float* res;              // [tiles][128 granules of 4 floats][128 rows][4]   fp32 residual stream
-    bf16* qg;                // [tiles][64 granules][128 rows][8]                cross-attention queries
+    float* aux;              // [tiles][aux_cols / 4][128 rows][4]               fp32 side stream (meshed gates, s-part)
+    int aux_cols;
     bf16* hbuf;              // [tiles * 128][2048] row-major                    FFN hidden
     float* logits;
     int ld_logits;
     float* part_ms;          // [R][stat_chunks][2]
     int vocab, vocab_tiles, stat_chunks;
     int t, T, R, B, beam;
-    float scale;
-    unsigned long long* trace;  // debug: 64 %globaltimer stamps per CTA (cap_debug_fused_trace), else nullptr
-    int dbg_skip;            // debug (timing only): bit 0 = issue no MMAs, bit 1 = load no weight tiles
-    // chain mode: the kernel runs jobs [job_begin, job_end] of the step's GEMM list only; its first A tile is the
-    // embedding (start_embed) or a TMA load of the attention output; the attention itself runs between the chains
-    // as stand-alone kernels that share SMs with everything else in flight
-    int job_begin, job_end, start_embed;
-    bf16* q_out;             // [R][512] cross-attention queries for the stand-alone kernel (chain mode)
+    float level_scale;       // 1 / sqrt(levels) of the meshed mix
     int sparse_logits;       // 1: store only the 32-column groups that can hold one of the row's top-5 candidates
+    unsigned long long* trace;  // debug: %globaltimer stamps per CTA (cap_debug_fused_trace), else nullptr
 };
 
 __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot, bool who) {
@@ -130,45 +158,7 @@ __device__ __forceinline__ void fstamp(const FusedParams& p, int tile, int slot,
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[static_cast<size_t>(tile) * 64 + slot] = t;
-        if (slot == 0 || slot == 1 + 8 * 3 + 2) p.trace[static_cast<size_t>(tile) * 64 + (slot == 0 ? 60 : 61)] = clock64();
     }
-}
-
-struct Job {
-    const CUtensorMap* map;
-    const CUtensorMap* map_half;   // same matrix, 64-row boxes
-    int row0, ntiles, kblocks, chunk;
-    bool stream;
-};
-
-__device__ __forceinline__ Job get_job(const FusedParams& p, int ji) {
-    Job j;
-    j.kblocks = FD / BLOCK_K;
-    j.stream = false;
-    j.map = &p.map_w512;
-    j.map_half = &p.map_w512_h;
-    if (ji == p.n_layers * 6) {
-        j.map = &p.map_vocab;
-        j.map_half = &p.map_vocab_h;
-        j.row0 = 0;
-        j.ntiles = p.vocab_tiles;
-        j.chunk = 2;
-        return j;
-    }
-    const int L = ji / 6, k = ji % 6;
-    const int base = L * W512_ROWS_PER_LAYER;
-    switch (k) {
-        case 0: j.row0 = base; j.ntiles = 12; j.chunk = 2; break;             // q | k | v of the new token
-        case 1: j.row0 = base + 1536; j.ntiles = 4; j.chunk = 4; break;       // self fc_o (+ LN)
-        case 2: j.row0 = base + 2048; j.ntiles = 4; j.chunk = 2; break;       // cross fc_q
-        case 3: j.row0 = base + 2560; j.ntiles = 4; j.chunk = 4; break;       // cross fc_o (+ LN)
-        case 4: j.row0 = base + 3072; j.ntiles = 16; j.chunk = 2; break;      // fc1 (+ ReLU)
-        default:
-            j.map = &p.map_w2; j.map_half = &p.map_w2_h; j.row0 = L * FD; j.ntiles = 4; j.chunk = 4; j.kblocks = FDFF / BLOCK_K;
-            j.stream = true;                                                  // fc2 (+ LN), A = hidden tile
-            break;
-    }
-    return j;
 }
 
 // 64 bytes per lane (the lane's row) -> global rows, through the warp's staging tile: every store instruction
@@ -199,59 +189,24 @@ __device__ __forceinline__ uint32_t a_tile_off(int row, int chunk) {
            (static_cast<uint32_t>((chunk & 7) ^ (row & 7)) << 4);
 }
 
-// 16-warp layout: 32 bytes per lane and pass (every store instruction covers 16 rows x 32 contiguous bytes)
-template <bool STREAMING = false>
-__device__ __forceinline__ void staged_store32(uint8_t* stage, int lane, const uint4& v0, const uint4& v1, uint8_t* gbase,
-                                               size_t row_stride, int rows_valid) {
-    uint8_t* mine = stage + lane * STAGE_PITCH_CHAIN;
-    *reinterpret_cast<uint4*>(mine) = v0;
-    *reinterpret_cast<uint4*>(mine + 16) = v1;
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int idx = it * 32 + lane;
-        const int rr = idx >> 1, part = idx & 1;
-        const uint4 x = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH_CHAIN + part * 16);
-        if (rr < rows_valid) {
-            uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(rr) * row_stride + part * 16);
-            if (STREAMING) __stcs(dst, x); else *dst = x;
-        }
-    }
-    __syncwarp();
-}
-
-// 64 bytes per lane to global rows through the warp's staging tile, in the layout of the kernel's warp count
-template <bool STREAMING = false>
-__device__ __forceinline__ void staged_store(bool wide, uint8_t* stage, int lane, const uint4 (&v)[4], uint8_t* gbase,
-                                             size_t row_stride, int rows_valid) {
-    if (wide) {
-        staged_store64<STREAMING>(stage, lane, v, gbase, row_stride, rows_valid);
-    } else {
-        staged_store32<STREAMING>(stage, lane, v[0], v[1], gbase, row_stride, rows_valid);
-        staged_store32<STREAMING>(stage, lane, v[2], v[3], gbase + 32, row_stride, rows_valid);
-    }
-}
-
 __device__ __forceinline__ uint4 pack8_u4(const float* f) {
     bf16x8 p = pack8(f);
     return *reinterpret_cast<uint4*>(&p);
 }
 
-__device__ __forceinline__ void workers_sync(int nw) { asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory"); }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
 
 struct WorkerCtx {
     uint8_t* A_buf;
     uint8_t* stage;   // this warp's staging tile
     float *s_bias, *s_cbias, *s_gamma, *s_beta, *s_stat;
-    uint64_t *acc_full, *acc_empty, *a_ready, *h_ready, *ring_free;
-    uint8_t* kv_ring;  // this warp's K|V row ring (inside the weight ring)
+    uint64_t *acc_full, *acc_empty, *a_ready, *h_ready;
     bool pair_peer;    // CTA pair, and this CTA is not the leader: consumer-side barriers live in the leader CTA
     uint32_t tmem_base;
     uint32_t use0, use1;  // completed uses of TMEM buffer 0 / 1 (scalars: no dynamically indexed state)
     int toggle;
-    int ww, quad, half, lane, wtid;
-    int nw, nsub;   // worker warps of this kernel (8 or 16) and column groups per TMEM quadrant (nw / 4); half = ww / 4 in [0, nsub)
-    int tile, r0, rows_valid_warp;  // rows of this warp's TMEM quadrant that exist (0..32)
+    int ww, quad, half, lane, wtid;   // half = ww / 4: which 128 (of 256) / 256 (of 512) columns of a quadrant's rows
+    int tile, r0, rows_valid_warp;    // rows of this warp's TMEM quadrant that exist (0..32)
 };
 
 __device__ __forceinline__ int acquire_acc(WorkerCtx& c, int chunk) {
@@ -295,106 +250,110 @@ __device__ __forceinline__ void publish_a(WorkerCtx& c) {
     }
 }
 
-enum { EPI_CACHE = 0, EPI_QG = 1, EPI_HID = 2 };
-
-// Epilogue of one 256-column chunk of a plain projection: + bias (ReLU for the hidden layer), bf16, to global.
+// Epilogue of one 256-column chunk of a plain projection: + bias (ReLU for the hidden layer), bf16, to global rows.
 // `bias_reg` carries this thread's bias value of the chunk across calls: the value of chunk c + 1 is requested
-// while chunk c is drained, so the global-load latency is off the per-chunk critical path (n_chunks = chunks of
-// the job; the first chunk of a job loads its own value).
+// while chunk c is drained, so the global-load latency is off the per-chunk critical path.
 // (Measured in round 2 and removed: software-pipelining the four tcgen05.ld of a warp one group ahead of the math
 // changed nothing -- 84.5 k vs 85.2 k captions/s -- and storing the bf16 rows straight from registers instead of
 // through the staging tile was slower, 81.9 k: the store sectors cost more than the shared-memory round trip.)
-template <int KIND>
-__device__ __forceinline__ void epilogue_chunk(WorkerCtx& c, const FusedParams& p, const float* bias, int chunk_idx,
-                                               int n_chunks, float& bias_reg, bf16* dst_rowmajor, int ld_rowmajor) {
-    // stage this chunk's 256 bias values (double-buffered by chunk parity; see the barrier note below)
-    const bool tr = (KIND == EPI_HID && chunk_idx == 3 && c.ww == 0 && c.lane == 0);
+__device__ __forceinline__ void epilogue_store(WorkerCtx& c, const FusedParams& p, const JobDesc& job, int chunk_idx,
+                                               int n_chunks, float& bias_reg) {
+    const int flags = job.flags;   // job fields are read once: the asm wrappers' memory clobbers would reload them
+    const float* bias = job.bias;
+    bf16* const dst = job.dst;
+    const int ld_dst = job.ld_dst;
+    const bool tr = ((flags & JF_RELU) && chunk_idx == 3 && c.ww == 0 && c.lane == 0);
     fstamp(p, c.tile, 40, tr);
-    float* sb = c.s_cbias + (chunk_idx & 1) * 256;
+    float* sb = c.s_cbias + (chunk_idx & 1) * 256;   // double-buffered by chunk parity (see the barrier note below)
     if (c.wtid < 256) {
         if (chunk_idx == 0) bias_reg = __ldg(bias + c.wtid);
         sb[c.wtid] = bias_reg;
         if (chunk_idx + 1 < n_chunks) bias_reg = __ldg(bias + (chunk_idx + 1) * 256 + c.wtid);
     }
-    workers_sync(c.nw);  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
+    workers_sync();  // a warp reaches the NEXT chunk's barrier only after it has finished reading this one
     fstamp(p, c.tile, 41, tr);
     const int b = acquire_acc(c, 2);
     fstamp(p, c.tile, 42, tr);
-    const int row = c.quad * 32 + c.lane;
-    const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains (4 with 8 warps, 2 with 16)
-    const bool wide = c.nw == NW;
+    const float relu_floor = (flags & JF_RELU) ? 0.f : -INFINITY;   // one FMNMX either way, no branch in the loop
+    const int rows_valid = (flags & JF_WHOLE_TILES) ? 32 : c.rows_valid_warp;   // scratch buffers hold whole tiles
+    uint8_t* const tile_base = reinterpret_cast<uint8_t*>(dst + static_cast<size_t>(c.r0 + c.quad * 32) * ld_dst + chunk_idx * 256);
 #pragma unroll 1
-    for (int i = 0; i < groups; ++i) {
-        const int colc = (c.half * groups + i) * 32;
+    for (int i = 0; i < 4; ++i) {
+        const int colc = (c.half * 4 + i) * 32;
         uint32_t v[32];
-        fstamp(p, c.tile, 48, tr && i == 1);
         tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
         tmem_ld_wait();
-        fstamp(p, c.tile, 49, tr && i == 1);
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            f[j] = __uint_as_float(v[j]) + sb[colc + j];
-            if (KIND == EPI_HID) f[j] = fmaxf(f[j], 0.f);
+            f[j] = fmaxf(__uint_as_float(v[j]) + sb[colc + j], relu_floor);
         }
         uint4 o[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) o[g] = pack8_u4(f + 8 * g);
-        if (tr && i == 1 && o[0].x == 0x12345678u) fstamp(p, c.tile, 63, true);  // keep the math before the stamp
-        fstamp(p, c.tile, 50, tr && i == 1);
-        const int gcol = chunk_idx * 256 + colc;
-        if (KIND == EPI_CACHE) {
-            uint8_t* gbase = reinterpret_cast<uint8_t*>(dst_rowmajor + static_cast<size_t>(c.r0 + c.quad * 32) * ld_rowmajor + gcol);
-            staged_store(wide, c.stage, c.lane, o, gbase, static_cast<size_t>(ld_rowmajor) * 2, c.rows_valid_warp);
-        } else if (KIND == EPI_HID) {
-            // row-major scratch [tiles * 128][2048] (whole tiles are allocated: no row guard), re-read by TMA
-            uint8_t* gbase = reinterpret_cast<uint8_t*>(p.hbuf + static_cast<size_t>(c.r0 + c.quad * 32) * FDFF + gcol);
-            staged_store(wide, c.stage, c.lane, o, gbase, static_cast<size_t>(FDFF) * 2, 32);
-        } else {
-            // granule layout [tile][granule][row][16 B]: 32 lanes write 512 contiguous bytes per granule
-            uint4* base = reinterpret_cast<uint4*>(p.qg) + (static_cast<size_t>(c.tile) * (FD / 8) + gcol / 8) * TILE_ROWS + row;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) base[static_cast<size_t>(g) * TILE_ROWS] = o[g];
-        }
+        staged_store64(c.stage, c.lane, o, tile_base + colc * 2, static_cast<size_t>(ld_dst) * 2, rows_valid);
         fstamp(p, c.tile, 43 + i, tr);
     }
     release_acc(c, 2, b);
     fstamp(p, c.tile, 47, tr);
 }
 
+// Epilogue of one 256-column chunk whose raw fp32 accumulators go to the side stream (granule layout): the s-part of
+// the meshed decoder's gates, s . W_alpha_i[:, :512]^T for the three levels (decoders.py:60-62), computed while the
+// self-attention output s is the resident tile and consumed by JE_ALPHA of the same layer.
+__device__ __forceinline__ void epilogue_f32(WorkerCtx& c, const FusedParams& p, int chunk_idx) {
+    const int b = acquire_acc(c, 2);
+    const int row = c.quad * 32 + c.lane;
+    float4* aux = reinterpret_cast<float4*>(p.aux) + static_cast<size_t>(c.tile) * (p.aux_cols / 4) * TILE_ROWS + row;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int colc = (c.half * 4 + i) * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
+        tmem_ld_wait();
+        const int gcol = chunk_idx * 256 + colc;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            aux[static_cast<size_t>(gcol / 4 + g) * TILE_ROWS] =
+                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                            __uint_as_float(v[4 * g + 3]));
+    }
+    release_acc(c, 2, b);
+}
+
 // Epilogue of an N = 512 projection followed by residual + LayerNorm (attentions.py:308-309,
 // positionwise_feed_forward.py:26): thread = row, the two warps of a TMEM quadrant take 256 columns each and
-// exchange (sum, sum of squares); the normalised row goes to the resident A tile (bf16) and back to the fp32
-// residual stream (in place: a thread only ever touches its own elements).
-// PARK (chain kernels): pass A writes y = projection + bias + residual back into the accumulator's TMEM columns, so
-// pass B needs neither the residual (global) nor the bias again; the residual granules of the next 32 columns are
-// requested while the current ones are consumed.
-template <bool PARK>
-__device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedParams& p, const float* bias,
-                                                   const float* gamma, const float* beta, const uint8_t* zero_rows) {
-    for (int i = c.wtid; i < FD; i += c.nw * 32) {
-        c.s_bias[i] = __ldg(bias + i);
-        c.s_gamma[i] = __ldg(gamma + i);
-        c.s_beta[i] = __ldg(beta + i);
+// exchange (sum, sum of squares); the normalised row goes to the resident A tile (bf16) and to the fp32 stream
+// res_out (which may be res_in: a thread only ever touches its own elements).  Pass A writes y = projection + bias +
+// residual back into the accumulator's TMEM columns, so pass B needs neither the residual (global) nor the bias
+// again; the residual granules of the next 32 columns are requested while the current TMEM load is in flight.
+__device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedParams& p, const JobDesc& job) {
+    // every warp has left the previous epilogue: a LayerNorm / gate epilogue may still be reading s_bias / s_gamma /
+    // s_beta in another quadrant (its quadrant barrier joins two warps only), and s_stat aliases the staging tiles
+    workers_sync();
+    for (int i = c.wtid; i < FD; i += NW * 32) {
+        c.s_bias[i] = __ldg(job.bias + i);
+        c.s_gamma[i] = __ldg(job.gamma + i);
+        c.s_beta[i] = __ldg(job.beta + i);
     }
-    workers_sync(c.nw);
+    workers_sync();
     acquire_acc(c, 4);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
     const bool live = grow < p.R;
-    float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS + row;
+    const size_t tile_off = static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS + row;
+    const float4* res_in = reinterpret_cast<const float4*>(job.res_in) + tile_off;
+    float4* res_out = reinterpret_cast<float4*>(job.res_out) + tile_off;
     const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
-    if constexpr (PARK) {
-    const int groups = 16 / c.nsub;   // 32-column groups of the 512-wide row this warp owns (8 or 4)
 #pragma unroll 1
-    for (int i = 0; i < groups; ++i) {
-        const int c0 = (c.half * groups + i) * 32;
+    for (int i = 0; i < 8; ++i) {
+        const int c0 = (c.half * 8 + i) * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         float4 r[8];   // requested while the TMEM load is in flight
 #pragma unroll
-        for (int g = 0; g < 8; ++g) r[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+        for (int g = 0; g < 8; ++g) r[g] = res_in[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -411,20 +370,17 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     }
     tmem_st_wait();
     c.s_stat[c.half * TILE_ROWS + row] = s1;
-    c.s_stat[(4 + c.half) * TILE_ROWS + row] = s2;
-    asm volatile("bar.sync %0, %1;" ::"r"(2 + c.quad), "r"(c.nsub * 32) : "memory");  // the quadrant's column groups
-    float S1 = 0.f, S2 = 0.f;
-    for (int k = 0; k < c.nsub; ++k) {
-        S1 += c.s_stat[k * TILE_ROWS + row];
-        S2 += c.s_stat[(4 + k) * TILE_ROWS + row];
-    }
+    c.s_stat[(2 + c.half) * TILE_ROWS + row] = s2;
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + c.quad) : "memory");  // the two warps of the quadrant
+    const float S1 = c.s_stat[row] + c.s_stat[TILE_ROWS + row];
+    const float S2 = c.s_stat[2 * TILE_ROWS + row] + c.s_stat[3 * TILE_ROWS + row];
     const float mean = S1 * (1.f / FD);
     const float var = fmaxf(S2 * (1.f / FD) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
-    const bool zero = !live || (zero_rows != nullptr && zero_rows[grow] != 0);
+    const bool zero = !live || (job.zero_rows != nullptr && job.zero_rows[grow] != 0);
 #pragma unroll 1
-    for (int i = 0; i < groups; ++i) {
-        const int c0 = (c.half * groups + i) * 32;
+    for (int i = 0; i < 8; ++i) {
+        const int c0 = (c.half * 8 + i) * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
@@ -434,70 +390,86 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
             f[j] = zero ? 0.f : (__uint_as_float(v[j]) - mean) * rstd * c.s_gamma[c0 + j] + c.s_beta[c0 + j];
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-            res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+            res_out[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
     }
-    } else {
+    release_acc(c, 4, 0);
+    publish_a(c);
+}
+
+// Epilogue of the meshed decoder's gate of one encoder level (decoders.py:60-67): the accumulator holds
+// c_i . W_alpha_i[:, 512:]^T; alpha_i = sigmoid(acc + s-part (aux stream) + bias); mix += alpha_i * c_i, all in fp32,
+// thread = row.  The last level scales the mix by 1/sqrt(levels) and hands it on as the resident A tile (bf16) and the
+// residual stream (fp32) of the feed-forward block.
+__device__ __forceinline__ void epilogue_alpha(WorkerCtx& c, const FusedParams& p, const JobDesc& job, float* mix_stream) {
+    workers_sync();   // the LayerNorm epilogue before this one reads s_bias until its last warp is through pass A
+    for (int i = c.wtid; i < FD; i += NW * 32) c.s_bias[i] = __ldg(job.bias + i);
+    workers_sync();
+    acquire_acc(c, 4);
+    const int row = c.quad * 32 + c.lane;
+    const bool live = c.r0 + row < p.R;
+    const bool first = (job.flags & JF_FIRST_LEVEL) != 0, last = (job.flags & JF_LAST_LEVEL) != 0;
+    const size_t tile_off = static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS + row;
+    const float4* cs = reinterpret_cast<const float4*>(job.res_in) + tile_off;
+    float4* mix = reinterpret_cast<float4*>(mix_stream) + tile_off;
+    float4* out = reinterpret_cast<float4*>(job.res_out) + tile_off;
+    const float4* gate = reinterpret_cast<const float4*>(p.aux) + static_cast<size_t>(c.tile) * (p.aux_cols / 4) * TILE_ROWS + row +
+                         static_cast<size_t>(job.aux_col0 / 4) * TILE_ROWS;
+    const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
-        const int c0 = c.half * 256 + i * 32;
+        const int c0 = (c.half * 8 + i) * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
-        float4 r4[8];
+        float4 r[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) r4[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const float y0 = __uint_as_float(v[4 * g]) + c.s_bias[c0 + 4 * g] + r4[g].x;
-            const float y1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r4[g].y;
-            const float y2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r4[g].z;
-            const float y3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r4[g].w;
-            s1 += (y0 + y1) + (y2 + y3);
-            s2 = fmaf(y0, y0, s2); s2 = fmaf(y1, y1, s2); s2 = fmaf(y2, y2, s2); s2 = fmaf(y3, y3, s2);
-        }
-    }
-    c.s_stat[c.half * TILE_ROWS + row] = s1;
-    c.s_stat[(2 + c.half) * TILE_ROWS + row] = s2;
-    asm volatile("bar.sync %0, 64;" ::"r"(2 + c.quad) : "memory");
-    const float S1 = c.s_stat[row] + c.s_stat[TILE_ROWS + row];
-    const float S2 = c.s_stat[2 * TILE_ROWS + row] + c.s_stat[3 * TILE_ROWS + row];
-    const float mean = S1 * (1.f / FD);
-    const float var = fmaxf(S2 * (1.f / FD) - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + 1e-5f);
-    const bool zero = !live || (zero_rows != nullptr && zero_rows[grow] != 0);
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        const int c0 = c.half * 256 + i * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
-        float4 r4[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) r4[g] = res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+        for (int g = 0; g < 8; ++g) r[g] = gate[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-            const float rr[4] = {r4[g].x, r4[g].y, r4[g].z, r4[g].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = 4 * g + e;
-                const float y = __uint_as_float(v[j]) + c.s_bias[c0 + j] + rr[e];
-                f[j] = zero ? 0.f : (y - mean) * rstd * c.s_gamma[c0 + j] + c.s_beta[c0 + j];
-            }
+            const float x0 = __uint_as_float(v[4 * g]) + c.s_bias[c0 + 4 * g] + r[g].x;
+            const float x1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r[g].y;
+            const float x2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r[g].z;
+            const float x3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r[g].w;
+            f[4 * g] = 1.f / (1.f + __expf(-x0));
+            f[4 * g + 1] = 1.f / (1.f + __expf(-x1));
+            f[4 * g + 2] = 1.f / (1.f + __expf(-x2));
+            f[4 * g + 3] = 1.f / (1.f + __expf(-x3));
         }
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-            res[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+        for (int g = 0; g < 8; ++g) r[g] = cs[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
-    }
+        for (int g = 0; g < 8; ++g) {
+            f[4 * g] *= r[g].x; f[4 * g + 1] *= r[g].y; f[4 * g + 2] *= r[g].z; f[4 * g + 3] *= r[g].w;
+        }
+        if (!first) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) r[g] = mix[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                f[4 * g] += r[g].x; f[4 * g + 1] += r[g].y; f[4 * g + 2] += r[g].z; f[4 * g + 3] += r[g].w;
+            }
+        }
+        if (last) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = live ? f[j] * p.level_scale : 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                out[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                mix[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+        }
     }
     release_acc(c, 4, 0);
-    publish_a(c);
+    if (last) publish_a(c);
 }
 
 // x = Emb[token] + pos[t + 1] (decoders.py:107-112); pad flag of the fed token; warp per row.
@@ -511,7 +483,7 @@ __device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) 
         pv[4 * i] = t4.x; pv[4 * i + 1] = t4.y; pv[4 * i + 2] = t4.z; pv[4 * i + 3] = t4.w;
     }
     float4* res = reinterpret_cast<float4*>(p.res) + static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS;
-    const int ROWS_PER_WARP = TILE_ROWS / c.nw;
+    constexpr int ROWS_PER_WARP = TILE_ROWS / NW;
     // lane i fetches the token of the warp's row i; rows are then embedded a few at a time (many loads in flight)
     int mytok = -1;
     if (c.lane < ROWS_PER_WARP) {
@@ -551,334 +523,87 @@ __device__ __forceinline__ void embed_phase(WorkerCtx& c, const FusedParams& p) 
     }
 }
 
-// ------------------------------------------------------------------------------ streamed K|V rows
-// Both attention phases read 2 KB rows (K | V of one key, contiguous in HBM) that nothing else on the SM
-// needs.  Each worker warp streams them with cp.async through a private 4-slot ring carved out of the weight
-// ring (idle during an attention phase: the producer is gated until the phase ends), three rows in flight
-// while the fourth is consumed -- the loads are decoupled from the arithmetic and cost no registers.
-// Chunk k (16 bytes) of a 1 KB half-row is stored at position k/2 + 32*(k%2): lane l then reads its 16
-// columns as two conflict-free 16-byte accesses (positions l and 32 + l).
-constexpr int KV_SLOTS = 4;
-constexpr uint32_t KV_ROW_BYTES = 2 * FD * 2;
-
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc))
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void kv_issue(uint8_t* slot, const bf16* src, int lane) {
-    const uint8_t* g = reinterpret_cast<const uint8_t*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = lane + 32 * i;
-        const int kk = k & 63;
-        const int pos = (k & 64) + (kk >> 1) + ((kk & 1) << 5);
-        cp_async_16(slot + pos * 16, g + k * 16);
-    }
-}
-
-__device__ __forceinline__ void kv_read(const uint8_t* slot, int lane, float* kf, float* vf) {
-    const bf16x8* s8 = reinterpret_cast<const bf16x8*>(slot);
-    unpack8(s8[lane], kf);
-    unpack8(s8[32 + lane], kf + 8);
-    unpack8(s8[64 + lane], vf);
-    unpack8(s8[96 + lane], vf + 8);
-}
-
-// Stateful self-attention of the new token over its beam history (attentions.py:297-304 with the running
-// mask of decoders.py:101-103): warp per row, lanes tile the 512-wide row (4 lanes per head), keys found
-// through the ancestry table, online softmax; output straight into the resident A tile.  The (row, key)
-// pairs of the warp's 16 rows form ONE stream of K|V rows, so the pipeline never drains between rows.
-__device__ __forceinline__ void self_attention_phase(WorkerCtx& c, const FusedParams& p, const bf16* cache_l) {
-    constexpr int EPL = 16;
-    constexpr int ROWS_PER_WARP = TILE_ROWS / NW;
-    const int t = p.t, R = p.R;
-    const size_t row_stride = 3 * FD;
-    const size_t step_stride = static_cast<size_t>(R) * row_stride;
-    const int nkeys = t + 1;
-    const int row0 = c.ww * ROWS_PER_WARP;
-    const int nrows = max(0, min(ROWS_PER_WARP, R - (c.r0 + row0)));
-    const int items = nrows * nkeys;
-    // slot | pad << 31 of every (row, key) of this warp, gathered with all lanes in parallel
-    int32_t* meta = reinterpret_cast<int32_t*>(c.stage);
-    for (int idx = c.lane; idx < items; idx += 32) {
-        const int i = idx / nkeys, j = idx - i * nkeys;
-        const int r = c.r0 + row0 + i;
-        const int sl = (j == t) ? r : p.ancestry[static_cast<size_t>(j) * R + r];
-        const int pad = p.padflag[static_cast<size_t>(j) * R + sl] != 0;
-        meta[idx] = sl | (pad << 31);
-    }
-    __syncwarp();
-    uint8_t* ring = c.kv_ring;
-    auto src_of = [&](int idx) -> const bf16* {
-        const int i = idx / nkeys, j = idx - i * nkeys;
-        return cache_l + j * step_stride + static_cast<size_t>(meta[idx] & 0x7fffffff) * row_stride + FD;
-    };
-#pragma unroll
-    for (int n = 0; n < KV_SLOTS - 1; ++n) {
-        if (n < items) kv_issue(ring + n * KV_ROW_BYTES, src_of(n), c.lane);
-        cp_async_commit();
-    }
-    float q[EPL], acc[EPL], m = -INFINITY, l = 0.f;
-    int i = 0, j = 0;
-#pragma unroll 1
-    for (int n = 0; n < items; ++n) {
-        if (n + KV_SLOTS - 1 < items) kv_issue(ring + ((n + KV_SLOTS - 1) % KV_SLOTS) * KV_ROW_BYTES, src_of(n + KV_SLOTS - 1), c.lane);
-        cp_async_commit();
-        if (j == 0) {
-            const bf16x8* qp = reinterpret_cast<const bf16x8*>(cache_l + t * step_stride + static_cast<size_t>(c.r0 + row0 + i) * row_stride + c.lane * EPL);
-            unpack8(qp[0], q);
-            unpack8(qp[1], q + 8);
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) { q[e] *= p.scale; acc[e] = 0.f; }
-            m = -INFINITY;
-            l = 0.f;
-        }
-        cp_async_wait<KV_SLOTS - 1>();
-        __syncwarp();  // every lane's copies of item n have landed
-        if (meta[n] >= 0) {  // key not fed <pad> (warp-uniform)
-            float kf[EPL], vf[EPL];
-            kv_read(ring + (n % KV_SLOTS) * KV_ROW_BYTES, c.lane, kf, vf);
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) s = fmaf(q[e], kf[e], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const float m_new = fmaxf(m, s);
-            const float corr = __expf(m - m_new);
-            const float pr = __expf(s - m_new);
-            l = l * corr + pr;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + pr * vf[e];
-            m = m_new;
-        }
-        __syncwarp();  // slot n % KV_SLOTS may be refilled by the next iteration's issue
-        if (++j == nkeys) {
-            const float inv = l > 0.f ? 1.f / l : 0.f;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) acc[e] *= inv;
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-                *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row0 + i, 2 * c.lane + g)) = pack8_u4(acc + 8 * g);
-            j = 0;
-            ++i;
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// Cross-attention over the image's cached K|V (decoders.py:23): warp per image, all heads and all of the
-// image's beams at once (lane owns 16 consecutive columns, 4 lanes per head), so every K/V row crosses HBM
-// once per step; the (image, key) pairs of the warp's images form one stream of K|V rows.
-__device__ __forceinline__ void cross_attention_phase(WorkerCtx& c, const FusedParams& p, const bf16* kv_l) {
-    constexpr int EPL = 16;
-    const int beam = p.beam, n = p.n_keys;
-    const int img_lo = c.r0 / beam;
-    const int last_row = min(c.r0 + TILE_ROWS, p.R) - 1;
-    const int img_hi = last_row / beam;
-    const int first = img_lo + c.ww;
-    const int nimg = first <= img_hi ? (img_hi - first) / NW + 1 : 0;
-    const int items = nimg * n;
-    const uint4* qg = reinterpret_cast<const uint4*>(p.qg) + static_cast<size_t>(c.tile) * (FD / 8) * TILE_ROWS;
-    uint8_t* ring = c.kv_ring;
-    auto src_of = [&](int idx) -> const bf16* {
-        const int ii = idx / n, j = idx - ii * n;
-        return kv_l + (static_cast<size_t>(first + ii * NW) * n + j) * 2 * FD;
-    };
-#pragma unroll
-    for (int k = 0; k < KV_SLOTS - 1; ++k) {
-        if (k < items) kv_issue(ring + k * KV_ROW_BYTES, src_of(k), c.lane);
-        cp_async_commit();
-    }
-    bf16x8 qreg[MAXB][2];
-    float m[MAXB], l[MAXB], acc[MAXB][EPL];
-    uint32_t maskbits = 0;  // bit i: key lane + 32*i of the current image is padding
-    int ii = 0, j = 0, nb = 0, lr0 = 0;
-#pragma unroll 1
-    for (int k = 0; k < items; ++k) {
-        if (k + KV_SLOTS - 1 < items) kv_issue(ring + ((k + KV_SLOTS - 1) % KV_SLOTS) * KV_ROW_BYTES, src_of(k + KV_SLOTS - 1), c.lane);
-        cp_async_commit();
-        if (j == 0) {
-            const int img = first + ii * NW;
-            const int row_begin = max(img * beam, c.r0);
-            nb = min(img * beam + beam, last_row + 1) - row_begin;
-            lr0 = row_begin - c.r0;
-#pragma unroll
-            for (int bb = 0; bb < MAXB; ++bb) {
-                const int lr = lr0 + min(bb, nb - 1);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint4 u = qg[static_cast<size_t>(2 * c.lane + g) * TILE_ROWS + lr];
-                    qreg[bb][g] = *reinterpret_cast<const bf16x8*>(&u);
-                }
-                m[bb] = -INFINITY;
-                l[bb] = 0.f;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) acc[bb][e] = 0.f;
-            }
-            maskbits = 0;
-            if (p.enc_mask != nullptr) {
-                const uint8_t* mrow = p.enc_mask + static_cast<size_t>(img) * n;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const int key = c.lane + 32 * w;
-                    if (key < n && mrow[key]) maskbits |= 1u << w;
-                }
-            }
-        }
-        const bool masked = ((__shfl_sync(0xffffffffu, maskbits, j & 31) >> (j >> 5)) & 1u) != 0;
-        cp_async_wait<KV_SLOTS - 1>();
-        __syncwarp();
-        if (!masked) {  // warp-uniform
-            float kf[EPL], vf[EPL];
-            kv_read(ring + (k % KV_SLOTS) * KV_ROW_BYTES, c.lane, kf, vf);
-#pragma unroll
-            for (int bb = 0; bb < MAXB; ++bb) {
-                if (bb >= nb) continue;  // warp-uniform
-                float qf[EPL];
-                unpack8(qreg[bb][0], qf);
-                unpack8(qreg[bb][1], qf + 8);
-                float s = 0.f;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) s = fmaf(qf[e], kf[e], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s *= p.scale;
-                const float m_new = fmaxf(m[bb], s);
-                const float corr = __expf(m[bb] - m_new);
-                const float pr = __expf(s - m_new);
-                l[bb] = l[bb] * corr + pr;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) acc[bb][e] = acc[bb][e] * corr + pr * vf[e];
-                m[bb] = m_new;
-            }
-        }
-        __syncwarp();
-        if (++j == n) {
-#pragma unroll
-            for (int bb = 0; bb < MAXB; ++bb) {
-                if (bb >= nb) continue;
-                const float inv = l[bb] > 0.f ? 1.f / l[bb] : 0.f;
-                float o[EPL];
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) o[e] = acc[bb][e] * inv;
-#pragma unroll
-                for (int g = 0; g < 2; ++g)
-                    *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(lr0 + bb, 2 * c.lane + g)) = pack8_u4(o + 8 * g);
-            }
-            j = 0;
-            ++ii;
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// end of an attention phase: the resident A tile is complete and the weight ring is handed back
-__device__ __forceinline__ void publish_attention(WorkerCtx& c) {
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (c.lane == 0) {
-        mbar_arrive(c.a_ready);
-        mbar_arrive(c.ring_free);
-    }
-}
-
 // Vocabulary projection epilogue (bias-free fc, decoders.py:90,121): fp32 logits + per-32-column-chunk
 // (max, sum exp(x - max)) for beam_chunkmerge_kernel (beam.cu).
 // Sparse mode: the selection (beam_chunkmerge_kernel) reads back only the `beam` <= 5 groups of 32 columns with
 // the largest maxima of a row.  A thread (= row, one half of every chunk) keeps the five largest group maxima it
 // has seen; a group is stored only if its maximum reaches the fifth of them -- every group of the row's final
 // top five passes that test when it is produced, and ~85 % of the 52 MB of logits per step are never written.
-// (the per-group body is vocab_group below)
-__device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, int chunk_idx, int colc, int grow, bool wide,
-                                            const uint32_t (&v)[32], float (&top)[5]);
-
-__device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx, float (&top)[5]) {
-    const int b = acquire_acc(c, 2);
-    const int row = c.quad * 32 + c.lane;
-    const int grow = c.r0 + row;
-    const int groups = 8 / c.nsub;   // 32-column groups of the chunk this warp drains
-    const bool wide = c.nw == NW;
-#pragma unroll 1
-    for (int i = 0; i < groups; ++i) {
-        const int colc = (c.half * groups + i) * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
-        tmem_ld_wait();
-        vocab_group(c, p, chunk_idx, colc, grow, wide, v, top);
-    }
-    release_acc(c, 2, b);
-}
-
-// statistics + (sparse) store of one 32-column group of the vocabulary projection
-__device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, int chunk_idx, int colc, int grow, bool wide,
+__device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, int chunk_idx, int colc, int grow,
                                             const uint32_t (&v)[32], float (&top)[5]) {
-    {
-        const int gcol = chunk_idx * 256 + colc;
-        const int valid = p.vocab - gcol;  // columns of this 32-chunk inside the vocabulary (warp-uniform)
-        float cm = -INFINITY, cs = 0.f;
-        if (valid >= 32) {
+    const int gcol = chunk_idx * 256 + colc;
+    const int valid = p.vocab - gcol;  // columns of this 32-chunk inside the vocabulary (warp-uniform)
+    float cm = -INFINITY, cs = 0.f;
+    if (valid >= 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
-            const float cm2 = cm * 1.4426950408889634f;
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+        const float cm2 = cm * 1.4426950408889634f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cs += exp2f(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -cm2));
-        } else if (valid > 0) {
+        for (int j = 0; j < 32; ++j) cs += exp2f(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -cm2));
+    } else if (valid > 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < valid ? __uint_as_float(v[j]) : -INFINITY);
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < valid ? __uint_as_float(v[j]) : -INFINITY);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cs += j < valid ? __expf(__uint_as_float(v[j]) - cm) : 0.f;
-        }
-        if (grow < p.R)
-            *reinterpret_cast<float2*>(p.part_ms + (static_cast<size_t>(grow) * p.stat_chunks + chunk_idx * 8 + colc / 32) * 2) =
-                make_float2(cm, cs);
-        if (gcol < p.ld_logits) {
-            if (p.sparse_logits) {
-                const bool keep = cm >= top[4] && grow < p.R;
-                float x = cm;   // insert into the descending top five
+        for (int j = 0; j < 32; ++j) cs += j < valid ? __expf(__uint_as_float(v[j]) - cm) : 0.f;
+    }
+    if (grow < p.R)
+        *reinterpret_cast<float2*>(p.part_ms + (static_cast<size_t>(grow) * p.stat_chunks + chunk_idx * 8 + colc / 32) * 2) =
+            make_float2(cm, cs);
+    if (gcol < p.ld_logits) {
+        if (p.sparse_logits) {
+            const bool keep = cm >= top[4] && grow < p.R;
+            float x = cm;   // insert into the descending top five
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float hi = fmaxf(top[k], x);
-                    x = fminf(top[k], x);
-                    top[k] = hi;
-                }
-                if (keep) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.logits + static_cast<size_t>(grow) * p.ld_logits + gcol);
+            for (int k = 0; k < 5; ++k) {
+                const float hi = fmaxf(top[k], x);
+                x = fminf(top[k], x);
+                top[k] = hi;
+            }
+            if (keep) {
+                uint4* dst = reinterpret_cast<uint4*>(p.logits + static_cast<size_t>(grow) * p.ld_logits + gcol);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) __stcs(dst + g, make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
-                }
-            } else {
+                for (int g = 0; g < 8; ++g) __stcs(dst + g, make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+            }
+        } else {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint4 o[4];
+            for (int hh = 0; hh < 2; ++hh) {
+                uint4 o[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
-                    uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
-                    staged_store<true>(wide, c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
-                }
+                for (int g = 0; g < 4; ++g)
+                    o[g] = make_uint4(v[hh * 16 + 4 * g], v[hh * 16 + 4 * g + 1], v[hh * 16 + 4 * g + 2], v[hh * 16 + 4 * g + 3]);
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(p.logits + static_cast<size_t>(c.r0 + c.quad * 32) * p.ld_logits + gcol + hh * 16);
+                staged_store64<true>(c.stage, c.lane, o, gbase, static_cast<size_t>(p.ld_logits) * 4, c.rows_valid_warp);
             }
         }
     }
 }
 
-// CHAIN = false: the whole step (attention phases on this CTA's CUDA cores).  CHAIN = true: a range of the
-// step's GEMM jobs with their epilogues (see FusedParams::job_begin).
-// The chain instantiation is capped at 128 registers per thread (setmaxnreg then moves them: 64 for the control
-// warps, 160 for the epilogue warps): a chain CTA then takes 3/4 of the SM's register file instead of all of it, so
-// it can start on an SM that still hosts a few small CTAs of other streams' kernels, and vice versa.
-// PAIR (chains only): two CTAs of a cluster, each with its own 128-row tile, share every weight tile -- each
-// stages HALF of it (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared
-// memories and both CTAs drain their own accumulator rows.  A ring byte then feeds 256 rows instead of 128: the
-// same 64 KB ring keeps 8 k-block stages in flight instead of 4 (the chains are bound by that ring's latency).
-template <bool CHAIN, bool PAIR = false>
-__global__ void __launch_bounds__(CHAIN ? CHAIN_THREADS : FUSED_THREADS, 1) __maxnreg__(CHAIN ? CHAIN_MAXNREG : 168)
-decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
-    constexpr int NWK = CHAIN ? NW_CHAIN : NW;   // worker warps of this instantiation
-    static_assert(CHAIN || !PAIR, "CTA pairs exist for the chain kernels only");
+__device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedParams& p, int chunk_idx, float (&top)[5]) {
+    const int b = acquire_acc(c, 2);
+    const int row = c.quad * 32 + c.lane;
+    const int grow = c.r0 + row;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int colc = (c.half * 4 + i) * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
+        tmem_ld_wait();
+        vocab_group(c, p, chunk_idx, colc, grow, v, top);
+    }
+    release_acc(c, 2, b);
+}
+
+// The chain kernel.  Capped at 128 registers per thread (setmaxnreg then moves them: 40 for the control warps, 168 for
+// the epilogue warps): a chain CTA then takes 3/4 of the SM's register file instead of all of it, so it can start on an
+// SM that still hosts a few small CTAs of other streams' kernels, and vice versa.
+// (nvcc rejects __launch_bounds__ next to __maxnreg__ unless their arguments depend on a template parameter.)
+// TRACE (cap_debug_fused_trace): a separate instantiation whose control warps account their waiting time per CTA into
+// trace[tile * 64 + k] (SM clock cycles): issuer k = 0 total, 1 waiting for weight stages (b_full), 2 for free
+// accumulators (epilogues), 3 for the A tile (a_ready / a_load), 4 for streamed A blocks; producer k = 8 total, 9 waiting
+// for free ring stages (b_empty), 10 for the hidden tile / free A slots.  The production instantiation carries none of it.
+template <bool PAIR, bool TRACE = false>
+__global__ void __launch_bounds__(PAIR ? CHAIN_THREADS : CHAIN_THREADS, 1) __maxnreg__(PAIR ? CHAIN_MAXNREG : CHAIN_MAXNREG)
+decode_chain_kernel(const __grid_constant__ FusedParams p) {
     constexpr int NBX = PAIR ? NB_PAIR : NB;
     constexpr uint32_t BST = PAIR ? B_STAGE_BYTES_PAIR : B_STAGE_BYTES;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -896,17 +621,16 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     uint64_t* a_empty = a_full + A_SLOTS;
     uint64_t* acc_full = a_empty + A_SLOTS;
     uint64_t* acc_empty = acc_full + 2;
-    uint64_t* a_ready = acc_empty + 2;
-    uint64_t* h_ready = a_ready + 1;
-    uint64_t* ring_free = h_ready + 1;
-    uint64_t* a_load = ring_free + 1;
+    uint64_t* a_ready = acc_empty + 2;   // workers -> issuer: the resident A tile is complete
+    uint64_t* h_ready = a_ready + 1;     // workers -> producer: the hidden tile is complete (global, proxy-fenced)
+    uint64_t* a_load = h_ready + 1;      // TMA -> issuer: a tile of attention output has landed in the resident A buffer
+    uint64_t* a_free = a_load + 1;       // issuer -> loader: every MMA that reads the resident A buffer has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
-    const int job_lo = CHAIN ? p.job_begin : 0;
-    const int job_hi = CHAIN ? p.job_end : p.n_layers * 6;
+    const int n_jobs = p.n_jobs;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w512)) : "memory");
@@ -916,14 +640,14 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     }
     if (warp == 1) {
         if (lane == 0) {
-            constexpr int consumers = PAIR ? 2 * NWK : NWK;   // pair: the leader's barriers hear both CTAs' workers
+            constexpr int consumers = PAIR ? 2 * NW : NW;   // pair: the leader's barriers hear both CTAs' workers
             for (int s = 0; s < NBX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
             for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
             for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], consumers); }
             mbar_init(a_ready, consumers);
-            mbar_init(h_ready, NWK);
-            mbar_init(ring_free, NWK);
+            mbar_init(h_ready, NW);
             mbar_init(a_load, 1);
+            mbar_init(a_free, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -937,51 +661,60 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
     if (warp < FIRST_WORKER_WARP) {
     // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
     // the register limit of each region is unambiguous to ptxas)
-    if constexpr (CHAIN) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // 128 x 40 + 512 x 104 regs
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");                    // to squeeze these warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // 128 x 40 + 256 x 168 = 48 k of the 64 k registers
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (weights never wait)
         // The whole warp runs the loop (uniform control flow); one elected lane issues the copies.
-        uint32_t bcount = 0, acount = 0, hphase = 0, rphase = 0;
+        uint32_t bcount = 0, acount = 0, hphase = 0;
+        uint32_t tr_t0 = 0, tr_b = 0, tr_a = 0;
+        if constexpr (TRACE) tr_t0 = static_cast<uint32_t>(clock64());
+#define TRACED_WAIT(acc, stmt)                                                \
+    do {                                                                      \
+        if constexpr (TRACE) {                                                \
+            const uint32_t t_ = static_cast<uint32_t>(clock64());             \
+            stmt;                                                             \
+            acc += static_cast<uint32_t>(clock64()) - t_;                     \
+        } else {                                                              \
+            stmt;                                                             \
+        }                                                                     \
+    } while (0)
         const uint64_t keep_policy = l2_policy_evict_last();   // weights: shared by every tile of every batch in flight
-        for (int ji = job_lo; ji <= job_hi; ++ji) {
-            const Job job = get_job(p, ji);
-            const int nch = job.ntiles / job.chunk;
-            if (!CHAIN && ji < p.n_layers * 6 && (ji % 6 == 1 || ji % 6 == 3)) {
-                // fc_o follows an attention phase, which borrows the weight ring for its K|V rows
-                mbar_wait(ring_free, rphase);
-                rphase ^= 1;
-            }
+        for (int ji = 0; ji < n_jobs; ++ji) {
+            const JobDesc& job = p.jobs[ji];
+            const CUtensorMap* map = job.wmap == 0 ? (PAIR ? &p.map_w512_h : &p.map_w512)
+                                   : job.wmap == 1 ? (PAIR ? &p.map_w2_h : &p.map_w2)
+                                                   : (PAIR ? &p.map_vocab_h : &p.map_vocab);
+            const int chunk = job.chunk, kblocks = job.kblocks;   // read once (see epilogue_store)
+            const int nch = job.ntiles / chunk;
+            const int row_base = job.row0 + (PAIR ? static_cast<int>(rank) * 64 : 0);
+            const bool stream = job.a_src == JA_STREAM_HIDDEN;
             for (int c = 0; c < nch; ++c) {
-                for (int kb = 0; kb < job.kblocks; ++kb) {
-                    for (int j = 0; j < job.chunk; ++j) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int j = 0; j < chunk; ++j) {
                         const uint32_t s = bcount % NBX;
-                        mbar_wait(&b_empty[s], ((bcount / NBX) & 1) ^ 1);
+                        TRACED_WAIT(tr_b, mbar_wait(&b_empty[s], ((bcount / NBX) & 1) ^ 1));
                         if (elect_one_sync()) {
                             if constexpr (PAIR) {
                                 // both CTAs signal the LEADER's barrier, which expects the two halves of the tile
                                 if (leader) mbar_arrive_expect_tx(&b_full[s], 2 * BST);
-                                tma_load_2d_2sm_hint(B_ring + s * BST, job.map_half, &b_full[s], kb * BLOCK_K,
-                                                     job.row0 + (c * job.chunk + j) * 128 + static_cast<int>(rank) * 64,
+                                tma_load_2d_2sm_hint(B_ring + s * BST, map, &b_full[s], kb * BLOCK_K, row_base + (c * chunk + j) * 128,
                                                      keep_policy);
-                            } else if (p.dbg_skip & 2) {
-                                mbar_arrive(&b_full[s]);
                             } else {
                                 mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
-                                tma_load_2d_hint(B_ring + s * B_STAGE_BYTES, job.map, &b_full[s], kb * BLOCK_K,
-                                                 job.row0 + (c * job.chunk + j) * 128, keep_policy);
+                                tma_load_2d_hint(B_ring + s * B_STAGE_BYTES, map, &b_full[s], kb * BLOCK_K,
+                                                 row_base + (c * chunk + j) * 128, keep_policy);
                             }
                         }
                         __syncwarp();
                         ++bcount;
                     }
-                    if (job.stream) {
+                    if (stream) {
                         if (kb == 0) {  // the workers have written (and proxy-fenced) the whole hidden tile
-                            mbar_wait(h_ready, hphase);
+                            TRACED_WAIT(tr_a, mbar_wait(h_ready, hphase));
                             hphase ^= 1;
                         }
                         const uint32_t slot = acount % A_SLOTS;
-                        mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1);
+                        TRACED_WAIT(tr_a, mbar_wait(&a_empty[slot], ((acount / A_SLOTS) & 1) ^ 1));
                         if (elect_one_sync()) {
                             if constexpr (PAIR) {
                                 if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * A_KB_BYTES);
@@ -997,6 +730,13 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                 }
             }
         }
+        if constexpr (TRACE) {
+            if (p.trace != nullptr && lane == 0) {
+                p.trace[static_cast<size_t>(tile) * 64 + 8] = static_cast<uint32_t>(clock64()) - tr_t0;
+                p.trace[static_cast<size_t>(tile) * 64 + 9] = tr_b;
+                p.trace[static_cast<size_t>(tile) * 64 + 10] = tr_a;
+            }
+        }
         pdl_launch_dependents();
     } else if (warp == 1 && leader) {
         // ------------------------------------------------------------------ MMA issuer (pair: the leader's only)
@@ -1009,71 +749,74 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         auto commit = [](uint64_t* bar) {
             if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar);
         };
-        uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0;
+        uint32_t bcount = 0, acount = 0, use0 = 0, use1 = 0, ar = 0, al = 0;
         int toggle = 0;
-        for (int ji = job_lo; ji <= job_hi; ++ji) {
-            const Job job = get_job(p, ji);
-            const int nch = job.ntiles / job.chunk;
-            if (CHAIN && ji == job_lo && !p.start_embed) {
-                mbar_wait(a_load, 0);   // the chain's first A tile arrives by TMA (warp 2)
-            } else if (!job.stream) {
-                wait_consumers(a_ready, ar & 1);
+        uint32_t tr_t0 = 0, tr_b = 0, tr_acc = 0, tr_a = 0, tr_s = 0;
+        if constexpr (TRACE) tr_t0 = static_cast<uint32_t>(clock64());
+        for (int ji = 0; ji < n_jobs; ++ji) {
+            const JobDesc& job = p.jobs[ji];
+            const int chunk = job.chunk, kblocks = job.kblocks;   // read once (see epilogue_store)
+            const int nch = job.ntiles / chunk;
+            const bool stream = job.a_src == JA_STREAM_HIDDEN;
+            if (job.a_src == JA_TMA_TILE) {
+                TRACED_WAIT(tr_a, mbar_wait(a_load, al & 1));   // this job's A tile arrives by TMA (warp 2)
+                ++al;
+            } else if (job.flags & JF_WAIT_A) {
+                TRACED_WAIT(tr_a, wait_consumers(a_ready, ar & 1));
                 ++ar;
             }
             tcgen05_fence_after();
             for (int c = 0; c < nch; ++c) {
                 int b = 0;
                 uint32_t colbase = 0;
-                if (job.chunk == 4) {
-                    wait_consumers(&acc_empty[0], (use0 & 1) ^ 1);
-                    wait_consumers(&acc_empty[1], (use1 & 1) ^ 1);
+                if (chunk == 4) {
+                    TRACED_WAIT(tr_acc, wait_consumers(&acc_empty[0], (use0 & 1) ^ 1));
+                    TRACED_WAIT(tr_acc, wait_consumers(&acc_empty[1], (use1 & 1) ^ 1));
                 } else {
                     b = toggle;
-                    wait_consumers(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
+                    TRACED_WAIT(tr_acc, wait_consumers(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1));
                     colbase = b * 256;
                 }
                 tcgen05_fence_after();
-                for (int kb = 0; kb < job.kblocks; ++kb) {
+                for (int kb = 0; kb < kblocks; ++kb) {
                     const uint8_t* a_tile;
                     uint32_t slot = 0;
-                    if (job.stream) {
+                    if (stream) {
                         slot = acount % A_SLOTS;
-                        mbar_wait(&a_full[slot], (acount / A_SLOTS) & 1);
+                        TRACED_WAIT(tr_s, mbar_wait(&a_full[slot], (acount / A_SLOTS) & 1));
                         a_tile = A_buf + slot * A_KB_BYTES;
                     } else {
                         a_tile = A_buf + kb * A_KB_BYTES;
                     }
                     const uint64_t a_desc = make_smem_desc(a_tile);
-                    for (int j = 0; j < job.chunk; ++j) {
+                    for (int j = 0; j < chunk; ++j) {
                         const uint32_t s = bcount % NBX;
-                        mbar_wait(&b_full[s], (bcount / NBX) & 1);
+                        TRACED_WAIT(tr_b, mbar_wait(&b_full[s], (bcount / NBX) & 1));
                         tcgen05_fence_after();
                         const uint64_t b_desc = make_smem_desc(B_ring + s * BST);
                         if (elect_one_sync()) {
-                            if (!(p.dbg_skip & 1)) {
 #pragma unroll
-                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                    if constexpr (PAIR)
-                                        umma_bf16_2sm(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                                      (kb | k) != 0 ? 1u : 0u);
-                                    else
-                                        umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                if constexpr (PAIR)
+                                    umma_bf16_2sm(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
                                                   (kb | k) != 0 ? 1u : 0u);
-                                }
+                                else
+                                    umma_bf16(tmem_base + colbase + j * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                              (kb | k) != 0 ? 1u : 0u);
                             }
                             commit(&b_empty[s]);  // stage reusable (in both CTAs) once these MMAs have read it
                         }
                         __syncwarp();
                         ++bcount;
                     }
-                    if (job.stream) {
+                    if (stream) {
                         if (elect_one_sync()) commit(&a_empty[slot]);
                         __syncwarp();
                         ++acount;
                     }
                 }
                 if (elect_one_sync()) {
-                    if (job.chunk == 4) {
+                    if (chunk == 4) {
                         commit(&acc_full[0]);
                         commit(&acc_full[1]);
                     } else {
@@ -1081,7 +824,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     }
                 }
                 __syncwarp();
-                if (job.chunk == 4) {
+                if (chunk == 4) {
                     ++use0; ++use1;
                     toggle = 0;
                 } else {
@@ -1089,32 +832,51 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
                     toggle ^= 1;
                 }
             }
+            // the next job's A tile comes by TMA into the resident buffer: free once every MMA issued so far has read it
+            if (ji + 1 < n_jobs && p.jobs[ji + 1].a_src == JA_TMA_TILE) {
+                if (elect_one_sync()) commit(a_free);
+                __syncwarp();
+            }
         }
 #undef wait_consumers
+        if constexpr (TRACE) {
+            if (p.trace != nullptr && lane == 0) {
+                unsigned long long* tr = p.trace + static_cast<size_t>(tile) * 64;
+                tr[0] = static_cast<uint32_t>(clock64()) - tr_t0;
+                tr[1] = tr_b; tr[2] = tr_acc; tr[3] = tr_a; tr[4] = tr_s;
+            }
+        }
+#undef TRACED_WAIT
         pdl_launch_dependents();
-    } else if (CHAIN && warp == 2) {
-        // ------------------------------------------------------------------ A-tile loader (chain mode)
-        if (!p.start_embed) {
-            pdl_wait();  // the attention kernel that wrote the tile is the stream predecessor
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ A-tile loader
+        uint32_t loads = 0, frees = 0;
+        for (int ji = 0; ji < n_jobs; ++ji) {
+            const JobDesc& job = p.jobs[ji];
+            if (job.a_src != JA_TMA_TILE) continue;
+            if (loads == 0) pdl_wait();  // the attention kernel that wrote the tile is a stream predecessor
+            if (ji > 0) {                // the buffer is still the operand of earlier jobs
+                mbar_wait(a_free, frees & 1);
+                ++frees;
+            }
             if (elect_one_sync()) {
                 if constexpr (PAIR) {
                     if (leader) mbar_arrive_expect_tx(a_load, 2 * A_SLOTS * A_KB_BYTES);
                     for (int kb = 0; kb < A_SLOTS; ++kb)
-                        tma_load_2d_2sm(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, tile * TILE_ROWS);
+                        tma_load_2d_2sm(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, job.att_row0 + tile * TILE_ROWS);
                 } else {
                     mbar_arrive_expect_tx(a_load, A_SLOTS * A_KB_BYTES);
                     for (int kb = 0; kb < A_SLOTS; ++kb)
-                        tma_load_2d(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, tile * TILE_ROWS);
+                        tma_load_2d(A_buf + kb * A_KB_BYTES, &p.map_att, a_load, kb * BLOCK_K, job.att_row0 + tile * TILE_ROWS);
                 }
             }
             __syncwarp();
+            ++loads;
         }
     }
     } else {
         // ------------------------------------------------------------------ workers
-        if constexpr (CHAIN && NW_CHAIN == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
-        else if constexpr (CHAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
         WorkerCtx c;
         c.A_buf = A_buf;
         c.ww = warp - FIRST_WORKER_WARP;
@@ -1122,9 +884,7 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.half = c.ww >> 2;
         c.lane = lane;
         c.wtid = threadIdx.x - FIRST_WORKER_WARP * 32;
-        c.nw = NWK;
-        c.nsub = NWK / 4;
-        c.stage = smem + OFF_STAGE + c.ww * 32 * (NWK == NW ? STAGE_PITCH : STAGE_PITCH_CHAIN);   // matches staged_store's `wide`
+        c.stage = smem + OFF_STAGE + c.ww * 32 * STAGE_PITCH;
         c.s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
         c.s_cbias = reinterpret_cast<float*>(smem + OFF_CBIAS);
         c.s_gamma = reinterpret_cast<float*>(smem + OFF_GAMMA);
@@ -1134,8 +894,6 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.acc_empty = acc_empty;
         c.a_ready = a_ready;
         c.h_ready = h_ready;
-        c.ring_free = ring_free;
-        c.kv_ring = B_ring + c.ww * KV_SLOTS * KV_ROW_BYTES;
         c.pair_peer = PAIR && !leader;
         c.tmem_base = tmem_base;
         c.use0 = c.use1 = 0;
@@ -1145,89 +903,39 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
         c.rows_valid_warp = max(0, min(32, p.R - (c.r0 + c.quad * 32)));
 
         float bias_reg = 0.f;
-        if constexpr (CHAIN) {
-            pdl_wait();  // everything this chain reads was written by stream predecessors
-            uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
-            if (p.start_embed) {
-                embed_phase(c, p);
-                workers_sync(c.nw);
-                publish_a(c);
-            }
-            for (int ji = job_lo; ji <= job_hi; ++ji) {
-                if (ji == p.n_layers * 6) {
-                    pdl_launch_dependents();
-                    const int vchunks = p.vocab_tiles / 2;
-                    float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
-                    break;
-                }
-                const int L = ji / 6, k = ji % 6;
-                const FusedLayerP& W = p.layer[L];
-                if (k == 0) {
-                    bf16* cache_t = p.qkv_cache + (static_cast<size_t>(L) * p.T + p.t) * p.R * 3 * FD;
-                    for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
-                } else if (k == 1) {
-                    epilogue_layernorm<true>(c, p, W.b_o1, W.g1, W.be1, nullptr);
-                } else if (k == 2) {
-                    for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_q, ch, 2, bias_reg, p.q_out, FD);
-                } else if (k == 3) {
-                    epilogue_layernorm<true>(c, p, W.b_o2, W.g2, W.be2, nullptr);
-                } else if (k == 4) {
-                    for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
+        pdl_wait();  // everything this chain reads was written by stream predecessors
+        if (p.start_embed) {
+            embed_phase(c, p);
+            workers_sync();   // the residual tile was written warp-per-row, the epilogues read it thread-per-row
+            publish_a(c);
+        }
+        float* mix_stream = nullptr;   // the meshed mix accumulates in the stream the first level's gate job names
+        for (int ji = 0; ji < n_jobs; ++ji) {
+            const JobDesc& job = p.jobs[ji];
+            if (job.epi == JE_STORE) {
+                const int nch = job.ntiles / 2;
+                for (int ch = 0; ch < nch; ++ch) epilogue_store(c, p, job, ch, nch, bias_reg);
+                if (job.flags & JF_HIDDEN_DONE) {
                     fence_proxy_async();  // hidden tile (global, generic proxy) -> TMA reads (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready);
-                } else {
-                    epilogue_layernorm<true>(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
                 }
+            } else if (job.epi == JE_LN) {
+                epilogue_layernorm(c, p, job);
+            } else if (job.epi == JE_F32) {
+                const int nch = job.ntiles / 2;
+                for (int ch = 0; ch < nch; ++ch) epilogue_f32(c, p, ch);
+            } else if (job.epi == JE_ALPHA) {
+                if (job.flags & JF_FIRST_LEVEL) mix_stream = job.res_out;
+                epilogue_alpha(c, p, job, mix_stream);
+            } else {   // JE_VOCAB: always the last job of its chain
+                pdl_launch_dependents();
+                const int vchunks = job.ntiles / 2;
+                float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
             }
-            pdl_launch_dependents();
-        } else {
-        const bool tr = (c.ww == 0 && lane == 0);
-        fstamp(p, tile, 0, tr);
-        pdl_wait();  // tokens / ancestry come from the previous step's selection kernel
-        fstamp(p, tile, 1, tr);
-        embed_phase(c, p);
-        workers_sync(c.nw);  // the residual tile was written warp-per-row, the epilogues read it thread-per-row
-        publish_a(c);
-
-        uint8_t* pad_t = p.padflag + static_cast<size_t>(p.t) * p.R;
-        for (int L = 0; L < p.n_layers; ++L) {
-            const FusedLayerP& W = p.layer[L];
-            bf16* cache_l = p.qkv_cache + static_cast<size_t>(L) * p.T * p.R * 3 * FD;
-            bf16* cache_t = cache_l + static_cast<size_t>(p.t) * p.R * 3 * FD;
-            const int sb = 2 + L * 8;
-            fstamp(p, tile, sb, tr);
-            for (int ch = 0; ch < 6; ++ch) epilogue_chunk<EPI_CACHE>(c, p, W.b_qkv, ch, 6, bias_reg, cache_t, 3 * FD);
-            workers_sync(c.nw);  // q|k|v of every row of the tile are in the cache
-            fstamp(p, tile, sb + 1, tr);
-            self_attention_phase(c, p, cache_l);
-            publish_attention(c);
-            fstamp(p, tile, sb + 2, tr);
-            epilogue_layernorm<false>(c, p, W.b_o1, W.g1, W.be1, nullptr);
-            fstamp(p, tile, sb + 3, tr);
-            for (int ch = 0; ch < 2; ++ch) epilogue_chunk<EPI_QG>(c, p, W.b_q, ch, 2, bias_reg, nullptr, 0);
-            workers_sync(c.nw);
-            fstamp(p, tile, sb + 4, tr);
-            cross_attention_phase(c, p, p.cross_kv + static_cast<size_t>(L) * p.cross_layer_stride);
-            publish_attention(c);
-            fstamp(p, tile, sb + 5, tr);
-            epilogue_layernorm<false>(c, p, W.b_o2, W.g2, W.be2, nullptr);
-            fstamp(p, tile, sb + 6, tr);
-            for (int ch = 0; ch < 8; ++ch) epilogue_chunk<EPI_HID>(c, p, W.b_w1, ch, 8, bias_reg, nullptr, 0);
-            fence_proxy_async();  // hidden tile (global, generic proxy) -> bulk-copy reads (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(h_ready);
-            fstamp(p, tile, sb + 7, tr);
-            epilogue_layernorm<false>(c, p, W.b_w2, W.g3, W.be3, pad_t);  // + zero rows fed <pad> (decoders.py:26)
         }
-        fstamp(p, tile, 2 + p.n_layers * 8, tr);
         pdl_launch_dependents();
-        const int vchunks = p.vocab_tiles / 2;
-        float top[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int ch = 0; ch < vchunks; ++ch) epilogue_vocab_chunk(c, p, ch, top);
-        fstamp(p, tile, 3 + p.n_layers * 8, tr);
-            }
     }
     tcgen05_fence_before();
     if constexpr (PAIR) cluster_sync(); else __syncthreads();   // pair: the leader's MMAs read the peer's shared memory
@@ -1240,14 +948,23 @@ decode_step_fused_kernel(const __grid_constant__ FusedParams p) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
-// Stacked bf16 copies of a decoder's projection weights: [layers * 5120][512] (q|k|v, self fc_o, cross fc_q, cross
-// fc_o, fc1 per layer) and [layers * 512][2048] (fc2), so that one TMA tensor map serves every GEMM of a chain.
+// Stacked bf16 copies of a decoder's projection weights, so that one TMA tensor map serves every GEMM of a chain:
+//   K = 512 stack, per layer (plain decoder, 5120 rows):  q|k|v 1536, self fc_o 512, cross fc_q 512, cross fc_o 512, fc1 2048
+//                  per layer (meshed decoder, 8192 rows): q|k|v 1536, self fc_o 512, cross fc_q 512, gates' s-part 3 x 512,
+//                                                          cross fc_o 512, gates' c-part 3 x 512, fc1 2048
+//   fc2 stack [layers * 512][2048].
+// The meshed gates fc_alphas.i are [512][1024] over [s ; c_i] (decoders.py:60-62): W_i[:, :512] multiplies the
+// self-attention output s (one N = 1536 GEMM for the three levels while s is the resident tile), W_i[:, 512:] the
+// level's cross-attention output c_i.
 // One set can serve any number of handles (cap_fused_desc::stacked): engines that pipeline independent batches then
 // stream the SAME addresses, which the evict_last hint keeps L2-resident.
 struct cap_fused_weights {
     void* w512 = nullptr;
     void* w2 = nullptr;
     int n_layers = 0;
+    int levels = 0;          // 0: plain decoder
+    int rows_per_layer = 0;
+    int off_o1 = 0, off_q = 0, off_gate_s = 0, off_o2 = 0, off_gate_c = 0, off_w1 = 0;
 };
 
 extern "C" int cap_fused_weights_destroy(cap_fused_weights* w) {
@@ -1261,23 +978,44 @@ extern "C" int cap_fused_weights_destroy(cap_fused_weights* w) {
 extern "C" int cap_fused_weights_create(const cap_fused_layer* layers, int n_layers, cap_fused_weights** out) {
     CAP_REQUIRE(layers && out, "cap_fused_weights_create: null pointer");
     CAP_REQUIRE(n_layers >= 1 && n_layers <= MAX_FUSED_LAYERS, "cap_fused_weights_create: 1..%d layers", MAX_FUSED_LAYERS);
+    const int levels = layers[0].n_levels;
+    CAP_REQUIRE(levels == 0 || levels == MAX_LEVELS, "cap_fused_weights_create: the meshed chains are written for %d encoder levels", MAX_LEVELS);
     cap_fused_weights* f = new cap_fused_weights();
     f->n_layers = n_layers;
+    f->levels = levels;
+    f->off_o1 = 3 * FD;
+    f->off_q = f->off_o1 + FD;
+    f->off_gate_s = f->off_q + FD;
+    f->off_o2 = f->off_gate_s + levels * FD;
+    f->off_gate_c = f->off_o2 + FD;
+    f->off_w1 = f->off_gate_c + levels * FD;
+    f->rows_per_layer = f->off_w1 + FDFF;
     auto fail = [&](int rc) { cap_fused_weights_destroy(f); return rc; };
-    const size_t w512_elems = static_cast<size_t>(n_layers) * W512_ROWS_PER_LAYER * FD;
+    const size_t w512_elems = static_cast<size_t>(n_layers) * f->rows_per_layer * FD;
     const size_t w2_elems = static_cast<size_t>(n_layers) * FD * FDFF;
     if (cudaMalloc(&f->w512, w512_elems * 2) != cudaSuccess || cudaMalloc(&f->w2, w2_elems * 2) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_weights_create: cudaMalloc of the stacked weights failed"));
     for (int l = 0; l < n_layers; ++l) {
         const cap_fused_layer& w = layers[l];
+        CAP_REQUIRE(w.n_levels == levels, "cap_fused_weights_create: layers disagree on the number of encoder levels");
+        bf16* base = static_cast<bf16*>(f->w512) + static_cast<size_t>(l) * f->rows_per_layer * FD;
         const void* srcs[5] = {w.w_qkv, w.w_o1, w.w_q, w.w_o2, w.w_fc1};
+        const int offs[5] = {0, f->off_o1, f->off_q, f->off_o2, f->off_w1};
         const int rows[5] = {3 * FD, FD, FD, FD, FDFF};
-        bf16* dst = static_cast<bf16*>(f->w512) + static_cast<size_t>(l) * W512_ROWS_PER_LAYER * FD;
         for (int i = 0; i < 5; ++i) {
             if (!srcs[i]) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_weights_create: null weight"));
-            if (cudaMemcpy(dst, srcs[i], static_cast<size_t>(rows[i]) * FD * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
+            if (cudaMemcpy(base + static_cast<size_t>(offs[i]) * FD, srcs[i], static_cast<size_t>(rows[i]) * FD * 2,
+                           cudaMemcpyDeviceToDevice) != cudaSuccess)
                 return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_weights_create: weight copy failed"));
-            dst += static_cast<size_t>(rows[i]) * FD;
+        }
+        for (int i = 0; i < levels; ++i) {   // fc_alphas.i [512][1024] -> s-part and c-part, [512][512] each
+            const bf16* src = static_cast<const bf16*>(w.w_alpha[i]);
+            if (!src) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_weights_create: null gate weight"));
+            bf16* dst_s = base + static_cast<size_t>(f->off_gate_s + i * FD) * FD;
+            bf16* dst_c = base + static_cast<size_t>(f->off_gate_c + i * FD) * FD;
+            if (cudaMemcpy2D(dst_s, FD * 2, src, 2 * FD * 2, FD * 2, FD, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+                cudaMemcpy2D(dst_c, FD * 2, src + FD, 2 * FD * 2, FD * 2, FD, cudaMemcpyDeviceToDevice) != cudaSuccess)
+                return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_weights_create: gate weight copy failed"));
         }
         if (!w.w_fc2 || cudaMemcpy(static_cast<bf16*>(f->w2) + static_cast<size_t>(l) * FD * FDFF, w.w_fc2,
                                    static_cast<size_t>(FD) * FDFF * 2, cudaMemcpyDeviceToDevice) != cudaSuccess)
@@ -1289,9 +1027,14 @@ extern "C" int cap_fused_weights_create(const cap_fused_layer* layers, int n_lay
 
 struct cap_fused_decoder {
     FusedParams base;
+    cap_fused_layer layers[MAX_FUSED_LAYERS];   // bias / LayerNorm pointers (the weight pointers are not used after creation)
     cap_fused_weights* stacked = nullptr;   // the stacked weights the tensor maps point into
     bool owns_stacked = false;              // false: cap_fused_desc::stacked, owned by the caller
+    int n_layers = 0, levels = 0, max_rows = 0;
     int tiles = 0;
+    bf16* qkv_cache = nullptr;   // [layers][T][R][1536]
+    bf16* q_out = nullptr;       // [R][512] cross-attention queries
+    float *res_c = nullptr, *res_mix = nullptr;   // meshed side streams
     bool has_att = false;
     bool use_pairs = true;      // CTA pairs (OPENVIIC_CHAIN_PAIR=0 at creation: single CTAs)
     bool full_logits = false;   // debug / parity: every logit is stored (cap_fused_set_full_logits, OPENVIIC_FULL_LOGITS)
@@ -1304,13 +1047,19 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     CAP_REQUIRE(d->beam >= 1 && d->beam <= MAXB, "cap_fused_create: beam must be 1..%d", MAXB);
     CAP_REQUIRE(d->max_rows > 0 && d->vocab > 8 && d->max_len > 0 && d->max_len <= 40, "cap_fused_create: bad sizes (max_len <= 40)");
     CAP_REQUIRE(d->ld_logits % 32 == 0 && d->ld_logits >= d->vocab, "cap_fused_create: ld_logits must be a multiple of 32");
-    CAP_REQUIRE(d->stacked == nullptr || d->stacked->n_layers == d->n_layers, "cap_fused_create: stacked weights of another model");
+    CAP_REQUIRE(d->layers != nullptr && d->att_in != nullptr && d->q_out != nullptr, "cap_fused_create: null layers / att_in / q_out");
+    const int levels = d->layers[0].n_levels;
+    CAP_REQUIRE(levels == 0 || levels == MAX_LEVELS, "cap_fused_create: the meshed chains are written for %d encoder levels", MAX_LEVELS);
+    CAP_REQUIRE(d->stacked == nullptr || (d->stacked->n_layers == d->n_layers && d->stacked->levels == levels),
+                "cap_fused_create: stacked weights of another model");
     CAP_PROPAGATE(install_fault_buffer());
     cap_fused_decoder* f = new cap_fused_decoder();
     FusedParams& p = f->base;
     memset(&p, 0, sizeof(p));
     const int L = d->n_layers;
-    p.n_layers = L;
+    f->n_layers = L;
+    f->levels = levels;
+    f->max_rows = d->max_rows;
     f->tiles = ((d->max_rows + TILE_ROWS - 1) / TILE_ROWS + 1) / 2 * 2;   // even: CTA pairs; scratch tiles exist for a dummy partner
     auto fail = [&](int rc) { cap_fused_destroy(f); return rc; };
     if (d->stacked) {
@@ -1322,56 +1071,63 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     }
     for (int l = 0; l < L; ++l) {
         const cap_fused_layer& w = d->layers[l];
-        FusedLayerP& lp = p.layer[l];
-        lp.b_qkv = w.b_qkv; lp.b_o1 = w.b_o1; lp.g1 = w.ln1_g; lp.be1 = w.ln1_b;
-        lp.b_q = w.b_q; lp.b_o2 = w.b_o2; lp.g2 = w.ln2_g; lp.be2 = w.ln2_b;
-        lp.b_w1 = w.b_fc1; lp.b_w2 = w.b_fc2; lp.g3 = w.ln3_g; lp.be3 = w.ln3_b;
-        const float* need[12] = {lp.b_qkv, lp.b_o1, lp.g1, lp.be1, lp.b_q, lp.b_o2, lp.g2, lp.be2, lp.b_w1, lp.b_w2, lp.g3, lp.be3};
+        f->layers[l] = w;
+        const float* need[12] = {w.b_qkv, w.b_o1, w.ln1_g, w.ln1_b, w.b_q, w.b_o2, w.ln2_g, w.ln2_b, w.b_fc1, w.b_fc2, w.ln3_g, w.ln3_b};
         for (const float* q : need)
             if (!q) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_create: null bias / LayerNorm parameter"));
+        for (int i = 0; i < levels; ++i)
+            if (!w.b_alpha[i]) return fail(cap_set_error(CAP_ERR_INVALID, "cap_fused_create: null gate bias"));
     }
     void* const w512 = f->stacked->w512;
     void* const w2 = f->stacked->w2;
-    int rc = cap_gemm::make_tmap(&p.map_w512, w512, L * W512_ROWS_PER_LAYER, FD, FD, 128);
+    const int rpl = f->stacked->rows_per_layer;
+    int rc = cap_gemm::make_tmap(&p.map_w512, w512, L * rpl, FD, FD, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, w2, L * FD, FDFF, FDFF, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, d->w_vocab, d->vocab, FD, FD, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, w512, L * W512_ROWS_PER_LAYER, FD, FD, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, w512, L * rpl, FD, FD, 64);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, w2, L * FD, FDFF, FDFF, 64);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab_h, d->w_vocab, d->vocab, FD, FD, 64);
     if (rc != CAP_OK) return fail(rc);
     p.tokens = d->tokens; p.word_emb = static_cast<const bf16*>(d->word_emb); p.word_pos = d->word_pos; p.pad_idx = d->pad_idx;
-    p.qkv_cache = static_cast<bf16*>(d->qkv_cache); p.ancestry = d->ancestry; p.padflag = d->padflag;
-    p.cross_kv = static_cast<const bf16*>(d->cross_kv); p.cross_layer_stride = d->cross_layer_stride; p.enc_mask = d->enc_mask;
+    p.padflag = d->padflag;
+    f->qkv_cache = static_cast<bf16*>(d->qkv_cache);
     p.logits = d->logits; p.ld_logits = d->ld_logits; p.part_ms = d->part_ms;
     p.vocab = d->vocab;
     p.vocab_tiles = ((d->vocab + 255) / 256) * 2;
     p.stat_chunks = ((d->vocab + 255) / 256) * 8;
     p.T = d->max_len; p.beam = d->beam;
-    p.scale = 1.0f / sqrtf(static_cast<float>(FD / FHEADS));
+    p.level_scale = levels > 0 ? 1.0f / sqrtf(static_cast<float>(levels)) : 1.0f;
+    p.aux_cols = levels * FD;
     const size_t tiles = f->tiles;
-    void *res = nullptr, *qg = nullptr, *hb = nullptr;
-    if (cudaMalloc(&res, tiles * TILE_ROWS * FD * 4) != cudaSuccess || cudaMalloc(&qg, tiles * TILE_ROWS * FD * 2) != cudaSuccess ||
-        cudaMalloc(&hb, tiles * TILE_ROWS * FDFF * 2) != cudaSuccess) {
-        cudaFree(res); cudaFree(qg); cudaFree(hb);
-        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cudaMalloc of the scratch tiles failed"));
-    }
-    cudaMemset(res, 0, tiles * TILE_ROWS * FD * 4);
-    cudaMemset(qg, 0, tiles * TILE_ROWS * FD * 2);
+    const size_t stream_bytes = tiles * TILE_ROWS * FD * 4;
+    void *res = nullptr, *hb = nullptr, *aux = nullptr, *rc_ = nullptr, *rm = nullptr;
+    bool ok = cudaMalloc(&res, stream_bytes) == cudaSuccess && cudaMalloc(&hb, tiles * TILE_ROWS * FDFF * 2) == cudaSuccess;
+    if (ok && levels > 0)
+        ok = cudaMalloc(&aux, stream_bytes * levels) == cudaSuccess && cudaMalloc(&rc_, stream_bytes) == cudaSuccess &&
+             cudaMalloc(&rm, stream_bytes) == cudaSuccess;
+    p.res = static_cast<float*>(res); p.hbuf = static_cast<bf16*>(hb); p.aux = static_cast<float*>(aux);
+    f->res_c = static_cast<float*>(rc_); f->res_mix = static_cast<float*>(rm);
+    if (!ok) return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cudaMalloc of the scratch tiles failed"));
+    cudaMemset(res, 0, stream_bytes);
     cudaMemset(hb, 0, tiles * TILE_ROWS * FDFF * 2);
-    p.res = static_cast<float*>(res); p.qg = static_cast<bf16*>(qg); p.hbuf = static_cast<bf16*>(hb);
+    if (levels > 0) {
+        cudaMemset(aux, 0, stream_bytes * levels);
+        cudaMemset(rc_, 0, stream_bytes);
+        cudaMemset(rm, 0, stream_bytes);
+    }
     rc = cap_gemm::make_tmap(&p.map_h, hb, static_cast<int>(tiles) * TILE_ROWS, FDFF, FDFF, 128);
     if (rc != CAP_OK) return fail(rc);
-    if (d->att_in) {
-        rc = cap_gemm::make_tmap(&p.map_att, d->att_in, d->max_rows, FD, FD, 128);
-        if (rc != CAP_OK) return fail(rc);
-    }
-    p.q_out = static_cast<bf16*>(d->q_out);
-    f->has_att = d->att_in != nullptr;
+    // attention outputs: [levels][max_rows][512] (one level for the plain decoder)
+    rc = cap_gemm::make_tmap(&p.map_att, d->att_in, (levels > 0 ? levels : 1) * d->max_rows, FD, FD, 128);
+    if (rc != CAP_OK) return fail(rc);
+    f->q_out = static_cast<bf16*>(d->q_out);
+    f->has_att = true;
     f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
     f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
-    if (cudaFuncSetAttribute(decode_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(decode_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
         return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
     *out = f;
     return CAP_OK;
@@ -1389,8 +1145,10 @@ extern "C" int cap_fused_destroy(cap_fused_decoder* f) {
     if (!f) return CAP_OK;
     if (f->owns_stacked) cap_fused_weights_destroy(f->stacked);
     cudaFree(f->base.res);
-    cudaFree(f->base.qg);
     cudaFree(f->base.hbuf);
+    cudaFree(f->base.aux);
+    cudaFree(f->res_c);
+    cudaFree(f->res_mix);
     delete f;
     return CAP_OK;
 }
@@ -1401,45 +1159,106 @@ extern "C" int cap_debug_fused_trace(unsigned long long* device_buffer) {
     return CAP_OK;
 }
 
-extern "C" int cap_fused_decode_step(cap_fused_decoder* f, int t, int B, int n_keys, cap_stream_t stream) {
-    CAP_REQUIRE(f != nullptr, "cap_fused_decode_step: null handle");
-    FusedParams p = f->base;
-    CAP_REQUIRE(t >= 0 && t < p.T, "cap_fused_decode_step: step %d outside [0,%d)", t, p.T);
-    const int R = B * p.beam;
-    const int tiles = (R + TILE_ROWS - 1) / TILE_ROWS;
-    CAP_REQUIRE(B > 0 && tiles <= f->tiles && n_keys > 0 && n_keys <= 128, "cap_fused_decode_step: batch %d / %d keys unsupported", B, n_keys);
-    p.t = t; p.R = R; p.B = B; p.n_keys = n_keys;
-    p.trace = g_fused_trace;
-    static const int dbg_skip = getenv("OPENVIIC_FUSED_DBG_SKIP") ? atoi(getenv("OPENVIIC_FUSED_DBG_SKIP")) : 0;
-    p.dbg_skip = dbg_skip;
-    // plain launch (no programmatic dependent launch), for the reason given in cap_fused_chain below
-    decode_step_fused_kernel<false><<<dim3(tiles), dim3(FUSED_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
-    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
-    return cap_check_launch("decode_step_fused_kernel");
-}
+namespace {
+// ---- job lists ------------------------------------------------------------------------------------------------
+struct JobList {
+    FusedParams& p;
+    const cap_fused_decoder& f;
+    int layer;
+    JobDesc& add() {
+        if (p.n_jobs >= MAX_JOBS) p.n_jobs = MAX_JOBS - 1;   // reported by the caller's size check (never hit by the lists below)
+        JobDesc& j = p.jobs[p.n_jobs++];
+        memset(&j, 0, sizeof(j));
+        j.kblocks = FD / BLOCK_K;
+        j.chunk = 2;
+        j.a_src = JA_RESIDENT;
+        return j;
+    }
+    int base() const { return layer * f.stacked->rows_per_layer; }
+    const cap_fused_layer& w() const { return f.layers[layer]; }
+    // q|k|v of the new token of `layer` -> cache slot of step t
+    void qkv() {
+        JobDesc& j = add();
+        j.row0 = base(); j.ntiles = 12; j.epi = JE_STORE; j.bias = w().b_qkv;
+        j.dst = f.qkv_cache + (static_cast<size_t>(layer) * p.T + p.t) * p.R * 3 * FD;
+        j.ld_dst = 3 * FD;
+    }
+    void vocab() {
+        JobDesc& j = add();
+        j.wmap = 2; j.row0 = 0; j.ntiles = p.vocab_tiles; j.epi = JE_VOCAB;
+    }
+    // fc_o of an attention + residual + LayerNorm; the tile of attention outputs arrives by TMA
+    void attention_out(const float* bias, const float* g, const float* b, int weight_off, int att_row0, const float* res_in, float* res_out) {
+        JobDesc& j = add();
+        j.row0 = base() + weight_off; j.ntiles = 4; j.chunk = 4; j.a_src = JA_TMA_TILE; j.att_row0 = att_row0; j.epi = JE_LN;
+        j.bias = bias; j.gamma = g; j.beta = b; j.res_in = res_in; j.res_out = res_out;
+    }
+    void ffn_and_next() {
+        JobDesc& a = add();   // fc1 + ReLU -> hidden scratch
+        a.row0 = base() + f.stacked->off_w1; a.ntiles = 16; a.epi = JE_STORE; a.flags = JF_RELU | JF_WHOLE_TILES | JF_HIDDEN_DONE;
+        a.bias = w().b_fc1; a.dst = p.hbuf; a.ld_dst = FDFF;
+        JobDesc& b = add();   // fc2 + residual + LayerNorm, rows fed <pad> zeroed (decoders.py:26)
+        b.wmap = 1; b.row0 = layer * FD; b.ntiles = 4; b.chunk = 4; b.kblocks = FDFF / BLOCK_K; b.a_src = JA_STREAM_HIDDEN; b.epi = JE_LN;
+        b.bias = w().b_fc2; b.gamma = w().ln3_g; b.beta = w().ln3_b; b.res_in = p.res; b.res_out = p.res;
+        b.zero_rows = p.padflag + static_cast<size_t>(p.t) * p.R;
+        if (layer + 1 < f.n_layers) { ++layer; qkv(); --layer; } else vocab();
+    }
+};
+}  // namespace
 
 extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t, int B, cap_stream_t stream) {
     CAP_REQUIRE(f != nullptr, "cap_fused_chain: null handle");
     FusedParams p = f->base;
     CAP_REQUIRE(t >= 0 && t < p.T, "cap_fused_chain: step %d outside [0,%d)", t, p.T);
-    CAP_REQUIRE(chain >= CAP_CHAIN_EMBED_QKV && chain <= CAP_CHAIN_FFN && layer >= 0 && layer < p.n_layers,
+    CAP_REQUIRE(chain >= CAP_CHAIN_EMBED_QKV && chain <= CAP_CHAIN_FFN && layer >= 0 && layer < f->n_layers,
                 "cap_fused_chain: bad chain %d / layer %d", chain, layer);
-    CAP_REQUIRE(p.q_out != nullptr && (chain == CAP_CHAIN_EMBED_QKV || f->has_att), "cap_fused_chain: handle has no att_in / q_out buffers");
     const int R = B * p.beam;
     const int tiles = (R + TILE_ROWS - 1) / TILE_ROWS;
-    CAP_REQUIRE(B > 0 && tiles <= f->tiles, "cap_fused_chain: batch %d exceeds the reservation", B);
-    p.t = t; p.R = R; p.B = B; p.n_keys = 0;
+    CAP_REQUIRE(B > 0 && tiles <= f->tiles && R <= f->max_rows, "cap_fused_chain: batch %d exceeds the reservation", B);
+    p.t = t; p.R = R; p.B = B;
     p.sparse_logits = (f->full_logits || p.beam > 5) ? 0 : 1;
-    p.trace = g_fused_trace;   // debug (cap_debug_fused_trace): the epilogue stamps of fc1's chunk 3, else nullptr
-    p.dbg_skip = 0;
+    // debug (cap_debug_fused_trace): one region of 64 tiles x 64 words per (chain kind, layer), else nullptr
+    p.trace = g_fused_trace ? g_fused_trace + static_cast<size_t>(chain * MAX_FUSED_LAYERS + layer) * 64 * 64 : nullptr;
+    CAP_REQUIRE(p.trace == nullptr || tiles <= 64, "cap_fused_chain: the trace buffer holds 64 tiles");
     p.start_embed = 0;
+    p.n_jobs = 0;
+    JobList jl{p, *f, layer};
+    const cap_fused_layer& w = f->layers[layer];
+    const cap_fused_weights& sw = *f->stacked;
     if (chain == CAP_CHAIN_EMBED_QKV) {          // x = Emb + pos; q|k|v of layer 0 -> cache
         CAP_REQUIRE(layer == 0, "cap_fused_chain: the embedding chain belongs to layer 0");
-        p.start_embed = 1; p.job_begin = 0; p.job_end = 0;
-    } else if (chain == CAP_CHAIN_SELF_OUT) {    // self fc_o + LN; cross fc_q -> q_out
-        p.job_begin = layer * 6 + 1; p.job_end = layer * 6 + 2;
-    } else {                                     // cross fc_o + LN; FFN + LN; next layer's q|k|v or the vocabulary
-        p.job_begin = layer * 6 + 3; p.job_end = layer * 6 + 6;
+        p.start_embed = 1;
+        jl.qkv();
+    } else if (chain == CAP_CHAIN_SELF_OUT) {    // self fc_o + LN; cross fc_q -> q_out; meshed: the gates' s-part
+        jl.attention_out(w.b_o1, w.ln1_g, w.ln1_b, sw.off_o1, 0, p.res, p.res);
+        JobDesc& q = jl.add();
+        q.row0 = jl.base() + sw.off_q; q.ntiles = 4; q.epi = JE_STORE; q.bias = w.b_q; q.dst = f->q_out; q.ld_dst = FD;
+        if (f->levels > 0) {
+            JobDesc& g = jl.add();
+            g.row0 = jl.base() + sw.off_gate_s; g.ntiles = 4 * f->levels; g.epi = JE_F32;
+        }
+    } else if (f->levels == 0) {                 // cross fc_o + LN; FFN + LN; next layer's q|k|v or the vocabulary
+        jl.attention_out(w.b_o2, w.ln2_g, w.ln2_b, sw.off_o2, 0, p.res, p.res);
+        jl.ffn_and_next();
+    } else {                                     // meshed: per level cross fc_o + LN -> c_i, gate_i, mix; then as above
+        for (int i = 0; i < f->levels; ++i) {
+            jl.attention_out(w.b_o2, w.ln2_g, w.ln2_b, sw.off_o2, i * f->max_rows, p.res, f->res_c);   // same enc_attn weights per level (decoders.py:35,56)
+            JobDesc& a = jl.add();
+            a.row0 = jl.base() + sw.off_gate_c + i * FD; a.ntiles = 4; a.chunk = 4; a.epi = JE_ALPHA; a.bias = w.b_alpha[i];
+            a.aux_col0 = i * FD; a.res_in = f->res_c;
+            a.flags = (i == 0 ? JF_FIRST_LEVEL : 0) | (i == f->levels - 1 ? JF_LAST_LEVEL : 0);
+            a.res_out = (i == f->levels - 1) ? p.res : f->res_mix;   // the last level hands the scaled mix on as the FFN's residual
+        }
+        jl.ffn_and_next();
+    }
+    CAP_REQUIRE(p.n_jobs <= MAX_JOBS, "cap_fused_chain: job list overflow");
+    for (int ji = 0; ji < p.n_jobs; ++ji) {   // which jobs start from a freshly written resident tile
+        JobDesc& j = p.jobs[ji];
+        if (j.a_src != JA_RESIDENT) continue;
+        const bool fresh = ji == 0 ? p.start_embed != 0
+                                   : (p.jobs[ji - 1].epi == JE_LN || (p.jobs[ji - 1].epi == JE_ALPHA && (p.jobs[ji - 1].flags & JF_LAST_LEVEL)));
+        if (fresh) j.flags |= JF_WAIT_A;
+        CAP_REQUIRE(ji > 0 || p.start_embed, "cap_fused_chain: the first job has no A tile");
     }
     // No programmatic dependent launch for a chain: its CTAs each take a whole SM, and an early-started chain
     // would hold them idle in griddepcontrol.wait until the attention kernel before it has drained.
@@ -1458,10 +1277,13 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, decode_step_fused_kernel<true, true>, p);
+        if (p.trace != nullptr) cudaLaunchKernelEx(&cfg, decode_chain_kernel<true, true>, p);
+        else cudaLaunchKernelEx(&cfg, decode_chain_kernel<true>, p);
+    } else if (p.trace != nullptr) {
+        decode_chain_kernel<false, true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     } else {
-        decode_step_fused_kernel<true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+        decode_chain_kernel<false><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
-    return cap_check_launch("decode_step_fused_kernel<chain>");
+    return cap_check_launch("decode_chain_kernel");
 }

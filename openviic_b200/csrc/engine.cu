@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -128,8 +129,7 @@ struct cap_engine {
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
     bool fuse_ln = true;                 // Linear + residual + LayerNorm as one cluster kernel (OPENVIIC_LN_FUSED=0: two kernels)
-    cap_fused_decoder* fused = nullptr;  // fused decode step (decode_fused.cu) when the model is covered
-    int fused_mode = 0;                  // 0 per-operator kernels, 1 one kernel per step, 2 GEMM chains + attention kernels
+    cap_fused_decoder* fused = nullptr;  // GEMM chains of the decode step (decode_fused.cu) when the model is covered
 
     // CUDA graph of a full beam search (begin + T steps + finalize)
     cudaGraphExec_t graph_exec = nullptr;
@@ -491,45 +491,47 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
     CAP_PROPAGATE(dev_alloc(e, &e->out_logp, R * T));
     CAP_PROPAGATE(cap_beam_create(max_batch, beam, T, m.vocab, m.eos_idx, &e->beam_state));
 
-    // Standard decoder at the reference's sizes: the decode step runs on the fused tcgen05 kernel (decode_fused.cu).
-    // OPENVIIC_FUSED_DECODE = 2 (default): three GEMM chains per layer with the stand-alone attention kernels in
-    // between; 1: ONE kernel per step (attention on the CTA's own CUDA cores -- parity-green, but it monopolises
-    // an SM at low IPC during the attention phases); 0: one kernel per operator.
+    // Standard and meshed decoders at the reference's sizes: the decode step runs as GEMM chains (decode_fused.cu) with
+    // the stand-alone attention kernels between them.  OPENVIIC_FUSED_DECODE=0: one kernel per operator (the path every
+    // other configuration -- attention-on-attention, other widths -- takes).
     const char* env = getenv("OPENVIIC_FUSED_DECODE");
-    const int mode = env ? atoi(env) : 2;
-    const bool want_fused = mode != 0;
-    if (want_fused && m.decoder_kind == CAP_DEC_PLAIN && !m.aoa_dec_self && !m.aoa_dec_cross && d == 512 && m.heads == 8 &&
-        m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && T <= 40 && n_tokens <= 128 &&
-        e->vocab_fc.b == nullptr &&
-        e->vocab_chunks <= 512) {
+    const bool want_fused = !(env && atoi(env) == 0);
+    const bool meshed = m.decoder_kind == CAP_DEC_MESHED;
+    if (want_fused && (!meshed || lv == 3) && !m.aoa_dec_self && !m.aoa_dec_cross && d == 512 && m.heads == 8 &&
+        m.d_k == 64 && m.d_ff == 2048 && m.dec_layers <= 6 && beam <= 5 && T <= 40 && n_tokens <= 104 &&
+        e->vocab_fc.b == nullptr && e->vocab_chunks <= 512) {
         std::vector<cap_fused_layer> layers(m.dec_layers);
         for (int l = 0; l < m.dec_layers; ++l) {
             const DecoderLayerW& L = e->dec[l];
             cap_fused_layer& f = layers[l];
+            memset(&f, 0, sizeof(f));
             f.w_qkv = L.self_att.qkv.w; f.b_qkv = L.self_att.qkv.b;
             f.w_o1 = L.self_att.o.w; f.b_o1 = L.self_att.o.b; f.ln1_g = L.self_att.ln.g; f.ln1_b = L.self_att.ln.b;
             f.w_q = L.cross_att.q.w; f.b_q = L.cross_att.q.b;
             f.w_o2 = L.cross_att.o.w; f.b_o2 = L.cross_att.o.b; f.ln2_g = L.cross_att.ln.g; f.ln2_b = L.cross_att.ln.b;
             f.w_fc1 = L.ffn.fc1.w; f.b_fc1 = L.ffn.fc1.b; f.w_fc2 = L.ffn.fc2.w; f.b_fc2 = L.ffn.fc2.b;
             f.ln3_g = L.ffn.ln.g; f.ln3_b = L.ffn.ln.b;
+            f.n_levels = meshed ? lv : 0;
+            for (int i = 0; meshed && i < lv; ++i) {
+                f.w_alpha[i] = L.alphas[i].w;
+                f.b_alpha[i] = L.alphas[i].b;
+            }
         }
         cap_fused_desc fd = {};
         fd.d_model = d; fd.heads = m.heads; fd.d_ff = m.d_ff; fd.n_layers = m.dec_layers; fd.vocab = m.vocab;
         fd.max_len = T; fd.beam = beam; fd.pad_idx = m.pad_idx; fd.max_rows = static_cast<int>(R);
         fd.layers = layers.data();
         fd.w_vocab = e->vocab_fc.w; fd.word_emb = e->word_emb; fd.word_pos = e->word_pos;
-        fd.tokens = cap_beam_tokens(e->beam_state); fd.ancestry = cap_beam_ancestry(e->beam_state);
+        fd.tokens = cap_beam_tokens(e->beam_state);
         fd.padflag = e->padflag; fd.qkv_cache = e->qkv_cache;
-        fd.cross_kv = e->cross_kv; fd.cross_layer_stride = rows_enc * 2 * hd; fd.enc_mask = e->enc_mask;
         fd.logits = e->logits; fd.ld_logits = e->ld_logits; fd.part_ms = e->part_ms;
-        fd.att_in = e->buf_att; fd.q_out = e->buf_q;
+        fd.att_in = e->buf_att; fd.q_out = e->buf_q;   // buf_att: [levels][max_rows][hd]
         {   // one stacked copy of the chain weights per weight set, shared by every engine over it
             std::lock_guard<std::mutex> guard(e->weights->lock);
             if (!e->weights->stacked) CAP_PROPAGATE(cap_fused_weights_create(layers.data(), m.dec_layers, &e->weights->stacked));
             fd.stacked = e->weights->stacked;
         }
         CAP_PROPAGATE(cap_fused_create(&fd, &e->fused));
-        e->fused_mode = mode == 1 ? 1 : 2;
     }
     return CAP_OK;
 }
@@ -613,12 +615,13 @@ namespace {
 int run_decoder_stack(cap_engine* e, int t, cudaStream_t s, bf16** hidden);
 
 
-// Decoder stack + vocabulary projection (logits and chunk statistics) of step t on the fused tcgen05 kernel.
+// Decoder stack + vocabulary projection (logits and chunk statistics) of step t: GEMM chains with the attention
+// kernels between them (decoders.py:21-28 / 51-73 per layer).
 int run_fused_stack(cap_engine* e, int t, cudaStream_t s) {
-    if (e->fused_mode == 1) return cap_fused_decode_step(e->fused, t, e->cur_batch, e->cur_n, s);
     const cap_model_desc& m = e->desc;
-    const int hd = e->hd(), T = m.max_len, B = e->cur_batch, R = B * e->beam;
+    const int hd = e->hd(), T = m.max_len, B = e->cur_batch, R = B * e->beam, lv = e->levels();
     const size_t rows_cap = static_cast<size_t>(e->max_batch) * e->n_tokens;
+    const size_t max_rows = static_cast<size_t>(e->max_batch) * e->beam;
     const float scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
     const int ab = dbg_ablate();
     if (!(ab & 4)) CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, B, s));
@@ -629,21 +632,10 @@ int run_fused_stack(cap_engine* e, int t, cudaStream_t s) {
                                                     R, m.heads, scale, s));
         if (!(ab & 4)) CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, B, s));
         if (!(ab & 8)) {
-            const bf16* kv = e->cross_kv + static_cast<size_t>(l) * rows_cap * 2 * hd;
-            static const bool cross_mma = getenv("OPENVIIC_CROSS_MMA") && atoi(getenv("OPENVIIC_CROSS_MMA")) != 0;
-            if (cross_mma) {  // the image's beams as the queries of a batched tensor-core attention (nq = beam)
-                cap_attention_args a = {};
-                a.q = e->buf_q; a.k = kv; a.v = kv + hd; a.out = e->buf_att;
-                a.q_bs = a.o_bs = static_cast<int64_t>(e->beam) * hd;
-                a.k_bs = a.v_bs = static_cast<int64_t>(e->cur_n) * 2 * hd;
-                a.ldq = a.ldo = hd; a.ldk = a.ldv = 2 * hd;
-                a.mask = e->enc_mask; a.mask_bs = e->cur_n; a.mask_qs = 0;
-                a.B = B; a.H = m.heads; a.nq = e->beam; a.nk = e->cur_n; a.scale = scale;
-                CAP_PROPAGATE(cap_attention(&a, s));
-            } else {
-                CAP_PROPAGATE(cap_decode_cross_attention(e->buf_q, hd, kv, e->enc_mask, e->buf_att, hd, B, e->beam, e->cur_n,
-                                                         m.heads, scale, s));
-            }
+            // every encoder level in ONE launch: level i reads cross_kv[l][i], writes att_in[i] (same queries)
+            const bf16* kv = e->cross_kv + static_cast<size_t>(l) * lv * rows_cap * 2 * hd;
+            CAP_PROPAGATE(cap_decode_cross_attention_levels(e->buf_q, hd, kv, rows_cap * 2 * hd, e->enc_mask, e->buf_att, hd,
+                                                            max_rows * hd, B, e->beam, e->cur_n, m.heads, lv, scale, s));
         }
         if (!(ab & 4)) CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_FFN, l, t, B, s));
     }
@@ -876,7 +868,7 @@ extern "C" int cap_engine_caption_device_async(cap_engine* e, const void* feats_
 // are whatever the last real step left behind).  Returns CAP_ERR_STATE when the engine does not run chains.
 extern "C" int cap_engine_debug_chains(cap_engine* e, int t, cap_stream_t stream) {
     CAP_REQUIRE(e && e->encoded, "cap_engine_debug_chains: encode first");
-    if (!e->fused || e->fused_mode != 2) return cap_set_error(CAP_ERR_STATE, "cap_engine_debug_chains: engine is not in chain mode");
+    if (!e->fused) return cap_set_error(CAP_ERR_STATE, "cap_engine_debug_chains: engine is not in chain mode");
     CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_EMBED_QKV, 0, t, e->cur_batch, stream));
     for (int l = 0; l < e->desc.dec_layers; ++l) {
         CAP_PROPAGATE(cap_fused_chain(e->fused, CAP_CHAIN_SELF_OUT, l, t, e->cur_batch, stream));

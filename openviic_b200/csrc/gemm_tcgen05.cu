@@ -55,6 +55,7 @@ __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == CAP_ACT_RELU) return fmaxf(v, 0.f);
     if (act == CAP_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == CAP_ACT_LEAKY_RELU) return v > 0.f ? v : 0.01f * v;   // F.leaky_relu default slope (encoders.py:243-245)
     return v;
 }
 

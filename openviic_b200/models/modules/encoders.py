@@ -88,3 +88,30 @@ class GeometricEncoder(_LayerStack):
             b_g = torch.cat([fc.bias for fc in self.fc_gs], dim=0)
             geometry = ops.geometry_bias(boxes, w_g, b_g, bool(self.trignometric_embedding))
         return self._run(features, padding_mask, relative_geometry_weights=geometry)[-1]
+
+
+@META_ENCODER.register()
+class CrossAttentionMultiLevelEncoder(_LayerStack):
+    """CamoTransformer's encoder (encoders.py:213-249): the three layer outputs attend to each other through one extra
+    attention block, and an MLP over the concatenation of the ORIGINAL three outputs is mixed in.  Kept as written:
+    three layers are assumed (:235), and mlp1 reads the un-updated outputs (:242)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.self_attn = MultiHeadAttention(config.SELF_ATTENTION)
+        self.mlp1 = nn.Linear(3 * config.D_MODEL, config.D_MODEL)
+        self.mlp2 = nn.Linear(config.D_MODEL, config.D_MODEL)
+
+    def forward(self, features: torch.Tensor, padding_mask: torch.Tensor):
+        with torch.no_grad():
+            outs = self._run(features, padding_mask)
+            out1, out2, out3 = outs
+            out2 = 0.1 * self.self_attn(queries=out2, keys=out1, values=out1, padding_mask=padding_mask,
+                                        attention_mask=padding_mask) + out2
+            out3 = 0.1 * self.self_attn(queries=out3, keys=out2, values=out2, padding_mask=padding_mask,
+                                        attention_mask=padding_mask) + out3
+            mixed = ops.linear(torch.cat(outs, dim=-1), ops.cached_bf16(self.mlp1.weight), self.mlp1.bias,
+                               act=ops.ACT_LEAKY_RELU, out_dtype=torch.float32)
+            mixed = ops.linear(mixed, ops.cached_bf16(self.mlp2.weight), self.mlp2.bias, act=ops.ACT_LEAKY_RELU,
+                               out_dtype=torch.float32)
+            return out3 + 0.2 * mixed

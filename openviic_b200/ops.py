@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import cabi
-from .cabi import ACT_NONE, ACT_RELU, ACT_SIGMOID, CAP_BF16, CAP_F32  # noqa: F401
+from .cabi import ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CAP_BF16, CAP_F32  # noqa: F401
 
 Tensor = torch.Tensor
 

@@ -229,6 +229,7 @@ def encode(w: Weights, model_cfg, feats: Tensor, boxes: Optional[Tensor] = None)
     FeatureEmbedding      models/modules/vision_embeddings.py:15-20
     Encoder               models/modules/encoders.py:35-40
     MultilevelEncoder     models/modules/encoders.py:53-63   (returns all levels, (B,L,n,d))
+    CrossAttentionMultiLevelEncoder  models/modules/encoders.py:213-249 (CamoTransformer)
     GeometricEncoder      models/modules/encoders.py:93-112  (called with boxes -- the documented
                           ORT call-site patch)
     """
@@ -248,6 +249,17 @@ def encode(w: Weights, model_cfg, feats: Tensor, boxes: Optional[Tensor] = None)
         return torch.stack(levels, dim=1), pad_mask
     if kind in ("Encoder", "GeometricEncoder"):
         return x, pad_mask
+    if kind == "CrossAttentionMultiLevelEncoder":
+        # models/modules/encoders.py:226-249: the layer outputs attend to each other through ONE extra attention block,
+        # an MLP over the concatenation of the ORIGINAL three outputs is mixed in (hard-coded three layers, :235; the
+        # un-updated `outs` feed mlp1, :242 -- both kept as written).
+        att_cfg = enc_cfg.SELF_ATTENTION
+        out1, out2, out3 = levels
+        out2 = 0.1 * multi_head_attention(w, "encoder.self_attn.", att_cfg, out2, out1, out1, pad_mask) + out2
+        out3 = 0.1 * multi_head_attention(w, "encoder.self_attn.", att_cfg, out3, out2, out2, pad_mask) + out3
+        mixed = F.leaky_relu(_lin(w, "encoder.mlp1", torch.cat(levels, dim=-1)))
+        mixed = F.leaky_relu(_lin(w, "encoder.mlp2", mixed))
+        return out3 + 0.2 * mixed, pad_mask
     raise KeyError(f"oracle has no encoder {kind!r}")
 
 

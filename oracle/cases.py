@@ -16,6 +16,8 @@ CASES = {
                      overrides={"MODEL": {"ENCODER": {"TRIGNOMETRIC_EMBEDDING": True}}}),
     "aoa": dict(config="attention_on_attention.yaml", batch=4, n=50, beam=5, max_len=16, vocab=800, seed=16),
     "aug_mem": dict(config="augmented_memory_transformer.yaml", batch=4, n=37, beam=4, max_len=16, vocab=777, seed=17),
+    # CamoTransformer: CrossAttentionMultiLevelEncoder (one 64-wide head in the encoder); module-level CUDA path
+    "camo": dict(config="camo_transformer.yaml", batch=4, n=44, beam=5, max_len=14, vocab=900, seed=18),
 }
 
 
@@ -32,3 +34,8 @@ def apply_overrides(cfg, case):
     if case.get("overrides"):
         _merge(cfg, case["overrides"])
     return cfg
+
+
+# cases the whole-path engine covers (the others run on the registered modules: the module-level CUDA path)
+MODULE_PATH_CASES = ("camo",)
+ENGINE_CASES = tuple(c for c in CASES if c not in MODULE_PATH_CASES)

@@ -47,9 +47,9 @@ def main():
         q = torch.randn(B * beam, hd, generator=g).to(torch.bfloat16).to(dev)
         mask = torch.zeros(B, n, dtype=torch.uint8)
         mask[B // 2, n // 2:] = 1
-        if B > 2:
-            mask[1, : n - 1] = 1   # a single live key
-            mask[2, ::2] = 1
+        if B > 4:
+            mask[0, : n - 1] = 1   # a single live key (image 0 is never B // 2 here: no fully masked image)
+            mask[1, ::2] = 1
         mask = mask.to(dev)
         ref = reference(q, kv, mask.bool(), beam, H)
         line = f"B={B} beam={beam} n={n}: max-abs err vs fp32"

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import caption_oracle as oracle
-from oracle.cases import CASES
+from oracle.cases import CASES, ENGINE_CASES
 from helpers import TOL_ACT, bf16_operand_yardstick, golden, load_case, make_items, stepwise_against_oracle
 
 pytestmark = pytest.mark.gpu
@@ -21,7 +21,7 @@ NEAR_TIE_STEP = 0.2  # first divergence of an image's beams: the engine's k-th p
 MIN_IDENTICAL_FP32 = 0.6   # token-identical best captions vs the fp32 reference, per case (random-weight models: near-ties)
 
 
-@pytest.fixture(scope="module", params=list(CASES))
+@pytest.fixture(scope="module", params=list(ENGINE_CASES))
 def case_run(request, device):
     name = request.param
     case, cfg, vocab, model, weights, field, feats, boxes = load_case(name, device)

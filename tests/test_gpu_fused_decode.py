@@ -1,4 +1,5 @@
-"""The one-kernel decode step (csrc/decode_fused.cu) against the per-operator CUDA path and the oracle.
+"""The GEMM chains of the decode step (csrc/decode_fused.cu; standard and meshed decoders) against the per-operator CUDA
+path and the oracle.
 
 Both engines carry the same weights and features; each decodes with its own beam state.  As long as the two
 beam states agree (they must, up to near-ties) every step's logits are compared over the full vocabulary.
@@ -21,7 +22,7 @@ TOL_FUSED = 6e-2   # max-abs logits, fused vs per-operator path: same bf16 opera
 
 
 def _engine(model, cfg, vocab, batch, n, beam, device, fused, full_logits=True):
-    """fused: 0 / False = one kernel per operator, 1 / True = one kernel per step, 2 = GEMM chains + attention kernels."""
+    """fused: 0 = one kernel per operator, otherwise GEMM chains + attention kernels (the default)."""
     os.environ["OPENVIIC_FUSED_DECODE"] = str(int(fused))
     os.environ["OPENVIIC_FULL_LOGITS"] = "1" if full_logits else "0"   # the step-wise comparison reads whole rows
     try:
@@ -34,7 +35,7 @@ def _engine(model, cfg, vocab, batch, n, beam, device, fused, full_logits=True):
 
 
 @pytest.mark.parametrize("mode", [2])
-@pytest.mark.parametrize("name,batch", [("std_grid", 6), ("std_region_A", 16), ("std_grid", 53), ("ort", 5)])
+@pytest.mark.parametrize("name,batch", [("std_grid", 6), ("std_region_A", 16), ("std_grid", 53), ("ort", 5), ("m2", 5), ("m2", 53)])
 def test_fused_step_matches_per_operator_path(name, batch, mode, device):
     case, cfg, vocab, model, weights, field, feats, boxes = load_case(name, device)
     beam, T = case["beam"], case["max_len"]
@@ -94,11 +95,12 @@ def test_fused_beam_search_against_oracle(mode, device):
     assert d.numel() == 0 or d.max().item() < 9e-2
 
 
+@pytest.mark.parametrize("name", ["std_region_A", "m2"])
 @pytest.mark.parametrize("env", [{"OPENVIIC_CHAIN_PAIR": "0"}, {"OPENVIIC_FULL_LOGITS": "1"}, {}])
-def test_chain_variants_agree(env, device):
+def test_chain_variants_agree(env, name, device):
     """Single-CTA chains vs CTA pairs, sparse vs full logits stores: identical captions and log-probs (the same
     arithmetic in the same order; only the staging of weights and the set of stored logits differ)."""
-    case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_region_A", device)
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case(name, device)
 
     def run(extra):
         old = {k: os.environ.get(k) for k in extra}

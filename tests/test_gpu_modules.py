@@ -1,0 +1,54 @@
+"""Architectures that run on the registered modules only (the whole-path engine does not cover their encoders): every
+module's forward is the sm_100a kernels through per-operator entry points.  Checked against the oracle and the golden
+fixtures the real reference produced."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import caption_oracle as oracle
+from oracle.cases import MODULE_PATH_CASES
+from helpers import golden, load_case, make_items
+
+pytestmark = pytest.mark.gpu
+
+TOL_ENC = 4e-2         # encoder output, max-abs (LayerNorm-scale values through 3+ layers of bf16 operands)
+TOL_LOGP = 9e-2        # full-vocabulary log-probs, max-abs
+TOL_LOGP_MEAN = 2.2e-2
+
+
+@pytest.mark.parametrize("name", list(MODULE_PATH_CASES))
+def test_module_path_architecture(name, device):
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case(name, device)
+    assert not model.engine_supported()
+    b, beam = case["batch"], case["beam"]
+    g = golden(name)
+    items = make_items(field, feats, boxes, device)
+    # encoder: against the oracle and the real reference's rows
+    with torch.no_grad():
+        enc, mask = model.encoder_forward(items)
+        ref_enc, ref_mask = oracle.encode(weights, cfg.MODEL, feats, boxes)
+    torch.cuda.synchronize()
+    assert torch.equal(mask.cpu().view(b, -1), ref_mask.view(b, -1))
+    err = (enc.float().cpu() - ref_enc).abs()
+    rows = enc.float().cpu().reshape(-1, enc.shape[-1])[:: int(g["enc_row_stride"])][:64]
+    print(f"[{name}] encoder max-abs {err.max():.4f} mean-abs {err.mean():.5f}; vs the reference's rows "
+          f"{np.abs(rows.numpy() - g['enc_rows']).max():.4f}")
+    assert err.max().item() < TOL_ENC and np.abs(rows.numpy() - g["enc_rows"]).max() < TOL_ENC
+    # teacher-forced forward against the real reference's log-probs
+    ids_ref = torch.from_numpy(g["ids"])
+    tokens = torch.cat([torch.full((b, 1), vocab.bos_idx, dtype=torch.long), ids_ref[:, :-1]], 1)
+    items.set("caption_tokens", tokens.to(device))
+    lp = model(items).float().cpu()
+    stride = max(1, case["vocab"] // 128)
+    diff = np.abs(lp[:, :, ::stride].numpy() - g["tf_logp"])
+    live = (tokens != vocab.padding_idx).numpy()
+    print(f"[{name}] teacher-forced log-prob max-abs {diff[live].max():.4f} mean-abs {diff[live].mean():.5f}")
+    assert diff[live].max() < TOL_LOGP and diff[live].mean() < TOL_LOGP_MEAN
+    # beam search through the reference-shaped public call (BeamSearch over step + the registered modules)
+    ids, logp = model.beam_search(items, batch_size=b, beam_size=beam, out_size=1)
+    torch.cuda.synchronize()
+    same = (ids.cpu() == ids_ref).all(1)
+    err_lp = (logp.cpu() - torch.from_numpy(g["logp"]))[same].abs().max().item() if same.any() else float("nan")
+    print(f"[{name}] captions identical to the reference's {int(same.sum())}/{b}; log-prob max-abs on those {err_lp:.4f}")
+    assert same.float().mean().item() >= 0.5 and (not same.any() or err_lp < TOL_LOGP)

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--host-every", type=int, default=4, help="every k-th iteration goes through the host-buffer entry point")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--seconds", type=float, default=0.0, help="stop after this many seconds (0 = run all iterations)")
+    ap.add_argument("--hang-seconds", type=float, default=40.0, help="watchdog: give up when one iteration takes longer")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     yaml_name, n, per_gpu_batch, _ = bench.WORKLOADS[args.workload]
@@ -68,6 +69,23 @@ def main():
     golden = {}
     mism, fault, done = [], None, 0
     t0 = time.perf_counter()
+    # watchdog: an iteration that does not finish within --hang-seconds is a device-side hang (a wait that is not
+    # bounded, or a scheduling deadlock): report what is known and leave without waiting for the GPU
+    import threading
+    progress = {"iter": -1, "at": time.perf_counter()}
+
+    def watchdog():
+        while True:
+            time.sleep(2.0)
+            if time.perf_counter() - progress["at"] > args.hang_seconds:
+                from openviic_b200 import cabi
+                print(json.dumps({"tool": "stress", "hang": True, "after_iteration": progress["iter"],
+                                  "seconds_without_progress": time.perf_counter() - progress["at"],
+                                  "timed_out_waits_at_source_lines": cabi.fault_records(),
+                                  "env": {k: v for k, v in os.environ.items() if k.startswith("OPENVIIC_")}}), flush=True)
+                os._exit(3)
+
+    threading.Thread(target=watchdog, daemon=True).start()
     try:
         for it in range(args.iters):
             host = args.host_every > 0 and it % args.host_every == args.host_every - 1
@@ -92,6 +110,7 @@ def main():
                     mism.append({"iter": it, "engine": k, "set": s, "host": host, "captions_differ": bad,
                                  "logp_max_abs": float((lp - g_lp).abs().max())})
             done = it + 1
+            progress["iter"], progress["at"] = it, time.perf_counter()
             if it % 20 == 0:
                 print(f"[stress] iter {it}: {len(mism)} mismatches, {time.perf_counter() - t0:.1f} s", file=sys.stderr, flush=True)
             if args.seconds > 0 and time.perf_counter() - t0 > args.seconds:
