@@ -302,7 +302,10 @@ def run_gpu_arm(args):
 
     t_start = time.perf_counter()
 
+    poke = install_watchdog(args.hang_seconds)
+
     def progress(what):   # stderr breadcrumbs: a multi-rank run that stalls shows where
+        poke(what)
         if rank == 0:
             print(f"[bench +{time.perf_counter() - t_start:6.1f}s] {what}", file=sys.stderr, flush=True)
 
@@ -540,6 +543,7 @@ def run_gpu_arm(args):
     roofline["step_algorithmic_tflops"] = gflop_per_caption * 1e9 * max(value, e2e_value) / world / 1e12
     roofline["step_frac_of_tensor_peak"] = roofline["step_algorithmic_tflops"] / peaks["tflops_sustained"]
 
+    progress("roofline timing done")
     cpu_base = None
     if not args.skip_cpu and world == 1:   # the CPU baseline is an N=1 figure (rank 0, host cores otherwise idle)
         cpu_base, _ = cpu_reference_run(args.workload, steps=args.cpu_steps, warmup=1, sample_batch=args.cpu_batch)
@@ -569,6 +573,37 @@ def run_gpu_arm(args):
     return 0
 
 
+def install_watchdog(seconds: float):
+    """A run that makes no progress for `seconds` (a device-side hang: every wait with a bound would have trapped)
+    prints the Python stacks, the fault records and the flight recorder's counters, and exits: the caller -- the driver,
+    torchrun, the peers of a multi-rank run -- must never be left waiting for a wedged rank."""
+    import faulthandler
+    import threading
+    state = {"at": time.perf_counter(), "what": "start"}
+
+    def poke(what):
+        state["at"], state["what"] = time.perf_counter(), what
+
+    def watch():
+        while True:
+            time.sleep(2.0)
+            if time.perf_counter() - state["at"] > seconds:
+                print(f"[bench] rank {os.environ.get('RANK', '0')}: no progress for {seconds:.0f} s after '{state['what']}'",
+                      file=sys.stderr)
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                try:
+                    from openviic_b200 import cabi
+                    print(f"[bench] timed-out waits at source lines {cabi.fault_records()}; flight recorder (entered, left): "
+                          f"{cabi.flight_records()}", file=sys.stderr)
+                except Exception:   # noqa: BLE001
+                    pass
+                sys.stderr.flush()
+                os._exit(4)
+
+    threading.Thread(target=watch, daemon=True).start()
+    return poke
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -585,6 +620,8 @@ def main():
                     help="device-resident loop: admit one batch every this many ms (0 = enqueue everything at once)")
     ap.add_argument("--min-timed-ms", type=float, default=500.0,
                     help="repeat the K steps inside the timed region until it lasts at least this long (0 = exactly K steps)")
+    ap.add_argument("--hang-seconds", type=float, default=90.0,
+                    help="watchdog: dump diagnostics and exit when no phase finishes within this many seconds")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=40)

@@ -92,6 +92,11 @@ int cap_feature_mask_cast(const void* feats, int feat_dtype, void* out_bf16, uin
 int cap_geometry_bias(const float* boxes, const float* w_g, const float* b_g, float* g, int B,
                       int n, int H, int d_g, int trig, cap_stream_t stream);
 
+/* Locally-constrained mask of the dual-path encoder (models/utils.py:100-154 get_combine_masks): boxes fp32
+ * [rows][4] in [0,1] image coordinates -> mask uint8 [rows][grid_size^2], 0 for the grid cells inside the box's
+ * corner-to-corner cell rectangle, 1 (masked) elsewhere. */
+int cap_region_grid_mask(const float* boxes, uint8_t* mask, int rows, int grid_size, cap_stream_t stream);
+
 typedef struct cap_attention_args {
     const void* q;            /* bf16 (B, nq, H*64), row stride ldq, batch stride q_bs (elements) */
     const void* k;            /* bf16 (B, nk, H*64) */
@@ -108,12 +113,16 @@ typedef struct cap_attention_args {
     int n_mem;
     int B, H, nq, nk;
     float scale;              /* 1/sqrt(d_k) */
+    const void* sentinel;     /* bf16 (B, nq, H*64): query i's own extra key = value ("language signal" of
+                                 AdaptiveScaledDotProductAttention, attentions.py:250-263), never masked; NULL = none */
+    int64_t s_bs;             /* batch stride of sentinel (elements) */
+    int lds;                  /* row stride of sentinel */
 } cap_attention_args;
 
-/* softmax(q.k^T*scale + mask + log g | memory slots).v per (batch, head); d_k = d_v = 64,
+/* softmax(q.k^T*scale + mask + log g | memory slots | per-query sentinel).v per (batch, head); d_k = d_v = 64,
  * nk + n_mem <= 160.  Replaces the body of ScaledDotProductAttention.forward
- * (models/modules/attentions.py:51-55), AugmentedGeometry... (:104-111) and AugmentedMemory...
- * (:164-182) between the projections. */
+ * (models/modules/attentions.py:51-55), AugmentedGeometry... (:104-111), AugmentedMemory... (:164-182) and
+ * Adaptive... (:244-263) between the projections. */
 int cap_attention(const cap_attention_args* args, cap_stream_t stream);
 
 /* Decode-step self-attention over the beam-indirected KV cache (nq = 1 per row).
@@ -347,6 +356,11 @@ cap_beam* cap_engine_beam(cap_engine* e);
  * AFTER the CUDA context has died.  Copies up to max_records source lines and returns the number of distinct waits
  * that timed out (0: none ever did). */
 int cap_fault_records(unsigned int* out, int max_records);
+/* Flight recorder (debug, OPENVIIC_FLIGHT=1 in the environment before the first launch): per kernel kind, how many
+ * CTAs entered and how many left, counted in pinned host memory -- after a device hang the kinds with entered > left
+ * are the ones that are stuck.  Copies [kind][entered, left] for up to max_kinds kinds, returns the number of kinds
+ * (0: recorder off).  Kinds: csrc/cap_common.cuh FlightKind. */
+int cap_flight_records(unsigned int* out, int max_kinds);
 /* Debug: when non-NULL, every later cap_linear writes 8 %globaltimer stamps (ns) per CTA into
  * device_buffer[cta*8 + k]: 0 entry, 1 prologue done, 2 first TMA issued, 3 first stage landed,
  * 4 last MMA committed, 5 accumulator visible to the epilogue, 6 stores issued, 7 TMEM freed. */

@@ -32,6 +32,7 @@ class AttentionArgs(C.Structure):
         ("geometry", _vp), ("mem_k", _vp), ("mem_v", _vp), ("n_mem", _i),
         ("B", _i), ("H", _i), ("nq", _i), ("nk", _i),
         ("scale", _f),
+        ("sentinel", _vp), ("s_bs", _i64), ("lds", _i),
     ]
 
 
@@ -51,11 +52,13 @@ SIGNATURES = {
     "cap_launch_count": (_i64, []),
     "cap_debug_gemm_trace": (_i, [_vp]),
     "cap_fault_records": (_i, [_vp, _i]),
+    "cap_flight_records": (_i, [_vp, _i]),
     "cap_linear": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_linear_simt": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cap_add_layernorm": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "cap_feature_mask_cast": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "cap_geometry_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cap_region_grid_mask": (_i, [_vp, _vp, _i, _i, _vp]),
     "cap_attention": (_i, [C.POINTER(AttentionArgs), _vp]),
     "cap_decode_self_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "cap_decode_cross_attention": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
@@ -118,7 +121,8 @@ SIGNATURES = {
 
 # entry points whose int return value is an error code
 _STATUS_FUNCS = {name for name, (res, _) in SIGNATURES.items()
-                 if res is _i and name not in ("cap_abi_version", "cap_fault_records", "cap_fused_get_full_logits")}
+                 if res is _i and name not in ("cap_abi_version", "cap_fault_records", "cap_flight_records",
+                                              "cap_fused_get_full_logits")}
 
 _lib: Optional[C.CDLL] = None
 
@@ -163,3 +167,15 @@ def fault_records():
     buf = (C.c_uint * 64)()
     n = int(load_library().cap_fault_records(buf, 64))
     return [int(r) for r in buf[:min(n, 64)]]
+
+
+FLIGHT_KINDS = ("chain", "chain_past_setup", "cross_producer", "cross_consumer", "cross_consumer_past_pdl_wait",
+                "self_attention", "gemm", "gemm_past_setup", "attention", "beam_merge", "beam_select", "beam_other",
+                "row_kernels")
+
+
+def flight_records():
+    """{kind: (CTAs entered, CTAs left)} from the flight recorder (OPENVIIC_FLIGHT=1), {} when it is off."""
+    buf = (C.c_uint * 32)()
+    n = int(load_library().cap_flight_records(buf, 16))
+    return {name: (int(buf[2 * i]), int(buf[2 * i + 1])) for i, name in enumerate(FLIGHT_KINDS[:n])}

@@ -43,6 +43,10 @@ struct AttnDev {
     const bf16 *mem_k, *mem_v;
     int n_mem, B, H, nq, nk;
     float scale;
+    // adaptive attention (attentions.py:229-268): query i has one extra key = value = sentinel[b, i] ("language signal")
+    const bf16* sentinel;
+    long long s_bs;
+    int lds;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnDev a) {
@@ -108,6 +112,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnDev a)
             mx = fmaxf(mx, s[c]);
         }
         mx = warp_max(mx);
+        // adaptive attention: the query's own sentinel is one more (never masked) column of the softmax
+        float2 sent = make_float2(0.f, 0.f);
+        float s_logit = -INFINITY;
+        if (a.sentinel != nullptr) {
+            const bf16* srow = a.sentinel + b * a.s_bs + static_cast<size_t>(i) * a.lds + h * HEAD_DIM;
+            sent = __bfloat1622float2(reinterpret_cast<const bf162*>(srow)[lane]);
+            s_logit = warp_sum(myq[2 * lane] * sent.x + myq[2 * lane + 1] * sent.y);
+            mx = fmaxf(mx, s_logit);
+        }
         float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < KEY_CHUNKS; ++c) {
@@ -117,9 +130,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnDev a)
             sum += p;
         }
         sum = warp_sum(sum);
+        const float p_sent = a.sentinel != nullptr ? __expf(s_logit - mx) : 0.f;
+        sum += p_sent;
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
         __syncwarp();
-        float o0 = 0.f, o1 = 0.f;
+        float o0 = p_sent * sent.x, o1 = p_sent * sent.y;
         for (int j = 0; j < nk_all; ++j) {
             const float p = myp[j];
             const float2 vv = __bfloat1622float2(reinterpret_cast<const bf162*>(sv + j * HEAD_DIM)[lane]);
@@ -157,6 +172,7 @@ constexpr int MMA_PITCH = HEAD_DIM + 8;  // bf16 elements: 36 words per row => c
 
 template <int NT>  // number of 8-key tiles: 8 (<= 64 keys) or 16 (<= 128 keys)
 __global__ void __launch_bounds__(128) attention_mma_kernel(const AttnDev a) {
+    if (threadIdx.x == 0) flight_mark(FK_ATTENTION, 0);
     pdl_prologue();
     constexpr int NKP = NT * 8;
     constexpr int VP = NKP + 8;  // V^T pitch (bf16): (NKP+8)/2 words == 4 mod 32 => conflict-free too
@@ -293,6 +309,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const AttnDev a) {
         if (va) *reinterpret_cast<bf162*>(oa + col) = __floats2bfloat162_rn(o[dt][0] * inva, o[dt][1] * inva);
         if (vb) *reinterpret_cast<bf162*>(ob + col) = __floats2bfloat162_rn(o[dt][2] * invb, o[dt][3] * invb);
     }
+    if (threadIdx.x == 0) flight_mark(FK_ATTENTION, 1);
 }
 
 // ------------------------------------------------------------------------------ decode self-attn
@@ -392,6 +409,7 @@ __global__ void __launch_bounds__(DEC_WARPS_MAX * 32)
 decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
                                   const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
                                   float scale) {
+    if (threadIdx.x == 0) flight_mark(FK_SELF_ATTENTION, 0);
     pdl_prologue();
     constexpr int LANES_PER_HEAD = HEAD_DIM / EPL;
     constexpr int VEC = EPL / 8;  // 16-byte vectors per lane
@@ -486,6 +504,7 @@ decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* _
         for (int i = 0; i < 8; ++i) o[i] = acc[c * 8 + i] * inv;
         reinterpret_cast<bf16x8*>(orow)[c] = pack8(o);
     }
+    if (threadIdx.x == 0) flight_mark(FK_SELF_ATTENTION, 1);
 }
 
 // Decode-step self-attention, split-key variant (opt-in: OPENVIIC_SELF_SPLIT=1; H = 8): SS_SPLITS warps share the
@@ -1077,6 +1096,7 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
 
     if (warp == XA_CONSUMERS) {
         // ------------------------------------------------------------------ producer
+        if (lane == 0) flight_mark(FK_CROSS_PRODUCER, 0);
         // K|V were projected at encode time and a serialising launch separates encode from decode: safe to stream
         // before (without) the PDL wait.  Read once per step: evict-first, the weights keep their place in L2.
         const uint64_t stream_policy = cap_ptx::l2_policy_evict_first();
@@ -1102,6 +1122,7 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
                     "l"(stream_policy)
                     : "memory");
         }
+        if (lane == 0) flight_mark(FK_CROSS_PRODUCER, 1);
         return;
     }
 
@@ -1110,7 +1131,9 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
     const int h = warp;
     const float sc = scale * 1.4426950408889634f;
     const int mi = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of 8x8 matrix mi of an x4 load
+    if (threadIdx.x == 0) flight_mark(FK_CROSS_CONSUMER, 0);
     pdl_wait();   // q comes from the previous kernel; out is read by nothing that is still running
+    if (threadIdx.x == 0) flight_mark(FK_CROSS_CONSUMER_READY, 0);
     // A operand of S = Q.K^T: rows g < beams of the image's queries, head h; rows 8..15 of the m16 tile are zero
     auto load_q = [&](int img, uint32_t (&qa)[4][4]) {
         const bf16* qrow = q + static_cast<size_t>(img * beams + (g < beams ? g : 0)) * ldq + h * HEAD_DIM + 2 * t;
@@ -1212,6 +1235,10 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
                 qa[ks][2] = qn[ks][2];
             }
         }
+    }
+    if (threadIdx.x == 0) {
+        flight_mark(FK_CROSS_CONSUMER, 1);
+        flight_mark(FK_CROSS_CONSUMER_READY, 1);
     }
 }
 
@@ -1409,8 +1436,7 @@ int launch_attention(const AttnDev& a, cudaStream_t stream) {
             return a.nk <= 56 ? launch_encoder_tc<7>(a, stream) : launch_encoder_tc<8>(a, stream);
         }
     }
-    static const bool force_simt = getenv("OPENVIIC_ATTENTION_SIMT") != nullptr;
-    if (nk_all <= 128 && !force_simt) {  // tensor-core variant
+    if (nk_all <= 128 && a.sentinel == nullptr) {  // tensor-core variant (the per-query sentinel lives in the CUDA-core kernel)
         dim3 grid((a.nq + MMA_Q_TILE - 1) / MMA_Q_TILE, a.H, a.B);
         if (nk_all <= 64)
             CAP_LAUNCH((attention_mma_kernel<8>), grid, 128, 0, stream, a);
@@ -1455,6 +1481,8 @@ extern "C" int cap_attention(const cap_attention_args* args, cap_stream_t stream
     a.mem_v = static_cast<const bf16*>(g.mem_v);
     a.n_mem = g.n_mem; a.B = g.B; a.H = g.H; a.nq = g.nq; a.nk = g.nk;
     a.scale = g.scale;
+    a.sentinel = static_cast<const bf16*>(g.sentinel); a.s_bs = g.s_bs; a.lds = g.lds;
+    CAP_REQUIRE(g.sentinel == nullptr || g.lds % 2 == 0, "cap_attention: sentinel leading dimension must be even");
     return launch_attention(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -1508,6 +1536,7 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
     a.ldq = ldq; a.ldk = a.ldv = 2 * hd; a.ldo = ldo;
     a.mask = key_mask; a.mask_bs = n; a.mask_qs = 0;
     a.geometry = nullptr; a.mem_k = a.mem_v = nullptr; a.n_mem = 0;
+    a.sentinel = nullptr; a.s_bs = 0; a.lds = 0;
     a.B = B; a.H = H; a.nq = beam; a.nk = n;
     a.scale = scale;
     return launch_attention(a, static_cast<cudaStream_t>(stream));

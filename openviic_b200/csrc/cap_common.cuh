@@ -49,10 +49,42 @@ int cap_set_error(int code, const char* fmt, ...);
 // (the device instructions are then no-ops).
 // ---------------------------------------------------------------------------------------------
 bool cap_pdl_enabled();
+// pinned, device-mapped host words for the flight recorder (cap_core.cu); nullptr unless OPENVIIC_FLIGHT=1
+extern "C" unsigned int* cap_flight_buffer_device();
+
+// "Already done on this device" flag: one atomic bit per device ordinal (used for per-device kernel attributes and
+// per-translation-unit device symbols; setting either twice is harmless).
+struct cap_device_once {
+    unsigned long long done = 0;
+};
+
+#ifdef __CUDACC__
+// ---- flight recorder (debug, OPENVIIC_FLIGHT=1) -----------------------------------------------------------------
+// One thread per CTA counts "entered" / "left" per kernel kind in pinned, device-mapped HOST memory (posted
+// reductions, nobody waits for them).  When the device hangs the host reads which kinds have CTAs that entered and
+// never left (cap_flight_records) -- without the recorder a hang in a wait that is not bounded (griddepcontrol.wait,
+// a cluster barrier, tcgen05.alloc) says nothing about where it is.  One pointer per translation unit; nullptr
+// (the default) costs one uniform branch per CTA.
+static __device__ unsigned int* g_flight = nullptr;
+// point this translation unit's g_flight at the process-wide buffer, once per device (no-op when the recorder is off)
+static inline void cap_install_flight() {
+    static cap_device_once once;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&once.done, __ATOMIC_ACQUIRE) & bit) return;
+    unsigned int* p = cap_flight_buffer_device();
+    if (p != nullptr) cudaMemcpyToSymbol(g_flight, &p, sizeof(p));
+    __atomic_fetch_or(&once.done, bit, __ATOMIC_RELEASE);
+}
+#endif
 
 template <bool PDL = true, typename Kernel, typename... Args>
 inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
                               Args&&... args) {
+#ifdef __CUDACC__
+    cap_install_flight();
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -86,10 +118,7 @@ inline void cap_launch_kernel(Kernel kernel, dim3 grid, dim3 block, size_t smem,
     cap_launch_kernel<false>(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__)
 
 // Opt-in to > 48 KB of dynamic shared memory: the attribute is PER DEVICE, and entry points may be called from several
-// host threads, so the "already done" flag is one atomic bit per device ordinal (setting it twice is harmless).
-struct cap_device_once {
-    unsigned long long done = 0;
-};
+// host threads.
 template <typename Kernel>
 inline int cap_opt_in_smem(cap_device_once& once, Kernel kernel, int bytes) {
     int dev = 0;
@@ -111,6 +140,17 @@ static inline int cap_check_launch(const char* what) {
 // Small device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+enum FlightKind {
+    FK_CHAIN = 0, FK_CHAIN_READY = 1 /* past TMEM allocation and the first cluster barrier */, FK_CROSS_PRODUCER = 2,
+    FK_CROSS_CONSUMER = 3, FK_CROSS_CONSUMER_READY = 4 /* past griddepcontrol.wait */, FK_SELF_ATTENTION = 5, FK_GEMM = 6,
+    FK_GEMM_READY = 7, FK_ATTENTION = 8, FK_BEAM_MERGE = 9, FK_BEAM_SELECT = 10, FK_BEAM_OTHER = 11, FK_ROW_KERNELS = 12,
+    FK_KINDS = 16
+};
+__device__ __forceinline__ void flight_mark(int kind, int left) {
+    unsigned int* f = g_flight;
+    if (f != nullptr) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(f + 2 * kind + left) : "memory");
+}
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

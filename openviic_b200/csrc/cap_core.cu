@@ -74,3 +74,21 @@ extern "C" int cap_fault_records(unsigned int* out, int max_records) {
     }
     return n;
 }
+
+// ---- flight recorder (cap_common.cuh) -----------------------------------------------------------------------------
+// u32 counters [kind][entered, left] behind the fault records in the same pinned page; off unless OPENVIIC_FLIGHT=1.
+extern "C" unsigned int* cap_flight_buffer_device() {
+    static const bool on = getenv("OPENVIIC_FLIGHT") && atoi(getenv("OPENVIIC_FLIGHT")) != 0;
+    if (!on) return nullptr;
+    unsigned long long* base = cap_fault_buffer_device();
+    return base ? reinterpret_cast<unsigned int*>(base) + 256 : nullptr;
+}
+
+// Copies the 2 * kinds counters ([kind][entered, left]) into out and returns the number of kinds (0: recorder off).
+extern "C" int cap_flight_records(unsigned int* out, int max_kinds) {
+    if (g_fault_host == nullptr || cap_flight_buffer_device() == nullptr) return 0;
+    const unsigned int* f = reinterpret_cast<const unsigned int*>(g_fault_host) + 256;
+    const int kinds = max_kinds < 16 ? max_kinds : 16;
+    for (int i = 0; i < 2 * kinds; ++i) out[i] = __atomic_load_n(f + i, __ATOMIC_ACQUIRE);
+    return kinds;
+}

@@ -631,6 +631,7 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int n_jobs = p.n_jobs;
+    if (threadIdx.x == 0) flight_mark(FK_CHAIN, 0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_w512)) : "memory");
@@ -657,6 +658,7 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
     if constexpr (PAIR) cluster_sync(); else __syncthreads();   // pair: the peer's barriers exist before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) flight_mark(FK_CHAIN_READY, 0);
 
     if (warp < FIRST_WORKER_WARP) {
     // control warpgroup: hand registers to the workers (the role split must sit INSIDE this branch so that
@@ -943,6 +945,10 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
         tcgen05_fence_after();
         if constexpr (PAIR) tmem_dealloc_2sm<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
+    if (threadIdx.x == 0) {
+        flight_mark(FK_CHAIN, 1);
+        flight_mark(FK_CHAIN_READY, 1);
+    }
 }
 
 }  // namespace
@@ -1053,6 +1059,7 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     CAP_REQUIRE(d->stacked == nullptr || (d->stacked->n_layers == d->n_layers && d->stacked->levels == levels),
                 "cap_fused_create: stacked weights of another model");
     CAP_PROPAGATE(install_fault_buffer());
+    cap_install_flight();
     cap_fused_decoder* f = new cap_fused_decoder();
     FusedParams& p = f->base;
     memset(&p, 0, sizeof(p));

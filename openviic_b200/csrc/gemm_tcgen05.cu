@@ -79,6 +79,7 @@ template <int BLOCK_N, bool STATS, bool CTA2, bool LN = false>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
+    if (threadIdx.x == 0) flight_mark(FK_GEMM, 0);
     pdl_launch_dependents();  // the next kernel may start its prologue now
     constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // B rows this CTA stages
     constexpr uint32_t B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
@@ -130,6 +131,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(p, 1);
+    if (threadIdx.x == 0) flight_mark(FK_GEMM_READY, 0);
 
     // Producer and MMA warps run their loops with the WHOLE warp (uniform control flow) and elect one lane for
     // the TMA / tcgen05 instructions: issued from an `if (lane == 0)` region every tcgen05.mma was wrapped in an
@@ -386,6 +388,10 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if constexpr (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
     }
     if (threadIdx.x == 32) stamp(p, 7);
+    if (threadIdx.x == 0) {
+        flight_mark(FK_GEMM, 1);
+        flight_mark(FK_GEMM_READY, 1);
+    }
 }
 
 // ---------------------------------------------------------------------------------- host launcher

@@ -172,6 +172,33 @@ __global__ void geometry_bias_kernel(const float* __restrict__ boxes, const floa
     }
 }
 
+// Locally-constrained attention mask of the dual-path encoder (models/utils.py:100-154, get_combine_masks): for box i
+// the grid cells inside its corner-to-corner cell rectangle stay visible (0), every other cell is masked (1).
+// lower_bound(edges, v) = last k with k / g <= v (0 when none), compared in double like numpy's float64 edges.
+__global__ void region_grid_mask_kernel(const float* __restrict__ boxes, uint8_t* __restrict__ mask, int rows, int g) {
+    pdl_prologue();
+    const int cells = g * g;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cells) return;
+    const int cell = idx % cells, r = idx / cells;
+    const float4 bx = *reinterpret_cast<const float4*>(boxes + static_cast<size_t>(r) * 4);
+    auto last_le = [g](float v) {
+        int pos = 0;
+        for (int k = 0; k < g; ++k)
+            if (static_cast<double>(k) / static_cast<double>(g) <= static_cast<double>(v)) pos = k;
+        return pos;
+    };
+    const int x1 = last_le(bx.x), y1 = last_le(bx.y), x2 = last_le(bx.z), y3 = last_le(bx.w);
+    const int top_left = y1 * g + x1, bot_left = y3 * g + x1, width = x2 - x1 + 1;
+    const int rel = cell - top_left;
+    bool covered = false;
+    if (rel >= 0) {
+        const int row = rel / g, col = rel % g;
+        covered = (row * g + top_left <= bot_left) && (col < width);
+    }
+    mask[idx] = covered ? 0 : 1;
+}
+
 // x[r] = emb[token[r]] + pos_table[position]; padflag[r] = token == pad
 __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ emb,
                                     const float* __restrict__ pos_table, int position, int pad_idx,
@@ -287,6 +314,15 @@ extern "C" int cap_geometry_bias(const float* boxes, const float* w_g, const flo
     CAP_LAUNCH((geometry_bias_kernel), (total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), boxes, w_g, b_g, g, B, n, H, d_g, trig);
     count_launch();
     return cap_check_launch("geometry_bias_kernel");
+}
+
+extern "C" int cap_region_grid_mask(const float* boxes, uint8_t* mask, int rows, int grid_size, cap_stream_t stream) {
+    CAP_REQUIRE(boxes && mask, "cap_region_grid_mask: null pointer");
+    CAP_REQUIRE(rows > 0 && grid_size > 0 && grid_size <= 64, "cap_region_grid_mask: bad shape");
+    const int total = rows * grid_size * grid_size;
+    CAP_LAUNCH((region_grid_mask_kernel), (total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), boxes, mask, rows, grid_size);
+    count_launch();
+    return cap_check_launch("region_grid_mask_kernel");
 }
 
 extern "C" int cap_embed_tokens(const int32_t* tokens, const void* word_emb_bf16, const float* pos_table,

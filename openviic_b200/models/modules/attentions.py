@@ -101,6 +101,26 @@ class AugmentedMemoryScaledDotProductAttention(_ProjectedAttention):
         return self._attend(queries, keys, values, attention_mask, mem_k=mem_k, mem_v=mem_v)
 
 
+@META_ATTENTION.register()
+class AdaptiveScaledDotProductAttention(_ProjectedAttention):
+    """Adaptive attention (attentions.py:188-268): every query also attends to its own projected language signal --
+    one extra softmax column q_i . s_i / sqrt(d_k) whose value is s_i (the reference builds it with Python loops over
+    the queries, :255-263).  Only AdaptiveDecoder uses it and that class cannot be constructed in the reference
+    (SURVEY.md section 8c), so parity is pinned at the operator level: tests/golden/adaptive_attention.npz holds the
+    reference class's own output."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.fc_s = nn.Linear(self.d_model, self.h * self.d_k)
+        nn.init.xavier_uniform_(self.fc_s.weight)
+        nn.init.constant_(self.fc_s.bias, 0)
+
+    def forward(self, queries, keys, values, language_signals, attention_mask=None):
+        with torch.no_grad():
+            signals = ops.linear(language_signals, ops.cached_bf16(self.fc_s.weight), self.fc_s.bias)
+        return self._attend(queries, keys, values, attention_mask, sentinel=signals)
+
+
 class MultiHeadAttention(Module):
     """Attention + residual LayerNorm (+ attention-on-attention gate), attentions.py:270-317."""
 

@@ -143,6 +143,17 @@ def geometry_bias(boxes: Tensor, w_g: Tensor, b_g: Tensor, trig: bool) -> Tensor
     return g
 
 
+def region_grid_mask(boxes: Tensor, grid_size: int) -> Tensor:
+    """get_combine_masks (models/utils.py:142-154) on the device: boxes (B,n,4) in [0,1] -> bool (B,1,n,g*g), True =
+    the grid cell lies outside the box's corner-to-corner cell rectangle (masked)."""
+    _need_cuda(boxes)
+    bx = boxes.float().contiguous()
+    b, n, _ = bx.shape
+    mask = torch.empty((b, n, grid_size * grid_size), device=bx.device, dtype=torch.uint8)
+    cabi.call("cap_region_grid_mask", bx.data_ptr(), mask.data_ptr(), b * n, int(grid_size), _stream())
+    return mask.bool().unsqueeze(1)
+
+
 def _canonical_mask(mask: Optional[Tensor], b: int, nq: int, nk: int):
     """bool/uint8 mask broadcastable to (B,1,nq,nk) -> uint8 (B, nq|1, nk) + strides."""
     if mask is None:
@@ -163,12 +174,14 @@ def _canonical_mask(mask: Optional[Tensor], b: int, nq: int, nk: int):
 
 def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, mask: Optional[Tensor] = None,
               geometry: Optional[Tensor] = None, mem_k: Optional[Tensor] = None, mem_v: Optional[Tensor] = None,
-              scale: Optional[float] = None) -> Tensor:
-    """Fused multi-head softmax(q k^T * scale [+mask] [+log g] [| memory]) v with d_k = d_v = 64.
+              scale: Optional[float] = None, sentinel: Optional[Tensor] = None) -> Tensor:
+    """Fused multi-head softmax(q k^T * scale [+mask] [+log g] [| memory] [| sentinel]) v with d_k = d_v = 64.
 
     q (B,nq,H*64), k/v (B,nk,H*64) bf16 (row-strided views are fine); returns (B,nq,H*64) bf16.
+    ``sentinel`` (B,nq,H*64): query i attends to one extra, never-masked key = value sentinel[:, i]
+    (AdaptiveScaledDotProductAttention's language signal, attentions.py:250-263).
     """
-    _need_cuda(q, k, v, mask, geometry, mem_k, mem_v)
+    _need_cuda(q, k, v, mask, geometry, mem_k, mem_v, sentinel)
     q, k, v = as_bf16(q), as_bf16(k), as_bf16(v)
     b, nq, hd = q.shape
     nk = k.shape[1]
@@ -186,13 +199,19 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, mask: Optional[Tensor
     geo = None if geometry is None else geometry.float().contiguous()
     mk = None if mem_k is None else as_bf16(mem_k).reshape(-1, hd).contiguous()
     mv = None if mem_v is None else as_bf16(mem_v).reshape(-1, hd).contiguous()
+    sn = None
+    if sentinel is not None:
+        if tuple(sentinel.shape) != (b, nq, hd):
+            raise RuntimeError(f"sentinel must be {(b, nq, hd)}, got {tuple(sentinel.shape)}")
+        sn = strided(as_bf16(sentinel))
     args = cabi.AttentionArgs(
         q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(),
         q_bs=q.stride(0), k_bs=k.stride(0), v_bs=v.stride(0), o_bs=out.stride(0),
         ldq=q.stride(1), ldk=k.stride(1), ldv=v.stride(1), ldo=out.stride(1),
         mask=_ptr(m), mask_bs=m_bs, mask_qs=m_qs, geometry=_ptr(geo), mem_k=_ptr(mk), mem_v=_ptr(mv),
         n_mem=0 if mk is None else mk.shape[0], B=b, H=heads, nq=nq, nk=nk,
-        scale=float(scale if scale is not None else 1.0 / math.sqrt(64)))
+        scale=float(scale if scale is not None else 1.0 / math.sqrt(64)),
+        sentinel=_ptr(sn), s_bs=0 if sn is None else sn.stride(0), lds=0 if sn is None else sn.stride(1))
     cabi.call("cap_attention", C.byref(args), _stream())
     return out
 

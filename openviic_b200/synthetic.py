@@ -139,6 +139,37 @@ def synth_boxes(batch: int, n: int, seed: int) -> torch.Tensor:
     return torch.from_numpy(np.concatenate([xy, xy + wh], axis=-1))
 
 
+def synth_grid_boxes(batch: int, grid_size: int) -> torch.Tensor:
+    """(B, g*g, 4) boxes of the g x g grid cells, row-major, in [0,1] image coordinates."""
+    k = torch.arange(grid_size * grid_size)
+    x, y = (k % grid_size).float(), torch.div(k, grid_size, rounding_mode="floor").float()
+    cells = torch.stack([x / grid_size, y / grid_size, (x + 1) / grid_size, (y + 1) / grid_size], dim=-1)
+    return cells.unsqueeze(0).expand(batch, -1, -1).contiguous()
+
+
+def synth_dual_inputs(model_cfg, batch: int, n_regions: int, grid_size: int, seed: int) -> Dict[str, torch.Tensor]:
+    """Inputs of the dual-path (region + grid) models: ragged region features with boxes, a full grid with its cells."""
+    ve = model_cfg.VISION_EMBEDDING
+    return {
+        "region_features": synth_features(batch, n_regions, ve.D_REGION_FEATURE, seed, ragged=True),
+        "region_boxes": synth_boxes(batch, n_regions, seed),
+        "grid_features": synth_features(batch, grid_size * grid_size, ve.D_GRID_FEATURE, seed + 1, ragged=False),
+        "grid_boxes": synth_grid_boxes(batch, grid_size),
+    }
+
+
+def synth_adaptive_inputs(case):
+    """(queries, keys, language signals, key mask (B,1,1,nk)) for the operator-level adaptive-attention case."""
+    b, nq, nk, d = case["batch"], case["nq"], case["nk"], case["config"]["D_MODEL"]
+    rng = _rng(case["seed"], "adaptive_attention")
+    q, k, s = (bf16_round(torch.from_numpy(rng.standard_normal(size=shape, dtype=np.float32)))
+               for shape in ((b, nq, d), (b, nk, d), (b, nq, d)))
+    mask = torch.zeros(b, 1, 1, nk, dtype=torch.bool)
+    mask[1, ..., nk // 2:] = True
+    mask[2, ..., ::3] = True
+    return q, k, s, mask
+
+
 def feature_field(model_cfg) -> str:
     return "grid_features" if model_cfg.ARCHITECTURE == "StandardTransformerUsingGrid" else "region_features"
 

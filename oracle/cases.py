@@ -18,6 +18,10 @@ CASES = {
     "aug_mem": dict(config="augmented_memory_transformer.yaml", batch=4, n=37, beam=4, max_len=16, vocab=777, seed=17),
     # CamoTransformer: CrossAttentionMultiLevelEncoder (one 64-wide head in the encoder); module-level CUDA path
     "camo": dict(config="camo_transformer.yaml", batch=4, n=44, beam=5, max_len=14, vocab=900, seed=18),
+    # dual-path DLCT encoder (n regions + grid x grid cells), standard decoder; module-level CUDA path; the reference side
+    # is the patched composition of oracle/ref_harness/gen_golden_dlct.py (the reference has no such architecture)
+    "dlct": dict(config="dlct_transformer.yaml", batch=4, n=30, grid=7, beam=5, max_len=12, vocab=800, seed=19,
+                 overrides={"MODEL": {"ENCODER": {"LAYERS": 2}}}),
 }
 
 
@@ -37,5 +41,10 @@ def apply_overrides(cfg, case):
 
 
 # cases the whole-path engine covers (the others run on the registered modules: the module-level CUDA path)
-MODULE_PATH_CASES = ("camo",)
+MODULE_PATH_CASES = ("camo", "dlct")
 ENGINE_CASES = tuple(c for c in CASES if c not in MODULE_PATH_CASES)
+
+# operator-level case (no runnable architecture reaches this class in the reference): oracle/ref_harness/gen_golden_ops.py
+ADAPTIVE_ATTENTION_CASE = dict(
+    config=dict(ARCHITECTURE="AdaptiveScaledDotProductAttention", D_MODEL=512, HEAD=8, D_KEY=64, D_VALUE=64, DROPOUT=0.1),
+    batch=5, nq=7, nk=37, seed=21)

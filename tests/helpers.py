@@ -20,13 +20,19 @@ TOL_F32 = 1e-4     # kernels whose arithmetic is fp32 end to end
 
 
 def load_case(name: str, device="cpu"):
-    """(case, config, vocab, model, weights, field, feats, boxes) for a table entry."""
+    """(case, config, vocab, model, weights, field, feats, boxes) for a table entry.  Dual-path cases (a "grid" key):
+    field is None, feats = (region features, grid features), boxes = (region boxes, grid boxes) -- the oracle's
+    calling convention for them; make_items() turns them into the four InstanceList fields."""
     case = CASES[name]
     cfg = apply_overrides(ov.get_config(case["config"]), case)
     cfg.MODEL.DEVICE = str(device)
     vocab = synthetic.SyntheticVocab(case["vocab"], case["max_len"])
     model = ov.build_model(cfg.MODEL, vocab).eval()
     weights = synthetic.load_synthetic_weights(model, case["seed"])
+    if "grid" in case:
+        x = synthetic.synth_dual_inputs(cfg.MODEL, case["batch"], case["n"], case["grid"], case["seed"])
+        return (case, cfg, vocab, model, weights, None, (x["region_features"], x["grid_features"]),
+                (x["region_boxes"], x["grid_boxes"]))
     field, feats, boxes = synthetic.synth_inputs(cfg.MODEL, case["batch"], case["n"], case["seed"])
     return case, cfg, vocab, model, weights, field, feats, boxes
 
@@ -37,6 +43,12 @@ def golden(name: str):
 
 def make_items(field, feats, boxes, device):
     items = ov.InstanceList()
+    if field is None:   # dual-path inputs
+        items.set("region_features", feats[0].to(device))
+        items.set("grid_features", feats[1].to(device))
+        items.set("region_boxes", boxes[0].to(device))
+        items.set("grid_boxes", boxes[1].to(device))
+        return items
     items.set(field, feats.to(device))
     if boxes is not None:
         items.set("region_boxes", boxes.to(device))

@@ -90,3 +90,16 @@ def test_position_tables_and_masks():
     emb = oracle.box_relation_embedding(boxes, 4, False)
     assert emb.shape == (1, 2, 2, 4) and abs(float(emb[0, 0, 0, 0]) - np.log(1e-3)) < 1e-6
     assert oracle.box_relation_embedding(boxes, 64, True).shape == (1, 2, 2, 64)
+
+
+def test_adaptive_attention_oracle_reproduces_the_reference_class():
+    """Operator-level pin (no runnable architecture reaches AdaptiveScaledDotProductAttention in the reference)."""
+    import openviic_b200 as ov
+    from openviic_b200 import synthetic
+    from openviic_b200.builders.attention_builder import build_attention
+    from oracle.cases import ADAPTIVE_ATTENTION_CASE as case
+    cfg = ov.CfgNode(dict(case["config"]))
+    weights = synthetic.load_synthetic_weights(build_attention(cfg), case["seed"])
+    q, k, sig, mask = synthetic.synth_adaptive_inputs(case)
+    out = oracle.adaptive_attention(weights, "", cfg, q, k, k, sig, mask)
+    assert np.abs(out.numpy() - golden("adaptive_attention")["out"]).max() < 2e-5

@@ -17,8 +17,10 @@ from helpers import load_case
 
 pytestmark = pytest.mark.gpu
 
-TOL_FUSED = 6e-2   # max-abs logits, fused vs per-operator path: same bf16 operand roundings, different fp32
-                   # summation order and a one-pass LayerNorm variance; measured ~1e-2
+TOL_FUSED = 8e-2   # max-abs logits over the full vocabulary, chains vs per-operator path: two bf16-operand evaluations
+                   # whose fp32 pre-rounding values differ in the last bits (summation order, one-pass LayerNorm
+                   # variance, fused gates), so some operands round to the neighbouring bf16 value: the same size
+                   # as either path's distance to the fp32 reference; measured 0.044-0.064
 
 
 def _engine(model, cfg, vocab, batch, n, beam, device, fused, full_logits=True):

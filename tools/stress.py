@@ -79,9 +79,12 @@ def main():
             time.sleep(2.0)
             if time.perf_counter() - progress["at"] > args.hang_seconds:
                 from openviic_b200 import cabi
+                import faulthandler
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
                 print(json.dumps({"tool": "stress", "hang": True, "after_iteration": progress["iter"],
                                   "seconds_without_progress": time.perf_counter() - progress["at"],
                                   "timed_out_waits_at_source_lines": cabi.fault_records(),
+                                  "flight_recorder_entered_left": cabi.flight_records(),
                                   "env": {k: v for k, v in os.environ.items() if k.startswith("OPENVIIC_")}}), flush=True)
                 os._exit(3)
 
