@@ -507,558 +507,26 @@ decode_self_attention_wide_kernel(const bf16* __restrict__ qkv, const int32_t* _
     if (threadIdx.x == 0) flight_mark(FK_SELF_ATTENTION, 1);
 }
 
-// Decode-step self-attention, split-key variant (opt-in: OPENVIIC_SELF_SPLIT=1; H = 8): SS_SPLITS warps share the
-// keys of one row, each warp has ALL of its keys' K and V vectors in flight at once (<= SS_KEYS keys per round, one
-// round for T <= SS_SPLITS * SS_KEYS = 20 steps) instead of walking the history four keys at a time, and softmax is
-// two-pass within a round (scores, max, then weights: no rescale of the accumulator per key).  The warp-per-row
-// kernel above is latency-bound: (t+1)/4 dependent rounds of HBM latency per launch.  The partial (max, sum,
-// accumulator) states of a row's warps are merged through shared memory, flash-decoding style.
-constexpr int SS_SPLITS = 4;
-constexpr int SS_KEYS = 5;
-constexpr int SS_ROWS = 2;                      // rows per CTA: SS_ROWS * SS_SPLITS warps
-constexpr int SS_EPL = 16;                      // elements per lane (H = 8: 4 lanes per head)
-
-__global__ void __launch_bounds__(SS_ROWS * SS_SPLITS * 32)
-decode_self_attention_split_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ ancestry,
-                                   const uint8_t* __restrict__ padflag, bf16* __restrict__ out, int ldo, int t, int R,
-                                   float scale) {
-    pdl_prologue();
-    __shared__ __align__(16) float part[SS_ROWS * SS_SPLITS * 32 * (SS_EPL + 2)];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = warp % SS_SPLITS;
-    const int r = blockIdx.x * SS_ROWS + warp / SS_SPLITS;
-    constexpr int hd = 32 * SS_EPL;
-    const size_t row_stride = static_cast<size_t>(3) * hd;
-    const size_t step_stride = static_cast<size_t>(R) * row_stride;
-    const int nkeys = t + 1;
-    const int per_split = (nkeys + SS_SPLITS - 1) / SS_SPLITS;
-    const int j_begin = split * per_split;
-    const int j_end = min(nkeys, j_begin + per_split);
-
-    float m = -INFINITY, l = 0.f, acc[SS_EPL];
-#pragma unroll
-    for (int i = 0; i < SS_EPL; ++i) acc[i] = 0.f;
-    if (r < R && j_begin < j_end) {
-        float q[SS_EPL];
-        {
-            const bf16x8* qp = reinterpret_cast<const bf16x8*>(qkv + t * step_stride + r * row_stride + lane * SS_EPL);
-            unpack8(qp[0], q);
-            unpack8(qp[1], q + 8);
-#pragma unroll
-            for (int i = 0; i < SS_EPL; ++i) q[i] *= scale * 1.4426950408889634f;   // scores in the log2 domain
-        }
-        for (int j0 = j_begin; j0 < j_end; j0 += SS_KEYS) {
-            uint4 kreg[SS_KEYS][2], vreg[SS_KEYS][2];
-            bool live[SS_KEYS];
-#pragma unroll
-            for (int u = 0; u < SS_KEYS; ++u) {   // every key of the round in flight before the first use
-                const int j = min(j0 + u, j_end - 1);
-                const int sl = (j == t) ? r : ancestry[static_cast<size_t>(j) * R + r];
-                live[u] = (j0 + u < j_end) && padflag[static_cast<size_t>(j) * R + sl] == 0;
-                const bf16* base = qkv + j * step_stride + sl * row_stride + lane * SS_EPL;
-                kreg[u][0] = __ldcs(reinterpret_cast<const uint4*>(base + hd));
-                kreg[u][1] = __ldcs(reinterpret_cast<const uint4*>(base + hd) + 1);
-                vreg[u][0] = __ldcs(reinterpret_cast<const uint4*>(base + 2 * hd));
-                vreg[u][1] = __ldcs(reinterpret_cast<const uint4*>(base + 2 * hd) + 1);
-            }
-            float sc[SS_KEYS], m_round = m;
-#pragma unroll
-            for (int u = 0; u < SS_KEYS; ++u) {
-                float kf[SS_EPL];
-                unpack8(*reinterpret_cast<const bf16x8*>(&kreg[u][0]), kf);
-                unpack8(*reinterpret_cast<const bf16x8*>(&kreg[u][1]), kf + 8);
-                float s0 = q[0] * kf[0], s1 = q[1] * kf[1], s2 = q[2] * kf[2], s3 = q[3] * kf[3];
-#pragma unroll
-                for (int i = 4; i < SS_EPL; i += 4) {
-                    s0 = fmaf(q[i], kf[i], s0);
-                    s1 = fmaf(q[i + 1], kf[i + 1], s1);
-                    s2 = fmaf(q[i + 2], kf[i + 2], s2);
-                    s3 = fmaf(q[i + 3], kf[i + 3], s3);
-                }
-                float x = (s0 + s1) + (s2 + s3);
-                x += __shfl_xor_sync(0xffffffffu, x, 2);
-                x += __shfl_xor_sync(0xffffffffu, x, 1);
-                sc[u] = live[u] ? x : -INFINITY;
-                m_round = fmaxf(m_round, sc[u]);
-            }
-            if (m_round == -INFINITY) continue;   // nothing live yet (warp-uniform per head group: every lane agrees on live[])
-            const float corr = exp2f(m - m_round);    // exp2(-inf) = 0 on the first live round
-            l *= corr;
-#pragma unroll
-            for (int i = 0; i < SS_EPL; ++i) acc[i] *= corr;
-#pragma unroll
-            for (int u = 0; u < SS_KEYS; ++u) {
-                const float p = exp2f(sc[u] - m_round);   // 0 for masked keys
-                l += p;
-                float vf[SS_EPL];
-                unpack8(*reinterpret_cast<const bf16x8*>(&vreg[u][0]), vf);
-                unpack8(*reinterpret_cast<const bf16x8*>(&vreg[u][1]), vf + 8);
-#pragma unroll
-                for (int i = 0; i < SS_EPL; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
-            }
-            m = m_round;
-        }
-    }
-    float* mine = part + (static_cast<size_t>(warp) * 32 + lane) * (SS_EPL + 2);
-#pragma unroll
-    for (int i = 0; i < SS_EPL; ++i) mine[i] = acc[i];
-    mine[SS_EPL] = m;
-    mine[SS_EPL + 1] = l;
-    __syncthreads();
-    if (split == 0 && r < R) {
-        const float* row_part = part + (static_cast<size_t>(warp) * 32 + lane) * (SS_EPL + 2);   // this row's split 0
-        constexpr int SPLIT_STRIDE = 32 * (SS_EPL + 2);
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < SS_SPLITS; ++c) mx = fmaxf(mx, row_part[c * SPLIT_STRIDE + SS_EPL]);
-        float lsum = 0.f, o[SS_EPL];
-#pragma unroll
-        for (int i = 0; i < SS_EPL; ++i) o[i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < SS_SPLITS; ++c) {
-            const float* pc = row_part + c * SPLIT_STRIDE;
-            const float mc = pc[SS_EPL];
-            const float f = (mc == -INFINITY) ? 0.f : exp2f(mc - mx);
-            lsum = fmaf(pc[SS_EPL + 1], f, lsum);
-#pragma unroll
-            for (int i = 0; i < SS_EPL; ++i) o[i] = fmaf(pc[i], f, o[i]);
-        }
-        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-#pragma unroll
-        for (int i = 0; i < SS_EPL; ++i) o[i] *= inv;
-        bf16* orow = out + static_cast<size_t>(r) * ldo + lane * SS_EPL;
-        reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
-        reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
-    }
-}
-
-// Decode-step cross-attention, wide variant (H = 8): one CTA per image, its 4 warps split the image's
-// keys round-robin, every warp serves ALL `BEAMS` rows of the image and all heads at once (lane l owns
-// 16 consecutive elements of the 512-wide rows, 4 lanes per head), so each K/V row is read from HBM
-// exactly once per step with 32 busy lanes; the per-warp online-softmax partials (m, l, acc) are
-// merged through shared memory (flash-decoding style).
-constexpr int XW_WARPS = 4;
-constexpr int XW_EPL = 16;
-
-template <int BEAMS>
-__global__ void __launch_bounds__(XW_WARPS * 32)
-decode_cross_attention_wide_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
-                                   const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
-                                   float scale, int n_images) {
-    pdl_prologue();
-    extern __shared__ __align__(16) float xw_smem[];
-    float* s_acc = xw_smem;                                             // [WARPS][BEAMS][32][EPL]
-    float* s_m = s_acc + XW_WARPS * BEAMS * 32 * XW_EPL;                // [WARPS][BEAMS][32]
-    float* s_l = s_m + XW_WARPS * BEAMS * 32;                           // [WARPS][BEAMS][32]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = blockIdx.x; b < n_images; b += gridDim.x) {   // grid-stride over images (grid < images: fewer SMs touched)
-    constexpr int hd = 32 * XW_EPL;
-    const bf16* kvb = kv + static_cast<size_t>(b) * n * 2 * hd + lane * XW_EPL;
-    const uint8_t* mrow = key_mask ? key_mask + static_cast<size_t>(b) * n : nullptr;
-
-    bf16x8 qreg[BEAMS][2];
-#pragma unroll
-    for (int bb = 0; bb < BEAMS; ++bb) {
-        const bf16x8* qp = reinterpret_cast<const bf16x8*>(q + static_cast<size_t>(b * BEAMS + bb) * ldq + lane * XW_EPL);
-        qreg[bb][0] = qp[0];
-        qreg[bb][1] = qp[1];
-    }
-    float m[BEAMS], l[BEAMS], acc[BEAMS][XW_EPL];
-#pragma unroll
-    for (int bb = 0; bb < BEAMS; ++bb) {
-        m[bb] = -INFINITY;
-        l[bb] = 0.f;
-#pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) acc[bb][i] = 0.f;
-    }
-    for (int j0 = warp; j0 < n; j0 += 2 * XW_WARPS) {
-        bf16x8 kreg[2][2], vreg[2][2];
-        bool live[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int j = j0 + u * XW_WARPS;
-            live[u] = j < n && !(mrow && mrow[j]);
-            const bf16* base = kvb + static_cast<size_t>(min(j, n - 1)) * 2 * hd;
-            kreg[u][0] = reinterpret_cast<const bf16x8*>(base)[0];
-            kreg[u][1] = reinterpret_cast<const bf16x8*>(base)[1];
-            vreg[u][0] = reinterpret_cast<const bf16x8*>(base + hd)[0];
-            vreg[u][1] = reinterpret_cast<const bf16x8*>(base + hd)[1];
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (!live[u]) continue;  // warp-uniform
-            float kf[XW_EPL], vf[XW_EPL];
-            unpack8(kreg[u][0], kf);
-            unpack8(kreg[u][1], kf + 8);
-            unpack8(vreg[u][0], vf);
-            unpack8(vreg[u][1], vf + 8);
-#pragma unroll
-            for (int bb = 0; bb < BEAMS; ++bb) {
-                float qf[XW_EPL];
-                unpack8(qreg[bb][0], qf);
-                unpack8(qreg[bb][1], qf + 8);
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < XW_EPL; ++i) s = fmaf(qf[i], kf[i], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s *= scale;
-                const float m_new = fmaxf(m[bb], s);
-                const float corr = __expf(m[bb] - m_new);
-                const float p = __expf(s - m_new);
-                l[bb] = l[bb] * corr + p;
-#pragma unroll
-                for (int i = 0; i < XW_EPL; ++i) acc[bb][i] = acc[bb][i] * corr + p * vf[i];
-                m[bb] = m_new;
-            }
-        }
-    }
-#pragma unroll
-    for (int bb = 0; bb < BEAMS; ++bb) {
-        const int slot = (warp * BEAMS + bb) * 32 + lane;
-        s_m[slot] = m[bb];
-        s_l[slot] = l[bb];
-        float4* dst = reinterpret_cast<float4*>(s_acc + static_cast<size_t>(slot) * XW_EPL);
-#pragma unroll
-        for (int i = 0; i < XW_EPL; i += 4) dst[i / 4] = make_float4(acc[bb][i], acc[bb][i + 1], acc[bb][i + 2], acc[bb][i + 3]);
-    }
-    __syncthreads();
-    for (int bb = warp; bb < BEAMS; bb += XW_WARPS) {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < XW_WARPS; ++w) mx = fmaxf(mx, s_m[(w * BEAMS + bb) * 32 + lane]);
-        float lsum = 0.f, o[XW_EPL];
-#pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) o[i] = 0.f;
-#pragma unroll
-        for (int w = 0; w < XW_WARPS; ++w) {
-            const int slot = (w * BEAMS + bb) * 32 + lane;
-            const float mw = s_m[slot];
-            const float f = (mw == -INFINITY) ? 0.f : __expf(mw - mx);
-            lsum += s_l[slot] * f;
-            const float4* src = reinterpret_cast<const float4*>(s_acc + static_cast<size_t>(slot) * XW_EPL);
-#pragma unroll
-            for (int i = 0; i < XW_EPL; i += 4) {
-                const float4 a4 = src[i / 4];
-                o[i] += a4.x * f; o[i + 1] += a4.y * f; o[i + 2] += a4.z * f; o[i + 3] += a4.w * f;
-            }
-        }
-        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-#pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) o[i] *= inv;
-        bf16* orow = out + static_cast<size_t>(b * BEAMS + bb) * ldo + lane * XW_EPL;
-        reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
-        reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
-    }
-    __syncthreads();  // the merge buffers are reused by the next image
-    }
-}
-
-// Decode-step cross-attention, bulk-staged variant (H = 8, n*2 KB fits shared memory): one CTA per image.
-// The image's whole K|V block is contiguous in HBM, so thread 0 streams it into shared memory with a few
-// cp.async.bulk copies (no registers, the full block in flight at once, one mbarrier per chunk); warp b
-// then serves beam b over all keys straight from shared memory (lanes tile the 512-wide rows, 4 lanes per
-// head, online softmax) while later chunks are still landing.  Every K/V byte crosses HBM once per step.
-constexpr int XS_CHUNKS = 4;
+// ---------------------------------------------------------------------------- decode cross-attention
+// Decode-step cross-attention on the warp-level tensor path (H = 8): one warp per head; an image's K|V rows are
+// bulk-copied (one cp.async.bulk per 2 KB row) into shared-memory rows of pitch 2 KB + 16 B, which makes both fragment
+// access patterns conflict-free: K as the col-major B operand of S = Q.K^T by 32-bit loads (lanes of a quad-group walk
+// rows, pitch = 4 banks), V as the B operand of O = P.V by ldmatrix.trans (8 rows x 16 B, pitch = one 16-byte bank
+// group).  The image's beams are rows 0..beams-1 of the m16 tile (the other rows are zero: most of the MMA is padding,
+// still ~7x fewer instructions than CUDA-core arithmetic, whose per-key unpack / FMA / exp chain is issue-bound -- the
+// round-1 kernels of that kind measured 23.3 us per launch at the bench shape against 16.4 us); keys past n read one
+// shared zero row.  S accumulators become the P operand in registers (bf16), softmax in fp32 in the log2 domain.
+constexpr int XT_PITCH = 2048 + 16;   // bytes per staged K|V row
 
 __device__ __forceinline__ uint32_t xs_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-template <int BEAMS>
-__global__ void __launch_bounds__(BEAMS * XS_CHUNKS * 32)
-decode_cross_attention_smem_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
-                                   const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int n,
-                                   float scale) {
-    // warp (beam, chunk): the image's keys are split into XS_CHUNKS row chunks, one bulk copy and one mbarrier each;
-    // a warp starts on its chunk the moment it has landed and the XS_CHUNKS partial softmax states of a beam are
-    // merged through the (by then dead) staging area.  Four times the warps of a warp-per-beam layout: the
-    // dependent exp / FMA chain per key is the long pole of this kernel, not the copy.
-    pdl_launch_dependents();
-    extern __shared__ __align__(128) uint8_t xs_smem[];
-    __shared__ __align__(8) uint64_t bars[XS_CHUNKS];
-    constexpr int hd = 32 * XW_EPL;          // 512
-    constexpr int ROW_BYTES = 2 * hd * 2;    // K|V row of one key: 2 KB
-    const int b = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int beam = warp % BEAMS, chunk = warp / BEAMS;
-    const int rows_per_chunk = (n + XS_CHUNKS - 1) / XS_CHUNKS;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int c = 0; c < XS_CHUNKS; ++c)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs_smem_u32(&bars[c])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // K/V were projected at encode time, many kernels ago: safe to fetch before the PDL wait below.
-        // Streamed once per step: evict-first, so that 77 MB of K|V per step do not push the weights out of L2.
-        uint64_t stream_policy;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + static_cast<size_t>(b) * n * ROW_BYTES;
-#pragma unroll
-        for (int c = 0; c < XS_CHUNKS; ++c) {
-            const int r0 = c * rows_per_chunk;
-            const int rows = min(rows_per_chunk, n - r0);
-            const uint32_t bytes = rows > 0 ? static_cast<uint32_t>(rows) * ROW_BYTES : 0u;
-            const uint32_t bar = xs_smem_u32(&bars[c]);
-            if (bytes) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                        xs_smem_u32(xs_smem + static_cast<size_t>(r0) * ROW_BYTES)),
-                    "l"(reinterpret_cast<uint64_t>(src + static_cast<size_t>(r0) * ROW_BYTES)), "r"(bytes), "r"(bar),
-                    "l"(stream_policy)
-                    : "memory");
-            } else {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-            }
-        }
-    }
-    pdl_wait();  // q comes from the previous kernel
-    __syncthreads();  // barrier inits visible to every waiter
-
-    const int row = b * BEAMS + beam;
-    float qf[XW_EPL];
-    {
-        const bf16x8* qp = reinterpret_cast<const bf16x8*>(q + static_cast<size_t>(row) * ldq + lane * XW_EPL);
-        unpack8(qp[0], qf);
-        unpack8(qp[1], qf + 8);
-#pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) qf[i] *= scale * 1.4426950408889634f;  // scores in the log2 domain
-    }
-    const uint8_t* mrow = key_mask ? key_mask + static_cast<size_t>(b) * n : nullptr;
-    float m = -INFINITY, l = 0.f, acc[XW_EPL];
-#pragma unroll
-    for (int i = 0; i < XW_EPL; ++i) acc[i] = 0.f;
-    const int r0 = chunk * rows_per_chunk;
-    const int r1 = min(r0 + rows_per_chunk, n);
-    if (r0 < r1) {
-        cap_ptx::mbar_wait(&bars[chunk], 0);   // this warp's chunk has landed (phase 0); bounded, leaves a fault record
-        for (int j = r0; j < r1; ++j) {
-            if (mrow && mrow[j]) continue;  // warp-uniform
-            const bf16x8* kp = reinterpret_cast<const bf16x8*>(xs_smem + static_cast<size_t>(j) * ROW_BYTES) + lane * 2;
-            const bf16x8* vp = kp + hd / 8;
-            float kf[XW_EPL], vf[XW_EPL];
-            unpack8(kp[0], kf);
-            unpack8(kp[1], kf + 8);
-            float s0 = qf[0] * kf[0], s1 = qf[1] * kf[1], s2 = qf[2] * kf[2], s3 = qf[3] * kf[3];
-#pragma unroll
-            for (int i = 4; i < XW_EPL; i += 4) {
-                s0 = fmaf(qf[i], kf[i], s0);
-                s1 = fmaf(qf[i + 1], kf[i + 1], s1);
-                s2 = fmaf(qf[i + 2], kf[i + 2], s2);
-                s3 = fmaf(qf[i + 3], kf[i + 3], s3);
-            }
-            float s = (s0 + s1) + (s2 + s3);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            unpack8(vp[0], vf);
-            unpack8(vp[1], vf + 8);
-            const float m_new = fmaxf(m, s);
-            const float corr = exp2f(m - m_new);
-            const float p = exp2f(s - m_new);
-            l = fmaf(l, corr, p);
-#pragma unroll
-            for (int i = 0; i < XW_EPL; ++i) acc[i] = fmaf(p, vf[i], acc[i] * corr);
-            m = m_new;
-        }
-    }
-    // merge the XS_CHUNKS partial states of each beam; the staging area is dead once every warp is past its keys
-    __syncthreads();
-    float* part = reinterpret_cast<float*>(xs_smem);                  // [warp][lane][XW_EPL + 2]
-    float* mine = part + (static_cast<size_t>(warp) * 32 + lane) * (XW_EPL + 2);
-#pragma unroll
-    for (int i = 0; i < XW_EPL; ++i) mine[i] = acc[i];
-    mine[XW_EPL] = m;
-    mine[XW_EPL + 1] = l;
-    __syncthreads();
-    if (chunk == 0) {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < XS_CHUNKS; ++c)
-            mx = fmaxf(mx, part[(static_cast<size_t>(c * BEAMS + beam) * 32 + lane) * (XW_EPL + 2) + XW_EPL]);
-        float lsum = 0.f, o[XW_EPL];
-#pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) o[i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < XS_CHUNKS; ++c) {
-            const float* pc = part + (static_cast<size_t>(c * BEAMS + beam) * 32 + lane) * (XW_EPL + 2);
-            const float mc = pc[XW_EPL];
-            const float f = (mc == -INFINITY) ? 0.f : exp2f(mc - mx);
-            lsum = fmaf(pc[XW_EPL + 1], f, lsum);
-#pragma unroll
-            for (int i = 0; i < XW_EPL; ++i) o[i] = fmaf(pc[i], f, o[i]);
-        }
-        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-#pragma unroll
-        for (int i = 0; i < XW_EPL; ++i) o[i] *= inv;
-        bf16* orow = out + static_cast<size_t>(row) * ldo + lane * XW_EPL;
-        reinterpret_cast<bf16x8*>(orow)[0] = pack8(o);
-        reinterpret_cast<bf16x8*>(orow)[1] = pack8(o + 8);
-    }
-}
-
-template <int BEAMS>
-int launch_cross_smem(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
-                      float scale, cudaStream_t stream) {
-    // K|V staging; the partial-state merge (XS_CHUNKS * BEAMS warps x 32 lanes x 18 floats) reuses it
-    const size_t smem = std::max(static_cast<size_t>(n) * 2048,
-                                 static_cast<size_t>(XS_CHUNKS) * BEAMS * 32 * (XW_EPL + 2) * sizeof(float));
-    static cap_device_once smem_once;
-    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_smem_kernel<BEAMS>, 208 * 1024));
-    CAP_LAUNCH((decode_cross_attention_smem_kernel<BEAMS>), B, BEAMS * XS_CHUNKS * 32, smem, stream, q, ldq, kv, key_mask,
-               out, ldo, n, scale);
-    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
-    return cap_check_launch("decode_cross_attention_smem_kernel");
-}
-
-// Decode-step cross-attention on the warp-level tensor path (opt-in: OPENVIIC_CROSS_TC=1; H = 8): one CTA per image,
-// one warp per head.  The image's K|V rows are bulk-copied (one cp.async.bulk per 2 KB row, all in flight at once)
-// into shared memory rows of pitch 2 KB + 16 B, which makes both fragment access patterns conflict-free: K as the
-// col-major B operand of S = Q.K^T by 32-bit loads (lanes of a quad-group walk rows, pitch = 4 banks), V as the B
-// operand of O = P.V by ldmatrix.trans (8 rows x 16 B, pitch = one 16-byte bank group).  The image's beams are rows
-// 0..BEAMS-1 of the m16 tile (rows BEAMS..15 are zero: 11/16 of the MMA is padding, still ~7x fewer instructions than
-// the CUDA-core kernel above, whose per-key unpack / FMA / exp chain is issue-bound); keys past n read one shared
-// zero row.  S accumulators become the P operand in registers (bf16), softmax in fp32 in the log2 domain.
-constexpr int XT_PITCH = 2048 + 16;   // bytes per staged K|V row
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-template <int NT>   // 8-key tiles: 7 (n <= 56) or 13 (n <= 104)
-__global__ void __launch_bounds__(256)
-decode_cross_attention_tc_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv,
-                                 const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int ldo, int beams, int n,
-                                 float scale) {
-    pdl_launch_dependents();
-    extern __shared__ __align__(128) uint8_t xt_smem[];     // [n + 1][XT_PITCH] (last row zero), then NT*8 mask bytes
-    __shared__ __align__(8) uint64_t bar;
-    const int b = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    uint8_t* zero_row = xt_smem + static_cast<size_t>(n) * XT_PITCH;
-    uint8_t* smask = zero_row + XT_PITCH;
-    const uint32_t bar_addr = xs_smem_u32(&bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(static_cast<uint32_t>(n) * 2048u)
-                     : "memory");
-    }
-    for (int i = threadIdx.x; i < XT_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zero_row)[i] = 0u;
-    for (int j = threadIdx.x; j < NT * 8; j += blockDim.x) smask[j] = (j >= n || (key_mask && key_mask[static_cast<size_t>(b) * n + j])) ? 1 : 0;
-    __syncthreads();   // barrier armed before any copy can complete on it; zero row and mask visible
-    if (threadIdx.x < n) {   // K|V were projected at encode time: safe to fetch before the PDL wait
-        uint64_t stream_policy;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(kv) + (static_cast<size_t>(b) * n + threadIdx.x) * 2048;
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                xs_smem_u32(xt_smem + static_cast<size_t>(threadIdx.x) * XT_PITCH)),
-            "l"(reinterpret_cast<uint64_t>(src)), "r"(2048u), "r"(bar_addr), "l"(stream_policy)
-            : "memory");
-    }
-    pdl_wait();   // q comes from the previous kernel
-
-    const int h = warp;
-    // A operand: rows g < beams of the image's queries, head h; rows 8..15 of the tile are zero
-    uint32_t qa[4][4];
-    {
-        const bf16* qrow = q + static_cast<size_t>(b * beams + (g < beams ? g : 0)) * ldq + h * HEAD_DIM + 2 * t;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t lo = *reinterpret_cast<const uint32_t*>(qrow + ks * 16);
-            const uint32_t hi = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8);
-            qa[ks][0] = g < beams ? lo : 0u;
-            qa[ks][1] = 0u;
-            qa[ks][2] = g < beams ? hi : 0u;
-            qa[ks][3] = 0u;
-        }
-    }
-    cap_ptx::mbar_wait(&bar, 0);   // all rows landed (phase 0); bounded, leaves a fault record
-    // S = Q.K^T
-    float s[NT][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const int key = nt * 8 + g;
-        const uint8_t* krow = (key < n ? xt_smem + static_cast<size_t>(key) * XT_PITCH : zero_row) + h * (HEAD_DIM * 2) + 4 * t;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            mma_bf16_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(krow + ks * 32),
-                           *reinterpret_cast<const uint32_t*>(krow + ks * 32 + 16));
-    }
-    // softmax over the keys of row g (log2 domain); a quad holds one row
-    const float sc = scale * 1.4426950408889634f;
-    float mx = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float x = smask[nt * 8 + 2 * t + e] ? -INFINITY : s[nt][e] * sc;
-            s[nt][e] = x;
-            mx = fmaxf(mx, x);
-        }
-    }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float sum = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float p = (mx == -INFINITY) ? 0.f : exp2f(s[nt][e] - mx);
-            s[nt][e] = p;
-            sum += p;
-        }
-    }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    // O = P.V : two 8-key score tiles are the A operand of one 16-key step; V fragments by ldmatrix.trans
-    float o[8][4];
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
-    const int mi = lane >> 3, mr = lane & 7;   // this lane addresses row mr of 8x8 matrix mi of an x4 load
-#pragma unroll
-    for (int kk = 0; kk < (NT + 1) / 2; ++kk) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = 0u;
-        pa[2] = (2 * kk + 1 < NT) ? pack_bf16x2(s[2 * kk + 1 < NT ? 2 * kk + 1 : 0][0], s[2 * kk + 1 < NT ? 2 * kk + 1 : 0][1]) : 0u;
-        pa[3] = 0u;
-        const int key = kk * 16 + (mi & 1) * 8 + mr;
-        const uint8_t* vrow = (key < n ? xt_smem + static_cast<size_t>(key) * XT_PITCH : zero_row) + 1024 + h * (HEAD_DIM * 2) +
-                              (mi >> 1) * 16;
-#pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {   // dims (2 dp) * 8 .. +15: matrices 0/1 = keys lo/hi of tile 2 dp, 2/3 of tile 2 dp + 1
-            uint32_t vb[4];
-            ldmatrix_x4_trans(vb, xs_smem_u32(vrow + dp * 32));
-            mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
-            mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
-        }
-    }
-    if (g < beams) {
-        const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        bf16* orow = out + static_cast<size_t>(b * beams + g) * ldo + h * HEAD_DIM + 2 * t;
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt)
-            *reinterpret_cast<bf162*>(orow + dt * 8) = __floats2bfloat162_rn(o[dt][0] * inv, o[dt][1] * inv);
-    }
-}
-
-template <int NT>
-int launch_cross_tc(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int beams,
-                    int n, float scale, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(n + 1) * XT_PITCH + NT * 8;
-    static cap_device_once smem_once;
-    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_tc_kernel<NT>, 220 * 1024));
-    CAP_LAUNCH((decode_cross_attention_tc_kernel<NT>), B, 256, smem, stream, q, ldq, kv, key_mask, out, ldo, beams, n, scale);
-    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
-    return cap_check_launch("decode_cross_attention_tc_kernel");
-}
-
-// Decode-step cross-attention, streamed (default since round 2; H = 8).  The tensor-path kernel above runs one CTA
-// per image: load 100 KB, wait, compute, exit -- nothing overlaps inside a CTA, and its 256 CTAs hold 200 KB of
-// shared memory on 128 SMs for the whole launch (12 us for 25.7 MB of K|V = 2.1 TB/s alone on the GPU).  Here a CTA is
-// a small pipeline: a PRODUCER warp streams image after image into a ring of shared-memory stages (one cp.async.bulk
+// Streamed: a first version ran one CTA per image -- load 100 KB, wait, compute, exit: nothing overlapped inside a CTA,
+// and its 256 CTAs held 200 KB of shared memory on 128 SMs for the whole launch.  Here a CTA is a small pipeline: a PRODUCER warp streams image after image into a ring of shared-memory stages (one cp.async.bulk
 // per 2 KB K|V row, one mbarrier phase per image), eight CONSUMER warps (one per head) run the same mma.sync
 // arithmetic on the stage that has landed while the next image is in flight, and hand the stage back through an
 // "empty" barrier.  A quarter of the CTAs (4 images each) then move the same bytes: the launch costs a fraction of
@@ -1268,21 +736,7 @@ int launch_cross_stream(const bf16* q, int ldq, const bf16* kv, const uint8_t* k
     return cap_check_launch("decode_cross_attention_stream_kernel");
 }
 
-template <int BEAMS>
-int launch_cross_wide(const bf16* q, int ldq, const bf16* kv, const uint8_t* key_mask, bf16* out, int ldo, int B, int n,
-                      float scale, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(XW_WARPS) * BEAMS * 32 * (XW_EPL + 2) * sizeof(float);
-    static cap_device_once smem_once;
-    CAP_PROPAGATE(cap_opt_in_smem(smem_once, decode_cross_attention_wide_kernel<BEAMS>, 64 * 1024));
-    static const int max_grid = getenv("OPENVIIC_CROSS_GRID") ? atoi(getenv("OPENVIIC_CROSS_GRID")) : 0;
-    const int grid = (max_grid > 0 && max_grid < B) ? max_grid : B;
-    CAP_LAUNCH((decode_cross_attention_wide_kernel<BEAMS>), grid, XW_WARPS * 32, smem, stream, q, ldq, kv, key_mask, out, ldo, n,
-               scale, B);
-    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
-    return cap_check_launch("decode_cross_attention_wide_kernel");
-}
-
-// Encoder self-attention with the whole image in shared memory (opt-in: OPENVIIC_ENC_TC=1; plain scaled dot-product,
+// Encoder self-attention with the whole image in shared memory (plain scaled dot-product,
 // H = 8, fused q|k|v rows, n <= 64): one CTA per image, one warp per head.  The image's n rows of q|k|v (3 KB each,
 // contiguous in the fused projection output) are bulk-copied once into rows of pitch 3 KB + 16 B; every warp then
 // walks the 16-query tiles of its head: S = Q.K^T with A and B fragments by conflict-free 32-bit loads, fp32 softmax
@@ -1425,10 +879,9 @@ int launch_encoder_tc(const AttnDev& a, cudaStream_t stream) {
 
 int launch_attention(const AttnDev& a, cudaStream_t stream) {
     const int nk_all = a.nk + a.n_mem;
-    {   // opt-in: whole-image encoder self-attention (plain attention over fused q|k|v rows, one CTA per image)
-        const char* enc_tc = getenv("OPENVIIC_ENC_TC");   // read per call: a probe compares both paths in one process
+    {   // whole-image encoder self-attention (plain attention over fused q|k|v rows, one CTA per image)
         const int hd = a.H * HEAD_DIM;
-        if (enc_tc && atoi(enc_tc) != 0 && a.H == 8 && a.geometry == nullptr && a.n_mem == 0 && a.nq == a.nk && a.nk <= 64 &&
+        if (a.H == 8 && a.geometry == nullptr && a.n_mem == 0 && a.nq == a.nk && a.nk <= 64 &&
             a.k == a.q + hd && a.v == a.q + 2 * hd && a.ldq == 3 * hd && a.ldk == 3 * hd && a.ldv == 3 * hd &&
             a.q_bs == static_cast<long long>(a.nk) * 3 * hd && a.o_bs == static_cast<long long>(a.nk) * a.ldo &&
             (a.mask == nullptr || (a.mask_qs == 0 && a.mask_bs == a.nk)) && a.ldo % 2 == 0 &&
@@ -1491,40 +944,15 @@ extern "C" int cap_decode_cross_attention(const void* q, int ldq, const void* kv
     CAP_REQUIRE(q && kv && out, "cap_decode_cross_attention: null pointer");
     CAP_REQUIRE(B > 0 && beam > 0 && n > 0 && n <= MAX_KEYS && H > 0, "cap_decode_cross_attention: bad shape");
     const int hd = H * HEAD_DIM;
-    if (H == 8 && beam <= 5 && ldq % 8 == 0 && ldo % 8 == 0) {
+    if (H == 8 && beam <= 8 && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
         const bf16* qp = static_cast<const bf16*>(q);
         const bf16* kvp = static_cast<const bf16*>(kv);
         bf16* op = static_cast<bf16*>(out);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
-        static const bool no_bulk = getenv("OPENVIIC_CROSS_NO_BULK") != nullptr;
-        const char* tc_env = getenv("OPENVIIC_CROSS_TC");   // read per call: a probe compares both paths in one process
-        const int tc_mode = tc_env ? atoi(tc_env) : 2;   // 0 CUDA cores, 1 tensor path one CTA per image, 2 streamed (default)
-        const bool tensor_path = tc_mode != 0;
-        if (tc_mode == 2 && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
-            if (n <= 56) return launch_cross_stream<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
-            return launch_cross_stream<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
-        }
-        if (tensor_path && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
-            if (n <= 56) return launch_cross_tc<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
-            return launch_cross_tc<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
-        }
-        if (!no_bulk && static_cast<size_t>(n) * 2048 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
-            switch (beam) {  // bulk-staged variant: the image's K|V block lives in shared memory
-                case 1: return launch_cross_smem<1>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-                case 2: return launch_cross_smem<2>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-                case 3: return launch_cross_smem<3>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-                case 4: return launch_cross_smem<4>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-                default: return launch_cross_smem<5>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-            }
-        }
-        switch (beam) {
-            case 1: return launch_cross_wide<1>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-            case 2: return launch_cross_wide<2>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-            case 3: return launch_cross_wide<3>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-            case 4: return launch_cross_wide<4>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-            default: return launch_cross_wide<5>(qp, ldq, kvp, key_mask, op, ldo, B, n, scale, s);
-        }
+        if (n <= 56) return launch_cross_stream<7>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
+        return launch_cross_stream<13>(qp, ldq, kvp, key_mask, op, ldo, B, beam, n, scale, s);
     }
+    // other shapes: the general attention kernels with the image's beams as the queries
     AttnDev a;
     a.q = static_cast<const bf16*>(q);
     a.k = static_cast<const bf16*>(kv);
@@ -1549,9 +977,7 @@ extern "C" int cap_decode_cross_attention_levels(const void* q, int ldq, const v
                                                  int beam, int n, int H, int levels, float scale, cap_stream_t stream) {
     CAP_REQUIRE(q && kv && out, "cap_decode_cross_attention_levels: null pointer");
     CAP_REQUIRE(B > 0 && beam > 0 && n > 0 && n <= MAX_KEYS && H > 0 && levels >= 1, "cap_decode_cross_attention_levels: bad shape");
-    const char* tc_env = getenv("OPENVIIC_CROSS_TC");
-    const bool streamed = (tc_env ? atoi(tc_env) : 2) == 2;
-    if (streamed && H == 8 && beam <= 8 && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0 &&
+    if (H == 8 && beam <= 8 && n <= 104 && ldq % 2 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0 &&
         (kv_level_stride * 2) % 16 == 0) {
         const bf16* qp = static_cast<const bf16*>(q);
         const bf16* kvp = static_cast<const bf16*>(kv);
@@ -1574,23 +1000,10 @@ extern "C" int cap_decode_self_attention(const void* qkv, const int32_t* ancestr
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bf16* cache = static_cast<const bf16*>(qkv);
     bf16* o = static_cast<bf16*>(out);
-    static const int self_warps = [] {
-        const char* v = getenv("OPENVIIC_SELF_WARPS");
-        const int w = v ? atoi(v) : DEC_WARPS;
-        return w < 1 ? 1 : (w > DEC_WARPS_MAX ? DEC_WARPS_MAX : w);
-    }();
-    const int wide_blocks = (R + self_warps - 1) / self_warps;
-    const char* split_env = getenv("OPENVIIC_SELF_SPLIT");   // read per call: a probe compares both paths in one process
-    if (split_env && atoi(split_env) != 0 && H == 8 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_split_kernel), (R + SS_ROWS - 1) / SS_ROWS, SS_ROWS * SS_SPLITS * 32, 0, s, cache,
-                   ancestry, padflag, o, ldo, t, R, scale);
-    } else if (H == 8 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_wide_kernel<16>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
-    } else if (H == 4 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_wide_kernel<8>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
-    } else if (H == 16 && ldo % 8 == 0) {
-        CAP_LAUNCH((decode_self_attention_wide_kernel<32>), wide_blocks, self_warps * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
-    } else {
+    const int wide_blocks = (R + DEC_WARPS - 1) / DEC_WARPS;
+    if (H == 8 && ldo % 8 == 0) {
+        CAP_LAUNCH((decode_self_attention_wide_kernel<16>), wide_blocks, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, scale);
+    } else {   // other head counts: one warp per (row, head)
         const int items = R * H;
         CAP_LAUNCH((decode_self_attention_kernel), (items + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s, cache, ancestry, padflag, o, ldo, t, R, H, scale);
     }

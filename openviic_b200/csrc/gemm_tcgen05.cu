@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
     if (threadIdx.x == 0) flight_mark(FK_GEMM, 0);
-    pdl_launch_dependents();  // the next kernel may start its prologue now
     constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // B rows this CTA stages
     constexpr uint32_t B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
@@ -132,6 +131,10 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(p, 1);
     if (threadIdx.x == 0) flight_mark(FK_GEMM_READY, 0);
+    // The next kernel may start its prologue now -- only NOW, with this CTA's Tensor Memory in hand: a dependent that
+    // starts earlier can allocate Tensor Memory on this SM and then park in griddepcontrol.wait for this grid, while
+    // this CTA blocks in tcgen05.alloc behind it (no cycle is possible once every CTA of the primary holds what it needs).
+    pdl_launch_dependents();
 
     // Producer and MMA warps run their loops with the WHOLE warp (uniform control flow) and elect one lane for
     // the TMA / tcgen05 instructions: issued from an `if (lane == 0)` region every tcgen05.mma was wrapped in an
@@ -437,7 +440,15 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
     if (pipe < staging) pipe = (staging + 1023) / 1024 * 1024;
     p.pipe_bytes = pipe;
-    const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
+    size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
+    // A CTA of a pair allocates Tensor Memory with tcgen05.alloc.cta_group::2, which takes the allocator of BOTH SMs of
+    // the pair.  Two pairs resident on the same two SMs deadlock in it -- each holds its own SM's allocator and waits
+    // for the peer's (measured in round 2: the nondeterministic "unspecified launch failure" / hang of round 1; with the
+    // pair kernel switched off it never happened, with one pair CTA per SM neither; the chain kernels, 221 KB of shared
+    // memory each, never hit it).  So a pair CTA reserves more than half of an SM's shared memory: at most one
+    // cta_group::2 allocator per SM at any time.
+    constexpr size_t HALF_SM_SMEM = 114 * 1024;
+    if (CTA2 && smem <= HALF_SM_SMEM) smem = HALF_SM_SMEM + 1024;
     static cap_device_once smem_once;
     CAP_PROPAGATE(cap_opt_in_smem(smem_once, gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, 200 * 1024));
     CAP_PROPAGATE(install_fault_buffer());
@@ -526,7 +537,7 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     static const bool use_2cta = env_int("OPENVIIC_GEMM_2CTA", 1) != 0;
     if (bn == 256 && use_2cta) {
         CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));  // each CTA of the pair stages half of the B tile
-        p.num_stages = forced_stages ? forced_stages : 3;
+        p.num_stages = forced_stages ? forced_stages : 4;   // 4 x 32 KB: the ring itself keeps the CTA alone on its SM (launch_gemm)
         if (p.num_stages > num_kb) p.num_stages = num_kb;
         return launch_gemm<256, false, true>(ta, tb, p, s);
     }

@@ -3,8 +3,9 @@ shapes (masks, ragged batches, beams 1..5, n up to 104) and launch time at the b
 
     python tests/gpu_scripts/probe_cross_stream.py
 
-OPENVIIC_CROSS_TC: 0 CUDA-core kernel, 1 tensor path (one CTA per image), 2 streamed tensor path (default).
-OPENVIIC_XATTN_IMAGES / OPENVIIC_XATTN_STAGES are read once per process: sweep them from the shell.
+OPENVIIC_XATTN_IMAGES / OPENVIIC_XATTN_STAGES (images per CTA, ring stages) are read once per process: sweep them from
+the shell.  (Round 2 measured the two kernels this one replaced at the bench shape: CUDA-core arithmetic 23.3 us per
+launch, tensor path with one CTA per image 16.4 us, this one 16.5 us alone and the same throughput in the pipeline.)
 """
 import ctypes as C
 import os
@@ -26,8 +27,7 @@ def reference(q, kv, mask, beam, H):
     return torch.einsum("rhn,rhnd->rhd", torch.softmax(s, -1), v).reshape(R, hd)
 
 
-def run(q, kv, mask, beam, H, mode):
-    os.environ["OPENVIIC_CROSS_TC"] = str(mode)
+def run(q, kv, mask, beam, H):
     B, n, _ = kv.shape
     out = torch.full_like(q, float("nan"))
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -40,7 +40,7 @@ def main():
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(5)
     H, hd = 8, 512
-    worst = {0: 0.0, 1: 0.0, 2: 0.0}
+    worst = 0.0
     for B, beam, n in [(1, 5, 49), (7, 5, 49), (3, 5, 50), (5, 3, 37), (4, 1, 56), (6, 5, 57), (2, 4, 99), (9, 2, 104), (13, 5, 8),
                        (33, 5, 50), (256, 5, 49), (128, 5, 50)]:
         kv = torch.randn(B, n, 2 * hd, generator=g).to(torch.bfloat16).to(dev)
@@ -52,34 +52,31 @@ def main():
             mask[1, ::2] = 1
         mask = mask.to(dev)
         ref = reference(q, kv, mask.bool(), beam, H)
-        line = f"B={B} beam={beam} n={n}: max-abs err vs fp32"
-        for mode in (0, 1, 2):
-            out = run(q, kv, mask, beam, H, mode)
-            torch.cuda.synchronize()
-            err = (out.float() - ref).abs().max().item()
-            worst[mode] = max(worst[mode], err if err == err else 9.0)
-            line += f"  mode {mode}: {err:.4f}"
-        print(line)
-    print("worst per mode:", worst)
-    assert all(v < 2e-2 for v in worst.values()), worst
+        out = run(q, kv, mask, beam, H)
+        torch.cuda.synchronize()
+        err = (out.float() - ref).abs().max().item()
+        worst = max(worst, err if err == err else 9.0)
+        print(f"B={B} beam={beam} n={n}: max-abs err vs fp32 {err:.4f}")
+    print("worst:", worst)
+    assert worst < 2e-2, worst
     # launch time at the bench shape, inputs rotated so that K|V (25.7 MB per set) does not stay in L2
     for B, beam, n in [(256, 5, 49), (128, 5, 50)]:
         sets = [(torch.randn(B * beam, hd, generator=g).to(torch.bfloat16).to(dev),
                  torch.randn(B, n, 2 * hd, generator=g).to(torch.bfloat16).to(dev)) for _ in range(8)]
         mask = torch.zeros(B, n, dtype=torch.uint8, device=dev)
-        for mode in (0, 1, 2):
+        for _ in range(1):
             for q, kv in sets:
-                run(q, kv, mask, beam, H, mode)
+                run(q, kv, mask, beam, H)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for rep in range(25):
                 for q, kv in sets:
-                    run(q, kv, mask, beam, H, mode)
+                    run(q, kv, mask, beam, H)
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (25 * len(sets))
-            print(f"B={B} n={n} mode {mode}: {us:.2f} us per launch back to back, {B * n * 2048 / us / 1e3:.0f} GB/s of K|V "
+            print(f"B={B} n={n}: {us:.2f} us per launch back to back, {B * n * 2048 / us / 1e3:.0f} GB/s of K|V "
                   f"(images/CTA {os.environ.get('OPENVIIC_XATTN_IMAGES', 'default')}, stages {os.environ.get('OPENVIIC_XATTN_STAGES', 'default')})")
 
 
