@@ -271,6 +271,46 @@ int cap_fused_get_full_logits(cap_fused_decoder* f);
 int cap_debug_fused_trace(unsigned long long* device_buffer);
 
 /* ------------------------------------------------------------------------------------------
+ * Encoder chains (csrc/decode_fused.cu): the vision embedding and the encoder layers (vision_embeddings.py:15-20,
+ * encoders.py:17-40) on the chain kernel -- stage 0 = vision projection + LayerNorm + position table and layer 0's
+ * q|k|v; stage 1 + l = layer l's fc_o + LN, fc1, fc2 + LN (padded rows zeroed, level output stored) and layer l + 1's
+ * q|k|v or the decoder's cross-attention K|V projections of the level outputs it attends to; the encoder's
+ * self-attention kernel (cap_attention on qkv_out -> att_in) runs between the stages.  d_model 512, d_ff 2048.
+ * ------------------------------------------------------------------------------------------ */
+#define CAP_ENC_MAX_KV 18
+typedef struct cap_enc_layer {
+    const void *w_qkv, *w_o, *w_fc1, *w_fc2;               /* bf16 [out,in] */
+    const float *b_qkv, *b_o, *ln1_g, *ln1_b, *b_fc1, *b_fc2, *ln2_g, *ln2_b;
+} cap_enc_layer;
+typedef struct cap_enc_chain_weights cap_enc_chain_weights;
+typedef struct cap_enc_chain_desc {
+    int d_model, d_ff, d_feature, n_layers;
+    int max_rows;                  /* max_batch * n_tokens */
+    const cap_enc_layer* layers;
+    const void* w_vis;             /* bf16 [d_model, d_feature]  vision_embedding.proj */
+    const float *b_vis, *ln0_g, *ln0_b;   /* its bias; encoder.layer_norm */
+    const float* pos;              /* fp32 [n_tokens, d_model] position table (row % n_tokens) */
+    int n_kv;                      /* cross K|V projections computed while their source level is resident */
+    const void* w_kv[CAP_ENC_MAX_KV];     /* bf16 [2*d_model, d_model] (fc_k | fc_v of a decoder layer's enc_attn) */
+    const float* b_kv[CAP_ENC_MAX_KV];
+    int kv_level[CAP_ENC_MAX_KV];         /* encoder layer whose output is projected */
+    void* kv_dst[CAP_ENC_MAX_KV];         /* bf16 [rows, 2*d_model] */
+    const void* feats;             /* bf16 [max_rows, d_feature] */
+    void* qkv_out;                 /* bf16 [max_rows, 3*d_model] */
+    const void* att_in;            /* bf16 [max_rows, d_model] */
+    void* levels_out;              /* bf16 [n_layers][level_stride]: every layer's output, row-major */
+    size_t level_stride;           /* elements */
+    const uint8_t* row_mask;       /* uint8 [max_rows]: 1 = padded visual token */
+    const cap_enc_chain_weights* stacked;   /* NULL: the handle builds and owns its stacked weight copies */
+} cap_enc_chain_desc;
+int cap_enc_chain_weights_create(const cap_enc_chain_desc* desc, cap_enc_chain_weights** out);
+int cap_enc_chain_weights_destroy(cap_enc_chain_weights* w);
+typedef struct cap_enc_chains cap_enc_chains;
+int cap_enc_chains_create(const cap_enc_chain_desc* desc, cap_enc_chains** out);
+int cap_enc_chains_destroy(cap_enc_chains* f);
+int cap_enc_chain(cap_enc_chains* f, int stage, int rows, int n_tokens, cap_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Whole-path engine: encoder_forward once + max_len decode steps (models/base_transformer.py:
  * 30-53), one handle per GPU / rank.
  * ------------------------------------------------------------------------------------------ */

@@ -87,6 +87,11 @@ SIGNATURES = {
     "cap_fused_set_full_logits": (_i, [_vp, _i]),
     "cap_fused_get_full_logits": (_i, [_vp]),
     "cap_fused_chain": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "cap_enc_chain_weights_create": (_i, [_vp, C.POINTER(_vp)]),
+    "cap_enc_chain_weights_destroy": (_i, [_vp]),
+    "cap_enc_chains_create": (_i, [_vp, C.POINTER(_vp)]),
+    "cap_enc_chains_destroy": (_i, [_vp]),
+    "cap_enc_chain": (_i, [_vp, _i, _i, _i, _vp]),
     "cap_linear_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cap_engine_create": (_i, [C.POINTER(ModelDesc), C.POINTER(_vp)]),
     "cap_engine_destroy": (_i, [_vp]),

@@ -765,8 +765,12 @@ encoder_self_attention_tc_kernel(const bf16* __restrict__ qkv, const uint8_t* __
                      : "memory");
     }
     for (int i = threadIdx.x; i < ET_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zero_row)[i] = 0u;
+    // Nothing a stream predecessor wrote may be read before this wait -- not even the key mask, which a kernel several
+    // launches back produced: with every kernel triggering its dependents at entry, a whole run of kernels can be
+    // resident before the first of them has finished (this read used to sit above the wait; two batches with different
+    // masks back to back then gave run-to-run differences).
+    pdl_wait();
     for (int j = threadIdx.x; j < NT * 8; j += blockDim.x) smask[j] = (j >= n || (key_mask && key_mask[static_cast<size_t>(b) * n + j])) ? 1 : 0;
-    pdl_wait();        // q|k|v come from the projection kernel right before this one
     __syncthreads();   // barrier armed before any copy can complete on it; zero row and mask visible
     if (threadIdx.x < n) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) + (static_cast<size_t>(b) * n + threadIdx.x) * 3072;

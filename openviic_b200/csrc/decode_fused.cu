@@ -96,14 +96,20 @@ enum JobEpi : int {
     JE_ALPHA = 4    // N = 512: sigmoid(acc + bias + aux[level]) * c (res_in) accumulated into the mix stream (res_out);
                     //          last level: scaled by 1/sqrt(levels) -> resident A tile + residual stream
 };
-enum JobASrc : int { JA_RESIDENT = 0, JA_TMA_TILE = 1, JA_STREAM_HIDDEN = 2 };
+enum JobASrc : int {
+    JA_RESIDENT = 0,         // the resident tile, written by the previous epilogue or the embedding
+    JA_TMA_TILE = 1,         // a tile of attention output arrives by TMA (att_in)
+    JA_STREAM_HIDDEN = 2,    // K = 2048: the FFN hidden tile streamed back from its scratch buffer
+    JA_STREAM_FEATURES = 3   // K = d_feature: the raw visual features streamed from global memory (encoder's first GEMM)
+};
 enum JobFlags : int {
     JF_RELU = 1, JF_WHOLE_TILES = 2, JF_HIDDEN_DONE = 4, JF_LAST_LEVEL = 8, JF_FIRST_LEVEL = 16,
-    JF_WAIT_A = 32   // the resident A tile is (re)written just before this job: the issuer waits for the workers' publish
+    JF_WAIT_A = 32,  // the resident A tile is (re)written just before this job: the issuer waits for the workers' publish
+    JF_NO_RESIDUAL = 64   // JE_LN: LayerNorm of the projection alone (vision embedding, encoders.py:36)
 };
 
 struct JobDesc {
-    int wmap;        // weight tensor map: 0 K = 512 stack, 1 fc2 stack (K = 2048), 2 vocabulary
+    int wmap;        // weight tensor map: 0 K = 512 stack, 1 fc2 stack (K = 2048), 2 vocabulary, 3 vision projection (K = d_feature)
     int row0;        // first weight row of the job inside that stack
     int ntiles;      // 128-row weight tiles (N / 128)
     int kblocks;     // K / 64
@@ -121,7 +127,9 @@ struct JobDesc {
     bf16* dst;               // JE_STORE
     const float* res_in;     // JE_LN residual / JE_ALPHA c stream   (granule layout, per tile)
     float* res_out;          // JE_LN output stream / JE_ALPHA mix or final stream
-    const uint8_t* zero_rows;  // JE_LN: rows to zero (fed <pad>), or nullptr
+    const uint8_t* zero_rows;  // JE_LN: rows to zero (fed <pad> / padded visual tokens), or nullptr
+    const float* pos;          // JE_LN: position table [pos_rows][512] added after the LayerNorm (row % pos_rows), or nullptr
+    bf16* ln_out;              // JE_LN: row-major bf16 copy of the result [R][512] (encoder level outputs), or nullptr
 };
 
 struct FusedParams {
@@ -131,6 +139,9 @@ struct FusedParams {
     CUtensorMap map_h;      // [tiles * 128][2048] FFN hidden scratch
     CUtensorMap map_att;    // [levels * max_rows][512] attention outputs of the stand-alone attention kernels
     CUtensorMap map_w512_h, map_w2_h, map_vocab_h;   // the three weight maps with 64-row boxes (CTA pairs)
+    CUtensorMap map_wvis, map_wvis_h;   // encoder: vision projection [512][d_feature]
+    CUtensorMap map_feat;    // encoder: raw features [rows][d_feature], the streamed A operand of the vision projection
+    int pos_rows;            // encoder: visual tokens per image (rows of the position table)
     JobDesc jobs[MAX_JOBS];
     int n_jobs;
     int start_embed;         // the chain starts with x = Emb[token] + pos (its first job reads the resident tile)
@@ -342,6 +353,7 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     const int grow = c.r0 + row;
     const bool live = grow < p.R;
     const size_t tile_off = static_cast<size_t>(c.tile) * (FD / 4) * TILE_ROWS + row;
+    const bool has_res = (job.flags & JF_NO_RESIDUAL) == 0;
     const float4* res_in = reinterpret_cast<const float4*>(job.res_in) + tile_off;
     float4* res_out = reinterpret_cast<float4*>(job.res_out) + tile_off;
     const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
@@ -353,7 +365,8 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
         tmem_ld_32x32b_x32(taddr + c0, v);
         float4 r[8];   // requested while the TMEM load is in flight
 #pragma unroll
-        for (int g = 0; g < 8; ++g) r[g] = res_in[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
+        for (int g = 0; g < 8; ++g)
+            r[g] = has_res ? res_in[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] : make_float4(0.f, 0.f, 0.f, 0.f);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -378,6 +391,9 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     const float var = fmaxf(S2 * (1.f / FD) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
     const bool zero = !live || (job.zero_rows != nullptr && job.zero_rows[grow] != 0);
+    // encoder extras: + pos[row % tokens] after the LayerNorm (encoders.py:36), and a row-major bf16 copy of the result
+    const float4* pos = job.pos != nullptr ? reinterpret_cast<const float4*>(job.pos + static_cast<size_t>(live ? grow % p.pos_rows : 0) * FD) : nullptr;
+    uint4* ln_out = (job.ln_out != nullptr && live) ? reinterpret_cast<uint4*>(job.ln_out + static_cast<size_t>(grow) * FD) : nullptr;
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
         const int c0 = (c.half * 8 + i) * 32;
@@ -388,12 +404,22 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             f[j] = zero ? 0.f : (__uint_as_float(v[j]) - mean) * rstd * c.s_gamma[c0 + j] + c.s_beta[c0 + j];
+        if (pos != nullptr && !zero) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 pp = __ldg(pos + c0 / 4 + g);
+                f[4 * g] += pp.x; f[4 * g + 1] += pp.y; f[4 * g + 2] += pp.z; f[4 * g + 3] += pp.w;
+            }
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g)
             res_out[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = pack8_u4(f + 8 * g);
+        for (int g = 0; g < 4; ++g) {
+            const uint4 packed = pack8_u4(f + 8 * g);
+            *reinterpret_cast<uint4*>(c.A_buf + a_tile_off(row, c0 / 8 + g)) = packed;
+            if (ln_out != nullptr) ln_out[c0 / 8 + g] = packed;
+        }
     }
     release_acc(c, 4, 0);
     publish_a(c);
@@ -685,11 +711,14 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
             const JobDesc& job = p.jobs[ji];
             const CUtensorMap* map = job.wmap == 0 ? (PAIR ? &p.map_w512_h : &p.map_w512)
                                    : job.wmap == 1 ? (PAIR ? &p.map_w2_h : &p.map_w2)
-                                                   : (PAIR ? &p.map_vocab_h : &p.map_vocab);
+                                   : job.wmap == 2 ? (PAIR ? &p.map_vocab_h : &p.map_vocab)
+                                                   : (PAIR ? &p.map_wvis_h : &p.map_wvis);
             const int chunk = job.chunk, kblocks = job.kblocks;   // read once (see epilogue_store)
             const int nch = job.ntiles / chunk;
             const int row_base = job.row0 + (PAIR ? static_cast<int>(rank) * 64 : 0);
-            const bool stream = job.a_src == JA_STREAM_HIDDEN;
+            const bool stream = job.a_src == JA_STREAM_HIDDEN || job.a_src == JA_STREAM_FEATURES;
+            const bool from_hidden = job.a_src == JA_STREAM_HIDDEN;
+            const CUtensorMap* amap = from_hidden ? &p.map_h : &p.map_feat;
             for (int c = 0; c < nch; ++c) {
                 for (int kb = 0; kb < kblocks; ++kb) {
                     for (int j = 0; j < chunk; ++j) {
@@ -711,7 +740,7 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
                         ++bcount;
                     }
                     if (stream) {
-                        if (kb == 0) {  // the workers have written (and proxy-fenced) the whole hidden tile
+                        if (kb == 0 && from_hidden) {  // the workers have written (and proxy-fenced) the whole hidden tile
                             TRACED_WAIT(tr_a, mbar_wait(h_ready, hphase));
                             hphase ^= 1;
                         }
@@ -720,10 +749,10 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
                         if (elect_one_sync()) {
                             if constexpr (PAIR) {
                                 if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * A_KB_BYTES);
-                                tma_load_2d_2sm(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
+                                tma_load_2d_2sm(A_buf + slot * A_KB_BYTES, amap, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
                             } else {
                                 mbar_arrive_expect_tx(&a_full[slot], A_KB_BYTES);
-                                tma_load_2d(A_buf + slot * A_KB_BYTES, &p.map_h, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
+                                tma_load_2d(A_buf + slot * A_KB_BYTES, amap, &a_full[slot], kb * BLOCK_K, tile * TILE_ROWS);
                             }
                         }
                         __syncwarp();
@@ -759,7 +788,7 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
             const JobDesc& job = p.jobs[ji];
             const int chunk = job.chunk, kblocks = job.kblocks;   // read once (see epilogue_store)
             const int nch = job.ntiles / chunk;
-            const bool stream = job.a_src == JA_STREAM_HIDDEN;
+            const bool stream = job.a_src == JA_STREAM_HIDDEN || job.a_src == JA_STREAM_FEATURES;
             if (job.a_src == JA_TMA_TILE) {
                 TRACED_WAIT(tr_a, mbar_wait(a_load, al & 1));   // this job's A tile arrives by TMA (warp 2)
                 ++al;
@@ -951,6 +980,9 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
     }
 }
 
+int launch_chain(FusedParams& p, int tiles, bool use_pairs, cudaStream_t stream);
+int set_chain_smem_attributes();
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1131,11 +1163,8 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     f->has_att = true;
     f->full_logits = getenv("OPENVIIC_FULL_LOGITS") && atoi(getenv("OPENVIIC_FULL_LOGITS")) != 0;
     f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
-    if (cudaFuncSetAttribute(decode_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
-        return fail(cap_set_error(CAP_ERR_CUDA, "cap_fused_create: cannot reserve %u bytes of shared memory", FUSED_SMEM));
+    rc = set_chain_smem_attributes();
+    if (rc != CAP_OK) return fail(rc);
     *out = f;
     return CAP_OK;
 }
@@ -1167,6 +1196,20 @@ extern "C" int cap_debug_fused_trace(unsigned long long* device_buffer) {
 }
 
 namespace {
+int set_chain_smem_attributes() {
+    static cap_device_once once;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&once.done, __ATOMIC_ACQUIRE) & bit) return CAP_OK;
+    if (cudaFuncSetAttribute(decode_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM) != cudaSuccess)
+        return cap_set_error(CAP_ERR_CUDA, "chain kernels: cannot reserve %u bytes of shared memory", FUSED_SMEM);
+    __atomic_fetch_or(&once.done, bit, __ATOMIC_RELEASE);
+    return CAP_OK;
+}
 // ---- job lists ------------------------------------------------------------------------------------------------
 struct JobList {
     FusedParams& p;
@@ -1226,7 +1269,6 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
     p.sparse_logits = (f->full_logits || p.beam > 5) ? 0 : 1;
     // debug (cap_debug_fused_trace): one region of 64 tiles x 64 words per (chain kind, layer), else nullptr
     p.trace = g_fused_trace ? g_fused_trace + static_cast<size_t>(chain * MAX_FUSED_LAYERS + layer) * 64 * 64 : nullptr;
-    CAP_REQUIRE(p.trace == nullptr || tiles <= 64, "cap_fused_chain: the trace buffer holds 64 tiles");
     p.start_embed = 0;
     p.n_jobs = 0;
     JobList jl{p, *f, layer};
@@ -1258,25 +1300,31 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         }
         jl.ffn_and_next();
     }
-    CAP_REQUIRE(p.n_jobs <= MAX_JOBS, "cap_fused_chain: job list overflow");
+    return launch_chain(p, tiles, f->use_pairs, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+// No programmatic dependent launch for a chain: its CTAs each take a whole SM, and an early-started chain
+// would hold them idle in griddepcontrol.wait until the attention kernel before it has drained.
+// CTA pairs (OPENVIIC_CHAIN_PAIR=0: single CTAs): clusters of two adjacent tiles, the second CTA of the last
+// pair is a dummy when the tile count is odd (every access of it is guarded by the row count).
+int launch_chain(FusedParams& p, int tiles, bool use_pairs, cudaStream_t stream) {
+    CAP_REQUIRE(p.n_jobs >= 1 && p.n_jobs <= MAX_JOBS, "chain: job list overflow");
     for (int ji = 0; ji < p.n_jobs; ++ji) {   // which jobs start from a freshly written resident tile
         JobDesc& j = p.jobs[ji];
         if (j.a_src != JA_RESIDENT) continue;
         const bool fresh = ji == 0 ? p.start_embed != 0
                                    : (p.jobs[ji - 1].epi == JE_LN || (p.jobs[ji - 1].epi == JE_ALPHA && (p.jobs[ji - 1].flags & JF_LAST_LEVEL)));
         if (fresh) j.flags |= JF_WAIT_A;
-        CAP_REQUIRE(ji > 0 || p.start_embed, "cap_fused_chain: the first job has no A tile");
+        CAP_REQUIRE(ji > 0 || p.start_embed, "chain: the first job has no A tile");
     }
-    // No programmatic dependent launch for a chain: its CTAs each take a whole SM, and an early-started chain
-    // would hold them idle in griddepcontrol.wait until the attention kernel before it has drained.
-    // CTA pairs (OPENVIIC_CHAIN_PAIR=0: single CTAs): clusters of two adjacent tiles, the second CTA of the last
-    // pair is a dummy when the tile count is odd (every access of it is guarded by the row count).
-    if (f->use_pairs) {
+    CAP_REQUIRE(p.trace == nullptr || tiles <= 64, "chain: the trace buffer holds 64 tiles");
+    if (use_pairs) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((tiles + 1) / 2 * 2);
         cfg.blockDim = dim3(CHAIN_THREADS);
         cfg.dynamicSmemBytes = FUSED_SMEM;
-        cfg.stream = static_cast<cudaStream_t>(stream);
+        cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
@@ -1287,10 +1335,206 @@ extern "C" int cap_fused_chain(cap_fused_decoder* f, int chain, int layer, int t
         if (p.trace != nullptr) cudaLaunchKernelEx(&cfg, decode_chain_kernel<true, true>, p);
         else cudaLaunchKernelEx(&cfg, decode_chain_kernel<true>, p);
     } else if (p.trace != nullptr) {
-        decode_chain_kernel<false, true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+        decode_chain_kernel<false, true><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, stream>>>(p);
     } else {
-        decode_chain_kernel<false><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+        decode_chain_kernel<false><<<dim3(tiles), dim3(CHAIN_THREADS), FUSED_SMEM, stream>>>(p);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("decode_chain_kernel");
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ encoder chains
+// The encoder (encoders.py:17-40, vision_embeddings.py:15-20) on the same chain kernel: a tile of 128 visual-token rows
+// is carried through
+//   stage 0     : vision projection (K = d_feature, the raw features streamed as the A operand) + LayerNorm + position
+//                 table, then layer 0's q|k|v projection;
+//   stage 1 + l : layer l's fc_o + residual + LayerNorm, fc1, fc2 + residual + LayerNorm (padded rows zeroed, the level
+//                 output also stored row-major), then layer l + 1's q|k|v -- or, from the level outputs the decoder
+//                 attends to, the decoder layers' cross-attention K|V projections;
+// with the encoder's self-attention kernel (attention.cu) between the stages: 1 + layers chain launches instead of
+// ~7 GEMM launches per layer, and no activation except q|k|v, the hidden tile and the final K|V leaves the SM.
+struct cap_enc_chain_weights {
+    void* w512 = nullptr;   // per layer: q|k|v 1536, fc_o 512, fc1 2048 rows; then n_kv x 1024 rows of cross K|V projections
+    void* w2 = nullptr;     // [layers * 512][2048]
+    int n_layers = 0, n_kv = 0;
+};
+
+extern "C" int cap_enc_chain_weights_destroy(cap_enc_chain_weights* w) {
+    if (!w) return CAP_OK;
+    cudaFree(w->w512);
+    cudaFree(w->w2);
+    delete w;
+    return CAP_OK;
+}
+
+namespace {
+constexpr int ENC_ROWS_PER_LAYER = 3 * FD + FD + FDFF;   // q|k|v, fc_o, fc1
+constexpr int MAX_ENC_LAYERS = 6;
+}  // namespace
+
+extern "C" int cap_enc_chain_weights_create(const cap_enc_chain_desc* d, cap_enc_chain_weights** out) {
+    CAP_REQUIRE(d && out && d->layers, "cap_enc_chain_weights_create: null pointer");
+    CAP_REQUIRE(d->n_layers >= 1 && d->n_layers <= MAX_ENC_LAYERS && d->n_kv >= 0 && d->n_kv <= CAP_ENC_MAX_KV,
+                "cap_enc_chain_weights_create: bad layer / projection count");
+    cap_enc_chain_weights* f = new cap_enc_chain_weights();
+    f->n_layers = d->n_layers;
+    f->n_kv = d->n_kv;
+    auto fail = [&](int rc) { cap_enc_chain_weights_destroy(f); return rc; };
+    const size_t rows512 = static_cast<size_t>(d->n_layers) * ENC_ROWS_PER_LAYER + static_cast<size_t>(d->n_kv) * 2 * FD;
+    if (cudaMalloc(&f->w512, rows512 * FD * 2) != cudaSuccess ||
+        cudaMalloc(&f->w2, static_cast<size_t>(d->n_layers) * FD * FDFF * 2) != cudaSuccess)
+        return fail(cap_set_error(CAP_ERR_CUDA, "cap_enc_chain_weights_create: cudaMalloc of the stacked weights failed"));
+    auto copy = [&](bf16* dst, const void* src, size_t rows, size_t cols) {
+        return src != nullptr && cudaMemcpy(dst, src, rows * cols * 2, cudaMemcpyDeviceToDevice) == cudaSuccess;
+    };
+    bf16* w512 = static_cast<bf16*>(f->w512);
+    for (int l = 0; l < d->n_layers; ++l) {
+        const cap_enc_layer& w = d->layers[l];
+        bf16* base = w512 + static_cast<size_t>(l) * ENC_ROWS_PER_LAYER * FD;
+        if (!copy(base, w.w_qkv, 3 * FD, FD) || !copy(base + static_cast<size_t>(3 * FD) * FD, w.w_o, FD, FD) ||
+            !copy(base + static_cast<size_t>(4 * FD) * FD, w.w_fc1, FDFF, FD) ||
+            !copy(static_cast<bf16*>(f->w2) + static_cast<size_t>(l) * FD * FDFF, w.w_fc2, FD, FDFF))
+            return fail(cap_set_error(CAP_ERR_INVALID, "cap_enc_chain_weights_create: null weight or copy failed (layer %d)", l));
+    }
+    for (int i = 0; i < d->n_kv; ++i)
+        if (!copy(w512 + (static_cast<size_t>(d->n_layers) * ENC_ROWS_PER_LAYER + static_cast<size_t>(i) * 2 * FD) * FD, d->w_kv[i], 2 * FD, FD))
+            return fail(cap_set_error(CAP_ERR_INVALID, "cap_enc_chain_weights_create: null K|V weight or copy failed (%d)", i));
+    *out = f;
+    return CAP_OK;
+}
+
+struct cap_enc_chains {
+    FusedParams base;
+    cap_enc_chain_desc desc;
+    cap_enc_layer layers[MAX_ENC_LAYERS];
+    cap_enc_chain_weights* stacked = nullptr;
+    bool owns_stacked = false;
+    int tiles = 0;
+    bool use_pairs = true;
+};
+
+extern "C" int cap_enc_chains_destroy(cap_enc_chains* f) {
+    if (!f) return CAP_OK;
+    if (f->owns_stacked) cap_enc_chain_weights_destroy(f->stacked);
+    cudaFree(f->base.res);
+    cudaFree(f->base.hbuf);
+    delete f;
+    return CAP_OK;
+}
+
+extern "C" int cap_enc_chains_create(const cap_enc_chain_desc* d, cap_enc_chains** out) {
+    CAP_REQUIRE(d && out && d->layers, "cap_enc_chains_create: null pointer");
+    CAP_REQUIRE(d->d_model == FD && d->d_ff == FDFF, "cap_enc_chains_create: needs d_model 512, d_ff 2048");
+    CAP_REQUIRE(d->d_feature >= BLOCK_K && d->d_feature % BLOCK_K == 0, "cap_enc_chains_create: d_feature must be a multiple of %d", BLOCK_K);
+    CAP_REQUIRE(d->n_layers >= 1 && d->n_layers <= MAX_ENC_LAYERS && d->n_kv >= 0 && d->n_kv <= CAP_ENC_MAX_KV, "cap_enc_chains_create: bad counts");
+    CAP_REQUIRE(d->max_rows > 0 && d->w_vis && d->b_vis && d->ln0_g && d->ln0_b && d->pos && d->feats && d->qkv_out && d->att_in && d->levels_out,
+                "cap_enc_chains_create: null tensor");
+    CAP_REQUIRE(d->stacked == nullptr || (d->stacked->n_layers == d->n_layers && d->stacked->n_kv == d->n_kv),
+                "cap_enc_chains_create: stacked weights of another model");
+    CAP_PROPAGATE(install_fault_buffer());
+    cap_install_flight();
+    cap_enc_chains* f = new cap_enc_chains();
+    FusedParams& p = f->base;
+    memset(&p, 0, sizeof(p));
+    f->desc = *d;
+    for (int l = 0; l < d->n_layers; ++l) f->layers[l] = d->layers[l];
+    f->desc.layers = f->layers;
+    f->tiles = ((d->max_rows + TILE_ROWS - 1) / TILE_ROWS + 1) / 2 * 2;
+    auto fail = [&](int rc) { cap_enc_chains_destroy(f); return rc; };
+    if (d->stacked) {
+        f->stacked = const_cast<cap_enc_chain_weights*>(d->stacked);
+    } else {
+        const int rc0 = cap_enc_chain_weights_create(d, &f->stacked);
+        if (rc0 != CAP_OK) return fail(rc0);
+        f->owns_stacked = true;
+    }
+    const int rows512 = d->n_layers * ENC_ROWS_PER_LAYER + d->n_kv * 2 * FD;
+    int rc = cap_gemm::make_tmap(&p.map_w512, f->stacked->w512, rows512, FD, FD, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, f->stacked->w512, rows512, FD, FD, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, f->stacked->w2, d->n_layers * FD, FDFF, FDFF, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, f->stacked->w2, d->n_layers * FD, FDFF, FDFF, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_wvis, d->w_vis, FD, d->d_feature, d->d_feature, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_wvis_h, d->w_vis, FD, d->d_feature, d->d_feature, 64);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_feat, d->feats, d->max_rows, d->d_feature, d->d_feature, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_att, d->att_in, d->max_rows, FD, FD, 128);
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, f->stacked->w512, rows512, FD, FD, 128);     // unused by encoder jobs: any valid map
+    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab_h, f->stacked->w512, rows512, FD, FD, 64);
+    if (rc != CAP_OK) return fail(rc);
+    const size_t tiles = f->tiles;
+    void *res = nullptr, *hb = nullptr;
+    if (cudaMalloc(&res, tiles * TILE_ROWS * FD * 4) != cudaSuccess || cudaMalloc(&hb, tiles * TILE_ROWS * FDFF * 2) != cudaSuccess) {
+        cudaFree(res);
+        return fail(cap_set_error(CAP_ERR_CUDA, "cap_enc_chains_create: cudaMalloc of the scratch tiles failed"));
+    }
+    p.res = static_cast<float*>(res);
+    p.hbuf = static_cast<bf16*>(hb);
+    cudaMemset(res, 0, tiles * TILE_ROWS * FD * 4);
+    cudaMemset(hb, 0, tiles * TILE_ROWS * FDFF * 2);
+    rc = cap_gemm::make_tmap(&p.map_h, hb, static_cast<int>(tiles) * TILE_ROWS, FDFF, FDFF, 128);
+    if (rc != CAP_OK) return fail(rc);
+    p.level_scale = 1.f;
+    p.beam = 1;
+    f->use_pairs = !(getenv("OPENVIIC_CHAIN_PAIR") && atoi(getenv("OPENVIIC_CHAIN_PAIR")) == 0);
+    rc = set_chain_smem_attributes();
+    if (rc != CAP_OK) return fail(rc);
+    *out = f;
+    return CAP_OK;
+}
+
+// stage 0: vision projection + LayerNorm + positions, q|k|v of layer 0; stage 1 + l: the rest of layer l (see above)
+extern "C" int cap_enc_chain(cap_enc_chains* f, int stage, int rows, int n_tokens, cap_stream_t stream) {
+    CAP_REQUIRE(f != nullptr, "cap_enc_chain: null handle");
+    const cap_enc_chain_desc& d = f->desc;
+    CAP_REQUIRE(stage >= 0 && stage <= d.n_layers, "cap_enc_chain: stage %d outside [0,%d]", stage, d.n_layers);
+    CAP_REQUIRE(rows > 0 && rows <= d.max_rows && n_tokens > 0, "cap_enc_chain: %d rows exceed the reservation", rows);
+    FusedParams p = f->base;
+    const int tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    p.R = rows; p.B = rows; p.t = 0; p.T = 1;
+    p.pos_rows = n_tokens;
+    p.start_embed = 0;
+    p.n_jobs = 0;
+    p.trace = g_fused_trace ? g_fused_trace + static_cast<size_t>(stage % (3 * MAX_FUSED_LAYERS)) * 64 * 64 : nullptr;
+    auto add = [&]() -> JobDesc& {
+        JobDesc& j = p.jobs[p.n_jobs < MAX_JOBS ? p.n_jobs++ : MAX_JOBS - 1];
+        memset(&j, 0, sizeof(j));
+        j.kblocks = FD / BLOCK_K;
+        j.chunk = 2;
+        j.a_src = JA_RESIDENT;
+        return j;
+    };
+    auto qkv = [&](int layer) {
+        JobDesc& j = add();
+        j.row0 = layer * ENC_ROWS_PER_LAYER; j.ntiles = 12; j.epi = JE_STORE; j.bias = f->layers[layer].b_qkv;
+        j.dst = static_cast<bf16*>(d.qkv_out); j.ld_dst = 3 * FD;
+    };
+    if (stage == 0) {
+        JobDesc& v = add();   // x = LN(W_vis . features + b) + pos   (vision_embeddings.py:18, encoders.py:36)
+        v.wmap = 3; v.row0 = 0; v.ntiles = 4; v.chunk = 4; v.kblocks = d.d_feature / BLOCK_K; v.a_src = JA_STREAM_FEATURES;
+        v.epi = JE_LN; v.flags = JF_NO_RESIDUAL; v.bias = d.b_vis; v.gamma = d.ln0_g; v.beta = d.ln0_b; v.pos = d.pos;
+        v.res_in = p.res; v.res_out = p.res;
+        qkv(0);
+    } else {
+        const int l = stage - 1;
+        const cap_enc_layer& w = f->layers[l];
+        JobDesc& o = add();   // LN(x + fc_o(attention))   (attentions.py:308-309)
+        o.row0 = l * ENC_ROWS_PER_LAYER + 3 * FD; o.ntiles = 4; o.chunk = 4; o.a_src = JA_TMA_TILE; o.att_row0 = 0; o.epi = JE_LN;
+        o.bias = w.b_o; o.gamma = w.ln1_g; o.beta = w.ln1_b; o.res_in = p.res; o.res_out = p.res;
+        JobDesc& a = add();   // fc1 + ReLU -> hidden scratch
+        a.row0 = l * ENC_ROWS_PER_LAYER + 4 * FD; a.ntiles = 16; a.epi = JE_STORE; a.flags = JF_RELU | JF_WHOLE_TILES | JF_HIDDEN_DONE;
+        a.bias = w.b_fc1; a.dst = p.hbuf; a.ld_dst = FDFF;
+        JobDesc& b = add();   // LN(a + fc2(hidden)), padded rows zeroed (encoders.py:20), level output stored
+        b.wmap = 1; b.row0 = l * FD; b.ntiles = 4; b.chunk = 4; b.kblocks = FDFF / BLOCK_K; b.a_src = JA_STREAM_HIDDEN; b.epi = JE_LN;
+        b.bias = w.b_fc2; b.gamma = w.ln2_g; b.beta = w.ln2_b; b.res_in = p.res; b.res_out = p.res; b.zero_rows = d.row_mask;
+        b.ln_out = static_cast<bf16*>(d.levels_out) + static_cast<size_t>(l) * d.level_stride;
+        if (l + 1 < d.n_layers) qkv(l + 1);
+        for (int i = 0; i < d.n_kv; ++i) {   // the decoder's cross K|V from this level's output, while it is resident
+            if (d.kv_level[i] != l) continue;
+            JobDesc& k = add();
+            k.row0 = d.n_layers * ENC_ROWS_PER_LAYER + i * 2 * FD; k.ntiles = 8; k.epi = JE_STORE; k.bias = d.b_kv[i];
+            k.dst = static_cast<bf16*>(d.kv_dst[i]); k.ld_dst = 2 * FD;
+        }
+    }
+    CAP_REQUIRE(p.n_jobs < MAX_JOBS, "cap_enc_chain: job list overflow");
+    return launch_chain(p, tiles, f->use_pairs, static_cast<cudaStream_t>(stream));
 }

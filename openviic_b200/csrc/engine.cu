@@ -30,9 +30,11 @@ namespace {
 struct WeightOwner {
     std::vector<void*> allocations;
     cap_fused_weights* stacked = nullptr;   // stacked chain weights (decode_fused.cu), built by the first engine that reserves
+    cap_enc_chain_weights* enc_stacked = nullptr;   // the encoder's
     std::mutex lock;
     ~WeightOwner() {
         if (stacked) cap_fused_weights_destroy(stacked);
+        if (enc_stacked) cap_enc_chain_weights_destroy(enc_stacked);
         for (void* p : allocations) cudaFree(p);
     }
 };
@@ -130,6 +132,7 @@ struct cap_engine {
     cap_beam* beam_state = nullptr;
     bool fuse_ln = true;                 // Linear + residual + LayerNorm as one cluster kernel (OPENVIIC_LN_FUSED=0: two kernels)
     cap_fused_decoder* fused = nullptr;  // GEMM chains of the decode step (decode_fused.cu) when the model is covered
+    cap_enc_chains* enc_chains = nullptr;  // GEMM chains of the encoder, ditto
 
     // CUDA graph of a full beam search (begin + T steps + finalize)
     cudaGraphExec_t graph_exec = nullptr;
@@ -350,6 +353,7 @@ extern "C" int cap_engine_destroy(cap_engine* e) {
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->beam_state) cap_beam_destroy(e->beam_state);
     if (e->fused) cap_fused_destroy(e->fused);
+    if (e->enc_chains) cap_enc_chains_destroy(e->enc_chains);
     for (void* p : e->allocations) cudaFree(p);
     delete e;
     return CAP_OK;
@@ -533,6 +537,50 @@ extern "C" int cap_engine_reserve(cap_engine* e, int max_batch, int n_tokens, in
         }
         CAP_PROPAGATE(cap_fused_create(&fd, &e->fused));
     }
+    // Encoder as chains (decode_fused.cu): vision projection + LayerNorm + positions, then per layer fc_o + LN, FFN + LN
+    // and the next q|k|v / the decoder's cross K|V projections, the self-attention kernel between the stages.
+    // OPENVIIC_ENC_CHAINS=0: one kernel per operator (also the path of the attention-on-attention encoder).
+    {
+        const char* enc_env = getenv("OPENVIIC_ENC_CHAINS");
+        const bool want = !(enc_env && atoi(enc_env) == 0);
+        const int n_kv = m.dec_layers * lv;
+        if (want && !m.aoa_enc && d == 512 && hd == 512 && m.d_ff == 2048 && m.enc_layers <= 6 && m.d_feature % 64 == 0 &&
+            n_kv <= CAP_ENC_MAX_KV && rows_enc <= (1u << 30)) {
+            std::vector<cap_enc_layer> layers(m.enc_layers);
+            for (int l = 0; l < m.enc_layers; ++l) {
+                const EncoderLayerW& L = e->enc[l];
+                cap_enc_layer& f = layers[l];
+                f.w_qkv = L.att.qkv.w; f.b_qkv = L.att.qkv.b; f.w_o = L.att.o.w; f.b_o = L.att.o.b;
+                f.ln1_g = L.att.ln.g; f.ln1_b = L.att.ln.b;
+                f.w_fc1 = L.ffn.fc1.w; f.b_fc1 = L.ffn.fc1.b; f.w_fc2 = L.ffn.fc2.w; f.b_fc2 = L.ffn.fc2.b;
+                f.ln2_g = L.ffn.ln.g; f.ln2_b = L.ffn.ln.b;
+            }
+            cap_enc_chain_desc ed = {};
+            ed.d_model = d; ed.d_ff = m.d_ff; ed.d_feature = m.d_feature; ed.n_layers = m.enc_layers;
+            ed.max_rows = static_cast<int>(rows_enc);
+            ed.layers = layers.data();
+            ed.w_vis = e->vis_proj.w; ed.b_vis = e->vis_proj.b; ed.ln0_g = e->enc_ln.g; ed.ln0_b = e->enc_ln.b;
+            ed.pos = e->vis_pos;
+            ed.n_kv = n_kv;
+            for (int l = 0; l < m.dec_layers; ++l)
+                for (int i = 0; i < lv; ++i) {
+                    const int k = l * lv + i;
+                    ed.w_kv[k] = e->dec[l].cross_att.kv.w;
+                    ed.b_kv[k] = e->dec[l].cross_att.kv.b;
+                    ed.kv_level[k] = (m.decoder_kind == CAP_DEC_MESHED) ? i : m.enc_layers - 1;
+                    ed.kv_dst[k] = e->cross_kv + static_cast<size_t>(k) * rows_enc * 2 * hd;
+                }
+            ed.feats = e->feat_bf16; ed.qkv_out = e->buf_qkv; ed.att_in = e->buf_att;
+            ed.levels_out = e->enc_levels; ed.level_stride = rows_enc * d;
+            ed.row_mask = e->enc_mask;
+            {
+                std::lock_guard<std::mutex> guard(e->weights->lock);
+                if (!e->weights->enc_stacked) CAP_PROPAGATE(cap_enc_chain_weights_create(&ed, &e->weights->enc_stacked));
+                ed.stacked = e->weights->enc_stacked;
+            }
+            CAP_PROPAGATE(cap_enc_chains_create(&ed, &e->enc_chains));
+        }
+    }
     return CAP_OK;
 }
 
@@ -551,19 +599,12 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
     e->cur_batch = B;
     e->cur_n = n;
 
-    // V1: padding mask from the RAW features + cast; projection; E0: LN(x) + pos
+    // V1: padding mask from the RAW features + cast
     CAP_PROPAGATE(cap_feature_mask_cast(feats, feat_dtype, e->feat_bf16, e->enc_mask, rows, m.d_feature, s));
-    CAP_PROPAGATE(run_linear_ln(e, e->feat_bf16, m.d_feature, e->vis_proj, nullptr, e->enc_ln, e->vis_pos, n, nullptr,
-                                e->buf_x, e->res_x, rows, s));
     if (m.encoder_kind == CAP_ENC_GEOMETRIC)
         CAP_PROPAGATE(cap_geometry_bias(boxes, e->geo_w, e->geo_b, e->geometry, B, n, m.heads, e->d_g,
                                         m.trig_geometry, s));
-
-    const bf16* x = e->buf_x;
-    for (int l = 0; l < ((dbg_ablate() & 2) ? 0 : m.enc_layers); ++l) {
-        const EncoderLayerW& L = e->enc[l];
-        bf16* level_out = e->enc_levels + static_cast<size_t>(l) * rows_cap * d;
-        CAP_PROPAGATE(run_linear(x, d, L.att.qkv, e->buf_qkv, 3 * hd, CAP_BF16, CAP_ACT_NONE, rows, s));
+    auto self_attention = [&](const AttentionW& att) -> int {   // A1-A3 on the fused q|k|v rows of the current layer
         cap_attention_args a = {};
         a.q = e->buf_qkv;
         a.k = e->buf_qkv + hd;
@@ -578,13 +619,35 @@ extern "C" int cap_engine_encode(cap_engine* e, const void* feats, int feat_dtyp
         a.mask_qs = 0;
         a.geometry = m.enc_attention == CAP_ATT_GEOMETRY ? e->geometry : nullptr;
         if (m.enc_attention == CAP_ATT_MEMORY) {
-            a.mem_k = L.att.mem_k;
-            a.mem_v = L.att.mem_v;
+            a.mem_k = att.mem_k;
+            a.mem_v = att.mem_v;
             a.n_mem = m.n_memory;
         }
         a.B = B; a.H = m.heads; a.nq = n; a.nk = n;
         a.scale = 1.0f / std::sqrt(static_cast<float>(m.d_k));
-        CAP_PROPAGATE(cap_attention(&a, s));
+        return cap_attention(&a, s);
+    };
+    if (e->enc_chains && !(dbg_ablate() & 2)) {
+        // the encoder as chains: 1 + layers launches of the chain kernel with the self-attention kernel between them;
+        // the cross K|V projections ride on the stages whose level output they read
+        CAP_PROPAGATE(cap_enc_chain(e->enc_chains, 0, rows, n, s));
+        for (int l = 0; l < m.enc_layers; ++l) {
+            CAP_PROPAGATE(self_attention(e->enc[l].att));
+            CAP_PROPAGATE(cap_enc_chain(e->enc_chains, 1 + l, rows, n, s));
+        }
+        e->encoded = true;
+        return CAP_OK;
+    }
+    // one kernel per operator.  E0: LN(projection) + pos
+    CAP_PROPAGATE(run_linear_ln(e, e->feat_bf16, m.d_feature, e->vis_proj, nullptr, e->enc_ln, e->vis_pos, n, nullptr,
+                                e->buf_x, e->res_x, rows, s));
+
+    const bf16* x = e->buf_x;
+    for (int l = 0; l < ((dbg_ablate() & 2) ? 0 : m.enc_layers); ++l) {
+        const EncoderLayerW& L = e->enc[l];
+        bf16* level_out = e->enc_levels + static_cast<size_t>(l) * rows_cap * d;
+        CAP_PROPAGATE(run_linear(x, d, L.att.qkv, e->buf_qkv, 3 * hd, CAP_BF16, CAP_ACT_NONE, rows, s));
+        CAP_PROPAGATE(self_attention(L.att));
         CAP_PROPAGATE(run_linear_ln(e, e->buf_att, hd, L.att.o, e->res_x, L.att.ln, nullptr, 0, nullptr, e->buf_a, e->res_a,
                                     rows, s));
         if (m.aoa_enc) CAP_PROPAGATE(run_aoa(e, L.att, x, e->buf_a, e->buf_a, e->res_a, rows, s));

@@ -440,15 +440,17 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
     if (pipe < staging) pipe = (staging + 1023) / 1024 * 1024;
     p.pipe_bytes = pipe;
-    size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
-    // A CTA of a pair allocates Tensor Memory with tcgen05.alloc.cta_group::2, which takes the allocator of BOTH SMs of
-    // the pair.  Two pairs resident on the same two SMs deadlock in it -- each holds its own SM's allocator and waits
-    // for the peer's (measured in round 2: the nondeterministic "unspecified launch failure" / hang of round 1; with the
-    // pair kernel switched off it never happened, with one pair CTA per SM neither; the chain kernels, 221 KB of shared
-    // memory each, never hit it).  So a pair CTA reserves more than half of an SM's shared memory: at most one
-    // cta_group::2 allocator per SM at any time.
-    constexpr size_t HALF_SM_SMEM = 114 * 1024;
-    if (CTA2 && smem <= HALF_SM_SMEM) smem = HALF_SM_SMEM + 1024;
+    const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
+    // CTA pairs (CTA2, tcgen05 cta_group::2) are NOT launched from this file any more.  Round 2 traced the
+    // nondeterministic "unspecified launch failure" / hang of round 1 to them: a pair allocates Tensor Memory with
+    // tcgen05.alloc.cta_group::2 on both of its SMs, and with 100 KB of shared memory per CTA another kernel's
+    // single-CTA allocator can be resident on ONE of the two SMs -- the pair then never leaves its allocation (flight
+    // recorder: exactly the two CTAs of one pair entered and never finished set-up, nothing else in flight; 0 of 7
+    // runs with the pair GEMM off, 2-4 of 4 with it on, whatever the programmatic-launch settings).  The chain kernels
+    // keep their pairs: 221 KB of shared memory and all 512 columns each, so a pair owns both SMs outright, which is
+    // also what CUTLASS's 2-SM kernels do.  The single-CTA 128 x 256 tile is faster here anyway (98.2 k vs 92.6 k
+    // captions/s with exclusive pairs).
+    static_assert(!CTA2, "pair GEMMs are retired: see the note above");
     static cap_device_once smem_once;
     CAP_PROPAGATE(cap_opt_in_smem(smem_once, gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, 200 * 1024));
     CAP_PROPAGATE(install_fault_buffer());
@@ -534,13 +536,6 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, bn));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static const bool use_2cta = env_int("OPENVIIC_GEMM_2CTA", 1) != 0;
-    if (bn == 256 && use_2cta) {
-        CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));  // each CTA of the pair stages half of the B tile
-        p.num_stages = forced_stages ? forced_stages : 4;   // 4 x 32 KB: the ring itself keeps the CTA alone on its SM (launch_gemm)
-        if (p.num_stages > num_kb) p.num_stages = num_kb;
-        return launch_gemm<256, false, true>(ta, tb, p, s);
-    }
     switch (bn) {
         case 256: return launch_gemm<256>(ta, tb, p, s);
         case 128: return launch_gemm<128>(ta, tb, p, s);
@@ -604,12 +599,6 @@ extern "C" int cap_vocab_logits_stats(const void* x, int ldx, const void* w, con
     if (chunks_out) *chunks_out = ((N + 255) / 256) * 8;
     CUtensorMap ta, tb;
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
-    static const bool use_2cta = env_int("OPENVIIC_GEMM_2CTA", 1) != 0;
-    if (use_2cta) {
-        p.num_stages = num_kb < 3 ? num_kb : 3;
-        CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));
-        return launch_gemm<256, true, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
-    }
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 256));
     return launch_gemm<256, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }

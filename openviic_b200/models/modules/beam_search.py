@@ -29,9 +29,11 @@ class BeamSearch(object):
     def apply(self, out_size=1, return_probs=False, **kwargs):
         if self.device.type != "cuda":
             raise RuntimeError("BeamSearch runs on CUDA only (no CPU fallback)")
-        if return_probs:
-            raise NotImplementedError("return_probs=True (the full per-step distributions) is not on the hot path")
         b_s, beam, T = self.b_s, self.beam_size, self.max_len
+        # return_probs (beam_search.py:68-81, 90, 103-118): the word log-probs of every step, masked like the
+        # reference's (zero rows for finished beams), in the beam order OF THAT STEP (the reference never reorders the
+        # earlier entries by later selections), gathered once by the final sort of the beams
+        all_log_probs, seq_mask = [], torch.ones((b_s, beam, 1), device=self.device)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         handle = C.c_void_p()
         state = None
@@ -49,20 +51,35 @@ class BeamSearch(object):
                     tokens = self._view(lib.cap_beam_tokens(state), b_s * beam, torch.int32)
                     parents = self._view(lib.cap_beam_parents(state), b_s * beam, torch.int32)
                 scores = word_logprob.expand(b_s, beam, vocab).contiguous() if cur == 1 else word_logprob.contiguous()
+                if return_probs:
+                    if t > 0:
+                        seq_mask = seq_mask * (selected_words.view(b_s, cur) != self.eos_idx).float().unsqueeze(-1)
+                        all_log_probs.append((word_logprob * seq_mask).unsqueeze(2))
+                    else:
+                        all_log_probs.append(scores.unsqueeze(2).clone())
                 cabi.call("cap_beam_step", state, t, scores.data_ptr(), vocab, 1, stream)
                 sel_beam = parents.view(b_s, beam).long()
+                if return_probs:
+                    seq_mask = torch.gather(seq_mask, 1, sel_beam.clone().unsqueeze(-1))
                 base = torch.arange(b_s, device=self.device).view(-1, 1) * cur
                 self.model.apply_to_states(self._expand_state((base + sel_beam).reshape(-1)))
                 selected_words = tokens.long().view(-1, 1).clone()
             ids = torch.empty((b_s, out_size, T), device=self.device, dtype=torch.int64)
             logp = torch.empty((b_s, out_size, T), device=self.device, dtype=torch.float32)
             cabi.call("cap_beam_finalize", state, out_size, ids.data_ptr(), logp.data_ptr(), stream)
+            if return_probs:   # the same final order: beams by seq_logprob, descending, stable
+                seq_lp = self._view(cabi.load_library().cap_beam_seq_logprob(state), b_s * beam, torch.float32).view(b_s, beam)
+                order = torch.sort(seq_lp, dim=1, descending=True, stable=True).indices
+                probs = torch.cat(all_log_probs, 2)
+                probs = torch.gather(probs, 1, order.view(b_s, beam, 1, 1).expand(b_s, beam, T, probs.shape[-1]))
             torch.cuda.current_stream().synchronize()
         finally:
             if state is not None:
                 cabi.call("cap_beam_destroy", state)
         if out_size == 1:
             ids, logp = ids.squeeze(1), logp.squeeze(1)
+        if return_probs:
+            return ids, logp, probs
         return ids, logp
 
     def _view(self, ptr: int, count: int, dtype: torch.dtype) -> torch.Tensor:

@@ -457,7 +457,7 @@ def _reorder(s: Tensor, b_s: int, cur: int, beam_idx: Tensor) -> Tensor:
 
 def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states: Callable[[Callable], None],
                 b_s: int, beam: int, max_len: int, eos_idx: int, out_size: int = 1,
-                trace: Optional[list] = None, stable_ties: bool = False) -> Tuple[Tensor, Tensor]:
+                trace: Optional[list] = None, stable_ties: bool = False, return_probs: bool = False):
     """BeamSearch.apply/iter/select, models/modules/beam_search.py:36-118.
 
     ``step(t, prev_tokens)`` returns (rows,1,V) log-probs; ``reorder_states(fn)`` maps ``fn`` over
@@ -476,6 +476,7 @@ def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states:
     seq_logprob = torch.zeros(b_s, 1, 1)
     outputs: List[Tensor] = []
     log_probs: List[Tensor] = []
+    all_log_probs: List[Tensor] = []   # return_probs: beam_search.py:68-81 -- never reordered by later selections
     selected_words: Optional[Tensor] = None
     for t in range(max_len):
         cur = 1 if t == 0 else beam
@@ -502,6 +503,8 @@ def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states:
         seq_mask = torch.gather(seq_mask, 1, sel_beam.unsqueeze(-1))
         outputs = [torch.gather(o, 1, sel_beam.unsqueeze(-1)) for o in outputs]
         outputs.append(sel_word.unsqueeze(-1))
+        if return_probs:
+            all_log_probs.append((word_lp.expand(b_s, beam, -1) if t == 0 else word_lp).unsqueeze(2))
         this_lp = torch.gather(word_lp, 1, sel_beam.unsqueeze(-1).expand(b_s, beam, vocab))
         this_lp = torch.gather(this_lp, 2, sel_word.unsqueeze(-1))
         log_probs = [torch.gather(o, 1, sel_beam.unsqueeze(-1)) for o in log_probs]
@@ -515,6 +518,10 @@ def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states:
     ids, lps = ids.contiguous()[:, :out_size], lps.contiguous()[:, :out_size]
     if out_size == 1:
         ids, lps = ids.squeeze(1), lps.squeeze(1)
+    if return_probs:   # beam_search.py:103-118: gathered by the final order only, all `beam` rows kept
+        probs = torch.cat(all_log_probs, 2)
+        probs = torch.gather(probs, 1, order.unsqueeze(-1).expand(b_s, beam, max_len, probs.shape[-1]))
+        return ids, lps, probs
     return ids, lps
 
 
@@ -524,7 +531,7 @@ def beam_search(step: Callable[[int, Optional[Tensor]], Tensor], reorder_states:
 
 def caption_beam_search(w: Weights, model_cfg, vocab, feats: Tensor, boxes: Optional[Tensor] = None,
                         beam: int = 5, out_size: int = 1, trace: Optional[list] = None,
-                        logits_trace: Optional[list] = None) -> Tuple[Tensor, Tensor]:
+                        logits_trace: Optional[list] = None, return_probs: bool = False):
     """BaseTransformer.beam_search + .step, models/base_transformer.py:30-53.
 
     Returns (ids (B,T) int64, log_probs (B,T) fp32) for out_size == 1, else (B,out_size,T).
@@ -551,7 +558,7 @@ def caption_beam_search(w: Weights, model_cfg, vocab, feats: Tensor, boxes: Opti
                 lay["keys"], lay["values"] = fn(lay["keys"]), fn(lay["values"])
 
         return beam_search(step, reorder_states, b_s, beam, vocab.max_caption_length, vocab.eos_idx,
-                           out_size, trace)
+                           out_size, trace, return_probs=return_probs)
 
 
 def teacher_forced_log_probs(w: Weights, model_cfg, vocab, feats: Tensor, tokens: Tensor,

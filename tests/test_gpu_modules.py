@@ -76,3 +76,26 @@ def test_adaptive_attention_matches_the_reference_class(device):
     out2 = att(q.to(device), k.to(device), k.to(device), sig.to(device)).float().cpu()
     ref2 = oracle.adaptive_attention(weights, "", cfg, q, k, k, sig, None)
     assert (out2 - ref2).abs().max().item() < 2e-2
+
+
+def test_beam_search_return_probs(device):
+    """return_probs=True (beam_search.py:68-81, 103-118): the masked word log-probs of every step, in that step's beam
+    order, gathered by the final order of the beams.  The oracle's restatement equals the real reference's output
+    exactly (checked in the build container); here the module path is compared with the oracle on the images whose
+    beams all agree."""
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case("aug_mem", device)
+    b, beam, T = case["batch"], case["beam"], case["max_len"]
+    items = make_items(field, feats, boxes, device)
+    ids, lp, probs = model.beam_search(items, batch_size=b, beam_size=beam, out_size=beam, return_probs=True)
+    torch.cuda.synchronize()
+    assert probs.shape == (b, beam, T, case["vocab"]) and ids.shape == (b, beam, T)
+    r_ids, r_lp, r_probs = oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=beam, out_size=beam,
+                                                      return_probs=True)
+    same = (ids.cpu() == r_ids).all(-1).all(-1)
+    print(f"[return_probs] images whose {beam} beams all equal the oracle's: {int(same.sum())}/{b}")
+    assert same.any()
+    diff = (probs.cpu() - r_probs)[same].abs()
+    print(f"[return_probs] all-steps log-prob max-abs {diff.max():.4f} mean-abs {diff.mean():.5f}")
+    assert diff.max().item() < TOL_LOGP and diff.mean().item() < TOL_LOGP_MEAN
+    # finished beams contribute exact zeros, as in the reference (word_logprob * seq_mask)
+    assert torch.equal((probs.cpu()[same] == 0).all(-1), (r_probs[same] == 0).all(-1))
