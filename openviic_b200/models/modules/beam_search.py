@@ -16,6 +16,9 @@ from ... import cabi
 
 
 class BeamSearch(object):
+    # tests set this to a list to receive every step's (selected beams, selected words), each (b_s, beam), int64
+    debug_trace = None
+
     def __init__(self, model, b_s: int, max_len: int, eos_idx: int, beam_size: int, device):
         self.model, self.b_s, self.max_len = model, b_s, max_len
         self.eos_idx, self.beam_size, self.device = eos_idx, beam_size, torch.device(device)
@@ -64,6 +67,8 @@ class BeamSearch(object):
                 base = torch.arange(b_s, device=self.device).view(-1, 1) * cur
                 self.model.apply_to_states(self._expand_state((base + sel_beam).reshape(-1)))
                 selected_words = tokens.long().view(-1, 1).clone()
+                if BeamSearch.debug_trace is not None:
+                    BeamSearch.debug_trace.append((sel_beam.clone(), selected_words.view(b_s, beam).clone()))
             ids = torch.empty((b_s, out_size, T), device=self.device, dtype=torch.int64)
             logp = torch.empty((b_s, out_size, T), device=self.device, dtype=torch.float32)
             cabi.call("cap_beam_finalize", state, out_size, ids.data_ptr(), logp.data_ptr(), stream)

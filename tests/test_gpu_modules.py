@@ -82,17 +82,27 @@ def test_beam_search_return_probs(device):
     """return_probs=True (beam_search.py:68-81, 103-118): the masked word log-probs of every step, in that step's beam
     order, gathered by the final order of the beams.  The oracle's restatement equals the real reference's output
     exactly (checked in the build container); here the module path is compared with the oracle on the images whose
-    beams all agree."""
+    selections agree at EVERY step (step t's rows are in step t's beam order, so equal final captions are not enough: a
+    beam that dies later may sit in a different slot)."""
+    from openviic_b200.models.modules.beam_search import BeamSearch
     case, cfg, vocab, model, weights, field, feats, boxes = load_case("aug_mem", device)
     b, beam, T = case["batch"], case["beam"], case["max_len"]
     items = make_items(field, feats, boxes, device)
-    ids, lp, probs = model.beam_search(items, batch_size=b, beam_size=beam, out_size=beam, return_probs=True)
-    torch.cuda.synchronize()
+    BeamSearch.debug_trace = []
+    try:
+        ids, lp, probs = model.beam_search(items, batch_size=b, beam_size=beam, out_size=beam, return_probs=True)
+        torch.cuda.synchronize()
+        got_trace = [(sb.cpu(), sw.cpu()) for sb, sw in BeamSearch.debug_trace]
+    finally:
+        BeamSearch.debug_trace = None
     assert probs.shape == (b, beam, T, case["vocab"]) and ids.shape == (b, beam, T)
+    ref_trace = []
     r_ids, r_lp, r_probs = oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=beam, out_size=beam,
-                                                      return_probs=True)
+                                                      trace=ref_trace, return_probs=True)
     same = (ids.cpu() == r_ids).all(-1).all(-1)
-    print(f"[return_probs] images whose {beam} beams all equal the oracle's: {int(same.sum())}/{b}")
+    for (sb, sw), ref in zip(got_trace, ref_trace):
+        same &= (sb == ref["beam"].view(b, beam)).all(-1) & (sw == ref["word"].view(b, beam)).all(-1)
+    print(f"[return_probs] images whose {beam} beams equal the oracle's at every step: {int(same.sum())}/{b}")
     assert same.any()
     diff = (probs.cpu() - r_probs)[same].abs()
     print(f"[return_probs] all-steps log-prob max-abs {diff.max():.4f} mean-abs {diff.mean():.5f}")
