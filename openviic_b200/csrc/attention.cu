@@ -719,10 +719,8 @@ int launch_cross_stream(const bf16* q, int ldq, const bf16* kv, const uint8_t* k
     const size_t budget = 226 * 1024;
     int stages = static_cast<int>((budget - fixed) / stage_bytes);
     if (stages < 1) return cap_set_error(CAP_ERR_INVALID, "cap_decode_cross_attention: %d keys do not fit shared memory", n);
-    static const int env_stages = getenv("OPENVIIC_XATTN_STAGES") ? atoi(getenv("OPENVIIC_XATTN_STAGES")) : 0;   // tuning
-    static const int env_per_cta = getenv("OPENVIIC_XATTN_IMAGES") ? atoi(getenv("OPENVIIC_XATTN_IMAGES")) : 0;
-    stages = std::min(stages, env_stages > 0 ? env_stages : XA_MAX_STAGES);
-    const int per_cta = env_per_cta > 0 ? env_per_cta : (stages > 1 ? XA_IMAGES_PER_CTA : 1);
+    stages = std::min(stages, XA_MAX_STAGES);
+    const int per_cta = stages > 1 ? XA_IMAGES_PER_CTA : 1;
     const int n_virtual = B * levels;
     const int grid = std::max(1, (n_virtual + per_cta - 1) / per_cta);
     stages = std::min(stages, (n_virtual + grid - 1) / grid);   // never more stages than images per CTA

@@ -130,7 +130,7 @@ struct cap_engine {
     int64_t* out_ids = nullptr;
     float* out_logp = nullptr;
     cap_beam* beam_state = nullptr;
-    bool fuse_ln = true;                 // Linear + residual + LayerNorm as one cluster kernel (OPENVIIC_LN_FUSED=0: two kernels)
+    bool fuse_ln = true;                 // Linear + residual + LayerNorm as one cluster kernel
     cap_fused_decoder* fused = nullptr;  // GEMM chains of the decode step (decode_fused.cu) when the model is covered
     cap_enc_chains* enc_chains = nullptr;  // GEMM chains of the encoder, ditto
 
@@ -323,7 +323,6 @@ extern "C" int cap_engine_create(const cap_model_desc* desc, cap_engine** out) {
     cap_engine* e = new cap_engine();
     e->desc = m;
     e->weights = std::make_shared<WeightOwner>();
-    if (const char* env = getenv("OPENVIIC_LN_FUSED")) e->fuse_ln = atoi(env) != 0;
     *out = e;
     return CAP_OK;
 }

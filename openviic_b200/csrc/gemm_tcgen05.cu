@@ -65,23 +65,17 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // reads only the `beam` chunks with the largest maxima -- the row's top-`beam` logits provably lie there --
 // so the 52 MB logits buffer is written once and almost never read back.
 //
-// CTA2: two CTAs of one cluster (adjacent M tiles, same N tile) form a pair; each loads its own 128 A rows
-// and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) reading both shared memories,
-// and every CTA drains its own 128 accumulator rows.  Per CTA the smem fill per k-block drops from
-// 16 + BLOCK_N/8 KB to 16 + BLOCK_N/16 KB for the same MMA work.
-//
 // LN (BLOCK_N = 128, 1-CTA MMA): the N/128 CTAs of one row tile form a cluster along N; the epilogue adds
 // bias and the fp32 residual, keeps the tile in shared memory, exchanges per-row sums and centred sums of
 // squares with its cluster peers through distributed shared memory (two cluster barriers), normalises and
 // writes a bf16 copy (next GEMM operand) and an fp32 copy (next residual).  One kernel instead of
 // GEMM -> fp32 round trip -> LayerNorm kernel.
-template <int BLOCK_N, bool STATS, bool CTA2, bool LN = false>
+template <int BLOCK_N, bool STATS, bool LN = false>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmParams p) {
     if (threadIdx.x == 0) flight_mark(FK_GEMM, 0);
-    constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // B rows this CTA stages
-    constexpr uint32_t B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
+    constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 
@@ -98,12 +92,9 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // 1-CTA: grid (n tiles, m tiles).  2-CTA: grid (m tiles rounded up to even, n tiles), cluster (2,1,1).
-    const int m_tile = CTA2 ? blockIdx.x : blockIdx.y;
-    const int n_tile = CTA2 ? blockIdx.y : blockIdx.x;
-    const int n_tiles = CTA2 ? gridDim.y : gridDim.x;
-    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
-    const bool leader = rank == 0;
+    const int m_tile = blockIdx.y;   // grid (n tiles, m tiles)
+    const int n_tile = blockIdx.x;
+    const int n_tiles = gridDim.x;
     const int m0 = m_tile * BLOCK_M;
     const int n0 = n_tile * BLOCK_N;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -123,10 +114,10 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        if constexpr (CTA2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot);
+        tmem_alloc<TMEM_COLS>(tmem_slot);
     }
     tcgen05_fence_before();
-    if constexpr (CTA2) cluster_sync(); else __syncthreads();  // barriers of BOTH CTAs initialised before use
+    __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(p, 1);
@@ -148,24 +139,17 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_wait(&empty_bar[s], phase ^ 1);
             uint8_t* a_tile = smem + s * STAGE_BYTES;
             if (elect_one_sync()) {
-                if constexpr (CTA2) {
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // both CTAs' four tiles
-                    tma_load_2d_2sm(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
-                    tma_load_2d_2sm_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K,
-                                         n0 + static_cast<int>(rank) * B_ROWS, keep_policy);
-                } else {
-                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
-                    tma_load_2d_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0, keep_policy);  // weights
-                }
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+                tma_load_2d_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0, keep_policy);  // weights
                 if (kb == 0) stamp(p, 2);
             }
             __syncwarp();
         }
         if constexpr (LN) { __syncwarp(); cluster_sync(); cluster_sync(); }  // the epilogue's two exchanges
     } else if (warp == 1) {
-        if (leader) {
-            constexpr uint32_t idesc = make_instr_desc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+        {
+            constexpr uint32_t idesc = make_instr_desc(BLOCK_M, BLOCK_N);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
@@ -179,15 +163,11 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        if constexpr (CTA2)
-                            umma_bf16_2sm(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else
-                            umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    // stage reusable (in both CTAs) once these MMAs have read it
-                    if constexpr (CTA2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
-                    if (kb == num_kb - 1) {  // accumulator complete (in both CTAs)
-                        if constexpr (CTA2) umma_commit_2sm(tmem_full_bar); else umma_commit(tmem_full_bar);
+                    umma_commit(&empty_bar[s]);   // stage reusable once these MMAs have read it
+                    if (kb == num_kb - 1) {       // accumulator complete
+                        umma_commit(tmem_full_bar);
                         stamp(p, 4);
                     }
                 }
@@ -385,10 +365,10 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (warp == 2 && lane == 0) stamp(p, 6);
     tcgen05_fence_before();
     // 2-CTA: both epilogues done before TMEM is released; LN: no CTA leaves while peers may read its statistics
-    if constexpr (CTA2 || LN) cluster_sync(); else __syncthreads();
+    if constexpr (LN) cluster_sync(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        if constexpr (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
+        tmem_dealloc<TMEM_COLS>(tmem_base);
     }
     if (threadIdx.x == 32) stamp(p, 7);
     if (threadIdx.x == 0) {
@@ -432,49 +412,40 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
     return CAP_OK;
 }
 
-template <int BLOCK_N, bool STATS = false, bool CTA2 = false, bool LN = false>
+template <int BLOCK_N, bool STATS = false, bool LN = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
-    constexpr uint32_t stage_bytes = A_TILE_BYTES + (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
+    constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
     constexpr int epi_n = BLOCK_N < 128 ? BLOCK_N : 128;
     const uint32_t staging = BLOCK_M * (epi_n * (p.out_f32 ? 4 : 2) + 16);
     uint32_t pipe = static_cast<uint32_t>(p.num_stages) * stage_bytes;
     if (pipe < staging) pipe = (staging + 1023) / 1024 * 1024;
     p.pipe_bytes = pipe;
     const size_t smem = 1024 + pipe + (2 * MAX_STAGES + 1) * 8 + 16 + BLOCK_N * 4 + (LN ? (2 * BLOCK_N + 4 * BLOCK_M) * 4 : 0);
-    // CTA pairs (CTA2, tcgen05 cta_group::2) are NOT launched from this file any more.  Round 2 traced the
-    // nondeterministic "unspecified launch failure" / hang of round 1 to them: a pair allocates Tensor Memory with
-    // tcgen05.alloc.cta_group::2 on both of its SMs, and with 100 KB of shared memory per CTA another kernel's
+    // There is deliberately no CTA-pair (tcgen05 cta_group::2) variant of this kernel.  Round 1 had one, and round 2
+    // traced the nondeterministic "unspecified launch failure" / hang of round 1 to it: a pair allocates Tensor Memory
+    // with tcgen05.alloc.cta_group::2 on both of its SMs, and with ~100 KB of shared memory per CTA another kernel's
     // single-CTA allocator can be resident on ONE of the two SMs -- the pair then never leaves its allocation (flight
     // recorder: exactly the two CTAs of one pair entered and never finished set-up, nothing else in flight; 0 of 7
-    // runs with the pair GEMM off, 2-4 of 4 with it on, whatever the programmatic-launch settings).  The chain kernels
-    // keep their pairs: 221 KB of shared memory and all 512 columns each, so a pair owns both SMs outright, which is
-    // also what CUTLASS's 2-SM kernels do.  The single-CTA 128 x 256 tile is faster here anyway (98.2 k vs 92.6 k
-    // captions/s with exclusive pairs).
-    static_assert(!CTA2, "pair GEMMs are retired: see the note above");
+    // runs hung with the pair GEMM off, 2-4 of 4 with it on, whatever the programmatic-launch settings).  The chain
+    // kernels keep their pairs: 221 KB of shared memory and all 512 columns each, so a pair owns both SMs outright,
+    // which is also what CUTLASS's 2-SM kernels do.  The single-CTA 128 x 256 tile is faster here anyway (98.2 k vs
+    // 92.6 k captions/s with exclusive pairs).
     static cap_device_once smem_once;
-    CAP_PROPAGATE(cap_opt_in_smem(smem_once, gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, 200 * 1024));
+    CAP_PROPAGATE(cap_opt_in_smem(smem_once, gemm_tn_bf16_tcgen05<BLOCK_N, STATS, LN>, 200 * 1024));
     CAP_PROPAGATE(install_fault_buffer());
     const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-    if constexpr (CTA2) {
-        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, dim3((tiles_m + 1) / 2 * 2, tiles_n),
-                          dim3(GEMM_THREADS), smem, stream, /*cluster_x=*/2, ta, tb, p);
-    } else if constexpr (LN) {  // the tiles_n CTAs of a row tile form one cluster along x
-        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>, dim3(tiles_n, tiles_m), dim3(GEMM_THREADS), smem,
+    if constexpr (LN) {  // the tiles_n CTAs of a row tile form one cluster along x
+        cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, LN>, dim3(tiles_n, tiles_m), dim3(GEMM_THREADS), smem,
                           stream, /*cluster_x=*/tiles_n, ta, tb, p);
     } else {
         dim3 grid(tiles_n, tiles_m);
-        CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS, CTA2, LN>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
+        CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS, LN>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("gemm_tn_bf16_tcgen05");
 }
 
 unsigned long long* g_gemm_trace = nullptr;
-
-int env_int(const char* name, int fallback) {
-    const char* s = getenv(name);
-    return s ? atoi(s) : fallback;
-}
 
 }  // namespace
 
@@ -494,23 +465,17 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     CAP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                 "cap_linear: x and w must be 16-byte aligned");
     CAP_REQUIRE(ldx >= K && ldy >= N, "cap_linear: leading dimensions too small");
-    static const int forced_bn = env_int("OPENVIIC_GEMM_BLOCK_N", 0);
-    static const int forced_stages = env_int("OPENVIIC_GEMM_STAGES", 0);
 
     const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
     int bn = 32;
-    if (forced_bn) {
-        bn = forced_bn;
-    } else {
+    {
         // Widest tile that N fills: with several batches pipelined on separate streams the SMs are kept
         // busy by other kernels, so total L2->smem fill traffic (A is re-read once per N tile) matters
         // more than the CTA count of one GEMM (measured: +8.6 % captions/s vs. "at least one wave").
         // 128x256 tiles pay off when the grid still fills the GPU (encoder, vocabulary: measured 690-820 vs
         // 510-730 TFLOP/s); for the small decode GEMMs 128-wide tiles gave the better end-to-end rate.
         bn = (N >= 256 && tiles_m >= 32) ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : 32));
-        (void)tiles_m;
     }
-    CAP_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "cap_linear: unsupported BLOCK_N %d", bn);
 
     GemmParams p;
     p.out = y;
@@ -523,7 +488,7 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
     p.act = act;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     // short K loops (<= 8 blocks) get a 2-deep ring: less smem per CTA, more CTAs of concurrent kernels per SM
-    int stages = forced_stages ? forced_stages : (bn == 256 ? 2 : (bn == 128 ? (num_kb <= 8 ? 2 : 3) : 4));
+    int stages = bn == 256 ? 2 : (bn == 128 ? (num_kb <= 8 ? 2 : 3) : 4);
     if (stages > num_kb) stages = num_kb;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 1) stages = 1;
@@ -574,7 +539,7 @@ extern "C" int cap_linear_layernorm(const void* x, int ldx, const void* w, const
     CUtensorMap ta, tb;
     CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
     CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, 128));
-    return launch_gemm<128, false, false, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    return launch_gemm<128, false, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }
 
 // Vocabulary projection: fp32 logits + per-32-column-chunk log-softmax statistics in one pass.

@@ -16,7 +16,8 @@ from ... import cabi
 
 
 class BeamSearch(object):
-    # tests set this to a list to receive every step's (selected beams, selected words), each (b_s, beam), int64
+    # tests set this to a list to receive every step's (selected beams, selected words), each (b_s, beam), int64, and
+    # (with return_probs) the final order of the beams as the last entry
     debug_trace = None
 
     def __init__(self, model, b_s: int, max_len: int, eos_idx: int, beam_size: int, device):
@@ -76,6 +77,8 @@ class BeamSearch(object):
                 seq_lp = self._view(cabi.load_library().cap_beam_seq_logprob(state), b_s * beam, torch.float32).view(b_s, beam)
                 order = torch.sort(seq_lp, dim=1, descending=True, stable=True).indices
                 probs = torch.cat(all_log_probs, 2)
+                if BeamSearch.debug_trace is not None:
+                    BeamSearch.debug_trace.append(order.clone())
                 probs = torch.gather(probs, 1, order.view(b_s, beam, 1, 1).expand(b_s, beam, T, probs.shape[-1]))
             torch.cuda.current_stream().synchronize()
         finally:

@@ -3,8 +3,7 @@ shapes (masks, ragged batches, beams 1..5, n up to 104) and launch time at the b
 
     python tests/gpu_scripts/probe_cross_stream.py
 
-OPENVIIC_XATTN_IMAGES / OPENVIIC_XATTN_STAGES (images per CTA, ring stages) are read once per process: sweep them from
-the shell.  (Round 2 measured the two kernels this one replaced at the bench shape: CUDA-core arithmetic 23.3 us per
+(Round 2 swept images per CTA and ring stages -- 4 and 4 are compiled in -- and measured the two kernels this one replaced at the bench shape: CUDA-core arithmetic 23.3 us per
 launch, tensor path with one CTA per image 16.4 us, this one 16.5 us alone and the same throughput in the pipeline.)
 """
 import ctypes as C
@@ -76,8 +75,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (25 * len(sets))
-            print(f"B={B} n={n}: {us:.2f} us per launch back to back, {B * n * 2048 / us / 1e3:.0f} GB/s of K|V "
-                  f"(images/CTA {os.environ.get('OPENVIIC_XATTN_IMAGES', 'default')}, stages {os.environ.get('OPENVIIC_XATTN_STAGES', 'default')})")
+            print(f"B={B} n={n}: {us:.2f} us per launch back to back, {B * n * 2048 / us / 1e3:.0f} GB/s of K|V ")
 
 
 if __name__ == "__main__":

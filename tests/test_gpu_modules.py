@@ -81,9 +81,9 @@ def test_adaptive_attention_matches_the_reference_class(device):
 def test_beam_search_return_probs(device):
     """return_probs=True (beam_search.py:68-81, 103-118): the masked word log-probs of every step, in that step's beam
     order, gathered by the final order of the beams.  The oracle's restatement equals the real reference's output
-    exactly (checked in the build container); here the module path is compared with the oracle on the images whose
-    selections agree at EVERY step (step t's rows are in step t's beam order, so equal final captions are not enough: a
-    beam that dies later may sit in a different slot)."""
+    exactly (checked in the build container).  Here the module path is compared with the oracle per image for every
+    step up to the first one whose selection differs (until then both sides computed step t from the same beams in
+    the same slots), slot by slot -- the final gather is undone with each side's own final order."""
     from openviic_b200.models.modules.beam_search import BeamSearch
     case, cfg, vocab, model, weights, field, feats, boxes = load_case("aug_mem", device)
     b, beam, T = case["batch"], case["beam"], case["max_len"]
@@ -92,20 +92,34 @@ def test_beam_search_return_probs(device):
     try:
         ids, lp, probs = model.beam_search(items, batch_size=b, beam_size=beam, out_size=beam, return_probs=True)
         torch.cuda.synchronize()
-        got_trace = [(sb.cpu(), sw.cpu()) for sb, sw in BeamSearch.debug_trace]
+        got_trace = [tuple(x.cpu() for x in e) if isinstance(e, tuple) else e.cpu() for e in BeamSearch.debug_trace]
     finally:
         BeamSearch.debug_trace = None
     assert probs.shape == (b, beam, T, case["vocab"]) and ids.shape == (b, beam, T)
+    got_order, got_trace = got_trace[-1], got_trace[:-1]
     ref_trace = []
     r_ids, r_lp, r_probs = oracle.caption_beam_search(weights, cfg.MODEL, vocab, feats, boxes, beam=beam, out_size=beam,
                                                       trace=ref_trace, return_probs=True)
-    same = (ids.cpu() == r_ids).all(-1).all(-1)
-    for (sb, sw), ref in zip(got_trace, ref_trace):
-        same &= (sb == ref["beam"].view(b, beam)).all(-1) & (sw == ref["word"].view(b, beam)).all(-1)
-    print(f"[return_probs] images whose {beam} beams equal the oracle's at every step: {int(same.sum())}/{b}")
-    assert same.any()
-    diff = (probs.cpu() - r_probs)[same].abs()
-    print(f"[return_probs] all-steps log-prob max-abs {diff.max():.4f} mean-abs {diff.mean():.5f}")
-    assert diff.max().item() < TOL_LOGP and diff.mean().item() < TOL_LOGP_MEAN
-    # finished beams contribute exact zeros, as in the reference (word_logprob * seq_mask)
-    assert torch.equal((probs.cpu()[same] == 0).all(-1), (r_probs[same] == 0).all(-1))
+    ref_order = torch.sort(ref_trace[-1]["seq_logprob"].view(b, beam), 1, descending=True).indices
+
+    def by_slot(p, order):   # undo the final gather: row `order[j]` of the per-step tensors is output row j
+        out = torch.empty_like(p)
+        out.scatter_(1, order.view(b, beam, 1, 1).expand_as(p), p)
+        return out
+
+    got, ref = by_slot(probs.cpu(), got_order), by_slot(r_probs, ref_order)
+    alive = torch.ones(b, dtype=torch.bool)
+    compared, worst, mean_sum = 0, 0.0, 0.0
+    for t, ((sb, sw), rt) in enumerate(zip(got_trace, ref_trace)):
+        slots = 1 if t == 0 else beam   # step 0: every slot holds the same row
+        d = (got[alive, :slots, t] - ref[alive, :slots, t]).abs()
+        if d.numel():
+            compared += int(alive.sum())
+            worst, mean_sum = max(worst, d.max().item()), mean_sum + d.mean().item() * int(alive.sum())
+            # finished beams contribute exact zeros, as in the reference (word_logprob * seq_mask)
+            assert torch.equal((got[alive, :slots, t] == 0).all(-1), (ref[alive, :slots, t] == 0).all(-1))
+        alive &= (sb == rt["beam"].view(b, beam)).all(-1) & (sw == rt["word"].view(b, beam)).all(-1)
+    print(f"[return_probs] {compared} image-steps compared (of {b * T}), log-prob max-abs {worst:.4f} "
+          f"mean-abs {mean_sum / max(compared, 1):.5f}; captions identical {int((ids.cpu() == r_ids).all(-1).all(-1).sum())}/{b}")
+    assert compared >= 3 * b
+    assert worst < TOL_LOGP and mean_sum / compared < TOL_LOGP_MEAN
