@@ -205,7 +205,11 @@ def time_decode_chains(eng, cfg, batch, device):
     e1.record()
     torch.cuda.synchronize()
     sec_per_step = e0.elapsed_time(e1) / 1e3 / (3 * MAX_LEN)
-    macs_per_row = layers * (3 * d * d + 3 * d * d + 2 * d * dff) + VOCAB * d
+    # per layer: q|k|v 3 d^2, self fc_o, cross fc_q, cross fc_o (plain: 6 d^2); the meshed decoder adds the gates' s-part
+    # (levels d^2) and runs fc_o + the gate's c-part once per encoder level
+    levels = dec.ATTENTION.N_ENCODER_LAYERS if dec.ARCHITECTURE == "MeshedDecoder" else 0
+    proj = (5 + 3 * levels) * d * d if levels else 6 * d * d
+    macs_per_row = layers * (proj + 2 * d * dff) + VOCAB * d
     return 2.0 * batch * BEAM * macs_per_row, sec_per_step, 1 + 2 * layers
 
 
@@ -445,7 +449,8 @@ def run_gpu_arm(args):
     # would be a visible part of it.  One untimed calibration pass, then the K steps are repeated `passes` times
     # inside one timed region of >= --min-timed-ms; ms_per_step = region / (K x passes).
     calib_ms, _, _ = timed_pass(1)
-    passes = max(1, int(-(-args.min_timed_ms // max(calib_ms, 1e-3)))) if args.min_timed_ms > 0 else 1
+    # 15 % on top: the calibration pass includes a little ramp-up, and the region must not end up shorter than asked
+    passes = max(1, int(-(-1.15 * args.min_timed_ms // max(calib_ms, 1e-3)))) if args.min_timed_ms > 0 else 1
     if world > 1:   # every rank must run the same number of passes
         pt = torch.tensor([passes], device=device)
         dist.all_reduce(pt, op=dist.ReduceOp.MAX)
@@ -533,6 +538,18 @@ def run_gpu_arm(args):
                     "alone_timing": "the same launches of ONE batch alone on the GPU (10 row tiles = 10 of 148 SMs busy): "
                                     "per-launch latency, not throughput",
                     "share_of_step": MAX_LEN * (sat_s if sat_s else chain_s) / (total_ms / 1e3 / steps_timed)}
+        # one batch alone on the GPU, the setting of the committed ncu launch list: the chains' share of THAT step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.caption_device(feats_dev[0], boxes_dev[0], 1, not args.no_graph, outs_dev[0])
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            eng.caption_device(feats_dev[0], boxes_dev[0], 1, not args.no_graph, outs_dev[0])
+        e1.record()
+        torch.cuda.synchronize()
+        alone_step_s = e0.elapsed_time(e1) / 3e3
+        roofline["alone_ms_per_step"] = alone_step_s * 1e3
+        roofline["alone_share_of_step"] = MAX_LEN * chain_s / alone_step_s
     else:
         flops, gemm_s = time_gemm_family(cfg, n, batch, levels, device)
         achieved = flops / gemm_s / 1e12

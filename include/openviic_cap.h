@@ -453,6 +453,52 @@ int cap_cider_score(const cap_cider* c, const int32_t* hyp_tokens, const int64_t
 /* Kernels launched by this library since load (all entry points); for bench.py's gpu_launches. */
 int64_t cap_launch_count(void);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * T1 -- the XE training step (trainers/vi_trainer.py:105-119; trainers/base_trainer.py:89-91, 114-117).
+ * The forward pass uses cap_linear / cap_attention above plus the two *_fwd entry points here; the GEMMs of the backward
+ * pass are cap_linear calls on transposed operands.  openviic_b200/training.py strings them together.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* pre = a (+ res) (kept for the backward pass); out = LayerNorm(pre) * gamma + beta (+ pos[row % pos_rows]), rows
+ * flagged in zero_rows zeroed; fp32 and bf16 copies of out.  a, res, pre, out_f32: fp32 [rows][d] dense.
+ * attentions.py:308-309, positionwise_feed_forward.py:26, encoders.py:20,36, decoders.py:26. */
+int cap_train_layernorm_fwd(const float* a, const float* res, const float* gamma, const float* beta, float eps,
+                            const float* pos, int pos_rows, const uint8_t* zero_rows, float* pre, float* out_f32,
+                            void* out_bf16, int rows, int d, cap_stream_t stream);
+/* Backward of the above: dout = dout_a (+ dout_b); dpre (fp32 and bf16) is the gradient of both summands of pre;
+ * dgamma / dbeta [d] are ACCUMULATED into (atomicAdd). */
+int cap_train_layernorm_bwd(const float* dout_a, const float* dout_b, const float* pre, const float* gamma, float eps,
+                            const uint8_t* zero_rows, float* dpre_f32, void* dpre_bf16, float* dgamma, float* dbeta,
+                            int rows, int d, cap_stream_t stream);
+/* out[c][r] = in[r][c] (bf16), out rows padded with zeros up to ldo >= rows; colsum[c] += sum_r in[r][c] (fp32,
+ * optional): the operands of dW = dY^T.X and the bias gradient of a Linear in one pass. */
+int cap_transpose_bf16(const void* in, int ld, void* out, int ldo, float* colsum, int rows, int cols,
+                       cap_stream_t stream);
+/* dh *= (h > 0), bf16, in place (positionwise_feed_forward.py:24). */
+int cap_train_relu_bwd(void* dh, const void* h, int64_t count, cap_stream_t stream);
+/* dst += src, fp32. */
+int cap_axpy_f32(float* dst, const float* src, int64_t count, cap_stream_t stream);
+/* Backward of cap_attention for the plain scaled dot-product attention (attentions.py:51-55): `args` as in the forward
+ * call (geometry / memory / sentinel must be NULL; nq, nk <= 128); d_out has out's layout; dq / dk / dv (bf16) have
+ * q's / k's / v's layout and strides. */
+int cap_attention_backward(const cap_attention_args* args, const void* d_out, void* dq, void* dk, void* dv,
+                           cap_stream_t stream);
+/* Teacher-forcing token embedding: out[row] = emb[tokens[row]] + pos[tokens[row] == pad ? 0 : row % T + 1]
+ * (decoders.py:105-112); emb, pos fp32; fp32 and bf16 outputs. */
+int cap_train_embed_fwd(const int64_t* tokens, const float* emb, const float* pos, int T, int pad_idx, float* out_f32,
+                        void* out_bf16, int rows, int d, cap_stream_t stream);
+/* d_emb[tokens[row]] += g_a[row] (+ g_b[row]) for tokens != pad (nn.Embedding(padding_idx), text_embeddings.py:15). */
+int cap_train_embed_bwd(const int64_t* tokens, const float* g_a, const float* g_b, int pad_idx, float* d_emb, int rows,
+                        int d, cap_stream_t stream);
+/* NLLLoss(ignore_index) over log_softmax(logits), mean over the counted targets (base_trainer.py:91, vi_trainer.py:110):
+ * stats[0] = number of targets != ignore_index, stats[1] = sum of their negative log-likelihoods (loss = stats[1] /
+ * stats[0]); dlogits bf16 [rows][ldd] = (softmax - onehot) / stats[0], zero for ignored rows and columns >= V. */
+int cap_train_xent(const float* logits, int ld, const int64_t* targets, int ignore_index, float* stats, void* dlogits,
+                   int ldd, int rows, int V, cap_stream_t stream);
+/* torch.optim.Adam (no weight decay) on flat fp32 buffers, step >= 1, and the bf16 copy of the new parameters. */
+int cap_train_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                   int64_t count, float lr, float beta1, float beta2, float eps, int step, cap_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,16 @@ SIGNATURES = {
     "cap_geometry_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "cap_region_grid_mask": (_i, [_vp, _vp, _i, _i, _vp]),
     "cap_attention": (_i, [C.POINTER(AttentionArgs), _vp]),
+    "cap_train_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cap_train_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cap_transpose_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "cap_train_relu_bwd": (_i, [_vp, _vp, _i64, _vp]),
+    "cap_axpy_f32": (_i, [_vp, _vp, _i64, _vp]),
+    "cap_attention_backward": (_i, [C.POINTER(AttentionArgs), _vp, _vp, _vp, _vp, _vp]),
+    "cap_train_embed_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "cap_train_embed_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "cap_train_xent": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "cap_train_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp]),
     "cap_decode_self_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "cap_decode_cross_attention": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "cap_decode_cross_attention_levels": (_i, [_vp, _i, _vp, C.c_size_t, _vp, _vp, _i, C.c_size_t, _i, _i, _i, _i, _i, _f, _vp]),

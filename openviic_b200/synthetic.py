@@ -186,3 +186,33 @@ def synth_inputs(model_cfg, batch: int, n: int, seed: int, ragged: Optional[bool
     feats = synth_features(batch, n, model_cfg.VISION_EMBEDDING.D_FEATURE, seed, ragged)
     boxes = synth_boxes(batch, n, seed) if needs_boxes(model_cfg) else None
     return field, feats, boxes
+
+
+def synth_captions(batch: int, max_len: int, vocab_size: int, seed: int, bos_idx: int = 1, eos_idx: int = 2,
+                   pad_idx: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Training captions as FeatureDataset.__getitem__ builds them (data_utils/dataset.py:56-61 over
+    Vocab.encode_caption, data_utils/vocab.py:97-102): the encoded caption is <bos> w.. <eos> <pad>.. in max_len tokens;
+    the targets (`shifted_right_caption_tokens`) are that row shifted left by one, and the INPUT row has its <eos>
+    replaced by <pad>.  3 .. max_len - 2 words per caption.  -> (tokens, targets), int64 (batch, max_len)."""
+    rng = _rng(seed, "captions")
+    tokens = np.full((batch, max_len), pad_idx, dtype=np.int64)
+    for i in range(batch):
+        words = int(rng.integers(3, max(4, max_len - 1)))
+        words = min(words, max_len - 2)
+        tokens[i, 0] = bos_idx
+        tokens[i, 1:1 + words] = rng.integers(4, vocab_size, size=words)
+        tokens[i, 1 + words] = eos_idx
+    targets = np.full_like(tokens, pad_idx)
+    targets[:, :-1] = tokens[:, 1:]
+    tokens[tokens == eos_idx] = pad_idx
+    return torch.from_numpy(tokens), torch.from_numpy(targets)
+
+
+def synth_train_batches(model_cfg, case: dict):
+    """The batches of a training case (oracle/cases.py TRAIN_CASES): [(field, feats, tokens, targets, boxes)] * steps."""
+    out = []
+    for i in range(case["steps"]):
+        field, feats, boxes = synth_inputs(model_cfg, case["batch"], case["n"], case["seed"] + 100 * i)
+        tokens, targets = synth_captions(case["batch"], case["max_len"], case["vocab"], case["seed"] + 100 * i)
+        out.append((field, bf16_round(feats), tokens, targets, boxes))
+    return out

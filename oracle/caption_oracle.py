@@ -567,3 +567,56 @@ def teacher_forced_log_probs(w: Weights, model_cfg, vocab, feats: Tensor, tokens
     with torch.no_grad():
         enc, enc_mask = encode(w, model_cfg, feats, boxes)
         return decode(w, model_cfg, tokens, enc, enc_mask, vocab.padding_idx, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# T1: the XE training step (trainers/vi_trainer.py:100-119, trainers/base_trainer.py:87-91, 114-117)
+# ----------------------------------------------------------------------------------------------
+# The reference's step is: out = model(items) (teacher forcing, log-probs), NLLLoss(ignore_index=<pad>) over
+# (B*T, V) against the shifted-right tokens, backward, Adam(lr, betas=(0.9, 0.98)) step, LambdaLR step with
+# lambda(s) = d_model^-0.5 * min((s+1)^-0.5, (s+1) * warmup^-1.5).  Dropout is NOT restated (p = 0: the stochastic part
+# of the reference's step has no portable generator); oracle/ref_harness/gen_golden_train.py pins this restatement to
+# the real reference's modules with every nn.Dropout set to p = 0.
+# nn.Embedding(padding_idx=<pad>) never updates the <pad> row: its gradient is zeroed here the same way; the
+# sinusoid position table is frozen (decoders.py:87-88).
+
+FROZEN = ("decoder.pos_emb.weight",)
+
+
+def noam_factor(step: int, d_model: int, warmup: int) -> float:
+    """base_trainer.py:114-117 (the scheduler's lambda; `step` counts completed optimizer steps)."""
+    s = step + 1
+    return (d_model ** -0.5) * min(s ** -0.5, s * warmup ** -1.5)
+
+
+def xe_loss(w: Weights, model_cfg, vocab, feats: Tensor, tokens: Tensor, targets: Tensor,
+            boxes: Optional[Tensor] = None) -> Tensor:
+    """loss_fn(model(items).view(-1, V), shifted_right_caption_tokens.view(-1)), vi_trainer.py:107-111 (autograd on)."""
+    enc, enc_mask = encode(w, model_cfg, feats, boxes)
+    logp = decode(w, model_cfg, tokens, enc, enc_mask, vocab.padding_idx, None)
+    return F.nll_loss(logp.reshape(-1, logp.shape[-1]), targets.reshape(-1), ignore_index=vocab.padding_idx)
+
+
+def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int):
+    """Runs len(batches) optimizer steps in place on a float32 copy of `w`.  batches: (feats, tokens, targets[, boxes]).
+    Returns (weights after the last step, [loss per step], gradients of the FIRST step)."""
+    params = {k: v.detach().clone().float().requires_grad_(k not in FROZEN) for k, v in w.items()}
+    trainable = [p for p in params.values() if p.requires_grad]
+    optim = torch.optim.Adam(trainable, lr=lr, betas=(0.9, 0.98))
+    sched = torch.optim.lr_scheduler.LambdaLR(optim, lambda s: noam_factor(s, model_cfg.ENCODER.D_MODEL, warmup))
+    emb, pad = "decoder.word_emb.components.weight", vocab.padding_idx
+    losses, first_grads = [], None
+    for batch in batches:
+        feats, tokens, targets = batch[:3]
+        boxes = batch[3] if len(batch) > 3 else None
+        optim.zero_grad()
+        loss = xe_loss(params, model_cfg, vocab, feats, tokens, targets, boxes)
+        loss.backward()
+        if params[emb].grad is not None:
+            params[emb].grad[pad].zero_()          # nn.Embedding(padding_idx=pad)
+        if first_grads is None:
+            first_grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in params.items()}
+        optim.step()
+        sched.step()
+        losses.append(float(loss.detach()))
+    return {k: v.detach() for k, v in params.items()}, losses, first_grads

@@ -48,3 +48,11 @@ ENGINE_CASES = tuple(c for c in CASES if c not in MODULE_PATH_CASES)
 ADAPTIVE_ATTENTION_CASE = dict(
     config=dict(ARCHITECTURE="AdaptiveScaledDotProductAttention", D_MODEL=512, HEAD=8, D_KEY=64, D_VALUE=64, DROPOUT=0.1),
     batch=5, nq=7, nk=37, seed=21)
+
+# T1, the XE training step (oracle/ref_harness/gen_golden_train.py): `steps` optimizer steps on fresh synthetic batches
+TRAIN_CASES = {
+    "std_grid": dict(config="standard_transformer.yaml", batch=8, n=49, max_len=20, vocab=1000, seed=31, steps=3,
+                     lr=1.0, warmup=10000),
+    "std_region": dict(config="standard_transformer_using_region.yaml", batch=8, n=50, max_len=16, vocab=777, seed=32,
+                       steps=2, lr=1.0, warmup=100),
+}

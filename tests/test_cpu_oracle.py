@@ -6,7 +6,9 @@ import torch
 
 from oracle import caption_oracle as oracle
 from oracle.cases import CASES
-from helpers import golden, load_case
+import openviic_b200 as ov
+from openviic_b200 import synthetic
+from helpers import GOLDEN, golden, load_case
 from kat import ScriptedModel, scripted_kat
 
 FAST = [c for c in CASES if c != "std_region_A"]
@@ -103,3 +105,31 @@ def test_adaptive_attention_oracle_reproduces_the_reference_class():
     q, k, sig, mask = synthetic.synth_adaptive_inputs(case)
     out = oracle.adaptive_attention(weights, "", cfg, q, k, k, sig, mask)
     assert np.abs(out.numpy() - golden("adaptive_attention")["out"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("name", ["std_grid", "std_region"])
+def test_oracle_training_step_reproduces_the_reference(name):
+    """T1: oracle.xe_train_steps (loss, backward, Adam, Noam) against the fixture written from the REAL reference's
+    modules, loss and optimizer by oracle/ref_harness/gen_golden_train.py (per parameter: norm + 16 strided samples of
+    the first-step gradient and of the weights after the last step)."""
+    from oracle.cases import TRAIN_CASES, apply_overrides
+    case = TRAIN_CASES[name]
+    cfg = apply_overrides(ov.get_config(case["config"]), case)
+    cfg.MODEL.DEVICE = "cpu"
+    vocab = synthetic.SyntheticVocab(case["vocab"], case["max_len"])
+    model = ov.build_model(cfg.MODEL, vocab)
+    weights = synthetic.load_synthetic_weights(model, case["seed"])
+    batches = [(f, t, y, b) for _, f, t, y, b in synthetic.synth_train_batches(cfg.MODEL, case)]
+    final, losses, grads = oracle.xe_train_steps(weights, cfg.MODEL, vocab, batches, case["lr"], case["warmup"])
+    g = np.load(GOLDEN / f"train_{name}.npz")
+    assert np.abs(np.asarray(losses) - g["losses"]).max() < 1e-5
+    checked = 0
+    for key in g.files:
+        kind, _, pname = key.partition("/")
+        if kind not in ("g", "w"):
+            continue
+        t = (grads if kind == "g" else final)[pname].reshape(-1)
+        got = np.concatenate([[float(t.norm())], t[:: max(1, t.numel() // 16)][:16].numpy()])
+        assert np.abs(got - g[key]).max() <= 1e-6 * max(1.0, np.abs(g[key]).max()), key
+        checked += 1
+    assert checked > 200

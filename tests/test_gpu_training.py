@@ -1,0 +1,260 @@
+"""T1, the XE training step: every training kernel against a plain fp32 PyTorch reference
+of the same operator (autograd for the backward ones), then the whole step -- loss, every parameter's gradient, the
+losses of consecutive optimizer steps -- against the oracle, whose training step reproduces the real reference's
+exactly (oracle/ref_harness/gen_golden_train.py, differences 0.0)."""
+
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import openviic_b200 as ov
+from openviic_b200 import cabi, synthetic
+from openviic_b200.training import XETrainer, noam_factor
+from oracle import caption_oracle as oracle
+from oracle.cases import TRAIN_CASES, apply_overrides
+
+pytestmark = pytest.mark.gpu
+
+TOL_GRAD_REL = 6e-2     # ||g - g_ref|| / ||g_ref|| per parameter: bf16 operands through 6 layers, forward and backward
+TOL_GRAD_COS = 0.995    # cosine between the full gradient vectors
+TOL_LOSS = 2e-2         # |loss - loss_ref| (losses ~ 10)
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def test_layernorm_pair_matches_autograd(device):
+    torch.manual_seed(1)
+    rows, d = 301, 512
+    a = torch.randn(rows, d, device=device)
+    res = torch.randn(rows, d, device=device)
+    gamma = torch.randn(d, device=device) * 0.5 + 1
+    beta = torch.randn(d, device=device) * 0.1
+    pos = torch.randn(7, d, device=device)
+    zero = (torch.rand(rows, device=device) < 0.2).to(torch.uint8)
+    pre = torch.empty_like(a)
+    o32 = torch.empty_like(a)
+    o16 = torch.empty(rows, d, device=device, dtype=torch.bfloat16)
+    cabi.call("cap_train_layernorm_fwd", a.data_ptr(), res.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, pos.data_ptr(), 7,
+              zero.data_ptr(), pre.data_ptr(), o32.data_ptr(), o16.data_ptr(), rows, d, _s())
+    ar, rr, gr, br = (t.clone().requires_grad_(True) for t in (a, res, gamma, beta))
+    ref = F.layer_norm(ar + rr, (d,), gr, br) + pos[torch.arange(rows, device=device) % 7]
+    ref = ref.masked_fill(zero.bool().unsqueeze(1), 0)
+    assert (pre - (a + res)).abs().max().item() == 0
+    assert (o32 - ref).abs().max().item() < 1e-4 and (o16.float() - ref).abs().max().item() < 4e-2
+    da, db = torch.randn(rows, d, device=device), torch.randn(rows, d, device=device)
+    ref.backward(da + db)
+    d32 = torch.empty_like(a)
+    d16 = torch.empty_like(o16)
+    dg = torch.zeros(d, device=device)
+    dbeta = torch.zeros(d, device=device)
+    cabi.call("cap_train_layernorm_bwd", da.data_ptr(), db.data_ptr(), pre.data_ptr(), gamma.data_ptr(), 1e-5, zero.data_ptr(),
+              d32.data_ptr(), d16.data_ptr(), dg.data_ptr(), dbeta.data_ptr(), rows, d, _s())
+    torch.cuda.synchronize()
+    assert (d32 - ar.grad).abs().max().item() < 2e-4 and (ar.grad - rr.grad).abs().max().item() == 0
+    assert (dg - gr.grad).abs().max().item() < 2e-3 and (dbeta - br.grad).abs().max().item() < 2e-3
+    assert (d16.float() - ar.grad).abs().max().item() < 5e-2
+
+
+def test_transpose_with_column_sums(device):
+    torch.manual_seed(2)
+    for rows, cols, ld in ((77, 130, 136), (256, 64, 64), (5, 10201, 10208)):
+        x = torch.zeros(rows, ld, device=device, dtype=torch.bfloat16)
+        x[:, :cols] = torch.randn(rows, cols, device=device)
+        ldo = (rows + 7) // 8 * 8
+        out = torch.full((cols, ldo), 7.0, device=device, dtype=torch.bfloat16)
+        colsum = torch.ones(cols, device=device)
+        cabi.call("cap_transpose_bf16", x.data_ptr(), ld, out.data_ptr(), ldo, colsum.data_ptr(), rows, cols, _s())
+        torch.cuda.synchronize()
+        assert torch.equal(out[:, :rows], x[:, :cols].t()) and (out[:, rows:] == 0).all()
+        assert (colsum - 1 - x[:, :cols].float().sum(0)).abs().max().item() < 1e-3
+
+
+def test_attention_backward_matches_autograd(device):
+    torch.manual_seed(3)
+    H, hd = 8, 512
+    for b, nq, nk, causal in ((3, 20, 20, True), (2, 16, 50, False), (2, 49, 49, False), (1, 128, 100, False)):
+        fused = nq == nk
+        if fused:   # fused q|k|v rows, as the projections produce them
+            qkv = _bf(torch.randn(b * nq, 3 * hd, device=device))
+            q, k, v = qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:]
+        else:
+            q = _bf(torch.randn(b * nq, hd, device=device))
+            kv = _bf(torch.randn(b * nk, 2 * hd, device=device))
+            k, v = kv[:, :hd], kv[:, hd:]
+        d_out = _bf(torch.randn(b * nq, hd, device=device) * 0.1)
+        key_pad = torch.rand(b, 1, nk, device=device) < 0.2
+        key_pad[:, :, 0] = False
+        if causal:
+            mask = (torch.triu(torch.ones(nq, nk, device=device, dtype=torch.bool), 1).unsqueeze(0) | key_pad).to(torch.uint8).contiguous()
+            mask_qs = nk
+        else:
+            mask, mask_qs = key_pad.to(torch.uint8).contiguous(), 0
+        dq, dk, dv = torch.zeros_like(q.contiguous()), torch.zeros_like(k.contiguous()), torch.zeros_like(v.contiguous())
+        if fused:
+            dqkv = torch.zeros_like(qkv)
+            dq, dk, dv = dqkv[:, :hd], dqkv[:, hd:2 * hd], dqkv[:, 2 * hd:]
+        elif True:
+            dkv = torch.zeros_like(kv)
+            dk, dv = dkv[:, :hd], dkv[:, hd:]
+        args = cabi.AttentionArgs(
+            q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=d_out.data_ptr(), q_bs=nq * q.stride(0), k_bs=nk * k.stride(0),
+            v_bs=nk * v.stride(0), o_bs=nq * hd, ldq=q.stride(0), ldk=k.stride(0), ldv=v.stride(0), ldo=hd, mask=mask.data_ptr(),
+            mask_bs=mask.shape[1] * nk, mask_qs=mask_qs, geometry=None, mem_k=None, mem_v=None, n_mem=0, B=b, H=H, nq=nq, nk=nk,
+            scale=1 / math.sqrt(64), sentinel=None, s_bs=0, lds=0)
+        cabi.call("cap_attention_backward", C.byref(args), d_out.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _s())
+        torch.cuda.synchronize()
+        qr, kr, vr = (t.float().reshape(b, -1, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True) for t in (q, k, v))
+        att = (qr @ kr.transpose(-1, -2)) / 8.0
+        att = att.masked_fill(mask.bool().view(b, 1, -1, nk), -math.inf)
+        o = torch.softmax(att, -1) @ vr
+        o.backward(d_out.float().view(b, nq, H, 64).permute(0, 2, 1, 3))
+        for name, got, ref in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dv, vr.grad)):
+            ref2 = ref.permute(0, 2, 1, 3).reshape(got.shape)
+            err = (got.float() - ref2).abs().max().item()
+            scale = ref2.abs().max().item()
+            assert err < 1.5e-2 * scale + 1e-4, (name, b, nq, nk, err, scale)
+
+
+def test_embedding_relu_axpy(device):
+    torch.manual_seed(4)
+    V, d, T, B, pad = 50, 512, 6, 5, 0
+    tokens = torch.randint(0, V, (B * T,), device=device)
+    tokens[::4] = pad
+    emb = torch.randn(V, d, device=device)
+    pos = torch.randn(T + 1, d, device=device)
+    o32 = torch.empty(B * T, d, device=device)
+    o16 = torch.empty(B * T, d, device=device, dtype=torch.bfloat16)
+    cabi.call("cap_train_embed_fwd", tokens.data_ptr(), emb.data_ptr(), pos.data_ptr(), T, pad, o32.data_ptr(), o16.data_ptr(), B * T, d, _s())
+    idx = torch.where(tokens == pad, torch.zeros_like(tokens), torch.arange(B * T, device=device) % T + 1)
+    ref = emb[tokens] + pos[idx]
+    assert torch.equal(o32, ref) and torch.equal(o16, ref.to(torch.bfloat16))
+    ga, gb = torch.randn(B * T, d, device=device), torch.randn(B * T, d, device=device)
+    d_emb = torch.zeros(V, d, device=device)
+    cabi.call("cap_train_embed_bwd", tokens.data_ptr(), ga.data_ptr(), gb.data_ptr(), pad, d_emb.data_ptr(), B * T, d, _s())
+    want = torch.zeros(V, d, device=device).index_add_(0, tokens, (ga + gb) * (tokens != pad).unsqueeze(1))
+    assert (d_emb - want).abs().max().item() < 1e-5 and d_emb[pad].abs().max().item() == 0
+    h = _bf(torch.randn(40, 2048, device=device))
+    dh = _bf(torch.randn(40, 2048, device=device))
+    want = torch.where(h > 0, dh, torch.zeros_like(dh))
+    cabi.call("cap_train_relu_bwd", dh.data_ptr(), h.data_ptr(), dh.numel(), _s())
+    assert torch.equal(dh, want)
+    x, y = torch.randn(1000, device=device), torch.randn(1000, device=device)
+    want = x + y
+    cabi.call("cap_axpy_f32", x.data_ptr(), y.data_ptr(), 1000, _s())
+    assert torch.equal(x, want)
+
+
+def test_xent_loss_and_gradient(device):
+    torch.manual_seed(5)
+    rows, V, ld, pad = 37, 1001, 1008, 0
+    logits = torch.zeros(rows, ld, device=device)
+    logits[:, :V] = torch.randn(rows, V, device=device) * 3
+    targets = torch.randint(1, V, (rows,), device=device)
+    targets[::5] = pad
+    stats = torch.empty(2, device=device)
+    dl = torch.full((rows, ld), 9.0, device=device, dtype=torch.bfloat16)
+    cabi.call("cap_train_xent", logits.data_ptr(), ld, targets.data_ptr(), pad, stats.data_ptr(), dl.data_ptr(), ld, rows, V, _s())
+    ref_in = logits[:, :V].clone().requires_grad_(True)
+    ref = F.nll_loss(F.log_softmax(ref_in, -1), targets, ignore_index=pad)
+    ref.backward()
+    assert stats[0].item() == (targets != pad).sum().item()
+    assert abs((stats[1] / stats[0]).item() - ref.item()) < 1e-4
+    assert (dl[:, :V].float() - ref_in.grad).abs().max().item() < 4e-3 * ref_in.grad.abs().max().item() + 1e-6
+    assert (dl[:, V:] == 0).all() and (dl[targets == pad] == 0).all()
+
+
+def test_adam_matches_torch(device):
+    torch.manual_seed(6)
+    n = 4099
+    p0 = torch.randn(n, device=device)
+    p = p0.clone()
+    m, v = torch.zeros(n, device=device), torch.zeros(n, device=device)
+    shadow = torch.empty(n, device=device, dtype=torch.bfloat16)
+    ref = p0.clone().requires_grad_(True)
+    optim = torch.optim.Adam([ref], lr=1.0, betas=(0.9, 0.98))
+    sched = torch.optim.lr_scheduler.LambdaLR(optim, lambda s: noam_factor(s, 512, 50))
+    for step in range(1, 5):
+        g = torch.randn(n, device=device) * (10.0 ** torch.randint(-6, 2, (n,), device=device).float())
+        g[::7] = 0
+        ref.grad = g.clone()
+        optim.step()
+        sched.step()
+        cabi.call("cap_train_adam", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), shadow.data_ptr(), n,
+                  1.0 * noam_factor(step - 1, 512, 50), 0.9, 0.98, 1e-8, step, _s())
+        torch.cuda.synchronize()
+        assert (p - ref.detach()).abs().max().item() < 2e-6 * max(1.0, (p0 - ref.detach()).abs().max().item() / 1e-3)
+        assert torch.equal(shadow, p.to(torch.bfloat16))
+    assert (p - p0).abs().max().item() > 0
+
+
+def _trainer_case(name, device):
+    case = TRAIN_CASES[name]
+    cfg = apply_overrides(ov.get_config(case["config"]), case)
+    cfg.MODEL.DEVICE = str(device)
+    vocab = synthetic.SyntheticVocab(case["vocab"], case["max_len"])
+    model = ov.build_model(cfg.MODEL, vocab).to(device)
+    weights = synthetic.load_synthetic_weights(model, case["seed"])
+    batches = synthetic.synth_train_batches(cfg.MODEL, case)
+    return case, cfg, vocab, model, weights, batches
+
+
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_training_step_matches_oracle(device, name):
+    case, cfg, vocab, model, weights, batches = _trainer_case(name, device)
+    with pytest.raises(NotImplementedError):
+        XETrainer(model, lr=case["lr"], warmup=case["warmup"])     # the YAML's DROPOUT is 0.1
+    trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], ignore_dropout=True)
+    o_final, o_losses, o_grads = oracle.xe_train_steps(
+        weights, cfg.MODEL, vocab, [(f, t, y, b) for _, f, t, y, b in batches], case["lr"], case["warmup"])
+
+    # ---- first step: loss and every parameter's gradient
+    _, feats, tokens, targets, _ = batches[0]
+    with torch.no_grad():
+        loss = trainer.loss_and_grads(feats.to(device).to(torch.bfloat16), tokens.to(device), targets.to(device))
+    torch.cuda.synchronize()
+    grads = {k: g.detach().float().cpu() for k, g in trainer.gradients().items()}
+    assert set(grads) == {k for k, g in o_grads.items() if g is not None}
+    worst, dot, n1, n2 = ("", 0.0), 0.0, 0.0, 0.0
+    for k, g in grads.items():
+        ref = o_grads[k]
+        rel = ((g - ref).norm() / ref.norm().clamp_min(1e-12)).item()
+        if rel > worst[1]:
+            worst = (k, rel)
+        dot, n1, n2 = dot + (g * ref).sum().item(), n1 + (g * g).sum().item(), n2 + (ref * ref).sum().item()
+    cos = dot / math.sqrt(n1 * n2)
+    pad_row = grads["decoder.word_emb.components.weight"][vocab.padding_idx]
+    print(f"[{name}] loss {loss.item():.5f} vs oracle {o_losses[0]:.5f}; gradients: cosine {cos:.6f}, worst relative L2 error "
+          f"{worst[1]:.4f} ({worst[0]}), {len(grads)} parameters")
+    assert abs(loss.item() - o_losses[0]) < TOL_LOSS
+    assert cos > TOL_GRAD_COS and worst[1] < TOL_GRAD_REL
+    assert pad_row.abs().max().item() == 0
+
+    # ---- consecutive optimizer steps from the same start
+    trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], ignore_dropout=True)
+    start = {k: v.detach().float().cpu().clone() for k, v in trainer.parameters().items()}
+    losses = []
+    for _, feats, tokens, targets, _ in batches:
+        losses.append(trainer.step(feats.to(device).to(torch.bfloat16), tokens.to(device), targets.to(device)))
+    torch.cuda.synchronize()
+    losses = [x.item() for x in losses]
+    print(f"[{name}] losses {['%.4f' % x for x in losses]} vs oracle {['%.4f' % x for x in o_losses]}")
+    assert all(abs(a - b) < TOL_LOSS for a, b in zip(losses, o_losses))
+    dot = n1 = n2 = 0.0
+    for k, v in trainer.parameters().items():
+        du, dr = v.detach().float().cpu() - start[k], o_final[k] - weights[k].float()
+        dot, n1, n2 = dot + (du * dr).sum().item(), n1 + (du * du).sum().item(), n2 + (dr * dr).sum().item()
+    cos_update = dot / math.sqrt(n1 * n2)
+    print(f"[{name}] cosine between the accumulated parameter updates and the oracle's: {cos_update:.4f} "
+          f"(Adam's first steps are sign-like: small gradients flip)")
+    assert n1 > 0 and cos_update > 0.8
+    trainer.sync_to_model()
+    assert torch.equal(model.state_dict()["decoder.fc.weight"].float(), trainer.parameters()["decoder.fc.weight"])
