@@ -27,9 +27,9 @@
 // fit: it goes through a row-major global scratch buffer and comes back through TMA as the streamed A operand of the
 // second FFN GEMM.  The fp32 residual stream (and the meshed decoder's fp32 side streams) live in global scratch
 // buffers in 16-byte-granule layout [granule][row] (coalesced for a thread-per-row reader; L2-resident).
-// CTA pairs: two CTAs of a cluster, each with its own 128-row tile, share every weight tile -- each stages HALF of it
-// (64 of the 128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256) over both shared memories and both CTAs
-// drain their own accumulator rows: the same 64 KB ring keeps 8 k-block stages in flight instead of 4.
+// CTA pairs: two CTAs of a cluster, each with its own 128-row tile, share every weight tile -- each stages HALF of a
+// 256-row tile pair (128 rows), the leader issues tcgen05.mma.cta_group::2 (M = 256, N = 256) over both shared
+// memories and both CTAs drain their own accumulator rows: per CTA the same 64 KB ring feeds twice the tensor work.
 //
 // (Removed in round 2, after measurement: the one-kernel-per-step mode that also ran both attention phases on the
 // CTA's CUDA cores -- parity-green but 2.4x slower per tile than chains + stand-alone attention, because a chain CTA
@@ -81,8 +81,14 @@ constexpr uint32_t OFF_BETA = OFF_GAMMA + FD * 4;
 constexpr uint32_t OFF_STAT = OFF_STAGE;
 static_assert(2 * 2 * TILE_ROWS * 4 <= STAGE_BYTES_ALL, "row statistics must fit the staging area");
 constexpr uint32_t OFF_BARS = OFF_BETA + FD * 4;
-constexpr int NB_PAIR = 8;            // CTA pairs stage HALF of every weight tile: the same 64 KB hold 8 k-block stages
-constexpr uint32_t B_STAGE_BYTES_PAIR = 64 * 64 * 2;
+// CTA pairs issue tcgen05.mma with N = 256 (two adjacent 128-column tiles per instruction): each CTA stages its 128 of
+// the 256 weight rows of a k-block, 16 KB per stage like a single CTA.  (Round 2 first ran pairs with N = 128 and 64-row
+// half tiles, 8 stages of 8 KB: the issuer warp then needed ~370 cycles of descriptor arithmetic, R2UR moves and barrier
+// traffic per stage for 256 cycles of tensor work -- ncu showed the tensor pipe active 45 % of an FFN chain while the
+// issuer accounted 66 % of its time to issuing.  Twice the work per issued instruction puts the pipe back in front.)
+constexpr int NB_PAIR = 4;
+constexpr uint32_t B_STAGE_BYTES_PAIR = 128 * 64 * 2;
+constexpr int TILE_STEP_PAIR = 2;     // 128-column tiles per MMA instruction
 constexpr int NUM_BARS = 2 * NB_PAIR + 2 * A_SLOTS + 2 + 2 + 4;
 constexpr uint32_t OFF_TMEM = OFF_BARS + NUM_BARS * 8;
 constexpr uint32_t FUSED_SMEM = OFF_TMEM + 16;
@@ -138,8 +144,7 @@ struct FusedParams {
     CUtensorMap map_vocab;  // [V][512]
     CUtensorMap map_h;      // [tiles * 128][2048] FFN hidden scratch
     CUtensorMap map_att;    // [levels * max_rows][512] attention outputs of the stand-alone attention kernels
-    CUtensorMap map_w512_h, map_w2_h, map_vocab_h;   // the three weight maps with 64-row boxes (CTA pairs)
-    CUtensorMap map_wvis, map_wvis_h;   // encoder: vision projection [512][d_feature]
+    CUtensorMap map_wvis;   // encoder: vision projection [512][d_feature]
     CUtensorMap map_feat;    // encoder: raw features [rows][d_feature], the streamed A operand of the vision projection
     int pos_rows;            // encoder: visual tokens per image (rows of the position table)
     JobDesc jobs[MAX_JOBS];
@@ -264,9 +269,11 @@ __device__ __forceinline__ void publish_a(WorkerCtx& c) {
 // Epilogue of one 256-column chunk of a plain projection: + bias (ReLU for the hidden layer), bf16, to global rows.
 // `bias_reg` carries this thread's bias value of the chunk across calls: the value of chunk c + 1 is requested
 // while chunk c is drained, so the global-load latency is off the per-chunk critical path.
-// (Measured in round 2 and removed: software-pipelining the four tcgen05.ld of a warp one group ahead of the math
-// changed nothing -- 84.5 k vs 85.2 k captions/s -- and storing the bf16 rows straight from registers instead of
-// through the staging tile was slower, 81.9 k: the store sectors cost more than the shared-memory round trip.)
+// The four tcgen05.ld of a warp run one group ahead of the math.  (First measured while the MMA issuer was the
+// bottleneck, where it changed nothing -- 84.5 k vs 85.2 k captions/s; with N = 256 instructions the chains wait for
+// free accumulators instead, and the epilogue is on the critical path.  Storing the bf16 rows straight from registers
+// instead of through the staging tile was slower, 81.9 k: the store sectors cost more than the shared-memory round
+// trip.)
 __device__ __forceinline__ void epilogue_store(WorkerCtx& c, const FusedParams& p, const JobDesc& job, int chunk_idx,
                                                int n_chunks, float& bias_reg) {
     const int flags = job.flags;   // job fields are read once: the asm wrappers' memory clobbers would reload them
@@ -288,12 +295,16 @@ __device__ __forceinline__ void epilogue_store(WorkerCtx& c, const FusedParams& 
     const float relu_floor = (flags & JF_RELU) ? 0.f : -INFINITY;   // one FMNMX either way, no branch in the loop
     const int rows_valid = (flags & JF_WHOLE_TILES) ? 32 : c.rows_valid_warp;   // scratch buffers hold whole tiles
     uint8_t* const tile_base = reinterpret_cast<uint8_t*>(dst + static_cast<size_t>(c.r0 + c.quad * 32) * ld_dst + chunk_idx * 256);
-#pragma unroll 1
+    // the tcgen05.ld of group i + 1 is in flight while group i is converted and stored
+    const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
+    uint32_t vv[2][32];
+    tmem_ld_32x32b_x32(taddr, vv[0]);
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int colc = (c.half * 4 + i) * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
-        tmem_ld_wait();
+        uint32_t* v = vv[i & 1];
+        tmem_ld_wait_on(v);
+        if (i + 1 < 4) tmem_ld_32x32b_x32(taddr + (i + 1) * 32, vv[(i + 1) & 1]);
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -608,13 +619,15 @@ __device__ __forceinline__ void epilogue_vocab_chunk(WorkerCtx& c, const FusedPa
     const int b = acquire_acc(c, 2);
     const int row = c.quad * 32 + c.lane;
     const int grow = c.r0 + row;
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
+    const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + c.half * 128;
+    uint32_t vv[2][32];
+    tmem_ld_32x32b_x32(taddr, vv[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // group i + 1 is in flight while group i is reduced and stored
         const int colc = (c.half * 4 + i) * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16) + b * 256 + colc, v);
-        tmem_ld_wait();
-        vocab_group(c, p, chunk_idx, colc, grow, v, top);
+        tmem_ld_wait_on(vv[i & 1]);
+        if (i + 1 < 4) tmem_ld_32x32b_x32(taddr + (i + 1) * 32, vv[(i + 1) & 1]);
+        vocab_group(c, p, chunk_idx, colc, grow, vv[i & 1], top);
     }
     release_acc(c, 2, b);
 }
@@ -631,6 +644,7 @@ template <bool PAIR, bool TRACE = false>
 __global__ void __launch_bounds__(PAIR ? CHAIN_THREADS : CHAIN_THREADS, 1) __maxnreg__(PAIR ? CHAIN_MAXNREG : CHAIN_MAXNREG)
 decode_chain_kernel(const __grid_constant__ FusedParams p) {
     constexpr int NBX = PAIR ? NB_PAIR : NB;
+    constexpr int TSTEP = PAIR ? TILE_STEP_PAIR : 1;
     constexpr uint32_t BST = PAIR ? B_STAGE_BYTES_PAIR : B_STAGE_BYTES;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -709,19 +723,17 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
         const uint64_t keep_policy = l2_policy_evict_last();   // weights: shared by every tile of every batch in flight
         for (int ji = 0; ji < n_jobs; ++ji) {
             const JobDesc& job = p.jobs[ji];
-            const CUtensorMap* map = job.wmap == 0 ? (PAIR ? &p.map_w512_h : &p.map_w512)
-                                   : job.wmap == 1 ? (PAIR ? &p.map_w2_h : &p.map_w2)
-                                   : job.wmap == 2 ? (PAIR ? &p.map_vocab_h : &p.map_vocab)
-                                                   : (PAIR ? &p.map_wvis_h : &p.map_wvis);
+            const CUtensorMap* map = job.wmap == 0 ? &p.map_w512 : job.wmap == 1 ? &p.map_w2 : job.wmap == 2 ? &p.map_vocab : &p.map_wvis;
             const int chunk = job.chunk, kblocks = job.kblocks;   // read once (see epilogue_store)
             const int nch = job.ntiles / chunk;
-            const int row_base = job.row0 + (PAIR ? static_cast<int>(rank) * 64 : 0);
+            // pair: this CTA stages rows [rank * 128, rank * 128 + 128) of every 256-row tile pair
+            const int row_base = job.row0 + (PAIR ? static_cast<int>(rank) * 128 : 0);
             const bool stream = job.a_src == JA_STREAM_HIDDEN || job.a_src == JA_STREAM_FEATURES;
             const bool from_hidden = job.a_src == JA_STREAM_HIDDEN;
             const CUtensorMap* amap = from_hidden ? &p.map_h : &p.map_feat;
             for (int c = 0; c < nch; ++c) {
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    for (int j = 0; j < chunk; ++j) {
+                    for (int j = 0; j < chunk; j += TSTEP) {
                         const uint32_t s = bcount % NBX;
                         TRACED_WAIT(tr_b, mbar_wait(&b_empty[s], ((bcount / NBX) & 1) ^ 1));
                         if (elect_one_sync()) {
@@ -772,7 +784,7 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
     } else if (warp == 1 && leader) {
         // ------------------------------------------------------------------ MMA issuer (pair: the leader's only)
         // Uniform control flow for the whole warp; the elected lane issues tcgen05.mma / tcgen05.commit.
-        constexpr uint32_t idesc = make_instr_desc(PAIR ? 256 : 128, 128);
+        constexpr uint32_t idesc = make_instr_desc(PAIR ? 256 : 128, PAIR ? 256 : 128);
         auto wait_consumers_at = [](uint64_t* bar, uint32_t parity, int line) {
             if constexpr (PAIR) mbar_wait_cluster_impl(bar, parity, line); else mbar_wait_impl(bar, parity, line);
         };
@@ -820,7 +832,7 @@ decode_chain_kernel(const __grid_constant__ FusedParams p) {
                         a_tile = A_buf + kb * A_KB_BYTES;
                     }
                     const uint64_t a_desc = make_smem_desc(a_tile);
-                    for (int j = 0; j < chunk; ++j) {
+                    for (int j = 0; j < chunk; j += TSTEP) {
                         const uint32_t s = bcount % NBX;
                         TRACED_WAIT(tr_b, mbar_wait(&b_full[s], (bcount / NBX) & 1));
                         tcgen05_fence_after();
@@ -1123,9 +1135,6 @@ extern "C" int cap_fused_create(const cap_fused_desc* d, cap_fused_decoder** out
     int rc = cap_gemm::make_tmap(&p.map_w512, w512, L * rpl, FD, FD, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, w2, L * FD, FDFF, FDFF, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, d->w_vocab, d->vocab, FD, FD, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, w512, L * rpl, FD, FD, 64);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, w2, L * FD, FDFF, FDFF, 64);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab_h, d->w_vocab, d->vocab, FD, FD, 64);
     if (rc != CAP_OK) return fail(rc);
     p.tokens = d->tokens; p.word_emb = static_cast<const bf16*>(d->word_emb); p.word_pos = d->word_pos; p.pad_idx = d->pad_idx;
     p.padflag = d->padflag;
@@ -1451,15 +1460,11 @@ extern "C" int cap_enc_chains_create(const cap_enc_chain_desc* d, cap_enc_chains
     }
     const int rows512 = d->n_layers * ENC_ROWS_PER_LAYER + d->n_kv * 2 * FD;
     int rc = cap_gemm::make_tmap(&p.map_w512, f->stacked->w512, rows512, FD, FD, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w512_h, f->stacked->w512, rows512, FD, FD, 64);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2, f->stacked->w2, d->n_layers * FD, FDFF, FDFF, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_w2_h, f->stacked->w2, d->n_layers * FD, FDFF, FDFF, 64);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_wvis, d->w_vis, FD, d->d_feature, d->d_feature, 128);
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_wvis_h, d->w_vis, FD, d->d_feature, d->d_feature, 64);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_feat, d->feats, d->max_rows, d->d_feature, d->d_feature, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_att, d->att_in, d->max_rows, FD, FD, 128);
     if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab, f->stacked->w512, rows512, FD, FD, 128);     // unused by encoder jobs: any valid map
-    if (rc == CAP_OK) rc = cap_gemm::make_tmap(&p.map_vocab_h, f->stacked->w512, rows512, FD, FD, 64);
     if (rc != CAP_OK) return fail(rc);
     const size_t tiles = f->tiles;
     void *res = nullptr, *hb = nullptr;

@@ -597,9 +597,14 @@ def xe_loss(w: Weights, model_cfg, vocab, feats: Tensor, tokens: Tensor, targets
     return F.nll_loss(logp.reshape(-1, logp.shape[-1]), targets.reshape(-1), ignore_index=vocab.padding_idx)
 
 
-def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int):
+def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int, bf16_linear_weights: bool = False):
     """Runs len(batches) optimizer steps in place on a float32 copy of `w`.  batches: (feats, tokens, targets[, boxes]).
-    Returns (weights after the last step, [loss per step], gradients of the FIRST step)."""
+    Returns (weights after the last step, [loss per step], gradients of the FIRST step).
+
+    ``bf16_linear_weights`` is the mixed-precision yardstick for the GPU trainer: the forward and backward passes see
+    every Linear weight rounded to bf16 (straight-through: the gradient is applied to the fp32 master weight), which is
+    what a bf16 shadow copy of fp32 master weights does.  The synthetic start weights are bf16-exact, so the first step
+    is unaffected; from the second step on the updated weights no longer are."""
     params = {k: v.detach().clone().float().requires_grad_(k not in FROZEN) for k, v in w.items()}
     trainable = [p for p in params.values() if p.requires_grad]
     optim = torch.optim.Adam(trainable, lr=lr, betas=(0.9, 0.98))
@@ -610,7 +615,11 @@ def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int
         feats, tokens, targets = batch[:3]
         boxes = batch[3] if len(batch) > 3 else None
         optim.zero_grad()
-        loss = xe_loss(params, model_cfg, vocab, feats, tokens, targets, boxes)
+        seen = params
+        if bf16_linear_weights:
+            seen = {k: (p + (p.detach().to(torch.bfloat16).float() - p.detach()))
+                    if (p.dim() == 2 and k.endswith(".weight") and "_emb" not in k) else p for k, p in params.items()}
+        loss = xe_loss(seen, model_cfg, vocab, feats, tokens, targets, boxes)
         loss.backward()
         if params[emb].grad is not None:
             params[emb].grad[pad].zero_()          # nn.Embedding(padding_idx=pad)

@@ -226,6 +226,11 @@ def test_training_step_matches_oracle(device, name):
     worst, dot, n1, n2 = ("", 0.0), 0.0, 0.0, 0.0
     for k, g in grads.items():
         ref = o_grads[k]
+        if k.endswith("fc_k.bias"):
+            # mathematically zero (a key bias shifts every logit of a query by the same amount): the reference holds
+            # fp32 rounding noise here, the GPU path bf16 rounding noise -- both tiny next to the query bias' gradient
+            assert g.norm().item() < 0.05 * grads[k.replace("fc_k", "fc_q")].norm().item(), k
+            continue
         rel = ((g - ref).norm() / ref.norm().clamp_min(1e-12)).item()
         if rel > worst[1]:
             worst = (k, rel)
@@ -238,7 +243,12 @@ def test_training_step_matches_oracle(device, name):
     assert cos > TOL_GRAD_COS and worst[1] < TOL_GRAD_REL
     assert pad_row.abs().max().item() == 0
 
-    # ---- consecutive optimizer steps from the same start
+    # ---- consecutive optimizer steps from the same start.  From the second step on the GPU's GEMMs read the bf16
+    # shadow of weights that are no longer bf16-exact; the yardstick for that is the same oracle with every Linear weight
+    # rounded to bf16 in the forward / backward pass (straight-through to the fp32 master weights).  The pure fp32
+    # losses are printed next to it: with Adam's sign-like first steps the two differ visibly (std_region: 9.70 vs 9.91).
+    m_final, m_losses, _ = oracle.xe_train_steps(
+        weights, cfg.MODEL, vocab, [(f, t, y, b) for _, f, t, y, b in batches], case["lr"], case["warmup"], bf16_linear_weights=True)
     trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], ignore_dropout=True)
     start = {k: v.detach().float().cpu().clone() for k, v in trainer.parameters().items()}
     losses = []
@@ -246,15 +256,17 @@ def test_training_step_matches_oracle(device, name):
         losses.append(trainer.step(feats.to(device).to(torch.bfloat16), tokens.to(device), targets.to(device)))
     torch.cuda.synchronize()
     losses = [x.item() for x in losses]
-    print(f"[{name}] losses {['%.4f' % x for x in losses]} vs oracle {['%.4f' % x for x in o_losses]}")
-    assert all(abs(a - b) < TOL_LOSS for a, b in zip(losses, o_losses))
+    print(f"[{name}] losses {['%.4f' % x for x in losses]} vs the oracle with bf16 Linear weights {['%.4f' % x for x in m_losses]} "
+          f"(fp32 weights: {['%.4f' % x for x in o_losses]})")
+    assert abs(m_losses[0] - o_losses[0]) < 1e-6          # the start weights are bf16-exact: same first step
+    assert all(abs(a - b) < TOL_LOSS for a, b in zip(losses, m_losses))
     dot = n1 = n2 = 0.0
     for k, v in trainer.parameters().items():
-        du, dr = v.detach().float().cpu() - start[k], o_final[k] - weights[k].float()
+        du, dr = v.detach().float().cpu() - start[k], m_final[k] - weights[k].float()
         dot, n1, n2 = dot + (du * dr).sum().item(), n1 + (du * du).sum().item(), n2 + (dr * dr).sum().item()
     cos_update = dot / math.sqrt(n1 * n2)
     print(f"[{name}] cosine between the accumulated parameter updates and the oracle's: {cos_update:.4f} "
           f"(Adam's first steps are sign-like: small gradients flip)")
-    assert n1 > 0 and cos_update > 0.8
+    assert n1 > 0 and cos_update > 0.9
     trainer.sync_to_model()
     assert torch.equal(model.state_dict()["decoder.fc.weight"].float(), trainer.parameters()["decoder.fc.weight"])
