@@ -583,6 +583,10 @@ def run_gpu_arm(args):
                              "full-size parity tests are tests/test_gpu_fullsize.py"}
         small.close()
 
+    others = None
+    if world == 1 and args.workload == "standard_grid" and not args.no_others and not args.batch:
+        others = other_workloads(args, progress)   # the GPU is idle now; each runs as its own process
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": total_ms / steps_timed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -603,9 +607,33 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches_per_step * steps_timed),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu_base, "parity_sample": parity, "clocks": clocks.summary(),
+        "other_workloads": others,
     }
     print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
+
+
+def other_workloads(args, progress):
+    """The same measurement for the other single-GPU configurations of BASELINE.json (the meshed-memory transformer at
+    config C's per-GPU batch, the object-relation transformer of config D), each in its own process after this one has
+    finished timing; their headline figures ride along in the default line (the full lines: --workload NAME)."""
+    import subprocess
+    out = {}
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    for name in ("meshed_memory", "object_relation"):
+        progress(f"other workload: {name}")
+        cmd = [sys.executable, str(Path(__file__).resolve()), "--workload", name, "--skip-cpu", "--no-others", "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--streams", str(args.streams), "--hang-seconds", str(args.hang_seconds)]
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=min(240.0, max(30.0, args.hang_seconds - 5)), env=env)
+            d = json.loads(res.stdout.strip().splitlines()[-1])
+            out[name] = {"value": d["value"], "e2e": d["e2e"]["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                         "workload": d["config"]["workload"], "roofline_frac": d["roofline"]["frac"],
+                         "step_frac_of_tensor_peak": d["roofline"]["step_frac_of_tensor_peak"],
+                         "gpu_launches_per_step": d["gpu_launches_per_step"]}
+        except Exception as err:   # noqa: BLE001 -- an extra figure must not take the headline line down
+            out[name] = {"error": f"{type(err).__name__}: {err}"[:300]}
+    return out
 
 
 def install_watchdog(seconds: float):
@@ -658,6 +686,8 @@ def main():
     ap.add_argument("--hang-seconds", type=float, default=90.0,
                     help="watchdog: dump diagnostics and exit when no phase finishes within this many seconds")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true",
+                    help="do not append the other single-GPU workloads' figures (other_workloads) to the default line")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=40)
     args = ap.parse_args()

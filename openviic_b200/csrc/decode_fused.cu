@@ -369,28 +369,39 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     float4* res_out = reinterpret_cast<float4*>(job.res_out) + tile_off;
     const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.quad * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        const int c0 = (c.half * 8 + i) * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
-        float4 r[8];   // requested while the TMEM load is in flight
+    {
+        // the residual granules of group i + 1 are requested while group i is summed and parked, and pass B requests the
+        // tcgen05.ld of group i + 1 as soon as group i has been normalised (the epilogue is a serial point of the chain --
+        // no GEMM of this tile can start before it ends -- so its latency is the chain's latency; double-buffering the
+        // accumulator registers as the store epilogues do spills at 128 registers)
+        const int cbase = c.half * 256;
+        float4 r[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-            r[g] = has_res ? res_in[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS] : make_float4(0.f, 0.f, 0.f, 0.f);
-        tmem_ld_wait();
+            r[g] = has_res ? res_in[static_cast<size_t>(cbase / 4 + g) * TILE_ROWS] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            const int c0 = cbase + i * 32;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const float y0 = __uint_as_float(v[4 * g]) + c.s_bias[c0 + 4 * g] + r[g].x;
-            const float y1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r[g].y;
-            const float y2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r[g].z;
-            const float y3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r[g].w;
-            s1 += (y0 + y1) + (y2 + y3);
-            s2 = fmaf(y0, y0, s2); s2 = fmaf(y1, y1, s2); s2 = fmaf(y2, y2, s2); s2 = fmaf(y3, y3, s2);
-            v[4 * g] = __float_as_uint(y0); v[4 * g + 1] = __float_as_uint(y1);
-            v[4 * g + 2] = __float_as_uint(y2); v[4 * g + 3] = __float_as_uint(y3);
+            for (int g = 0; g < 8; ++g) {
+                const float y0 = __uint_as_float(v[4 * g]) + c.s_bias[c0 + 4 * g] + r[g].x;
+                const float y1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r[g].y;
+                const float y2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r[g].z;
+                const float y3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r[g].w;
+                s1 += (y0 + y1) + (y2 + y3);
+                s2 = fmaf(y0, y0, s2); s2 = fmaf(y1, y1, s2); s2 = fmaf(y2, y2, s2); s2 = fmaf(y3, y3, s2);
+                v[4 * g] = __float_as_uint(y0); v[4 * g + 1] = __float_as_uint(y1);
+                v[4 * g + 2] = __float_as_uint(y2); v[4 * g + 3] = __float_as_uint(y3);
+            }
+            if (i + 1 < 8 && has_res) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) r[g] = res_in[static_cast<size_t>((c0 + 32) / 4 + g) * TILE_ROWS];
+            }
+            tmem_st_32x32b_x32(taddr + c0, v);
         }
-        tmem_st_32x32b_x32(taddr + c0, v);
     }
     tmem_st_wait();
     c.s_stat[c.half * TILE_ROWS + row] = s1;
@@ -405,16 +416,17 @@ __device__ __forceinline__ void epilogue_layernorm(WorkerCtx& c, const FusedPara
     // encoder extras: + pos[row % tokens] after the LayerNorm (encoders.py:36), and a row-major bf16 copy of the result
     const float4* pos = job.pos != nullptr ? reinterpret_cast<const float4*>(job.pos + static_cast<size_t>(live ? grow % p.pos_rows : 0) * FD) : nullptr;
     uint4* ln_out = (job.ln_out != nullptr && live) ? reinterpret_cast<uint4*>(job.ln_out + static_cast<size_t>(grow) * FD) : nullptr;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c.half * 256, v);
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
         const int c0 = (c.half * 8 + i) * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
-        tmem_ld_wait();
+        tmem_ld_wait_on(v);
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             f[j] = zero ? 0.f : (__uint_as_float(v[j]) - mean) * rstd * c.s_gamma[c0 + j] + c.s_beta[c0 + j];
+        if (i + 1 < 8) tmem_ld_32x32b_x32(taddr + c0 + 32, v);   // v is dead: the next group loads while this one is stored
         if (pos != nullptr && !zero) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
