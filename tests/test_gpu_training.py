@@ -270,3 +270,30 @@ def test_training_step_matches_oracle(device, name):
     assert n1 > 0 and cos_update > 0.9
     trainer.sync_to_model()
     assert torch.equal(model.state_dict()["decoder.fc.weight"].float(), trainer.parameters()["decoder.fc.weight"])
+
+
+def test_training_step_at_the_benchmarked_size(device):
+    """The same first-step comparison at config B's full size (256 images x 49 visual tokens, captions of 20 tokens,
+    vocabulary 10201): loss and the full gradient vector against the oracle's autograd (about a minute of CPU work)."""
+    import bench
+    cfg, vocab, model, weights = bench.build_model("standard_grid", device)
+    n, T, V, B = bench.WORKLOADS["standard_grid"][1], bench.MAX_LEN, bench.VOCAB, 256
+    feats = synthetic.bf16_round(synthetic.synth_features(B, n, 2048, 4242, ragged=False))
+    tokens, targets = synthetic.synth_captions(B, T, V, 4242)
+    trainer = XETrainer(model, lr=1.0, warmup=10000, ignore_dropout=True)
+    with torch.no_grad():
+        loss = trainer.loss_and_grads(feats.to(device).to(torch.bfloat16), tokens.to(device), targets.to(device))
+    torch.cuda.synchronize()
+    _, o_losses, o_grads = oracle.xe_train_steps(weights, cfg.MODEL, vocab, [(feats, tokens, targets)], 1.0, 10000)
+    dot = n1 = n2 = 0.0
+    worst = ("", 0.0)
+    for k, g in trainer.gradients().items():
+        g, ref = g.detach().float().cpu(), o_grads[k]
+        dot, n1, n2 = dot + (g * ref).sum().item(), n1 + (g * g).sum().item(), n2 + (ref * ref).sum().item()
+        if not k.endswith("fc_k.bias"):
+            rel = ((g - ref).norm() / ref.norm().clamp_min(1e-12)).item()
+            worst = max(worst, (k, rel), key=lambda kv: kv[1])
+    cos = dot / math.sqrt(n1 * n2)
+    print(f"[full size, {B} images] loss {loss.item():.5f} vs oracle {o_losses[0]:.5f}; gradient cosine {cos:.6f}, worst relative "
+          f"L2 error {worst[1]:.4f} ({worst[0]})")
+    assert abs(loss.item() - o_losses[0]) < TOL_LOSS and cos > TOL_GRAD_COS and worst[1] < TOL_GRAD_REL
