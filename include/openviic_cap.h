@@ -495,6 +495,12 @@ int cap_train_embed_bwd(const int64_t* tokens, const float* g_a, const float* g_
  * stats[0]); dlogits bf16 [rows][ldd] = (softmax - onehot) / stats[0], zero for ignored rows and columns >= V. */
 int cap_train_xent(const float* logits, int ld, const int64_t* targets, int ignore_index, float* stats, void* dlogits,
                    int ldd, int rows, int V, cap_stream_t stream);
+/* Dropout with a counter-based mask, in place: x[i] = hash(i, seed, site) >= threshold ? x[i] * scale : 0 (threshold =
+ * floor(p * 2^32), scale = 1 / (1 - p)); the backward pass calls it on the gradient with the same (seed, site).  The
+ * hash is restated in oracle/caption_oracle.py (dropout_keep).  nn.Dropout at vision_embeddings.py:18,
+ * attentions.py:308, positionwise_feed_forward.py:24-25. */
+int cap_train_dropout(void* x, int dtype, int64_t count, unsigned int threshold, float scale, unsigned int seed,
+                      unsigned int site, cap_stream_t stream);
 /* torch.optim.Adam (no weight decay) on flat fp32 buffers, step >= 1, and the bf16 copy of the new parameters. */
 int cap_train_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                    int64_t count, float lr, float beta1, float beta2, float eps, int step, cap_stream_t stream);

@@ -508,6 +508,32 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------ dropout
+// x[i] = keep(i) ? x[i] * scale : 0, in place, with keep(i) = hash(i, seed, site) >= threshold: a counter-based mask,
+// so the backward pass regenerates it from (seed, site) instead of storing it, and the oracle (and the patched
+// reference of oracle/ref_harness/gen_golden_train.py) can generate the very same mask on the CPU.  The reference's
+// sites are nn.Dropout modules (vision_embeddings.py:18, attentions.py:308, positionwise_feed_forward.py:24-25); `site`
+// is the CRC-32 of the module's qualified name.
+__device__ __forceinline__ uint32_t dropout_hash(uint32_t idx, uint32_t seed, uint32_t site) {
+    uint32_t x = idx * 0x9E3779B1u + seed * 0x85EBCA77u + site * 0xC2B2AE3Du;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+    return x;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(T* __restrict__ x, size_t n, uint32_t threshold, float scale, uint32_t seed, uint32_t site) {
+    pdl_prologue();
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const bool keep = dropout_hash(static_cast<uint32_t>(i), seed, site) >= threshold;
+        float v = 0.f;
+        if (keep) {
+            if constexpr (sizeof(T) == 2) v = __bfloat162float(x[i]) * scale; else v = x[i] * scale;
+        }
+        if constexpr (sizeof(T) == 2) x[i] = __float2bfloat16(v); else x[i] = v;
+    }
+}
+
 inline int grid_for(size_t items, int block) {
     const size_t g = (items + block - 1) / block;
     return static_cast<int>(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -630,4 +656,18 @@ extern "C" int cap_train_adam(float* params, const float* grads, float* exp_avg,
                       inv_bc2_sqrt, eps);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("adam_kernel");
+}
+
+extern "C" int cap_train_dropout(void* x, int dtype, int64_t count, unsigned int threshold, float scale, unsigned int seed,
+                                 unsigned int site, cap_stream_t stream) {
+    CAP_REQUIRE(x && count > 0 && count <= 0xFFFFFFFFll, "cap_train_dropout: 1 .. 2^32 - 1 elements");
+    CAP_REQUIRE(dtype == CAP_BF16 || dtype == CAP_F32, "cap_train_dropout: bf16 or fp32");
+    const size_t n = static_cast<size_t>(count);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CAP_BF16)
+        CAP_LAUNCH(dropout_kernel<bf16>, grid_for(n, 256), 256, 0, s, static_cast<bf16*>(x), n, threshold, scale, seed, site);
+    else
+        CAP_LAUNCH(dropout_kernel<float>, grid_for(n, 256), 256, 0, s, static_cast<float*>(x), n, threshold, scale, seed, site);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("dropout_kernel");
 }

@@ -68,7 +68,13 @@ class BaseTransformer(Module):
                 self._engine = CaptionEngine(self.model_config, self.vocab, self.state_dict(),
                                              next(self.parameters()).device)
                 self._engine_key = key
-            else:  # same weights, larger shapes: rebuild (reservations are fixed-size)
+            else:
+                # same weights, larger shapes: rebuild (reservations are fixed-size) at the element-wise maximum of the
+                # old and the new request, so that batches of ragged sizes grow the reservation monotonically instead
+                # of rebuilding the engine every time n or the batch changes
+                old = self._engine.reserved
+                if old is not None and old[2] == beam_size:
+                    batch_size, n_tokens = max(batch_size, old[0]), max(n_tokens, old[1])
                 self._engine.close()
                 self._engine = CaptionEngine(self.model_config, self.vocab, self.state_dict(),
                                              next(self.parameters()).device)

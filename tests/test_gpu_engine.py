@@ -191,6 +191,17 @@ def test_engine_rejects_bad_calls(device):
         CaptionEngine(cfg.MODEL, vocab, broken, device)
 
 
+def test_engine_reservation_grows_monotonically(device):
+    """Ragged batches must not rebuild the engine back and forth: a request that does not fit rebuilds at the
+    element-wise maximum of the old and the new shape (base_transformer.py engine())."""
+    case, cfg, vocab, model, weights, field, feats, boxes = load_case("std_grid", device)
+    first = model.engine(4, 30, 5)
+    assert first.reserved == (4, 30, 5)
+    second = model.engine(2, 40, 5)
+    assert second is not first and second.reserved == (4, 40, 5)
+    assert model.engine(4, 30, 5) is second and model.engine(3, 40, 5) is second
+
+
 def test_graph_replay_follows_the_number_of_visual_tokens(device):
     """The captured beam search bakes n into its launches: a later batch with the same B but another n must re-capture
     (the replayed graph would otherwise read cross K|V and the mask with the old n) -- ADVICE r1, engine.cu graph key."""
