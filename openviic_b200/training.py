@@ -14,14 +14,20 @@ its gradient in ``cap_train_xent``; the update in ``cap_train_adam``.  torch sup
 Precision: fp32 master weights, Adam moments, gradients, residual stream, LayerNorm and loss; bf16 GEMM / attention
 operands (a bf16 shadow copy of the weights is rewritten by the optimizer kernel) -- the mixed-precision recipe.
 
-Dropout: the reference trains with DROPOUT = 0.1; this step is the p = 0 computation (the deterministic part, which is
-what can be pinned against the reference); ``XETrainer`` refuses other values unless ``ignore_dropout=True``.
+Dropout: the reference's nn.Dropout modules (vision_embeddings.py:18, attentions.py:308,
+positionwise_feed_forward.py:24-25) draw from torch's generator.  Here the same sites, probabilities and scaling run on a
+counter-based mask (``cap_train_dropout``: element i of the tensor at the module named ``site`` is kept iff
+hash(i, seed, crc32(site)) >= p * 2^32), regenerated in the backward pass instead of stored; ``dropout_seed`` + the step
+number seeds each step.  The oracle restates the hash, and the fixture generator pins it against the real reference with
+its Dropout modules' forward wrapped to use the same mask.  Without a seed ``XETrainer`` refuses configs with dropout
+unless ``ignore_dropout=True`` (the p = 0 computation).
 """
 
 from __future__ import annotations
 
 import ctypes as C
 import math
+import zlib
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -56,7 +62,7 @@ class _Linear:
 
 class XETrainer:
     def __init__(self, model, lr: float = 1.0, warmup: int = 10000, betas: Tuple[float, float] = (0.9, 0.98),
-                 eps: float = 1e-8, ignore_dropout: bool = False):
+                 eps: float = 1e-8, ignore_dropout: bool = False, dropout_seed: Optional[int] = None):
         cfg = model.model_config
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
@@ -71,9 +77,11 @@ class XETrainer:
             raise NotImplementedError("XETrainer covers the standard transformer (FeatureEmbedding, Encoder, Decoder, plain "
                                       "scaled dot-product attention); other registry variants have no backward kernels")
         drops = [cfg.VISION_EMBEDDING.DROPOUT] + [a.DROPOUT for a in att_cfgs]
-        if any(float(p) != 0.0 for p in drops) and not ignore_dropout:
-            raise NotImplementedError("the training step is the DROPOUT = 0 computation; pass ignore_dropout=True to run a "
-                                      "config with dropout as if it were 0")
+        if any(float(p) != 0.0 for p in drops) and dropout_seed is None and not ignore_dropout:
+            raise NotImplementedError("this config trains with dropout: pass dropout_seed=<int> (counter-based masks), or "
+                                      "ignore_dropout=True to run it as if DROPOUT were 0")
+        self.dropout_seed = None if ignore_dropout else dropout_seed
+        self.p_vision, self.p_enc, self.p_self, self.p_cross = (float(p) for p in drops)
         self.model, self.vocab = model, model.vocab
         self.d, self.heads, self.dff = enc.D_MODEL, enc.SELF_ATTENTION.HEAD, enc.SELF_ATTENTION.D_FF
         self.enc_layers, self.dec_layers = enc.LAYERS, dec.LAYERS
@@ -213,6 +221,15 @@ class XETrainer:
                   _stream())
         return d32, d16
 
+    def _dropout(self, t: Tensor, site: str, p: float) -> None:
+        """In place; forward and backward call it with the same site (the mask is regenerated, not stored)."""
+        if self.dropout_seed is None or p == 0.0:
+            return
+        assert t.is_contiguous()
+        seed = (self.dropout_seed + self.steps_done) & 0xFFFFFFFF
+        cabi.call("cap_train_dropout", t.data_ptr(), CAP_F32 if t.dtype == torch.float32 else CAP_BF16, t.numel(),
+                  int(p * 4294967296.0), 1.0 / (1.0 - p), seed, zlib.crc32(site.encode()), _stream())
+
     def _att_args(self, q, k, v, out, b, nq, nk, mask, mask_qs):
         return cabi.AttentionArgs(
             q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(),
@@ -271,6 +288,7 @@ class XETrainer:
         if n not in self._visual_pos:
             self._visual_pos[n] = visual_position_table(n, d).to(dev).float().contiguous()
         x0 = self._lin_fwd(proj, f16, True)
+        self._dropout(x0, "vision_embedding.dropout", self.p_vision)
         pre0, x32, x16 = self._ln_fwd(x0, None, "encoder.layer_norm", pos=self._visual_pos[n])
         enc_saved = []
         for l, w in enumerate(enc):
@@ -278,9 +296,12 @@ class XETrainer:
             qkv = self._lin_fwd(w["qkv"], x16, False)
             att = self._att_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, n, n, enc_mask, 0)
             o32 = self._lin_fwd(w["o"], att, True)
+            self._dropout(o32, p + "mhatt.dropout", self.p_enc)
             pre1, y32, y16 = self._ln_fwd(o32, x32, p + "mhatt.layer_norm")
             h16 = self._lin_fwd(w["fc1"], y16, False, ACT_RELU)
+            self._dropout(h16, p + "pwff.dropout_2", self.p_enc)
             f32 = self._lin_fwd(w["fc2"], h16, True)
+            self._dropout(f32, p + "pwff.dropout", self.p_enc)
             pre2, nx32, nx16 = self._ln_fwd(f32, y32, p + "pwff.layer_norm", zero_rows=enc_rows)
             enc_saved.append((x16, qkv, att, pre1, y16, h16, pre2))
             x32, x16 = nx32, nx16
@@ -301,14 +322,18 @@ class XETrainer:
             qkv = self._lin_fwd(w["qkv"], e16, False)
             att1 = self._att_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, T, T, self_mask, T)
             o32 = self._lin_fwd(w["o1"], att1, True)
+            self._dropout(o32, p + "self_attn.dropout", self.p_self)
             pre1, s32, s16 = self._ln_fwd(o32, e32, p + "self_attn.layer_norm")
             q16 = self._lin_fwd(w["q"], s16, False)
             kv16 = self._lin_fwd(w["kv"], enc16, False)
             att2 = self._att_fwd(q16, kv16[:, :hd], kv16[:, hd:], B, T, n, enc_mask, 0)
             o32 = self._lin_fwd(w["o2"], att2, True)
+            self._dropout(o32, p + "enc_attn.dropout", self.p_cross)
             pre2, c32, c16 = self._ln_fwd(o32, s32, p + "enc_attn.layer_norm")
             h16 = self._lin_fwd(w["fc1"], c16, False, ACT_RELU)
+            self._dropout(h16, p + "pwff.dropout_2", self.p_cross)      # PositionWiseFeedForward(config.ENC_ATTENTION)
             f32 = self._lin_fwd(w["fc2"], h16, True)
+            self._dropout(f32, p + "pwff.dropout", self.p_cross)
             pre3, ne32, ne16 = self._ln_fwd(f32, c32, p + "pwff.layer_norm", zero_rows=pad_rows)
             dec_saved.append((e16, qkv, att1, pre1, s16, q16, kv16, att2, pre2, c16, h16, pre3))
             e32, e16 = ne32, ne16
@@ -329,10 +354,13 @@ class XETrainer:
             w, p = dec[l], f"decoder.layers.{l}."
             e16_in, qkv, att1, pre1, s16, q16, kv16, att2, pre2, c16, h16, pre3 = dec_saved[l]
             d3_32, d3_16 = self._ln_bwd(g_a, g_b, pre3, p + "pwff.layer_norm", zero_rows=pad_rows)
+            self._dropout(d3_16, p + "pwff.dropout", self.p_cross)      # only the GEMM branch is dropped, not the residual
             dh16 = self._lin_bwd(w["fc2"], h16, d3_16, dx_f32=False)
+            self._dropout(dh16, p + "pwff.dropout_2", self.p_cross)
             cabi.call("cap_train_relu_bwd", dh16.data_ptr(), h16.data_ptr(), dh16.numel(), _stream())
             dc_ffn = self._lin_bwd(w["fc1"], c16, dh16)
             d2_32, d2_16 = self._ln_bwd(d3_32, dc_ffn, pre2, p + "enc_attn.layer_norm")
+            self._dropout(d2_16, p + "enc_attn.dropout", self.p_cross)
             datt2 = self._lin_bwd(w["o2"], att2, d2_16, dx_f32=False)
             dq16 = torch.empty_like(q16)
             dkv16 = torch.empty_like(kv16)
@@ -341,6 +369,7 @@ class XETrainer:
             denc_l = self._lin_bwd(w["kv"], enc16, dkv16)
             cabi.call("cap_axpy_f32", denc.data_ptr(), denc_l.data_ptr(), denc.numel(), _stream())
             d1_32, d1_16 = self._ln_bwd(d2_32, ds_q, pre1, p + "self_attn.layer_norm")
+            self._dropout(d1_16, p + "self_attn.dropout", self.p_self)
             datt1 = self._lin_bwd(w["o1"], att1, d1_16, dx_f32=False)
             dqkv = torch.empty_like(qkv)
             self._att_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], datt1, dqkv[:, :hd], dqkv[:, hd:2 * hd], dqkv[:, 2 * hd:],
@@ -356,10 +385,13 @@ class XETrainer:
             w, p = enc[l], f"encoder.layers.{l}."
             x16_in, qkv, att, pre1, y16, h16, pre2 = enc_saved[l]
             d2_32, d2_16 = self._ln_bwd(g_a, g_b, pre2, p + "pwff.layer_norm", zero_rows=enc_rows)
+            self._dropout(d2_16, p + "pwff.dropout", self.p_enc)
             dh16 = self._lin_bwd(w["fc2"], h16, d2_16, dx_f32=False)
+            self._dropout(dh16, p + "pwff.dropout_2", self.p_enc)
             cabi.call("cap_train_relu_bwd", dh16.data_ptr(), h16.data_ptr(), dh16.numel(), _stream())
             dy_ffn = self._lin_bwd(w["fc1"], y16, dh16)
             d1_32, d1_16 = self._ln_bwd(d2_32, dy_ffn, pre1, p + "mhatt.layer_norm")
+            self._dropout(d1_16, p + "mhatt.dropout", self.p_enc)
             datt = self._lin_bwd(w["o"], att, d1_16, dx_f32=False)
             dqkv = torch.empty_like(qkv)
             self._att_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], datt, dqkv[:, :hd], dqkv[:, hd:2 * hd], dqkv[:, 2 * hd:],
@@ -367,6 +399,7 @@ class XETrainer:
             dx_qkv = self._lin_bwd(w["qkv"], x16_in, dqkv)
             g_a, g_b = d1_32, dx_qkv
         _, d0_16 = self._ln_bwd(g_a, g_b, pre0, "encoder.layer_norm")
+        self._dropout(d0_16, "vision_embedding.dropout", self.p_vision)
         self._lin_bwd(proj, f16, d0_16, need_dx=False)
         return loss
 

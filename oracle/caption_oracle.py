@@ -134,6 +134,59 @@ def _rnd(x: Tensor) -> Tensor:
     return x.to(torch.bfloat16).to(torch.float32) if _OPERANDS == "bf16" else x
 
 
+# Dropout of the training step (T1).  The reference's nn.Dropout draws from torch's generator, which nothing outside
+# torch can reproduce; the training restatement (and the patched reference of oracle/ref_harness/gen_golden_train.py, and
+# the CUDA kernel cap_train_dropout) use a counter-based mask instead: element i of the tensor at the nn.Dropout module
+# named `site` is kept iff hash(i, seed, crc32(site)) >= floor(p * 2^32); kept elements are scaled by float32(1 / (1 - p)).
+_DROPOUT_SEED: Optional[int] = None   # None: eval semantics (dropout = identity)
+
+
+class train_dropout:
+    """Context manager: dropout active with this seed (one seed per optimizer step)."""
+
+    def __init__(self, seed: Optional[int]):
+        self.seed = seed
+
+    def __enter__(self):
+        global _DROPOUT_SEED
+        self.prev, _DROPOUT_SEED = _DROPOUT_SEED, self.seed
+        return self
+
+    def __exit__(self, *exc):
+        global _DROPOUT_SEED
+        _DROPOUT_SEED = self.prev
+
+
+def dropout_site(name: str) -> int:
+    import zlib
+    return zlib.crc32(name.encode())
+
+
+def dropout_threshold(p: float) -> int:
+    return int(float(p) * 4294967296.0)
+
+
+def dropout_keep(numel: int, seed: int, site: str, p: float) -> Tensor:
+    """bool (numel,): the mask of cap_train_dropout (csrc/train.cu dropout_hash), in 32-bit wrap-around arithmetic."""
+    import numpy as np
+    m = np.uint64(0xFFFFFFFF)
+    x = (np.arange(numel, dtype=np.uint64) * np.uint64(0x9E3779B1) + np.uint64(seed & 0xFFFFFFFF) * np.uint64(0x85EBCA77)
+         + np.uint64(dropout_site(site)) * np.uint64(0xC2B2AE3D)) & m
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x2C1B3C6D)) & m
+    x ^= x >> np.uint64(12)
+    x = (x * np.uint64(0x297A2D39)) & m
+    x ^= x >> np.uint64(15)
+    return torch.from_numpy(x >= np.uint64(dropout_threshold(p)))
+
+
+def _drop(x: Tensor, site: str, p: float) -> Tensor:
+    if _DROPOUT_SEED is None or not p:
+        return x
+    keep = dropout_keep(x.numel(), _DROPOUT_SEED, site, p).view(x.shape)
+    return x * keep * torch.tensor(1.0 / (1.0 - float(p)), dtype=torch.float32)
+
+
 def _lin(w: Weights, name: str, x: Tensor) -> Tensor:
     y = F.linear(_rnd(x), w[name + ".weight"], w.get(name + ".bias"))
     return _rnd(y) if name.rsplit(".", 1)[-1] in _BF16_STORED else y
@@ -208,6 +261,8 @@ def multi_head_attention(w: Weights, p: str, att_cfg, queries: Tensor, keys: Ten
         cache["values"] = torch.cat([cache["values"], values], 1)
         keys, values = cache["keys"], cache["values"]
     out = dot_product_attention(w, p + "attention.", att_cfg, queries, keys, values, mask, geometry)
+    if _DROPOUT_SEED is not None:
+        out = _drop(out, p + "dropout", att_cfg.DROPOUT)        # attentions.py:308
     d = queries.shape[-1]
     out = F.layer_norm(queries + out, (d,), w[p + "layer_norm.weight"], w[p + "layer_norm.bias"])
     if att_cfg.USE_AOA:
@@ -216,9 +271,10 @@ def multi_head_attention(w: Weights, p: str, att_cfg, queries: Tensor, keys: Ten
     return out
 
 
-def feed_forward(w: Weights, p: str, x: Tensor) -> Tensor:
+def feed_forward(w: Weights, p: str, x: Tensor, p_drop: float = 0.0) -> Tensor:
     """PositionWiseFeedForward.forward, models/modules/positionwise_feed_forward.py:23-28."""
-    y = _lin(w, p + "fc2", F.relu(_lin(w, p + "fc1", x)))
+    y = _lin(w, p + "fc2", _drop(F.relu(_lin(w, p + "fc1", x)), p + "dropout_2", p_drop))
+    y = _drop(y, p + "dropout", p_drop)
     return F.layer_norm(x + y, (x.shape[-1],), w[p + "layer_norm.weight"], w[p + "layer_norm.bias"])
 
 
@@ -229,7 +285,7 @@ def feed_forward(w: Weights, p: str, x: Tensor) -> Tensor:
 def _encoder_layer(w: Weights, p: str, att_cfg, x: Tensor, pad_mask: Tensor, geometry=None) -> Tensor:
     """EncoderLayer.forward, models/modules/encoders.py:17-22."""
     att = multi_head_attention(w, p + "mhatt.", att_cfg, x, x, x, pad_mask, geometry=geometry)
-    ff = feed_forward(w, p + "pwff.", att)
+    ff = feed_forward(w, p + "pwff.", att, att_cfg.DROPOUT if _DROPOUT_SEED is not None else 0.0)
     return ff.masked_fill(pad_mask.squeeze(1).squeeze(1).unsqueeze(-1), 0)
 
 
@@ -261,6 +317,8 @@ def encode(w: Weights, model_cfg, feats: Tensor, boxes: Optional[Tensor] = None)
         return dual_collaborative_encode(w, enc_cfg, region, boxes[0], region_mask, region2all, grid, boxes[1], grid_mask, grid2all)
     pad_mask = feature_padding_mask(feats)
     x = _lin(w, "vision_embedding.proj", feats)
+    if _DROPOUT_SEED is not None:
+        x = _drop(x, "vision_embedding.dropout", model_cfg.VISION_EMBEDDING.DROPOUT)   # vision_embeddings.py:18
     d = enc_cfg.D_MODEL
     kind = enc_cfg.ARCHITECTURE
     geometry = geometry_weights(w, "encoder.", enc_cfg, boxes) if kind == "GeometricEncoder" else None
@@ -412,7 +470,8 @@ def _decoder_layer(w: Weights, p: str, dec_cfg, x: Tensor, enc: Tensor, pad_rows
         c = mixed / n_lv ** 0.5
     else:
         c = multi_head_attention(w, p + "enc_attn.", att_cfg.ENC_ATTENTION, s, enc, enc, enc_mask)
-    ff = feed_forward(w, p + "pwff.", c)
+    # PositionWiseFeedForward(config.ENC_ATTENTION), decoders.py:19
+    ff = feed_forward(w, p + "pwff.", c, att_cfg.ENC_ATTENTION.DROPOUT if _DROPOUT_SEED is not None else 0.0)
     return ff.masked_fill(pad_rows.unsqueeze(-1), 0)
 
 
@@ -574,9 +633,11 @@ def teacher_forced_log_probs(w: Weights, model_cfg, vocab, feats: Tensor, tokens
 # ----------------------------------------------------------------------------------------------
 # The reference's step is: out = model(items) (teacher forcing, log-probs), NLLLoss(ignore_index=<pad>) over
 # (B*T, V) against the shifted-right tokens, backward, Adam(lr, betas=(0.9, 0.98)) step, LambdaLR step with
-# lambda(s) = d_model^-0.5 * min((s+1)^-0.5, (s+1) * warmup^-1.5).  Dropout is NOT restated (p = 0: the stochastic part
-# of the reference's step has no portable generator); oracle/ref_harness/gen_golden_train.py pins this restatement to
-# the real reference's modules with every nn.Dropout set to p = 0.
+# lambda(s) = d_model^-0.5 * min((s+1)^-0.5, (s+1) * warmup^-1.5).  Dropout: the reference's nn.Dropout modules draw from
+# torch's generator, which has no portable restatement; `dropout_seeds` (one per step) switches the counter-based masks
+# of _drop() on instead, None is the p = 0 computation.  oracle/ref_harness/gen_golden_train.py pins BOTH to the real
+# reference's modules: with every nn.Dropout set to p = 0, and with every nn.Dropout's forward wrapped to apply the
+# same counter-based mask at the same site name.
 # nn.Embedding(padding_idx=<pad>) never updates the <pad> row: its gradient is zeroed here the same way; the
 # sinusoid position table is frozen (decoders.py:87-88).
 
@@ -597,7 +658,8 @@ def xe_loss(w: Weights, model_cfg, vocab, feats: Tensor, tokens: Tensor, targets
     return F.nll_loss(logp.reshape(-1, logp.shape[-1]), targets.reshape(-1), ignore_index=vocab.padding_idx)
 
 
-def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int, bf16_linear_weights: bool = False):
+def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int, bf16_linear_weights: bool = False,
+                   dropout_seeds=None):
     """Runs len(batches) optimizer steps in place on a float32 copy of `w`.  batches: (feats, tokens, targets[, boxes]).
     Returns (weights after the last step, [loss per step], gradients of the FIRST step).
 
@@ -619,7 +681,8 @@ def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int
         if bf16_linear_weights:
             seen = {k: (p + (p.detach().to(torch.bfloat16).float() - p.detach()))
                     if (p.dim() == 2 and k.endswith(".weight") and "_emb" not in k) else p for k, p in params.items()}
-        loss = xe_loss(seen, model_cfg, vocab, feats, tokens, targets, boxes)
+        with train_dropout(None if dropout_seeds is None else dropout_seeds[len(losses)]):
+            loss = xe_loss(seen, model_cfg, vocab, feats, tokens, targets, boxes)
         loss.backward()
         if params[emb].grad is not None:
             params[emb].grad[pad].zero_()          # nn.Embedding(padding_idx=pad)

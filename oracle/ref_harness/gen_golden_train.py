@@ -1,7 +1,10 @@
 """Golden fixture of the XE training step (T1): the REAL reference model, loss and optimizer.
 
-Builds the reference model from this repo's YAML, sets every nn.Dropout to p = 0 (the stochastic part of the step has no
-portable generator), loads the synthetic weights, and runs the body of trainers/vi_trainer.py:105-119 --
+Builds the reference model from this repo's YAML, loads the synthetic weights, and runs the body of
+trainers/vi_trainer.py:105-119 twice: with every nn.Dropout set to p = 0, and (cases with "dropout_seed") with every
+nn.Dropout module's forward WRAPPED to apply the counter-based mask of oracle.dropout_keep at the site named by the
+module's qualified name (torch's own dropout generator has no portable restatement; p, the sites and the scaling are the
+reference's) --
 out = model(items); loss = NLLLoss(ignore_index=pad)(out.view(-1, V), shifted.view(-1)); backward; Adam(lr, betas=(0.9,
 0.98)).step(); LambdaLR(lambda_lr).step() (trainers/base_trainer.py:89-91, 114-117) -- for STEPS batches.  It refuses
 to write the fixture unless oracle.xe_train_steps reproduces losses, first-step gradients and final weights.
@@ -39,7 +42,7 @@ from oracle import caption_oracle as oracle  # noqa: E402
 from oracle.cases import TRAIN_CASES, apply_overrides  # noqa: E402
 
 
-def run_case(name: str, case: dict) -> dict:
+def run_case(name: str, case: dict, dropout: bool = False) -> dict:
     cfg_path = REPO / "openviic_b200" / "configs" / case["config"]
     ref_cfg = apply_overrides(ref_get_config(str(cfg_path)), case)
     ref_cfg.MODEL.DEVICE = "cpu"
@@ -48,9 +51,20 @@ def run_case(name: str, case: dict) -> dict:
     model = ref_build_model(ref_cfg.MODEL, vocab)
     weights = synthetic.load_synthetic_weights(model, case["seed"])
     model.train()
-    for m in model.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
+    seeds = None
+    if dropout:
+        seeds = [case["dropout_seed"] + i for i in range(case["steps"])]
+        step_box = {"i": 0}
+        for qual, m in model.named_modules():
+            if isinstance(m, torch.nn.Dropout) and m.p > 0:
+                def masked(x, _name=qual, _p=m.p):
+                    keep = oracle.dropout_keep(x.numel(), seeds[step_box["i"]], _name, _p).view(x.shape)
+                    return x * keep * torch.tensor(1.0 / (1.0 - float(_p)), dtype=torch.float32)
+                m.forward = masked
+    else:
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
     batches = synthetic.synth_train_batches(ref_cfg.MODEL, case)
     optim = Adam(model.parameters(), lr=case["lr"], betas=(0.9, 0.98))
     d_model, warmup = model.encoder.d_model, case["warmup"]
@@ -71,17 +85,19 @@ def run_case(name: str, case: dict) -> dict:
             first_grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in model.named_parameters()}
         optim.step()
         sched.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
+        if dropout:
+            step_box["i"] += 1
     final = {k: v.detach().clone() for k, v in model.state_dict().items()}
 
     our_cfg = apply_overrides(get_config(cfg_path), case)
     o_final, o_losses, o_grads = oracle.xe_train_steps(
-        weights, our_cfg.MODEL, vocab, [(f, t, y, b) for _, f, t, y, b in batches], case["lr"], case["warmup"])
+        weights, our_cfg.MODEL, vocab, [(f, t, y, b) for _, f, t, y, b in batches], case["lr"], case["warmup"], dropout_seeds=seeds)
     worst_g = max(float((first_grads[k] - o_grads[k]).abs().max()) for k in first_grads if first_grads[k] is not None)
     missing = [k for k in first_grads if (first_grads[k] is None) != (o_grads.get(k) is None)]
     worst_w = max(float((final[k].float() - o_final[k]).abs().max()) for k in final if k in o_final and final[k].numel())
     worst_l = max(abs(a - b) for a, b in zip(losses, o_losses))
-    print(f"[{name}] reference losses {losses}; oracle-vs-reference: loss {worst_l:.2e}, first-step gradients {worst_g:.2e}, "
+    print(f"[{name}{' + dropout' if dropout else ''}] reference losses {losses}; oracle-vs-reference: loss {worst_l:.2e}, first-step gradients {worst_g:.2e}, "
           f"weights after {len(batches)} steps {worst_w:.2e}, parameters whose gradient exists on one side only: {missing}")
     if worst_l > 1e-5 or worst_g > 1e-6 or worst_w > 1e-6 or missing:
         raise SystemExit(f"oracle does not reproduce the reference's training step on case {name}")
@@ -104,6 +120,10 @@ def main():
         out = REPO / "tests" / "golden" / f"train_{name}.npz"
         np.savez_compressed(out, **run_case(name, case))
         print("wrote", out, out.stat().st_size, "bytes")
+        if "dropout_seed" in case:
+            out = REPO / "tests" / "golden" / f"train_{name}_dropout.npz"
+            np.savez_compressed(out, **run_case(name, case, dropout=True))
+            print("wrote", out, out.stat().st_size, "bytes")
 
 
 if __name__ == "__main__":

@@ -107,12 +107,14 @@ def test_adaptive_attention_oracle_reproduces_the_reference_class():
     assert np.abs(out.numpy() - golden("adaptive_attention")["out"]).max() < 2e-5
 
 
-@pytest.mark.parametrize("name", ["std_grid", "std_region"])
+@pytest.mark.parametrize("name", ["std_grid", "std_region", "std_region_dropout"])
 def test_oracle_training_step_reproduces_the_reference(name):
     """T1: oracle.xe_train_steps (loss, backward, Adam, Noam) against the fixture written from the REAL reference's
     modules, loss and optimizer by oracle/ref_harness/gen_golden_train.py (per parameter: norm + 16 strided samples of
     the first-step gradient and of the weights after the last step)."""
     from oracle.cases import TRAIN_CASES, apply_overrides
+    dropout = name.endswith("_dropout")     # the fixture of the reference with its nn.Dropout forwards on the counter-based masks
+    fixture, name = name, name.replace("_dropout", "")
     case = TRAIN_CASES[name]
     cfg = apply_overrides(ov.get_config(case["config"]), case)
     cfg.MODEL.DEVICE = "cpu"
@@ -120,8 +122,9 @@ def test_oracle_training_step_reproduces_the_reference(name):
     model = ov.build_model(cfg.MODEL, vocab)
     weights = synthetic.load_synthetic_weights(model, case["seed"])
     batches = [(f, t, y, b) for _, f, t, y, b in synthetic.synth_train_batches(cfg.MODEL, case)]
-    final, losses, grads = oracle.xe_train_steps(weights, cfg.MODEL, vocab, batches, case["lr"], case["warmup"])
-    g = np.load(GOLDEN / f"train_{name}.npz")
+    seeds = [case["dropout_seed"] + i for i in range(case["steps"])] if dropout else None
+    final, losses, grads = oracle.xe_train_steps(weights, cfg.MODEL, vocab, batches, case["lr"], case["warmup"], dropout_seeds=seeds)
+    g = np.load(GOLDEN / f"train_{fixture}.npz")
     assert np.abs(np.asarray(losses) - g["losses"]).max() < 1e-5
     checked = 0
     for key in g.files:

@@ -196,6 +196,25 @@ def test_adam_matches_torch(device):
     assert (p - p0).abs().max().item() > 0
 
 
+def test_dropout_mask_equals_the_oracle_hash(device):
+    """cap_train_dropout against oracle.dropout_keep (the mask the patched reference used for the dropout fixture)."""
+    torch.manual_seed(7)
+    for n, p, seed, site in ((100003, 0.1, 9001, "encoder.layers.0.pwff.dropout_2"), (4096, 0.5, 0xFFFFFFF0, "vision_embedding.dropout")):
+        x = torch.randn(n, device=device)
+        keep = oracle.dropout_keep(n, seed, site, p)
+        want = x.cpu() * keep * torch.tensor(1.0 / (1.0 - p), dtype=torch.float32)
+        y = x.clone()
+        cabi.call("cap_train_dropout", y.data_ptr(), cabi.CAP_F32, n, oracle.dropout_threshold(p), 1.0 / (1.0 - p), seed & 0xFFFFFFFF,
+                  oracle.dropout_site(site), _s())
+        assert torch.equal(y.cpu(), want)
+        assert abs(keep.float().mean().item() - (1 - p)) < 4 * math.sqrt(p * (1 - p) / n)
+        yb = _bf(x)
+        cabi.call("cap_train_dropout", yb.data_ptr(), cabi.CAP_BF16, n, oracle.dropout_threshold(p), 1.0 / (1.0 - p), seed & 0xFFFFFFFF,
+                  oracle.dropout_site(site), _s())
+        want_b = (_bf(x).float().cpu() * keep * torch.tensor(1.0 / (1.0 - p), dtype=torch.float32)).to(torch.bfloat16)
+        assert torch.equal(yb.cpu(), want_b)
+
+
 def _trainer_case(name, device):
     case = TRAIN_CASES[name]
     cfg = apply_overrides(ov.get_config(case["config"]), case)
@@ -297,3 +316,40 @@ def test_training_step_at_the_benchmarked_size(device):
     print(f"[full size, {B} images] loss {loss.item():.5f} vs oracle {o_losses[0]:.5f}; gradient cosine {cos:.6f}, worst relative "
           f"L2 error {worst[1]:.4f} ({worst[0]})")
     assert abs(loss.item() - o_losses[0]) < TOL_LOSS and cos > TOL_GRAD_COS and worst[1] < TOL_GRAD_REL
+
+
+def test_training_step_with_dropout_matches_oracle(device):
+    """DROPOUT = 0.1 as in the YAML, on the counter-based masks: the oracle with the same masks reproduces the real
+    reference whose nn.Dropout forwards were wrapped to apply them (gen_golden_train.py, differences 0.0)."""
+    name = "std_region"
+    case, cfg, vocab, model, weights, batches = _trainer_case(name, device)
+    seeds = [case["dropout_seed"] + i for i in range(case["steps"])]
+    plain = [(f, t, y, b) for _, f, t, y, b in batches]
+    _, o_losses, o_grads = oracle.xe_train_steps(weights, cfg.MODEL, vocab, plain, case["lr"], case["warmup"], dropout_seeds=seeds)
+    _, m_losses, _ = oracle.xe_train_steps(weights, cfg.MODEL, vocab, plain, case["lr"], case["warmup"], bf16_linear_weights=True,
+                                           dropout_seeds=seeds)
+    _, p0_losses, _ = oracle.xe_train_steps(weights, cfg.MODEL, vocab, plain[:1], case["lr"], case["warmup"])
+    trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], dropout_seed=case["dropout_seed"])
+    _, feats, tokens, targets, _ = batches[0]
+    with torch.no_grad():
+        loss = trainer.loss_and_grads(feats.to(device).to(torch.bfloat16), tokens.to(device), targets.to(device))
+    torch.cuda.synchronize()
+    dot = n1 = n2 = 0.0
+    worst = ("", 0.0)
+    for k, g in trainer.gradients().items():
+        g, ref = g.detach().float().cpu(), o_grads[k]
+        dot, n1, n2 = dot + (g * ref).sum().item(), n1 + (g * g).sum().item(), n2 + (ref * ref).sum().item()
+        if not k.endswith("fc_k.bias"):
+            worst = max(worst, (k, ((g - ref).norm() / ref.norm().clamp_min(1e-12)).item()), key=lambda kv: kv[1])
+    cos = dot / math.sqrt(n1 * n2)
+    print(f"[{name} + dropout] loss {loss.item():.5f} vs oracle {o_losses[0]:.5f} (without dropout {p0_losses[0]:.5f}); gradient "
+          f"cosine {cos:.6f}, worst relative L2 error {worst[1]:.4f} ({worst[0]})")
+    assert abs(o_losses[0] - p0_losses[0]) > 1e-3                 # the masks do change the step
+    assert abs(loss.item() - o_losses[0]) < TOL_LOSS and cos > TOL_GRAD_COS and worst[1] < TOL_GRAD_REL
+    trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], dropout_seed=case["dropout_seed"])
+    losses = [trainer.step(f.to(device).to(torch.bfloat16), t.to(device), y.to(device)) for _, f, t, y, _ in batches]
+    torch.cuda.synchronize()
+    losses = [x.item() for x in losses]
+    print(f"[{name} + dropout] losses {['%.4f' % x for x in losses]} vs the oracle with bf16 Linear weights {['%.4f' % x for x in m_losses]} "
+          f"(fp32 weights: {['%.4f' % x for x in o_losses]})")
+    assert all(abs(a - b) < TOL_LOSS for a, b in zip(losses, m_losses))
