@@ -492,9 +492,11 @@ int cap_train_embed_bwd(const int64_t* tokens, const float* g_a, const float* g_
                         int d, cap_stream_t stream);
 /* NLLLoss(ignore_index) over log_softmax(logits), mean over the counted targets (base_trainer.py:91, vi_trainer.py:110):
  * stats[0] = number of targets != ignore_index, stats[1] = sum of their negative log-likelihoods (loss = stats[1] /
- * stats[0]); dlogits bf16 [rows][ldd] = (softmax - onehot) / stats[0], zero for ignored rows and columns >= V. */
-int cap_train_xent(const float* logits, int ld, const int64_t* targets, int ignore_index, float* stats, void* dlogits,
-                   int ldd, int rows, int V, cap_stream_t stream);
+ * stats[0]); dlogits bf16 [rows][ldd] = (softmax - onehot) / stats[0], zero for ignored rows and columns >= V.
+ * row_weight (fp32 [rows], optional): stats[1] = sum w[row] * nll (the loss itself), dlogits = w[row] * (softmax -
+ * onehot) -- the self-critical loss of vi_trainer.py:146-148 with w = advantage / (T * B * beam). */
+int cap_train_xent(const float* logits, int ld, const int64_t* targets, int ignore_index, const float* row_weight,
+                   float* stats, void* dlogits, int ldd, int rows, int V, cap_stream_t stream);
 /* Dropout with a counter-based mask, in place: x[i] = hash(i, seed, site) >= threshold ? x[i] * scale : 0 (threshold =
  * floor(p * 2^32), scale = 1 / (1 - p)); the backward pass calls it on the gradient with the same (seed, site).  The
  * hash is restated in oracle/caption_oracle.py (dropout_keep).  nn.Dropout at vision_embeddings.py:18,

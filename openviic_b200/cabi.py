@@ -68,7 +68,7 @@ SIGNATURES = {
     "cap_attention_backward": (_i, [C.POINTER(AttentionArgs), _vp, _vp, _vp, _vp, _vp]),
     "cap_train_embed_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "cap_train_embed_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
-    "cap_train_xent": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "cap_train_xent": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "cap_train_dropout": (_i, [_vp, _i, _i64, C.c_uint, _f, C.c_uint, C.c_uint, _vp]),
     "cap_train_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp]),
     "cap_decode_self_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -446,10 +446,12 @@ count_targets_kernel(const int64_t* __restrict__ targets, int ignore, float* __r
 
 // Per row: lse = log sum exp(logits); stats[1] += lse - logits[target]; dlogits = (softmax - onehot) / stats[0], zero for
 // ignored rows and for the padding columns V .. ld.  NLLLoss(ignore_index) over log_softmax (base_trainer.py:91,
-// decoders.py:123), mean over the counted targets.
+// decoders.py:123), mean over the counted targets.  With row_weight: stats[1] += w[row] * nll, dlogits = w[row] *
+// (softmax - onehot) -- the self-critical loss -(mean_T log p) * (r - mean_b r), mean over B * b rows
+// (vi_trainer.py:146-148), whose per-token weight is advantage / (T * B * b); finished positions carry <pad> targets.
 __global__ void __launch_bounds__(256)
 xent_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict__ targets, int ignore,
-            float* __restrict__ stats, bf16* __restrict__ dlogits, int ldd, int V) {
+            const float* __restrict__ row_weight, float* __restrict__ stats, bf16* __restrict__ dlogits, int ldd, int V) {
     pdl_prologue();
     __shared__ float sh[8];
     const int row = blockIdx.x;
@@ -479,8 +481,9 @@ xent_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict_
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += sh[w];
     const float lse = m + logf(s);
-    const float inv_n = 1.f / stats[0];
-    if (threadIdx.x == 0) atomicAdd(stats + 1, lse - x[tgt]);
+    // mean over the counted targets (XE), or the caller's per-row weight (the self-critical loss: advantage / (T B b))
+    const float inv_n = row_weight != nullptr ? row_weight[row] : 1.f / stats[0];
+    if (threadIdx.x == 0) atomicAdd(stats + 1, row_weight != nullptr ? (lse - x[tgt]) * inv_n : lse - x[tgt]);
     for (int c = threadIdx.x; c < ldd; c += blockDim.x) {
         float v = 0.f;
         if (c < V) v = (__expf(x[c] - lse) - (c == tgt ? 1.f : 0.f)) * inv_n;
@@ -632,14 +635,15 @@ extern "C" int cap_train_embed_bwd(const int64_t* tokens, const float* g_a, cons
     return cap_check_launch("train_embed_bwd_kernel");
 }
 
-extern "C" int cap_train_xent(const float* logits, int ld, const int64_t* targets, int ignore_index, float* stats, void* dlogits,
-                              int ldd, int rows, int V, cap_stream_t stream) {
+extern "C" int cap_train_xent(const float* logits, int ld, const int64_t* targets, int ignore_index, const float* row_weight,
+                              float* stats, void* dlogits, int ldd, int rows, int V, cap_stream_t stream) {
     CAP_REQUIRE(logits && targets && stats && dlogits, "cap_train_xent: null pointer");
     CAP_REQUIRE(rows > 0 && V > 0 && ld >= V && ldd >= V, "cap_train_xent: bad shape");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CAP_CHECK_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(float), s));
     CAP_LAUNCH_SERIAL(count_targets_kernel, grid_for(rows, 256), 256, 0, s, targets, ignore_index, stats, rows);
-    CAP_LAUNCH_SERIAL(xent_kernel, rows, 256, 0, s, logits, ld, targets, ignore_index, stats, static_cast<bf16*>(dlogits), ldd, V);
+    CAP_LAUNCH_SERIAL(xent_kernel, rows, 256, 0, s, logits, ld, targets, ignore_index, row_weight, stats, static_cast<bf16*>(dlogits),
+                      ldd, V);
     g_cap_launches.fetch_add(2, std::memory_order_relaxed);
     return cap_check_launch("xent_kernel");
 }

@@ -216,3 +216,18 @@ def synth_train_batches(model_cfg, case: dict):
         tokens, targets = synth_captions(case["batch"], case["max_len"], case["vocab"], case["seed"] + 100 * i)
         out.append((field, bf16_round(feats), tokens, targets, boxes))
     return out
+
+
+def synth_rewards(batch: int, beam: int, seed: int) -> torch.Tensor:
+    """Stand-in CIDEr rewards (batch, beam) fp32 in [0, 2) for the self-critical step's parity cases."""
+    return torch.from_numpy(_rng(seed, "rewards").random((batch, beam)).astype(np.float32) * 2.0)
+
+
+def boost_eos(model: torch.nn.Module, weights: Dict[str, torch.Tensor], eos_idx: int, scale: float) -> None:
+    """Scales the <eos> row of the vocabulary projection (in the model and in the weight dict): synthetic weights almost
+    never emit <eos>; with the row scaled a good share of the beams finish early, which is what the parity cases of the
+    self-critical step need (finished beams, <pad> after <eos>)."""
+    with torch.no_grad():
+        row = bf16_round(weights["decoder.fc.weight"][eos_idx] * scale)
+        weights["decoder.fc.weight"][eos_idx] = row
+        model.state_dict()["decoder.fc.weight"][eos_idx] = row

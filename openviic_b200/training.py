@@ -226,7 +226,7 @@ class XETrainer:
         if self.dropout_seed is None or p == 0.0:
             return
         assert t.is_contiguous()
-        seed = (self.dropout_seed + self.steps_done) & 0xFFFFFFFF
+        seed = (self.dropout_seed + self.steps_done + getattr(self, "rl_steps_done", 0)) & 0xFFFFFFFF
         cabi.call("cap_train_dropout", t.data_ptr(), CAP_F32 if t.dtype == torch.float32 else CAP_BF16, t.numel(),
                   int(p * 4294967296.0), 1.0 / (1.0 - p), seed, zlib.crc32(site.encode()), _stream())
 
@@ -250,19 +250,28 @@ class XETrainer:
         cabi.call("cap_attention_backward", C.byref(args), d_out.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _stream())
 
     # ------------------------------------------------------------------------------------------------ one step
-    def loss_and_grads(self, feats: Tensor, tokens: Tensor, targets: Tensor) -> Tensor:
-        """Forward + backward; gradients land in ``self.gradients()``; returns the loss (0-d fp32 device tensor)."""
+    def loss_and_grads(self, feats: Tensor, tokens: Tensor, targets: Tensor, row_weights: Optional[Tensor] = None) -> Tensor:
+        """Forward + backward; gradients land in ``self.gradients()``; returns the loss (0-d fp32 device tensor).
+
+        tokens / targets (B, T): one caption per image (the XE step).  (B, S, T): S captions per image that share the
+        image's encoder output -- the S sequences of an image are S * T queries of one cross-attention problem; used by
+        the self-critical step with ``row_weights`` (B * S,) fp32: loss = sum over sequences of weight * sum_t nll_t."""
         if not (feats.is_cuda and tokens.is_cuda and targets.is_cuda):
             raise RuntimeError("XETrainer.step takes CUDA tensors (no CPU fallback)")
         B, n, dfeat = feats.shape
-        T = tokens.shape[1]
-        if tuple(tokens.shape) != (B, T) or tuple(targets.shape) != (B, T) or tokens.dtype != torch.int64 or targets.dtype != torch.int64:
-            raise ValueError("tokens / targets must be int64 (B, T)")
-        if n > 128 or T > 128 or T + 1 > self.pos_words.shape[0]:
-            raise ValueError("at most 128 visual tokens and max_caption_length tokens per caption")
+        S = tokens.shape[1] if tokens.dim() == 3 else 1     # sequences per image
+        T = tokens.shape[-1]
+        want = (B, S, T) if tokens.dim() == 3 else (B, T)
+        if tuple(tokens.shape) != want or tuple(targets.shape) != want or tokens.dtype != torch.int64 or targets.dtype != torch.int64:
+            raise ValueError("tokens / targets must be int64 (B, T) or (B, S, T)")
+        if n > 128 or S * T > 128 or T + 1 > self.pos_words.shape[0]:
+            raise ValueError("at most 128 visual tokens, 128 caption tokens per image, max_caption_length tokens per caption")
+        if row_weights is not None and (tuple(row_weights.shape) != (B * S,) or row_weights.dtype != torch.float32 or not row_weights.is_cuda):
+            raise ValueError("row_weights must be a CUDA fp32 tensor (B * S,)")
         d, hd, L = self.d, self.heads * 64, self.enc_layers
         dev = self.device
-        Me, Md = B * n, B * T
+        R = B * S                   # decoder sequences
+        Me, Md = B * n, R * T
         self.g32.zero_()
         tokens = tokens.contiguous().view(-1)
         targets = targets.contiguous().view(-1)
@@ -310,7 +319,7 @@ class XETrainer:
         # ---------------- forward: decoder (decoders.py:21-28, 95-123)
         pad_rows = (tokens == self.pad).to(torch.uint8)
         causal = torch.triu(torch.ones((T, T), device=dev, dtype=torch.bool), diagonal=1)
-        self_mask = (causal.unsqueeze(0) | (tokens.view(B, 1, T) == self.pad)).to(torch.uint8).contiguous()   # (B, T, T)
+        self_mask = (causal.unsqueeze(0) | (tokens.view(R, 1, T) == self.pad)).to(torch.uint8).contiguous()   # (R, T, T)
         emb = self._view(self.p32, "decoder.word_emb.components.weight")
         e32 = torch.empty((Md, d), device=dev, dtype=torch.float32)
         e16 = torch.empty((Md, d), device=dev, dtype=torch.bfloat16)
@@ -320,13 +329,13 @@ class XETrainer:
         for l, w in enumerate(dec):
             p = f"decoder.layers.{l}."
             qkv = self._lin_fwd(w["qkv"], e16, False)
-            att1 = self._att_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, T, T, self_mask, T)
+            att1 = self._att_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], R, T, T, self_mask, T)
             o32 = self._lin_fwd(w["o1"], att1, True)
             self._dropout(o32, p + "self_attn.dropout", self.p_self)
             pre1, s32, s16 = self._ln_fwd(o32, e32, p + "self_attn.layer_norm")
             q16 = self._lin_fwd(w["q"], s16, False)
             kv16 = self._lin_fwd(w["kv"], enc16, False)
-            att2 = self._att_fwd(q16, kv16[:, :hd], kv16[:, hd:], B, T, n, enc_mask, 0)
+            att2 = self._att_fwd(q16, kv16[:, :hd], kv16[:, hd:], B, S * T, n, enc_mask, 0)   # an image's S sequences: S * T queries
             o32 = self._lin_fwd(w["o2"], att2, True)
             self._dropout(o32, p + "enc_attn.dropout", self.p_cross)
             pre2, c32, c16 = self._ln_fwd(o32, s32, p + "enc_attn.layer_norm")
@@ -342,9 +351,10 @@ class XETrainer:
         # ---------------- loss (base_trainer.py:91, vi_trainer.py:110)
         stats = torch.empty(2, device=dev, dtype=torch.float32)
         dlogits = torch.empty((Md, self.ldv), device=dev, dtype=torch.bfloat16)
-        cabi.call("cap_train_xent", logits.data_ptr(), self.ldv, targets.data_ptr(), self.pad, stats.data_ptr(), dlogits.data_ptr(),
-                  self.ldv, Md, self.V, _stream())
-        loss = stats[1] / stats[0]
+        per_token = None if row_weights is None else row_weights.repeat_interleave(T).contiguous()
+        cabi.call("cap_train_xent", logits.data_ptr(), self.ldv, targets.data_ptr(), self.pad, None if per_token is None else per_token.data_ptr(),
+                  stats.data_ptr(), dlogits.data_ptr(), self.ldv, Md, self.V, _stream())
+        loss = stats[1] / stats[0] if row_weights is None else stats[1].clone()
 
         # ---------------- backward: decoder
         g_a = self._lin_bwd(fc, e16, dlogits)                                  # (Md, d) fp32: gradient of the last layer's output
@@ -364,7 +374,7 @@ class XETrainer:
             datt2 = self._lin_bwd(w["o2"], att2, d2_16, dx_f32=False)
             dq16 = torch.empty_like(q16)
             dkv16 = torch.empty_like(kv16)
-            self._att_bwd(q16, kv16[:, :hd], kv16[:, hd:], datt2, dq16, dkv16[:, :hd], dkv16[:, hd:], B, T, n, enc_mask, 0)
+            self._att_bwd(q16, kv16[:, :hd], kv16[:, hd:], datt2, dq16, dkv16[:, :hd], dkv16[:, hd:], B, S * T, n, enc_mask, 0)
             ds_q = self._lin_bwd(w["q"], s16, dq16)
             denc_l = self._lin_bwd(w["kv"], enc16, dkv16)
             cabi.call("cap_axpy_f32", denc.data_ptr(), denc_l.data_ptr(), denc.numel(), _stream())
@@ -373,7 +383,7 @@ class XETrainer:
             datt1 = self._lin_bwd(w["o1"], att1, d1_16, dx_f32=False)
             dqkv = torch.empty_like(qkv)
             self._att_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], datt1, dqkv[:, :hd], dqkv[:, hd:2 * hd], dqkv[:, 2 * hd:],
-                          B, T, T, self_mask, T)
+                          R, T, T, self_mask, T)
             de_qkv = self._lin_bwd(w["qkv"], e16_in, dqkv)
             g_a, g_b = d1_32, de_qkv
         cabi.call("cap_train_embed_bwd", tokens.data_ptr(), g_a.data_ptr(), g_b.data_ptr(), self.pad,
@@ -409,6 +419,34 @@ class XETrainer:
         lr_t = self.lr * noam_factor(self.steps_done - 1, self.d, self.warmup)
         cabi.call("cap_train_adam", self.p32.data_ptr(), self.g32.data_ptr(), self.m32.data_ptr(), self.v32.data_ptr(), self.p16.data_ptr(),
                   self.p32.numel(), lr_t, self.betas[0], self.betas[1], self.eps, self.steps_done, _stream())
+
+    def scst_step(self, feats: Tensor, captions: Tensor, rewards: Tensor, rl_lr: float) -> Tensor:
+        """One self-critical update (vi_trainer.py:121-151) given the beam search's output: ``captions`` (B, b, T) int64
+        as ``model.beam_search(..., out_size=b)`` returns them, ``rewards`` (B, b) fp32 (CIDEr of each caption).
+
+        loss = mean over the B * b beams of -(mean_T log p_t) * (r - mean_b r) (:146-148).  The log-probs the reference
+        differentiates are those of the step-wise stateful decode; they equal the teacher-forced log-probs of the final
+        sequences (each step attends to exactly its beam's prefix), positions after <eos> hold <pad> with log-prob 0 and
+        no gradient (beam_search.py:49-55) -- so the gradient is the weighted teacher-forced backward with per-sequence
+        weight advantage / (T * B * b), pinned against the reference's own backward through its beam search by
+        oracle/ref_harness/gen_golden_train.py.  The optimizer of that phase is Adam(lr=RL_LEARNING_RATE), default betas,
+        no scheduler (vi_trainer.py:213)."""
+        B, b, T = captions.shape
+        if tuple(rewards.shape) != (B, b):
+            raise ValueError("rewards must be (B, beam)")
+        with torch.cuda.device(self.device), torch.no_grad():
+            adv = rewards.float() - rewards.float().mean(dim=1, keepdim=True)
+            weights = (adv / float(T * B * b)).reshape(-1).contiguous()
+            bos = torch.full((B, b, 1), self.vocab.bos_idx, dtype=torch.int64, device=captions.device)
+            tokens = torch.cat([bos, captions[:, :, :-1]], dim=2).contiguous()
+            loss = self.loss_and_grads(feats, tokens, captions.contiguous(), row_weights=weights)
+            self.rl_steps_done = getattr(self, "rl_steps_done", 0) + 1
+            if self.rl_steps_done == 1:      # a fresh optimizer: Adam's moments restart (vi_trainer.py:213)
+                self.m32.zero_()
+                self.v32.zero_()
+            cabi.call("cap_train_adam", self.p32.data_ptr(), self.g32.data_ptr(), self.m32.data_ptr(), self.v32.data_ptr(),
+                      self.p16.data_ptr(), self.p32.numel(), float(rl_lr), 0.9, 0.999, self.eps, self.rl_steps_done, _stream())
+        return loss
 
     def step(self, feats: Tensor, tokens: Tensor, targets: Tensor) -> Tensor:
         """One iteration of vi_trainer.py:105-119; returns the loss of the batch (device tensor, no sync)."""

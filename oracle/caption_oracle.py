@@ -692,3 +692,47 @@ def xe_train_steps(w: Weights, model_cfg, vocab, batches, lr: float, warmup: int
         sched.step()
         losses.append(float(loss.detach()))
     return {k: v.detach() for k, v in params.items()}, losses, first_grads
+
+
+# The self-critical step (trainers/vi_trainer.py:121-151): captions and their log-probs come from a beam search run with
+# autograd on, the reward of each caption from CIDEr, and
+#     loss = mean over (B, b) of  -(mean_T log_probs) * (reward - mean_b reward)                       (:146-148)
+# The log-probs the reference differentiates are produced step by step by the stateful decoder; each equals the
+# teacher-forced log-prob of the same token given the same prefix, and positions of finished beams hold <pad> with a
+# constant 0 (beam_search.py:49-55).  This restatement therefore evaluates the FINAL sequences teacher-forced -- one
+# decoder pass instead of max_len stateful steps -- and gen_golden_train.py checks loss, per-token log-probs and every
+# gradient against the reference's own backward through its beam search (dropout p = 0).
+
+def scst_loss(w: Weights, model_cfg, vocab, feats: Tensor, captions: Tensor, rewards: Tensor,
+              boxes: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """captions (B, b, T) int64 as beam_search(out_size=b) returns them, rewards (B, b).  -> (loss, token log-probs (B, b, T))."""
+    b_s, beam, t_len = captions.shape
+    enc, enc_mask = encode(w, model_cfg, feats, boxes)
+    enc = enc.repeat_interleave(beam, 0)
+    enc_mask = enc_mask.repeat_interleave(beam, 0)
+    seqs = captions.reshape(b_s * beam, t_len)
+    tokens = torch.cat([torch.full((b_s * beam, 1), vocab.bos_idx, dtype=torch.long), seqs[:, :-1]], dim=1)
+    logp = decode(w, model_cfg, tokens, enc, enc_mask, vocab.padding_idx, None)
+    tok_lp = logp.gather(-1, seqs.unsqueeze(-1)).squeeze(-1) * (seqs != vocab.padding_idx)
+    tok_lp = tok_lp.view(b_s, beam, t_len)
+    loss = (-tok_lp.mean(-1) * (rewards - rewards.mean(-1, keepdim=True))).mean()
+    return loss, tok_lp
+
+
+def scst_step(w: Weights, model_cfg, vocab, feats: Tensor, captions: Tensor, rewards: Tensor, rl_lr: float,
+              boxes: Optional[Tensor] = None, bf16_linear_weights: bool = False):
+    """One update with Adam(lr=rl_lr), default betas, no scheduler (vi_trainer.py:213).  -> (weights, loss, grads)."""
+    params = {k: v.detach().clone().float().requires_grad_(k not in FROZEN) for k, v in w.items()}
+    optim = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=rl_lr)
+    seen = params
+    if bf16_linear_weights:
+        seen = {k: (p + (p.detach().to(torch.bfloat16).float() - p.detach()))
+                if (p.dim() == 2 and k.endswith(".weight") and "_emb" not in k) else p for k, p in params.items()}
+    loss, _ = scst_loss(seen, model_cfg, vocab, feats, captions, rewards, boxes)
+    loss.backward()
+    emb = "decoder.word_emb.components.weight"
+    if params[emb].grad is not None:
+        params[emb].grad[vocab.padding_idx].zero_()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in params.items()}
+    optim.step()
+    return {k: v.detach() for k, v in params.items()}, float(loss.detach()), grads

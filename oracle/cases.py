@@ -54,5 +54,5 @@ TRAIN_CASES = {
     "std_grid": dict(config="standard_transformer.yaml", batch=8, n=49, max_len=20, vocab=1000, seed=31, steps=3,
                      lr=1.0, warmup=10000),
     "std_region": dict(config="standard_transformer_using_region.yaml", batch=8, n=50, max_len=16, vocab=777, seed=32,
-                       steps=2, lr=1.0, warmup=100, dropout_seed=9001),
+                       steps=2, lr=1.0, warmup=100, dropout_seed=9001, scst_beam=5, rl_lr=5e-6, eos_scale=4.0),
 }

@@ -115,8 +115,73 @@ def run_case(name: str, case: dict, dropout: bool = False) -> dict:
     return fixture
 
 
+def run_scst(name: str, case: dict) -> dict:
+    """The self-critical step: the REAL reference's beam search with autograd on, its loss expression and Adam (dropout
+    p = 0; rewards are synthetic constants -- the CIDEr scorer is pinned separately by gen_golden_cider.py)."""
+    cfg_path = REPO / "openviic_b200" / "configs" / case["config"]
+    ref_cfg = apply_overrides(ref_get_config(str(cfg_path)), case)
+    ref_cfg.MODEL.DEVICE = "cpu"
+    vocab = synthetic.SyntheticVocab(case["vocab"], case["max_len"])
+    torch.manual_seed(0)
+    model = ref_build_model(ref_cfg.MODEL, vocab)
+    weights = synthetic.load_synthetic_weights(model, case["seed"])
+    synthetic.boost_eos(model, weights, vocab.eos_idx, case["eos_scale"])
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    field, feats, tokens, targets, boxes = synthetic.synth_train_batches(ref_cfg.MODEL, case)[0]
+    b, beam = case["batch"], case["scst_beam"]
+    items = RefInstanceList()
+    items.set(field, feats)
+    if boxes is not None:
+        items.set("region_boxes", boxes)
+    optim = Adam(model.parameters(), lr=case["rl_lr"])
+    outs, log_probs = model.beam_search(items, batch_size=b, beam_size=beam, out_size=beam)      # vi_trainer.py:132-133
+    reward = synthetic.synth_rewards(b, beam, case["seed"])
+    optim.zero_grad()
+    reward_baseline = torch.mean(reward, dim=-1, keepdim=True)
+    loss = -torch.mean(log_probs, -1) * (reward - reward_baseline)                                 # :146
+    loss = loss.mean()
+    loss.backward()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+    optim.step()
+    final = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    our_cfg = apply_overrides(get_config(cfg_path), case)
+    captions = outs.detach()
+    with torch.no_grad():
+        _, o_tok_lp = oracle.scst_loss(weights, our_cfg.MODEL, vocab, feats, captions, reward, boxes)
+    o_final, o_loss, o_grads = oracle.scst_step(weights, our_cfg.MODEL, vocab, feats, captions, reward, case["rl_lr"], boxes)
+    worst_lp = float((log_probs.detach() - o_tok_lp).abs().max())
+    # key-projection biases have a mathematically zero gradient (a key bias shifts all logits of a query alike): both sides
+    # hold rounding noise there (1e-10), compared absolutely; every other parameter relative to its largest entry
+    worst_g = max(float((grads[k] - o_grads[k]).abs().max() / grads[k].abs().max().clamp_min(1e-12))
+                  for k in grads if grads[k] is not None and not k.endswith("fc_k.bias"))
+    worst_zero = max(float(max(grads[k].abs().max(), o_grads[k].abs().max())) for k in grads if k.endswith("fc_k.bias"))
+    missing = [k for k in grads if (grads[k] is None) != (o_grads.get(k) is None)]
+    worst_w = max(float((final[k].float() - o_final[k]).abs().max()) for k in final if k in o_final and final[k].numel())
+    n_eos = int((captions == vocab.eos_idx).sum())
+    print(f"[{name} scst] reference loss {float(loss.detach()):.8f}, captions with <eos>: {n_eos}; oracle (teacher-forced restatement) vs reference "
+          f"(backward through the beam search): loss {abs(float(loss) - o_loss):.2e}, per-token log-probs {worst_lp:.2e}, gradients "
+          f"(relative to each parameter's largest entry) {worst_g:.2e} (key biases, zero by construction: {worst_zero:.1e}), weights after the Adam step {worst_w:.2e}, one-sided: {missing}")
+    if abs(float(loss) - o_loss) > 1e-6 or worst_lp > 1e-4 or worst_g > 1e-4 or worst_zero > 1e-7 or missing:
+        raise SystemExit(f"the teacher-forced restatement of the self-critical step does not reproduce the reference on {name}")
+    fixture = {"loss": np.float64(float(loss)), "captions": captions.numpy(), "rewards": reward.numpy(), "log_probs": log_probs.detach().numpy()}
+    for k, g in grads.items():
+        if g is None:
+            continue
+        flat = g.reshape(-1)
+        fixture["g/" + k] = np.concatenate([[float(flat.norm())], flat[:: max(1, flat.numel() // 16)][:16].numpy()])
+    return fixture
+
+
 def main():
     for name, case in TRAIN_CASES.items():
+        if "scst_beam" in case:
+            out = REPO / "tests" / "golden" / f"train_{name}_scst.npz"
+            np.savez_compressed(out, **run_scst(name, case))
+            print("wrote", out, out.stat().st_size, "bytes")
         out = REPO / "tests" / "golden" / f"train_{name}.npz"
         np.savez_compressed(out, **run_case(name, case))
         print("wrote", out, out.stat().st_size, "bytes")

@@ -136,3 +136,35 @@ def test_oracle_training_step_reproduces_the_reference(name):
         assert np.abs(got - g[key]).max() <= 1e-6 * max(1.0, np.abs(g[key]).max()), key
         checked += 1
     assert checked > 200
+
+
+def test_oracle_self_critical_step_reproduces_the_reference():
+    """T1, SCST: the oracle's teacher-forced restatement of the self-critical loss against the fixture taken from the
+    REAL reference's backward through its own beam search (loss, per-token log-probs, gradient samples)."""
+    from oracle.cases import TRAIN_CASES, apply_overrides
+    name = "std_region"
+    case = TRAIN_CASES[name]
+    cfg = apply_overrides(ov.get_config(case["config"]), case)
+    cfg.MODEL.DEVICE = "cpu"
+    vocab = synthetic.SyntheticVocab(case["vocab"], case["max_len"])
+    model = ov.build_model(cfg.MODEL, vocab)
+    weights = synthetic.load_synthetic_weights(model, case["seed"])
+    synthetic.boost_eos(model, weights, vocab.eos_idx, case["eos_scale"])
+    _, feats, _, _, boxes = synthetic.synth_train_batches(cfg.MODEL, case)[0]
+    g = np.load(GOLDEN / f"train_{name}_scst.npz")
+    captions, rewards = torch.from_numpy(g["captions"]), torch.from_numpy(g["rewards"])
+    with torch.no_grad():
+        _, tok_lp = oracle.scst_loss(weights, cfg.MODEL, vocab, feats, captions, rewards, boxes)
+    assert np.abs(tok_lp.numpy() - g["log_probs"]).max() < 1e-4            # step-wise stateful decode == teacher forcing
+    assert (g["log_probs"][g["captions"] == vocab.padding_idx] == 0).all()   # finished beams: constant 0
+    _, loss, grads = oracle.scst_step(weights, cfg.MODEL, vocab, feats, captions, rewards, case["rl_lr"], boxes)
+    assert abs(loss - float(g["loss"])) < 1e-6
+    checked = 0
+    for key in g.files:
+        if not key.startswith("g/") or key.endswith("fc_k.bias"):
+            continue
+        t = grads[key[2:]].reshape(-1)
+        got = np.concatenate([[float(t.norm())], t[:: max(1, t.numel() // 16)][:16].numpy()])
+        assert np.abs(got - g[key]).max() <= 1e-4 * np.abs(g[key]).max() + 1e-9, key
+        checked += 1
+    assert checked > 100

@@ -6,6 +6,7 @@ exactly (oracle/ref_harness/gen_golden_train.py, differences 0.0)."""
 import ctypes as C
 import math
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -15,6 +16,7 @@ from openviic_b200 import cabi, synthetic
 from openviic_b200.training import XETrainer, noam_factor
 from oracle import caption_oracle as oracle
 from oracle.cases import TRAIN_CASES, apply_overrides
+from helpers import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -162,7 +164,7 @@ def test_xent_loss_and_gradient(device):
     targets[::5] = pad
     stats = torch.empty(2, device=device)
     dl = torch.full((rows, ld), 9.0, device=device, dtype=torch.bfloat16)
-    cabi.call("cap_train_xent", logits.data_ptr(), ld, targets.data_ptr(), pad, stats.data_ptr(), dl.data_ptr(), ld, rows, V, _s())
+    cabi.call("cap_train_xent", logits.data_ptr(), ld, targets.data_ptr(), pad, None, stats.data_ptr(), dl.data_ptr(), ld, rows, V, _s())
     ref_in = logits[:, :V].clone().requires_grad_(True)
     ref = F.nll_loss(F.log_softmax(ref_in, -1), targets, ignore_index=pad)
     ref.backward()
@@ -170,6 +172,15 @@ def test_xent_loss_and_gradient(device):
     assert abs((stats[1] / stats[0]).item() - ref.item()) < 1e-4
     assert (dl[:, :V].float() - ref_in.grad).abs().max().item() < 4e-3 * ref_in.grad.abs().max().item() + 1e-6
     assert (dl[:, V:] == 0).all() and (dl[targets == pad] == 0).all()
+    # per-row weights (the self-critical loss): loss = sum_rows w * nll over the non-ignored rows
+    w = torch.randn(rows, device=device) * 0.01
+    cabi.call("cap_train_xent", logits.data_ptr(), ld, targets.data_ptr(), pad, w.data_ptr(), stats.data_ptr(), dl.data_ptr(), ld, rows, V, _s())
+    ref_in = logits[:, :V].clone().requires_grad_(True)
+    nll = F.nll_loss(F.log_softmax(ref_in, -1), targets, ignore_index=pad, reduction="none")
+    ref = (nll * w).sum()
+    ref.backward()
+    assert abs(stats[1].item() - ref.item()) < 1e-5
+    assert (dl[:, :V].float() - ref_in.grad).abs().max().item() < 4e-3 * ref_in.grad.abs().max().item() + 1e-7
 
 
 def test_adam_matches_torch(device):
@@ -353,3 +364,39 @@ def test_training_step_with_dropout_matches_oracle(device):
     print(f"[{name} + dropout] losses {['%.4f' % x for x in losses]} vs the oracle with bf16 Linear weights {['%.4f' % x for x in m_losses]} "
           f"(fp32 weights: {['%.4f' % x for x in o_losses]})")
     assert all(abs(a - b) < TOL_LOSS for a, b in zip(losses, m_losses))
+
+
+def test_self_critical_step_matches_oracle(device):
+    """The SCST update (vi_trainer.py:121-151) given the beam search's captions and their rewards.  The fixture holds the
+    REAL reference's captions (its own beam search, 40 of 40 beams finish with <eos> thanks to the boosted <eos> row),
+    loss and gradient samples from its backward THROUGH that beam search; the oracle's teacher-forced restatement
+    reproduces them to 4e-6 (gen_golden_train.py).  Here: XETrainer.scst_step on those captions against the oracle."""
+    name = "std_region"
+    case, cfg, vocab, model, weights, batches = _trainer_case(name, device)
+    synthetic.boost_eos(model, weights, vocab.eos_idx, case["eos_scale"])
+    g = np.load(GOLDEN / f"train_{name}_scst.npz")
+    captions, rewards = torch.from_numpy(g["captions"]), torch.from_numpy(g["rewards"])
+    _, feats, _, _, boxes = batches[0]
+    o_final, o_loss, o_grads = oracle.scst_step(weights, cfg.MODEL, vocab, feats, captions, rewards, case["rl_lr"], boxes)
+    assert abs(o_loss - float(g["loss"])) < 1e-6                       # the oracle against the reference's own loss
+    assert (captions == vocab.eos_idx).any() and (captions == vocab.padding_idx).any()
+    trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], ignore_dropout=True)
+    start = {k: v.detach().float().cpu().clone() for k, v in trainer.parameters().items()}
+    loss = trainer.scst_step(feats.to(device).to(torch.bfloat16), captions.to(device), rewards.to(device), case["rl_lr"])
+    torch.cuda.synchronize()
+    dot = n1 = n2 = 0.0
+    worst = ("", 0.0)
+    for k, gr in trainer.gradients().items():
+        gr, ref = gr.detach().float().cpu(), o_grads[k]
+        dot, n1, n2 = dot + (gr * ref).sum().item(), n1 + (gr * gr).sum().item(), n2 + (ref * ref).sum().item()
+        if not k.endswith("fc_k.bias"):
+            worst = max(worst, (k, ((gr - ref).norm() / ref.norm().clamp_min(1e-12)).item()), key=lambda kv: kv[1])
+    cos = dot / math.sqrt(n1 * n2)
+    du = dr = dd = 0.0
+    for k, v in trainer.parameters().items():
+        a, b = v.detach().float().cpu() - start[k], o_final[k] - weights[k].float()
+        du, dr, dd = du + (a * a).sum().item(), dr + (b * b).sum().item(), dd + (a * b).sum().item()
+    print(f"[{name} scst] loss {loss.item():.6f} vs oracle {o_loss:.6f} (reference {float(g['loss']):.6f}); gradient cosine {cos:.6f}, worst "
+          f"relative L2 error {worst[1]:.4f} ({worst[0]}); Adam update cosine {dd / math.sqrt(du * dr):.4f}")
+    assert abs(loss.item() - o_loss) < 2e-4 and cos > TOL_GRAD_COS and worst[1] < 0.1
+    assert dd / math.sqrt(du * dr) > 0.9
