@@ -454,3 +454,26 @@ class XETrainer:
             loss = self.loss_and_grads(feats, tokens, targets)
             self.optimizer_step()
         return loss
+
+
+def self_critical_iteration(trainer: XETrainer, items, references, cider, beam_size: int, rl_lr: float):
+    """The body of ``Trainer.train_scst``'s loop (trainers/vi_trainer.py:130-151) on the native pieces: beam search on
+    the engine (``out_size = beam_size``), ids -> words (``Vocab.decode_caption``), CIDEr-D reward of every beam against
+    the image's references (``evaluation.Cider``), the self-critical update (``XETrainer.scst_step``).
+
+    items: InstanceList with the model's feature field (and region_boxes); references: per image, a list of reference
+    captions (strings); cider: ``openviic_b200.evaluation.Cider(train references)``.
+    Returns (loss, mean reward, mean baseline) -- the three numbers the reference's progress bar shows."""
+    import itertools
+    model, vocab = trainer.model, trainer.vocab
+    trainer.sync_to_model()                       # the engine reads the model's weights (rebuilt when they changed)
+    feats, _ = model.engine_inputs(items)
+    bs = feats.shape[0]
+    outs, _ = model.beam_search(items, batch_size=bs, beam_size=beam_size, out_size=beam_size)      # (B, b, T)
+    caps_gen = vocab.decode_caption(outs.reshape(-1, outs.shape[-1]), join_words=True)
+    caps_gt = list(itertools.chain(*([r] * beam_size for r in references)))
+    gens = {f"{i}": [c] for i, c in enumerate(caps_gen)}
+    gts = {f"{i}": r for i, r in enumerate(caps_gt)}
+    reward = torch.from_numpy(cider.compute_score(gts, gens)[1].astype("float32")).to(feats.device).view(bs, beam_size)
+    loss = trainer.scst_step(feats.to(trainer.device), outs.to(trainer.device), reward, rl_lr)
+    return loss, reward.mean(), reward.mean(dim=1).mean()

@@ -404,3 +404,32 @@ def test_self_critical_step_matches_oracle(device):
     total_weight = ((captions != vocab.padding_idx).sum(-1) * adv.abs()).sum().item() / float(captions.numel())
     assert abs(loss.item() - o_loss) < 1e-2 * total_weight and cos > TOL_GRAD_COS and worst[1] < 0.1
     assert dd / math.sqrt(du * dr) > 0.9
+
+
+def test_self_critical_iteration_runs_the_whole_loop(device):
+    """train_scst's loop body (vi_trainer.py:130-151) on the native pieces: engine beam search -> words -> CIDEr-D reward
+    -> self-critical update; two iterations (the second one after the weights changed: the engine is rebuilt)."""
+    import openviic_b200 as ov_pkg
+    from openviic_b200.evaluation import Cider
+    from openviic_b200.training import self_critical_iteration
+    name = "std_region"
+    case, cfg, vocab, model, weights, batches = _trainer_case(name, device)
+    synthetic.boost_eos(model, weights, vocab.eos_idx, case["eos_scale"])
+    field, feats, _, _, boxes = batches[0]
+    b = feats.shape[0]
+    items = ov_pkg.InstanceList()
+    items.set(field, feats.to(device))
+    # references that overlap with what the model generates (two of each image's own beams), so that the rewards differ
+    # between the beams of an image and the advantage is not identically zero
+    outs, _ = model.beam_search(items, batch_size=b, beam_size=5, out_size=5)
+    caps = vocab.decode_caption(outs.reshape(-1, outs.shape[-1]), join_words=True)
+    references = [[caps[5 * i] or "w4", caps[5 * i + 3] or "w5"] for i in range(b)]
+    cider = Cider({str(i): r for i, r in enumerate(references)})
+    trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], ignore_dropout=True)
+    before = trainer.parameters()["decoder.fc.weight"].clone()
+    out = [self_critical_iteration(trainer, items, references, cider, beam_size=5, rl_lr=case["rl_lr"]) for _ in range(2)]
+    torch.cuda.synchronize()
+    for loss, reward, baseline in out:
+        assert math.isfinite(loss.item()) and 0.0 <= reward.item() < 10.0 and abs(reward.item() - baseline.item()) < 1e-5
+    assert not torch.equal(before, trainer.parameters()["decoder.fc.weight"])
+    print(f"[scst loop] losses {[round(x[0].item(), 6) for x in out]}, mean rewards {[round(x[1].item(), 4) for x in out]}")
