@@ -658,7 +658,7 @@ decode_cross_attention_stream_kernel(const bf16* __restrict__ q, int ldq, const 
         for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const float p = (mx == -INFINITY) ? 0.f : exp2f(sv[nt][e] - mx);
+                const float p = (mx == -INFINITY) ? 0.f : fast_exp2(sv[nt][e] - mx);
                 sv[nt][e] = p;
                 sum += p;
             }
@@ -824,7 +824,7 @@ encoder_self_attention_tc_kernel(const bf16* __restrict__ qkv, const uint8_t* __
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float m = e < 2 ? ma : mb;
-                const float p = (m == -INFINITY) ? 0.f : exp2f(s[nt][e] - m);
+                const float p = (m == -INFINITY) ? 0.f : fast_exp2(s[nt][e] - m);
                 s[nt][e] = p;
                 if (e < 2) suma += p; else sumb += p;
             }

@@ -160,6 +160,15 @@ __device__ __forceinline__ void pdl_prologue() {
     pdl_wait();
 }
 
+// 2^x on the SFU, one instruction (results below 2^-126 flush to zero).  exp2f() wraps the same MUFU.EX2 in a range
+// test and two multiplies for denormal results: four instructions per element in the softmax / log-sum-exp loops,
+// which are issue-bound.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -483,10 +483,10 @@ __device__ __forceinline__ void epilogue_alpha(WorkerCtx& c, const FusedParams& 
             const float x1 = __uint_as_float(v[4 * g + 1]) + c.s_bias[c0 + 4 * g + 1] + r[g].y;
             const float x2 = __uint_as_float(v[4 * g + 2]) + c.s_bias[c0 + 4 * g + 2] + r[g].z;
             const float x3 = __uint_as_float(v[4 * g + 3]) + c.s_bias[c0 + 4 * g + 3] + r[g].w;
-            f[4 * g] = 1.f / (1.f + __expf(-x0));
-            f[4 * g + 1] = 1.f / (1.f + __expf(-x1));
-            f[4 * g + 2] = 1.f / (1.f + __expf(-x2));
-            f[4 * g + 3] = 1.f / (1.f + __expf(-x3));
+            f[4 * g] = 1.f / (1.f + fast_exp2(-1.4426950408889634f * x0));
+            f[4 * g + 1] = 1.f / (1.f + fast_exp2(-1.4426950408889634f * x1));
+            f[4 * g + 2] = 1.f / (1.f + fast_exp2(-1.4426950408889634f * x2));
+            f[4 * g + 3] = 1.f / (1.f + fast_exp2(-1.4426950408889634f * x3));
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) r[g] = cs[static_cast<size_t>(c0 / 4 + g) * TILE_ROWS];
@@ -588,7 +588,7 @@ __device__ __forceinline__ void vocab_group(WorkerCtx& c, const FusedParams& p, 
         for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
         const float cm2 = cm * 1.4426950408889634f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cs += exp2f(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -cm2));
+        for (int j = 0; j < 32; ++j) cs += fast_exp2(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -cm2));
     } else if (valid > 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < valid ? __uint_as_float(v[j]) : -INFINITY);

@@ -310,7 +310,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     for (int j = 0; j < 32; ++j) cm = fmaxf(cm, f[j]);
                     const float cm2 = cm * 1.4426950408889634f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) cs += exp2f(fmaf(f[j], 1.4426950408889634f, -cm2));
+                    for (int j = 0; j < 32; ++j) cs += fast_exp2(fmaf(f[j], 1.4426950408889634f, -cm2));
                 } else if (valid > 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < valid ? f[j] : -INFINITY);
