@@ -80,3 +80,26 @@ def gather_captions(ids: torch.Tensor, logp: torch.Tensor, total: int, group=Non
     full_ids = torch.cat([a[:s] for a, s in zip(all_ids, sizes)], 0).to(torch.int64)
     full_lp = torch.cat([a[:s] for a, s in zip(all_lp, sizes)], 0)
     return full_ids, full_lp
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Data-parallel training (the training step's only exchange): every rank runs the step on its shard of the batch; the
+# loss is the mean over the valid target tokens of the WHOLE batch, so the ranks first agree on that count, weight
+# their tokens by 1 / count, and sum the flat gradient buffers.  The result is the single-process gradient of the
+# global batch (up to fp32 summation order), not an average of per-rank means.
+# ---------------------------------------------------------------------------------------------------------------
+def global_token_weight(n_valid_local: torch.Tensor, group=None) -> torch.Tensor:
+    """1 / (number of valid target tokens over all ranks), a 0-d fp32 tensor on n_valid_local's device (no host sync)."""
+    total = n_valid_local.detach().to(torch.float32).clone()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / total
+
+
+def sum_gradients_(flat_grads: torch.Tensor, loss: Optional[torch.Tensor] = None, group=None) -> None:
+    """In-place sum over ranks of the flat gradient buffer (ONE collective) and of the loss contribution."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    if loss is not None:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)

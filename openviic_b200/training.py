@@ -449,9 +449,22 @@ class XETrainer:
         return loss
 
     def step(self, feats: Tensor, tokens: Tensor, targets: Tensor) -> Tensor:
-        """One iteration of vi_trainer.py:105-119; returns the loss of the batch (device tensor, no sync)."""
+        """One iteration of vi_trainer.py:105-119; returns the loss of the batch (device tensor, no sync).
+
+        Under ``torch.distributed`` (one process per GPU, NCCL) the arguments are this rank's shard of the batch: the
+        ranks agree on the number of valid target tokens of the whole batch, weight their tokens by its inverse and sum
+        the flat gradient buffers with one all-reduce -- every rank then applies the update of the GLOBAL batch, and the
+        returned loss is the global mean."""
+        import torch.distributed as dist
+        from . import parallel
         with torch.cuda.device(self.device), torch.no_grad():
-            loss = self.loss_and_grads(feats, tokens, targets)
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                inv = parallel.global_token_weight((targets != self.pad).sum())
+                weights = inv.expand(tokens.shape[0] * (tokens.shape[1] if tokens.dim() == 3 else 1)).contiguous()
+                loss = self.loss_and_grads(feats, tokens, targets, row_weights=weights)
+                parallel.sum_gradients_(self.g32, loss)
+            else:
+                loss = self.loss_and_grads(feats, tokens, targets)
             self.optimizer_step()
         return loss
 

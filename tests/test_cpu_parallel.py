@@ -66,3 +66,41 @@ def test_gather_is_identity_without_a_process_group():
     ids, lp = torch.arange(6).view(2, 3), torch.zeros(2, 3)
     out_ids, out_lp = parallel.gather_captions(ids, lp, 2)
     assert out_ids is ids and out_lp is lp
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    r, w, _ = parallel.init_distributed("gloo")
+    # a stand-in "model": loss = mean over valid tokens of the whole batch of (theta . x_token)^2
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(7, 5, generator=g)                 # 7 tokens over 2 ranks, uneven
+    valid = torch.tensor([1, 1, 0, 1, 1, 1, 0], dtype=torch.bool)
+    theta = torch.linspace(-1, 1, 5)
+    lo, hi = parallel.shard_bounds(7, w, r)
+    xs, vs = x[lo:hi], valid[lo:hi]
+    inv = parallel.global_token_weight(vs.sum())
+    pred = xs @ theta
+    loss = ((pred ** 2) * vs).sum() * inv
+    grad = ((2 * pred * vs).unsqueeze(1) * xs).sum(0) * inv
+    parallel.sum_gradients_(grad, loss)
+    np.save(os.path.join(out_dir, f"train_{r}.npy"), np.concatenate([[loss.item(), inv.item()], grad.numpy()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_exchange_equals_the_global_batch(tmp_path):
+    """The training step's N > 1 path (parallel.global_token_weight + sum_gradients_), world size 2 on gloo, uneven
+    shards: every rank ends up with the loss and gradient of the whole batch, not an average of per-rank means."""
+    mp.spawn(_train_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(7, 5, generator=g)
+    valid = torch.tensor([1, 1, 0, 1, 1, 1, 0], dtype=torch.bool)
+    theta = torch.linspace(-1, 1, 5).requires_grad_(True)
+    loss = (((x @ theta) ** 2) * valid).sum() / valid.sum()
+    loss.backward()
+    for r in range(2):
+        got = np.load(tmp_path / f"train_{r}.npy")
+        assert abs(got[0] - loss.item()) < 1e-6 and abs(got[1] - 1.0 / 5) < 1e-7
+        assert np.abs(got[2:] - theta.grad.numpy()).max() < 1e-6
