@@ -94,7 +94,9 @@ class BaseTransformer(Module):
         device = next(self.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("openviic_b200 models decode on a CUDA device only (no CPU fallback)")
-        if not return_probs and not kwargs and self.engine_supported():
+        # `disable_engine` (set by the training loop while the weights change every iteration) keeps decoding on the
+        # module-level CUDA path, whose bf16 weight copies follow the parameters' versions without an engine rebuild
+        if not return_probs and not kwargs and not getattr(self, "disable_engine", False) and self.engine_supported():
             feats, boxes = self.engine_inputs(input_features)
             eng = self.engine(batch_size, feats.shape[1], beam_size)
             eng.encode(feats.to(device), None if boxes is None else boxes.to(device))

@@ -469,20 +469,28 @@ class XETrainer:
         return loss
 
 
-def self_critical_iteration(trainer: XETrainer, items, references, cider, beam_size: int, rl_lr: float):
+def self_critical_iteration(trainer: XETrainer, items, references, cider, beam_size: int, rl_lr: float,
+                            use_engine: bool = False):
     """The body of ``Trainer.train_scst``'s loop (trainers/vi_trainer.py:130-151) on the native pieces: beam search on
     the engine (``out_size = beam_size``), ids -> words (``Vocab.decode_caption``), CIDEr-D reward of every beam against
-    the image's references (``evaluation.Cider``), the self-critical update (``XETrainer.scst_step``).
+    the image's references (``evaluation.Cider``), the self-critical update (``XETrainer.scst_step``).  ``use_engine=True`` samples on the whole-path engine (rebuilt
+    whenever the weights changed: worth it only for large batches).
 
     items: InstanceList with the model's feature field (and region_boxes); references: per image, a list of reference
     captions (strings); cider: ``openviic_b200.evaluation.Cider(train references)``.
     Returns (loss, mean reward, mean baseline) -- the three numbers the reference's progress bar shows."""
     import itertools
     model, vocab = trainer.model, trainer.vocab
-    trainer.sync_to_model()                       # the engine reads the model's weights (rebuilt when they changed)
+    trainer.sync_to_model()
     feats, _ = model.engine_inputs(items)
     bs = feats.shape[0]
-    outs, _ = model.beam_search(items, batch_size=bs, beam_size=beam_size, out_size=beam_size)      # (B, b, T)
+    # the weights change every iteration: sample on the module-level CUDA path (its bf16 weight copies follow the
+    # parameters' versions) instead of rebuilding the whole-path engine -- a state_dict round trip -- per iteration
+    previous, model.disable_engine = getattr(model, "disable_engine", False), not use_engine
+    try:
+        outs, _ = model.beam_search(items, batch_size=bs, beam_size=beam_size, out_size=beam_size)  # (B, b, T)
+    finally:
+        model.disable_engine = previous
     caps_gen = vocab.decode_caption(outs.reshape(-1, outs.shape[-1]), join_words=True)
     caps_gt = list(itertools.chain(*([r] * beam_size for r in references)))
     gens = {f"{i}": [c] for i, c in enumerate(caps_gen)}

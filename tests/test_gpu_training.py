@@ -427,7 +427,8 @@ def test_self_critical_iteration_runs_the_whole_loop(device):
     cider = Cider({str(i): r for i, r in enumerate(references)})
     trainer = XETrainer(model, lr=case["lr"], warmup=case["warmup"], ignore_dropout=True)
     before = trainer.parameters()["decoder.fc.weight"].clone()
-    out = [self_critical_iteration(trainer, items, references, cider, beam_size=5, rl_lr=case["rl_lr"]) for _ in range(2)]
+    out = [self_critical_iteration(trainer, items, references, cider, beam_size=5, rl_lr=case["rl_lr"], use_engine=k == 2)
+           for k in range(3)]     # two iterations sampling on the module-level path, one on a rebuilt engine
     torch.cuda.synchronize()
     for loss, reward, baseline in out:
         assert math.isfinite(loss.item()) and 0.0 <= reward.item() < 10.0 and abs(reward.item() - baseline.item()) < 1e-5
