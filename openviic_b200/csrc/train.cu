@@ -280,114 +280,206 @@ axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n4) {
 // ------------------------------------------------------------------------------------------ attention backward
 // One CTA per (batch, head).  With P = softmax(q.k^T * scale + mask) (recomputed), O = P.v, D_i = dO_i . O_i:
 //   dV = P^T.dO,   dS = P * (dO.v^T - D),   dQ = scale * dS.k,   dK = scale * dS^T.q        (attentions.py:51-55)
-// q, k, v, dO tiles and P live in shared memory as fp32 (row pitch 65 / nk + 1 words: conflict-free column walks).
+// q, k, v, dO tiles and P live in shared memory as fp32; the six small matrix products run on 4 x 4 register tiles
+// (one 16-byte shared-memory load per 8 FMAs; the first version, one output per thread with two scalar loads per FMA,
+// was shared-memory-bandwidth bound at 280 us per launch).  Rows are 272 bytes apart, so the 8 lanes of a load phase
+// that read 8 consecutive rows hit 8 different 16-byte bank groups; sizes are padded to multiples of 4 with zero rows /
+// masked columns.
 constexpr int AB_THREADS = 256;
-constexpr int AB_PITCH = 65;
+constexpr int AB_PITCH = 68;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& b) {
+    acc.x = fmaf(s, b.x, acc.x); acc.y = fmaf(s, b.y, acc.y); acc.z = fmaf(s, b.z, acc.z); acc.w = fmaf(s, b.w, acc.w);
+}
+__device__ __forceinline__ void store_bf16x4(bf16* p, const float4& v) {
+    bf162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// acc[u][v] = A[4 * ti + u] . B[tj + tiles_n * v]   (rows of A and B contracted over their 64 columns)
+__device__ __forceinline__ void tile_nt(const float* A, const float* B, int ti, int tj, int tiles_n, float (&acc)[4][4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 64; c += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = ld4(A + (4 * ti + u) * AB_PITCH + c);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) b[v] = ld4(B + (tj + tiles_n * v) * AB_PITCH + c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] += dot4(a[u], b[v]);
+    }
+}
+
+// acc[u] = sum_j P[4 * ti + u][j] * B[j][c0 .. c0 + 3]
+__device__ __forceinline__ void tile_nn(const float* P, int pp, const float* B, int ti, int c0, int n, float4 (&acc)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+        const float4 b = ld4(B + j * AB_PITCH + c0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fma4(acc[u], P[(4 * ti + u) * pp + j], b);
+    }
+}
+
+// acc[v] = sum_i P[i][4 * tj + v] * A[i][c0 .. c0 + 3]
+__device__ __forceinline__ void tile_tn(const float* P, int pp, const float* A, int tj, int c0, int n, float4 (&acc)[4]) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n; ++i) {
+        const float4 p4 = ld4(P + i * pp + 4 * tj);
+        const float4 a = ld4(A + i * AB_PITCH + c0);
+        fma4(acc[0], p4.x, a); fma4(acc[1], p4.y, a); fma4(acc[2], p4.z, a); fma4(acc[3], p4.w, a);
+    }
+}
 
 __global__ void __launch_bounds__(AB_THREADS)
 attention_bwd_kernel(cap_attention_args a, const bf16* __restrict__ d_out, bf16* __restrict__ dq, bf16* __restrict__ dk,
                      bf16* __restrict__ dv) {
     pdl_prologue();
-    extern __shared__ float ab_smem[];
+    extern __shared__ __align__(16) float ab_smem[];
     const int nq = a.nq, nk = a.nk;
+    const int nqp = (nq + 3) & ~3, nkp = (nk + 3) & ~3;   // padded to whole 4 x 4 tiles
+    const int tiles_m = nqp >> 2, tiles_n = nkp >> 2;
+    const int pp = nkp + 4;                                // row pitch of P (a multiple of 4 floats)
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
     float* Qs = ab_smem;
-    float* Ks = Qs + nq * AB_PITCH;
-    float* Vs = Ks + nk * AB_PITCH;
-    float* Gs = Vs + nk * AB_PITCH;          // dO
-    float* P = Gs + nq * AB_PITCH;           // [nq][nk + 1]
-    float* D = P + nq * (nk + 1);            // [nq]
-    const int pp = nk + 1;
+    float* Ks = Qs + nqp * AB_PITCH;
+    float* Vs = Ks + nkp * AB_PITCH;
+    float* Gs = Vs + nkp * AB_PITCH;         // dO
+    float* P = Gs + nqp * AB_PITCH;          // [nqp][pp]
+    float* D = P + nqp * pp;                 // [nqp]
     const bf16* qg = static_cast<const bf16*>(a.q) + b * a.q_bs + h * 64;
     const bf16* kg = static_cast<const bf16*>(a.k) + b * a.k_bs + h * 64;
     const bf16* vg = static_cast<const bf16*>(a.v) + b * a.v_bs + h * 64;
     const bf16* gg = d_out + b * a.o_bs + h * 64;
-    for (int idx = threadIdx.x; idx < nq * 32; idx += AB_THREADS) {   // bf16 pairs
+    for (int idx = threadIdx.x; idx < nqp * 32; idx += AB_THREADS) {   // bf16 pairs; pad rows are zero
         const int r = idx >> 5, c = (idx & 31) * 2;
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const bf162*>(qg + static_cast<size_t>(r) * a.ldq + c));
-        const float2 y = __bfloat1622float2(*reinterpret_cast<const bf162*>(gg + static_cast<size_t>(r) * a.ldo + c));
-        Qs[r * AB_PITCH + c] = x.x; Qs[r * AB_PITCH + c + 1] = x.y;
-        Gs[r * AB_PITCH + c] = y.x; Gs[r * AB_PITCH + c + 1] = y.y;
+        float2 x = make_float2(0.f, 0.f), y = make_float2(0.f, 0.f);
+        if (r < nq) {
+            x = __bfloat1622float2(*reinterpret_cast<const bf162*>(qg + static_cast<size_t>(r) * a.ldq + c));
+            y = __bfloat1622float2(*reinterpret_cast<const bf162*>(gg + static_cast<size_t>(r) * a.ldo + c));
+        }
+        *reinterpret_cast<float2*>(Qs + r * AB_PITCH + c) = x;
+        *reinterpret_cast<float2*>(Gs + r * AB_PITCH + c) = y;
     }
-    for (int idx = threadIdx.x; idx < nk * 32; idx += AB_THREADS) {
+    for (int idx = threadIdx.x; idx < nkp * 32; idx += AB_THREADS) {
         const int r = idx >> 5, c = (idx & 31) * 2;
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const bf162*>(kg + static_cast<size_t>(r) * a.ldk + c));
-        const float2 y = __bfloat1622float2(*reinterpret_cast<const bf162*>(vg + static_cast<size_t>(r) * a.ldv + c));
-        Ks[r * AB_PITCH + c] = x.x; Ks[r * AB_PITCH + c + 1] = x.y;
-        Vs[r * AB_PITCH + c] = y.x; Vs[r * AB_PITCH + c + 1] = y.y;
+        float2 x = make_float2(0.f, 0.f), y = make_float2(0.f, 0.f);
+        if (r < nk) {
+            x = __bfloat1622float2(*reinterpret_cast<const bf162*>(kg + static_cast<size_t>(r) * a.ldk + c));
+            y = __bfloat1622float2(*reinterpret_cast<const bf162*>(vg + static_cast<size_t>(r) * a.ldv + c));
+        }
+        *reinterpret_cast<float2*>(Ks + r * AB_PITCH + c) = x;
+        *reinterpret_cast<float2*>(Vs + r * AB_PITCH + c) = y;
     }
     __syncthreads();
-    // S = q.k^T * scale, masked entries -inf
+    // S = q.k^T * scale; masked entries and pad columns -inf
     const uint8_t* mask = a.mask ? a.mask + b * a.mask_bs : nullptr;
-    for (int idx = threadIdx.x; idx < nq * nk; idx += AB_THREADS) {
-        const int i = idx / nk, j = idx - i * nk;
-        float s = 0.f;
-#pragma unroll 16
-        for (int c = 0; c < 64; ++c) s += Qs[i * AB_PITCH + c] * Ks[j * AB_PITCH + c];
-        s *= a.scale;
-        if (mask != nullptr && mask[static_cast<size_t>(i) * a.mask_qs + j]) s = -INFINITY;
-        P[i * pp + j] = s;
+    for (int t = threadIdx.x; t < tiles_m * tiles_n; t += AB_THREADS) {
+        const int ti = t / tiles_n, tj = t - ti * tiles_n;
+        float acc[4][4];
+        tile_nt(Qs, Ks, ti, tj, tiles_n, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = 4 * ti + u;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int j = tj + tiles_n * v;
+                float sv = acc[u][v] * a.scale;
+                if (j >= nk || (mask != nullptr && i < nq && mask[static_cast<size_t>(i) * a.mask_qs + j])) sv = -INFINITY;
+                P[i * pp + j] = sv;
+            }
+        }
     }
     __syncthreads();
     // row softmax (one warp per row)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < nq; i += AB_THREADS / 32) {
+    for (int i = warp; i < nqp; i += AB_THREADS / 32) {
         float m = -INFINITY;
-        for (int j = lane; j < nk; j += 32) m = fmaxf(m, P[i * pp + j]);
+        for (int j = lane; j < nkp; j += 32) m = fmaxf(m, P[i * pp + j]);
         m = warp_max(m);
         float sum = 0.f;
-        for (int j = lane; j < nk; j += 32) {
+        for (int j = lane; j < nkp; j += 32) {
             const float e = (m == -INFINITY) ? 0.f : __expf(P[i * pp + j] - m);
             P[i * pp + j] = e;
             sum += e;
         }
         sum = warp_sum(sum);
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        for (int j = lane; j < nk; j += 32) P[i * pp + j] *= inv;
+        for (int j = lane; j < nkp; j += 32) P[i * pp + j] *= inv;
     }
     __syncthreads();
-    // D_i = dO_i . O_i with O = P.v ; thread per (i, c), warp-reduced over c
-    for (int i = warp; i < nq; i += AB_THREADS / 32) {
-        float acc = 0.f;
-        for (int c = lane; c < 64; c += 32) {
-            float o = 0.f;
-            for (int j = 0; j < nk; ++j) o += P[i * pp + j] * Vs[j * AB_PITCH + c];
-            acc += o * Gs[i * AB_PITCH + c];
+    // D_i = dO_i . O_i with O = P.v: 4 rows x 4 columns per thread, the 16 column groups of a row tile are 16 lanes
+    for (int t0 = 0; t0 < tiles_m * 16; t0 += AB_THREADS) {
+        const int t = t0 + threadIdx.x;
+        const bool active = t < tiles_m * 16;
+        const int ti = active ? t >> 4 : 0, c0 = (t & 15) * 4;
+        float4 acc[4];
+        tile_nn(P, pp, Vs, ti, c0, nkp, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float dsum = active ? dot4(acc[u], ld4(Gs + (4 * ti + u) * AB_PITCH + c0)) : 0.f;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+            if (active && (t & 15) == 0) D[4 * ti + u] = dsum;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) D[i] = acc;
     }
     // dV[j][c] = sum_i P[i][j] * dO[i][c]
     bf16* dvg = dv + b * a.v_bs + h * 64;
-    for (int idx = threadIdx.x; idx < nk * 64; idx += AB_THREADS) {
-        const int j = idx >> 6, c = idx & 63;
-        float acc = 0.f;
-        for (int i = 0; i < nq; ++i) acc += P[i * pp + j] * Gs[i * AB_PITCH + c];
-        dvg[static_cast<size_t>(j) * a.ldv + c] = __float2bfloat16(acc);
+    for (int t = threadIdx.x; t < tiles_n * 16; t += AB_THREADS) {
+        const int tj = t >> 4, c0 = (t & 15) * 4;
+        float4 acc[4];
+        tile_tn(P, pp, Gs, tj, c0, nqp, acc);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            if (4 * tj + v < nk) store_bf16x4(dvg + static_cast<size_t>(4 * tj + v) * a.ldv + c0, acc[v]);
     }
     __syncthreads();
-    // dS in place
-    for (int idx = threadIdx.x; idx < nq * nk; idx += AB_THREADS) {
-        const int i = idx / nk, j = idx - i * nk;
-        float dp = 0.f;
-#pragma unroll 16
-        for (int c = 0; c < 64; ++c) dp += Gs[i * AB_PITCH + c] * Vs[j * AB_PITCH + c];
-        P[i * pp + j] = P[i * pp + j] * (dp - D[i]) * a.scale;
+    // dS in place: P * (dO.v^T - D) * scale
+    for (int t = threadIdx.x; t < tiles_m * tiles_n; t += AB_THREADS) {
+        const int ti = t / tiles_n, tj = t - ti * tiles_n;
+        float acc[4][4];
+        tile_nt(Gs, Vs, ti, tj, tiles_n, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = 4 * ti + u;
+            const float di = D[i];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int j = tj + tiles_n * v;
+                P[i * pp + j] = P[i * pp + j] * (acc[u][v] - di) * a.scale;
+            }
+        }
     }
     __syncthreads();
     bf16* dqg = dq + b * a.q_bs + h * 64;
-    for (int idx = threadIdx.x; idx < nq * 64; idx += AB_THREADS) {
-        const int i = idx >> 6, c = idx & 63;
-        float acc = 0.f;
-        for (int j = 0; j < nk; ++j) acc += P[i * pp + j] * Ks[j * AB_PITCH + c];
-        dqg[static_cast<size_t>(i) * a.ldq + c] = __float2bfloat16(acc);
+    for (int t = threadIdx.x; t < tiles_m * 16; t += AB_THREADS) {
+        const int ti = t >> 4, c0 = (t & 15) * 4;
+        float4 acc[4];
+        tile_nn(P, pp, Ks, ti, c0, nkp, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (4 * ti + u < nq) store_bf16x4(dqg + static_cast<size_t>(4 * ti + u) * a.ldq + c0, acc[u]);
     }
     bf16* dkg = dk + b * a.k_bs + h * 64;
-    for (int idx = threadIdx.x; idx < nk * 64; idx += AB_THREADS) {
-        const int j = idx >> 6, c = idx & 63;
-        float acc = 0.f;
-        for (int i = 0; i < nq; ++i) acc += P[i * pp + j] * Qs[i * AB_PITCH + c];
-        dkg[static_cast<size_t>(j) * a.ldk + c] = __float2bfloat16(acc);
+    for (int t = threadIdx.x; t < tiles_n * 16; t += AB_THREADS) {
+        const int tj = t >> 4, c0 = (t & 15) * 4;
+        float4 acc[4];
+        tile_tn(P, pp, Qs, tj, c0, nqp, acc);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            if (4 * tj + v < nk) store_bf16x4(dkg + static_cast<size_t>(4 * tj + v) * a.ldk + c0, acc[v]);
     }
 }
 
@@ -606,8 +698,13 @@ extern "C" int cap_attention_backward(const cap_attention_args* a, const void* d
     CAP_REQUIRE(!a->geometry && !a->mem_k && !a->mem_v && !a->sentinel,
                 "cap_attention_backward: only the plain scaled dot-product attention (attentions.py:44-58) is differentiated");
     CAP_REQUIRE(a->nq >= 1 && a->nk >= 1 && a->nq <= 128 && a->nk <= 128, "cap_attention_backward: 1..128 queries and keys");
-    CAP_REQUIRE(a->ldq % 2 == 0 && a->ldk % 2 == 0 && a->ldv % 2 == 0 && a->ldo % 2 == 0, "cap_attention_backward: even row strides");
-    const size_t smem = (static_cast<size_t>(2 * a->nq + 2 * a->nk) * AB_PITCH + static_cast<size_t>(a->nq) * (a->nk + 1) + a->nq) * sizeof(float);
+    CAP_REQUIRE(a->ldq % 4 == 0 && a->ldk % 4 == 0 && a->ldv % 4 == 0 && a->ldo % 2 == 0 && a->q_bs % 4 == 0 && a->k_bs % 4 == 0 &&
+                    a->v_bs % 4 == 0 && a->o_bs % 2 == 0,
+                "cap_attention_backward: row / batch strides of q, k, v must be multiples of 4 elements (8-byte gradient stores)");
+    CAP_REQUIRE((reinterpret_cast<uintptr_t>(dq) & 7) == 0 && (reinterpret_cast<uintptr_t>(dk) & 7) == 0 && (reinterpret_cast<uintptr_t>(dv) & 7) == 0,
+                "cap_attention_backward: dq / dk / dv must be 8-byte aligned");
+    const int nqp = (a->nq + 3) & ~3, nkp = (a->nk + 3) & ~3;
+    const size_t smem = (static_cast<size_t>(2 * nqp + 2 * nkp) * AB_PITCH + static_cast<size_t>(nqp) * (nkp + 4) + nqp) * sizeof(float);
     static cap_device_once once;
     CAP_PROPAGATE(cap_opt_in_smem(once, attention_bwd_kernel, 227 * 1024));
     CAP_REQUIRE(smem <= 227 * 1024, "cap_attention_backward: tiles do not fit shared memory");

@@ -83,7 +83,8 @@ def test_transpose_with_column_sums(device):
 def test_attention_backward_matches_autograd(device):
     torch.manual_seed(3)
     H, hd = 8, 512
-    for b, nq, nk, causal in ((3, 20, 20, True), (2, 16, 50, False), (2, 49, 49, False), (1, 128, 100, False)):
+    for b, nq, nk, causal in ((3, 20, 20, True), (2, 16, 50, False), (2, 49, 49, False), (1, 128, 100, False), (2, 100, 50, False),
+                              (2, 18, 18, True), (3, 5, 7, False)):
         fused = nq == nk
         if fused:   # fused q|k|v rows, as the projections produce them
             qkv = _bf(torch.randn(b * nq, 3 * hd, device=device))
