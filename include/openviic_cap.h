@@ -474,6 +474,12 @@ int cap_train_layernorm_bwd(const float* dout_a, const float* dout_b, const floa
  * optional): the operands of dW = dY^T.X and the bias gradient of a Linear in one pass. */
 int cap_transpose_bf16(const void* in, int ld, void* out, int ldo, float* colsum, int rows, int cols,
                        cap_stream_t stream);
+/* Split-K product for few output tiles over a long contraction (the weight gradients dW = dY^T.X): `splits` CTAs per
+ * output tile write fp32 partial products partials[z][M][ldy] over consecutive K ranges; cap_sum_partials adds them up
+ * (count = M * ldy elements per partial).  x [M][K] and w [N][K] bf16 as in cap_linear; no bias, no activation. */
+int cap_linear_splitk(const void* x, int ldx, const void* w, float* partials, int ldy, int M, int N, int K, int splits,
+                      cap_stream_t stream);
+int cap_sum_partials(const float* partials, int splits, int64_t count, float* out, cap_stream_t stream);
 /* dh *= (h > 0), bf16, in place (positionwise_feed_forward.py:24). */
 int cap_train_relu_bwd(void* dh, const void* h, int64_t count, cap_stream_t stream);
 /* dst += src, fp32. */

@@ -63,6 +63,8 @@ SIGNATURES = {
     "cap_train_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cap_train_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cap_transpose_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "cap_linear_splitk": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cap_sum_partials": (_i, [_vp, _i, _i64, _vp, _vp]),
     "cap_train_relu_bwd": (_i, [_vp, _vp, _i64, _vp]),
     "cap_axpy_f32": (_i, [_vp, _vp, _i64, _vp]),
     "cap_attention_backward": (_i, [C.POINTER(AttentionArgs), _vp, _vp, _vp, _vp, _vp]),

@@ -42,6 +42,10 @@ struct GemmParams {
     int ldr, ldo32, pos_rows;
     float eps;
     unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (cap_debug_gemm_trace), else nullptr
+    // split-K (cap_linear_splitk): blockIdx.z takes k-blocks [z * kb_per_split, ...) and writes its partial product to
+    // out + z * split_stride_bytes; 0 = the whole K in one CTA
+    int kb_per_split;
+    size_t split_stride_bytes;
 };
 
 __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
@@ -97,7 +101,9 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int n_tiles = gridDim.x;
     const int m0 = m_tile * BLOCK_M;
     const int n0 = n_tile * BLOCK_N;
-    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_begin = p.kb_per_split > 0 ? static_cast<int>(blockIdx.z) * p.kb_per_split : 0;
+    const int num_kb = p.kb_per_split > 0 ? min(p.kb_per_split, num_kb_total - kb_begin) : num_kb_total;
 
     if (threadIdx.x == 0) stamp(p, 0);
     if (warp == 0 && lane == 0) {
@@ -140,8 +146,8 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint8_t* a_tile = smem + s * STAGE_BYTES;
             if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(a_tile, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
-                tma_load_2d_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], kb * BLOCK_K, n0, keep_policy);  // weights
+                tma_load_2d(a_tile, &tmap_a, &full_bar[s], (kb_begin + kb) * BLOCK_K, m0);
+                tma_load_2d_hint(a_tile + A_TILE_BYTES, &tmap_b, &full_bar[s], (kb_begin + kb) * BLOCK_K, n0, keep_policy);  // weights
                 if (kb == 0) stamp(p, 2);
             }
             __syncwarp();
@@ -339,7 +345,7 @@ gemm_tn_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int vecs_per_row = row_bytes / 16;
         const int elems_per_vec = 16 / esz;
         const int n_valid = min(EPI_N, p.N - (n0 + h0));            // valid columns of this pass
-        uint8_t* gout = reinterpret_cast<uint8_t*>(p.out);
+        uint8_t* gout = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(blockIdx.z) * p.split_stride_bytes;
         for (int idx = half * 16 * vecs_per_row + lane; idx < (half + 1) * 16 * vecs_per_row; idx += 32) {
             const int rr = idx / vecs_per_row, vv = idx % vecs_per_row;
             const int grow = m0 + quad * 32 + rr;
@@ -413,7 +419,7 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
 }
 
 template <int BLOCK_N, bool STATS = false, bool LN = false>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream, int splits = 1) {
     constexpr uint32_t stage_bytes = A_TILE_BYTES + BLOCK_N * BLOCK_K * 2;
     constexpr int epi_n = BLOCK_N < 128 ? BLOCK_N : 128;
     const uint32_t staging = BLOCK_M * (epi_n * (p.out_f32 ? 4 : 2) + 16);
@@ -438,7 +444,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
         cap_launch_kernel(gemm_tn_bf16_tcgen05<BLOCK_N, STATS, LN>, dim3(tiles_n, tiles_m), dim3(GEMM_THREADS), smem,
                           stream, /*cluster_x=*/tiles_n, ta, tb, p);
     } else {
-        dim3 grid(tiles_n, tiles_m);
+        dim3 grid(tiles_n, tiles_m, splits);
         CAP_LAUNCH((gemm_tn_bf16_tcgen05<BLOCK_N, STATS, LN>), grid, GEMM_THREADS, smem, stream, ta, tb, p);
     }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
@@ -477,7 +483,7 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
         bn = (N >= 256 && tiles_m >= 32) ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : 32));
     }
 
-    GemmParams p;
+    GemmParams p = {};
     p.out = y;
     p.bias = bias;
     p.M = M;
@@ -506,6 +512,47 @@ extern "C" int cap_linear(const void* x, int ldx, const void* w, const float* bi
         case 128: return launch_gemm<128>(ta, tb, p, s);
         case 64: return launch_gemm<64>(ta, tb, p, s);
         default: return launch_gemm<32>(ta, tb, p, s);
+    }
+}
+
+// Split-K variant for products with few output tiles and a long contraction (the weight gradients dW = dY^T.X of the
+// training step: N x K outputs of 512 .. 2048 over M = thousands of rows): `splits` CTAs per output tile take
+// consecutive k-block ranges and write fp32 partial products to partials[z][M][ldy]; the caller sums them
+// (cap_sum_partials).  No bias, no activation.
+extern "C" int cap_linear_splitk(const void* x, int ldx, const void* w, float* partials, int ldy, int M, int N, int K,
+                                 int splits, cap_stream_t stream) {
+    CAP_REQUIRE(x && w && partials, "cap_linear_splitk: null pointer");
+    CAP_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "cap_linear_splitk: empty problem");
+    CAP_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldx >= K && ldy >= N, "cap_linear_splitk: K, ldx multiples of 8; ldx >= K, ldy >= N");
+    CAP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                "cap_linear_splitk: x and w must be 16-byte aligned");
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_per = (num_kb + splits - 1) / splits;
+    CAP_REQUIRE((splits - 1) * kb_per < num_kb, "cap_linear_splitk: %d splits leave an empty k range (K = %d)", splits, K);
+    const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : 32));
+    GemmParams p = {};
+    p.out = partials;
+    p.bias = nullptr;
+    p.M = M; p.N = N; p.K = K; p.ldo = ldy;
+    p.out_f32 = 1;
+    p.act = CAP_ACT_NONE;
+    int stages = bn == 256 ? 2 : (bn == 128 ? 3 : 4);
+    if (stages > kb_per) stages = kb_per;
+    p.num_stages = stages;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(partials) & 15) == 0) && ((static_cast<size_t>(ldy) * 4) % 16 == 0) &&
+               ((static_cast<size_t>(M) * ldy * 4) % 16 == 0);
+    p.trace = nullptr;
+    p.kb_per_split = kb_per;
+    p.split_stride_bytes = static_cast<size_t>(M) * ldy * sizeof(float);
+    CUtensorMap ta, tb;
+    CAP_PROPAGATE(make_tmap(&ta, x, M, K, ldx, BLOCK_M));
+    CAP_PROPAGATE(make_tmap(&tb, w, N, K, K, bn));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (bn) {
+        case 256: return launch_gemm<256>(ta, tb, p, s, splits);
+        case 128: return launch_gemm<128>(ta, tb, p, s, splits);
+        case 64: return launch_gemm<64>(ta, tb, p, s, splits);
+        default: return launch_gemm<32>(ta, tb, p, s, splits);
     }
 }
 

@@ -629,6 +629,20 @@ dropout_kernel(T* __restrict__ x, size_t n, uint32_t threshold, float scale, uin
     }
 }
 
+// out = sum over z of parts[z] (fp32): the partial products of a split-K GEMM (cap_linear_splitk)
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ parts, int splits, size_t stride4, float* __restrict__ out, size_t n4) {
+    pdl_prologue();
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 acc = reinterpret_cast<const float4*>(parts)[i];
+        for (int z = 1; z < splits; ++z) {
+            const float4 b = reinterpret_cast<const float4*>(parts)[z * stride4 + i];
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = acc;
+    }
+}
+
 inline int grid_for(size_t items, int block) {
     const size_t g = (items + block - 1) / block;
     return static_cast<int>(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -771,4 +785,12 @@ extern "C" int cap_train_dropout(void* x, int dtype, int64_t count, unsigned int
         CAP_LAUNCH(dropout_kernel<float>, grid_for(n, 256), 256, 0, s, static_cast<float*>(x), n, threshold, scale, seed, site);
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("dropout_kernel");
+}
+
+extern "C" int cap_sum_partials(const float* partials, int splits, int64_t count, float* out, cap_stream_t stream) {
+    CAP_REQUIRE(partials && out && splits >= 1 && count > 0 && count % 4 == 0, "cap_sum_partials: count must be a positive multiple of 4");
+    const size_t n4 = static_cast<size_t>(count) / 4;
+    CAP_LAUNCH(sum_partials_kernel, grid_for(n4, 256), 256, 0, static_cast<cudaStream_t>(stream), partials, splits, n4, out, n4);
+    g_cap_launches.fetch_add(1, std::memory_order_relaxed);
+    return cap_check_launch("sum_partials_kernel");
 }

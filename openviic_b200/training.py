@@ -186,7 +186,18 @@ class XETrainer:
         dyt = self._transpose(dy16, m, n, lin.gb)                       # (N, M8)
         xt = self._transpose(x16, m, k)                                  # (K, M8)
         m8 = dyt.shape[1]
-        cabi.call("cap_linear", dyt.data_ptr(), m8, xt.data_ptr(), None, lin.gw.data_ptr(), k, CAP_F32, ACT_NONE, n, k, m8, _stream())
+        # few output tiles over a long contraction: split the M axis over enough CTAs to fill the GPU
+        tiles = ((n + 127) // 128) * ((k + 255) // 256 if k >= 256 else 1)
+        kb = (m8 + 63) // 64
+        splits = max(1, min(16, kb, -(-148 // tiles)))
+        per = -(-kb // splits)
+        splits = -(-kb // per)
+        if splits > 1:
+            parts = torch.empty((splits, n, k), device=self.device, dtype=torch.float32)
+            cabi.call("cap_linear_splitk", dyt.data_ptr(), m8, xt.data_ptr(), parts.data_ptr(), k, n, k, m8, splits, _stream())
+            cabi.call("cap_sum_partials", parts.data_ptr(), splits, n * k, lin.gw.data_ptr(), _stream())
+        else:
+            cabi.call("cap_linear", dyt.data_ptr(), m8, xt.data_ptr(), None, lin.gw.data_ptr(), k, CAP_F32, ACT_NONE, n, k, m8, _stream())
         if not need_dx:
             return None
         n8 = lin.wt16.shape[1]

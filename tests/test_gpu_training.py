@@ -80,6 +80,24 @@ def test_transpose_with_column_sums(device):
         assert (colsum - 1 - x[:, :cols].float().sum(0)).abs().max().item() < 1e-3
 
 
+def test_split_k_gemm_matches_fp32(device):
+    """cap_linear_splitk + cap_sum_partials (the weight-gradient GEMMs: few output tiles, contraction over thousands of
+    rows) against an fp32 matmul of the same bf16 operands."""
+    torch.manual_seed(8)
+    for m, n, k, splits in ((512, 2048, 12544, 5), (1536, 512, 5128, 16), (128, 64, 200, 3), (77, 130, 64, 1)):
+        x = _bf(torch.randn(m, k, device=device))
+        w = _bf(torch.randn(n, k, device=device))
+        ldy = (n + 3) // 4 * 4
+        parts = torch.full((splits, m, ldy), float("nan"), device=device)
+        out = torch.empty(m, ldy, device=device)
+        cabi.call("cap_linear_splitk", x.data_ptr(), k, w.data_ptr(), parts.data_ptr(), ldy, m, n, k, splits, _s())
+        cabi.call("cap_sum_partials", parts.data_ptr(), splits, m * ldy, out.data_ptr(), _s())
+        torch.cuda.synchronize()
+        ref = x.float() @ w.float().t()
+        err = (out[:, :n] - ref).abs().max().item()
+        assert err < 2e-4 * math.sqrt(k), (m, n, k, splits, err)
+
+
 def test_attention_backward_matches_autograd(device):
     torch.manual_seed(3)
     H, hd = 8, 512
