@@ -139,6 +139,26 @@ class XETrainer:
         return _Linear(self._view(self.p16, name + ".weight", rows), self._view(self.p32, name + ".bias", rows) if bias else None,
                        self._view(self.g32, name + ".weight", rows), self._view(self.g32, name + ".bias", rows) if bias else None)
 
+    def _linears(self):
+        """(proj, encoder layers, decoder layers, vocabulary projection) as _Linear views; built on first use and kept
+        (the flat buffers never move, and each _Linear owns the scratch for its transposed weight)."""
+        if getattr(self, "_lin_cache", None) is None:
+            L = self.enc_layers
+            proj = self._linear("vision_embedding.proj")
+            enc = [dict(qkv=self._linear(f"encoder.layers.{l}.mhatt.attention.", "fc_q", 3),
+                        o=self._linear(f"encoder.layers.{l}.mhatt.attention.fc_o"),
+                        fc1=self._linear(f"encoder.layers.{l}.pwff.fc1"), fc2=self._linear(f"encoder.layers.{l}.pwff.fc2")) for l in range(L)]
+            dec = [dict(qkv=self._linear(f"decoder.layers.{l}.self_attn.attention.", "fc_q", 3),
+                        o1=self._linear(f"decoder.layers.{l}.self_attn.attention.fc_o"),
+                        q=self._linear(f"decoder.layers.{l}.enc_attn.attention.fc_q"),
+                        kv=self._linear(f"decoder.layers.{l}.enc_attn.attention.", "fc_k", 2),
+                        o2=self._linear(f"decoder.layers.{l}.enc_attn.attention.fc_o"),
+                        fc1=self._linear(f"decoder.layers.{l}.pwff.fc1"), fc2=self._linear(f"decoder.layers.{l}.pwff.fc2"))
+                   for l in range(self.dec_layers)]
+            fc = self._linear("decoder.fc", bias=False)
+            self._lin_cache = (proj, enc, dec, fc)
+        return self._lin_cache
+
     def parameters(self) -> Dict[str, Tensor]:
         """fp32 master weights by state_dict name (views)."""
         return {k: self._view(self.p32, k) for k in self.shapes}
@@ -287,15 +307,8 @@ class XETrainer:
         tokens = tokens.contiguous().view(-1)
         targets = targets.contiguous().view(-1)
 
-        # the Linears (views into the flat buffers), W^T refreshed from the current weights
-        proj = self._linear("vision_embedding.proj")
-        enc = [dict(qkv=self._linear(f"encoder.layers.{l}.mhatt.attention.", "fc_q", 3), o=self._linear(f"encoder.layers.{l}.mhatt.attention.fc_o"),
-                    fc1=self._linear(f"encoder.layers.{l}.pwff.fc1"), fc2=self._linear(f"encoder.layers.{l}.pwff.fc2")) for l in range(L)]
-        dec = [dict(qkv=self._linear(f"decoder.layers.{l}.self_attn.attention.", "fc_q", 3), o1=self._linear(f"decoder.layers.{l}.self_attn.attention.fc_o"),
-                    q=self._linear(f"decoder.layers.{l}.enc_attn.attention.fc_q"),
-                    kv=self._linear(f"decoder.layers.{l}.enc_attn.attention.", "fc_k", 2), o2=self._linear(f"decoder.layers.{l}.enc_attn.attention.fc_o"),
-                    fc1=self._linear(f"decoder.layers.{l}.pwff.fc1"), fc2=self._linear(f"decoder.layers.{l}.pwff.fc2")) for l in range(self.dec_layers)]
-        fc = self._linear("decoder.fc", bias=False)
+        # the Linears (views into the flat buffers, built once); W^T refreshed from the current weights
+        proj, enc, dec, fc = self._linears()
         self._refresh_transposed([x for layer in enc for x in layer.values()] + [x for layer in dec for x in layer.values()] + [fc])
 
         # ---------------- forward: encoder (vision_embeddings.py:15-20, encoders.py:17-40)
