@@ -619,14 +619,37 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 dropout_kernel(T* __restrict__ x, size_t n, uint32_t threshold, float scale, uint32_t seed, uint32_t site) {
     pdl_prologue();
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const bool keep = dropout_hash(static_cast<uint32_t>(i), seed, site) >= threshold;
-        float v = 0.f;
-        if (keep) {
-            if constexpr (sizeof(T) == 2) v = __bfloat162float(x[i]) * scale; else v = x[i] * scale;
+    constexpr int VEC = 16 / sizeof(T);     // one 16-byte vector per thread and iteration; n is a multiple of VEC
+    const size_t nv = n / VEC;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        uint4 raw = reinterpret_cast<const uint4*>(x)[i];
+        const uint32_t base = static_cast<uint32_t>(i * VEC);
+        if constexpr (sizeof(T) == 2) {
+            bf16* e = reinterpret_cast<bf16*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                e[j] = dropout_hash(base + j, seed, site) >= threshold ? __float2bfloat16(__bfloat162float(e[j]) * scale) : __float2bfloat16(0.f);
+        } else {
+            float* e = reinterpret_cast<float*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) e[j] = dropout_hash(base + j, seed, site) >= threshold ? e[j] * scale : 0.f;
         }
-        if constexpr (sizeof(T) == 2) x[i] = __float2bfloat16(v); else x[i] = v;
+        reinterpret_cast<uint4*>(x)[i] = raw;
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_tail_kernel(T* __restrict__ x, size_t begin, size_t n, uint32_t threshold, float scale, uint32_t seed, uint32_t site) {
+    pdl_prologue();
+    const size_t i = begin + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const bool keep = dropout_hash(static_cast<uint32_t>(i), seed, site) >= threshold;
+    float v = 0.f;
+    if (keep) {
+        if constexpr (sizeof(T) == 2) v = __bfloat162float(x[i]) * scale; else v = x[i] * scale;
+    }
+    if constexpr (sizeof(T) == 2) x[i] = __float2bfloat16(v); else x[i] = v;
 }
 
 // out = sum over z of parts[z] (fp32): the partial products of a split-K GEMM (cap_linear_splitk)
@@ -779,10 +802,16 @@ extern "C" int cap_train_dropout(void* x, int dtype, int64_t count, unsigned int
     CAP_REQUIRE(dtype == CAP_BF16 || dtype == CAP_F32, "cap_train_dropout: bf16 or fp32");
     const size_t n = static_cast<size_t>(count);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (dtype == CAP_BF16)
-        CAP_LAUNCH(dropout_kernel<bf16>, grid_for(n, 256), 256, 0, s, static_cast<bf16*>(x), n, threshold, scale, seed, site);
-    else
-        CAP_LAUNCH(dropout_kernel<float>, grid_for(n, 256), 256, 0, s, static_cast<float*>(x), n, threshold, scale, seed, site);
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (dtype == CAP_BF16) {
+        const size_t body = aligned ? n / 8 * 8 : 0;
+        if (body) CAP_LAUNCH(dropout_kernel<bf16>, grid_for(body / 8, 256), 256, 0, s, static_cast<bf16*>(x), body, threshold, scale, seed, site);
+        if (body < n) CAP_LAUNCH(dropout_tail_kernel<bf16>, static_cast<int>((n - body + 255) / 256), 256, 0, s, static_cast<bf16*>(x), body, n, threshold, scale, seed, site);
+    } else {
+        const size_t body = aligned ? n / 4 * 4 : 0;
+        if (body) CAP_LAUNCH(dropout_kernel<float>, grid_for(body / 4, 256), 256, 0, s, static_cast<float*>(x), body, threshold, scale, seed, site);
+        if (body < n) CAP_LAUNCH(dropout_tail_kernel<float>, static_cast<int>((n - body + 255) / 256), 256, 0, s, static_cast<float*>(x), body, n, threshold, scale, seed, site);
+    }
     g_cap_launches.fetch_add(1, std::memory_order_relaxed);
     return cap_check_launch("dropout_kernel");
 }
