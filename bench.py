@@ -177,7 +177,7 @@ def time_gemm_family(cfg, n, batch, levels, device):
 
 def time_decode_chains(eng, cfg, batch, device):
     """Average duration of the fused tcgen05 GEMM-chain launches of one decode step (1 + 2 * layers launches of
-    decode_step_fused_kernel<chain>), with CUDA events on the launching stream around graph replays of all 20 steps'
+    decode_chain_kernel), with CUDA events on the launching stream around graph replays of all 20 steps'
     chains back to back; returns (algorithmic GEMM flops per step, seconds per step, launches per step) or None when
     the engine does not decode with chains."""
     import ctypes as C
