@@ -572,7 +572,7 @@ def run_gpu_arm(args):
     parity = None
     if cpu_base is not None:   # the same sample through the GPU path (outside every timed region), against the oracle
         f32, bx, ref_ids, ref_lp = cpu_reference_run.sample
-        small = model.engine(f32.shape[0], n, BEAM)
+        small = model.engine(f32.shape[0], n, BEAM)   # the model's cached engine (engines[0]): the sample fits its reservation
         got_ids, got_lp = small.caption_host(f32.to(torch.bfloat16).pin_memory(), None if bx is None else bx.pin_memory(), 1,
                                              use_graph=False)
         got_ids, got_lp = got_ids.squeeze(1).cpu(), got_lp.squeeze(1).cpu()
@@ -581,7 +581,6 @@ def run_gpu_arm(args):
                   "logprob_max_abs_on_identical": float((got_lp - ref_lp)[same].abs().max()) if same.any() else None,
                   "against": "oracle/caption_oracle.py (fp32, the reference's algorithm) on the cpu_baseline sample; the "
                              "full-size parity tests are tests/test_gpu_fullsize.py"}
-        small.close()
 
     others = None
     if world == 1 and args.workload == "standard_grid" and not args.no_others and not args.batch:
