@@ -433,7 +433,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cuda
     // single-CTA allocator can be resident on ONE of the two SMs -- the pair then never leaves its allocation (flight
     // recorder: exactly the two CTAs of one pair entered and never finished set-up, nothing else in flight; 0 of 7
     // runs hung with the pair GEMM off, 2-4 of 4 with it on, whatever the programmatic-launch settings).  The chain
-    // kernels keep their pairs: 221 KB of shared memory and all 512 columns each, so a pair owns both SMs outright,
+    // kernels keep their pairs: 226 KB of shared memory and all 512 columns each, so a pair owns both SMs outright,
     // which is also what CUTLASS's 2-SM kernels do.  The single-CTA 128 x 256 tile is faster here anyway (98.2 k vs
     // 92.6 k captions/s with exclusive pairs).
     static cap_device_once smem_once;
