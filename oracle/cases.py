@@ -56,3 +56,11 @@ TRAIN_CASES = {
     "std_region": dict(config="standard_transformer_using_region.yaml", batch=8, n=50, max_len=16, vocab=777, seed=32,
                        steps=2, lr=1.0, warmup=100, dropout_seed=9001, scst_beam=5, rl_lr=5e-6, eos_scale=4.0),
 }
+
+# T1 on the other architectures: the ORACLE's training step pinned to the reference (no GPU trainer for them yet -- the
+# backward kernels cover the standard transformer; these fixtures are the checker the next ones will be held to)
+ORACLE_ONLY_TRAIN_CASES = {
+    "m2": dict(config="meshed_memory_transformer.yaml", batch=4, n=50, max_len=12, vocab=600, seed=41, steps=2, lr=1.0, warmup=100),
+    "ort": dict(config="object_relation_transformer.yaml", batch=4, n=50, max_len=12, vocab=600, seed=42, steps=2, lr=1.0, warmup=100),
+    "aoa": dict(config="attention_on_attention.yaml", batch=4, n=50, max_len=12, vocab=600, seed=43, steps=2, lr=1.0, warmup=100),
+}

@@ -39,7 +39,10 @@ sys.path.insert(0, str(REPO))
 from openviic_b200 import synthetic  # noqa: E402
 from openviic_b200.configs import get_config  # noqa: E402
 from oracle import caption_oracle as oracle  # noqa: E402
-from oracle.cases import TRAIN_CASES, apply_overrides  # noqa: E402
+from oracle.cases import ORACLE_ONLY_TRAIN_CASES, TRAIN_CASES, apply_overrides  # noqa: E402
+
+sys.path.insert(0, str(HERE))
+import gen_golden  # noqa: E402,F401  (applies the documented ORT encoder_forward call-site patch to the reference class)
 
 
 def run_case(name: str, case: dict, dropout: bool = False) -> dict:
@@ -99,7 +102,11 @@ def run_case(name: str, case: dict, dropout: bool = False) -> dict:
     worst_l = max(abs(a - b) for a, b in zip(losses, o_losses))
     print(f"[{name}{' + dropout' if dropout else ''}] reference losses {losses}; oracle-vs-reference: loss {worst_l:.2e}, first-step gradients {worst_g:.2e}, "
           f"weights after {len(batches)} steps {worst_w:.2e}, parameters whose gradient exists on one side only: {missing}")
-    if worst_l > 1e-5 or worst_g > 1e-6 or worst_w > 1e-6 or missing:
+    # exact (0.0) on the standard transformer; the meshed / geometric / AoA graphs sum a few terms in another order, which
+    # shows as fp32 rounding in loss and gradients -- and, through Adam's sign-like first steps (a gradient entry that is
+    # zero up to rounding moves its weight by +-lr), as differences of up to 2 lr per step in a handful of weights
+    lr_max = case["lr"] * (d_model ** -.5) * case["steps"] * warmup ** -1.5
+    if worst_l > 1e-5 or worst_g > 1e-6 or worst_w > max(1e-6, 2.2 * case["steps"] * lr_max) or missing:
         raise SystemExit(f"oracle does not reproduce the reference's training step on case {name}")
 
     # the fixture: losses, and for every parameter the first-step gradient's and the final weight's norm plus a strided
@@ -177,6 +184,10 @@ def run_scst(name: str, case: dict) -> dict:
 
 
 def main():
+    for name, case in ORACLE_ONLY_TRAIN_CASES.items():
+        out = REPO / "tests" / "golden" / f"train_{name}.npz"
+        np.savez_compressed(out, **run_case(name, case))
+        print("wrote", out, out.stat().st_size, "bytes")
     for name, case in TRAIN_CASES.items():
         if "scst_beam" in case:
             out = REPO / "tests" / "golden" / f"train_{name}_scst.npz"

@@ -107,15 +107,15 @@ def test_adaptive_attention_oracle_reproduces_the_reference_class():
     assert np.abs(out.numpy() - golden("adaptive_attention")["out"]).max() < 2e-5
 
 
-@pytest.mark.parametrize("name", ["std_grid", "std_region", "std_region_dropout"])
+@pytest.mark.parametrize("name", ["std_grid", "std_region", "std_region_dropout", "ort", "aoa", "m2"])
 def test_oracle_training_step_reproduces_the_reference(name):
     """T1: oracle.xe_train_steps (loss, backward, Adam, Noam) against the fixture written from the REAL reference's
     modules, loss and optimizer by oracle/ref_harness/gen_golden_train.py (per parameter: norm + 16 strided samples of
     the first-step gradient and of the weights after the last step)."""
-    from oracle.cases import TRAIN_CASES, apply_overrides
+    from oracle.cases import ORACLE_ONLY_TRAIN_CASES, TRAIN_CASES, apply_overrides
     dropout = name.endswith("_dropout")     # the fixture of the reference with its nn.Dropout forwards on the counter-based masks
     fixture, name = name, name.replace("_dropout", "")
-    case = TRAIN_CASES[name]
+    case = {**ORACLE_ONLY_TRAIN_CASES, **TRAIN_CASES}[name]   # ort / aoa / m2: the oracle's step only (no GPU trainer yet)
     cfg = apply_overrides(ov.get_config(case["config"]), case)
     cfg.MODEL.DEVICE = "cpu"
     vocab = synthetic.SyntheticVocab(case["vocab"], case["max_len"])
@@ -133,7 +133,13 @@ def test_oracle_training_step_reproduces_the_reference(name):
             continue
         t = (grads if kind == "g" else final)[pname].reshape(-1)
         got = np.concatenate([[float(t.norm())], t[:: max(1, t.numel() // 16)][:16].numpy()])
-        assert np.abs(got - g[key]).max() <= 1e-6 * max(1.0, np.abs(g[key]).max()), key
+        tol = np.full(17, 1e-6 * max(1.0, np.abs(g[key]).max()))
+        if name == "m2" and kind == "w":
+            # the meshed graph sums a few terms in another order than the reference: fp32 rounding in the gradients
+            # (4e-8), which Adam's sign-like first steps turn into +-lr on weights whose gradient is zero up to rounding
+            per_weight = 2.2 * case["steps"] * case["lr"] * 512 ** -0.5 * case["steps"] * case["warmup"] ** -1.5
+            tol = np.concatenate([[per_weight * np.sqrt(t.numel())], np.full(16, per_weight)])   # [norm, 16 samples]
+        assert (np.abs(got - g[key]) <= tol[: got.size]).all(), key
         checked += 1
     assert checked > 200
 
